@@ -1,0 +1,189 @@
+"""TEST INFRASTRUCTURE -- ctypes bindings for the C oracle (liborc.so) and the compiled reference iSWIFT
+core (_ref/libiswift_ref.so).  Importable only from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; the product package never imports this module."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NV_MAX, NEQ, MROWS_MAX = 41, 28, 112
+
+
+class Options(C.Structure):
+    _fields_ = [("qp_reltol", C.c_double), ("qp_abstol", C.c_double), ("qp_maxit", C.c_int),
+                ("tol", C.c_double), ("mu_init", C.c_double), ("kappa_eps", C.c_double), ("kappa_mu", C.c_double),
+                ("theta_mu", C.c_double), ("tau_min", C.c_double), ("push", C.c_double),
+                ("gamma_theta", C.c_double), ("gamma_phi", C.c_double), ("delta", C.c_double),
+                ("s_theta", C.c_double), ("s_phi", C.c_double), ("eta_phi", C.c_double),
+                ("kappa_sigma", C.c_double), ("alpha_min", C.c_double),
+                ("dw_first", C.c_double), ("dw_min", C.c_double), ("kw_minus", C.c_double), ("kw_plus", C.c_double),
+                ("kw_plus_first", C.c_double), ("dw_max", C.c_double), ("rho_lambda", C.c_double), ("z_div", C.c_double),
+                ("max_iter", C.c_int), ("filter_cap", C.c_int)]
+
+
+class Gains(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("Qw", "Rw", "Pw", "slack_w", "mu_fric", "h_com", "g_acc", "Ts", "eps_dist",
+                                          "v_max", "box")]
+
+
+class Result(C.Structure):
+    _fields_ = [("x", C.c_double * NV_MAX), ("x_qp", C.c_double * NV_MAX), ("y", C.c_double * NEQ),
+                ("z", C.c_double * MROWS_MAX), ("s", C.c_double * MROWS_MAX), ("alpha", C.c_double * 20),
+                ("alpha_buf_next", C.c_double * 4), ("obs", C.c_double * 2), ("kkt", C.c_double), ("mu", C.c_double),
+                ("nv", C.c_int), ("c", C.c_int), ("m", C.c_int), ("status", C.c_int), ("qp_flag", C.c_int),
+                ("qp_iters", C.c_int), ("nlp_iters", C.c_int), ("n_fact", C.c_int), ("n_ls", C.c_int)]
+
+
+def build(force=False):
+    """Compile liborc.so (always possible) and _ref/libiswift_ref.so (only where /root/reference exists)."""
+    lib = os.path.join(HERE, "liborc.so")
+    src = [os.path.join(HERE, f) for f in ("cbfnmpc_oracle.c", "cbfnmpc_oracle.h")]
+    stale = (not os.path.exists(lib)) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in src)
+    ref = os.path.join(HERE, "_ref", "libiswift_ref.so")
+    need_ref = os.path.isdir("/root/reference/optimization/iSWIFT/src") and (
+        force or not os.path.exists(ref) or os.path.getmtime(os.path.join(HERE, "ref_driver.c")) > os.path.getmtime(ref))
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-C", HERE, "liborc.so"] + (["-B"] if force else []))
+    if need_ref:
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+_lib = None
+_ref = None
+dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(os.path.join(HERE, "liborc.so"))
+        _lib.orc_default_options.argtypes = [C.POINTER(Options)]
+        _lib.orc_default_gains.argtypes = [C.POINTER(Gains)]
+        _lib.orc_lip_discrete.argtypes = [C.POINTER(Gains), dp, dp]
+        _lib.orc_stance_matrix.argtypes = [dp, ip, dp]
+        _lib.orc_pack_dense.argtypes = [C.POINTER(Gains), dp, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp]
+        _lib.orc_closest_obstacle.argtypes = [dp, dp, C.c_int, dp]
+        _lib.orc_bezier_fit.argtypes = [dp, dp, dp, dp]
+        _lib.orc_qp_mehrotra.argtypes = [C.c_int] * 3 + [dp] * 6 + [C.c_double, C.c_double, C.c_int, C.c_double] + [dp] * 4 + [C.POINTER(C.c_int)]
+        _lib.orc_nlp_ipm.argtypes = [C.c_int, C.c_int] + [dp] * 6 + [dp, dp, C.c_int, C.POINTER(Gains), C.POINTER(Options), C.POINTER(Result)]
+        _lib.orc_solve_instance.argtypes = [C.POINTER(Gains), C.POINTER(Options), dp, dp, dp, ip, dp, C.c_int, dp, C.c_int, C.POINTER(Result)]
+        _lib.orc_solve_batch.argtypes = [C.POINTER(Gains), C.POINTER(Options), C.c_int, dp, dp, dp, ip, dp, C.c_int, dp, C.c_int, C.c_int, C.POINTER(Result)]
+    return _lib
+
+
+def ref_lib():
+    """The reference's own iSWIFT C core (None when it was never built, e.g. a checkout without _ref/)."""
+    global _ref
+    if _ref is None:
+        build()
+        path = os.path.join(HERE, "_ref", "libiswift_ref.so")
+        if not os.path.exists(path):
+            return None
+        _ref = C.CDLL(path)
+        _ref.iswift_ref_solve_dense.argtypes = [C.c_int] * 3 + [dp] * 6 + [dp, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _ref.iswift_ref_solve_ccs.argtypes = [C.c_int] * 3 + [ip, ip, dp] * 3 + [dp, dp, dp, C.c_double, ip, dp, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    return _ref
+
+
+def default_options():
+    o = Options(); lib().orc_default_options(C.byref(o)); return o
+
+
+def default_gains():
+    g = Gains(); lib().orc_default_gains(C.byref(g)); return g
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def lip_discrete(g=None):
+    g = g or default_gains()
+    Ad = np.zeros(16); Bd = np.zeros(8)
+    lib().orc_lip_discrete(C.byref(g), Ad, Bd)
+    return Ad.reshape(4, 4), Bd.reshape(4, 2)
+
+
+def pack_dense(x0, xdes, F, g=None):
+    g = g or default_gains()
+    c = F.shape[1]
+    nv, p, mi = 25 + 4 * c, 28, 60 + 8 * c
+    Q = np.zeros(nv * nv); f = np.zeros(nv); A = np.zeros(p * nv); b = np.zeros(p); G = np.zeros(mi * nv); h = np.zeros(mi)
+    lib().orc_pack_dense(C.byref(g), _f(x0), _f(xdes), _f(F).ravel(), c, Q, f, A, b, G, h)
+    return (Q.reshape(nv, nv, order="F"), f, A.reshape(p, nv, order="F"), b, G.reshape(mi, nv, order="F"), h)
+
+
+def qp_mehrotra(P, c, A, b, G, h, reltol=1e-6, abstol=1e-6, maxit=25, sigma_d=0.0):
+    n, m, p = P.shape[0], G.shape[0], A.shape[0]
+    x = np.zeros(n); y = np.zeros(max(p, 1)); z = np.zeros(m); s = np.zeros(m); it = C.c_int(0)
+    flag = lib().orc_qp_mehrotra(n, m, p, _f(P.ravel(order="F")), _f(c), _f(A.ravel(order="F")), _f(b),
+                                 _f(G.ravel(order="F")), _f(h), reltol, abstol, maxit, sigma_d, x, y, z, s, C.byref(it))
+    return x, y[:p], z, s, it.value, flag
+
+
+def iswift_ref_dense(P, c, A, b, G, h):
+    r = ref_lib()
+    n, m, p = P.shape[0], G.shape[0], A.shape[0]
+    x = np.zeros(n); y = np.zeros(max(p, 1)); z = np.zeros(m); s = np.zeros(m); it = C.c_int(0)
+    ts, tv = C.c_double(0), C.c_double(0)
+    flag = r.iswift_ref_solve_dense(n, m, p, _f(P.ravel(order="F")), _f(c), _f(A.ravel(order="F")), _f(b),
+                                    _f(G.ravel(order="F")), _f(h), x, y, z, s, C.byref(it), C.byref(ts), C.byref(tv))
+    return x, y[:p], z, s, it.value, flag, ts.value, tv.value
+
+
+def res_to_dict(r):
+    nv, m = r.nv, r.m
+    return dict(x=np.array(r.x[:nv]), x_qp=np.array(r.x_qp[:nv]), y=np.array(r.y[:]), z=np.array(r.z[:m]), s=np.array(r.s[:m]),
+                alpha=np.array(r.alpha[:]).reshape(4, 5), alpha_buf_next=np.array(r.alpha_buf_next[:]), obs=np.array(r.obs[:]),
+                kkt=r.kkt, mu=r.mu, nv=nv, c=r.c, m=m, status=r.status, qp_flag=r.qp_flag, qp_iters=r.qp_iters,
+                nlp_iters=r.nlp_iters, n_fact=r.n_fact, n_ls=r.n_ls)
+
+
+def nlp_ipm(Q, f, A, b, G, h, obs, x_start, with_nl=True, g=None, o=None):
+    g = g or default_gains(); o = o or default_options()
+    nv, mi = Q.shape[0], G.shape[0]
+    r = Result()
+    lib().orc_nlp_ipm(nv, mi, _f(Q.ravel(order="F")), _f(f), _f(A.ravel(order="F")), _f(b), _f(G.ravel(order="F")), _f(h),
+                      _f(obs), _f(x_start), int(with_nl), C.byref(g), C.byref(o), C.byref(r))
+    return res_to_dict(r)
+
+
+def solve_instance(x0, xdes, feet, contact, obs, alpha_buf=None, mode=1, g=None, o=None):
+    g = g or default_gains(); o = o or default_options()
+    r = Result()
+    obs = _f(obs)
+    ab = _f(alpha_buf if alpha_buf is not None else [x0[0], 0, x0[2], 0])
+    lib().orc_solve_instance(C.byref(g), C.byref(o), _f(x0), _f(xdes), _f(feet).ravel(), np.ascontiguousarray(contact, np.int32),
+                             obs.ravel(), obs.shape[1], ab, mode, C.byref(r))
+    return res_to_dict(r)
+
+
+def solve_batch(x0, xdes, feet, contact, obs, alpha_buf, mode=1, nthreads=1, g=None, o=None, raw=False):
+    """AoS batch: x0 (B,4) xdes (B,16) feet (B,2,4) contact (B,4) obs (B,2,K) alpha_buf (B,4)."""
+    g = g or default_gains(); o = o or default_options()
+    B = x0.shape[0]; K = obs.shape[2]
+    res = (Result * B)()
+    lib().orc_solve_batch(C.byref(g), C.byref(o), B, _f(x0).ravel(), _f(xdes).ravel(), _f(feet).ravel(),
+                          np.ascontiguousarray(contact, np.int32).ravel(), _f(obs).ravel(), K, _f(alpha_buf).ravel(), mode,
+                          nthreads, res)
+    if raw:
+        return res
+    out = dict(X=np.zeros((B, 16)), U=np.zeros((B, 8)), lam=np.zeros((B, 16)), slack=np.zeros(B), x_qp=np.zeros((B, NV_MAX)),
+               alpha=np.zeros((B, 20)), alpha_buf_next=np.zeros((B, 4)), status=np.zeros(B, np.int32), kkt=np.zeros(B),
+               qp_iters=np.zeros(B, np.int32), qp_flag=np.zeros(B, np.int32), nlp_iters=np.zeros(B, np.int32),
+               n_fact=np.zeros(B, np.int32), n_ls=np.zeros(B, np.int32), c=np.zeros(B, np.int32), obs=np.zeros((B, 2)),
+               z=np.zeros((B, MROWS_MAX)), s=np.zeros((B, MROWS_MAX)), y=np.zeros((B, NEQ)))
+    for i in range(B):
+        r = res[i]; nv = r.nv; c = r.c
+        xx = np.array(r.x[:NV_MAX])
+        out["X"][i] = xx[:16]; out["U"][i] = xx[16:24]
+        if nv > 0:
+            out["lam"][i, :4 * c] = xx[24:24 + 4 * c]; out["slack"][i] = xx[nv - 1]
+        out["x_qp"][i] = r.x_qp[:]; out["alpha"][i] = r.alpha[:]; out["alpha_buf_next"][i] = r.alpha_buf_next[:]
+        out["status"][i] = r.status; out["kkt"][i] = r.kkt; out["qp_iters"][i] = r.qp_iters; out["qp_flag"][i] = r.qp_flag
+        out["nlp_iters"][i] = r.nlp_iters; out["n_fact"][i] = r.n_fact; out["n_ls"][i] = r.n_ls; out["c"][i] = c
+        out["obs"][i] = r.obs[:]; out["z"][i] = r.z[:]; out["s"][i] = r.s[:]; out["y"][i] = r.y[:]
+    return out

@@ -310,7 +310,7 @@ def interior_start(prob, x_start, push):
     return x
 
 
-def nlp_ipm(prob, x_start, opts=None, verbose=False):
+def nlp_ipm(prob, x_start, opts=None, verbose=False, direction_fn=None, compare=None):
     o = dict(DEFAULT_OPTS)
     if opts:
         o.update(opts)
@@ -371,10 +371,16 @@ def nlp_ipm(prob, x_start, opts=None, verbose=False):
         rhs = np.concatenate([-(g + A.T @ y - J.T @ z) - Jb.T @ (z[bnd] - mu / s[bnd]), -r_e, mu / z[gen] - s[gen]])
         dw = 0.0
         while True:
-            H = Hc + dw * np.eye(n)
-            K = np.block([[H, A.T, Jg.T], [A, np.zeros((p, p + ng))], [Jg, np.zeros((ng, p)), -np.diag(s[gen] / z[gen])]])
-            info['n_fact'] += 1
-            if _ldl_inertia(K) == (n, p + ng, 0):
+            if direction_fn is not None:
+                info['n_fact'] += 1
+                out = direction_fn(x, y, z, s, mu, dw)
+                if out is not None:
+                    break
+            else:
+              H = Hc + dw * np.eye(n)
+              K = np.block([[H, A.T, Jg.T], [A, np.zeros((p, p + ng))], [Jg, np.zeros((ng, p)), -np.diag(s[gen] / z[gen])]])
+              info['n_fact'] += 1
+              if _ldl_inertia(K) == (n, p + ng, 0):
                 break
             if dw == 0.0:
                 dw = o['dw_first'] if dw_last == 0.0 else max(o['dw_min'], o['kw_minus'] * dw_last)
@@ -386,10 +392,24 @@ def nlp_ipm(prob, x_start, opts=None, verbose=False):
         if dw > 0:
             dw_last = dw
             first_ic = False
-        sol = np.linalg.solve(K, rhs)
-        dx, dy = sol[:n], sol[n:n + p]
+        if direction_fn is not None:
+            dx, dy = out[0], out[1]
+            if compare is not None:
+                H = Hc + dw * np.eye(n)
+                K = np.block([[H, A.T, Jg.T], [A, np.zeros((p, p + ng))], [Jg, np.zeros((ng, p)), -np.diag(s[gen] / z[gen])]])
+                sol = np.linalg.solve(K, rhs)
+                compare.append((np.abs(sol[:n] - dx).max() / max(np.abs(sol[:n]).max(), 1e-300), np.abs(sol[n:n+p] - dy).max() / max(np.abs(sol[n:n+p]).max(), 1e-300), mu))
+        else:
+            sol = np.linalg.solve(K, rhs)
+            dx, dy = sol[:n], sol[n:n + p]
+            out = (dx, dy, None)
+            dz_gen = -sol[n + p:]
         ds = J @ dx
         dz = mu / s - z - Sig * ds
+        if direction_fn is not None and len(out) > 2 and out[2] is not None and out[2].shape == dz.shape:
+            dz = out[2]
+        elif direction_fn is None:
+            dz[gen] = dz_gen
         neg = ds < 0
         a_pmax = min(1.0, (-tau * s[neg] / ds[neg]).min()) if neg.any() else 1.0
         neg = dz < 0
