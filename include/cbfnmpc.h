@@ -1,0 +1,124 @@
+/* cbfnmpc.h -- C ABI of the B200-native batched CBF-NMPC solver (drop-in for the MPC_dist::run_NMPC hot path).
+ *
+ * Every entry point replaces an in-process C++ call of the reference (there is no FFI in the reference; these
+ * are the calls a maintainer would bind instead -- see INTEGRATION.md):
+ *
+ *   cbfnmpc_create / destroy      <- MPC_dist::MPC_dist(), ~MPC_dist()          include/MPC_dist.hpp:141-157, src/MPC_dist.cpp:42-77
+ *   cbfnmpc_set_gains             <- hard-coded gains / constants               src/MPC_dist.cpp:90-104,164-188,315-318; dec_vars_constr_cost.h:306-307,401
+ *   cbfnmpc_set_options           <- iSWIFT GlobalOptions.h:23-26 (QP stage); NLP-stage IPM options (no reference counterpart:
+ *                                    the reference never sets an ifopt/SNOPT option, src/MPC_dist.cpp:363-413)
+ *   cbfnmpc_solve_batch           <- MPC_dist::updateState + run_NMPC + get_alphaCOM/get_MPCsol, B agents at once, device buffers
+ *                                    src/MPC_dist.cpp:1195-1202, 81-454; include/MPC_dist.hpp:178-181
+ *   cbfnmpc_solve_batch_host      <- same, host buffers (copies inside): the call LocoWrapper-side code makes   src/A1_Sim.cpp:227-244
+ *   cbfnmpc_solve_dense_nlptuple  <- the nlpTuple boundary type                 include/pack_nlp_data.h:11-29, src/MPC_dist.cpp:403-421
+ *
+ * Plain pointers and sizes only.  All floating point is IEEE FP64.  No CPU fallback exists: every solve runs in
+ * the CUDA kernels of libcbfnmpc.so, and every call returns a negative code when no CUDA device is usable.
+ */
+#ifndef CBFNMPC_H
+#define CBFNMPC_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBFNMPC_N 4          /* grid points per domain (src/MPC_dist.cpp:92, global_loco_opts.h:9) */
+#define CBFNMPC_MAX_ROWS 128 /* bits in the active-set mask (112 one-sided rows at 4 stance feet)     */
+
+/* return codes */
+#define CBFNMPC_OK 0
+#define CBFNMPC_ERR_ARG (-1)
+#define CBFNMPC_ERR_CUDA (-2)
+#define CBFNMPC_ERR_NODEVICE (-3)
+#define CBFNMPC_ERR_STRUCTURE (-4) /* dense nlpTuple does not have the MPC_dist structure */
+
+/* per-instance status */
+#define CBFNMPC_ST_CONVERGED 0
+#define CBFNMPC_ST_MAXITER 1
+#define CBFNMPC_ST_INFEASIBLE 2  /* line search / multiplier divergence: NLP has no interior */
+#define CBFNMPC_ST_NUMERICAL 3   /* inertia correction exhausted */
+#define CBFNMPC_ST_BADINPUT 4    /* contact pattern other than 4 feet or a diagonal pair (src/MPC_dist.cpp:1238-1252) */
+
+#define CBFNMPC_MODE_QP 0      /* use_snopt == false: the iSWIFT-equivalent QP optimum is the answer (MPC_dist.hpp:139) */
+#define CBFNMPC_MODE_QP_NLP 1  /* use_snopt == true : QP optimum -> NLP (src/MPC_dist.cpp:348 -> 402-427)              */
+
+typedef struct cbfnmpc_ctx cbfnmpc_ctx;
+
+typedef struct {
+  double Qw, Rw, Pw, slack_w;        /* src/MPC_dist.cpp:172-175 */
+  double mu_fric, h_com, g_acc, Ts;  /* :90, :99-100, :104       */
+  double eps_dist, v_max, box;       /* dec_vars_constr_cost.h:401, :306-307; MPC_dist.cpp:317-318 */
+} cbfnmpc_gains;
+
+typedef struct {
+  double qp_reltol, qp_abstol; int qp_maxit;     /* iSWIFT GlobalOptions.h:23-26 */
+  double tol, mu_init, kappa_eps, kappa_mu, tau_min, push;
+  double gamma_theta, gamma_phi, eta_phi, kappa_sigma, alpha_min;
+  double dw_first, dw_min, kw_minus, kw_plus, kw_plus_first, dw_max, rho_lambda, z_div;
+  double sigma_cap, refine_rel, refine_abs;
+  int max_iter, filter_cap, max_refine;
+} cbfnmpc_options;
+
+/* Structure-of-arrays batch inputs: field-major, batch index fastest ( a[f * B + b] ).
+ *   x0      [4][B]   measured LIP state (q[0], dq[0], q[1], dq[1])                    src/MPC_dist.cpp:226-229
+ *   xdes    [16][B]  com_desired_Traj_vec_eventbased_ ([x,xd,y,yd] x 4)               :702-782
+ *   feet_xy [8][B]   toePos_(0:1, 0:3): x of FR,FL,RR,RL then y of FR,FL,RR,RL        :1195-1252
+ *   contact [4][B]   contactInd (int32)                                               :1198
+ *   obs_xy  [2*K][B] Pobs_real: x of the K obstacles then y (closest one is used)     :371-396
+ *   alpha_buf [4][B] mpc_state_alpha_buffer_                                          :792-798
+ */
+typedef struct {
+  const double *x0, *xdes, *feet_xy;
+  const int32_t *contact;
+  const double *obs_xy;
+  int n_obs;
+  const double *alpha_buf;
+} cbfnmpc_in;
+
+/* Outputs (any pointer may be NULL to skip it):
+ *   X [16][B]  mpc_state_e_x_eventbased_          U [8][B] COP inputs (u_x,u_y) x 4     src/MPC_dist.cpp:431-440
+ *   lam [16][B] support weights (4c used)         slack [B] distance-row slack variable
+ *   x_qp [24][B] X,U of the QP stage (qp_solution_eventbased_)                          :350-354
+ *   alpha [20][B] alpha_COM_traj_e_ (row-major 4x5)   alpha_buf_next [4][B]              :784-855
+ *   status, qp_iters, nlp_iters, n_fact [B] (int32)   kkt [B] final unscaled KKT error
+ *   active [2][B] (uint64) bit r set <=> one-sided row r (reference row order) is active (z > s)
+ */
+typedef struct {
+  double *X, *U, *lam, *slack, *x_qp, *alpha, *alpha_buf_next, *kkt;
+  int32_t *status, *qp_iters, *nlp_iters, *n_fact;
+  uint64_t *active;
+} cbfnmpc_out;
+
+int cbfnmpc_version(void);
+const char *cbfnmpc_last_error(void);
+void cbfnmpc_default_gains(cbfnmpc_gains *g);
+void cbfnmpc_default_options(cbfnmpc_options *o);
+
+int cbfnmpc_create(cbfnmpc_ctx **ctx, int device, int max_batch, int max_obs);
+void cbfnmpc_destroy(cbfnmpc_ctx *ctx);
+int cbfnmpc_set_gains(cbfnmpc_ctx *ctx, const cbfnmpc_gains *g);
+int cbfnmpc_set_options(cbfnmpc_ctx *ctx, const cbfnmpc_options *o);
+
+/* device pointers; asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream) */
+int cbfnmpc_solve_batch(cbfnmpc_ctx *ctx, int B, int mode, const cbfnmpc_in *in, const cbfnmpc_out *out, void *cuda_stream);
+/* host pointers; copies in, solves, copies out, synchronises */
+int cbfnmpc_solve_batch_host(cbfnmpc_ctx *ctx, int B, int mode, const cbfnmpc_in *in, const cbfnmpc_out *out);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+long long cbfnmpc_launch_count(const cbfnmpc_ctx *ctx);
+/* last solve kernel's duration in ms measured with CUDA events on the launch stream (synchronises) */
+int cbfnmpc_last_kernel_ms(cbfnmpc_ctx *ctx, float *ms);
+
+/* One instance in the reference's own dense layout (column-major Eigen matrices of pack_nlp_data.h:11-29).
+ * The compact form is recovered from the matrices; CBFNMPC_ERR_STRUCTURE if they are not MPC_dist-shaped. */
+int cbfnmpc_solve_dense_nlptuple(cbfnmpc_ctx *ctx, int nv, int p, int mi, const double *Q, const double *f,
+                                 const double *Aeq, const double *beq, const double *G, const double *h,
+                                 const double *x0_start, const double obs[2], int mode_nlp, double *x_out, int *status,
+                                 double *kkt);
+
+/* FP64 DFMA peak microbenchmark (TFLOP/s) used as the roofline denominator by bench.py */
+int cbfnmpc_measure_fp64_peak(cbfnmpc_ctx *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,135 @@
+"""Product binding: loads srb-cbf-nmpc_b200/lib/libcbfnmpc.so (hand-written CUDA for sm_100a) through ctypes.
+
+There is no CPU path.  Importing works anywhere (so that host-side logic can be tested), but creating a solver
+raises unless the CUDA library is built and a CUDA device is visible."""
+import ctypes as C
+import os
+import numpy as np
+from . import capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libcbfnmpc.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include", "cbfnmpc.h")
+_lib = None
+
+
+class CbfNmpcError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the CUDA library and declare the prototypes of include/cbfnmpc.h.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CbfNmpcError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                           "There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.cbfnmpc_version.restype = C.c_int
+    L.cbfnmpc_last_error.restype = C.c_char_p
+    L.cbfnmpc_default_gains.argtypes = [C.POINTER(capi.Gains)]
+    L.cbfnmpc_default_options.argtypes = [C.POINTER(capi.Options)]
+    L.cbfnmpc_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
+    L.cbfnmpc_destroy.argtypes = [C.c_void_p]
+    L.cbfnmpc_set_gains.argtypes = [C.c_void_p, C.POINTER(capi.Gains)]
+    L.cbfnmpc_set_options.argtypes = [C.c_void_p, C.POINTER(capi.Options)]
+    L.cbfnmpc_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.In), C.POINTER(capi.Out), C.c_void_p]
+    L.cbfnmpc_solve_batch_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.In), C.POINTER(capi.Out)]
+    L.cbfnmpc_launch_count.argtypes = [C.c_void_p]
+    L.cbfnmpc_launch_count.restype = C.c_longlong
+    L.cbfnmpc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.cbfnmpc_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.cbfnmpc_solve_dense_nlptuple.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+EXPORTS = ["cbfnmpc_version", "cbfnmpc_last_error", "cbfnmpc_default_gains", "cbfnmpc_default_options", "cbfnmpc_create",
+           "cbfnmpc_destroy", "cbfnmpc_set_gains", "cbfnmpc_set_options", "cbfnmpc_solve_batch", "cbfnmpc_solve_batch_host",
+           "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak"]
+
+
+def default_gains():
+    g = capi.Gains(); load().cbfnmpc_default_gains(C.byref(g)); return g
+
+
+def default_options():
+    o = capi.Options(); load().cbfnmpc_default_options(C.byref(o)); return o
+
+
+class BatchSolver:
+    """Owns one cbfnmpc_ctx (device buffers + stream) on one GPU."""
+
+    def __init__(self, device=0, max_batch=4096, max_obs=20, gains=None, options=None):
+        self.L = load()
+        self.ctx = C.c_void_p()
+        rc = self.L.cbfnmpc_create(C.byref(self.ctx), device, max_batch, max_obs)
+        if rc != 0:
+            raise CbfNmpcError("cbfnmpc_create failed (%d): %s" % (rc, self.L.cbfnmpc_last_error().decode()))
+        self.device, self.max_batch, self.max_obs = device, max_batch, max_obs
+        self.gains, self.options = default_gains(), default_options()
+        if gains: self.set_gains(**gains)
+        if options: self.set_options(**options)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise CbfNmpcError("cbfnmpc call failed (%d): %s" % (rc, self.L.cbfnmpc_last_error().decode()))
+
+    def set_gains(self, **kw):
+        for k, v in kw.items(): setattr(self.gains, k, v)
+        self._ck(self.L.cbfnmpc_set_gains(self.ctx, C.byref(self.gains)))
+
+    def set_options(self, **kw):
+        for k, v in kw.items(): setattr(self.options, k, v)
+        self._ck(self.L.cbfnmpc_set_options(self.ctx, C.byref(self.options)))
+
+    def close(self):
+        if self.ctx:
+            self.L.cbfnmpc_destroy(self.ctx); self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+    # ---- host buffers (numpy, ideally views of one pinned block): copies inside the call
+    def solve_host(self, d, mode=capi.MODE_QP_NLP, out=None):
+        B = d["x0"].shape[1]
+        out = out if out is not None else capi.alloc_out(B)
+        si, so = capi.in_struct(d), capi.out_struct(out)
+        self._ck(self.L.cbfnmpc_solve_batch_host(self.ctx, B, mode, C.byref(si), C.byref(so)))
+        return out
+
+    # ---- device buffers: dicts of raw device pointers (ints), e.g. torch tensors' .data_ptr()
+    def solve_device(self, B, in_ptrs, out_ptrs, n_obs, mode=capi.MODE_QP_NLP, stream=None):
+        si = capi.In(); so = capi.Out()
+        for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy", "alpha_buf"):
+            setattr(si, k, in_ptrs.get(k))
+        si.n_obs = n_obs
+        for k, _ in capi.Out._fields_:
+            setattr(so, k, out_ptrs.get(k))
+        self._ck(self.L.cbfnmpc_solve_batch(self.ctx, B, mode, C.byref(si), C.byref(so), stream))
+
+    def launch_count(self):
+        return int(self.L.cbfnmpc_launch_count(self.ctx))
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0); self._ck(self.L.cbfnmpc_last_kernel_ms(self.ctx, C.byref(ms))); return ms.value
+
+    def fp64_peak_tflops(self):
+        t = C.c_double(0); self._ck(self.L.cbfnmpc_measure_fp64_peak(self.ctx, C.byref(t))); return t.value
+
+    def solve_dense_nlptuple(self, Q, f, Aeq, beq, G, h, x0_start, obs, mode_nlp=True):
+        """Reference layout: Eigen column-major matrices of pack_nlp_data.h:11-29."""
+        nv, p, mi = Q.shape[0], Aeq.shape[0], G.shape[0]
+        cm = lambda a: np.asfortranarray(a, dtype=np.float64)
+        Qc, Ac, Gc = cm(Q), cm(Aeq), cm(G)
+        fv, bv, hv = (np.ascontiguousarray(v, dtype=np.float64).ravel() for v in (f, beq, h))
+        xs = np.ascontiguousarray(x0_start, dtype=np.float64); ob = np.ascontiguousarray(obs, dtype=np.float64)
+        xo = np.zeros(nv); st = C.c_int(0); kk = C.c_double(0)
+        rc = self.L.cbfnmpc_solve_dense_nlptuple(self.ctx, nv, p, mi, Qc.ctypes.data, fv.ctypes.data, Ac.ctypes.data, bv.ctypes.data,
+                                                 Gc.ctypes.data, hv.ctypes.data, xs.ctypes.data, ob.ctypes.data, int(mode_nlp),
+                                                 xo.ctypes.data, C.byref(st), C.byref(kk))
+        if rc != 0:
+            raise CbfNmpcError("cbfnmpc_solve_dense_nlptuple failed (%d): %s" % (rc, self.L.cbfnmpc_last_error().decode()))
+        return xo, st.value, kk.value

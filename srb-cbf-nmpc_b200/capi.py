@@ -1,0 +1,74 @@
+"""ctypes view of include/cbfnmpc.h (structs + prototypes).  Pure declarations: used by the product binding
+(api.py, which loads libcbfnmpc.so -- CUDA only) and by tests/emu (which loads the host emulator of the kernel
+source for CPU-side logic tests)."""
+import ctypes as C
+import numpy as np
+
+
+class Gains(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("Qw", "Rw", "Pw", "slack_w", "mu_fric", "h_com", "g_acc", "Ts", "eps_dist", "v_max", "box")]
+
+
+class Options(C.Structure):
+    _fields_ = [("qp_reltol", C.c_double), ("qp_abstol", C.c_double), ("qp_maxit", C.c_int),
+                ("tol", C.c_double), ("mu_init", C.c_double), ("kappa_eps", C.c_double), ("kappa_mu", C.c_double),
+                ("tau_min", C.c_double), ("push", C.c_double), ("gamma_theta", C.c_double), ("gamma_phi", C.c_double),
+                ("eta_phi", C.c_double), ("kappa_sigma", C.c_double), ("alpha_min", C.c_double),
+                ("dw_first", C.c_double), ("dw_min", C.c_double), ("kw_minus", C.c_double), ("kw_plus", C.c_double),
+                ("kw_plus_first", C.c_double), ("dw_max", C.c_double), ("rho_lambda", C.c_double), ("z_div", C.c_double),
+                ("sigma_cap", C.c_double), ("refine_rel", C.c_double), ("refine_abs", C.c_double),
+                ("max_iter", C.c_int), ("filter_cap", C.c_int), ("max_refine", C.c_int)]
+
+
+class In(C.Structure):
+    _fields_ = [("x0", C.c_void_p), ("xdes", C.c_void_p), ("feet_xy", C.c_void_p), ("contact", C.c_void_p),
+                ("obs_xy", C.c_void_p), ("n_obs", C.c_int), ("alpha_buf", C.c_void_p)]
+
+
+class Out(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("X", "U", "lam", "slack", "x_qp", "alpha", "alpha_buf_next", "kkt",
+                                          "status", "qp_iters", "nlp_iters", "n_fact", "active")]
+
+
+OUT_F64 = dict(X=16, U=8, lam=16, slack=1, x_qp=24, alpha=20, alpha_buf_next=4, kkt=1)
+OUT_I32 = dict(status=1, qp_iters=1, nlp_iters=1, n_fact=1)
+IN_F64 = dict(x0=4, xdes=16, feet_xy=8, alpha_buf=4)  # + obs_xy 2K, contact (int32) 4
+
+MODE_QP, MODE_QP_NLP = 0, 1
+ST_CONVERGED, ST_MAXITER, ST_INFEASIBLE, ST_NUMERICAL, ST_BADINPUT = range(5)
+
+
+def soa_from_instances(insts, alpha_buf=None):
+    """[(x0, xdes, feet(2,4), contact, obs(2,K)), ...] -> dict of SoA numpy arrays ([field][B], C-contiguous)."""
+    B = len(insts)
+    K = insts[0][4].shape[1]
+    d = dict(x0=np.zeros((4, B)), xdes=np.zeros((16, B)), feet_xy=np.zeros((8, B)), contact=np.zeros((4, B), np.int32),
+             obs_xy=np.zeros((2 * K, B)), alpha_buf=np.zeros((4, B)))
+    for b, (x0, xdes, feet, contact, obs) in enumerate(insts):
+        d["x0"][:, b] = x0; d["xdes"][:, b] = xdes; d["feet_xy"][:, b] = np.asarray(feet).reshape(8)
+        d["contact"][:, b] = contact; d["obs_xy"][:, b] = np.asarray(obs).reshape(2 * K)
+        d["alpha_buf"][:, b] = (x0[0], 0.0, x0[2], 0.0) if alpha_buf is None else alpha_buf[b]
+    d["n_obs"] = K
+    return d
+
+
+def alloc_out(B):
+    o = {k: np.zeros((n, B)) for k, n in OUT_F64.items()}
+    o.update({k: np.zeros((n, B), np.int32) for k, n in OUT_I32.items()})
+    o["active"] = np.zeros((2, B), np.uint64)
+    return o
+
+
+def in_struct(d):
+    s = In()
+    for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy", "alpha_buf"):
+        setattr(s, k, d[k].ctypes.data)
+    s.n_obs = int(d["n_obs"])
+    return s
+
+
+def out_struct(o):
+    s = Out()
+    for k in o:
+        setattr(s, k, o[k].ctypes.data)
+    return s

@@ -1,0 +1,356 @@
+// cbfnmpc_api.cu -- C ABI (include/cbfnmpc.h) + the CUDA kernels.  sm_100a only; no CPU path of any kind.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include "cbfnmpc_host.h"
+#include "cbfnmpc_instance.h"
+
+#define WARPS_PER_CTA 4
+
+// One warp per instance; the CTA only shares the launch.  Dynamic shared memory: WARPS_PER_CTA workspaces.
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA) cbfnmpc_solve_kernel(const __grid_constant__ KParams P,
+                                                                          const __grid_constant__ BatchIO io) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WSB* wsall = reinterpret_cast<WSB*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * WARPS_PER_CTA + warp;
+  if (b >= io.B) return;
+  solve_warp(wsall[warp], P, io, b);
+}
+
+// FP64 pipe microbenchmark: 8 independent DFMA chains per thread.
+__global__ void cbfnmpc_dfma_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail(CBFNMPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct cbfnmpc_ctx {
+  int device, max_batch, max_obs;
+  cbfnmpc_gains gains;
+  cbfnmpc_options opts;
+  KParams kp;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  bool timed;
+  long long launches;
+  // staging for the host-pointer entry points
+  double* d_in;   // (32 + 2 max_obs) * max_batch
+  int* d_contact; // 4 * max_batch
+  double* d_out;  // 90 * max_batch
+  int* d_outi;    // 4 * max_batch
+  unsigned long long* d_active;  // 2 * max_batch
+  double* d_xstart;              // 41 (dense entry point)
+};
+
+extern "C" {
+
+int cbfnmpc_version(void) { return 100; }
+const char* cbfnmpc_last_error(void) { return g_err.c_str(); }
+void cbfnmpc_default_gains(cbfnmpc_gains* g) { host_default_gains(g); }
+void cbfnmpc_default_options(cbfnmpc_options* o) { host_default_options(o); }
+
+int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
+  if (!out || max_batch < 1 || max_obs < 1) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_create: bad argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(CBFNMPC_ERR_NODEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_create: device index out of range");
+  CK(cudaSetDevice(device));
+  cbfnmpc_ctx* c = new cbfnmpc_ctx();
+  c->device = device; c->max_batch = max_batch; c->max_obs = max_obs; c->launches = 0; c->timed = false;
+  host_default_gains(&c->gains); host_default_options(&c->opts);
+  host_fill_kparams(&c->gains, &c->opts, &c->kp);
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+  CK(cudaMalloc(&c->d_in, sizeof(double) * (size_t)(32 + 2 * max_obs) * max_batch));
+  CK(cudaMalloc(&c->d_contact, sizeof(int) * 4 * (size_t)max_batch));
+  CK(cudaMalloc(&c->d_out, sizeof(double) * 90 * (size_t)max_batch));
+  CK(cudaMalloc(&c->d_outi, sizeof(int) * 4 * (size_t)max_batch));
+  CK(cudaMalloc(&c->d_active, sizeof(unsigned long long) * 2 * (size_t)max_batch));
+  CK(cudaMalloc(&c->d_xstart, sizeof(double) * 41));
+  CK(cudaFuncSetAttribute(cbfnmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * sizeof(WSB))));
+  *out = c;
+  return CBFNMPC_OK;
+}
+
+void cbfnmpc_destroy(cbfnmpc_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_in); cudaFree(c->d_contact); cudaFree(c->d_out); cudaFree(c->d_outi); cudaFree(c->d_active); cudaFree(c->d_xstart);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int cbfnmpc_set_gains(cbfnmpc_ctx* c, const cbfnmpc_gains* g) {
+  if (!c || !g) return fail(CBFNMPC_ERR_ARG, "null argument");
+  if (!(g->h_com > 0) || !(g->Ts > 0) || !(g->Rw > 0) || !(g->slack_w > 0) || !(g->box > 0) || !(g->v_max > 0))
+    return fail(CBFNMPC_ERR_ARG, "cbfnmpc_set_gains: non-positive gain");
+  c->gains = *g;
+  host_fill_kparams(&c->gains, &c->opts, &c->kp);
+  return CBFNMPC_OK;
+}
+
+int cbfnmpc_set_options(cbfnmpc_ctx* c, const cbfnmpc_options* o) {
+  if (!c || !o) return fail(CBFNMPC_ERR_ARG, "null argument");
+  if (o->qp_maxit < 1 || o->max_iter < 1 || !(o->tol > 0) || !(o->push > 0) || o->filter_cap < 1 || o->max_refine < 0)
+    return fail(CBFNMPC_ERR_ARG, "cbfnmpc_set_options: bad option");
+  c->opts = *o;
+  host_fill_kparams(&c->gains, &c->opts, &c->kp);
+  return CBFNMPC_OK;
+}
+
+static int launch(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const cbfnmpc_out* out, const double* xstart,
+                  cudaStream_t st) {
+  BatchIO io;
+  io.x0 = in->x0; io.xdes = in->xdes; io.feet = in->feet_xy; io.contact = in->contact; io.obs = in->obs_xy; io.n_obs = in->n_obs;
+  io.abuf = in->alpha_buf; io.xstart = xstart;
+  io.X = out->X; io.U = out->U; io.lam = out->lam; io.slack = out->slack; io.xqp = out->x_qp; io.alpha = out->alpha;
+  io.abuf_next = out->alpha_buf_next; io.kkt = out->kkt; io.status = out->status; io.qp_iters = out->qp_iters;
+  io.nlp_iters = out->nlp_iters; io.n_fact = out->n_fact; io.active = (unsigned long long*)out->active;
+  io.B = B; io.mode = mode;
+  const int grid = (B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  CK(cudaEventRecord(c->ev0, st));
+  cbfnmpc_solve_kernel<<<grid, 32 * WARPS_PER_CTA, WARPS_PER_CTA * sizeof(WSB), st>>>(c->kp, io);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev1, st));
+  c->timed = true;
+  c->launches++;
+  return CBFNMPC_OK;
+}
+
+int cbfnmpc_solve_batch(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const cbfnmpc_out* out, void* cuda_stream) {
+  if (!c || !in || !out || B < 1) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_solve_batch: bad argument");
+  if (mode != CBFNMPC_MODE_QP && mode != CBFNMPC_MODE_QP_NLP) return fail(CBFNMPC_ERR_ARG, "bad mode");
+  if (!in->x0 || !in->xdes || !in->feet_xy || !in->contact) return fail(CBFNMPC_ERR_ARG, "missing input array");
+  if (mode == CBFNMPC_MODE_QP_NLP && (!in->obs_xy || in->n_obs < 1)) return fail(CBFNMPC_ERR_ARG, "NLP mode needs obstacles");
+  CK(cudaSetDevice(c->device));
+  return launch(c, B, mode, in, out, nullptr, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
+
+int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const cbfnmpc_out* out) {
+  if (!c || !in || !out || B < 1) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_solve_batch_host: bad argument");
+  if (B > c->max_batch) return fail(CBFNMPC_ERR_ARG, "batch larger than max_batch");
+  if (mode != CBFNMPC_MODE_QP && mode != CBFNMPC_MODE_QP_NLP) return fail(CBFNMPC_ERR_ARG, "bad mode");
+  if (!in->x0 || !in->xdes || !in->feet_xy || !in->contact) return fail(CBFNMPC_ERR_ARG, "missing input array");
+  const int K = (mode == CBFNMPC_MODE_QP_NLP) ? in->n_obs : 0;
+  if (mode == CBFNMPC_MODE_QP_NLP && (!in->obs_xy || K < 1 || K > c->max_obs)) return fail(CBFNMPC_ERR_ARG, "NLP mode needs 1..max_obs obstacles");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const size_t Bs = (size_t)B;
+  // device staging layout (doubles): x0 4 | xdes 16 | feet 8 | alpha_buf 4 | obs 2K
+  double* d = c->d_in;
+  struct Seg { const double* h; size_t off, n; };
+  Seg segs[5] = {{in->x0, 0, 4 * Bs}, {in->xdes, 4 * Bs, 16 * Bs}, {in->feet_xy, 20 * Bs, 8 * Bs}, {in->alpha_buf, 28 * Bs, 4 * Bs},
+                 {in->obs_xy, 32 * Bs, 2 * (size_t)K * Bs}};
+  // adjacent host arrays (one pinned block, as the Python binding allocates) are merged into a single copy
+  for (int i = 0; i < 5;) {
+    if (!segs[i].h || segs[i].n == 0) { i++; continue; }
+    int j = i; size_t n = segs[i].n;
+    while (j + 1 < 5 && segs[j + 1].h == segs[j].h + segs[j].n && segs[j + 1].n > 0) { j++; n += segs[j].n; }
+    CK(cudaMemcpyAsync(d + segs[i].off, segs[i].h, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    i = j + 1;
+  }
+  if (!in->alpha_buf) CK(cudaMemsetAsync(d + 28 * Bs, 0, sizeof(double) * 4 * Bs, st));
+  CK(cudaMemcpyAsync(c->d_contact, in->contact, sizeof(int) * 4 * Bs, cudaMemcpyHostToDevice, st));
+  cbfnmpc_in din = {d, d + 4 * Bs, d + 20 * Bs, c->d_contact, d + 32 * Bs, K, d + 28 * Bs};
+  // device output layout (doubles): X 16 | U 8 | lam 16 | slack 1 | x_qp 24 | alpha 20 | abuf_next 4 | kkt 1
+  double* o = c->d_out;
+  cbfnmpc_out dout;
+  dout.X = o; dout.U = o + 16 * Bs; dout.lam = o + 24 * Bs; dout.slack = o + 40 * Bs; dout.x_qp = o + 41 * Bs;
+  dout.alpha = o + 65 * Bs; dout.alpha_buf_next = o + 85 * Bs; dout.kkt = o + 89 * Bs;
+  dout.status = c->d_outi; dout.qp_iters = c->d_outi + Bs; dout.nlp_iters = c->d_outi + 2 * Bs; dout.n_fact = c->d_outi + 3 * Bs;
+  dout.active = (uint64_t*)c->d_active;
+  int rc = launch(c, B, mode, &din, &dout, nullptr, st);
+  if (rc) return rc;
+  struct OSeg { double* h; size_t off, n; };
+  OSeg os[8] = {{out->X, 0, 16 * Bs}, {out->U, 16 * Bs, 8 * Bs}, {out->lam, 24 * Bs, 16 * Bs}, {out->slack, 40 * Bs, Bs},
+                {out->x_qp, 41 * Bs, 24 * Bs}, {out->alpha, 65 * Bs, 20 * Bs}, {out->alpha_buf_next, 85 * Bs, 4 * Bs}, {out->kkt, 89 * Bs, Bs}};
+  for (int i = 0; i < 8;) {
+    if (!os[i].h) { i++; continue; }
+    int j = i; size_t n = os[i].n;
+    while (j + 1 < 8 && os[j + 1].h == os[j].h + os[j].n) { j++; n += os[j].n; }
+    CK(cudaMemcpyAsync(os[i].h, o + os[i].off, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    i = j + 1;
+  }
+  int32_t* oi[4] = {out->status, out->qp_iters, out->nlp_iters, out->n_fact};
+  for (int i = 0; i < 4;) {
+    if (!oi[i]) { i++; continue; }
+    int j = i; size_t n = Bs;
+    while (j + 1 < 4 && oi[j + 1] == oi[j] + Bs) { j++; n += Bs; }
+    CK(cudaMemcpyAsync(oi[i], c->d_outi + (size_t)i * Bs, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    i = j + 1;
+  }
+  if (out->active) CK(cudaMemcpyAsync(out->active, c->d_active, sizeof(unsigned long long) * 2 * Bs, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return CBFNMPC_OK;
+}
+
+long long cbfnmpc_launch_count(const cbfnmpc_ctx* c) { return c ? c->launches : 0; }
+
+int cbfnmpc_last_kernel_ms(cbfnmpc_ctx* c, float* ms) {
+  if (!c || !ms) return fail(CBFNMPC_ERR_ARG, "null argument");
+  if (!c->timed) return fail(CBFNMPC_ERR_ARG, "no kernel launched yet");
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventSynchronize(c->ev1));
+  CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return CBFNMPC_OK;
+}
+
+int cbfnmpc_measure_fp64_peak(cbfnmpc_ctx* c, double* tflops) {
+  if (!c || !tflops) return fail(CBFNMPC_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  double* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(double) * (size_t)blocks * threads));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(a, c->stream));
+    cbfnmpc_dfma_kernel<<<blocks, threads, 0, c->stream>>>(d, iters);
+    CK(cudaEventRecord(b, c->stream));
+    CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  c->launches += 4;
+  CK(cudaEventDestroy(a)); CK(cudaEventDestroy(b)); CK(cudaFree(d));
+  *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) * 1e-12;
+  return CBFNMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Dense nlpTuple entry point (include/pack_nlp_data.h:11-29): recover the compact form, check the structure by
+// re-packing exactly as src/MPC_dist.cpp:164-321, then solve one instance.
+// ---------------------------------------------------------------------------------------------------------
+static void host_pack_dense(const cbfnmpc_gains* g, const double* x0, const double* xdes, const double* F /*2x4, stride 4*/, int c,
+                            std::vector<double>& Q, std::vector<double>& f, std::vector<double>& A, std::vector<double>& b,
+                            std::vector<double>& G, std::vector<double>& h) {
+  const int n = 4, m = 2, N = 4, nv = 25 + 4 * c, p = 28, mi = 60 + 8 * c;
+  double Ad[16], Bd[8];
+  host_lip(g, Ad, Bd);
+  Q.assign((size_t)nv * nv, 0.0); f.assign(nv, 0.0); A.assign((size_t)p * nv, 0.0); b.assign(p, 0.0); G.assign((size_t)mi * nv, 0.0); h.assign(mi, 1.0);
+  for (int i = 0; i < 16; i++) { double w = i >= 12 ? g->Pw : g->Qw; Q[i + (size_t)i * nv] = w; f[i] = -xdes[i] * w; }
+  for (int i = 0; i < 8; i++) Q[(16 + i) + (size_t)(16 + i) * nv] = g->Rw;
+  Q[(nv - 1) + (size_t)(nv - 1) * nv] = g->slack_w;
+  for (int k = 0; k < N; k++) {
+    for (int i = 0; i < n; i++) {
+      A[(4 * k + i) + (size_t)(4 * k + i) * p] = -1.0;
+      if (k >= 1) for (int j = 0; j < n; j++) A[(4 * k + i) + (size_t)(4 * (k - 1) + j) * p] += Ad[4 * i + j];
+      for (int j = 0; j < m; j++) A[(4 * k + i) + (size_t)(16 + 2 * k + j) * p] = Bd[2 * i + j];
+    }
+    for (int a = 0; a < 2; a++) {
+      A[(16 + 2 * k + a) + (size_t)(16 + 2 * k + a) * p] = 1.0;
+      for (int j = 0; j < c; j++) A[(16 + 2 * k + a) + (size_t)(24 + c * k + j) * p] = -F[4 * a + j];
+    }
+    for (int j = 0; j < c; j++) A[(24 + k) + (size_t)(24 + c * k + j) * p] = 1.0;
+    b[24 + k] = 1.0;
+  }
+  for (int i = 0; i < 4; i++) { double s = 0; for (int j = 0; j < 4; j++) s += Ad[4 * i + j] * x0[j]; b[i] = -s; }
+  const int r = 6;
+  for (int i = 0; i < 3; i++)
+    for (int a = 0; a < 2; a++) {
+      G[(2 * i + a) + (size_t)(4 * i + 2 * a) * mi] = 1.0; G[(2 * i + a) + (size_t)(16 + 2 * (i + 1) + a) * mi] = -1.0;
+      G[(r + 2 * i + a) + (size_t)(4 * i + 2 * a) * mi] = -1.0; G[(r + 2 * i + a) + (size_t)(16 + 2 * (i + 1) + a) * mi] = 1.0;
+    }
+  int o = 12;
+  for (int i = 0; i < 16; i++) { G[(o + i) + (size_t)i * mi] = 1.0; G[(o + 16 + i) + (size_t)i * mi] = -1.0; }
+  o += 32;
+  for (int i = 0; i < 8; i++) { G[(o + i) + (size_t)(16 + i) * mi] = 1.0; G[(o + 8 + i) + (size_t)(16 + i) * mi] = -1.0; }
+  o += 16;
+  for (int i = 0; i < 4 * c; i++) { G[(o + i) + (size_t)(24 + i) * mi] = -1.0; G[(o + 4 * c + i) + (size_t)(24 + i) * mi] = 1.0; }
+  const double fb = g->mu_fric * g->h_com / sqrt(2.0);
+  for (int i = 0; i < 12; i++) h[i] = fb;
+  for (int i = 12; i < 60; i++) h[i] = g->box;
+  for (int i = 0; i < 4 * c; i++) h[60 + i] = 0.0;
+}
+
+static bool close_vec(const double* a, const std::vector<double>& b, double tol) {
+  for (size_t i = 0; i < b.size(); i++) if (!(fabs(a[i] - b[i]) <= tol * (1.0 + fabs(b[i])))) return false;
+  return true;
+}
+
+int cbfnmpc_solve_dense_nlptuple(cbfnmpc_ctx* c, int nv, int p, int mi, const double* Q, const double* f, const double* Aeq,
+                                 const double* beq, const double* G, const double* h, const double* x0_start, const double obs[2],
+                                 int mode_nlp, double* x_out, int* status, double* kkt) {
+  if (!c || !Q || !f || !Aeq || !beq || !G || !h || !x_out) return fail(CBFNMPC_ERR_ARG, "null argument");
+  int cc = (nv - 25) / 4;
+  if ((cc != 2 && cc != 4) || nv != 25 + 4 * cc || p != 28 || mi != 60 + 8 * cc)
+    return fail(CBFNMPC_ERR_STRUCTURE, "dimensions are not those of MPC_dist (nv = 25+4c, p = 28, mi = 60+8c, c in {2,4})");
+  if (mode_nlp && (!x0_start || !obs)) return fail(CBFNMPC_ERR_ARG, "NLP mode needs x0 and the obstacle");
+  const cbfnmpc_gains* g = &c->gains;
+  // compact form: F from the u = F lambda rows, x0 from beq = -Ad x0, xdes from f = -Pbig xdes
+  double F[8] = {0}, x0[4], xdes[16], Ad[16], Bd[8];
+  for (int a = 0; a < 2; a++) for (int j = 0; j < cc; j++) F[4 * a + j] = -Aeq[(16 + a) + (size_t)(24 + j) * p];
+  host_lip(g, Ad, Bd);
+  {  // per-axis 2x2 inverse
+    double det = Ad[0] * Ad[5] - Ad[1] * Ad[4];
+    for (int bx = 0; bx < 2; bx++) {
+      double r0 = -beq[2 * bx], r1 = -beq[2 * bx + 1];
+      x0[2 * bx] = (Ad[5] * r0 - Ad[1] * r1) / det;
+      x0[2 * bx + 1] = (-Ad[4] * r0 + Ad[0] * r1) / det;
+    }
+  }
+  for (int i = 0; i < 16; i++) xdes[i] = -f[i] / (i >= 12 ? g->Pw : g->Qw);
+  std::vector<double> Q2, f2, A2, b2, G2, h2;
+  host_pack_dense(g, x0, xdes, F, cc, Q2, f2, A2, b2, G2, h2);
+  if (!close_vec(Q, Q2, 1e-12) || !close_vec(f, f2, 1e-12) || !close_vec(Aeq, A2, 1e-12) || !close_vec(beq, b2, 1e-9) ||
+      !close_vec(G, G2, 1e-12) || !close_vec(h, h2, 1e-12))
+    return fail(CBFNMPC_ERR_STRUCTURE, "matrices do not have the MPC_dist structure for the context's gains");
+  // one-instance SoA inputs (B = 1): contact pattern that reproduces F's column order
+  CK(cudaSetDevice(c->device));
+  double hin[34];
+  double feet[8] = {0};
+  int contact[4];
+  if (cc == 4) { for (int i = 0; i < 8; i++) feet[i] = F[i]; contact[0] = contact[1] = contact[2] = contact[3] = 1; }
+  else { feet[1] = F[0]; feet[2] = F[1]; feet[5] = F[4]; feet[6] = F[5]; contact[0] = 0; contact[1] = 1; contact[2] = 1; contact[3] = 0; }
+  memcpy(hin, x0, 32); memcpy(hin + 4, xdes, 128); memcpy(hin + 20, feet, 64);
+  for (int i = 0; i < 4; i++) hin[28 + i] = 0.0;
+  hin[32] = obs ? obs[0] : 0.0; hin[33] = obs ? obs[1] : 0.0;
+  cudaStream_t st = c->stream;
+  CK(cudaMemcpyAsync(c->d_in, hin, sizeof(hin), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->d_contact, contact, sizeof(contact), cudaMemcpyHostToDevice, st));
+  double xs[41] = {0};
+  if (mode_nlp) { memcpy(xs, x0_start, sizeof(double) * nv); CK(cudaMemcpyAsync(c->d_xstart, xs, sizeof(xs), cudaMemcpyHostToDevice, st)); }
+  double* d = c->d_in;
+  cbfnmpc_in din = {d, d + 4, d + 20, c->d_contact, d + 32, 1, d + 28};
+  double* o = c->d_out;
+  cbfnmpc_out dout;
+  memset(&dout, 0, sizeof(dout));
+  dout.X = o; dout.U = o + 16; dout.lam = o + 24; dout.slack = o + 40; dout.kkt = o + 89; dout.status = c->d_outi;
+  int rc = launch(c, 1, mode_nlp ? CBFNMPC_MODE_QP_NLP : CBFNMPC_MODE_QP, &din, &dout, mode_nlp ? c->d_xstart : nullptr, st);
+  if (rc) return rc;
+  double ho[41]; int hs = 0; double hk = 0;
+  CK(cudaMemcpyAsync(ho, o, sizeof(double) * 41, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&hk, o + 89, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&hs, c->d_outi, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(x_out, ho, sizeof(double) * 24);
+  for (int i = 0; i < 4 * cc; i++) x_out[24 + i] = ho[24 + i];
+  x_out[nv - 1] = ho[40];
+  if (status) *status = hs;
+  if (kkt) *kkt = hk;
+  return CBFNMPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+"""Shared helpers for the parity tests: oracle batch call from a list of instances."""
+import numpy as np
+import oracle as O
+
+
+def pad_obs(insts, K=20):
+    out = []
+    for a, b, c, d, e in insts:
+        e = np.asarray(e, float)
+        if e.shape[1] < K:
+            e = np.hstack([e, np.repeat(e[:, -1:], K - e.shape[1], 1)])
+        out.append((a, b, c, d, e))
+    return out
+
+
+def oracle_batch(insts, mode=1, nthreads=8, alpha_buf=None, options=None):
+    x0 = np.array([i[0] for i in insts]); xd = np.array([i[1] for i in insts])
+    ft = np.array([np.asarray(i[2]).reshape(2, 4) for i in insts]); ct = np.array([i[3] for i in insts], np.int32)
+    ob = np.array([i[4] for i in insts])
+    ab = np.stack([x0[:, 0], 0 * x0[:, 0], x0[:, 2], 0 * x0[:, 0]], 1) if alpha_buf is None else np.asarray(alpha_buf, float)
+    o = O.default_options()
+    for k, v in (options or {}).items():
+        setattr(o, k, v)
+    return O.solve_batch(x0, xd, ft, ct, ob, ab, mode=mode, nthreads=nthreads, o=o)
+
+
+def compare(out, ref, tol=1e-6):
+    """Parity bar of BASELINE.json: X, U, slack to `tol` relative (scale = max(1, |value|_inf per instance))."""
+    st = out["status"][0]
+    both = (st == 0) & (ref["status"] == 0)
+    sx = np.maximum(1.0, np.abs(ref["X"]).max(1)); su = np.maximum(1.0, np.abs(ref["U"]).max(1))
+    ex = np.abs(out["X"].T - ref["X"]).max(1) / sx
+    eu = np.abs(out["U"].T - ref["U"]).max(1) / su
+    es = np.abs(out["slack"][0] - ref["slack"]) / np.maximum(1.0, np.abs(ref["slack"]))
+    return dict(status_equal=(st == ref["status"]), both=both, ex=ex, eu=eu, es=es,
+                worst=float(max(ex[both].max(), eu[both].max(), es[both].max())) if both.any() else 0.0)
+
+
+# reference row numbers (0-based inside NeqConstraints, DV:245-324) used for active-set comparison
+def active_rows_oracle(ref, i, c):
+    """Set of active rows (z > s) among friction, distance and velocity rows (lambda / box rows excluded)."""
+    mG = 60 + 8 * c
+    rows = list(range(12)) + list(range(mG, mG + 20))
+    z, s = ref["z"][i], ref["s"][i]
+    return {r for r in rows if z[r] > s[r]}
+
+
+def active_rows_mask(out, i, c):
+    mG = 60 + 8 * c
+    rows = list(range(12)) + list(range(mG, mG + 20))
+    lo, hi = int(out["active"][0, i]), int(out["active"][1, i])
+    m = lo | (hi << 64)
+    return {r for r in rows if (m >> r) & 1}
