@@ -8,7 +8,7 @@ import numpy as np
 from . import capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libcbfnmpc.so")
+LIB_PATH = os.environ.get("CBFNMPC_LIB", os.path.join(HERE, "lib", "libcbfnmpc.so"))  # override: tuning experiments only
 INCLUDE = os.path.join(os.path.dirname(HERE), "include", "cbfnmpc.h")
 _lib = None
 

@@ -7,16 +7,23 @@
 #include "cbfnmpc_host.h"
 #include "cbfnmpc_instance.h"
 
-#define WARPS_PER_CTA 4
+// One CTA = CBF_WARPS warps = CBF_WARPS instances kept in lockstep; CBF_WARPS * CBF_MIN_BLOCKS warps resident per SM.
+// 28 x 1 fills an SM's 227 KB of shared memory (28 x 7.6 KB workspaces) at 72 registers per thread (tuned on B200).
+#ifndef CBF_WARPS
+#define CBF_WARPS 28
+#endif
+#ifndef CBF_MIN_BLOCKS
+#define CBF_MIN_BLOCKS 1
+#endif
+#define WARPS_PER_CTA CBF_WARPS
 
 // One warp per instance; the CTA only shares the launch.  Dynamic shared memory: WARPS_PER_CTA workspaces.
-__global__ void __launch_bounds__(32 * WARPS_PER_CTA) cbfnmpc_solve_kernel(const __grid_constant__ KParams P,
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, CBF_MIN_BLOCKS) cbfnmpc_solve_kernel(const __grid_constant__ KParams P,
                                                                           const __grid_constant__ BatchIO io) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WSB* wsall = reinterpret_cast<WSB*>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.x * WARPS_PER_CTA + warp;
-  if (b >= io.B) return;
   solve_warp(wsall[warp], P, io, b);
 }
 

@@ -50,37 +50,54 @@ DEV void run_instance(WSB& ws, const KParams& P, const BatchIO& io, int b) {
   }
   wsync();
   SolveInfo info; info.status = 1; info.qp_iters = 0; info.qp_flag = 3; info.nlp_iters = 0; info.n_fact = 0; info.kkt = 0.0;
+  // Lockstep state machine: every warp of the CTA executes one iteration of its current stage per round and then meets
+  // the others at a CTA barrier, so that the warps of an SM share the instruction stream (DESIGN.md "lockstep").
+  enum { PH_QP = 0, PH_NLP = 1, PH_DONE = 2 };
+  int phase = PH_QP;
+  QpState qs; NlpState ns;
+  bool qp_done;
   if (io.xstart == nullptr) {
-    qp_stage<C>(ws, P, ls, info);
+    qp_done = qp_init<C>(ws, P, ls, info, qs);
   } else {
 #pragma unroll
     for (int q = 0; q < 2; q++) { int v = lane + 32 * q; if (v < d::NV) ws.x[v] = io.xstart[(size_t)v * B + b]; }
     info.qp_flag = 0;
+    qp_done = true;
     wsync();
   }
-  if (io.xqp && lane < 24) io.xqp[(size_t)lane * B + b] = ws.x[lane];
-  if (io.mode == 1) {
-    nlp_stage<C>(ws, P, ls, info);
-  } else {
-    // QP-only answer: unscaled KKT error of the QP
-    double* sb = ws.u.a.sb;
-    double ec = 0.0, ep = 0.0;
+  for (;;) {
+    if (phase == PH_QP) {
+      if (!qp_done) qp_done = qp_iter<C>(ws, P, ls, info, qs);
+      if (qp_done) {
+        if (io.xqp && lane < 24) io.xqp[(size_t)lane * B + b] = ws.x[lane];
+        if (io.mode == 1) { nlp_init<C>(ws, P, ls, info, ns); phase = PH_NLP; }
+        else {
+          // QP-only answer: unscaled KKT error of the QP
+          double* sb = ws.u.a.sb;
+          double ec = 0.0, ep = 0.0;
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-      sb[lane + 32 * q] = ls.zlo[q] - ls.zhi[q];
-      if (ls.m[q].qp) {
-        double e = slot_e(ls.m[q], ws.x, 0.0, 0.0, 0.0);
-        ec = fmax(ec, fmax(fabs(ls.slo[q] * ls.zlo[q]), fabs(ls.shi[q] * ls.zhi[q])));
-        ep = fmax(ep, fmax(fmax(ls.m[q].lo - e, e - ls.m[q].hi), 0.0));
+          for (int q = 0; q < 2; q++) {
+            sb[lane + 32 * q] = ls.zlo[q] - ls.zhi[q];
+            if (ls.m[q].qp) {
+              double e = slot_e(ls.m[q], ws.x, 0.0, 0.0, 0.0);
+              ec = fmax(ec, fmax(fabs(ls.slo[q] * ls.zlo[q]), fabs(ls.shi[q] * ls.zhi[q])));
+              ep = fmax(ep, fmax(fmax(ls.m[q].lo - e, e - ls.m[q].hi), 0.0));
+            }
+          }
+          wsync();
+          double rd = fabs(grad_plus_Aty<C>(ws, P, ws.x, ws.y, lane, true) - gatherJT<C>(sb, ws.gv, lane));
+          if (lane + 32 < d::NV) rd = fmax(rd, fabs(grad_plus_Aty<C>(ws, P, ws.x, ws.y, lane + 32, true) - gatherJT<C>(sb, ws.gv, lane + 32)));
+          double re = (lane < 28) ? fabs(eq_residual<C>(ws, P, ws.x, lane, false)) : 0.0;
+          info.kkt = wmax_nn(fmax(fmax(rd, re), fmax(ec, ep)));
+          info.status = (info.qp_flag == 0) ? 0 : 1;
+          wsync();
+          phase = PH_DONE;
+        }
       }
+    } else if (phase == PH_NLP) {
+      if (nlp_iter<C>(ws, P, ls, info, ns)) phase = PH_DONE;
     }
-    wsync();
-    double rd = fabs(grad_plus_Aty<C>(ws, P, ws.x, ws.y, lane, true) - gatherJT<C>(sb, ws.gv, lane));
-    if (lane + 32 < d::NV) rd = fmax(rd, fabs(grad_plus_Aty<C>(ws, P, ws.x, ws.y, lane + 32, true) - gatherJT<C>(sb, ws.gv, lane + 32)));
-    double re = (lane < 28) ? fabs(eq_residual<C>(ws, P, ws.x, lane, false)) : 0.0;
-    info.kkt = wmax_nn(fmax(fmax(rd, re), fmax(ec, ep)));
-    info.status = (info.qp_flag == 0) ? 0 : 1;
-    wsync();
+    if (!cta_or(phase != PH_DONE)) break;
   }
   // ---- store
   if (lane < 16) { if (io.X) io.X[(size_t)lane * B + b] = ws.x[lane]; }
@@ -119,6 +136,10 @@ DEV void run_instance(WSB& ws, const KParams& P, const BatchIO& io, int b) {
 DEV void solve_warp(WSB& ws, const KParams& P, const BatchIO& io, int b) {
   const int lane = lane_id();
   const int B = io.B;
+  if (b >= B) {  // padding warp of the last CTA: only keeps the CTA barriers balanced
+    for (;;) if (!cta_or(false)) break;
+    return;
+  }
   // ---- load (SoA, one instance)
   if (lane < 4) { ws.x0[lane] = io.x0[(size_t)lane * B + b]; ws.abuf[lane] = io.abuf ? io.abuf[(size_t)lane * B + b] : 0.0; }
   if (lane >= 16) ws.xdes[lane - 16] = io.xdes[(size_t)(lane - 16) * B + b];
@@ -165,5 +186,6 @@ DEV void solve_warp(WSB& ws, const KParams& P, const BatchIO& io, int b) {
       if (io.slack) io.slack[b] = 0.0;
       if (io.active) { io.active[b] = 0ull; io.active[(size_t)B + b] = 0ull; }
     }
+    for (;;) if (!cta_or(false)) break;
   }
 }

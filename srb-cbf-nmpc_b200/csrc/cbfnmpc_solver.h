@@ -614,12 +614,15 @@ struct LaneSlots {
 };
 
 struct SolveInfo { int status, qp_iters, qp_flag, nlp_iters, n_fact; double kkt; };
+struct QpState { double sigma; int it; };
+struct NlpState { double mu, tau, dw_last, theta_max, theta_min, E0; int it, nfilt, status; bool first_ic; };
 
 // =========================================================================================================
 // Stage 1: QP, iSWIFT restated (Prime.c:127-230; kkt_initialize Auxilary.c:680-755)
 // =========================================================================================================
+// qp_init: initial point.  Returns true when the stage is already finished (factorisation failure).
 template <int C>
-DEV void qp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) {
+DEV bool qp_init(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, QpState& st) {
   typedef Dm<C> d;
   const int lane = lane_id();
   const int v0 = lane, v1 = lane + 32;
@@ -647,8 +650,8 @@ DEV void qp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) {
     if (lane < 28) ws.r2[lane] = -eq_residual<C>(ws, P, ws.x, lane, false);
   }
   wsync();
-  info.qp_flag = 3; info.qp_iters = 0;
-  if (!riccati_factor<C>(ws, P, 0.0)) { info.qp_flag = 1; return; }
+  info.qp_flag = 3; info.qp_iters = 0; st.it = 0; st.sigma = 100.0;  // GlobalOptions.h:26
+  if (!riccati_factor<C>(ws, P, 0.0)) { info.qp_flag = 1; return true; }
   kkt_solve<C>(ws, P, 0.0, false);
   ws.x[v0] = ws.dx[v0]; if (hv1) ws.x[v1] = ws.dx[v1];
   if (lane < 28) ws.y[lane] = ws.dy[lane];
@@ -672,10 +675,22 @@ DEV void qp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) {
       ls.zhi[q] = act ? ((ad < 0) ? -rh[q] : -rh[q] + (1.0 + ad)) : 0.0;
     }
   }
-  double sigma = 100.0;  // GlobalOptions.h:26
   info.qp_flag = 2;
-  int it;
-  for (it = 0; it < P.qp_maxit; it++) {
+  return false;
+}
+
+// qp_iter: one Mehrotra predictor-corrector iteration (Prime.c:138-218).  Returns true when the stage is finished.
+template <int C>
+DEV bool qp_iter(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, QpState& st) {
+  typedef Dm<C> d;
+  const int lane = lane_id();
+  const int v0 = lane, v1 = lane + 32;
+  const bool hv1 = v1 < d::NV;
+  const int mrows = d::MQP;
+  double* sa = ws.u.a.sa; double* sb = ws.u.a.sb;
+  double sigma = st.sigma;
+  if (st.it >= P.qp_maxit) return true;
+  {
     // residuals (computeresiduals, Auxilary.c:524-553)
     double rzl[2], rzh[2], acc_rz = 0.0, acc_sz = 0.0;
 #pragma unroll
@@ -694,7 +709,7 @@ DEV void qp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) {
     double ry = (lane < 28) ? -eq_residual<C>(ws, P, ws.x, lane, false) : 0.0;
     double nrx = wsum(rx0 * rx0 + rx1 * rx1), nry = wsum(ry * ry), nrz = wsum(acc_rz), sz = wsum(acc_sz);
     const double lim = P.qp_reltol / sqrt(3.0);
-    if (sqrt(nrx) < lim && sqrt(nrz) < lim && sqrt(nry) < lim && sz / mrows < P.qp_abstol) { info.qp_flag = 0; break; }
+    if (sqrt(nrx) < lim && sqrt(nrz) < lim && sqrt(nry) < lim && sz / mrows < P.qp_abstol) { info.qp_flag = 0; return true; }
     const double mu = sz / mrows;
     double dsl[2], dsh[2], dzl[2], dzh[2];   // affine (then final) slack / multiplier steps
     double cds_l[2], cds_h[2];               // "ds" of form_ds (Auxilary.c:250-267)
@@ -715,7 +730,7 @@ DEV void qp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) {
       if (lane < 28) ws.r2[lane] = ry;
       wsync();
       info.n_fact++;
-      if (!riccati_factor<C>(ws, P, 0.0)) { info.qp_flag = 1; break; }
+      if (!riccati_factor<C>(ws, P, 0.0)) { info.qp_flag = 1; return true; }
       kkt_solve<C>(ws, P, 0.0, false);
       double ap = 1e10, ad = 1e10;
 #pragma unroll
@@ -799,14 +814,17 @@ DEV void qp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) {
     }
     wsync();
   }
-  info.qp_iters = it;
+  st.sigma = sigma;
+  st.it++;
+  info.qp_iters = st.it;
+  return false;
 }
 
 // =========================================================================================================
 // Stage 2: NLP, IPM-F
 // =========================================================================================================
 template <int C>
-DEV void nlp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) {
+DEV void nlp_init(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, NlpState& st) {
   typedef Dm<C> d;
   const int lane = lane_id();
   const int v0 = lane, v1 = lane + 32;
@@ -842,9 +860,8 @@ DEV void nlp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) 
   if (lane < 28) ws.y[lane] = 0.0;
   if (lane < 16) ws.filt[lane] = 0.0;
   wsync();
-  double mu = P.mu_init, tau = fmax(P.tau_min, 1.0 - mu), dw_last = 0.0;
-  bool first_ic = true;
-  int nfilt = 0;
+  const double mu = P.mu_init;
+  st.mu = mu; st.tau = fmax(P.tau_min, 1.0 - mu); st.dw_last = 0.0; st.first_ic = true; st.nfilt = 0; st.it = 0; st.status = 1; st.E0 = 1e300;
 #pragma unroll
   for (int q = 0; q < 2; q++) {
     double e = slot_e(ls.m[q], ws.x, ox, oy, ws.x[d::XD]);
@@ -853,15 +870,30 @@ DEV void nlp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) 
     ls.zlo[q] = ls.m[q].vlo ? mu / ls.slo[q] : 0.0;
     ls.zhi[q] = ls.m[q].vhi ? mu / ls.shi[q] : 0.0;
   }
-  double theta_max, theta_min;
   {
     double r = (lane < 28) ? fabs(eq_residual<C>(ws, P, ws.x, lane, false)) : 0.0;
     double th0 = wsum(r);
-    theta_max = 1e4 * fmax(1.0, th0); theta_min = 1e-4 * fmax(1.0, th0);
+    st.theta_max = 1e4 * fmax(1.0, th0); st.theta_min = 1e-4 * fmax(1.0, th0);
   }
-  int status = 1, it = 0;
-  double E0 = 1e300;
-  for (it = 0; it <= P.max_iter; it++) {
+  info.status = 1; info.nlp_iters = 0;
+}
+
+// nlp_iter: one IPM-F iteration.  Returns true when the stage is finished (info.status set).
+template <int C>
+DEV bool nlp_iter(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, NlpState& st) {
+  typedef Dm<C> d;
+  const int lane = lane_id();
+  const int v0 = lane, v1 = lane + 32;
+  const bool hv1 = v1 < d::NV;
+  double* sa = ws.u.a.sa; double* sb = ws.u.a.sb;
+  const double ox = ws.obs[0], oy = ws.obs[1];
+  double mu = st.mu, tau = st.tau, dw_last = st.dw_last, E0;
+  const double theta_max = st.theta_max, theta_min = st.theta_min;
+  bool first_ic = st.first_ic;
+  int nfilt = st.nfilt;
+  const int it = st.it;
+  int status = 1;
+  {
     // ---- slots at x: s = c(x) (feasible IPM), multiplier safeguard, gradients of the distance rows
     double gx[2] = {0, 0}, gy[2] = {0, 0}, e_c = 0.0, zmax = 0.0, smin = 1e300;
     const double xdl = ws.x[d::XD];
@@ -898,11 +930,11 @@ DEV void nlp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) 
     zmax = wmax_nn(zmax);
     const double th = wsum(fabs(re));
     E0 = fmax(e_d, fmax(e_p, e_c));
-    info.kkt = E0;
+    info.kkt = E0; info.nlp_iters = it;
     CBF_DBG("it %d mu %.2e E0 %.3e ed %.2e ep %.2e ec %.2e zmax %.2e th %.2e\n", it, mu, E0, e_d, e_p, e_c, zmax, th);
-    if (E0 <= P.tol) { status = 0; break; }
-    if (it == P.max_iter) break;
-    if (!(zmax < P.z_div) || !(E0 < 1e300) || wany(!(smin > 0.0))) { status = 2; break; }
+    if (E0 <= P.tol) { info.status = 0; return true; }
+    if (it == P.max_iter) { info.status = 1; return true; }
+    if (!(zmax < P.z_div) || !(E0 < 1e300) || wany(!(smin > 0.0))) { info.status = 2; return true; }
     // ---- barrier update (Ipopt eq. 7)
     for (;;) {
       double emu = 0.0;
@@ -954,7 +986,7 @@ DEV void nlp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) 
       if (dw > P.dw_max) break;
       wsync();
     }
-    if (!ok) { status = 3; break; }
+    if (!ok) { info.status = 3; return true; }
     if (dw > 0.0) { dw_last = dw; first_ic = false; }
     kkt_solve<C>(ws, P, dw, true);
     // ---- slot steps
@@ -1109,7 +1141,7 @@ DEV void nlp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) 
       alpha *= 0.5;
     }
     CBF_DBG("   alpha %.3e acc %d ftype %d ph %.10e dphi %.3e\n", alpha, (int)accepted, (int)ftype, ph, dphi);
-    if (!accepted) { status = 2; break; }
+    if (!accepted) { info.status = 2; return true; }
     wsync();
     if (!ftype) {
       if (nfilt >= P.filter_cap) {
@@ -1129,5 +1161,7 @@ DEV void nlp_stage(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info) 
     for (int q = 0; q < 2; q++) { ls.zlo[q] += a_dmax * dzl[q]; ls.zhi[q] += a_dmax * dzh[q]; }
     wsync();
   }
-  info.status = status; info.nlp_iters = it; info.kkt = E0;
+  (void)status;
+  st.mu = mu; st.tau = tau; st.dw_last = dw_last; st.first_ic = first_ic; st.nfilt = nfilt; st.it = it + 1;
+  return false;
 }

@@ -45,6 +45,8 @@ DEV double wmin_nn(double v) {
 }
 DEV int wmin_i(int v) { return __reduce_min_sync(FULL, v); }
 DEV unsigned wor(unsigned v) { return __reduce_or_sync(FULL, v); }
+// CTA-wide barrier + OR of a predicate: keeps the warps of a CTA in lockstep (one IPM iteration per round)
+DEV bool cta_or(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
 DEV double rcp(double v) { return 1.0 / v; }
 DEV double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 DEV double add_rn(double a, double b) { return __dadd_rn(a, b); }
@@ -116,6 +118,7 @@ DEV unsigned wor(unsigned v) {
   emu::barrier();
   return r;
 }
+DEV bool cta_or(bool p) { return wany(p); }  // the emulated CTA is a single warp
 DEV double rcp(double v) { return 1.0 / v; }
 DEV double mul_rn(double a, double b) { volatile double r = a * b; return r; }
 DEV double add_rn(double a, double b) { volatile double r = a + b; return r; }

@@ -1,0 +1,86 @@
+"""NLP stage of the oracle ("parity unpinned": no reference implementation is runnable here).  Checks that the restated
+NLP has the structure of the reference's SNOPT print file, that the oracle's answers are KKT points verified by an
+independent residual computation, and that scipy SLSQP reaches the same local solution from the same start."""
+import os
+import numpy as np
+import oracle as O
+import proto_numpy as P
+from srb_cbf_nmpc_b200 import scenarios as S
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_structure_matches_snopt_print_file():
+    """print_file.out:15,94-226: 133 rows = 1 objective + 28 equalities + 92 linear + 4 distance + 8 velocity at 4 stance feet;
+    friction bound 0.14354, distance lower bound 1.90000, velocity bounds +-0.35000; 4981 declared derivatives = 121*41+20."""
+    x0, xdes, feet, contact, obs = S.cfg1_instance(4)
+    Q, f, A, b, G, h = O.pack_dense(x0, xdes, P.stance_matrix(feet, contact))
+    assert Q.shape == (41, 41) and A.shape == (28, 41) and G.shape == (92, 41)
+    assert 1 + A.shape[0] + G.shape[0] + 4 + 8 == 133
+    assert (A.shape[0] + 1 + G.shape[0]) * 41 + 4 * 3 + 8 == 4981
+    g = O.default_gains()
+    assert abs(h[0] - 0.14354) < 5e-6 and abs(g.eps_dist - 1.9) < 1e-6 and abs(g.v_max - 0.35) < 1e-7
+    assert g.eps_dist == float(np.float32(1.9)) and g.v_max == float(np.float32(0.35))   # float literals promoted to double
+    Q2, *_ = O.pack_dense(x0, xdes, P.stance_matrix(feet, [0, 1, 1, 0]))
+    assert Q2.shape == (33, 33)
+
+
+def kkt_numpy(r, inst):
+    x0, xdes, feet, contact, obs = inst
+    Q, f, A, b, G, h = P.pack_dense(x0, xdes, P.stance_matrix(feet, contact))
+    prob = P.NlpProblem(Q, f, A, b, G, h, r["obs"])
+    x, y, z = r["x"], r["y"], r["z"]
+    c = prob.cons(x)
+    rd = prob.grad(x) + A.T @ y - prob.jac(x).T @ z
+    return max(np.abs(rd).max(), np.abs(A @ x - b).max(), np.abs(c * z).max()), c.min(), z.min()
+
+
+def test_oracle_returns_kkt_points():
+    insts = [S.cfg1_instance(4), S.cfg1_instance(2)] + S.cfg3_instances(40)
+    nconv = 0
+    for inst in insts:
+        obs = inst[4]
+        r = O.solve_instance(*inst[:4], obs)
+        if r["status"] != 0:
+            assert r["status"] == 2
+            continue
+        nconv += 1
+        e, cmin, zmin = kkt_numpy(r, inst)
+        assert e < 1e-8 and cmin > 0 and zmin >= 0
+    assert nconv >= 36
+
+
+def test_cfg1_matches_survey_probe():
+    """objective 1093.0396, distance rows 1 and 4 active at 1.9, slack ~0.8527 (scipy probe)."""
+    inst = S.cfg1_instance(4)
+    r = O.solve_instance(*inst)
+    assert r["status"] == 0 and r["qp_iters"] == 5
+    assert np.abs(r["x_qp"][:2] - [0.0032120922582, 0.100424967798]).max() < 1e-9
+    x = r["x"]
+    d = [(x[4 * k] - 1.0) ** 2 + (x[4 * k + 2] - 0.2) ** 2 + x[-1] for k in range(4)]
+    assert abs(d[0] - 1.9) < 1e-6 and abs(d[3] - 1.9) < 1e-6 and d[1] > 1.9 + 1e-3 and d[2] > 1.9 + 1e-3
+    assert abs(x[-1] - 0.8527) < 1e-3
+
+
+def test_golden_scipy_agreement():
+    """Independent solver (scipy SLSQP, run when the fixture was minted) reaches the same local solution."""
+    g = np.load(os.path.join(GOLD, "mpc_golden.npz"))
+    for i in range(len(g["nv"])):
+        nv = int(g["nv"][i])
+        r = O.solve_instance(g["x0"][i], g["xdes"][i], g["feet"][i], list(g["contact"][i]), g["obs"][i])
+        assert r["status"] == int(g["status"][i])
+        if r["status"] != 0:
+            continue
+        assert np.abs(r["x"][:24] - g["x_oracle"][i][:24]).max() < 1e-9
+        xs = g["x_scipy"][i][:nv]
+        assert np.abs(r["x"][:24] - xs[:24]).max() < 2e-5 and abs(r["x"][-1] - xs[-1]) < 1e-6
+        assert abs(g["obj_oracle"][i] - g["obj_scipy"][i]) < 1e-3 * max(1.0, abs(g["obj_oracle"][i]) * 1e-4)
+
+
+def test_numpy_prototype_follows_c_oracle():
+    for inst in [S.cfg1_instance(4)] + S.cfg3_instances(6):
+        rc = O.solve_instance(*inst)
+        rn = P.solve_instance(*inst)
+        assert (rc["status"] == 0) == (rn["info"]["status"] == 0)
+        if rc["status"] == 0:
+            assert np.abs(rc["x"][:24] - rn["x"][:24]).max() < 1e-9
