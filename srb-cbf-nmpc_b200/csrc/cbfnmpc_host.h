@@ -20,7 +20,7 @@ static inline void host_default_options(cbfnmpc_options* o) {
   o->gamma_theta = 1e-5; o->gamma_phi = 1e-5; o->eta_phi = 1e-4; o->kappa_sigma = 1e10; o->alpha_min = 1e-10;
   o->dw_first = 1e-4; o->dw_min = 1e-20; o->kw_minus = 1.0 / 3.0; o->kw_plus = 8.0; o->kw_plus_first = 100.0;
   o->dw_max = 1e40; o->rho_lambda = 1e-6; o->z_div = 1e13;
-  o->sigma_cap = 1e8; o->refine_rel = 1e-8; o->refine_abs = 1e-13;
+  o->sigma_cap = 1e8; o->refine_rel = 1e-4; o->refine_abs = 1e-11;
   o->max_iter = 200; o->filter_cap = 8; o->max_refine = 2;
 }
 

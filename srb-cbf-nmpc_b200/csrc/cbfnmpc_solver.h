@@ -217,17 +217,17 @@ DEV bool chol_small(const double* R, double* L) {  // R packed lower (00,10,11,2
   bool ok = true;
   double d0 = R[0];
   ok = ok && (d0 > 0.0) && (d0 < 1e300);
-  double i0 = 1.0 / sqrt(d0);
+  double i0 = rsq(d0);
   L[0] = i0;
   if (NW == 3) {
     double l10 = R[1] * i0, l20 = R[3] * i0;
     double d1 = R[2] - l10 * l10;
     ok = ok && (d1 > 0.0) && (d1 < 1e300);
-    double i1 = 1.0 / sqrt(d1);
+    double i1 = rsq(d1);
     double l21 = (R[4] - l20 * l10) * i1;
     double d2 = R[5] - l20 * l20 - l21 * l21;
     ok = ok && (d2 > 0.0) && (d2 < 1e300);
-    double i2 = 1.0 / sqrt(d2);
+    double i2 = rsq(d2);
     L[1] = l10; L[2] = i1; L[3] = l20; L[4] = l21; L[5] = i2;
   }
   return ok;
@@ -275,7 +275,7 @@ DEVNI bool riccati_factor(WS<C>& ws, const KParams& P, double dw) {
     // round 2: R~ (NR), S~ (4 NW), Q~ (10)
     if (lane < d::NR) {
       int a = 0, b = 0;
-      if (NW == 3) { const int ra[6] = {0, 1, 1, 2, 2, 2}, rb[6] = {0, 0, 1, 0, 1, 2}; a = ra[lane]; b = rb[lane]; }
+      if (NW == 3) { a = (lane >= 3) ? 2 : ((lane >= 1) ? 1 : 0); b = lane - ((a * (a + 1)) >> 1); }
       double s = ws.D[a] * (ws.hu[2 * j] + dw) * ws.D[b] + ws.D[NW + a] * (ws.hu[2 * j + 1] + dw) * ws.D[NW + b];
       s += ws.hl[C * j + C - 1] + dw;
       if (a == b) s += ws.hl[C * j + a] + dw;
@@ -292,8 +292,7 @@ DEVNI bool riccati_factor(WS<C>& ws, const KParams& P, double dw) {
       }
     } else if (lane < d::NR + d::NS + 10) {
       if (j >= 1) {
-        const int qi[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3}, qk[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
-        int t = lane - d::NR - d::NS, i = qi[t], k = qk[t], bi = i >> 1, ri = i & 1;
+        int t = lane - d::NR - d::NS, i = (t >= 6) ? 3 : ((t >= 3) ? 2 : ((t >= 1) ? 1 : 0)), k = t - ((i * (i + 1)) >> 1), bi = i >> 1, ri = i & 1;
         double s = (ri ? P.a12 : P.a11) * PA[4 * (2 * bi) + k] + (ri ? P.a22 : P.a21) * PA[4 * (2 * bi + 1) + k];
         if (i == k) s += ws.hx[4 * (j - 1) + i] + dw;
         else if (i == 2 && k == 0) s += ws.hxy[j - 1];
@@ -319,8 +318,7 @@ DEVNI bool riccati_factor(WS<C>& ws, const KParams& P, double dw) {
     wsync();
     // round 5: P_j = Q~ - S~' K
     if (lane < 10) {
-      const int qi[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3}, qk[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
-      int i = qi[lane], k = qk[lane];
+      int i = (lane >= 6) ? 3 : ((lane >= 3) ? 2 : ((lane >= 1) ? 1 : 0)), k = lane - ((i * (i + 1)) >> 1);
       double s = Qt[lane];
 #pragma unroll
       for (int a = 0; a < NW; a++) s -= ws.St[j][a * 4 + i] * ws.K[j][a * 4 + k];
@@ -467,13 +465,13 @@ DEVNI bool border_factor(WS<C>& ws, const KParams& P, double dw) {
   bool ok = true;
   double L[10];
   {
-    double d0 = T[0]; ok = ok && d0 > 0.0; double i0 = 1.0 / sqrt(d0);
+    double d0 = T[0]; ok = ok && d0 > 0.0 && d0 < 1e300; double i0 = rsq(d0);
     double l10 = T[1] * i0, l20 = T[3] * i0, l30 = T[6] * i0;
-    double d1 = T[2] - l10 * l10; ok = ok && d1 > 0.0; double i1 = 1.0 / sqrt(d1);
+    double d1 = T[2] - l10 * l10; ok = ok && d1 > 0.0; double i1 = rsq(d1);
     double l21 = (T[4] - l20 * l10) * i1, l31 = (T[7] - l30 * l10) * i1;
-    double d2 = T[5] - l20 * l20 - l21 * l21; ok = ok && d2 > 0.0; double i2 = 1.0 / sqrt(d2);
+    double d2 = T[5] - l20 * l20 - l21 * l21; ok = ok && d2 > 0.0; double i2 = rsq(d2);
     double l32 = (T[8] - l30 * l20 - l31 * l21) * i2;
-    double d3 = T[9] - l30 * l30 - l31 * l31 - l32 * l32; ok = ok && d3 > 0.0; double i3 = 1.0 / sqrt(d3);
+    double d3 = T[9] - l30 * l30 - l31 * l31 - l32 * l32; ok = ok && d3 > 0.0; double i3 = rsq(d3);
     L[0] = i0; L[1] = l10; L[2] = i1; L[3] = l20; L[4] = l21; L[5] = i2; L[6] = l30; L[7] = l31; L[8] = l32; L[9] = i3;
   }
   if (!ok) return false;
@@ -713,15 +711,21 @@ DEV bool qp_iter(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, Qp
     const double mu = sz / mrows;
     double dsl[2], dsh[2], dzl[2], dzh[2];   // affine (then final) slack / multiplier steps
     double cds_l[2], cds_h[2];               // "ds" of form_ds (Auxilary.c:250-267)
+    double isl[2], ish[2], izl[2], izh[2], wl[2], wh[2];  // 1/s, 1/z, W^-1 = z/s  (one reciprocal each per iteration)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const bool act = ls.m[q].qp;
+      isl[q] = rcp(ls.slo[q]); ish[q] = rcp(ls.shi[q]);
+      izl[q] = act ? rcp(ls.zlo[q]) : 0.0; izh[q] = act ? rcp(ls.zhi[q]) : 0.0;
+      wl[q] = act ? ls.zlo[q] * isl[q] : 0.0; wh[q] = act ? ls.zhi[q] * ish[q] : 0.0;
+    }
     wsync();
     if (sigma > 0.0) {
       // predictor: W = s/z, ds = -s z, rhs3 = rz - ds/z = rz + s
 #pragma unroll
       for (int q = 0; q < 2; q++) {
-        bool act = ls.m[q].qp;
-        double wl = act ? ls.zlo[q] / ls.slo[q] : 0.0, wh = act ? ls.zhi[q] / ls.shi[q] : 0.0;
-        sa[lane + 32 * q] = wl + wh;
-        sb[lane + 32 * q] = wh * (rzh[q] + ls.shi[q]) - wl * (rzl[q] + ls.slo[q]);
+        sa[lane + 32 * q] = wl[q] + wh[q];
+        sb[lane + 32 * q] = wh[q] * (rzh[q] + ls.shi[q]) - wl[q] * (rzl[q] + ls.slo[q]);
       }
       wsync();
       assemble_hessian<C>(ws, P, false, 0.0);
@@ -732,24 +736,20 @@ DEV bool qp_iter(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, Qp
       info.n_fact++;
       if (!riccati_factor<C>(ws, P, 0.0)) { info.qp_flag = 1; return true; }
       kkt_solve<C>(ws, P, 0.0, false);
-      double ap = 1e10, ad = 1e10;
+      double rp = 0.0, rdm = 0.0;   // max(-ds/s), max(-dz/z): alpha^max = 1/that (findsteplength, Auxilary.c:271-294)
 #pragma unroll
       for (int q = 0; q < 2; q++) {
-        bool act = ls.m[q].qp;
+        const bool act = ls.m[q].qp;
         double de = slot_de(ls.m[q], ws.dx, 0.0, 0.0, 0.0);
-        double wl = act ? ls.zlo[q] / ls.slo[q] : 0.0, wh = act ? ls.zhi[q] / ls.shi[q] : 0.0;
-        dzh[q] = wh * (de - (rzh[q] + ls.shi[q]));
-        dzl[q] = wl * (-de - (rzl[q] + ls.slo[q]));
-        dsh[q] = act ? (-ls.shi[q] * ls.zhi[q] - ls.shi[q] * dzh[q]) / ls.zhi[q] : 0.0;
-        dsl[q] = act ? (-ls.slo[q] * ls.zlo[q] - ls.slo[q] * dzl[q]) / ls.zlo[q] : 0.0;
-        if (dsh[q] < 0) ap = fmin(ap, -ls.shi[q] / dsh[q]);
-        if (dsl[q] < 0) ap = fmin(ap, -ls.slo[q] / dsl[q]);
-        if (dzh[q] < 0) ad = fmin(ad, -ls.zhi[q] / dzh[q]);
-        if (dzl[q] < 0) ad = fmin(ad, -ls.zlo[q] / dzl[q]);
+        dzh[q] = wh[q] * (de - (rzh[q] + ls.shi[q]));
+        dzl[q] = wl[q] * (-de - (rzl[q] + ls.slo[q]));
+        dsh[q] = act ? (-ls.shi[q] * ls.zhi[q] - ls.shi[q] * dzh[q]) * izh[q] : 0.0;
+        dsl[q] = act ? (-ls.slo[q] * ls.zlo[q] - ls.slo[q] * dzl[q]) * izl[q] : 0.0;
+        rp = fmax(rp, fmax(-dsh[q] * ish[q], -dsl[q] * isl[q]));
+        rdm = fmax(rdm, fmax(-dzh[q] * izh[q], -dzl[q] * izl[q]));
       }
-      ap = wmin_nn(ap); ad = wmin_nn(ad);
-      if (ap == 1e10) ap = 1.0;
-      if (ad == 1e10) ad = 1.0;
+      rp = wmax_nn(rp); rdm = wmax_nn(rdm);
+      const double ap = (rp > 0.0) ? 1.0 / rp : 1.0, ad = (rdm > 0.0) ? 1.0 / rdm : 1.0;
       double num = 0.0;
 #pragma unroll
       for (int q = 0; q < 2; q++)
@@ -774,11 +774,10 @@ DEV bool qp_iter(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, Qp
     wsync();
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-      bool act = ls.m[q].qp;
-      double wl = act ? ls.zlo[q] / ls.slo[q] : 0.0, wh = act ? ls.zhi[q] / ls.shi[q] : 0.0;
-      r3l[q] = act ? rzl[q] - cds_l[q] / ls.zlo[q] : 0.0;
-      r3h[q] = act ? rzh[q] - cds_h[q] / ls.zhi[q] : 0.0;
-      sb[lane + 32 * q] = wh * r3h[q] - wl * r3l[q];
+      const bool act = ls.m[q].qp;
+      r3l[q] = act ? rzl[q] - cds_l[q] * izl[q] : 0.0;
+      r3h[q] = act ? rzh[q] - cds_h[q] * izh[q] : 0.0;
+      sb[lane + 32 * q] = wh[q] * r3h[q] - wl[q] * r3l[q];
     }
     wsync();
     ws.r1[v0] = rx0 + gatherJT<C>(sb, ws.gv, v0);
@@ -786,24 +785,20 @@ DEV bool qp_iter(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, Qp
     if (lane < 28) ws.r2[lane] = ry;
     wsync();
     kkt_solve<C>(ws, P, 0.0, false);
-    double ap = 1e10, ad = 1e10;
+    double rp = 0.0, rdm = 0.0;
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-      bool act = ls.m[q].qp;
+      const bool act = ls.m[q].qp;
       double de = slot_de(ls.m[q], ws.dx, 0.0, 0.0, 0.0);
-      double wl = act ? ls.zlo[q] / ls.slo[q] : 0.0, wh = act ? ls.zhi[q] / ls.shi[q] : 0.0;
-      dzh[q] = wh * (de - r3h[q]);
-      dzl[q] = wl * (-de - r3l[q]);
-      dsh[q] = act ? (cds_h[q] - ls.shi[q] * dzh[q]) / ls.zhi[q] : 0.0;
-      dsl[q] = act ? (cds_l[q] - ls.slo[q] * dzl[q]) / ls.zlo[q] : 0.0;
-      if (dsh[q] < 0) ap = fmin(ap, -ls.shi[q] / dsh[q]);
-      if (dsl[q] < 0) ap = fmin(ap, -ls.slo[q] / dsl[q]);
-      if (dzh[q] < 0) ad = fmin(ad, -ls.zhi[q] / dzh[q]);
-      if (dzl[q] < 0) ad = fmin(ad, -ls.zlo[q] / dzl[q]);
+      dzh[q] = wh[q] * (de - r3h[q]);
+      dzl[q] = wl[q] * (-de - r3l[q]);
+      dsh[q] = act ? (cds_h[q] - ls.shi[q] * dzh[q]) * izh[q] : 0.0;
+      dsl[q] = act ? (cds_l[q] - ls.slo[q] * dzl[q]) * izl[q] : 0.0;
+      rp = fmax(rp, fmax(-dsh[q] * ish[q], -dsl[q] * isl[q]));
+      rdm = fmax(rdm, fmax(-dzh[q] * izh[q], -dzl[q] * izl[q]));
     }
-    ap = wmin_nn(ap); ad = wmin_nn(ad);
-    if (ap == 1e10) ap = 1.0;
-    if (ad == 1e10) ad = 1.0;
+    rp = wmax_nn(rp); rdm = wmax_nn(rdm);
+    double ap = (rp > 0.0) ? 1.0 / rp : 1.0, ad = (rdm > 0.0) ? 1.0 / rdm : 1.0;
     ap = fmin(0.99 * ap, 1.0); ad = fmin(0.99 * ad, 1.0);
     ws.x[v0] += ap * ws.dx[v0]; if (hv1) ws.x[v1] += ap * ws.dx[v1];
     if (lane < 28) ws.y[lane] += ad * ws.dy[lane];
@@ -867,8 +862,8 @@ DEV void nlp_init(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, N
     double e = slot_e(ls.m[q], ws.x, ox, oy, ws.x[d::XD]);
     ls.slo[q] = ls.m[q].vlo ? e - ls.m[q].lo : 1.0;
     ls.shi[q] = ls.m[q].vhi ? ls.m[q].hi - e : 1.0;
-    ls.zlo[q] = ls.m[q].vlo ? mu / ls.slo[q] : 0.0;
-    ls.zhi[q] = ls.m[q].vhi ? mu / ls.shi[q] : 0.0;
+    ls.zlo[q] = ls.m[q].vlo ? mu * rcp(ls.slo[q]) : 0.0;
+    ls.zhi[q] = ls.m[q].vhi ? mu * rcp(ls.shi[q]) : 0.0;
   }
   {
     double r = (lane < 28) ? fabs(eq_residual<C>(ws, P, ws.x, lane, false)) : 0.0;
@@ -905,8 +900,9 @@ DEV bool nlp_iter(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, N
       ls.shi[q] = m.vhi ? m.hi - e : 1.0;
       smin = fmin(smin, fmin(ls.slo[q], ls.shi[q]));
       if (it > 0) {  // z reset (Ipopt eq. 16) with the mu of the step just taken
-        if (m.vlo) ls.zlo[q] = fmin(fmax(ls.zlo[q], mu / (P.kappa_sigma * ls.slo[q])), P.kappa_sigma * mu / ls.slo[q]);
-        if (m.vhi) ls.zhi[q] = fmin(fmax(ls.zhi[q], mu / (P.kappa_sigma * ls.shi[q])), P.kappa_sigma * mu / ls.shi[q]);
+        const double mr_lo = mu * rcp(ls.slo[q]), mr_hi = mu * rcp(ls.shi[q]), iks = 1.0 / P.kappa_sigma;
+        if (m.vlo) ls.zlo[q] = fmin(fmax(ls.zlo[q], mr_lo * iks), P.kappa_sigma * mr_lo);
+        if (m.vhi) ls.zhi[q] = fmin(fmax(ls.zhi[q], mr_hi * iks), P.kappa_sigma * mr_hi);
       }
       if (m.kind == 2) {
         gx[q] = 2.0 * (ws.x[m.i1] - ox); gy[q] = 2.0 * (ws.x[m.i2] - oy);
@@ -956,7 +952,7 @@ DEV bool nlp_iter(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, N
 #pragma unroll
     for (int q = 0; q < 2; q++) {
       const SlotMeta& m = ls.m[q];
-      rlo[q] = 1.0 / ls.slo[q]; rhi[q] = 1.0 / ls.shi[q];
+      rlo[q] = rcp(ls.slo[q]); rhi[q] = rcp(ls.shi[q]);
       double sg = ls.zlo[q] * rlo[q] + ls.zhi[q] * rhi[q];
       sa[lane + 32 * q] = sg;
       sb[lane + 32 * q] = (m.vlo ? mu * rlo[q] : 0.0) - (m.vhi ? mu * rhi[q] : 0.0);
@@ -964,7 +960,7 @@ DEV bool nlp_iter(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, N
         int k = (lane + 32 * q) - d::S_DIST;
         double scap = fmin(sg, P.sigma_cap);
         bool cap = sg > P.sigma_cap;
-        ws.sc[k] = scap; ws.capped[k] = cap ? 1 : 0; ws.srinv[k] = cap ? 1.0 / (sg - scap) : 0.0; ws.zdist[k] = ls.zlo[q];
+        ws.sc[k] = scap; ws.capped[k] = cap ? 1 : 0; ws.srinv[k] = cap ? rcp(sg - scap) : 0.0; ws.zdist[k] = ls.zlo[q];
       }
     }
     wsync();
@@ -1064,16 +1060,18 @@ DEV bool nlp_iter(WS<C>& ws, const KParams& P, LaneSlots& ls, SolveInfo& info, N
         quad[q] = (ls.m[q].kind == 2) ? ws.dx[ls.m[q].i1] * ws.dx[ls.m[q].i1] + ws.dx[ls.m[q].i2] * ws.dx[ls.m[q].i2] : 0.0;
     }
     // ---- fraction to the boundary
-    double a_pmax = 1.0, a_dmax = 1.0;
+    // alpha_max = min(1, tau / max_i(-ds_i / s_i)): one reciprocal per lane instead of one division per row
+    double rp = 0.0, rdm = 0.0;
 #pragma unroll
     for (int q = 0; q < 2; q++) {
       const SlotMeta& m = ls.m[q];
-      if (m.vlo && de[q] < 0) a_pmax = fmin(a_pmax, -tau * ls.slo[q] / de[q]);
-      if (m.vhi && de[q] > 0) a_pmax = fmin(a_pmax, tau * ls.shi[q] / de[q]);
-      if (m.vlo && dzl[q] < 0) a_dmax = fmin(a_dmax, -tau * ls.zlo[q] / dzl[q]);
-      if (m.vhi && dzh[q] < 0) a_dmax = fmin(a_dmax, -tau * ls.zhi[q] / dzh[q]);
+      if (m.vlo) rp = fmax(rp, -de[q] * rlo[q]);
+      if (m.vhi) rp = fmax(rp, de[q] * rhi[q]);
+      double zq = fmax(m.vlo ? -dzl[q] * rcp(ls.zlo[q]) : 0.0, m.vhi ? -dzh[q] * rcp(ls.zhi[q]) : 0.0);
+      rdm = fmax(rdm, zq);
     }
-    a_pmax = wmin_nn(a_pmax); a_dmax = wmin_nn(a_dmax);
+    rp = wmax_nn(rp); rdm = wmax_nn(rdm);
+    double a_pmax = (rp > tau) ? tau / rp : 1.0, a_dmax = (rdm > tau) ? tau / rdm : 1.0;
     CBF_DBG("   dw %.1e apmax %.3e admax %.3e ddl %.3e\n", dw, a_pmax, a_dmax, ws.dx[d::XD]);
     // ---- filter line search on phi = f - mu sum log s  (theta = ||A x - b||_1 shrinks by (1 - alpha))
     double ph, dphi, dQd, gdx;

@@ -47,7 +47,23 @@ DEV int wmin_i(int v) { return __reduce_min_sync(FULL, v); }
 DEV unsigned wor(unsigned v) { return __reduce_or_sync(FULL, v); }
 // CTA-wide barrier + OR of a predicate: keeps the warps of a CTA in lockstep (one IPM iteration per round)
 DEV bool cta_or(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
-DEV double rcp(double v) { return 1.0 / v; }
+// 1/v and 1/sqrt(v) for normal, positive-range operands: hardware seed (MUFU.RCP64H / RSQ64H) + two Newton steps (~1 ulp),
+// ~6 instructions instead of the ~20-instruction IEEE sequences with their slow-path calls.
+DEV double rcp(double v) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+  r = fma(fma(-v, r, 1.0), r, r);
+  r = fma(fma(-v, r, 1.0), r, r);
+  return r;
+}
+DEV double rsq(double v) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+  double h = 0.5 * v;
+  r = fma(fma(-h * r, r, 0.5), r, r);
+  r = fma(fma(-h * r, r, 0.5), r, r);
+  return r;
+}
 DEV double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 DEV double add_rn(double a, double b) { return __dadd_rn(a, b); }
 
@@ -120,6 +136,7 @@ DEV unsigned wor(unsigned v) {
 }
 DEV bool cta_or(bool p) { return wany(p); }  // the emulated CTA is a single warp
 DEV double rcp(double v) { return 1.0 / v; }
+DEV double rsq(double v) { return 1.0 / sqrt(v); }
 DEV double mul_rn(double a, double b) { volatile double r = a * b; return r; }
 DEV double add_rn(double a, double b) { volatile double r = a + b; return r; }
 #endif
