@@ -1,0 +1,78 @@
+// team_cycles.cpp -- host-side C++ driver above the C ABI: the call sequence of the reference's 1 kHz loop
+// (/root/reference/src/A1_Sim.cpp:227-244: updateState -> run_NMPC -> get_alphaCOM/get_MPCsol) for a 4-agent team
+// (/root/reference/src/A1_Sim_4_agents.cpp:857-873 start positions and obstacles), with the LIP state rolled forward
+// between cycles by the planned trajectory (the reference rolls it forward in RaiSim, which is not part of this path).
+//
+//   build:  g++ -std=c++17 -O2 -Iinclude examples/team_cycles.cpp -Lsrb-cbf-nmpc_b200/lib -lcbfnmpc -Wl,-rpath,'$ORIGIN/../srb-cbf-nmpc_b200/lib' -o examples/team_cycles
+//   run  :  examples/team_cycles [cycles] [use_snopt 0/1]      prints one line per agent and cycle:
+//           cycle agent status kkt slack X[16] alpha[20]
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include "mpc_dist_gpu.hpp"
+
+int main(int argc, char** argv) {
+  using namespace cbfnmpc;
+  const int cycles = argc > 1 ? atoi(argv[1]) : 3;
+  const bool nlp = argc > 2 ? atoi(argv[2]) != 0 : true;
+  const int ncols = 4 * (cycles + 1);
+  const double Ts = 0.043, goal[2] = {10.0, 0.0};
+  const double Pstart[8] = {0.0, 0.0, 0.0, -0.9, -1.0, 0.0, -1.0, -0.9};            // SIM4:862
+  const int K = 9;
+  const double obs_x[K] = {2.2, 1, 0.85, 1, 1, 3, 3.0, 3, -100}, obs_y[K] = {0.9, 1.2, -0.65, 2, -1.75, 0.2, -0.70, -2.2, 99.5};  // SIM4:872-873
+  double Pobs[2 * K];
+  for (int k = 0; k < K; k++) { Pobs[2 * k] = obs_x[k]; Pobs[2 * k + 1] = obs_y[k]; }
+  // straight-line reference toward the goal at 0.2 m/s (stand-in for generateReferenceTrajectory, MPC_dist.cpp:930-1104)
+  std::vector<double> Pr(8 * (size_t)ncols), Prd(8 * (size_t)ncols);
+  for (int a = 0; a < 4; a++) {
+    double dx = goal[0] - Pstart[2 * a], dy = goal[1] - Pstart[2 * a + 1], n = std::sqrt(dx * dx + dy * dy);
+    double vx = 0.2 * dx / n, vy = 0.2 * dy / n;
+    for (int j = 0; j < ncols; j++) {
+      Pr[(size_t)j * 8 + 2 * a] = Pstart[2 * a] + vx * (j + 1) * Ts; Pr[(size_t)j * 8 + 2 * a + 1] = Pstart[2 * a + 1] + vy * (j + 1) * Ts;
+      Prd[(size_t)j * 8 + 2 * a] = vx; Prd[(size_t)j * 8 + 2 * a + 1] = vy;
+    }
+  }
+  try {
+    Context ctx(0, 4, K);
+    std::vector<std::unique_ptr<MPC_dist_gpu>> agents;
+    std::vector<MPC_dist_gpu*> ptrs;
+    double q[4][18] = {{0}}, dq[4][18] = {{0}};
+    for (int a = 0; a < 4; a++) {
+      agents.emplace_back(new MPC_dist_gpu(&ctx));
+      MPC_dist_gpu& m = *agents.back();
+      m.setAgentID(a); m.setPstart(Pstart); m.setPobs(Pobs, K); m.setPobs_real(Pobs, K);
+      m.setReferenceTrajectory(Pr.data(), Prd.data(), ncols);
+      m.use_snopt = nlp;
+      q[a][0] = Pstart[2 * a]; q[a][1] = Pstart[2 * a + 1];
+      ptrs.push_back(&m);
+    }
+    MPC_dist_gpu_team team(&ctx, ptrs);
+    for (int c = 0; c < cycles; c++) {
+      for (int a = 0; a < 4; a++) {
+        int ind[4] = {1, 1, 1, 1};
+        if (c >= 2) { bool even = (c % 2) == 0; ind[0] = even; ind[1] = !even; ind[2] = !even; ind[3] = even; }  // trot after stand-up
+        double toe[12];
+        const double fx[4] = {0.2188, 0.2188, -0.1472, -0.1472}, fy[4] = {-0.1320, 0.1320, -0.1320, 0.1320};
+        for (int i = 0; i < 4; i++) { toe[3 * i] = q[a][0] + fx[i]; toe[3 * i + 1] = q[a][1] + fy[i]; toe[3 * i + 2] = 0.0; }
+        double other[4];
+        agents[a ^ 1]->get_lastState(other);  // pairwise neighbour exchange, shared_structs.hpp:63,94
+        agents[a]->updateState(q[a], dq[a], ind, toe, other);
+      }
+      team.run_NMPC();
+      for (int a = 0; a < 4; a++) {
+        double X[16], al[20];
+        agents[a]->get_MPCsol(X); agents[a]->get_alphaCOM(al);
+        printf("%d %d %d %.3e %.17g", c, a, agents[a]->status(), agents[a]->kkt(), agents[a]->slack());
+        for (int i = 0; i < 16; i++) printf(" %.17g", X[i]);
+        for (int i = 0; i < 20; i++) printf(" %.17g", al[i]);
+        printf("\n");
+        q[a][0] = X[12]; dq[a][0] = X[13]; q[a][1] = X[14]; dq[a][1] = X[15];  // end of the planned domain
+      }
+    }
+  } catch (const Error& e) {
+    fprintf(stderr, "cbfnmpc error %d: %s\n", e.code, e.what());
+    return e.code == CBFNMPC_ERR_NODEVICE ? 3 : 1;
+  }
+  return 0;
+}
