@@ -33,42 +33,49 @@ def algorithmic_bytes(n_obs):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (same counters as the nvidia-smi line of
+    B200_PROFILING.md, but at 2 ms period: the timed region of the default run is only tens of milliseconds long)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.t, self.err = index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._run, daemon=True); self.t.start()
+        except Exception as e:  # noqa
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try: self.proc.wait(timeout=2)
-        except Exception: self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for r in self.rows:
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
-                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                    if r[col].lower().startswith("active"): reasons.add(name)
-            except Exception:
-                pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception as e:  # noqa
+                self.err = repr(e); break
+            time.sleep(0.002)
+
+    def mark(self):
+        """index of the next sample: call at the start / end of the timed region"""
+        return len(self.rows)
+
+    def stop(self, lo=0, hi=None):
+        self.stop_flag = True
+        if self.t: self.t.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: %s" % self.err], "samples": 0}
+        nv = self.nv
+        rows = self.rows[lo:hi] or self.rows
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        reasons = sorted({n for _, r in rows for n, bit in names if r & bit})
+        return {"sm_mhz": statistics.median(c for c, _ in rows), "sm_max_mhz": float(self.smax), "reasons": reasons, "samples": len(rows)}
 
 
 def cpu_baseline(insts, seconds_target=12.0, nthreads=None):
@@ -147,7 +154,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     # ---- this rank's shard of the global instance set (contiguous range)
-    insts = S.cfg3_instances(B * world, seed=20251018 + 3000)[rank * B:(rank + 1) * B]
+    from srb_cbf_nmpc_b200 import sharding as SH
+    lo, hi = SH.shard_range(B * world, rank, world)
+    insts = S.cfg3_instances(B * world, seed=20251018 + 3000)[lo:hi]
     d = capi.soa_from_instances(insts)
     K_obs = int(d["n_obs"])
     solver = pkg.BatchSolver(device=local, max_batch=B, max_obs=K_obs)
@@ -172,9 +181,11 @@ def main():
             step()
     barrier()
     sampler = ClockSampler(local); sampler.start()
+    time.sleep(0.02)
     l0 = solver.launch_count()
     evs = []
     barrier()
+    mark0 = sampler.mark()
     t_wall0 = time.perf_counter()
     with torch.cuda.stream(stream):
         for _ in range(args.steps):
@@ -213,14 +224,10 @@ def main():
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     conv_e2e = int((oh["status"][0] == 0).sum())
-    clocks = sampler.stop()
+    clocks = sampler.stop(mark0, None)
     # ---- reduce over ranks: max time, summed work
-    red = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
-    work = torch.tensor([conv, conv_e2e, flops, launches, B], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX); dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    total_ms_max, e2e_s_max = float(red[0]), float(red[1])
-    conv_all, conv_e2e_all, flops_all, launches_all, inst_all = (float(x) for x in work)
+    (total_ms_max, e2e_s_max), (conv_all, conv_e2e_all, flops_all, launches_all, inst_all) = SH.reduce_over_ranks(
+        dist, [total_ms, e2e_s], [conv, conv_e2e, flops, launches, B], dev)
     fp64_peak = solver.fp64_peak_tflops()
     bi, bo = algorithmic_bytes(K_obs)
     if rank == 0:
@@ -230,7 +237,12 @@ def main():
         try: peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception: pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        kern_ms = statistics.mean(step_ms)  # one launch per step on this rank
+        kern_ms = statistics.mean(step_ms)  # one solve launch per step on this rank
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic, traffic_src = tj["traffic_bytes"], tj["source"]
+        except Exception: pass
         ach_gbs = (bi + bo) * B / (kern_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -242,7 +254,7 @@ def main():
                 "gpu_launches": int(launches_all),
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                             "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                              "kernel": "cbfnmpc_solve_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_solve": bi + bo,
                              "note": "latency/FP64-issue bound: 1.3 KB of HBM traffic per ~0.2 MFLOP solve; see roofline_fp64"},
                 "roofline_fp64": {"bound": "fp64", "achieved": flops_all / world / (kern_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",

@@ -93,6 +93,10 @@ if os.path.exists(rep):
     summary["inst_total"] = tot; summary["inst_static"] = len(sr) - 2; summary["fp64_share"] = fp / tot; summary["local_share"] = (c["LDL"] + c["STL"]) / tot
 
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+if "traffic_bytes" in summary:
+    json.dump({"traffic_bytes": summary["traffic_bytes"], "read_bytes": summary["traffic_read_bytes"], "write_bytes": summary["traffic_write_bytes"],
+               "source": "profiles/%s_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one cbfnmpc_solve_kernel launch (4096 cfg-3 instances, ncu --set full)" % tag},
+              open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 open(os.path.join(ROOT, "profiles", "%s_ncu_summary.md" % tag), "w").write("\n".join(out_md) + "\n")
 json.dump(summary, open(os.path.join(ROOT, "profiles", "%s_ncu_summary.json" % tag), "w"), indent=1)
 print("\n".join(out_md))

@@ -1,0 +1,45 @@
+"""Multi-GPU plumbing of the batch path: instances are independent, so ranks own contiguous ranges of the
+global instance set and exchange nothing in the data path; torch.distributed is used only for the barrier and for the
+max-over-ranks / sum-over-ranks reduction of the timing and work counters."""
+import torch
+
+
+def shard_range(n_total, rank, world):
+    """Contiguous range [lo, hi) of rank `rank`; remainders go to the first ranks.  Team-major: with `team` > 1 use shard_teams."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_teams(n_teams, team, rank, world):
+    """Same, in whole teams of `team` agents (a team's agents stay on one GPU)."""
+    lo, hi = shard_range(n_teams, rank, world)
+    return lo * team, hi * team
+
+
+def reduce_over_ranks(dist, times, work, device):
+    """MAX over ranks of `times` (list of floats), SUM over ranks of `work` (list of floats)."""
+    t = torch.tensor(times, dtype=torch.float64, device=device)
+    w = torch.tensor(work, dtype=torch.float64, device=device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t], [float(x) for x in w]
+
+
+def gather_results(dist, local, device):
+    """Optional final gather of per-rank result arrays (dict of [n][B_local] numpy arrays) onto every rank, rank-major."""
+    import numpy as np
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    out = {}
+    for k, v in local.items():
+        t = torch.from_numpy(np.ascontiguousarray(v.T)).to(device)          # [B_local][n]: batch-major so that ranks concatenate
+        sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(dist.get_world_size())]
+        dist.all_gather(sizes, torch.tensor([t.shape[0]], dtype=torch.int64, device=device))
+        bmax = int(max(int(s) for s in sizes))
+        pad = torch.zeros((bmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=device); pad[:t.shape[0]] = t
+        parts = [torch.zeros_like(pad) for _ in sizes]
+        dist.all_gather(parts, pad)
+        out[k] = torch.cat([p[:int(s)] for p, s in zip(parts, sizes)]).cpu().numpy().T
+    return out
