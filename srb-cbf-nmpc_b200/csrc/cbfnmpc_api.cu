@@ -6,6 +6,10 @@
 #include <vector>
 #include "cbfnmpc_host.h"
 #include "cbfnmpc_instance.h"
+#ifndef LANE_NT
+#define LANE_NT 32  // one warp (8 instances) per CTA; 4 CTAs of 48.5 KB shared memory fit an SM
+#endif
+#include "cbfnmpc_lane.h"
 
 // One CTA = CBF_WARPS warps = CBF_WARPS instances kept in lockstep; CBF_WARPS * CBF_MIN_BLOCKS warps resident per SM.
 // 28 x 1 fills an SM's 227 KB of shared memory (28 x 7.6 KB workspaces) at 72 registers per thread (tuned on B200).
@@ -25,6 +29,64 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, CBF_MIN_BLOCKS) cbfnmpc_so
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.x * WARPS_PER_CTA + warp;
   solve_warp(wsall[warp], P, io, b);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Lane-per-stage path (cbfnmpc_lane.h): one instance = 4 adjacent lanes, 8 instances per warp, one warp per CTA.
+// A pre-pass sorts the instances by stance class (4 feet / diagonal pair) so that every warp runs one template
+// instantiation; the order inside a class is the batch order (deterministic).
+// ---------------------------------------------------------------------------------------------------------
+// perm[0 .. n4) = instances with 4 stance feet, perm[B .. B + n2) = instances with a diagonal pair; counts = {n4, n2}.
+// One CTA; bad contact patterns are answered here (status 4).
+__global__ void __launch_bounds__(1024, 1) cbfnmpc_classify_kernel(const __grid_constant__ BatchIO io, int* __restrict__ perm,
+                                                                   int* __restrict__ counts) {
+  __shared__ int wcnt[2][32];
+  __shared__ int base[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 2) base[threadIdx.x] = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < io.B; b0 += 1024) {
+    const int b = b0 + threadIdx.x;
+    const int cls = (b < io.B) ? lane_classify(io, b) : 0;
+    if (b < io.B && cls < 0) lane_store_bad(io, b);
+    const unsigned m4 = __ballot_sync(0xffffffffu, cls == 4), m2 = __ballot_sync(0xffffffffu, cls == 2);
+    if (lane == 0) { wcnt[0][warp] = __popc(m4); wcnt[1][warp] = __popc(m2); }
+    __syncthreads();
+    if (warp < 2) {  // exclusive scan of the 32 per-warp counts of class `warp`
+      const int v = wcnt[warp][lane];
+      int s = v;
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+      wcnt[warp][lane] = base[warp] + s - v;
+      __syncwarp();
+      if (lane == 31) base[warp] += s;
+    }
+    __syncthreads();
+    const unsigned below = (1u << lane) - 1u;
+    if (cls == 4) perm[wcnt[0][warp] + __popc(m4 & below)] = b;
+    if (cls == 2) perm[io.B + wcnt[1][warp] + __popc(m2 & below)] = b;
+    __syncthreads();
+  }
+  if (threadIdx.x < 2) counts[threadIdx.x] = base[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(LANE_NT, 1) cbfnmpc_lane_kernel(const __grid_constant__ KParams P, const __grid_constant__ BatchIO io,
+                                                                  const int* __restrict__ perm, const int* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Priv pr; pr.base = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
+  const int gw = blockIdx.x * (LANE_NT / 32) + (threadIdx.x >> 5);  // warp index in the grid
+  const int grp = (threadIdx.x & 31) >> 2;
+  const int n4 = counts[0], n2 = counts[1];
+  const int w4 = (n4 + 7) >> 3;
+  if (gw < w4) {
+    const int slot = gw * 8 + grp;
+    const bool valid = slot < n4;
+    lane_run_group<4>(P, io, valid ? perm[slot] : 0, valid, pr);
+  } else {
+    const int slot = (gw - w4) * 8 + grp;
+    if ((gw - w4) * 8 >= n2) return;
+    const bool valid = slot < n2;
+    lane_run_group<2>(P, io, valid ? perm[io.B + slot] : 0, valid, pr);
+  }
 }
 
 // FP64 pipe microbenchmark: 8 independent DFMA chains per thread.
@@ -62,6 +124,9 @@ struct cbfnmpc_ctx {
   int* d_outi;    // 4 * max_batch
   unsigned long long* d_active;  // 2 * max_batch
   double* d_xstart;              // 41 (dense entry point)
+  int* d_perm;                   // 2 * max_batch + 2: class lists + counts (grown on demand for device-pointer batches)
+  int perm_cap;
+  bool use_warp_kernel;          // CBFNMPC_KERNEL=warp: the v3 warp-per-instance kernel (A/B measurement only)
 };
 
 extern "C" {
@@ -91,7 +156,12 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
   CK(cudaMalloc(&c->d_outi, sizeof(int) * 4 * (size_t)max_batch));
   CK(cudaMalloc(&c->d_active, sizeof(unsigned long long) * 2 * (size_t)max_batch));
   CK(cudaMalloc(&c->d_xstart, sizeof(double) * 41));
+  CK(cudaMalloc(&c->d_perm, sizeof(int) * (2 * (size_t)max_batch + 2)));
+  c->perm_cap = max_batch;
+  const char* kn = getenv("CBFNMPC_KERNEL");
+  c->use_warp_kernel = kn && std::string(kn) == "warp";
   CK(cudaFuncSetAttribute(cbfnmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * sizeof(WSB))));
+  CK(cudaFuncSetAttribute(cbfnmpc_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LANE_NPRIV * LANE_NT * sizeof(double))));
   *out = c;
   return CBFNMPC_OK;
 }
@@ -100,7 +170,7 @@ void cbfnmpc_destroy(cbfnmpc_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_in); cudaFree(c->d_contact); cudaFree(c->d_out); cudaFree(c->d_outi); cudaFree(c->d_active); cudaFree(c->d_xstart);
+  cudaFree(c->d_in); cudaFree(c->d_contact); cudaFree(c->d_out); cudaFree(c->d_outi); cudaFree(c->d_active); cudaFree(c->d_xstart); cudaFree(c->d_perm);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -133,13 +203,32 @@ static int launch(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const c
   io.abuf_next = out->alpha_buf_next; io.kkt = out->kkt; io.status = out->status; io.qp_iters = out->qp_iters;
   io.nlp_iters = out->nlp_iters; io.n_fact = out->n_fact; io.active = (unsigned long long*)out->active;
   io.B = B; io.mode = mode;
-  const int grid = (B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  if (c->use_warp_kernel) {
+    const int grid = (B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    CK(cudaEventRecord(c->ev0, st));
+    cbfnmpc_solve_kernel<<<grid, 32 * WARPS_PER_CTA, WARPS_PER_CTA * sizeof(WSB), st>>>(c->kp, io);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, st));
+    c->timed = true;
+    c->launches++;
+    return CBFNMPC_OK;
+  }
+  if (B > c->perm_cap) {  // device-pointer batches larger than max_batch: grow the class lists
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(c->d_perm));
+    CK(cudaMalloc(&c->d_perm, sizeof(int) * (2 * (size_t)B + 2)));
+    c->perm_cap = B;
+  }
+  int* counts = c->d_perm + 2 * (size_t)c->perm_cap;
+  const int warps = (B + 7) / 8 + 1, wpc = LANE_NT / 32;
   CK(cudaEventRecord(c->ev0, st));
-  cbfnmpc_solve_kernel<<<grid, 32 * WARPS_PER_CTA, WARPS_PER_CTA * sizeof(WSB), st>>>(c->kp, io);
+  cbfnmpc_classify_kernel<<<1, 1024, 0, st>>>(io, c->d_perm, counts);
+  CK(cudaGetLastError());
+  cbfnmpc_lane_kernel<<<(warps + wpc - 1) / wpc, LANE_NT, LANE_NPRIV * LANE_NT * sizeof(double), st>>>(c->kp, io, c->d_perm, counts);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev1, st));
   c->timed = true;
-  c->launches++;
+  c->launches += 2;
   return CBFNMPC_OK;
 }
 
@@ -209,6 +298,28 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
   CK(cudaStreamSynchronize(st));
   return CBFNMPC_OK;
 }
+
+#ifdef CBF_DBGBUF
+int cbfnmpc_debug_read(double* out, int reset) {  // debug builds only
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_dbg_n, sizeof(int));
+  cudaMemcpyFromSymbol(out, g_dbg, sizeof(double) * 8192);
+  if (reset) { int z = 0; cudaMemcpyToSymbol(g_dbg_n, &z, sizeof(int)); }
+  return n;
+}
+#endif
+
+#ifdef CBF_DBGBUF
+int cbfnmpc_debug_read4(double* out, int reset) {  // debug builds only
+  int n[4] = {0, 0, 0, 0};
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(n, g_dbg4_n, sizeof(n));
+  cudaMemcpyFromSymbol(out, g_dbg4, sizeof(double) * 4 * 8192);
+  if (reset) { int z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_dbg4_n, z, sizeof(z)); }
+  return n[0];
+}
+#endif
 
 long long cbfnmpc_launch_count(const cbfnmpc_ctx* c) { return c ? c->launches : 0; }
 

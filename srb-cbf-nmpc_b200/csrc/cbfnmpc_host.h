@@ -4,7 +4,7 @@
 #include <math.h>
 #include <string.h>
 #include "../../include/cbfnmpc.h"
-#include "cbfnmpc_solver.h"
+#include "cbfnmpc_types.h"
 
 static inline void host_default_gains(cbfnmpc_gains* g) {
   g->Qw = 3e2; g->Rw = 1e-1; g->Pw = 2e3; g->slack_w = 0.3e4;            // src/MPC_dist.cpp:172-175

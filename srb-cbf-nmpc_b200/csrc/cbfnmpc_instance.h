@@ -3,16 +3,6 @@
 #pragma once
 #include "cbfnmpc_solver.h"
 
-struct BatchIO {
-  // inputs, SoA [field][B]
-  const double *x0, *xdes, *feet; const int* contact; const double* obs; int n_obs; const double* abuf;
-  const double* xstart;  // optional [41][B]: skip the QP stage and start the NLP here (dense nlpTuple entry point)
-  // outputs, SoA
-  double *X, *U, *lam, *slack, *xqp, *alpha, *abuf_next, *kkt;
-  int *status, *qp_iters, *nlp_iters, *n_fact;
-  unsigned long long* active;
-  int B, mode;
-};
 
 template <int C>
 DEV void active_bits(const LaneSlots& ls, int q, int slot, unsigned w[4]) {

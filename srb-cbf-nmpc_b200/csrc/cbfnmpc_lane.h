@@ -1,0 +1,1408 @@
+// cbfnmpc_lane.h -- lane-per-stage CBF-NMPC solver: one instance = 4 adjacent lanes (lane j owns horizon stage j:
+// x_{j+1}, u_j, lambda_j, their multipliers and their constraint rows), 8 instances per warp, FP64.
+//
+// Replaces, for a whole batch at once, what MPC_dist::run_NMPC() does per agent per gait domain
+// (/root/reference/src/MPC_dist.cpp:81-454):
+//   stage 1 (QP)  : iSWIFT's Mehrotra predictor-corrector (optimization/iSWIFT/src/Prime.c:127-230) on the LIP
+//                   tracking QP of MPC_dist.cpp:164-321;
+//   stage 2 (NLP) : the same QP plus the 4 squared-distance rows and 8 velocity boxes of
+//                   include/dec_vars_constr_cost.h:245-324, solved by the primal-dual filter interior-point method
+//                   "IPM-F" of DESIGN.md (feasible w.r.t. inequalities, exact Hessian, inertia correction);
+//   epilogue      : Bezier fit of MPC_dist.cpp:784-855.
+// KKT systems: per-stage elimination of (u_j, lambda_j) through u = F lambda, 1'lambda = 1; Riccati/Cholesky
+// recursion over the horizon as a chain lane 3 -> 2 -> 1 -> 0 (each lane keeps its stage's factors in registers);
+// 5x5 Schur complement for the global slack variable and the (capped) distance rows.
+//
+// Everything a lane touches is addressed with compile-time indices: the iterate, the Hessian blocks and the Riccati
+// factors live in registers; per-row state (slacks, multipliers, reciprocals) lives in thread-private columns of shared
+// memory (element f of thread t at priv[f * LANE_NT + t]: conflict-free, immediate offsets).
+#pragma once
+#include "cbfnmpc_types.h"
+#include "lane_prims.h"
+
+#ifndef LANE_NT
+#define LANE_NT 128  // threads per CTA = stride of the thread-private shared-memory columns
+#endif
+#define LUNR _Pragma("unroll")
+
+// ---------------------------------------------------------------------------------------------------------------
+// KKT vector restricted to one lane: primal part (xs = x_{j+1}, us = u_j, lm = lambda_j, dl = slack variable,
+// replicated in the 4 lanes) and dual part (pi: dynamics rows of stage j, nu: u = F lambda rows, eta: 1'lambda = 1).
+// ---------------------------------------------------------------------------------------------------------------
+struct KV { double xs[4], us[2], lm[4], dl, pi[4], nu[2], eta; };
+
+struct LaneConst {       // per-instance constants of this lane
+  double xdes[4];        // desired x_{j+1}                                   (MPC_dist.cpp:702-782)
+  double xin[4];         // lane 0: measured state x_0 (MPC_dist.cpp:226-229); other lanes: unused
+  double F[8];           // stance feet, F[4 a + i] = axis a of foot i         (MPC_dist.cpp:1238-1252)
+  double D[6];           // D = F E, D[c * NW + a] = F[c][a] - F[c][C-1]
+  double ox, oy;         // closest obstacle                                   (MPC_dist.cpp:371-396)
+  double qw;             // state weight of this stage (Pw at the last stage)
+};
+
+struct LaneHess {        // stage blocks of H = W + dw I + J' Sigma J  (dw is added inside the factorisation)
+  double hx[4], hxy;     // x_{j+1}: diagonal, (p_x, p_y) coupling
+  double hu[2], hxu[2];  // u_j diagonal; coupling x_j position <-> u_j (friction rows)
+  double hl[4];          // lambda_j diagonal
+  double bd[2], hd;      // coupling p_{j+1} <-> slack variable; slack-variable diagonal (group value)
+  double gv[2];          // gradient of the distance row wrt p_{j+1}: 2 (p - o)
+  double sc, srinv;      // capped Sigma of the distance row, 1 / (Sigma - sc) when capped
+  int capped;
+};
+
+struct LaneFact {        // Riccati factors of stage j
+  double Pn[10];         // P_{j+1}, packed lower (i >= k: i (i + 1) / 2 + k)
+  double K[12], St[12];  // K_j = R~^-1 S~_j, S~_j: [a * 4 + k]
+  double Lc[6];          // chol(R~_j): (1/l00, l10, 1/l11, l20, l21, 1/l22)
+};
+
+struct LaneBorder {      // border part of the factorisation (NLP): group values replicated in the 4 lanes
+  double L[10], Tic[4], cb[4], den;
+  int cap[4];
+};
+
+LDEV int sy(int i, int k) { return i >= k ? (i * (i + 1)) / 2 + k : (k * (k + 1)) / 2 + i; }
+LDEV double l_sel4(const double* v, int j) { return j == 0 ? v[0] : (j == 1 ? v[1] : (j == 2 ? v[2] : v[3])); }
+
+// thread-private shared-memory column
+struct Priv {
+  double* base;
+  LMEM double& operator()(int f) const { return base[f * LANE_NT]; }
+};
+
+template <int C>
+struct LaneDims {
+  static constexpr int NW = C - 1, NR = NW * (NW + 1) / 2, MQP = 60 + 8 * C;
+  // two-sided slots of one lane
+  static constexpr int SX = 0, SU = 4, SL = 6, SF = 6 + C, SV = 8 + C, SD = 10 + C, NS = 11 + C, NSQP = 8 + C;
+  // thread-private shared-memory fields: 10 per slot, then the border vectors and the filter
+  static constexpr int F_SLO = 0, F_SHI = NS, F_ZLO = 2 * NS, F_ZHI = 3 * NS, F_A = 4 * NS, F_B = 5 * NS, F_C = 6 * NS, F_D = 7 * NS,
+                       F_E = 8 * NS, F_G = 9 * NS;
+  static constexpr int F_PVB = 10 * NS;        // 4 border columns x 4
+  static constexpr int F_KVB = F_PVB + 16;     // 4 border columns x NW (3)
+  static constexpr int F_FILT = F_KVB + 12;    // 8 filter entries x 2
+  static constexpr int NPRIV = F_FILT + 16;
+};
+constexpr int LANE_NPRIV = LaneDims<4>::NPRIV;
+
+// ---------------------------------------------------------------------------------------------------------------
+// small dense pieces
+// ---------------------------------------------------------------------------------------------------------------
+// FLOOR (QP stage): a pivot that rounding has pushed below CHOL_FLOOR * diagonal is replaced by that value instead of
+// failing.  This happens when every lambda of a stage is strictly inside (0, 1): the reduced Hessian D'N D + Sigma_lambda
+// then has one direction (F n = 0, 1'n = 0) whose curvature is only Sigma_lambda ~ mu / s^2, far below the rounding error
+// of D'N D.  The direction does not move X, U or the objective; flooring only damps the motion of lambda inside the
+// optimal face (iSWIFT's LDL' on the unreduced KKT matrix does not see this cancellation, Auxilary.c:332-420).
+#define CHOL_FLOOR 1e-10
+template <int NW, bool FLOOR>
+LDEV bool l_chol(const double* R, double* L) {  // R packed lower (00,10,11,20,21,22)
+  bool ok = true;
+  const double d0 = R[0];
+  ok = ok && (d0 > 0.0) && (d0 < 1e300);
+  const double i0 = l_rsq(d0);
+  L[0] = i0;
+  if (NW == 3) {
+    const double l10 = R[1] * i0, l20 = R[3] * i0;
+    double d1 = R[2] - l10 * l10;
+    if (FLOOR) d1 = fmax(d1, CHOL_FLOOR * R[2]);
+    ok = ok && (d1 > 0.0) && (d1 < 1e300);
+    const double i1 = l_rsq(d1);
+    const double l21 = (R[4] - l20 * l10) * i1;
+    double d2 = R[5] - l20 * l20 - l21 * l21;
+    if (FLOOR) d2 = fmax(d2, CHOL_FLOOR * R[5]);
+    ok = ok && (d2 > 0.0) && (d2 < 1e300);
+    const double i2 = l_rsq(d2);
+    L[1] = l10; L[2] = i1; L[3] = l20; L[4] = l21; L[5] = i2;
+  }
+  return ok;
+}
+template <int NW>
+LDEV void l_chol_fwd(const double* L, double* b) {  // b <- L^-1 b
+  if (NW == 1) { b[0] = b[0] * L[0]; return; }
+  const double y0 = b[0] * L[0];
+  const double y1 = (b[1] - L[1] * y0) * L[2];
+  const double y2 = (b[2] - L[3] * y0 - L[4] * y1) * L[5];
+  b[0] = y0; b[1] = y1; b[2] = y2;
+}
+template <int NW>
+LDEV void l_chol_bwd(const double* L, double* b) {  // b <- L^-T b
+  if (NW == 1) { b[0] = b[0] * L[0]; return; }
+  const double k2 = b[2] * L[5];
+  const double k1 = (b[1] - L[4] * k2) * L[2];
+  const double k0 = (b[0] - L[1] * k1 - L[3] * k2) * L[0];
+  b[0] = k0; b[1] = k1; b[2] = k2;
+}
+template <int NW>
+LDEV void l_chol_solve(const double* L, double* b) { l_chol_fwd<NW>(L, b); l_chol_bwd<NW>(L, b); }
+
+// 4x4 Cholesky (packed lower, inverse diagonals stored) and solve
+LDEV bool l_chol4(const double* T, double* L) {
+  bool ok = true;
+  const double d0 = T[0]; ok = ok && d0 > 0.0 && d0 < 1e300; const double i0 = l_rsq(d0);
+  const double l10 = T[1] * i0, l20 = T[3] * i0, l30 = T[6] * i0;
+  const double d1 = T[2] - l10 * l10; ok = ok && d1 > 0.0; const double i1 = l_rsq(d1);
+  const double l21 = (T[4] - l20 * l10) * i1, l31 = (T[7] - l30 * l10) * i1;
+  const double d2 = T[5] - l20 * l20 - l21 * l21; ok = ok && d2 > 0.0; const double i2 = l_rsq(d2);
+  const double l32 = (T[8] - l30 * l20 - l31 * l21) * i2;
+  const double d3 = T[9] - l30 * l30 - l31 * l31 - l32 * l32; ok = ok && d3 > 0.0; const double i3 = l_rsq(d3);
+  L[0] = i0; L[1] = l10; L[2] = i1; L[3] = l20; L[4] = l21; L[5] = i2; L[6] = l30; L[7] = l31; L[8] = l32; L[9] = i3;
+  return ok;
+}
+LDEV void l_chol4_solve(const double* L, const double* b, double* k) {
+  const double y0 = b[0] * L[0], y1 = (b[1] - L[1] * y0) * L[2], y2 = (b[2] - L[3] * y0 - L[4] * y1) * L[5],
+               y3 = (b[3] - L[6] * y0 - L[7] * y1 - L[8] * y2) * L[9];
+  k[3] = y3 * L[9]; k[2] = (y2 - L[8] * k[3]) * L[5]; k[1] = (y1 - L[4] * k[2] - L[7] * k[3]) * L[2];
+  k[0] = (y0 - L[1] * k[1] - L[3] * k[2] - L[6] * k[3]) * L[0];
+}
+
+// LIP maps (per axis b: position index 2b, velocity index 2b+1; MPC_dist.cpp:117-127)
+LDEV void l_Ax(const KParams& P, const double* x, double* y) {        // y = A x
+  LUNR for (int b = 0; b < 2; b++) {
+    y[2 * b] = P.a11 * x[2 * b] + P.a12 * x[2 * b + 1];
+    y[2 * b + 1] = P.a21 * x[2 * b] + P.a22 * x[2 * b + 1];
+  }
+}
+LDEV void l_ATx(const KParams& P, const double* x, double* y) {       // y = A' x
+  LUNR for (int b = 0; b < 2; b++) {
+    y[2 * b] = P.a11 * x[2 * b] + P.a21 * x[2 * b + 1];
+    y[2 * b + 1] = P.a12 * x[2 * b] + P.a22 * x[2 * b + 1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Residuals that do not involve the inequality rows
+// ---------------------------------------------------------------------------------------------------------------
+// (Aeq x - beq) of this lane's rows; xp = x_j (previous lane's xs; lane 0: measured state, or 0 when homogeneous)
+template <int C>
+LDEV void l_eq_residual(const KParams& P, const LaneConst& c, const KV& v, const double* xp, bool homogeneous, double* rpi, double* rnu, double& reta) {
+  double ax[4];
+  l_Ax(P, xp, ax);
+  LUNR for (int b = 0; b < 2; b++) {
+    rpi[2 * b] = ax[2 * b] - v.xs[2 * b] + P.bp * v.us[b];
+    rpi[2 * b + 1] = ax[2 * b + 1] - v.xs[2 * b + 1] + P.bv * v.us[b];
+  }
+  LUNR for (int a = 0; a < 2; a++) {
+    double s = v.us[a];
+    LUNR for (int i = 0; i < C; i++) s -= c.F[4 * a + i] * v.lm[i];
+    rnu[a] = s;
+  }
+  double s = homogeneous ? 0.0 : -1.0;
+  LUNR for (int i = 0; i < C; i++) s += v.lm[i];
+  reta = s;
+}
+
+// grad f(x) + A' y restricted to this lane's variables; pin = pi of lane j+1 (0 at lane 3)
+template <int C>
+LDEV void l_grad_Aty(const KParams& P, const LaneConst& c, const KV& x, const KV& y, const double* pin, bool with_grad, KV& g) {
+  double at[4];
+  l_ATx(P, pin, at);
+  LUNR for (int i = 0; i < 4; i++) {
+    double t = at[i] - y.pi[i];
+    if (with_grad) t += c.qw * (x.xs[i] - c.xdes[i]);
+    g.xs[i] = t;
+  }
+  LUNR for (int a = 0; a < 2; a++) {
+    double t = P.bp * y.pi[2 * a] + P.bv * y.pi[2 * a + 1] + y.nu[a];
+    if (with_grad) t += P.Rw * x.us[a];
+    g.us[a] = t;
+  }
+  LUNR for (int i = 0; i < C; i++) g.lm[i] = -(c.F[i] * y.nu[0] + c.F[4 + i] * y.nu[1]) + y.eta;
+  g.dl = with_grad ? P.slw * x.dl : 0.0;
+}
+
+// shuffle helpers: 4-vector from the previous / next lane (zero at the chain ends unless `first` supplies lane 0's value)
+LDEV void l_from_prev(const Grp& g, const double* v, double* out) {
+  LUNR for (int i = 0; i < 4; i++) { const double t = g_up(g, v[i]); out[i] = (g.j > 0) ? t : 0.0; }
+}
+LDEV void l_from_next(const Grp& g, const double* v, double* out) {
+  LUNR for (int i = 0; i < 4; i++) { const double t = g_down(g, v[i]); out[i] = (g.j < 3) ? t : 0.0; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Riccati / Cholesky factorisation as a chain over the 4 lanes.  Every lane evaluates its stage at every step; lane j
+// holds valid data from step 4 - j on, so after 4 steps all stages are factorised (no divergent code, no extra issue
+// slots: the idle lanes of a step would execute the same instructions masked off).
+// Returns false when a pivot block of this group is not positive definite.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C, bool FLOOR>
+LDEV bool l_riccati(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, double dw, LaneFact& f) {
+  constexpr int NW = LaneDims<C>::NW, NR = LaneDims<C>::NR;
+  // cost on x_j (previous lane's hx, hxy), needed by stage j
+  double hxp[4], hxyp;
+  LUNR for (int i = 0; i < 4; i++) hxp[i] = g_up(g, H.hx[i]);
+  hxyp = g_up(g, H.hxy);
+  // terminal cost-to-go at this lane if it were the last stage; P_{j+1} of lanes < 3 arrives through the chain
+  double Pown[10];
+  LUNR for (int i = 0; i < 4; i++) LUNR for (int k = 0; k <= i; k++) Pown[sy(i, k)] = (i == k) ? H.hx[i] + dw : ((i == 2 && k == 0) ? H.hxy : 0.0);
+  double Pout[10];
+  LUNR for (int t = 0; t < 10; t++) { Pout[t] = 0.0; f.Pn[t] = Pown[t]; }
+  bool ok = true;
+#pragma unroll 1
+  for (int step = 0; step < 4; step++) {
+    // P_{j+1}: lane 3 uses its own terminal block, the others what lane j+1 produced in the previous step
+    if (step > 0) {
+      LUNR for (int t = 0; t < 10; t++) { const double v = g_down(g, Pout[t]); if (g.j < 3) f.Pn[t] = v; }
+    }
+    const double* Pn = f.Pn;
+    // PA = Pn A   (A block diagonal per axis)
+    double PA[16];
+    LUNR for (int i = 0; i < 4; i++) LUNR for (int b = 0; b < 2; b++) {
+      const double p0 = Pn[sy(i, 2 * b)], p1 = Pn[sy(i, 2 * b + 1)];
+      PA[4 * i + 2 * b] = p0 * P.a11 + p1 * P.a21;
+      PA[4 * i + 2 * b + 1] = p0 * P.a12 + p1 * P.a22;
+    }
+    // G = Bd' Pn (2 x 4), M2 = Bd' Pn Bd (2 x 2 sym), GA = Bd' PA (2 x 4)
+    double G[8], GA[8];
+    LUNR for (int cc = 0; cc < 2; cc++) LUNR for (int m = 0; m < 4; m++) {
+      G[4 * cc + m] = P.bp * Pn[sy(2 * cc, m)] + P.bv * Pn[sy(2 * cc + 1, m)];
+      GA[4 * cc + m] = P.bp * PA[4 * (2 * cc) + m] + P.bv * PA[4 * (2 * cc + 1) + m];
+    }
+    double N2[3];  // (00, 10, 11) of M2 + diag(hu + dw)
+    N2[0] = P.bp * G[0] + P.bv * G[1] + (H.hu[0] + dw);
+    N2[1] = P.bp * G[4] + P.bv * G[5];
+    N2[2] = P.bp * G[6] + P.bv * G[7] + (H.hu[1] + dw);
+    // R~ = D' N2 D + (hl_last + dw) 11' + diag(hl + dw)
+    double Rt[6];
+    {
+      double T1[6];  // T1[cc][b] = sum_c' N2[cc][c'] D[c'][b]
+      LUNR for (int b = 0; b < NW; b++) {
+        T1[b] = N2[0] * c.D[b] + N2[1] * c.D[NW + b];
+        T1[NW + b] = N2[1] * c.D[b] + N2[2] * c.D[NW + b];
+      }
+      const double hlast = H.hl[C - 1] + dw;
+      LUNR for (int a = 0; a < NW; a++) LUNR for (int b = 0; b <= a; b++) {
+        double s = c.D[a] * T1[b] + c.D[NW + a] * T1[NW + b] + hlast;
+        if (a == b) s += H.hl[a] + dw;
+        Rt[(a * (a + 1)) / 2 + b] = s;
+      }
+    }
+    const bool okc = l_chol<NW, FLOOR>(Rt, f.Lc);
+    if (!okc && step == 3) LANE_DBGA("   riccati: stage-%d block not PD: Rt %.6e %.6e %.6e %.6e %.6e %.6e\n", g.j, Rt[0], Rt[1], Rt[2], Rt[3], Rt[4], Rt[5]);
+    if (!okc && step == 3 && g.j == 3) LANE_DBGA("   N2 %.6e %.6e %.6e hl %.6e %.6e %.6e %.6e D %.4f %.4f %.4f %.4f %.4f %.4f dw %.3e Pn %.4e %.4e %.4e %.4e\n", N2[0], N2[1], N2[2], H.hl[0], H.hl[1], H.hl[2], H.hl[3], c.D[0], c.D[1], c.D[2], c.D[3], c.D[4], c.D[5], dw, Pn[0], Pn[2], Pn[5], Pn[9]);
+    // S~ = D' (GA + hxu on the position columns)
+    GA[0] += H.hxu[0]; GA[4 + 2] += H.hxu[1];
+    double Y[12];
+    LUNR for (int a = 0; a < NW; a++) LUNR for (int k = 0; k < 4; k++) f.St[4 * a + k] = c.D[a] * GA[k] + c.D[NW + a] * GA[4 + k];
+    // Y = L^-1 S~, K = L^-T Y, column by column
+    LUNR for (int k = 0; k < 4; k++) {
+      double col[3] = {0.0, 0.0, 0.0};
+      LUNR for (int a = 0; a < NW; a++) col[a] = f.St[4 * a + k];
+      l_chol_fwd<NW>(f.Lc, col);
+      LUNR for (int a = 0; a < NW; a++) Y[4 * a + k] = col[a];
+      l_chol_bwd<NW>(f.Lc, col);
+      LUNR for (int a = 0; a < NW; a++) f.K[4 * a + k] = col[a];
+    }
+    // P_j = Q~ - Y'Y,  Q~ = A' PA + diag(hx_{j} + dw) + hxy_{j}
+    LUNR for (int i = 0; i < 4; i++) LUNR for (int k = 0; k <= i; k++) {
+      const int bi = i >> 1, ri = i & 1;
+      double s = (ri ? P.a12 : P.a11) * PA[4 * (2 * bi) + k] + (ri ? P.a22 : P.a21) * PA[4 * (2 * bi + 1) + k];
+      if (i == k) s += hxp[i] + dw;
+      if (i == 2 && k == 0) s += hxyp;
+      LUNR for (int a = 0; a < NW; a++) s -= Y[4 * a + i] * Y[4 * a + k];
+      Pout[sy(i, k)] = s;
+    }
+    ok = okc;
+  }
+  if (g.j == 0) { LUNR for (int t = 0; t < 12; t++) f.K[t] = 0.0; }  // x_0 is fixed: no feedback at stage 0
+  return g_all(g, ok);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Substitutions.  NB = number of border right-hand sides carried along with the (optional) main one.
+//   backward: lane j receives from lane j+1, adds its own right-hand side, keeps pv (p_{j+1}) and kv, passes on;
+//   forward : lane j receives x_j from lane j-1, produces x_{j+1} (and, for the main RHS, w and the dynamics multiplier).
+// ---------------------------------------------------------------------------------------------------------------
+struct LaneMain { double rx[4], rw[3], cv[4], pv[4], kv[3]; };  // main RHS after the stage elimination + its backward vectors
+
+template <int C, bool MAIN, int NB>
+LDEV void l_backward(const Grp& g, const KParams& P, const LaneConst& c, const LaneFact& f, LaneMain& m, const double (*brhs)[4],
+                     double (*bpv)[4], double (*bkv)[3]) {
+  constexpr int NW = LaneDims<C>::NW, NCH = (MAIN ? 1 : 0) + NB;
+  double out[NCH > 0 ? NCH : 1][4];
+  LUNR for (int r = 0; r < NCH; r++) LUNR for (int i = 0; i < 4; i++) out[r][i] = 0.0;
+#pragma unroll 1
+  for (int step = 0; step < 4; step++) {
+    LUNR for (int r = 0; r < NCH; r++) {
+      const bool is_main = MAIN && r == 0;
+      const int rb = MAIN ? r - 1 : r;
+      double inc[4];
+      if (step > 0) l_from_next(g, out[r], inc);
+      else { LUNR for (int i = 0; i < 4; i++) inc[i] = 0.0; }
+      double pn[4], q[4];
+      LUNR for (int i = 0; i < 4; i++) pn[i] = (is_main ? m.rx[i] : brhs[rb][i]) + inc[i];
+      LUNR for (int i = 0; i < 4; i++) {
+        double s = -pn[i];
+        if (is_main) { LUNR for (int k = 0; k < 4; k++) s += f.Pn[sy(i, k)] * m.cv[k]; }
+        q[i] = s;
+      }
+      const double g0 = P.bp * q[0] + P.bv * q[1], g1 = P.bp * q[2] + P.bv * q[3];
+      double k[3] = {0.0, 0.0, 0.0};
+      LUNR for (int a = 0; a < NW; a++) k[a] = (is_main ? m.rw[a] : 0.0) - (c.D[a] * g0 + c.D[NW + a] * g1);
+      l_chol_solve<NW>(f.Lc, k);
+      double aq[4];
+      l_ATx(P, q, aq);
+      LUNR for (int i = 0; i < 4; i++) {
+        double s = -aq[i];
+        LUNR for (int a = 0; a < NW; a++) s -= f.St[4 * a + i] * k[a];
+        out[r][i] = s;
+      }
+      if (is_main) { LUNR for (int i = 0; i < 4; i++) m.pv[i] = pn[i]; LUNR for (int a = 0; a < NW; a++) m.kv[a] = k[a]; }
+      else { LUNR for (int i = 0; i < 4; i++) bpv[rb][i] = pn[i]; LUNR for (int a = 0; a < NW; a++) bkv[rb][a] = k[a]; }
+    }
+  }
+}
+
+// mode 0: positions of x_{j+1} only (pos[r][2]);  mode 1 (main only): dx.xs, w, dy.pi
+template <int C, bool MAIN, int NB, int MODE>
+LDEV void l_forward(const Grp& g, const KParams& P, const LaneConst& c, const LaneFact& f, const LaneMain& m, const double (*bpv)[4],
+                    const double (*bkv)[3], double (*pos)[2], double* dxs, double* wout, double* dpi) {
+  constexpr int NW = LaneDims<C>::NW, NCH = (MAIN ? 1 : 0) + NB;
+  double xn[NCH > 0 ? NCH : 1][4];
+  LUNR for (int r = 0; r < NCH; r++) LUNR for (int i = 0; i < 4; i++) xn[r][i] = 0.0;
+#pragma unroll 1
+  for (int step = 0; step < 4; step++) {
+    LUNR for (int r = 0; r < NCH; r++) {
+      const bool is_main = MAIN && r == 0;
+      const int rb = MAIN ? r - 1 : r;
+      double xp[4];
+      if (step > 0) l_from_prev(g, xn[r], xp);
+      else { LUNR for (int i = 0; i < 4; i++) xp[i] = 0.0; }
+      double w[3] = {0.0, 0.0, 0.0};
+      LUNR for (int a = 0; a < NW; a++) {
+        double s = is_main ? m.kv[a] : bkv[rb][a];
+        LUNR for (int k = 0; k < 4; k++) s -= f.K[4 * a + k] * xp[k];
+        w[a] = s;
+      }
+      double d0 = 0.0, d1 = 0.0;
+      LUNR for (int a = 0; a < NW; a++) { d0 += c.D[a] * w[a]; d1 += c.D[NW + a] * w[a]; }
+      double ax[4];
+      l_Ax(P, xp, ax);
+      ax[0] += P.bp * d0; ax[1] += P.bv * d0; ax[2] += P.bp * d1; ax[3] += P.bv * d1;
+      if (is_main) { LUNR for (int i = 0; i < 4; i++) ax[i] += m.cv[i]; }
+      LUNR for (int i = 0; i < 4; i++) xn[r][i] = ax[i];
+      if (MODE == 0) { pos[r][0] = ax[0]; pos[r][1] = ax[2]; }
+      else if (is_main) {
+        LUNR for (int i = 0; i < 4; i++) {
+          double s = -m.pv[i];
+          LUNR for (int k = 0; k < 4; k++) s += f.Pn[sy(i, k)] * ax[k];
+          dxs[i] = ax[i]; dpi[i] = s;
+        }
+        LUNR for (int a = 0; a < NW; a++) wout[a] = w[a];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Solve  [H A'; A 0][dx; dy] = [r1; r2]  with the current factorisation (r.xs,us,lm,dl = r1; r.pi,nu,eta = r2).
+// BORDER: the slack variable and the capped distance rows are coupled through the 5x5 Schur complement of `bf`, whose
+// border vectors are read from the thread-private columns; tb = border multipliers of the capped rows (group values).
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+LDEV void l_stage_eliminate(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, double dw, const KV& r, LaneMain& m, double* d0) {
+  constexpr int NW = LaneDims<C>::NW;
+  const double e0 = r.eta;
+  LUNR for (int a = 0; a < 2; a++) d0[a] = c.F[4 * a + C - 1] * e0 + r.nu[a];
+  const double last = r.lm[C - 1] - (H.hl[C - 1] + dw) * e0;
+  const double ru0 = r.us[0] - (H.hu[0] + dw) * d0[0], ru1 = r.us[1] - (H.hu[1] + dw) * d0[1];
+  LUNR for (int a = 0; a < 3; a++) m.rw[a] = 0.0;
+  LUNR for (int a = 0; a < NW; a++) m.rw[a] = r.lm[a] - last + c.D[a] * ru0 + c.D[NW + a] * ru1;
+  LUNR for (int b = 0; b < 2; b++) {
+    m.cv[2 * b] = P.bp * d0[b] - r.pi[2 * b];
+    m.cv[2 * b + 1] = P.bv * d0[b] - r.pi[2 * b + 1];
+  }
+  // the friction coupling hxu_j d0_j acts on the position rows of x_j, i.e. of the previous lane
+  LUNR for (int b = 0; b < 2; b++) {
+    const double t = g_down(g, H.hxu[b] * d0[b]);
+    m.rx[2 * b] = r.xs[2 * b] - ((g.j < 3) ? t : 0.0);
+    m.rx[2 * b + 1] = r.xs[2 * b + 1];
+  }
+}
+
+template <int C>
+LDEV void l_recover(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, double dw, const KV& r, const double* d0,
+                    const double* w, double ddl, KV& d) {
+  constexpr int NW = LaneDims<C>::NW;
+  const double e0 = r.eta;
+  double wsum_ = 0.0, du0 = d0[0], du1 = d0[1];
+  LUNR for (int a = 0; a < NW; a++) { d.lm[a] = w[a]; wsum_ += w[a]; du0 += c.D[a] * w[a]; du1 += c.D[NW + a] * w[a]; }
+  const double dll = e0 - wsum_;
+  d.lm[C - 1] = dll;
+  LUNR for (int i = C; i < 4; i++) d.lm[i] = 0.0;
+  d.us[0] = du0; d.us[1] = du1;
+  // dx of the previous lane's positions (x_j), zero at lane 0
+  const double xp0 = g_up(g, d.xs[0]), xp2 = g_up(g, d.xs[2]);
+  const double du[2] = {du0, du1};
+  const double xpp[2] = {(g.j > 0) ? xp0 : 0.0, (g.j > 0) ? xp2 : 0.0};
+  LUNR for (int a = 0; a < 2; a++)
+    d.nu[a] = r.us[a] - (H.hu[a] + dw) * du[a] - (P.bp * d.pi[2 * a] + P.bv * d.pi[2 * a + 1]) - H.hxu[a] * xpp[a];
+  d.eta = r.lm[C - 1] - (H.hl[C - 1] + dw) * dll + c.F[C - 1] * d.nu[0] + c.F[4 + C - 1] * d.nu[1];
+  d.dl = ddl;
+}
+
+// plain solve (QP stage): the slack variable is decoupled
+template <int C>
+LDEV void l_kkt_solve_plain(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, const LaneFact& f, double dw, const KV& r, KV& d) {
+  LaneMain m; double d0[2], w[3];
+  l_stage_eliminate<C>(g, P, c, H, dw, r, m, d0);
+  l_backward<C, true, 0>(g, P, c, f, m, nullptr, nullptr, nullptr);
+  l_forward<C, true, 0, 1>(g, P, c, f, m, nullptr, nullptr, nullptr, d.xs, w, d.pi);
+  l_recover<C>(g, P, c, H, dw, r, d0, w, r.dl / (H.hd + dw), d);
+}
+
+// border factorisation (NLP stage): solves the 4 distance-row columns (column k: gv at stage k), derives the slack
+// variable's column by superposition (its x-part is sum_k sc_k * column k), builds and factorises the Schur complement.
+template <int C>
+LDEV bool l_border_factor(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, const LaneFact& f, double dw,
+                          const Priv& pr, LaneBorder& bf) {
+  typedef LaneDims<C> d;
+  constexpr int NW = d::NW;
+  double brhs[4][4], bpv[4][4], bkv[4][3], posb[4][2], posd[2];
+  LUNR for (int k = 0; k < 4; k++) {
+    brhs[k][0] = (g.j == k) ? H.gv[0] : 0.0; brhs[k][1] = 0.0; brhs[k][2] = (g.j == k) ? H.gv[1] : 0.0; brhs[k][3] = 0.0;
+  }
+  LaneMain dummy;
+  l_backward<C, false, 4>(g, P, c, f, dummy, brhs, bpv, bkv);
+  l_forward<C, false, 4, 0>(g, P, c, f, dummy, bpv, bkv, posb, nullptr, nullptr, nullptr);
+  LUNR for (int k = 0; k < 4; k++) {
+    LUNR for (int i = 0; i < 4; i++) pr(d::F_PVB + 4 * k + i) = bpv[k][i];
+    LUNR for (int a = 0; a < NW; a++) pr(d::F_KVB + 3 * k + a) = bkv[k][a];
+  }
+  // group values: sc_k, capped_k of every stage
+  double sck[4];
+  const unsigned capbits = g_bits(g, H.capped != 0);
+  LUNR for (int k = 0; k < 4; k++) { sck[k] = g_idx(g, H.sc, k); bf.cap[k] = (int)((capbits >> k) & 1u); }
+  // slack-variable column by superposition; positions at this lane's stage
+  posd[0] = 0.0; posd[1] = 0.0;
+  LUNR for (int k = 0; k < 4; k++) { posd[0] += sck[k] * posb[k][0]; posd[1] += sck[k] * posb[k][1]; }
+  // row j of T, cb_j, and this lane's share of a
+  double Trow[4];
+  LUNR for (int l = 0; l < 4; l++) {
+    double v;
+    if (H.capped && bf.cap[l]) { v = H.gv[0] * posb[l][0] + H.gv[1] * posb[l][1]; if (l == g.j) v += H.srinv; }
+    else v = (l == g.j) ? 1.0 : 0.0;
+    Trow[l] = v;
+  }
+  const double cbj = H.capped ? 1.0 - (H.gv[0] * posd[0] + H.gv[1] * posd[1]) : 0.0;
+  const double a = H.hd + dw - g_sum(g, H.bd[0] * posd[0] + H.bd[1] * posd[1]);
+  double T[10];
+  LUNR for (int k = 0; k < 4; k++) LUNR for (int l = 0; l <= k; l++) T[(k * (k + 1)) / 2 + l] = g_idx(g, Trow[l], k);
+  LUNR for (int k = 0; k < 4; k++) bf.cb[k] = g_idx(g, cbj, k);
+  bool ok = l_chol4(T, bf.L);
+  l_chol4_solve(bf.L, bf.cb, bf.Tic);
+  bf.den = a + bf.cb[0] * bf.Tic[0] + bf.cb[1] * bf.Tic[1] + bf.cb[2] * bf.Tic[2] + bf.cb[3] * bf.Tic[3];
+  ok = ok && (bf.den > 0.0);
+  return g_all(g, ok);
+}
+
+// bordered solve (NLP stage).  posb / posd: positions of the border columns at this lane's stage (from l_border_factor).
+template <int C>
+LDEV void l_kkt_solve_border(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, const LaneFact& f, double dw,
+                             const Priv& pr, const LaneBorder& bf, const KV& r, KV& d, double* tb) {
+  typedef LaneDims<C> dm;
+  constexpr int NW = dm::NW;
+  LaneMain m; double d0[2], w[3];
+  l_stage_eliminate<C>(g, P, c, H, dw, r, m, d0);
+  l_backward<C, true, 0>(g, P, c, f, m, nullptr, nullptr, nullptr);
+  double pos0[1][2];
+  l_forward<C, true, 0, 0>(g, P, c, f, m, nullptr, nullptr, pos0, nullptr, nullptr, nullptr);
+  const double rtj = H.capped ? H.gv[0] * pos0[0][0] + H.gv[1] * pos0[0][1] : 0.0;
+  const double rd = r.dl - g_sum(g, H.bd[0] * pos0[0][0] + H.bd[1] * pos0[0][1]);
+  double rt[4], kk[4];
+  LUNR for (int k = 0; k < 4; k++) rt[k] = g_idx(g, rtj, k);
+  l_chol4_solve(bf.L, rt, kk);
+  const double ddl = (rd - (bf.cb[0] * kk[0] + bf.cb[1] * kk[1] + bf.cb[2] * kk[2] + bf.cb[3] * kk[3])) * l_rcp(bf.den);
+  double t[4], sck[4];
+  LUNR for (int k = 0; k < 4; k++) { t[k] = bf.Tic[k] * ddl + kk[k]; sck[k] = g_idx(g, H.sc, k); tb[k] = t[k]; }
+  // combine the backward-pass vectors: p <- p0 - ddl p_delta - sum_{k capped} t_k p_k, p_delta = sum_k sc_k p_k
+  double coef[4];
+  LUNR for (int k = 0; k < 4; k++) coef[k] = ddl * sck[k] + (bf.cap[k] ? t[k] : 0.0);
+  LUNR for (int i = 0; i < 4; i++) { double s = m.pv[i]; LUNR for (int k = 0; k < 4; k++) s -= coef[k] * pr(dm::F_PVB + 4 * k + i); m.pv[i] = s; }
+  LUNR for (int a = 0; a < NW; a++) { double s = m.kv[a]; LUNR for (int k = 0; k < 4; k++) s -= coef[k] * pr(dm::F_KVB + 3 * k + a); m.kv[a] = s; }
+  l_forward<C, true, 0, 1>(g, P, c, f, m, nullptr, nullptr, nullptr, d.xs, w, d.pi);
+  l_recover<C>(g, P, c, H, dw, r, d0, w, ddl, d);
+}
+
+// ===============================================================================================================
+// Slots: two-sided scalar constraints lo <= e(x) <= hi owned by this lane (reference rows: DESIGN.md "row map")
+//   SX i : x_{j+1}[i]            +-box   MD:294-297,317-318        SU a : u_j[a]  +-box
+//   SL i : lambda_j[i] in [0,1]  MD:299-300,320-321                SF a : p_j[a] - u_j[a], +-mu h / sqrt 2 (j >= 1)  MD:278-292,315
+//   SV a : v_{j+1}[a]  +-v_max   DV:270-279,306-317 (NLP only)     SD   : |p_{j+1} - o|^2 + delta >= eps   DV:262-265,299-302 (NLP only)
+// ===============================================================================================================
+template <int C> LDEV bool l_slot_valid(int s, const Grp& g) { typedef LaneDims<C> d; return (s >= d::SF && s < d::SF + 2) ? (g.j > 0) : true; }
+template <int C> LDEV void l_slot_bounds(int s, const KParams& P, double& lo, double& hi) {
+  typedef LaneDims<C> d;
+  if (s < d::SL) { lo = -P.box; hi = P.box; }
+  else if (s < d::SF) { lo = 0.0; hi = 1.0; }
+  else if (s < d::SV) { lo = -P.fb; hi = P.fb; }
+  else if (s < d::SD) { lo = -P.vmax; hi = P.vmax; }
+  else { lo = P.eps; hi = 0.0; }
+}
+// linear part of e: v = lane vector, vp = previous lane's xs (x_j)
+template <int C> LDEV double l_slot_lin(int s, const KV& v, const double* vp) {
+  typedef LaneDims<C> d;
+  if (s < d::SU) return v.xs[s];
+  if (s < d::SL) return v.us[s - d::SU];
+  if (s < d::SF) return v.lm[s - d::SL];
+  if (s < d::SV) { const int a = s - d::SF; return vp[2 * a] - v.us[a]; }
+  if (s < d::SD) { const int a = s - d::SV; return v.xs[2 * a + 1]; }
+  return 0.0;
+}
+// acc.(xs,us,lm) = J'w for per-slot weights w (weight of +grad e); wd = sum over the group of the distance-row weights
+template <int C, bool NL>
+LDEV void l_gather(const Grp& g, const double* w, const double* gv, KV& acc, double& wd) {
+  typedef LaneDims<C> d;
+  LUNR for (int i = 0; i < 4; i++) acc.xs[i] = w[d::SX + i];
+  LUNR for (int a = 0; a < 2; a++) acc.us[a] = w[d::SU + a] - w[d::SF + a];
+  LUNR for (int i = 0; i < 4; i++) acc.lm[i] = (i < C) ? w[d::SL + i] : 0.0;
+  LUNR for (int a = 0; a < 2; a++) { const double t = g_down(g, w[d::SF + a]); acc.xs[2 * a] += (g.j < 3) ? t : 0.0; }
+  wd = 0.0;
+  if (NL) {
+    LUNR for (int a = 0; a < 2; a++) { acc.xs[2 * a + 1] += w[d::SV + a]; acc.xs[2 * a] += gv[a] * w[d::SD]; }
+    wd = g_sum(g, w[d::SD]);
+  }
+}
+// stage Hessian blocks from the slot weights sa (Sigma); NL: distance-row data already in H (gv, sc, zd)
+template <int C, bool NL>
+LDEV void l_assemble(const Grp& g, const KParams& P, const LaneConst& c, const double* sa, double rho, double zd, LaneHess& H) {
+  typedef LaneDims<C> d;
+  LUNR for (int i = 0; i < 4; i++) H.hx[i] = c.qw + sa[d::SX + i];
+  LUNR for (int a = 0; a < 2; a++) {
+    const double sf = sa[d::SF + a];
+    H.hu[a] = P.Rw + sa[d::SU + a] + sf;
+    H.hxu[a] = -sf;
+    const double t = g_down(g, sf);
+    H.hx[2 * a] += (g.j < 3) ? t : 0.0;
+  }
+  LUNR for (int i = 0; i < 4; i++) H.hl[i] = (i < C) ? rho + sa[d::SL + i] : 0.0;
+  if (NL) {
+    LUNR for (int a = 0; a < 2; a++) { H.hx[2 * a + 1] += sa[d::SV + a]; H.hx[2 * a] += H.sc * H.gv[a] * H.gv[a] - 2.0 * zd; H.bd[a] = H.sc * H.gv[a]; }
+    H.hxy = H.sc * H.gv[0] * H.gv[1];
+    H.hd = P.slw + g_sum(g, H.sc);
+  } else {
+    H.hxy = 0.0; H.bd[0] = 0.0; H.bd[1] = 0.0; H.hd = P.slw;
+  }
+}
+
+struct LaneInfo { int status, qp_iters, qp_flag, nlp_iters, n_fact; double kkt; };
+
+// everything a lane keeps in registers across iterations
+template <int C>
+struct LaneSolver {
+  typedef LaneDims<C> d;
+  Grp g;
+  Priv pr;
+  LaneConst c;
+  KV x;            // iterate: xs, us, lm, dl | pi, nu, eta
+  LaneHess H;
+  LaneFact f;
+  LaneInfo info;
+
+  LMEM void prev_state(const KV& v, bool homogeneous, double* xp) const {  // x_j: previous lane's xs; lane 0: measured state
+    LUNR for (int i = 0; i < 4; i++) { const double t = g_up(g, v.xs[i]); xp[i] = (g.j > 0) ? t : (homogeneous ? 0.0 : c.xin[i]); }
+  }
+  LMEM void next_pi(const KV& v, double* pin) const { l_from_next(g, v.pi, pin); }
+
+  // =============================================================================================================
+  // Stage 1: QP, iSWIFT restated (Prime.c:127-230; kkt_initialize Auxilary.c:680-755)
+  // =============================================================================================================
+  double sigma; int qp_it;
+
+  // initial point.  Returns true when the stage is already finished (factorisation failure).
+  LMEM bool qp_init(const KParams& P) {
+    // W = I, rhs [-c; b; h]
+    double sa[d::NS], sb[d::NS];
+    LUNR for (int s = 0; s < d::NS; s++) {
+      double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
+      const bool act = s < d::NSQP && l_slot_valid<C>(s, g);
+      sa[s] = act ? 2.0 : 0.0; sb[s] = act ? hi + lo : 0.0;
+    }
+    LUNR for (int i = 0; i < 4; i++) { x.xs[i] = 0.0; x.lm[i] = 0.0; x.pi[i] = 0.0; }
+    x.us[0] = x.us[1] = 0.0; x.dl = 0.0; x.nu[0] = x.nu[1] = 0.0; x.eta = 0.0;
+    H.gv[0] = H.gv[1] = 0.0; H.sc = 0.0; H.srinv = 0.0; H.capped = 0;
+    l_assemble<C, false>(g, P, c, sa, 0.0, 0.0, H);
+    KV r, dd; double wd;
+    l_gather<C, false>(g, sb, H.gv, r, wd);
+    LUNR for (int i = 0; i < 4; i++) r.xs[i] += c.qw * c.xdes[i];
+    r.dl = 0.0;
+    {
+      double xp[4]; prev_state(x, false, xp);
+      double rpi[4], rnu[2], reta;
+      l_eq_residual<C>(P, c, x, xp, false, rpi, rnu, reta);
+      LUNR for (int i = 0; i < 4; i++) r.pi[i] = -rpi[i];
+      r.nu[0] = -rnu[0]; r.nu[1] = -rnu[1]; r.eta = -reta;
+    }
+    info.qp_flag = 3; info.qp_iters = 0; qp_it = 0; sigma = 100.0;  // GlobalOptions.h:26
+    if (!l_riccati<C, true>(g, P, c, H, 0.0, f)) { info.qp_flag = 1; return true; }
+    l_kkt_solve_plain<C>(g, P, c, H, f, 0.0, r, dd);
+    x = dd;
+    LUNR for (int i = C; i < 4; i++) x.lm[i] = 0.0;
+    // slacks and multipliers shifted positive (Auxilary.c:724-746)
+    double xp[4]; prev_state(x, false, xp);
+    double rl[d::NSQP], rh[d::NSQP], rmin = 1e300, rmax = -1e300;
+    LUNR for (int s = 0; s < d::NSQP; s++) {
+      double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
+      const double e = l_slot_lin<C>(s, x, xp);
+      rl[s] = e - lo; rh[s] = hi - e;
+      if (l_slot_valid<C>(s, g)) { rmin = fmin(rmin, fmin(rl[s], rh[s])); rmax = fmax(rmax, fmax(rl[s], rh[s])); }
+    }
+    rmin = g_min(g, rmin); rmax = g_max(g, rmax);
+    const double ap = -rmin, ad = rmax;
+    LUNR for (int s = 0; s < d::NSQP; s++) {
+      const bool act = l_slot_valid<C>(s, g);
+      pr(d::F_SLO + s) = act ? ((ap < 0) ? rl[s] : rl[s] + (1.0 + ap)) : 1.0;
+      pr(d::F_SHI + s) = act ? ((ap < 0) ? rh[s] : rh[s] + (1.0 + ap)) : 1.0;
+      pr(d::F_ZLO + s) = act ? ((ad < 0) ? -rl[s] : -rl[s] + (1.0 + ad)) : 0.0;
+      pr(d::F_ZHI + s) = act ? ((ad < 0) ? -rh[s] : -rh[s] + (1.0 + ad)) : 0.0;
+    }
+    info.qp_flag = 2;
+    return false;
+  }
+
+  // one Mehrotra predictor-corrector iteration (Prime.c:138-218).  Returns true when the stage is finished.
+  LMEM bool qp_iter(const KParams& P) {
+    if (qp_it >= P.qp_maxit) return true;
+    double xp[4], pin[4];
+    prev_state(x, false, xp); next_pi(x, pin);
+    // ---- residuals (computeresiduals, Auxilary.c:524-553)
+    KV rx;  // rx.(xs,us,lm,dl) = -(Px + G'z + A'y + c), rx.(pi,nu,eta) = b - Ax
+    double sz, mu;
+    {
+      double wz[d::NS], acc_rz = 0.0, acc_sz = 0.0;
+      LUNR for (int s = 0; s < d::NS; s++) wz[s] = 0.0;
+      LUNR for (int s = 0; s < d::NSQP; s++) {
+        if (l_slot_valid<C>(s, g)) {
+          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
+          const double e = l_slot_lin<C>(s, x, xp);
+          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+          const double rzh = hi - shi - e, rzl = -lo - slo + e;
+          acc_rz += rzh * rzh + rzl * rzl;
+          acc_sz += slo * zlo + shi * zhi;
+          wz[s] = zlo - zhi;
+        }
+      }
+      KV gfy, jz; double wd;
+      l_grad_Aty<C>(P, c, x, x, pin, true, gfy);
+      l_gather<C, false>(g, wz, H.gv, jz, wd);
+      double acc_rx = 0.0, acc_ry = 0.0;
+      LUNR for (int i = 0; i < 4; i++) { rx.xs[i] = -(gfy.xs[i] - jz.xs[i]); acc_rx += rx.xs[i] * rx.xs[i]; }
+      LUNR for (int a = 0; a < 2; a++) { rx.us[a] = -(gfy.us[a] - jz.us[a]); acc_rx += rx.us[a] * rx.us[a]; }
+      LUNR for (int i = 0; i < 4; i++) { rx.lm[i] = (i < C) ? -(gfy.lm[i] - jz.lm[i]) : 0.0; acc_rx += rx.lm[i] * rx.lm[i]; }
+      rx.dl = -gfy.dl;
+      if (g.j == 0) acc_rx += rx.dl * rx.dl;
+      double rpi[4], rnu[2], reta;
+      l_eq_residual<C>(P, c, x, xp, false, rpi, rnu, reta);
+      LUNR for (int i = 0; i < 4; i++) { rx.pi[i] = -rpi[i]; acc_ry += rpi[i] * rpi[i]; }
+      LUNR for (int a = 0; a < 2; a++) { rx.nu[a] = -rnu[a]; acc_ry += rnu[a] * rnu[a]; }
+      rx.eta = -reta; acc_ry += reta * reta;
+      const double nrx = g_sum(g, acc_rx), nry = g_sum(g, acc_ry), nrz = g_sum(g, acc_rz);
+      sz = g_sum(g, acc_sz);
+      const double lim = P.qp_reltol / sqrt(3.0);
+      if (sqrt(nrx) < lim && sqrt(nrz) < lim && sqrt(nry) < lim && sz / d::MQP < P.qp_abstol) { info.qp_flag = 0; return true; }
+      mu = sz / d::MQP;
+    }
+    // ---- reciprocals, once per iteration: 1/s -> F_A, F_B ; 1/z -> F_C, F_D
+    LUNR for (int s = 0; s < d::NSQP; s++) {
+      if (l_slot_valid<C>(s, g)) {
+        pr(d::F_A + s) = l_rcp(pr(d::F_SLO + s)); pr(d::F_B + s) = l_rcp(pr(d::F_SHI + s));
+        pr(d::F_C + s) = l_rcp(pr(d::F_ZLO + s)); pr(d::F_D + s) = l_rcp(pr(d::F_ZHI + s));
+      }
+    }
+    KV r, dd;
+    if (sigma > 0.0) {
+      // predictor: W = s/z, ds = -s z, rhs3 = rz - ds/z = rz + s
+      double sa[d::NS], sb[d::NS];
+      LUNR for (int s = 0; s < d::NS; s++) { sa[s] = 0.0; sb[s] = 0.0; }
+      LUNR for (int s = 0; s < d::NSQP; s++) {
+        if (l_slot_valid<C>(s, g)) {
+          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
+          const double e = l_slot_lin<C>(s, x, xp);
+          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+          const double wl = zlo * pr(d::F_A + s), wh = zhi * pr(d::F_B + s);
+          const double rzh = hi - shi - e, rzl = -lo - slo + e;
+          sa[s] = wl + wh;
+          sb[s] = wh * (rzh + shi) - wl * (rzl + slo);
+        }
+      }
+      l_assemble<C, false>(g, P, c, sa, 0.0, 0.0, H);
+      double wd;
+      l_gather<C, false>(g, sb, H.gv, r, wd);
+      LUNR for (int i = 0; i < 4; i++) { r.xs[i] += rx.xs[i]; r.lm[i] += rx.lm[i]; r.pi[i] = rx.pi[i]; }
+      LUNR for (int a = 0; a < 2; a++) { r.us[a] += rx.us[a]; r.nu[a] = rx.nu[a]; }
+      r.dl = rx.dl; r.eta = rx.eta;
+      info.n_fact++;
+      if (!l_riccati<C, true>(g, P, c, H, 0.0, f)) { info.qp_flag = 1; return true; }
+      l_kkt_solve_plain<C>(g, P, c, H, f, 0.0, r, dd);
+      // affine step: max step lengths (findsteplength, Auxilary.c:271-294) and rho (Auxilary.c:600-609)
+      double dxp[4]; prev_state(dd, true, dxp);
+      double rp = 0.0, rdm = 0.0, s_dsz = 0.0, s_sdz = 0.0, s_dsdz = 0.0;
+      LUNR for (int s = 0; s < d::NSQP; s++) {
+        if (l_slot_valid<C>(s, g)) {
+          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
+          const double e = l_slot_lin<C>(s, x, xp), de = l_slot_lin<C>(s, dd, dxp);
+          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+          const double isl = pr(d::F_A + s), ish = pr(d::F_B + s), izl = pr(d::F_C + s), izh = pr(d::F_D + s);
+          const double wl = zlo * isl, wh = zhi * ish;
+          const double rzh = hi - shi - e, rzl = -lo - slo + e;
+          const double dzh = wh * (de - (rzh + shi)), dzl = wl * (-de - (rzl + slo));
+          const double dsh = (-shi * zhi - shi * dzh) * izh, dsl = (-slo * zlo - slo * dzl) * izl;
+          rp = fmax(rp, fmax(-dsh * ish, -dsl * isl));
+          rdm = fmax(rdm, fmax(-dzh * izh, -dzl * izl));
+          s_dsz += dsl * zlo + dsh * zhi; s_sdz += slo * dzl + shi * dzh; s_dsdz += dsl * dzl + dsh * dzh;
+          pr(d::F_E + s) = dsl * dzl; pr(d::F_G + s) = dsh * dzh;
+        }
+      }
+      rp = g_max(g, rp); rdm = g_max(g, rdm);
+      const double ap = (rp > 0.0) ? 1.0 / rp : 1.0, ad = (rdm > 0.0) ? 1.0 / rdm : 1.0;
+      // sum (s + ap ds)(z + ad dz) = s'z + ap ds'z + ad s'dz + ap ad ds'dz
+      const double num = sz + g_sum(g, ap * s_dsz + ad * s_sdz + (ap * ad) * s_dsdz);
+      const double rho = num / sz, mr = rho < 1.0 ? rho : 1.0;
+      sigma = mr * mr * mr;
+      if (sigma < 0.0) sigma = 0.0;
+    } else {
+      sigma = 0.0;
+      LUNR for (int s = 0; s < d::NSQP; s++) { pr(d::F_E + s) = 0.0; pr(d::F_G + s) = 0.0; }
+    }
+    // ---- corrector solve with the same factor: ds = -s z - ds_aff dz_aff + sigma mu (form_ds, Auxilary.c:250-267)
+    {
+      double sb[d::NS];
+      LUNR for (int s = 0; s < d::NS; s++) sb[s] = 0.0;
+      LUNR for (int s = 0; s < d::NSQP; s++) {
+        if (l_slot_valid<C>(s, g)) {
+          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
+          const double e = l_slot_lin<C>(s, x, xp);
+          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+          const double wl = zlo * pr(d::F_A + s), wh = zhi * pr(d::F_B + s);
+          const double rzh = hi - shi - e, rzl = -lo - slo + e;
+          const double cdl = -slo * zlo - pr(d::F_E + s) + sigma * mu, cdh = -shi * zhi - pr(d::F_G + s) + sigma * mu;
+          const double r3l = rzl - cdl * pr(d::F_C + s), r3h = rzh - cdh * pr(d::F_D + s);
+          sb[s] = wh * r3h - wl * r3l;
+        }
+      }
+      double wd;
+      l_gather<C, false>(g, sb, H.gv, r, wd);
+      LUNR for (int i = 0; i < 4; i++) { r.xs[i] += rx.xs[i]; r.lm[i] += rx.lm[i]; r.pi[i] = rx.pi[i]; }
+      LUNR for (int a = 0; a < 2; a++) { r.us[a] += rx.us[a]; r.nu[a] = rx.nu[a]; }
+      r.dl = rx.dl; r.eta = rx.eta;
+    }
+    l_kkt_solve_plain<C>(g, P, c, H, f, 0.0, r, dd);
+    double ap, ad;
+    {
+      double dxp[4]; prev_state(dd, true, dxp);
+      double rp = 0.0, rdm = 0.0;
+      LUNR for (int s = 0; s < d::NSQP; s++) {
+        if (l_slot_valid<C>(s, g)) {
+          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
+          const double e = l_slot_lin<C>(s, x, xp), de = l_slot_lin<C>(s, dd, dxp);
+          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+          const double isl = pr(d::F_A + s), ish = pr(d::F_B + s), izl = pr(d::F_C + s), izh = pr(d::F_D + s);
+          const double wl = zlo * isl, wh = zhi * ish;
+          const double rzh = hi - shi - e, rzl = -lo - slo + e;
+          const double cdl = -slo * zlo - pr(d::F_E + s) + sigma * mu, cdh = -shi * zhi - pr(d::F_G + s) + sigma * mu;
+          const double r3l = rzl - cdl * izl, r3h = rzh - cdh * izh;
+          const double dzh = wh * (de - r3h), dzl = wl * (-de - r3l);
+          const double dsh = (cdh - shi * dzh) * izh, dsl = (cdl - slo * dzl) * izl;
+          rp = fmax(rp, fmax(-dsh * ish, -dsl * isl));
+          rdm = fmax(rdm, fmax(-dzh * izh, -dzl * izl));
+          pr(d::F_A + s) = dsl; pr(d::F_B + s) = dsh; pr(d::F_C + s) = dzl; pr(d::F_D + s) = dzh;
+        }
+      }
+      rp = g_max(g, rp); rdm = g_max(g, rdm);
+      ap = (rp > 0.0) ? 1.0 / rp : 1.0; ad = (rdm > 0.0) ? 1.0 / rdm : 1.0;
+      ap = fmin(0.99 * ap, 1.0); ad = fmin(0.99 * ad, 1.0);
+    }
+    LUNR for (int i = 0; i < 4; i++) { x.xs[i] += ap * dd.xs[i]; x.pi[i] += ad * dd.pi[i]; }
+    LUNR for (int i = 0; i < C; i++) x.lm[i] += ap * dd.lm[i];
+    LUNR for (int a = 0; a < 2; a++) { x.us[a] += ap * dd.us[a]; x.nu[a] += ad * dd.nu[a]; }
+    x.dl += ap * dd.dl; x.eta += ad * dd.eta;
+    LUNR for (int s = 0; s < d::NSQP; s++) {
+      if (l_slot_valid<C>(s, g)) {
+        pr(d::F_SLO + s) += ap * pr(d::F_A + s); pr(d::F_SHI + s) += ap * pr(d::F_B + s);
+        pr(d::F_ZLO + s) += ad * pr(d::F_C + s); pr(d::F_ZHI + s) += ad * pr(d::F_D + s);
+      }
+    }
+    qp_it++;
+    info.qp_iters = qp_it;
+    return false;
+  }
+
+  // QP-only answer (use_snopt == false): unscaled KKT error of the QP
+  LMEM void qp_final_kkt(const KParams& P) {
+    double xp[4], pin[4];
+    prev_state(x, false, xp); next_pi(x, pin);
+    double wz[d::NS], ec = 0.0, ep = 0.0;
+    LUNR for (int s = 0; s < d::NS; s++) wz[s] = 0.0;
+    LUNR for (int s = 0; s < d::NSQP; s++) {
+      if (l_slot_valid<C>(s, g)) {
+        double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
+        const double e = l_slot_lin<C>(s, x, xp);
+        const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+        wz[s] = zlo - zhi;
+        ec = fmax(ec, fmax(fabs(slo * zlo), fabs(shi * zhi)));
+        ep = fmax(ep, fmax(fmax(lo - e, e - hi), 0.0));
+      }
+    }
+    KV gfy, jz; double wd;
+    l_grad_Aty<C>(P, c, x, x, pin, true, gfy);
+    l_gather<C, false>(g, wz, H.gv, jz, wd);
+    double rd = fabs(gfy.dl);
+    LUNR for (int i = 0; i < 4; i++) rd = fmax(rd, fabs(gfy.xs[i] - jz.xs[i]));
+    LUNR for (int a = 0; a < 2; a++) rd = fmax(rd, fabs(gfy.us[a] - jz.us[a]));
+    LUNR for (int i = 0; i < C; i++) rd = fmax(rd, fabs(gfy.lm[i] - jz.lm[i]));
+    double rpi[4], rnu[2], reta;
+    l_eq_residual<C>(P, c, x, xp, false, rpi, rnu, reta);
+    double re = fabs(reta);
+    LUNR for (int i = 0; i < 4; i++) re = fmax(re, fabs(rpi[i]));
+    re = fmax(re, fmax(fabs(rnu[0]), fabs(rnu[1])));
+    info.kkt = g_max(g, fmax(fmax(rd, re), fmax(ec, ep)));
+    info.status = (info.qp_flag == 0) ? 0 : 1;
+  }
+
+  // =============================================================================================================
+  // Stage 2: NLP, IPM-F
+  // =============================================================================================================
+  double mu, tau, dw_last, theta_max, theta_min; int nl_it, nfilt; bool first_ic;
+
+  LMEM double slot_e_nl(const KParams& P, int s, const double* xp) const {
+    if (s == d::SD) { const double a = x.xs[0] - c.ox, b = x.xs[2] - c.oy; return a * a + b * b + x.dl; }
+    return l_slot_lin<C>(s, x, xp);
+  }
+
+  LMEM void nlp_init(const KParams& P) {
+    // ---- step 0: strictly interior start (X, then U against friction, then lambda, then the slack variable)
+    LUNR for (int i = 0; i < 4; i++) {
+      const double lim = (i & 1) ? fmin(P.box, P.vmax) : P.box;
+      x.xs[i] = fmin(fmax(x.xs[i], -lim + P.push), lim - P.push);
+    }
+    LUNR for (int i = 0; i < C; i++) x.lm[i] = fmin(fmax(x.lm[i], P.push), 1.0 - P.push);
+    double xp[4]; prev_state(x, false, xp);
+    LUNR for (int a = 0; a < 2; a++) {
+      double lo = -P.box + P.push, hi = P.box - P.push;
+      if (g.j >= 1) { lo = fmax(lo, xp[2 * a] - P.fb + P.push); hi = fmin(hi, xp[2 * a] + P.fb - P.push); }
+      x.us[a] = fmin(fmax(x.us[a], lo), hi);
+    }
+    {
+      const double a = x.xs[0] - c.ox, b = x.xs[2] - c.oy;
+      const double cmin = g_min(g, a * a + b * b + x.dl - P.eps);
+      if (cmin < P.push) x.dl += P.push - cmin;
+    }
+    LUNR for (int i = 0; i < 4; i++) x.pi[i] = 0.0;
+    x.nu[0] = x.nu[1] = 0.0; x.eta = 0.0;
+    LUNR for (int t = 0; t < 16; t++) pr(d::F_FILT + t) = 0.0;
+    mu = P.mu_init; tau = fmax(P.tau_min, 1.0 - mu); dw_last = 0.0; first_ic = true; nfilt = 0; nl_it = 0;
+    LUNR for (int s = 0; s < d::NS; s++) {
+      double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
+      const bool v = l_slot_valid<C>(s, g), vhi = v && s != d::SD;
+      const double e = slot_e_nl(P, s, xp);
+      const double slo = v ? e - lo : 1.0, shi = vhi ? hi - e : 1.0;
+      pr(d::F_SLO + s) = slo; pr(d::F_SHI + s) = shi;
+      pr(d::F_ZLO + s) = v ? mu * l_rcp(slo) : 0.0; pr(d::F_ZHI + s) = vhi ? mu * l_rcp(shi) : 0.0;
+    }
+    {
+      double rpi[4], rnu[2], reta;
+      l_eq_residual<C>(P, c, x, xp, false, rpi, rnu, reta);
+      double r = fabs(reta) + fabs(rnu[0]) + fabs(rnu[1]);
+      LUNR for (int i = 0; i < 4; i++) r += fabs(rpi[i]);
+      const double th0 = g_sum(g, r);
+      theta_max = 1e4 * fmax(1.0, th0); theta_min = 1e-4 * fmax(1.0, th0);
+    }
+    info.status = 1; info.nlp_iters = 0;
+  }
+
+  // one IPM-F iteration.  Returns true when the stage is finished (info.status set).
+  LMEM bool nlp_iter(const KParams& P) {
+    const int it = nl_it;
+    double xp[4], pin[4];
+    prev_state(x, false, xp); next_pi(x, pin);
+    // ---- slots at x: s = c(x) (feasible IPM), multiplier safeguard, gradient of the distance row
+    KV gfy; double re_pi[4], re_nu[2], re_eta, e_d, e_p, th, zd;
+    {
+      double wz[d::NS], e_c = 0.0, zmax = 0.0, smin = 1e300;
+      const double iks = 1.0 / P.kappa_sigma;
+      LUNR for (int s = 0; s < d::NS; s++) {
+        wz[s] = 0.0;
+        if (l_slot_valid<C>(s, g)) {
+          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
+          const bool vhi = s != d::SD;
+          const double e = slot_e_nl(P, s, xp);
+          const double slo = e - lo, shi = vhi ? hi - e : 1.0;
+          double zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+          smin = fmin(smin, fmin(slo, shi));
+          if (it > 0) {  // z reset (Ipopt eq. 16) with the mu of the step just taken
+            const double mr_lo = mu * l_rcp(slo), mr_hi = mu * l_rcp(shi);
+            zlo = fmin(fmax(zlo, mr_lo * iks), P.kappa_sigma * mr_lo);
+            if (vhi) zhi = fmin(fmax(zhi, mr_hi * iks), P.kappa_sigma * mr_hi);
+            pr(d::F_ZLO + s) = zlo; pr(d::F_ZHI + s) = zhi;
+          }
+          pr(d::F_SLO + s) = slo; pr(d::F_SHI + s) = shi;
+          e_c = fmax(e_c, fmax(fabs(slo * zlo), fabs(shi * zhi)));
+          zmax = fmax(zmax, fmax(zlo, zhi));
+          wz[s] = zlo - zhi;
+        }
+      }
+      H.gv[0] = 2.0 * (x.xs[0] - c.ox); H.gv[1] = 2.0 * (x.xs[2] - c.oy);
+      zd = pr(d::F_ZLO + d::SD);
+      // ---- KKT error
+      KV jz; double wd;
+      l_grad_Aty<C>(P, c, x, x, pin, true, gfy);
+      l_gather<C, true>(g, wz, H.gv, jz, wd);
+      double rdm = fabs(gfy.dl - wd);
+      LUNR for (int i = 0; i < 4; i++) rdm = fmax(rdm, fabs(gfy.xs[i] - jz.xs[i]));
+      LUNR for (int a = 0; a < 2; a++) rdm = fmax(rdm, fabs(gfy.us[a] - jz.us[a]));
+      LUNR for (int i = 0; i < C; i++) rdm = fmax(rdm, fabs(gfy.lm[i] - jz.lm[i]));
+      // fold J'z into gfy: from here on gfy = grad f + A'y (kept) and gz = J'z are both needed
+      l_eq_residual<C>(P, c, x, xp, false, re_pi, re_nu, re_eta);
+      double rem = fabs(re_eta), res = fabs(re_eta);
+      LUNR for (int i = 0; i < 4; i++) { rem = fmax(rem, fabs(re_pi[i])); res += fabs(re_pi[i]); }
+      LUNR for (int a = 0; a < 2; a++) { rem = fmax(rem, fabs(re_nu[a])); res += fabs(re_nu[a]); }
+      e_d = g_max(g, rdm); e_p = g_max(g, rem); e_c = g_max(g, e_c); zmax = g_max(g, zmax);
+      th = g_sum(g, res);
+      const bool nan_seen = g_any(g, !(rdm == rdm) || !(rem == rem) || !(e_c == e_c) || !(zmax == zmax));
+      const double E0 = nan_seen ? 1e300 : fmax(e_d, fmax(e_p, e_c));
+      info.kkt = E0; info.nlp_iters = it;
+      LANE_LOG(1000.0 + it); LANE_LOG(mu); LANE_LOG(E0); LANE_LOG(e_d); LANE_LOG(e_p); LANE_LOG(e_c); LANE_LOG(th);
+      LANE_DBG("it %d mu %.2e E0 %.3e ed %.2e ep %.2e ec %.2e zmax %.2e th %.2e\n", it, mu, E0, e_d, e_p, e_c, zmax, th);
+      if (E0 <= P.tol) { info.status = 0; return true; }
+      if (it == P.max_iter) { info.status = 1; return true; }
+      if (!(zmax < P.z_div) || !(E0 < 1e300) || g_any(g, !(smin > 0.0))) { info.status = 2; return true; }
+    }
+    // ---- barrier update (Ipopt eq. 7)
+    for (;;) {
+      double emu = 0.0;
+      LUNR for (int s = 0; s < d::NS; s++) {
+        if (l_slot_valid<C>(s, g)) {
+          emu = fmax(emu, fabs(pr(d::F_SLO + s) * pr(d::F_ZLO + s) - mu));
+          if (s != d::SD) emu = fmax(emu, fabs(pr(d::F_SHI + s) * pr(d::F_ZHI + s) - mu));
+        }
+      }
+      emu = fmax(g_max(g, emu), fmax(e_d, e_p));
+      if (emu <= P.kappa_eps * mu && mu > P.tol / 10.0) {
+        mu = fmax(P.tol / 10.0, fmin(P.kappa_mu * mu, mu * sqrt(mu)));
+        tau = fmax(P.tau_min, 1.0 - mu);
+        nfilt = 0;
+      } else break;
+    }
+    // ---- slot weights: Sigma, mu/s_lo - mu/s_hi; distance row: capped split.  1/s -> F_A, F_B
+    KV r;
+    {
+      double sa[d::NS], sb[d::NS];
+      LUNR for (int s = 0; s < d::NS; s++) {
+        sa[s] = 0.0; sb[s] = 0.0;
+        if (l_slot_valid<C>(s, g)) {
+          const bool vhi = s != d::SD;
+          const double rlo = l_rcp(pr(d::F_SLO + s)), rhi = l_rcp(pr(d::F_SHI + s));
+          pr(d::F_A + s) = rlo; pr(d::F_B + s) = rhi;
+          sa[s] = pr(d::F_ZLO + s) * rlo + pr(d::F_ZHI + s) * rhi;
+          sb[s] = mu * rlo - (vhi ? mu * rhi : 0.0);
+        }
+      }
+      {
+        const double sg = sa[d::SD];
+        const bool cap = sg > P.sigma_cap;
+        H.sc = fmin(sg, P.sigma_cap); H.capped = cap ? 1 : 0; H.srinv = cap ? l_rcp(sg - H.sc) : 0.0;
+      }
+      l_assemble<C, true>(g, P, c, sa, P.rho_lambda, zd, H);
+      double wd;
+      l_gather<C, true>(g, sb, H.gv, r, wd);
+      LUNR for (int i = 0; i < 4; i++) { r.xs[i] -= gfy.xs[i]; r.lm[i] = (i < C) ? r.lm[i] - gfy.lm[i] : 0.0; r.pi[i] = -re_pi[i]; }
+      LUNR for (int a = 0; a < 2; a++) { r.us[a] -= gfy.us[a]; r.nu[a] = -re_nu[a]; }
+      r.dl = wd - gfy.dl; r.eta = -re_eta;
+    }
+    // ---- factorisation with inertia correction (Ipopt algorithm IC)
+    double dw = 0.0;
+    LaneBorder bf;
+    {
+      bool ok = false;
+      for (;;) {
+        info.n_fact++;
+        ok = l_riccati<C, false>(g, P, c, H, dw, f);
+        if (ok) ok = l_border_factor<C>(g, P, c, H, f, dw, pr, bf);
+        if (ok) break;
+        if (dw == 0.0) dw = (dw_last == 0.0) ? P.dw_first : fmax(P.dw_min, P.kw_minus * dw_last);
+        else dw *= (first_ic && dw_last == 0.0) ? P.kw_plus_first : P.kw_plus;
+        if (dw > P.dw_max) break;
+      }
+      if (!ok) { info.status = 3; return true; }
+      if (dw > 0.0) { dw_last = dw; first_ic = false; }
+    }
+    KV dd; double tb[4];
+    l_kkt_solve_border<C>(g, P, c, H, f, dw, pr, bf, r, dd, tb);
+#ifdef CBF_DBGBUF
+    if (it <= 3) {
+      LANE_LOG4(2000.0 + it);
+      for (int i = 0; i < 4; i++) LANE_LOG4(H.hx[i]);
+      LANE_LOG4(H.hxy); LANE_LOG4(H.hu[0]); LANE_LOG4(H.hu[1]); LANE_LOG4(H.hxu[0]); LANE_LOG4(H.hxu[1]);
+      for (int i = 0; i < 4; i++) LANE_LOG4(H.hl[i]);
+      LANE_LOG4(H.bd[0]); LANE_LOG4(H.bd[1]); LANE_LOG4(H.hd); LANE_LOG4(H.gv[0]); LANE_LOG4(H.gv[1]); LANE_LOG4(H.sc); LANE_LOG4(H.srinv); LANE_LOG4((double)H.capped);
+      LANE_LOG4(3000.0);
+      for (int i = 0; i < 10; i++) LANE_LOG4(f.Pn[i]);
+      for (int i = 0; i < 4 * (C - 1); i++) LANE_LOG4(f.K[i]);
+      for (int i = 0; i < 4 * (C - 1); i++) LANE_LOG4(f.St[i]);
+      LANE_LOG4(f.Lc[0]);
+      LANE_LOG4(4000.0);
+      for (int i = 0; i < 10; i++) LANE_LOG4(bf.L[i]);
+      for (int i = 0; i < 4; i++) { LANE_LOG4(bf.Tic[i]); LANE_LOG4(bf.cb[i]); LANE_LOG4((double)bf.cap[i]); }
+      LANE_LOG4(bf.den);
+      LANE_LOG4(5000.0);
+      for (int i = 0; i < 4; i++) { LANE_LOG4(r.xs[i]); LANE_LOG4(r.lm[i]); LANE_LOG4(r.pi[i]); }
+      LANE_LOG4(r.us[0]); LANE_LOG4(r.us[1]); LANE_LOG4(r.nu[0]); LANE_LOG4(r.nu[1]); LANE_LOG4(r.dl); LANE_LOG4(r.eta);
+      LANE_LOG4(6000.0);
+      for (int i = 0; i < 4; i++) { LANE_LOG4(dd.xs[i]); LANE_LOG4(dd.lm[i]); LANE_LOG4(dd.pi[i]); LANE_LOG4(tb[i]); }
+      LANE_LOG4(dd.us[0]); LANE_LOG4(dd.us[1]); LANE_LOG4(dd.nu[0]); LANE_LOG4(dd.nu[1]); LANE_LOG4(dd.dl); LANE_LOG4(dd.eta);
+    }
+#endif
+    // ---- slot steps: de -> F_C, dz_lo -> F_D, dz_hi -> F_E
+    double quad;
+    {
+      double dxp[4]; prev_state(dd, true, dxp);
+      LUNR for (int s = 0; s < d::NS; s++) {
+        if (l_slot_valid<C>(s, g)) {
+          const bool vhi = s != d::SD;
+          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+          const double rlo = pr(d::F_A + s), rhi = pr(d::F_B + s);
+          const double de = (s == d::SD) ? H.gv[0] * dd.xs[0] + H.gv[1] * dd.xs[2] + dd.dl : l_slot_lin<C>(s, dd, dxp);
+          double dzl = (mu - slo * zlo) * rlo - zlo * rlo * de;
+          const double dzh = vhi ? (mu - shi * zhi) * rhi + zhi * rhi * de : 0.0;
+          if (s == d::SD && H.capped) dzl = (mu - slo * zlo) * rlo - H.sc * de - l_sel4(tb, g.j);
+          pr(d::F_C + s) = de; pr(d::F_D + s) = dzl; pr(d::F_E + s) = dzh;
+        }
+      }
+      quad = dd.xs[0] * dd.xs[0] + dd.xs[2] * dd.xs[2];
+    }
+    // ---- iterative refinement on the unreduced Newton system
+    for (int rf = 0; rf < P.max_refine; rf++) {
+      double sa2[d::NS], sb2[d::NS];
+      LUNR for (int s = 0; s < d::NS; s++) {
+        sa2[s] = 0.0; sb2[s] = 0.0;
+        if (l_slot_valid<C>(s, g)) {
+          const bool vhi = s != d::SD;
+          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+          const double de = pr(d::F_C + s), dzl = pr(d::F_D + s), dzh = pr(d::F_E + s);
+          const double rcl = (mu - slo * zlo) - (slo * dzl + zlo * de);
+          const double rch = vhi ? (mu - shi * zhi) - (shi * dzh - zhi * de) : 0.0;
+          sa2[s] = (zlo + dzl) - (zhi + dzh);
+          sb2[s] = rcl * pr(d::F_A + s) - rch * pr(d::F_B + s);
+        }
+      }
+      // rho1 = -(grad f + A'(y+dy) + Htilde dx - J'(z+dz)),  rho2 = -(A (x+dx) - b)
+      KV gd, jz2, rr; double wd2, dpin[4], dxp[4];
+      next_pi(dd, dpin); prev_state(dd, true, dxp);
+      l_grad_Aty<C>(P, c, dd, dd, dpin, false, gd);
+      l_gather<C, true>(g, sa2, H.gv, jz2, wd2);
+      double nres = 0.0;
+      LUNR for (int i = 0; i < 4; i++) {
+        const double ht = c.qw + dw - ((i & 1) ? 0.0 : 2.0 * zd);
+        rr.xs[i] = -(gfy.xs[i] + gd.xs[i] + ht * dd.xs[i] - jz2.xs[i]);
+        nres = fmax(nres, fabs(rr.xs[i]));
+      }
+      LUNR for (int a = 0; a < 2; a++) { rr.us[a] = -(gfy.us[a] + gd.us[a] + (P.Rw + dw) * dd.us[a] - jz2.us[a]); nres = fmax(nres, fabs(rr.us[a])); }
+      LUNR for (int i = 0; i < 4; i++) {
+        rr.lm[i] = (i < C) ? -(gfy.lm[i] + gd.lm[i] + (dw + P.rho_lambda) * dd.lm[i] - jz2.lm[i]) : 0.0;
+        nres = fmax(nres, fabs(rr.lm[i]));
+      }
+      rr.dl = -(gfy.dl + (P.slw + dw) * dd.dl - wd2);
+      nres = fmax(nres, fabs(rr.dl));
+      {
+        double hp[4], hn[2], he;
+        l_eq_residual<C>(P, c, dd, dxp, true, hp, hn, he);
+        LUNR for (int i = 0; i < 4; i++) { rr.pi[i] = -(re_pi[i] + hp[i]); nres = fmax(nres, fabs(rr.pi[i])); }
+        LUNR for (int a = 0; a < 2; a++) { rr.nu[a] = -(re_nu[a] + hn[a]); nres = fmax(nres, fabs(rr.nu[a])); }
+        rr.eta = -(re_eta + he); nres = fmax(nres, fabs(rr.eta));
+      }
+      nres = g_max(g, nres);
+      const double nrhs = fmax(e_d, e_p);
+      LANE_DBG("   refine %d nres %.2e nrhs %.2e\n", rf, nres, nrhs);
+      if (!(nres > fmax(P.refine_rel * nrhs, P.refine_abs))) break;
+      {
+        KV jb; double wdb;
+        l_gather<C, true>(g, sb2, H.gv, jb, wdb);
+        LUNR for (int i = 0; i < 4; i++) { rr.xs[i] += jb.xs[i]; rr.lm[i] += jb.lm[i]; }
+        LUNR for (int a = 0; a < 2; a++) rr.us[a] += jb.us[a];
+        rr.dl += wdb;
+      }
+      KV d2; double tb2[4];
+      l_kkt_solve_border<C>(g, P, c, H, f, dw, pr, bf, rr, d2, tb2);
+      double d2p[4]; prev_state(d2, true, d2p);
+      LUNR for (int s = 0; s < d::NS; s++) {
+        if (l_slot_valid<C>(s, g)) {
+          const bool vhi = s != d::SD;
+          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+          const double rlo = pr(d::F_A + s), rhi = pr(d::F_B + s);
+          const double de = pr(d::F_C + s), dzl = pr(d::F_D + s), dzh = pr(d::F_E + s);
+          const double rcl = (mu - slo * zlo) - (slo * dzl + zlo * de);
+          const double rch = vhi ? (mu - shi * zhi) - (shi * dzh - zhi * de) : 0.0;
+          const double dde = (s == d::SD) ? H.gv[0] * d2.xs[0] + H.gv[1] * d2.xs[2] + d2.dl : l_slot_lin<C>(s, d2, d2p);
+          double cl = rcl * rlo - zlo * rlo * dde;
+          const double ch = vhi ? rch * rhi + zhi * rhi * dde : 0.0;
+          if (s == d::SD && H.capped) cl = rcl * rlo - H.sc * dde - l_sel4(tb2, g.j);
+          pr(d::F_C + s) = de + dde; pr(d::F_D + s) = dzl + cl; pr(d::F_E + s) = dzh + ch;
+        }
+      }
+      LUNR for (int i = 0; i < 4; i++) { dd.xs[i] += d2.xs[i]; dd.lm[i] += d2.lm[i]; dd.pi[i] += d2.pi[i]; }
+      LUNR for (int a = 0; a < 2; a++) { dd.us[a] += d2.us[a]; dd.nu[a] += d2.nu[a]; }
+      dd.dl += d2.dl; dd.eta += d2.eta;
+      quad = dd.xs[0] * dd.xs[0] + dd.xs[2] * dd.xs[2];
+    }
+    // ---- fraction to the boundary: alpha_max = min(1, tau / max_i(-ds_i / s_i))
+    double a_pmax, a_dmax;
+    {
+      double rp = 0.0, rdm = 0.0;
+      LUNR for (int s = 0; s < d::NS; s++) {
+        if (l_slot_valid<C>(s, g)) {
+          const bool vhi = s != d::SD;
+          const double de = pr(d::F_C + s);
+          rp = fmax(rp, -de * pr(d::F_A + s));
+          if (vhi) rp = fmax(rp, de * pr(d::F_B + s));
+          double zq = -pr(d::F_D + s) * l_rcp(pr(d::F_ZLO + s));
+          if (vhi) zq = fmax(zq, -pr(d::F_E + s) * l_rcp(pr(d::F_ZHI + s)));
+          rdm = fmax(rdm, zq);
+        }
+      }
+      rp = g_max(g, rp); rdm = g_max(g, rdm);
+      a_pmax = (rp > tau) ? tau / rp : 1.0; a_dmax = (rdm > tau) ? tau / rdm : 1.0;
+    }
+    LANE_LOG(dw); LANE_LOG(a_pmax); LANE_LOG(a_dmax); LANE_LOG(dd.dl); LANE_LOG(dd.xs[0]); LANE_LOG(dd.us[0]); LANE_LOG(dd.lm[0]); LANE_LOG(dd.pi[0]); LANE_LOG(dd.nu[0]); LANE_LOG(dd.eta);
+    LANE_DBG("   dw %.1e apmax %.3e admax %.3e ddl %.3e\n", dw, a_pmax, a_dmax, dd.dl);
+    // ---- filter line search on phi = f - mu sum log s  (theta = ||A x - b||_1 shrinks by (1 - alpha))
+    double ph, dphi, dQd, gdx;
+    {
+      // f(x) = sum_j x_j (1/2 Q_jj x_j + f_j)   (DV:423-428)
+      double f0 = 0.0, gd = 0.0, qd = 0.0;
+      LUNR for (int i = 0; i < 4; i++) {
+        const double xv = x.xs[i], dv = dd.xs[i], fv = -c.qw * c.xdes[i];
+        f0 += xv * (0.5 * c.qw * xv + fv); gd += (c.qw * xv + fv) * dv; qd += c.qw * dv * dv;
+      }
+      LUNR for (int a = 0; a < 2; a++) { const double xv = x.us[a], dv = dd.us[a]; f0 += xv * (0.5 * P.Rw * xv); gd += P.Rw * xv * dv; qd += P.Rw * dv * dv; }
+      if (g.j == 0) { const double xv = x.dl, dv = dd.dl; f0 += xv * (0.5 * P.slw * xv); gd += P.slw * xv * dv; qd += P.slw * dv * dv; }
+      double prod = 1.0, prod2 = 1.0, dsum = 0.0;
+      LUNR for (int s = 0; s < d::NS; s++) {
+        if (l_slot_valid<C>(s, g)) {
+          const bool vhi = s != d::SD;
+          const double de = pr(d::F_C + s);
+          if (s & 1) prod *= pr(d::F_SLO + s) * pr(d::F_SHI + s); else prod2 *= pr(d::F_SLO + s) * pr(d::F_SHI + s);
+          dsum += de * pr(d::F_A + s) - (vhi ? de * pr(d::F_B + s) : 0.0);
+        }
+      }
+      ph = g_sum(g, f0 - mu * (log(prod) + log(prod2)));
+      gdx = g_sum(g, gd);
+      dphi = gdx - mu * g_sum(g, dsum);
+      dQd = g_sum(g, qd);
+    }
+    double alpha = a_pmax;
+    bool accepted = false, ftype = false;
+    while (alpha >= P.alpha_min) {
+      // phi(x + alpha dx) - phi(x) = alpha g'dx + 1/2 alpha^2 dx'Q dx - mu sum log(s_t / s)
+      double prod = 1.0, prod2 = 1.0;
+      bool pos = true;
+      LUNR for (int s = 0; s < d::NS; s++) {
+        if (l_slot_valid<C>(s, g)) {
+          const bool vhi = s != d::SD;
+          const double et = alpha * pr(d::F_C + s) + ((s == d::SD) ? alpha * alpha * quad : 0.0);
+          const double sl = pr(d::F_SLO + s) + et, sh = vhi ? pr(d::F_SHI + s) - et : 1.0;
+          pos = pos && (sl > 0.0) && (sh > 0.0);
+          const double t = (sl * pr(d::F_A + s)) * (vhi ? sh * pr(d::F_B + s) : 1.0);
+          if (s & 1) prod *= t; else prod2 *= t;
+        }
+      }
+      const bool allpos = g_all(g, pos);
+      const double dlog = g_sum(g, allpos ? log(prod) + log(prod2) : 0.0);
+      if (allpos) {
+        const double tht = (1.0 - alpha) * th;
+        const double dph = alpha * gdx + 0.5 * alpha * alpha * dQd - mu * dlog;
+        const double pht = ph + dph;
+        bool okf = tht <= theta_max;
+        for (int fi = 0; fi < nfilt && okf; fi++)
+          if (tht >= pr(d::F_FILT + 2 * fi) && pht >= pr(d::F_FILT + 2 * fi + 1)) okf = false;
+        if (okf) {
+          const bool sw = dphi < 0.0 && alpha * (dphi * dphi) > th;  // switching condition, s_phi = 2, s_theta = 1, delta = 1
+          if (th <= theta_min && sw) {
+            if (dph - 10.0 * CBF_EPSM * fabs(ph) <= P.eta_phi * alpha * dphi) { accepted = true; ftype = true; }
+          } else if (tht <= (1.0 - P.gamma_theta) * th || dph - 10.0 * CBF_EPSM * fabs(ph) <= -P.gamma_phi * th) {
+            accepted = true; ftype = false;
+          }
+        }
+      }
+      if (accepted) break;
+      alpha *= 0.5;
+    }
+    LANE_LOG(alpha); LANE_LOG(ph); LANE_LOG(dphi);
+    LANE_DBG("   alpha %.3e acc %d ftype %d ph %.10e dphi %.3e\n", alpha, (int)accepted, (int)ftype, ph, dphi);
+    if (!accepted) { info.status = 2; return true; }
+    if (!ftype) {
+      if (nfilt >= P.filter_cap) {
+        for (int t = 0; t < 2 * (P.filter_cap - 1); t++) pr(d::F_FILT + t) = pr(d::F_FILT + t + 2);
+        nfilt--;
+      }
+      pr(d::F_FILT + 2 * nfilt) = (1.0 - P.gamma_theta) * th; pr(d::F_FILT + 2 * nfilt + 1) = ph - P.gamma_phi * th;
+      nfilt++;
+    }
+    // ---- update
+    LUNR for (int i = 0; i < 4; i++) { x.xs[i] += alpha * dd.xs[i]; x.pi[i] += alpha * dd.pi[i]; }
+    LUNR for (int i = 0; i < C; i++) x.lm[i] += alpha * dd.lm[i];
+    LUNR for (int a = 0; a < 2; a++) { x.us[a] += alpha * dd.us[a]; x.nu[a] += alpha * dd.nu[a]; }
+    x.dl += alpha * dd.dl; x.eta += alpha * dd.eta;
+    LUNR for (int s = 0; s < d::NS; s++) {
+      if (l_slot_valid<C>(s, g)) { pr(d::F_ZLO + s) += a_dmax * pr(d::F_D + s); if (s != d::SD) pr(d::F_ZHI + s) += a_dmax * pr(d::F_E + s); }
+    }
+    nl_it = it + 1;
+    return false;
+  }
+};
+
+// ===============================================================================================================
+// One group = one run_NMPC(): load (updateState + planners' outputs), closest obstacle, QP stage, NLP stage,
+// Bezier epilogue, store.  Shared by the CUDA kernel and the tests/emu harness.
+// ===============================================================================================================
+template <int C>
+LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid, Priv pr) {
+  typedef LaneDims<C> d;
+  constexpr int NW = d::NW;
+  LaneSolver<C> S;
+  S.g = grp_make(); S.pr = pr;
+  const Grp& g = S.g;
+  const int j = g.j;
+  const size_t B = (size_t)io.B;
+  S.info.status = 1; S.info.qp_iters = 0; S.info.qp_flag = 3; S.info.nlp_iters = 0; S.info.n_fact = 0; S.info.kkt = 0.0;
+  double abuf_j = 0.0;
+  bool qp_done = true;
+  if (valid) {
+    // ---- load (SoA, one instance; lane j takes stage j)
+    LUNR for (int i = 0; i < 4; i++) { S.c.xdes[i] = io.xdes[(size_t)(4 * j + i) * B + b]; S.c.xin[i] = io.x0[(size_t)i * B + b]; }
+    abuf_j = io.abuf ? io.abuf[(size_t)j * B + b] : 0.0;
+    double feet[8];
+    LUNR for (int t = 0; t < 8; t++) feet[t] = io.feet[(size_t)t * B + b];
+    const int c0 = io.contact[b];
+    // stance matrix (MPC_dist.cpp:1238-1252)
+    LUNR for (int a = 0; a < 2; a++) {
+      if (C == 4) { LUNR for (int i = 0; i < 4; i++) S.c.F[4 * a + i] = feet[4 * a + i]; }
+      else {
+        S.c.F[4 * a] = (c0 == 0) ? feet[4 * a + 1] : feet[4 * a]; S.c.F[4 * a + 1] = (c0 == 0) ? feet[4 * a + 2] : feet[4 * a + 3];
+        S.c.F[4 * a + 2] = 0.0; S.c.F[4 * a + 3] = 0.0;
+      }
+    }
+    LUNR for (int t = 0; t < 6; t++) S.c.D[t] = 0.0;
+    LUNR for (int k = 0; k < 2; k++) LUNR for (int a = 0; a < NW; a++) S.c.D[k * NW + a] = S.c.F[4 * k + a] - S.c.F[4 * k + C - 1];
+    S.c.qw = (j == 3) ? P.Pw : P.Qw;
+    // closest obstacle to the current position: first strict minimum of the Euclidean distance (MPC_dist.cpp:371-396)
+    S.c.ox = 0.0; S.c.oy = 0.0;
+    if (io.mode == 1) {
+      const double px = S.c.xin[0], py = S.c.xin[2];
+      double best = 1000.0; int bi = 0x7fffffff;
+      for (int k = j; k < io.n_obs; k += 4) {
+        const double dx = px - io.obs[(size_t)k * B + b], dy = py - io.obs[(size_t)(io.n_obs + k) * B + b];
+        const double dd = sqrt(l_add_rn(l_mul_rn(dx, dx), l_mul_rn(dy, dy)));
+        if (dd < best) { best = dd; bi = k; }
+      }
+      LUNR for (int m = 1; m < 4; m <<= 1) {
+        const double ob = g_xor(g, best, m); const int oi = (int)g_xor_u(g, (unsigned)bi, m);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (bi == 0x7fffffff) bi = 0;
+      S.c.ox = io.obs[(size_t)bi * B + b]; S.c.oy = io.obs[(size_t)(io.n_obs + bi) * B + b];
+    }
+    if (io.xstart == nullptr) {
+      qp_done = S.qp_init(P);
+    } else {
+      LUNR for (int i = 0; i < 4; i++) { S.x.xs[i] = io.xstart[(size_t)(4 * j + i) * B + b]; S.x.lm[i] = (i < C) ? io.xstart[(size_t)(24 + C * j + i) * B + b] : 0.0; S.x.pi[i] = 0.0; }
+      LUNR for (int a = 0; a < 2; a++) { S.x.us[a] = io.xstart[(size_t)(16 + 2 * j + a) * B + b]; S.x.nu[a] = 0.0; }
+      S.x.dl = io.xstart[(size_t)(24 + 4 * C) * B + b]; S.x.eta = 0.0;
+      S.info.qp_flag = 0;
+    }
+  }
+  // ---- QP stage: the groups of a warp iterate together until the last one has finished
+  for (;;) {
+    const bool act = valid && !qp_done;
+    if (!w_any(act)) break;
+    if (act) qp_done = S.qp_iter(P);
+  }
+  bool nl_done = true;
+  if (valid) {
+    if (io.xqp) {
+      LUNR for (int i = 0; i < 4; i++) io.xqp[(size_t)(4 * j + i) * B + b] = S.x.xs[i];
+      LUNR for (int a = 0; a < 2; a++) io.xqp[(size_t)(16 + 2 * j + a) * B + b] = S.x.us[a];
+    }
+    if (io.mode == 1) { S.nlp_init(P); nl_done = false; }
+    else S.qp_final_kkt(P);
+  }
+  // ---- NLP stage
+  for (;;) {
+    const bool act = valid && !nl_done;
+    if (!w_any(act)) break;
+    if (act) nl_done = S.nlp_iter(P);
+  }
+  if (!valid) return;
+  // ---- store
+  if (io.X) { LUNR for (int i = 0; i < 4; i++) io.X[(size_t)(4 * j + i) * B + b] = S.x.xs[i]; }
+  if (io.U) { LUNR for (int a = 0; a < 2; a++) io.U[(size_t)(2 * j + a) * B + b] = S.x.us[a]; }
+  if (io.lam) {
+    LUNR for (int i = 0; i < C; i++) io.lam[(size_t)(C * j + i) * B + b] = S.x.lm[i];
+    LUNR for (int i = 0; i < 4 - C; i++) io.lam[(size_t)(4 * C + (4 - C) * j + i) * B + b] = 0.0;
+  }
+  // Bezier fit  alpha = Y Minv'   (MPC_dist.cpp:784-855, effective semantics): lane r fits state row r
+  {
+    double Y[5];
+    Y[0] = abuf_j;
+    LUNR for (int st = 0; st < 4; st++) {
+      double v = 0.0;
+      LUNR for (int t = 0; t < 4; t++) { const double w = g_idx(g, S.x.xs[t], st); if (t == j) v = w; }
+      Y[1 + st] = v;
+    }
+    LUNR for (int jj = 0; jj < 5; jj++) {
+      double s = 0.0;
+      LUNR for (int i = 0; i < 5; i++) s += P.minv[5 * jj + i] * Y[i];
+      if (io.alpha) io.alpha[(size_t)(5 * j + jj) * B + b] = s;
+    }
+    if (io.abuf_next) io.abuf_next[(size_t)j * B + b] = Y[4];
+  }
+  // active-set mask in the reference's row numbering (DESIGN.md row map): bit set <=> z > s
+  unsigned w[4] = {0u, 0u, 0u, 0u};
+  {
+    const bool nlp = io.mode == 1;
+    LUNR for (int s = 0; s < d::NS; s++) {
+      if (l_slot_valid<C>(s, g) && (s < d::NSQP || nlp)) {
+        int rlo = -1, rhi = -1;
+        if (s < d::SU) { rhi = 12 + 4 * j + s; rlo = 28 + 4 * j + s; }
+        else if (s < d::SL) { rhi = 44 + 2 * j + (s - d::SU); rlo = 52 + 2 * j + (s - d::SU); }
+        else if (s < d::SF) { rlo = 60 + C * j + (s - d::SL); rhi = 60 + 4 * C + C * j + (s - d::SL); }
+        else if (s < d::SV) { rhi = 2 * (j - 1) + (s - d::SF); rlo = 6 + rhi; }
+        else if (s < d::SD) { const int q = (s - d::SV) ? 4 + j : j; rhi = d::MQP + 4 + q; rlo = d::MQP + 12 + q; }
+        else { rlo = d::MQP + j; }
+        if (rlo >= 0 && pr(d::F_ZLO + s) > pr(d::F_SLO + s)) w[rlo >> 5] |= 1u << (rlo & 31);
+        if (rhi >= 0 && s != d::SD && pr(d::F_ZHI + s) > pr(d::F_SHI + s)) w[rhi >> 5] |= 1u << (rhi & 31);
+      }
+    }
+    LUNR for (int k = 0; k < 4; k++) w[k] = g_or(g, w[k]);
+  }
+  if (j == 0) {
+    if (io.slack) io.slack[b] = S.x.dl;
+    if (io.kkt) io.kkt[b] = S.info.kkt;
+    if (io.status) io.status[b] = S.info.status;
+    if (io.qp_iters) io.qp_iters[b] = S.info.qp_iters;
+    if (io.nlp_iters) io.nlp_iters[b] = S.info.nlp_iters;
+    if (io.n_fact) io.n_fact[b] = S.info.n_fact;
+    if (io.active) {
+      io.active[b] = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+      io.active[B + b] = (unsigned long long)w[2] | ((unsigned long long)w[3] << 32);
+    }
+  }
+}
+
+// contact pattern -> number of stance feet: 4, 2 (a diagonal pair) or -1 (MPC_dist.cpp:1238-1252)
+LDEV int lane_classify(const BatchIO& io, int b) {
+  const size_t B = (size_t)io.B;
+  const int c0 = io.contact[b], c1 = io.contact[B + b], c2 = io.contact[2 * B + b], c3 = io.contact[3 * B + b];
+  const int csum = c0 + c1 + c2 + c3;
+  if (csum == 4) return 4;
+  if (csum == 2 && (c0 == 0 || c0 == 1)) return 2;
+  return -1;
+}
+LDEV void lane_store_bad(const BatchIO& io, int b) {
+  const size_t B = (size_t)io.B;
+  if (io.status) io.status[b] = 4;
+  if (io.kkt) io.kkt[b] = 0.0;
+  if (io.qp_iters) io.qp_iters[b] = 0;
+  if (io.nlp_iters) io.nlp_iters[b] = 0;
+  if (io.n_fact) io.n_fact[b] = 0;
+  if (io.slack) io.slack[b] = 0.0;
+  if (io.active) { io.active[b] = 0ull; io.active[B + b] = 0ull; }
+}

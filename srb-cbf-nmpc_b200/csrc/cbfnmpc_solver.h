@@ -16,18 +16,9 @@
 // lane); <-> 28 equality rows; Riccati matrix products use up to 28 lanes; right-hand sides run 4 lanes per RHS.
 #pragma once
 #include "warp_prims.h"
+#include "cbfnmpc_types.h"
 
-struct KParams {
-  double a11, a12, a21, a22, bp, bv;  // per-axis LIP: A2 = [[a11,a12],[a21,a22]], B2 = [bp; bv]  (MPC_dist.cpp:117-127)
-  double Qw, Pw, Rw, slw, fb, box, vmax, eps;
-  double minv[25];                    // inverse Bernstein matrix (row-major)                     (MPC_dist.cpp:803-807)
-  double qp_reltol, qp_abstol;
-  double tol, mu_init, kappa_eps, kappa_mu, tau_min, push, gamma_theta, gamma_phi, eta_phi, kappa_sigma, alpha_min;
-  double dw_first, dw_min, kw_minus, kw_plus, kw_plus_first, dw_max, rho_lambda, z_div, sigma_cap, refine_rel, refine_abs;
-  int qp_maxit, max_iter, filter_cap, max_refine;
-};
 
-#define CBF_EPSM 2.220446049250313e-16
 #if defined(CBF_HOST_EMU) && defined(CBF_TRACE)
 #include <stdio.h>
 #define CBF_DBG(...) do { if (lane_id() == 0) fprintf(stderr, __VA_ARGS__); } while (0)
