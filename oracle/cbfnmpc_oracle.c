@@ -13,7 +13,7 @@ static const int VEL_IDX[8] = {1, 5, 9, 13, 3, 7, 11, 15}; /* include/dec_vars_c
 
 void orc_default_options(orc_options *o) {
   o->qp_reltol = 1e-6; o->qp_abstol = 1e-6; o->qp_maxit = 25;
-  o->tol = 1e-9; o->mu_init = 0.1; o->kappa_eps = 10.0; o->kappa_mu = 0.2; o->theta_mu = 1.5; o->tau_min = 0.99;
+  o->tol = 3e-9; o->mu_init = 0.1; o->kappa_eps = 10.0; o->kappa_mu = 0.2; o->theta_mu = 1.5; o->tau_min = 0.99;
   o->push = 1e-2; o->gamma_theta = 1e-5; o->gamma_phi = 1e-5; o->delta = 1.0; o->s_theta = 1.1; o->s_phi = 2.3;
   o->eta_phi = 1e-4; o->kappa_sigma = 1e10; o->alpha_min = 1e-10;
   o->dw_first = 1e-4; o->dw_min = 1e-20; o->kw_minus = 1.0 / 3.0; o->kw_plus = 8.0; o->kw_plus_first = 100.0;

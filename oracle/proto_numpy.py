@@ -244,7 +244,7 @@ class NlpProblem:
         return self.Q @ x + self.f
 
 
-DEFAULT_OPTS = dict(tol=1e-9, mu_init=0.1, kappa_eps=10.0, kappa_mu=0.2, theta_mu=1.5, tau_min=0.99,
+DEFAULT_OPTS = dict(tol=3e-9, mu_init=0.1, kappa_eps=10.0, kappa_mu=0.2, theta_mu=1.5, tau_min=0.99,
                     s_push=1e-2, max_iter=200, gamma_theta=1e-5, gamma_phi=1e-5, delta=1.0, s_theta=1.1,
                     s_phi=2.3, eta_phi=1e-4, kappa_sigma=1e10, alpha_min=1e-10, filter_cap=8,
                     dw_first=1e-4, dw_min=1e-20, kw_minus=1.0 / 3, kw_plus=8.0, kw_plus_first=100.0,

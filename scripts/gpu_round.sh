@@ -12,6 +12,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_launch_$TAG.log
 python bench_quick.py 4096 > gpurun_out/plainq_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:cbfnmpc_solve -s 5 -c 1 -f -o gpurun_out/prof_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:cbfnmpc_lane -s 5 -c 1 -f -o gpurun_out/prof_$TAG \
     python bench_quick.py 4096 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_full_$TAG.log

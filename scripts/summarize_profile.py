@@ -50,8 +50,8 @@ if os.path.exists(rep):
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__average_warp_latency_per_inst_issued.ratio",
             "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
-            "sm__icc_requests_lookup_hit.sum", "sm__icc_requests_lookup_miss.sum"]
-    out_md.append("## `ncu --set full --clock-control none` of one `cbfnmpc_solve_kernel` launch (4096 cfg-3 instances, `bench_quick.py 4096`)\n")
+            "sm__icc_request_hit_rate.pct", "sm__cycles_active.avg"]
+    out_md.append("## `ncu --set full --clock-control none` of one `cbfnmpc_lane_kernel` launch (4096 cfg-3 instances, `bench_quick.py 4096`)\n")
     out_md.append("| metric | value | unit |\n|---|---|---|")
     summary["metrics"] = {}
     for k in keys:
@@ -95,7 +95,7 @@ if os.path.exists(rep):
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 if "traffic_bytes" in summary:
     json.dump({"traffic_bytes": summary["traffic_bytes"], "read_bytes": summary["traffic_read_bytes"], "write_bytes": summary["traffic_write_bytes"],
-               "source": "profiles/%s_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one cbfnmpc_solve_kernel launch (4096 cfg-3 instances, ncu --set full)" % tag},
+               "source": "profiles/%s_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one cbfnmpc_lane_kernel launch (4096 cfg-3 instances, ncu --set full)" % tag},
               open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 open(os.path.join(ROOT, "profiles", "%s_ncu_summary.md" % tag), "w").write("\n".join(out_md) + "\n")
 json.dump(summary, open(os.path.join(ROOT, "profiles", "%s_ncu_summary.json" % tag), "w"), indent=1)

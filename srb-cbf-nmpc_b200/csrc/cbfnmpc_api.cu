@@ -5,34 +5,13 @@
 #include <string>
 #include <vector>
 #include "cbfnmpc_host.h"
-#include "cbfnmpc_instance.h"
 #ifndef LANE_NT
 #define LANE_NT 32  // one warp (8 instances) per CTA; 4 CTAs of 48.5 KB shared memory fit an SM
 #endif
 #include "cbfnmpc_lane.h"
 
-// One CTA = CBF_WARPS warps = CBF_WARPS instances kept in lockstep; CBF_WARPS * CBF_MIN_BLOCKS warps resident per SM.
-// 28 x 1 fills an SM's 227 KB of shared memory (28 x 7.6 KB workspaces) at 72 registers per thread (tuned on B200).
-#ifndef CBF_WARPS
-#define CBF_WARPS 28
-#endif
-#ifndef CBF_MIN_BLOCKS
-#define CBF_MIN_BLOCKS 1
-#endif
-#define WARPS_PER_CTA CBF_WARPS
-
-// One warp per instance; the CTA only shares the launch.  Dynamic shared memory: WARPS_PER_CTA workspaces.
-__global__ void __launch_bounds__(32 * WARPS_PER_CTA, CBF_MIN_BLOCKS) cbfnmpc_solve_kernel(const __grid_constant__ KParams P,
-                                                                          const __grid_constant__ BatchIO io) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  WSB* wsall = reinterpret_cast<WSB*>(smem_raw);
-  const int warp = threadIdx.x >> 5;
-  const int b = blockIdx.x * WARPS_PER_CTA + warp;
-  solve_warp(wsall[warp], P, io, b);
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// Lane-per-stage path (cbfnmpc_lane.h): one instance = 4 adjacent lanes, 8 instances per warp, one warp per CTA.
+// The solver (cbfnmpc_lane.h): one instance = 4 adjacent lanes, 8 instances per warp, one warp per CTA.
 // A pre-pass sorts the instances by stance class (4 feet / diagonal pair) so that every warp runs one template
 // instantiation; the order inside a class is the batch order (deterministic).
 // ---------------------------------------------------------------------------------------------------------
@@ -126,7 +105,6 @@ struct cbfnmpc_ctx {
   double* d_xstart;              // 41 (dense entry point)
   int* d_perm;                   // 2 * max_batch + 2: class lists + counts (grown on demand for device-pointer batches)
   int perm_cap;
-  bool use_warp_kernel;          // CBFNMPC_KERNEL=warp: the v3 warp-per-instance kernel (A/B measurement only)
 };
 
 extern "C" {
@@ -158,9 +136,6 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
   CK(cudaMalloc(&c->d_xstart, sizeof(double) * 41));
   CK(cudaMalloc(&c->d_perm, sizeof(int) * (2 * (size_t)max_batch + 2)));
   c->perm_cap = max_batch;
-  const char* kn = getenv("CBFNMPC_KERNEL");
-  c->use_warp_kernel = kn && std::string(kn) == "warp";
-  CK(cudaFuncSetAttribute(cbfnmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * sizeof(WSB))));
   CK(cudaFuncSetAttribute(cbfnmpc_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LANE_NPRIV * LANE_NT * sizeof(double))));
   *out = c;
   return CBFNMPC_OK;
@@ -203,16 +178,6 @@ static int launch(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const c
   io.abuf_next = out->alpha_buf_next; io.kkt = out->kkt; io.status = out->status; io.qp_iters = out->qp_iters;
   io.nlp_iters = out->nlp_iters; io.n_fact = out->n_fact; io.active = (unsigned long long*)out->active;
   io.B = B; io.mode = mode;
-  if (c->use_warp_kernel) {
-    const int grid = (B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    CK(cudaEventRecord(c->ev0, st));
-    cbfnmpc_solve_kernel<<<grid, 32 * WARPS_PER_CTA, WARPS_PER_CTA * sizeof(WSB), st>>>(c->kp, io);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev1, st));
-    c->timed = true;
-    c->launches++;
-    return CBFNMPC_OK;
-  }
   if (B > c->perm_cap) {  // device-pointer batches larger than max_batch: grow the class lists
     CK(cudaStreamSynchronize(st));
     CK(cudaFree(c->d_perm));
@@ -221,9 +186,9 @@ static int launch(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const c
   }
   int* counts = c->d_perm + 2 * (size_t)c->perm_cap;
   const int warps = (B + 7) / 8 + 1, wpc = LANE_NT / 32;
-  CK(cudaEventRecord(c->ev0, st));
   cbfnmpc_classify_kernel<<<1, 1024, 0, st>>>(io, c->d_perm, counts);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev0, st));  // the event pair brackets the solve kernel alone
   cbfnmpc_lane_kernel<<<(warps + wpc - 1) / wpc, LANE_NT, LANE_NPRIV * LANE_NT * sizeof(double), st>>>(c->kp, io, c->d_perm, counts);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev1, st));

@@ -16,7 +16,7 @@ static inline void host_default_gains(cbfnmpc_gains* g) {
 
 static inline void host_default_options(cbfnmpc_options* o) {
   o->qp_reltol = 1e-6; o->qp_abstol = 1e-6; o->qp_maxit = 25;            // iSWIFT GlobalOptions.h:23-26
-  o->tol = 1e-9; o->mu_init = 0.1; o->kappa_eps = 10.0; o->kappa_mu = 0.2; o->tau_min = 0.99; o->push = 1e-2;
+  o->tol = 3e-9; o->mu_init = 0.1; o->kappa_eps = 10.0; o->kappa_mu = 0.2; o->tau_min = 0.99; o->push = 1e-2;  // tol: see DESIGN.md 4
   o->gamma_theta = 1e-5; o->gamma_phi = 1e-5; o->eta_phi = 1e-4; o->kappa_sigma = 1e10; o->alpha_min = 1e-10;
   o->dw_first = 1e-4; o->dw_min = 1e-20; o->kw_minus = 1.0 / 3.0; o->kw_plus = 8.0; o->kw_plus_first = 100.0;
   o->dw_max = 1e40; o->rho_lambda = 1e-6; o->z_div = 1e13;
@@ -73,4 +73,16 @@ static inline void host_fill_kparams(const cbfnmpc_gains* g, const cbfnmpc_optio
   P->rho_lambda = o->rho_lambda; P->z_div = o->z_div; P->sigma_cap = o->sigma_cap; P->refine_rel = o->refine_rel;
   P->refine_abs = o->refine_abs; P->max_iter = o->max_iter; P->filter_cap = o->filter_cap > 8 ? 8 : o->filter_cap;
   P->max_refine = o->max_refine;
+  for (int k = 0; k < 2; k++) {  // slots: X 4 | U 2 | lambda C | friction 2 | velocity 2 | distance 1
+    const int C = k == 0 ? 4 : 2;
+    for (int s = 0; s < 16; s++) {
+      double lo = 0.0, hi = 0.0;
+      if (s < 6) { lo = -P->box; hi = P->box; }
+      else if (s < 6 + C) { lo = 0.0; hi = 1.0; }
+      else if (s < 8 + C) { lo = -P->fb; hi = P->fb; }
+      else if (s < 10 + C) { lo = -P->vmax; hi = P->vmax; }
+      else if (s < 11 + C) { lo = P->eps; hi = 0.0; }
+      P->slot_lo[k][s] = lo; P->slot_hi[k][s] = hi;
+    }
+  }
 }

@@ -75,10 +75,13 @@ struct LaneDims {
   static constexpr int NW = C - 1, NR = NW * (NW + 1) / 2, MQP = 60 + 8 * C;
   // two-sided slots of one lane
   static constexpr int SX = 0, SU = 4, SL = 6, SF = 6 + C, SV = 8 + C, SD = 10 + C, NS = 11 + C, NSQP = 8 + C;
-  // thread-private shared-memory fields: 10 per slot, then the border vectors and the filter
-  static constexpr int F_SLO = 0, F_SHI = NS, F_ZLO = 2 * NS, F_ZHI = 3 * NS, F_A = 4 * NS, F_B = 5 * NS, F_C = 6 * NS, F_D = 7 * NS,
-                       F_E = 8 * NS, F_G = 9 * NS;
-  static constexpr int F_PVB = 10 * NS;        // 4 border columns x 4
+  // thread-private shared-memory fields.  QP stage: 12 per slot, stride NSQP; NLP stage: 11 per slot, stride NS (the two
+  // stages never overlap); then the border vectors and the filter.
+  static constexpr int Q_SLO = 0, Q_SHI = NSQP, Q_ZLO = 2 * NSQP, Q_ZHI = 3 * NSQP, Q_A = 4 * NSQP, Q_B = 5 * NSQP, Q_C = 6 * NSQP,
+                       Q_D = 7 * NSQP, Q_E = 8 * NSQP, Q_G = 9 * NSQP, Q_EV = 10 * NSQP, Q_DE = 11 * NSQP, Q_END = 12 * NSQP;
+  static constexpr int N_SLO = 0, N_SHI = NS, N_ZLO = 2 * NS, N_ZHI = 3 * NS, N_A = 4 * NS, N_B = 5 * NS, N_C = 6 * NS, N_D = 7 * NS,
+                       N_E = 8 * NS, N_G = 9 * NS, N_EV = 10 * NS, N_END = 11 * NS;
+  static constexpr int F_PVB = Q_END > N_END ? Q_END : N_END;  // 4 border columns x 4
   static constexpr int F_KVB = F_PVB + 16;     // 4 border columns x NW (3)
   static constexpr int F_FILT = F_KVB + 12;    // 8 filter entries x 2
   static constexpr int NPRIV = F_FILT + 16;
@@ -88,12 +91,20 @@ constexpr int LANE_NPRIV = LaneDims<4>::NPRIV;
 // ---------------------------------------------------------------------------------------------------------------
 // small dense pieces
 // ---------------------------------------------------------------------------------------------------------------
-// FLOOR (QP stage): a pivot that rounding has pushed below CHOL_FLOOR * diagonal is replaced by that value instead of
-// failing.  This happens when every lambda of a stage is strictly inside (0, 1): the reduced Hessian D'N D + Sigma_lambda
-// then has one direction (F n = 0, 1'n = 0) whose curvature is only Sigma_lambda ~ mu / s^2, far below the rounding error
-// of D'N D.  The direction does not move X, U or the objective; flooring only damps the motion of lambda inside the
-// optimal face (iSWIFT's LDL' on the unreduced KKT matrix does not see this cancellation, Auxilary.c:332-420).
+// Pivot rule of the 3 x 3 Cholesky.  When every lambda of a stage is strictly inside (0, 1), the reduced Hessian
+// D'N D + Sigma_lambda has one direction (F n = 0, 1'n = 0) whose curvature is only Sigma_lambda ~ mu / s^2, below the
+// rounding error of D'N D, so the last pivot comes out as +-1e-13 |R|.  That direction moves neither X, U nor the
+// objective.  A pivot inside the noise window (> -CHOL_NOISE * diagonal) is therefore replaced by CHOL_FLOOR * diagonal
+// in the QP stage (FLOOR; this only damps the motion of lambda inside its optimal face).  The NLP stage reports every
+// non-positive pivot instead and lets the inertia correction add dw I, which is what keeps its line search well scaled.  iSWIFT's LDL' / the oracle's Bunch-Kaufman work on the
+// unreduced KKT matrix and do not meet this cancellation (Auxilary.c:332-420).
 #define CHOL_FLOOR 1e-10
+#define CHOL_NOISE 1e-9
+template <bool FLOOR>
+LDEV double l_pivot(double d, double diag, bool& ok) {
+  ok = ok && (d > (FLOOR ? -CHOL_NOISE * diag : 0.0)) && (d < 1e300);
+  return FLOOR ? fmax(d, CHOL_FLOOR * diag) : d;
+}
 template <int NW, bool FLOOR>
 LDEV bool l_chol(const double* R, double* L) {  // R packed lower (00,10,11,20,21,22)
   bool ok = true;
@@ -103,14 +114,10 @@ LDEV bool l_chol(const double* R, double* L) {  // R packed lower (00,10,11,20,2
   L[0] = i0;
   if (NW == 3) {
     const double l10 = R[1] * i0, l20 = R[3] * i0;
-    double d1 = R[2] - l10 * l10;
-    if (FLOOR) d1 = fmax(d1, CHOL_FLOOR * R[2]);
-    ok = ok && (d1 > 0.0) && (d1 < 1e300);
+    const double d1 = l_pivot<FLOOR>(R[2] - l10 * l10, R[2], ok);
     const double i1 = l_rsq(d1);
     const double l21 = (R[4] - l20 * l10) * i1;
-    double d2 = R[5] - l20 * l20 - l21 * l21;
-    if (FLOOR) d2 = fmax(d2, CHOL_FLOOR * R[5]);
-    ok = ok && (d2 > 0.0) && (d2 < 1e300);
+    const double d2 = l_pivot<FLOOR>(R[5] - l20 * l20 - l21 * l21, R[5], ok);
     const double i2 = l_rsq(d2);
     L[1] = l10; L[2] = i1; L[3] = l20; L[4] = l21; L[5] = i2;
   }
@@ -528,55 +535,63 @@ LDEV void l_kkt_solve_border(const Grp& g, const KParams& P, const LaneConst& c,
 //   SX i : x_{j+1}[i]            +-box   MD:294-297,317-318        SU a : u_j[a]  +-box
 //   SL i : lambda_j[i] in [0,1]  MD:299-300,320-321                SF a : p_j[a] - u_j[a], +-mu h / sqrt 2 (j >= 1)  MD:278-292,315
 //   SV a : v_{j+1}[a]  +-v_max   DV:270-279,306-317 (NLP only)     SD   : |p_{j+1} - o|^2 + delta >= eps   DV:262-265,299-302 (NLP only)
+// Per-slot numbers live in the thread-private columns.  Everything that is the same formula for every slot runs as a
+// ROLLED loop over the slot index (small code: the kernel is instruction-fetch bound otherwise);
+// only the maps between slots and variables (l_scatter: e = J v, l_gather: J'w, l_assemble) are unrolled.
 // ===============================================================================================================
+#ifndef LSLOT_UNROLL
+#define LSLOT_UNROLL 3
+#endif
+#define LPRAGMA_(x) _Pragma(#x)
+#define LPRAGMA(x) LPRAGMA_(x)
+#define LSLOTS LPRAGMA(unroll LSLOT_UNROLL)
 template <int C> LDEV bool l_slot_valid(int s, const Grp& g) { typedef LaneDims<C> d; return (s >= d::SF && s < d::SF + 2) ? (g.j > 0) : true; }
-template <int C> LDEV void l_slot_bounds(int s, const KParams& P, double& lo, double& hi) {
-  typedef LaneDims<C> d;
-  if (s < d::SL) { lo = -P.box; hi = P.box; }
-  else if (s < d::SF) { lo = 0.0; hi = 1.0; }
-  else if (s < d::SV) { lo = -P.fb; hi = P.fb; }
-  else if (s < d::SD) { lo = -P.vmax; hi = P.vmax; }
-  else { lo = P.eps; hi = 0.0; }
-}
-// linear part of e: v = lane vector, vp = previous lane's xs (x_j)
-template <int C> LDEV double l_slot_lin(int s, const KV& v, const double* vp) {
-  typedef LaneDims<C> d;
-  if (s < d::SU) return v.xs[s];
-  if (s < d::SL) return v.us[s - d::SU];
-  if (s < d::SF) return v.lm[s - d::SL];
-  if (s < d::SV) { const int a = s - d::SF; return vp[2 * a] - v.us[a]; }
-  if (s < d::SD) { const int a = s - d::SV; return v.xs[2 * a + 1]; }
-  return 0.0;
-}
-// acc.(xs,us,lm) = J'w for per-slot weights w (weight of +grad e); wd = sum over the group of the distance-row weights
+template <int C> LDEV double l_slot_lo(const KParams& P, int s) { return P.slot_lo[C == 4 ? 0 : 1][s]; }
+template <int C> LDEV double l_slot_hi(const KParams& P, int s) { return P.slot_hi[C == 4 ? 0 : 1][s]; }
+// e = J v of the linear slots -> field fld (stride-1 slot index); v = lane vector, vp = previous lane's xs (x_j).
+// The distance slot (NLP) is written by the caller.
 template <int C, bool NL>
-LDEV void l_gather(const Grp& g, const double* w, const double* gv, KV& acc, double& wd) {
+LDEV void l_scatter(const Grp& g, const Priv& pr, int fld, const KV& v, const double* vp) {
   typedef LaneDims<C> d;
-  LUNR for (int i = 0; i < 4; i++) acc.xs[i] = w[d::SX + i];
-  LUNR for (int a = 0; a < 2; a++) acc.us[a] = w[d::SU + a] - w[d::SF + a];
-  LUNR for (int i = 0; i < 4; i++) acc.lm[i] = (i < C) ? w[d::SL + i] : 0.0;
-  LUNR for (int a = 0; a < 2; a++) { const double t = g_down(g, w[d::SF + a]); acc.xs[2 * a] += (g.j < 3) ? t : 0.0; }
+  LUNR for (int i = 0; i < 4; i++) pr(fld + d::SX + i) = v.xs[i];
+  LUNR for (int a = 0; a < 2; a++) pr(fld + d::SU + a) = v.us[a];
+  LUNR for (int i = 0; i < C; i++) pr(fld + d::SL + i) = v.lm[i];
+  LUNR for (int a = 0; a < 2; a++) pr(fld + d::SF + a) = vp[2 * a] - v.us[a];
+  if (NL) { LUNR for (int a = 0; a < 2; a++) pr(fld + d::SV + a) = v.xs[2 * a + 1]; }
+}
+// acc.(xs,us,lm) = J'w for the per-slot weights w in field fld (weight of +grad e; 0 in the invalid slots);
+// wd = sum over the group of the distance-row weights
+template <int C, bool NL>
+LDEV void l_gather(const Grp& g, const Priv& pr, int fld, const double* gv, KV& acc, double& wd) {
+  typedef LaneDims<C> d;
+  const double wf0 = pr(fld + d::SF), wf1 = pr(fld + d::SF + 1);
+  LUNR for (int i = 0; i < 4; i++) acc.xs[i] = pr(fld + d::SX + i);
+  acc.us[0] = pr(fld + d::SU) - wf0; acc.us[1] = pr(fld + d::SU + 1) - wf1;
+  LUNR for (int i = 0; i < 4; i++) acc.lm[i] = (i < C) ? pr(fld + d::SL + i) : 0.0;
+  { const double t = g_down(g, wf0); acc.xs[0] += (g.j < 3) ? t : 0.0; }
+  { const double t = g_down(g, wf1); acc.xs[2] += (g.j < 3) ? t : 0.0; }
   wd = 0.0;
   if (NL) {
-    LUNR for (int a = 0; a < 2; a++) { acc.xs[2 * a + 1] += w[d::SV + a]; acc.xs[2 * a] += gv[a] * w[d::SD]; }
-    wd = g_sum(g, w[d::SD]);
+    const double wdj = pr(fld + d::SD);
+    LUNR for (int a = 0; a < 2; a++) { acc.xs[2 * a + 1] += pr(fld + d::SV + a); acc.xs[2 * a] += gv[a] * wdj; }
+    wd = g_sum(g, wdj);
   }
 }
-// stage Hessian blocks from the slot weights sa (Sigma); NL: distance-row data already in H (gv, sc, zd)
+// stage Hessian blocks from the slot weights Sigma in field fld; NL: distance-row data already in H (gv, sc, zd)
 template <int C, bool NL>
-LDEV void l_assemble(const Grp& g, const KParams& P, const LaneConst& c, const double* sa, double rho, double zd, LaneHess& H) {
+LDEV void l_assemble(const Grp& g, const KParams& P, const LaneConst& c, const Priv& pr, int fld, double rho, double zd, LaneHess& H) {
   typedef LaneDims<C> d;
-  LUNR for (int i = 0; i < 4; i++) H.hx[i] = c.qw + sa[d::SX + i];
+  LUNR for (int i = 0; i < 4; i++) H.hx[i] = c.qw + pr(fld + d::SX + i);
   LUNR for (int a = 0; a < 2; a++) {
-    const double sf = sa[d::SF + a];
-    H.hu[a] = P.Rw + sa[d::SU + a] + sf;
+    const double sf = pr(fld + d::SF + a);
+    H.hu[a] = P.Rw + pr(fld + d::SU + a) + sf;
     H.hxu[a] = -sf;
     const double t = g_down(g, sf);
     H.hx[2 * a] += (g.j < 3) ? t : 0.0;
   }
-  LUNR for (int i = 0; i < 4; i++) H.hl[i] = (i < C) ? rho + sa[d::SL + i] : 0.0;
+  LUNR for (int i = 0; i < 4; i++) H.hl[i] = (i < C) ? rho + pr(fld + d::SL + i) : 0.0;
   if (NL) {
-    LUNR for (int a = 0; a < 2; a++) { H.hx[2 * a + 1] += sa[d::SV + a]; H.hx[2 * a] += H.sc * H.gv[a] * H.gv[a] - 2.0 * zd; H.bd[a] = H.sc * H.gv[a]; }
+    LUNR for (int a = 0; a < 2; a++) { H.hx[2 * a + 1] += pr(fld + d::SV + a); H.hx[2 * a] += H.sc * H.gv[a] * H.gv[a] - 2.0 * zd; H.bd[a] = H.sc * H.gv[a]; }
     H.hxy = H.sc * H.gv[0] * H.gv[1];
     H.hd = P.slw + g_sum(g, H.sc);
   } else {
@@ -605,24 +620,43 @@ struct LaneSolver {
 
   // =============================================================================================================
   // Stage 1: QP, iSWIFT restated (Prime.c:127-230; kkt_initialize Auxilary.c:680-755)
+  // Slot fields (stride NSQP): SLO SHI ZLO ZHI | A = 1/s_lo  B = 1/s_hi  C = 1/z_lo  D = 1/z_hi (then the step) |
+  //                            E G = ds dz of the affine step (before that: Sigma, rhs weights) | EV = e(x) | DE = e(dx), weights
   // =============================================================================================================
   double sigma; int qp_it;
+
+  // residual parts shared by qp_iter and qp_final_kkt: -(Px + c + A'y + G'z) and b - Ax; z-weights must be in Q_DE
+  LMEM void qp_dual_eq(const KParams& P, const double* xp, const double* pin, KV& rx, double& acc_rx, double& acc_ry) {
+    KV gfy, jz; double wd;
+    l_grad_Aty<C>(P, c, x, x, pin, true, gfy);
+    l_gather<C, false>(g, pr, d::Q_DE, H.gv, jz, wd);
+    acc_rx = 0.0; acc_ry = 0.0;
+    LUNR for (int i = 0; i < 4; i++) { rx.xs[i] = -(gfy.xs[i] - jz.xs[i]); acc_rx += rx.xs[i] * rx.xs[i]; }
+    LUNR for (int a = 0; a < 2; a++) { rx.us[a] = -(gfy.us[a] - jz.us[a]); acc_rx += rx.us[a] * rx.us[a]; }
+    LUNR for (int i = 0; i < 4; i++) { rx.lm[i] = (i < C) ? -(gfy.lm[i] - jz.lm[i]) : 0.0; acc_rx += rx.lm[i] * rx.lm[i]; }
+    rx.dl = -gfy.dl;
+    if (g.j == 0) acc_rx += rx.dl * rx.dl;
+    double rpi[4], rnu[2], reta;
+    l_eq_residual<C>(P, c, x, xp, false, rpi, rnu, reta);
+    LUNR for (int i = 0; i < 4; i++) { rx.pi[i] = -rpi[i]; acc_ry += rpi[i] * rpi[i]; }
+    LUNR for (int a = 0; a < 2; a++) { rx.nu[a] = -rnu[a]; acc_ry += rnu[a] * rnu[a]; }
+    rx.eta = -reta; acc_ry += reta * reta;
+  }
 
   // initial point.  Returns true when the stage is already finished (factorisation failure).
   LMEM bool qp_init(const KParams& P) {
     // W = I, rhs [-c; b; h]
-    double sa[d::NS], sb[d::NS];
-    LUNR for (int s = 0; s < d::NS; s++) {
-      double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
-      const bool act = s < d::NSQP && l_slot_valid<C>(s, g);
-      sa[s] = act ? 2.0 : 0.0; sb[s] = act ? hi + lo : 0.0;
+    LSLOTS for (int s = 0; s < d::NSQP; s++) {
+      const bool act = l_slot_valid<C>(s, g);
+      pr(d::Q_E + s) = act ? 2.0 : 0.0;
+      pr(d::Q_G + s) = act ? l_slot_hi<C>(P, s) + l_slot_lo<C>(P, s) : 0.0;
     }
     LUNR for (int i = 0; i < 4; i++) { x.xs[i] = 0.0; x.lm[i] = 0.0; x.pi[i] = 0.0; }
     x.us[0] = x.us[1] = 0.0; x.dl = 0.0; x.nu[0] = x.nu[1] = 0.0; x.eta = 0.0;
     H.gv[0] = H.gv[1] = 0.0; H.sc = 0.0; H.srinv = 0.0; H.capped = 0;
-    l_assemble<C, false>(g, P, c, sa, 0.0, 0.0, H);
+    l_assemble<C, false>(g, P, c, pr, d::Q_E, 0.0, 0.0, H);
     KV r, dd; double wd;
-    l_gather<C, false>(g, sb, H.gv, r, wd);
+    l_gather<C, false>(g, pr, d::Q_G, H.gv, r, wd);
     LUNR for (int i = 0; i < 4; i++) r.xs[i] += c.qw * c.xdes[i];
     r.dl = 0.0;
     {
@@ -639,21 +673,25 @@ struct LaneSolver {
     LUNR for (int i = C; i < 4; i++) x.lm[i] = 0.0;
     // slacks and multipliers shifted positive (Auxilary.c:724-746)
     double xp[4]; prev_state(x, false, xp);
-    double rl[d::NSQP], rh[d::NSQP], rmin = 1e300, rmax = -1e300;
-    LUNR for (int s = 0; s < d::NSQP; s++) {
-      double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
-      const double e = l_slot_lin<C>(s, x, xp);
-      rl[s] = e - lo; rh[s] = hi - e;
-      if (l_slot_valid<C>(s, g)) { rmin = fmin(rmin, fmin(rl[s], rh[s])); rmax = fmax(rmax, fmax(rl[s], rh[s])); }
+    l_scatter<C, false>(g, pr, d::Q_EV, x, xp);
+    double rmin = 1e300, rmax = -1e300;
+    LSLOTS for (int s = 0; s < d::NSQP; s++) {
+      if (l_slot_valid<C>(s, g)) {
+        const double e = pr(d::Q_EV + s);
+        const double rl = e - l_slot_lo<C>(P, s), rh = l_slot_hi<C>(P, s) - e;
+        rmin = fmin(rmin, fmin(rl, rh)); rmax = fmax(rmax, fmax(rl, rh));
+      }
     }
     rmin = g_min(g, rmin); rmax = g_max(g, rmax);
     const double ap = -rmin, ad = rmax;
-    LUNR for (int s = 0; s < d::NSQP; s++) {
+    LSLOTS for (int s = 0; s < d::NSQP; s++) {
       const bool act = l_slot_valid<C>(s, g);
-      pr(d::F_SLO + s) = act ? ((ap < 0) ? rl[s] : rl[s] + (1.0 + ap)) : 1.0;
-      pr(d::F_SHI + s) = act ? ((ap < 0) ? rh[s] : rh[s] + (1.0 + ap)) : 1.0;
-      pr(d::F_ZLO + s) = act ? ((ad < 0) ? -rl[s] : -rl[s] + (1.0 + ad)) : 0.0;
-      pr(d::F_ZHI + s) = act ? ((ad < 0) ? -rh[s] : -rh[s] + (1.0 + ad)) : 0.0;
+      const double e = pr(d::Q_EV + s);
+      const double rl = e - l_slot_lo<C>(P, s), rh = l_slot_hi<C>(P, s) - e;
+      pr(d::Q_SLO + s) = act ? ((ap < 0) ? rl : rl + (1.0 + ap)) : 1.0;
+      pr(d::Q_SHI + s) = act ? ((ap < 0) ? rh : rh + (1.0 + ap)) : 1.0;
+      pr(d::Q_ZLO + s) = act ? ((ad < 0) ? -rl : -rl + (1.0 + ad)) : 0.0;
+      pr(d::Q_ZHI + s) = act ? ((ad < 0) ? -rh : -rh + (1.0 + ad)) : 0.0;
     }
     info.qp_flag = 2;
     return false;
@@ -664,69 +702,57 @@ struct LaneSolver {
     if (qp_it >= P.qp_maxit) return true;
     double xp[4], pin[4];
     prev_state(x, false, xp); next_pi(x, pin);
+    l_scatter<C, false>(g, pr, d::Q_EV, x, xp);
     // ---- residuals (computeresiduals, Auxilary.c:524-553)
     KV rx;  // rx.(xs,us,lm,dl) = -(Px + G'z + A'y + c), rx.(pi,nu,eta) = b - Ax
     double sz, mu;
     {
-      double wz[d::NS], acc_rz = 0.0, acc_sz = 0.0;
-      LUNR for (int s = 0; s < d::NS; s++) wz[s] = 0.0;
-      LUNR for (int s = 0; s < d::NSQP; s++) {
+      double acc_rz = 0.0, acc_sz = 0.0;
+      LSLOTS for (int s = 0; s < d::NSQP; s++) {
+        double wz = 0.0;
         if (l_slot_valid<C>(s, g)) {
-          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
-          const double e = l_slot_lin<C>(s, x, xp);
-          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+          const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s);
+          const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
           const double rzh = hi - shi - e, rzl = -lo - slo + e;
           acc_rz += rzh * rzh + rzl * rzl;
           acc_sz += slo * zlo + shi * zhi;
-          wz[s] = zlo - zhi;
+          wz = zlo - zhi;
         }
+        pr(d::Q_DE + s) = wz;
       }
-      KV gfy, jz; double wd;
-      l_grad_Aty<C>(P, c, x, x, pin, true, gfy);
-      l_gather<C, false>(g, wz, H.gv, jz, wd);
-      double acc_rx = 0.0, acc_ry = 0.0;
-      LUNR for (int i = 0; i < 4; i++) { rx.xs[i] = -(gfy.xs[i] - jz.xs[i]); acc_rx += rx.xs[i] * rx.xs[i]; }
-      LUNR for (int a = 0; a < 2; a++) { rx.us[a] = -(gfy.us[a] - jz.us[a]); acc_rx += rx.us[a] * rx.us[a]; }
-      LUNR for (int i = 0; i < 4; i++) { rx.lm[i] = (i < C) ? -(gfy.lm[i] - jz.lm[i]) : 0.0; acc_rx += rx.lm[i] * rx.lm[i]; }
-      rx.dl = -gfy.dl;
-      if (g.j == 0) acc_rx += rx.dl * rx.dl;
-      double rpi[4], rnu[2], reta;
-      l_eq_residual<C>(P, c, x, xp, false, rpi, rnu, reta);
-      LUNR for (int i = 0; i < 4; i++) { rx.pi[i] = -rpi[i]; acc_ry += rpi[i] * rpi[i]; }
-      LUNR for (int a = 0; a < 2; a++) { rx.nu[a] = -rnu[a]; acc_ry += rnu[a] * rnu[a]; }
-      rx.eta = -reta; acc_ry += reta * reta;
+      double acc_rx, acc_ry;
+      qp_dual_eq(P, xp, pin, rx, acc_rx, acc_ry);
       const double nrx = g_sum(g, acc_rx), nry = g_sum(g, acc_ry), nrz = g_sum(g, acc_rz);
       sz = g_sum(g, acc_sz);
       const double lim = P.qp_reltol / sqrt(3.0);
+      LANE_DBG("qp it %d rx %.3e ry %.3e rz %.3e mu %.3e sigma %.3e\n", qp_it, sqrt(nrx), sqrt(nry), sqrt(nrz), sz / d::MQP, sigma);
       if (sqrt(nrx) < lim && sqrt(nrz) < lim && sqrt(nry) < lim && sz / d::MQP < P.qp_abstol) { info.qp_flag = 0; return true; }
       mu = sz / d::MQP;
     }
-    // ---- reciprocals, once per iteration: 1/s -> F_A, F_B ; 1/z -> F_C, F_D
-    LUNR for (int s = 0; s < d::NSQP; s++) {
+    // ---- reciprocals, once per iteration: 1/s -> A, B ; 1/z -> C, D ; predictor weights: Sigma -> E, rhs -> G
+    const bool predictor = sigma > 0.0;
+    LSLOTS for (int s = 0; s < d::NSQP; s++) {
+      double sa = 0.0, sb = 0.0;
       if (l_slot_valid<C>(s, g)) {
-        pr(d::F_A + s) = l_rcp(pr(d::F_SLO + s)); pr(d::F_B + s) = l_rcp(pr(d::F_SHI + s));
-        pr(d::F_C + s) = l_rcp(pr(d::F_ZLO + s)); pr(d::F_D + s) = l_rcp(pr(d::F_ZHI + s));
-      }
-    }
-    KV r, dd;
-    if (sigma > 0.0) {
-      // predictor: W = s/z, ds = -s z, rhs3 = rz - ds/z = rz + s
-      double sa[d::NS], sb[d::NS];
-      LUNR for (int s = 0; s < d::NS; s++) { sa[s] = 0.0; sb[s] = 0.0; }
-      LUNR for (int s = 0; s < d::NSQP; s++) {
-        if (l_slot_valid<C>(s, g)) {
-          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
-          const double e = l_slot_lin<C>(s, x, xp);
-          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
-          const double wl = zlo * pr(d::F_A + s), wh = zhi * pr(d::F_B + s);
+        const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
+        const double isl = l_rcp(slo), ish = l_rcp(shi);
+        pr(d::Q_A + s) = isl; pr(d::Q_B + s) = ish;
+        pr(d::Q_C + s) = l_rcp(zlo); pr(d::Q_D + s) = l_rcp(zhi);
+        if (predictor) {  // W = s/z, ds = -s z, rhs3 = rz - ds/z = rz + s
+          const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s);
+          const double wl = zlo * isl, wh = zhi * ish;
           const double rzh = hi - shi - e, rzl = -lo - slo + e;
-          sa[s] = wl + wh;
-          sb[s] = wh * (rzh + shi) - wl * (rzl + slo);
+          sa = wl + wh;
+          sb = wh * (rzh + shi) - wl * (rzl + slo);
         }
       }
-      l_assemble<C, false>(g, P, c, sa, 0.0, 0.0, H);
+      pr(d::Q_E + s) = sa; pr(d::Q_G + s) = sb;
+    }
+    KV r, dd;
+    if (predictor) {
+      l_assemble<C, false>(g, P, c, pr, d::Q_E, 0.0, 0.0, H);
       double wd;
-      l_gather<C, false>(g, sb, H.gv, r, wd);
+      l_gather<C, false>(g, pr, d::Q_G, H.gv, r, wd);
       LUNR for (int i = 0; i < 4; i++) { r.xs[i] += rx.xs[i]; r.lm[i] += rx.lm[i]; r.pi[i] = rx.pi[i]; }
       LUNR for (int a = 0; a < 2; a++) { r.us[a] += rx.us[a]; r.nu[a] = rx.nu[a]; }
       r.dl = rx.dl; r.eta = rx.eta;
@@ -735,13 +761,13 @@ struct LaneSolver {
       l_kkt_solve_plain<C>(g, P, c, H, f, 0.0, r, dd);
       // affine step: max step lengths (findsteplength, Auxilary.c:271-294) and rho (Auxilary.c:600-609)
       double dxp[4]; prev_state(dd, true, dxp);
+      l_scatter<C, false>(g, pr, d::Q_DE, dd, dxp);
       double rp = 0.0, rdm = 0.0, s_dsz = 0.0, s_sdz = 0.0, s_dsdz = 0.0;
-      LUNR for (int s = 0; s < d::NSQP; s++) {
+      LSLOTS for (int s = 0; s < d::NSQP; s++) {
         if (l_slot_valid<C>(s, g)) {
-          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
-          const double e = l_slot_lin<C>(s, x, xp), de = l_slot_lin<C>(s, dd, dxp);
-          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
-          const double isl = pr(d::F_A + s), ish = pr(d::F_B + s), izl = pr(d::F_C + s), izh = pr(d::F_D + s);
+          const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s), de = pr(d::Q_DE + s);
+          const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
+          const double isl = pr(d::Q_A + s), ish = pr(d::Q_B + s), izl = pr(d::Q_C + s), izh = pr(d::Q_D + s);
           const double wl = zlo * isl, wh = zhi * ish;
           const double rzh = hi - shi - e, rzl = -lo - slo + e;
           const double dzh = wh * (de - (rzh + shi)), dzl = wl * (-de - (rzl + slo));
@@ -749,7 +775,7 @@ struct LaneSolver {
           rp = fmax(rp, fmax(-dsh * ish, -dsl * isl));
           rdm = fmax(rdm, fmax(-dzh * izh, -dzl * izl));
           s_dsz += dsl * zlo + dsh * zhi; s_sdz += slo * dzl + shi * dzh; s_dsdz += dsl * dzl + dsh * dzh;
-          pr(d::F_E + s) = dsl * dzl; pr(d::F_G + s) = dsh * dzh;
+          pr(d::Q_E + s) = dsl * dzl; pr(d::Q_G + s) = dsh * dzh;
         }
       }
       rp = g_max(g, rp); rdm = g_max(g, rdm);
@@ -760,27 +786,26 @@ struct LaneSolver {
       sigma = mr * mr * mr;
       if (sigma < 0.0) sigma = 0.0;
     } else {
-      sigma = 0.0;
-      LUNR for (int s = 0; s < d::NSQP; s++) { pr(d::F_E + s) = 0.0; pr(d::F_G + s) = 0.0; }
+      sigma = 0.0;  // E, G already hold zeros
     }
     // ---- corrector solve with the same factor: ds = -s z - ds_aff dz_aff + sigma mu (form_ds, Auxilary.c:250-267)
     {
-      double sb[d::NS];
-      LUNR for (int s = 0; s < d::NS; s++) sb[s] = 0.0;
-      LUNR for (int s = 0; s < d::NSQP; s++) {
+      const double sm = sigma * mu;
+      LSLOTS for (int s = 0; s < d::NSQP; s++) {
+        double sb = 0.0;
         if (l_slot_valid<C>(s, g)) {
-          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
-          const double e = l_slot_lin<C>(s, x, xp);
-          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
-          const double wl = zlo * pr(d::F_A + s), wh = zhi * pr(d::F_B + s);
+          const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s);
+          const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
+          const double wl = zlo * pr(d::Q_A + s), wh = zhi * pr(d::Q_B + s);
           const double rzh = hi - shi - e, rzl = -lo - slo + e;
-          const double cdl = -slo * zlo - pr(d::F_E + s) + sigma * mu, cdh = -shi * zhi - pr(d::F_G + s) + sigma * mu;
-          const double r3l = rzl - cdl * pr(d::F_C + s), r3h = rzh - cdh * pr(d::F_D + s);
-          sb[s] = wh * r3h - wl * r3l;
+          const double cdl = -slo * zlo - pr(d::Q_E + s) + sm, cdh = -shi * zhi - pr(d::Q_G + s) + sm;
+          const double r3l = rzl - cdl * pr(d::Q_C + s), r3h = rzh - cdh * pr(d::Q_D + s);
+          sb = wh * r3h - wl * r3l;
         }
+        pr(d::Q_DE + s) = sb;
       }
       double wd;
-      l_gather<C, false>(g, sb, H.gv, r, wd);
+      l_gather<C, false>(g, pr, d::Q_DE, H.gv, r, wd);
       LUNR for (int i = 0; i < 4; i++) { r.xs[i] += rx.xs[i]; r.lm[i] += rx.lm[i]; r.pi[i] = rx.pi[i]; }
       LUNR for (int a = 0; a < 2; a++) { r.us[a] += rx.us[a]; r.nu[a] = rx.nu[a]; }
       r.dl = rx.dl; r.eta = rx.eta;
@@ -789,36 +814,38 @@ struct LaneSolver {
     double ap, ad;
     {
       double dxp[4]; prev_state(dd, true, dxp);
+      l_scatter<C, false>(g, pr, d::Q_DE, dd, dxp);
+      const double sm = sigma * mu;
       double rp = 0.0, rdm = 0.0;
-      LUNR for (int s = 0; s < d::NSQP; s++) {
+      LSLOTS for (int s = 0; s < d::NSQP; s++) {
         if (l_slot_valid<C>(s, g)) {
-          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
-          const double e = l_slot_lin<C>(s, x, xp), de = l_slot_lin<C>(s, dd, dxp);
-          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
-          const double isl = pr(d::F_A + s), ish = pr(d::F_B + s), izl = pr(d::F_C + s), izh = pr(d::F_D + s);
+          const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s), de = pr(d::Q_DE + s);
+          const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
+          const double isl = pr(d::Q_A + s), ish = pr(d::Q_B + s), izl = pr(d::Q_C + s), izh = pr(d::Q_D + s);
           const double wl = zlo * isl, wh = zhi * ish;
           const double rzh = hi - shi - e, rzl = -lo - slo + e;
-          const double cdl = -slo * zlo - pr(d::F_E + s) + sigma * mu, cdh = -shi * zhi - pr(d::F_G + s) + sigma * mu;
+          const double cdl = -slo * zlo - pr(d::Q_E + s) + sm, cdh = -shi * zhi - pr(d::Q_G + s) + sm;
           const double r3l = rzl - cdl * izl, r3h = rzh - cdh * izh;
           const double dzh = wh * (de - r3h), dzl = wl * (-de - r3l);
           const double dsh = (cdh - shi * dzh) * izh, dsl = (cdl - slo * dzl) * izl;
           rp = fmax(rp, fmax(-dsh * ish, -dsl * isl));
           rdm = fmax(rdm, fmax(-dzh * izh, -dzl * izl));
-          pr(d::F_A + s) = dsl; pr(d::F_B + s) = dsh; pr(d::F_C + s) = dzl; pr(d::F_D + s) = dzh;
+          pr(d::Q_A + s) = dsl; pr(d::Q_B + s) = dsh; pr(d::Q_C + s) = dzl; pr(d::Q_D + s) = dzh;
         }
       }
       rp = g_max(g, rp); rdm = g_max(g, rdm);
       ap = (rp > 0.0) ? 1.0 / rp : 1.0; ad = (rdm > 0.0) ? 1.0 / rdm : 1.0;
       ap = fmin(0.99 * ap, 1.0); ad = fmin(0.99 * ad, 1.0);
+      LANE_DBG("      ap %.3e ad %.3e dlm %.3e %.3e %.3e %.3e\n", ap, ad, dd.lm[0], dd.lm[1], dd.lm[2], dd.lm[3]);
     }
     LUNR for (int i = 0; i < 4; i++) { x.xs[i] += ap * dd.xs[i]; x.pi[i] += ad * dd.pi[i]; }
     LUNR for (int i = 0; i < C; i++) x.lm[i] += ap * dd.lm[i];
     LUNR for (int a = 0; a < 2; a++) { x.us[a] += ap * dd.us[a]; x.nu[a] += ad * dd.nu[a]; }
     x.dl += ap * dd.dl; x.eta += ad * dd.eta;
-    LUNR for (int s = 0; s < d::NSQP; s++) {
+    LSLOTS for (int s = 0; s < d::NSQP; s++) {
       if (l_slot_valid<C>(s, g)) {
-        pr(d::F_SLO + s) += ap * pr(d::F_A + s); pr(d::F_SHI + s) += ap * pr(d::F_B + s);
-        pr(d::F_ZLO + s) += ad * pr(d::F_C + s); pr(d::F_ZHI + s) += ad * pr(d::F_D + s);
+        pr(d::Q_SLO + s) += ap * pr(d::Q_A + s); pr(d::Q_SHI + s) += ap * pr(d::Q_B + s);
+        pr(d::Q_ZLO + s) += ad * pr(d::Q_C + s); pr(d::Q_ZHI + s) += ad * pr(d::Q_D + s);
       }
     }
     qp_it++;
@@ -830,42 +857,47 @@ struct LaneSolver {
   LMEM void qp_final_kkt(const KParams& P) {
     double xp[4], pin[4];
     prev_state(x, false, xp); next_pi(x, pin);
-    double wz[d::NS], ec = 0.0, ep = 0.0;
-    LUNR for (int s = 0; s < d::NS; s++) wz[s] = 0.0;
-    LUNR for (int s = 0; s < d::NSQP; s++) {
+    l_scatter<C, false>(g, pr, d::Q_EV, x, xp);
+    double ec = 0.0, ep = 0.0;
+    LSLOTS for (int s = 0; s < d::NSQP; s++) {
+      double wz = 0.0;
       if (l_slot_valid<C>(s, g)) {
-        double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
-        const double e = l_slot_lin<C>(s, x, xp);
-        const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
-        wz[s] = zlo - zhi;
+        const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s);
+        const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
+        wz = zlo - zhi;
         ec = fmax(ec, fmax(fabs(slo * zlo), fabs(shi * zhi)));
         ep = fmax(ep, fmax(fmax(lo - e, e - hi), 0.0));
       }
+      pr(d::Q_DE + s) = wz;
     }
-    KV gfy, jz; double wd;
-    l_grad_Aty<C>(P, c, x, x, pin, true, gfy);
-    l_gather<C, false>(g, wz, H.gv, jz, wd);
-    double rd = fabs(gfy.dl);
-    LUNR for (int i = 0; i < 4; i++) rd = fmax(rd, fabs(gfy.xs[i] - jz.xs[i]));
-    LUNR for (int a = 0; a < 2; a++) rd = fmax(rd, fabs(gfy.us[a] - jz.us[a]));
-    LUNR for (int i = 0; i < C; i++) rd = fmax(rd, fabs(gfy.lm[i] - jz.lm[i]));
-    double rpi[4], rnu[2], reta;
-    l_eq_residual<C>(P, c, x, xp, false, rpi, rnu, reta);
-    double re = fabs(reta);
-    LUNR for (int i = 0; i < 4; i++) re = fmax(re, fabs(rpi[i]));
-    re = fmax(re, fmax(fabs(rnu[0]), fabs(rnu[1])));
+    KV rx; double acc_rx, acc_ry;
+    qp_dual_eq(P, xp, pin, rx, acc_rx, acc_ry);
+    double rd = fabs(rx.dl), re = fabs(rx.eta);
+    LUNR for (int i = 0; i < 4; i++) { rd = fmax(rd, fabs(rx.xs[i])); re = fmax(re, fabs(rx.pi[i])); }
+    LUNR for (int a = 0; a < 2; a++) { rd = fmax(rd, fabs(rx.us[a])); re = fmax(re, fabs(rx.nu[a])); }
+    LUNR for (int i = 0; i < C; i++) rd = fmax(rd, fabs(rx.lm[i]));
     info.kkt = g_max(g, fmax(fmax(rd, re), fmax(ec, ep)));
     info.status = (info.qp_flag == 0) ? 0 : 1;
   }
 
   // =============================================================================================================
   // Stage 2: NLP, IPM-F
+  // Slot fields (stride NS): SLO SHI ZLO ZHI | A = 1/s_lo  B = 1/s_hi | C = e(dx)  D = dz_lo  E = dz_hi |
+  //                          G, EV = scratch weights (e(x) at the top of the iteration; refinement)
+  // The distance slot SD is one-sided: its "hi" half is inert (s_hi = 1, z_hi = 0, never updated).
   // =============================================================================================================
   double mu, tau, dw_last, theta_max, theta_min; int nl_it, nfilt; bool first_ic;
 
-  LMEM double slot_e_nl(const KParams& P, int s, const double* xp) const {
-    if (s == d::SD) { const double a = x.xs[0] - c.ox, b = x.xs[2] - c.oy; return a * a + b * b + x.dl; }
-    return l_slot_lin<C>(s, x, xp);
+  // e(x) of every slot -> field fld
+  LMEM void nlp_scatter_e(int fld, const double* xp) {
+    l_scatter<C, true>(g, pr, fld, x, xp);
+    const double a = x.xs[0] - c.ox, b = x.xs[2] - c.oy;
+    pr(fld + d::SD) = a * a + b * b + x.dl;
+  }
+  // e(dx) (directional derivative) of every slot -> field fld
+  LMEM void nlp_scatter_de(int fld, const KV& dv, const double* dvp) {
+    l_scatter<C, true>(g, pr, fld, dv, dvp);
+    pr(fld + d::SD) = H.gv[0] * dv.xs[0] + H.gv[1] * dv.xs[2] + dv.dl;
   }
 
   LMEM void nlp_init(const KParams& P) {
@@ -890,13 +922,13 @@ struct LaneSolver {
     x.nu[0] = x.nu[1] = 0.0; x.eta = 0.0;
     LUNR for (int t = 0; t < 16; t++) pr(d::F_FILT + t) = 0.0;
     mu = P.mu_init; tau = fmax(P.tau_min, 1.0 - mu); dw_last = 0.0; first_ic = true; nfilt = 0; nl_it = 0;
-    LUNR for (int s = 0; s < d::NS; s++) {
-      double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
+    nlp_scatter_e(d::N_EV, xp);
+    LSLOTS for (int s = 0; s < d::NS; s++) {
       const bool v = l_slot_valid<C>(s, g), vhi = v && s != d::SD;
-      const double e = slot_e_nl(P, s, xp);
-      const double slo = v ? e - lo : 1.0, shi = vhi ? hi - e : 1.0;
-      pr(d::F_SLO + s) = slo; pr(d::F_SHI + s) = shi;
-      pr(d::F_ZLO + s) = v ? mu * l_rcp(slo) : 0.0; pr(d::F_ZHI + s) = vhi ? mu * l_rcp(shi) : 0.0;
+      const double e = pr(d::N_EV + s);
+      const double slo = v ? e - l_slot_lo<C>(P, s) : 1.0, shi = vhi ? l_slot_hi<C>(P, s) - e : 1.0;
+      pr(d::N_SLO + s) = slo; pr(d::N_SHI + s) = shi;
+      pr(d::N_ZLO + s) = v ? mu * l_rcp(slo) : 0.0; pr(d::N_ZHI + s) = vhi ? mu * l_rcp(shi) : 0.0;
     }
     {
       double rpi[4], rnu[2], reta;
@@ -917,40 +949,40 @@ struct LaneSolver {
     // ---- slots at x: s = c(x) (feasible IPM), multiplier safeguard, gradient of the distance row
     KV gfy; double re_pi[4], re_nu[2], re_eta, e_d, e_p, th, zd;
     {
-      double wz[d::NS], e_c = 0.0, zmax = 0.0, smin = 1e300;
+      double e_c = 0.0, zmax = 0.0, smin = 1e300;
       const double iks = 1.0 / P.kappa_sigma;
-      LUNR for (int s = 0; s < d::NS; s++) {
-        wz[s] = 0.0;
+      nlp_scatter_e(d::N_EV, xp);
+      LSLOTS for (int s = 0; s < d::NS; s++) {
+        double wz = 0.0;
         if (l_slot_valid<C>(s, g)) {
-          double lo, hi; l_slot_bounds<C>(s, P, lo, hi);
           const bool vhi = s != d::SD;
-          const double e = slot_e_nl(P, s, xp);
-          const double slo = e - lo, shi = vhi ? hi - e : 1.0;
-          double zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
+          const double e = pr(d::N_EV + s);
+          const double slo = e - l_slot_lo<C>(P, s), shi = vhi ? l_slot_hi<C>(P, s) - e : 1.0;
+          double zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
           smin = fmin(smin, fmin(slo, shi));
           if (it > 0) {  // z reset (Ipopt eq. 16) with the mu of the step just taken
             const double mr_lo = mu * l_rcp(slo), mr_hi = mu * l_rcp(shi);
             zlo = fmin(fmax(zlo, mr_lo * iks), P.kappa_sigma * mr_lo);
             if (vhi) zhi = fmin(fmax(zhi, mr_hi * iks), P.kappa_sigma * mr_hi);
-            pr(d::F_ZLO + s) = zlo; pr(d::F_ZHI + s) = zhi;
+            pr(d::N_ZLO + s) = zlo; pr(d::N_ZHI + s) = zhi;
           }
-          pr(d::F_SLO + s) = slo; pr(d::F_SHI + s) = shi;
+          pr(d::N_SLO + s) = slo; pr(d::N_SHI + s) = shi;
           e_c = fmax(e_c, fmax(fabs(slo * zlo), fabs(shi * zhi)));
           zmax = fmax(zmax, fmax(zlo, zhi));
-          wz[s] = zlo - zhi;
+          wz = zlo - zhi;
         }
+        pr(d::N_G + s) = wz;
       }
       H.gv[0] = 2.0 * (x.xs[0] - c.ox); H.gv[1] = 2.0 * (x.xs[2] - c.oy);
-      zd = pr(d::F_ZLO + d::SD);
+      zd = pr(d::N_ZLO + d::SD);
       // ---- KKT error
       KV jz; double wd;
       l_grad_Aty<C>(P, c, x, x, pin, true, gfy);
-      l_gather<C, true>(g, wz, H.gv, jz, wd);
+      l_gather<C, true>(g, pr, d::N_G, H.gv, jz, wd);
       double rdm = fabs(gfy.dl - wd);
       LUNR for (int i = 0; i < 4; i++) rdm = fmax(rdm, fabs(gfy.xs[i] - jz.xs[i]));
       LUNR for (int a = 0; a < 2; a++) rdm = fmax(rdm, fabs(gfy.us[a] - jz.us[a]));
       LUNR for (int i = 0; i < C; i++) rdm = fmax(rdm, fabs(gfy.lm[i] - jz.lm[i]));
-      // fold J'z into gfy: from here on gfy = grad f + A'y (kept) and gz = J'z are both needed
       l_eq_residual<C>(P, c, x, xp, false, re_pi, re_nu, re_eta);
       double rem = fabs(re_eta), res = fabs(re_eta);
       LUNR for (int i = 0; i < 4; i++) { rem = fmax(rem, fabs(re_pi[i])); res += fabs(re_pi[i]); }
@@ -969,10 +1001,10 @@ struct LaneSolver {
     // ---- barrier update (Ipopt eq. 7)
     for (;;) {
       double emu = 0.0;
-      LUNR for (int s = 0; s < d::NS; s++) {
+      LSLOTS for (int s = 0; s < d::NS; s++) {
         if (l_slot_valid<C>(s, g)) {
-          emu = fmax(emu, fabs(pr(d::F_SLO + s) * pr(d::F_ZLO + s) - mu));
-          if (s != d::SD) emu = fmax(emu, fabs(pr(d::F_SHI + s) * pr(d::F_ZHI + s) - mu));
+          emu = fmax(emu, fabs(pr(d::N_SLO + s) * pr(d::N_ZLO + s) - mu));
+          if (s != d::SD) emu = fmax(emu, fabs(pr(d::N_SHI + s) * pr(d::N_ZHI + s) - mu));
         }
       }
       emu = fmax(g_max(g, emu), fmax(e_d, e_p));
@@ -982,28 +1014,28 @@ struct LaneSolver {
         nfilt = 0;
       } else break;
     }
-    // ---- slot weights: Sigma, mu/s_lo - mu/s_hi; distance row: capped split.  1/s -> F_A, F_B
+    // ---- slot weights: Sigma -> C, mu/s_lo - mu/s_hi -> D; distance row: capped split.  1/s -> A, B
     KV r;
     {
-      double sa[d::NS], sb[d::NS];
-      LUNR for (int s = 0; s < d::NS; s++) {
-        sa[s] = 0.0; sb[s] = 0.0;
+      LSLOTS for (int s = 0; s < d::NS; s++) {
+        double sa = 0.0, sb = 0.0;
         if (l_slot_valid<C>(s, g)) {
           const bool vhi = s != d::SD;
-          const double rlo = l_rcp(pr(d::F_SLO + s)), rhi = l_rcp(pr(d::F_SHI + s));
-          pr(d::F_A + s) = rlo; pr(d::F_B + s) = rhi;
-          sa[s] = pr(d::F_ZLO + s) * rlo + pr(d::F_ZHI + s) * rhi;
-          sb[s] = mu * rlo - (vhi ? mu * rhi : 0.0);
+          const double rlo = l_rcp(pr(d::N_SLO + s)), rhi = l_rcp(pr(d::N_SHI + s));
+          pr(d::N_A + s) = rlo; pr(d::N_B + s) = rhi;
+          sa = pr(d::N_ZLO + s) * rlo + pr(d::N_ZHI + s) * rhi;
+          sb = mu * rlo - (vhi ? mu * rhi : 0.0);
         }
+        pr(d::N_C + s) = sa; pr(d::N_D + s) = sb;
       }
       {
-        const double sg = sa[d::SD];
+        const double sg = pr(d::N_C + d::SD);
         const bool cap = sg > P.sigma_cap;
         H.sc = fmin(sg, P.sigma_cap); H.capped = cap ? 1 : 0; H.srinv = cap ? l_rcp(sg - H.sc) : 0.0;
       }
-      l_assemble<C, true>(g, P, c, sa, P.rho_lambda, zd, H);
+      l_assemble<C, true>(g, P, c, pr, d::N_C, P.rho_lambda, zd, H);
       double wd;
-      l_gather<C, true>(g, sb, H.gv, r, wd);
+      l_gather<C, true>(g, pr, d::N_D, H.gv, r, wd);
       LUNR for (int i = 0; i < 4; i++) { r.xs[i] -= gfy.xs[i]; r.lm[i] = (i < C) ? r.lm[i] - gfy.lm[i] : 0.0; r.pi[i] = -re_pi[i]; }
       LUNR for (int a = 0; a < 2; a++) { r.us[a] -= gfy.us[a]; r.nu[a] = -re_nu[a]; }
       r.dl = wd - gfy.dl; r.eta = -re_eta;
@@ -1027,68 +1059,45 @@ struct LaneSolver {
     }
     KV dd; double tb[4];
     l_kkt_solve_border<C>(g, P, c, H, f, dw, pr, bf, r, dd, tb);
-#ifdef CBF_DBGBUF
-    if (it <= 3) {
-      LANE_LOG4(2000.0 + it);
-      for (int i = 0; i < 4; i++) LANE_LOG4(H.hx[i]);
-      LANE_LOG4(H.hxy); LANE_LOG4(H.hu[0]); LANE_LOG4(H.hu[1]); LANE_LOG4(H.hxu[0]); LANE_LOG4(H.hxu[1]);
-      for (int i = 0; i < 4; i++) LANE_LOG4(H.hl[i]);
-      LANE_LOG4(H.bd[0]); LANE_LOG4(H.bd[1]); LANE_LOG4(H.hd); LANE_LOG4(H.gv[0]); LANE_LOG4(H.gv[1]); LANE_LOG4(H.sc); LANE_LOG4(H.srinv); LANE_LOG4((double)H.capped);
-      LANE_LOG4(3000.0);
-      for (int i = 0; i < 10; i++) LANE_LOG4(f.Pn[i]);
-      for (int i = 0; i < 4 * (C - 1); i++) LANE_LOG4(f.K[i]);
-      for (int i = 0; i < 4 * (C - 1); i++) LANE_LOG4(f.St[i]);
-      LANE_LOG4(f.Lc[0]);
-      LANE_LOG4(4000.0);
-      for (int i = 0; i < 10; i++) LANE_LOG4(bf.L[i]);
-      for (int i = 0; i < 4; i++) { LANE_LOG4(bf.Tic[i]); LANE_LOG4(bf.cb[i]); LANE_LOG4((double)bf.cap[i]); }
-      LANE_LOG4(bf.den);
-      LANE_LOG4(5000.0);
-      for (int i = 0; i < 4; i++) { LANE_LOG4(r.xs[i]); LANE_LOG4(r.lm[i]); LANE_LOG4(r.pi[i]); }
-      LANE_LOG4(r.us[0]); LANE_LOG4(r.us[1]); LANE_LOG4(r.nu[0]); LANE_LOG4(r.nu[1]); LANE_LOG4(r.dl); LANE_LOG4(r.eta);
-      LANE_LOG4(6000.0);
-      for (int i = 0; i < 4; i++) { LANE_LOG4(dd.xs[i]); LANE_LOG4(dd.lm[i]); LANE_LOG4(dd.pi[i]); LANE_LOG4(tb[i]); }
-      LANE_LOG4(dd.us[0]); LANE_LOG4(dd.us[1]); LANE_LOG4(dd.nu[0]); LANE_LOG4(dd.nu[1]); LANE_LOG4(dd.dl); LANE_LOG4(dd.eta);
-    }
-#endif
-    // ---- slot steps: de -> F_C, dz_lo -> F_D, dz_hi -> F_E
+    // ---- slot steps: de -> C, dz_lo -> D, dz_hi -> E
     double quad;
     {
       double dxp[4]; prev_state(dd, true, dxp);
-      LUNR for (int s = 0; s < d::NS; s++) {
+      nlp_scatter_de(d::N_C, dd, dxp);
+      const double tbj = l_sel4(tb, g.j);
+      LSLOTS for (int s = 0; s < d::NS; s++) {
         if (l_slot_valid<C>(s, g)) {
           const bool vhi = s != d::SD;
-          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
-          const double rlo = pr(d::F_A + s), rhi = pr(d::F_B + s);
-          const double de = (s == d::SD) ? H.gv[0] * dd.xs[0] + H.gv[1] * dd.xs[2] + dd.dl : l_slot_lin<C>(s, dd, dxp);
+          const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
+          const double rlo = pr(d::N_A + s), rhi = pr(d::N_B + s), de = pr(d::N_C + s);
           double dzl = (mu - slo * zlo) * rlo - zlo * rlo * de;
           const double dzh = vhi ? (mu - shi * zhi) * rhi + zhi * rhi * de : 0.0;
-          if (s == d::SD && H.capped) dzl = (mu - slo * zlo) * rlo - H.sc * de - l_sel4(tb, g.j);
-          pr(d::F_C + s) = de; pr(d::F_D + s) = dzl; pr(d::F_E + s) = dzh;
+          if (s == d::SD && H.capped) dzl = (mu - slo * zlo) * rlo - H.sc * de - tbj;
+          pr(d::N_D + s) = dzl; pr(d::N_E + s) = dzh;
         }
       }
       quad = dd.xs[0] * dd.xs[0] + dd.xs[2] * dd.xs[2];
     }
     // ---- iterative refinement on the unreduced Newton system
     for (int rf = 0; rf < P.max_refine; rf++) {
-      double sa2[d::NS], sb2[d::NS];
-      LUNR for (int s = 0; s < d::NS; s++) {
-        sa2[s] = 0.0; sb2[s] = 0.0;
+      LSLOTS for (int s = 0; s < d::NS; s++) {
+        double sa2 = 0.0, sb2 = 0.0;
         if (l_slot_valid<C>(s, g)) {
           const bool vhi = s != d::SD;
-          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
-          const double de = pr(d::F_C + s), dzl = pr(d::F_D + s), dzh = pr(d::F_E + s);
+          const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
+          const double de = pr(d::N_C + s), dzl = pr(d::N_D + s), dzh = pr(d::N_E + s);
           const double rcl = (mu - slo * zlo) - (slo * dzl + zlo * de);
           const double rch = vhi ? (mu - shi * zhi) - (shi * dzh - zhi * de) : 0.0;
-          sa2[s] = (zlo + dzl) - (zhi + dzh);
-          sb2[s] = rcl * pr(d::F_A + s) - rch * pr(d::F_B + s);
+          sa2 = (zlo + dzl) - (zhi + dzh);
+          sb2 = rcl * pr(d::N_A + s) - rch * pr(d::N_B + s);
         }
+        pr(d::N_G + s) = sa2; pr(d::N_EV + s) = sb2;
       }
       // rho1 = -(grad f + A'(y+dy) + Htilde dx - J'(z+dz)),  rho2 = -(A (x+dx) - b)
       KV gd, jz2, rr; double wd2, dpin[4], dxp[4];
       next_pi(dd, dpin); prev_state(dd, true, dxp);
       l_grad_Aty<C>(P, c, dd, dd, dpin, false, gd);
-      l_gather<C, true>(g, sa2, H.gv, jz2, wd2);
+      l_gather<C, true>(g, pr, d::N_G, H.gv, jz2, wd2);
       double nres = 0.0;
       LUNR for (int i = 0; i < 4; i++) {
         const double ht = c.qw + dw - ((i & 1) ? 0.0 : 2.0 * zd);
@@ -1115,7 +1124,7 @@ struct LaneSolver {
       if (!(nres > fmax(P.refine_rel * nrhs, P.refine_abs))) break;
       {
         KV jb; double wdb;
-        l_gather<C, true>(g, sb2, H.gv, jb, wdb);
+        l_gather<C, true>(g, pr, d::N_EV, H.gv, jb, wdb);
         LUNR for (int i = 0; i < 4; i++) { rr.xs[i] += jb.xs[i]; rr.lm[i] += jb.lm[i]; }
         LUNR for (int a = 0; a < 2; a++) rr.us[a] += jb.us[a];
         rr.dl += wdb;
@@ -1123,19 +1132,20 @@ struct LaneSolver {
       KV d2; double tb2[4];
       l_kkt_solve_border<C>(g, P, c, H, f, dw, pr, bf, rr, d2, tb2);
       double d2p[4]; prev_state(d2, true, d2p);
-      LUNR for (int s = 0; s < d::NS; s++) {
+      nlp_scatter_de(d::N_G, d2, d2p);
+      const double tbj = l_sel4(tb2, g.j);
+      LSLOTS for (int s = 0; s < d::NS; s++) {
         if (l_slot_valid<C>(s, g)) {
           const bool vhi = s != d::SD;
-          const double slo = pr(d::F_SLO + s), shi = pr(d::F_SHI + s), zlo = pr(d::F_ZLO + s), zhi = pr(d::F_ZHI + s);
-          const double rlo = pr(d::F_A + s), rhi = pr(d::F_B + s);
-          const double de = pr(d::F_C + s), dzl = pr(d::F_D + s), dzh = pr(d::F_E + s);
+          const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
+          const double rlo = pr(d::N_A + s), rhi = pr(d::N_B + s);
+          const double de = pr(d::N_C + s), dzl = pr(d::N_D + s), dzh = pr(d::N_E + s), dde = pr(d::N_G + s);
           const double rcl = (mu - slo * zlo) - (slo * dzl + zlo * de);
           const double rch = vhi ? (mu - shi * zhi) - (shi * dzh - zhi * de) : 0.0;
-          const double dde = (s == d::SD) ? H.gv[0] * d2.xs[0] + H.gv[1] * d2.xs[2] + d2.dl : l_slot_lin<C>(s, d2, d2p);
           double cl = rcl * rlo - zlo * rlo * dde;
           const double ch = vhi ? rch * rhi + zhi * rhi * dde : 0.0;
-          if (s == d::SD && H.capped) cl = rcl * rlo - H.sc * dde - l_sel4(tb2, g.j);
-          pr(d::F_C + s) = de + dde; pr(d::F_D + s) = dzl + cl; pr(d::F_E + s) = dzh + ch;
+          if (s == d::SD && H.capped) cl = rcl * rlo - H.sc * dde - tbj;
+          pr(d::N_C + s) = de + dde; pr(d::N_D + s) = dzl + cl; pr(d::N_E + s) = dzh + ch;
         }
       }
       LUNR for (int i = 0; i < 4; i++) { dd.xs[i] += d2.xs[i]; dd.lm[i] += d2.lm[i]; dd.pi[i] += d2.pi[i]; }
@@ -1143,29 +1153,29 @@ struct LaneSolver {
       dd.dl += d2.dl; dd.eta += d2.eta;
       quad = dd.xs[0] * dd.xs[0] + dd.xs[2] * dd.xs[2];
     }
-    // ---- fraction to the boundary: alpha_max = min(1, tau / max_i(-ds_i / s_i))
-    double a_pmax, a_dmax;
+    // ---- fraction to the boundary (alpha_max = min(1, tau / max_i(-ds_i / s_i))) and the line-search constants
+    //      phi = f - mu sum log s, its directional derivative, sum of slack products (for log)
+    double a_pmax, a_dmax, ph, dphi, dQd, gdx;
     {
-      double rp = 0.0, rdm = 0.0;
-      LUNR for (int s = 0; s < d::NS; s++) {
+      double rp = 0.0, rdm = 0.0, prod = 1.0, prod2 = 1.0, dsum = 0.0;
+      LSLOTS for (int s = 0; s < d::NS; s++) {
         if (l_slot_valid<C>(s, g)) {
           const bool vhi = s != d::SD;
-          const double de = pr(d::F_C + s);
-          rp = fmax(rp, -de * pr(d::F_A + s));
-          if (vhi) rp = fmax(rp, de * pr(d::F_B + s));
-          double zq = -pr(d::F_D + s) * l_rcp(pr(d::F_ZLO + s));
-          if (vhi) zq = fmax(zq, -pr(d::F_E + s) * l_rcp(pr(d::F_ZHI + s)));
+          const double de = pr(d::N_C + s), rlo = pr(d::N_A + s), rhi = pr(d::N_B + s);
+          rp = fmax(rp, -de * rlo);
+          if (vhi) rp = fmax(rp, de * rhi);
+          double zq = -pr(d::N_D + s) * l_rcp(pr(d::N_ZLO + s));
+          if (vhi) zq = fmax(zq, -pr(d::N_E + s) * l_rcp(pr(d::N_ZHI + s)));
           rdm = fmax(rdm, zq);
+          const double ss = pr(d::N_SLO + s) * pr(d::N_SHI + s);
+          if (s & 1) prod *= ss; else prod2 *= ss;
+          dsum += de * rlo - (vhi ? de * rhi : 0.0);
         }
       }
       rp = g_max(g, rp); rdm = g_max(g, rdm);
       a_pmax = (rp > tau) ? tau / rp : 1.0; a_dmax = (rdm > tau) ? tau / rdm : 1.0;
-    }
-    LANE_LOG(dw); LANE_LOG(a_pmax); LANE_LOG(a_dmax); LANE_LOG(dd.dl); LANE_LOG(dd.xs[0]); LANE_LOG(dd.us[0]); LANE_LOG(dd.lm[0]); LANE_LOG(dd.pi[0]); LANE_LOG(dd.nu[0]); LANE_LOG(dd.eta);
-    LANE_DBG("   dw %.1e apmax %.3e admax %.3e ddl %.3e\n", dw, a_pmax, a_dmax, dd.dl);
-    // ---- filter line search on phi = f - mu sum log s  (theta = ||A x - b||_1 shrinks by (1 - alpha))
-    double ph, dphi, dQd, gdx;
-    {
+      LANE_LOG(dw); LANE_LOG(a_pmax); LANE_LOG(a_dmax);
+      LANE_DBG("   dw %.1e apmax %.3e admax %.3e ddl %.3e\n", dw, a_pmax, a_dmax, dd.dl);
       // f(x) = sum_j x_j (1/2 Q_jj x_j + f_j)   (DV:423-428)
       double f0 = 0.0, gd = 0.0, qd = 0.0;
       LUNR for (int i = 0; i < 4; i++) {
@@ -1174,33 +1184,26 @@ struct LaneSolver {
       }
       LUNR for (int a = 0; a < 2; a++) { const double xv = x.us[a], dv = dd.us[a]; f0 += xv * (0.5 * P.Rw * xv); gd += P.Rw * xv * dv; qd += P.Rw * dv * dv; }
       if (g.j == 0) { const double xv = x.dl, dv = dd.dl; f0 += xv * (0.5 * P.slw * xv); gd += P.slw * xv * dv; qd += P.slw * dv * dv; }
-      double prod = 1.0, prod2 = 1.0, dsum = 0.0;
-      LUNR for (int s = 0; s < d::NS; s++) {
-        if (l_slot_valid<C>(s, g)) {
-          const bool vhi = s != d::SD;
-          const double de = pr(d::F_C + s);
-          if (s & 1) prod *= pr(d::F_SLO + s) * pr(d::F_SHI + s); else prod2 *= pr(d::F_SLO + s) * pr(d::F_SHI + s);
-          dsum += de * pr(d::F_A + s) - (vhi ? de * pr(d::F_B + s) : 0.0);
-        }
-      }
       ph = g_sum(g, f0 - mu * (log(prod) + log(prod2)));
       gdx = g_sum(g, gd);
       dphi = gdx - mu * g_sum(g, dsum);
       dQd = g_sum(g, qd);
     }
+    // ---- filter line search (theta = ||A x - b||_1 shrinks by (1 - alpha))
     double alpha = a_pmax;
     bool accepted = false, ftype = false;
     while (alpha >= P.alpha_min) {
       // phi(x + alpha dx) - phi(x) = alpha g'dx + 1/2 alpha^2 dx'Q dx - mu sum log(s_t / s)
       double prod = 1.0, prod2 = 1.0;
       bool pos = true;
-      LUNR for (int s = 0; s < d::NS; s++) {
+      const double aq = alpha * alpha * quad;
+      LSLOTS for (int s = 0; s < d::NS; s++) {
         if (l_slot_valid<C>(s, g)) {
           const bool vhi = s != d::SD;
-          const double et = alpha * pr(d::F_C + s) + ((s == d::SD) ? alpha * alpha * quad : 0.0);
-          const double sl = pr(d::F_SLO + s) + et, sh = vhi ? pr(d::F_SHI + s) - et : 1.0;
+          const double et = alpha * pr(d::N_C + s) + ((s == d::SD) ? aq : 0.0);
+          const double sl = pr(d::N_SLO + s) + et, sh = vhi ? pr(d::N_SHI + s) - et : 1.0;
           pos = pos && (sl > 0.0) && (sh > 0.0);
-          const double t = (sl * pr(d::F_A + s)) * (vhi ? sh * pr(d::F_B + s) : 1.0);
+          const double t = (sl * pr(d::N_A + s)) * (vhi ? sh * pr(d::N_B + s) : 1.0);
           if (s & 1) prod *= t; else prod2 *= t;
         }
       }
@@ -1241,8 +1244,8 @@ struct LaneSolver {
     LUNR for (int i = 0; i < C; i++) x.lm[i] += alpha * dd.lm[i];
     LUNR for (int a = 0; a < 2; a++) { x.us[a] += alpha * dd.us[a]; x.nu[a] += alpha * dd.nu[a]; }
     x.dl += alpha * dd.dl; x.eta += alpha * dd.eta;
-    LUNR for (int s = 0; s < d::NS; s++) {
-      if (l_slot_valid<C>(s, g)) { pr(d::F_ZLO + s) += a_dmax * pr(d::F_D + s); if (s != d::SD) pr(d::F_ZHI + s) += a_dmax * pr(d::F_E + s); }
+    LSLOTS for (int s = 0; s < d::NS; s++) {
+      if (l_slot_valid<C>(s, g)) { pr(d::N_ZLO + s) += a_dmax * pr(d::N_D + s); if (s != d::SD) pr(d::N_ZHI + s) += a_dmax * pr(d::N_E + s); }
     }
     nl_it = it + 1;
     return false;
@@ -1367,8 +1370,9 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
         else if (s < d::SV) { rhi = 2 * (j - 1) + (s - d::SF); rlo = 6 + rhi; }
         else if (s < d::SD) { const int q = (s - d::SV) ? 4 + j : j; rhi = d::MQP + 4 + q; rlo = d::MQP + 12 + q; }
         else { rlo = d::MQP + j; }
-        if (rlo >= 0 && pr(d::F_ZLO + s) > pr(d::F_SLO + s)) w[rlo >> 5] |= 1u << (rlo & 31);
-        if (rhi >= 0 && s != d::SD && pr(d::F_ZHI + s) > pr(d::F_SHI + s)) w[rhi >> 5] |= 1u << (rhi & 31);
+        const int st = nlp ? d::NS : d::NSQP;  // field stride of the stage that ran last
+        if (rlo >= 0 && pr(2 * st + s) > pr(s)) w[rlo >> 5] |= 1u << (rlo & 31);
+        if (rhi >= 0 && s != d::SD && pr(3 * st + s) > pr(st + s)) w[rhi >> 5] |= 1u << (rhi & 31);
       }
     }
     LUNR for (int k = 0; k < 4; k++) w[k] = g_or(g, w[k]);

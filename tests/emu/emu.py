@@ -1,5 +1,9 @@
-"""DEV/TEST TOOL: loads the host emulation of the kernel source (tests/emu/libcbfnmpc_emu.so).  Never imported by
-the product package."""
+"""DEV/TEST TOOL: loads the host emulation of the kernel source (tests/emu/libcbfnmpc_lane_emu.so: the product's
+cbfnmpc_lane.h compiled for the host, each 4-lane group on 4 cooperative fibers).  Never imported by the product package.
+
+Two builds: the default -O2 one, and a "sitecheck" build (-O0 -DCBF_EMU_SITECHECK) in which every source-level shuffle site
+has its own call address and the harness verifies that the 4 lanes of a group always meet at the SAME site -- the
+convergence requirement of __shfl_sync with the group mask on the device."""
 import ctypes as C
 import importlib.util
 import os
@@ -11,31 +15,32 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 _spec = importlib.util.spec_from_file_location("cbf_capi", os.path.join(ROOT, "srb-cbf-nmpc_b200", "capi.py"))
 capi = importlib.util.module_from_spec(_spec); _spec.loader.exec_module(capi)
 
-_lib = None
+_libs = {}
 
 
-def build(force=False):
-    lib = os.path.join(HERE, "libcbfnmpc_emu.so")
+def build(force=False, sitecheck=False):
+    lib = os.path.join(HERE, "libcbfnmpc_lane_emu_sitecheck.so" if sitecheck else "libcbfnmpc_lane_emu.so")
     csrc = os.path.join(ROOT, "srb-cbf-nmpc_b200", "csrc")
-    srcs = [os.path.join(HERE, "emu_warp.cpp")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")]
+    srcs = [os.path.join(HERE, "emu_lane.cpp")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")]
     srcs.append(os.path.join(ROOT, "include", "cbfnmpc.h"))
     if force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", lib,
-                               os.path.join(HERE, "emu_warp.cpp")])
+        flags = ["-O0", "-DCBF_EMU_SITECHECK"] if sitecheck else ["-O2"]
+        subprocess.check_call(["g++"] + flags + ["-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", lib,
+                               os.path.join(HERE, "emu_lane.cpp"), "-ldl"])
     return lib
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(build())
-        _lib.emu_solve_batch_host.argtypes = [C.POINTER(capi.Gains), C.POINTER(capi.Options), C.c_int, C.c_int,
-                                              C.POINTER(capi.In), C.POINTER(capi.Out), C.c_void_p]
-    return _lib
+def lib(sitecheck=False):
+    if sitecheck not in _libs:
+        L = C.CDLL(build(sitecheck=sitecheck))
+        L.emu_solve_batch_host.argtypes = [C.POINTER(capi.Gains), C.POINTER(capi.Options), C.c_int, C.c_int,
+                                           C.POINTER(capi.In), C.POINTER(capi.Out), C.c_void_p]
+        _libs[sitecheck] = L
+    return _libs[sitecheck]
 
 
-def solve(insts, mode=1, gains=None, options=None, xstart=None):
-    L = lib()
+def solve(insts, mode=1, gains=None, options=None, xstart=None, sitecheck=False):
+    L = lib(sitecheck)
     g = capi.Gains(); L.cbfnmpc_default_gains(C.byref(g))
     o = capi.Options(); L.cbfnmpc_default_options(C.byref(o))
     for k, v in (gains or {}).items(): setattr(g, k, v)

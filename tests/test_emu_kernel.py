@@ -1,5 +1,6 @@
-"""CPU-side check of the *kernel source*: srb-cbf-nmpc_b200/csrc compiled for the host with 32 cooperative fibers per warp
-(tests/emu).  This is a logic test of the product kernels, not a fallback: the C ABI never reaches the emulator."""
+"""CPU-side check of the *kernel source*: srb-cbf-nmpc_b200/csrc/cbfnmpc_lane.h compiled for the host, each 4-lane group on 4
+cooperative fibers (tests/emu).  This is a logic test of the product kernel, not a fallback: the C ABI never reaches the
+emulator."""
 import numpy as np
 import helpers as H
 import emu
@@ -32,3 +33,24 @@ def test_bad_contact_pattern_is_flagged():
     inst = list(S.cfg1_instance(4)); inst[3] = [1, 1, 1, 0]
     out = emu.solve(H.pad_obs([tuple(inst)]), mode=1)
     assert out["status"][0, 0] == 4
+
+
+def test_group_lanes_meet_at_the_same_shuffle_sites():
+    """-O0 build: one call address per source-level shuffle; the harness fails if the 4 lanes of a group ever wait at
+    different sites (which __shfl_sync with the group mask would not tolerate on the device)."""
+    insts = H.pad_obs([S.cfg1_instance(4), S.cfg1_instance(2)]) + S.cfg3_instances(14)
+    for mode in (0, 1):
+        out = emu.solve(insts, mode=mode, sitecheck=True)
+        ref = H.oracle_batch(insts, mode=mode)
+        assert (out["status"][0] == ref["status"]).all()
+
+
+def test_degenerate_support_weights_qp():
+    """Instances whose lambdas end strictly inside (0, 1) at every stage: the reduced Hessian loses one pivot to rounding
+    (cbfnmpc_lane.h, l_chol pivot rule); the QP stage must still reach the iSWIFT answer."""
+    allinst = S.cfg3_instances(2400)
+    insts = [allinst[i] for i in (159, 1064, 1356, 1631, 2229, 2308)]
+    out = emu.solve(insts, mode=0)
+    ref = H.oracle_batch(insts, mode=0)
+    assert (out["status"][0] == 0).all() and (ref["status"] == 0).all()
+    assert np.abs(out["X"].T - ref["X"]).max() < 1e-8 and np.abs(out["U"].T - ref["U"]).max() < 1e-8
