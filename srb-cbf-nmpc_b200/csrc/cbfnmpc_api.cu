@@ -6,7 +6,7 @@
 #include <vector>
 #include "cbfnmpc_host.h"
 #ifndef LANE_NT
-#define LANE_NT 32  // one warp (8 instances) per CTA; 4 CTAs of 48.5 KB shared memory fit an SM
+#define LANE_NT 128  // 4 warps (32 instances, one stance class) per CTA, one CTA per SM; the warps re-synchronise every solver iteration
 #endif
 #include "cbfnmpc_lane.h"
 
@@ -52,17 +52,17 @@ __global__ void __launch_bounds__(LANE_NT, 1) cbfnmpc_lane_kernel(const __grid_c
                                                                   const int* __restrict__ perm, const int* __restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Priv pr; pr.base = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
-  const int gw = blockIdx.x * (LANE_NT / 32) + (threadIdx.x >> 5);  // warp index in the grid
-  const int grp = (threadIdx.x & 31) >> 2;
+  constexpr int IPC = LANE_NT / 4;  // instances per CTA; a CTA runs one stance class
+  const int grp = threadIdx.x >> 2;
   const int n4 = counts[0], n2 = counts[1];
-  const int w4 = (n4 + 7) >> 3;
-  if (gw < w4) {
-    const int slot = gw * 8 + grp;
+  const int c4 = (n4 + IPC - 1) / IPC;
+  if ((int)blockIdx.x < c4) {
+    const int slot = blockIdx.x * IPC + grp;
     const bool valid = slot < n4;
     lane_run_group<4>(P, io, valid ? perm[slot] : 0, valid, pr);
   } else {
-    const int slot = (gw - w4) * 8 + grp;
-    if ((gw - w4) * 8 >= n2) return;
+    const int slot = (blockIdx.x - c4) * IPC + grp;
+    if ((int)(blockIdx.x - c4) * IPC >= n2) return;
     const bool valid = slot < n2;
     lane_run_group<2>(P, io, valid ? perm[io.B + slot] : 0, valid, pr);
   }
@@ -185,11 +185,11 @@ static int launch(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const c
     c->perm_cap = B;
   }
   int* counts = c->d_perm + 2 * (size_t)c->perm_cap;
-  const int warps = (B + 7) / 8 + 1, wpc = LANE_NT / 32;
+  const int ipc = LANE_NT / 4;
   cbfnmpc_classify_kernel<<<1, 1024, 0, st>>>(io, c->d_perm, counts);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev0, st));  // the event pair brackets the solve kernel alone
-  cbfnmpc_lane_kernel<<<(warps + wpc - 1) / wpc, LANE_NT, LANE_NPRIV * LANE_NT * sizeof(double), st>>>(c->kp, io, c->d_perm, counts);
+  cbfnmpc_lane_kernel<<<(B + ipc - 1) / ipc + 1, LANE_NT, LANE_NPRIV * LANE_NT * sizeof(double), st>>>(c->kp, io, c->d_perm, counts);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev1, st));
   c->timed = true;

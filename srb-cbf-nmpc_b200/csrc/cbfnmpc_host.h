@@ -73,16 +73,17 @@ static inline void host_fill_kparams(const cbfnmpc_gains* g, const cbfnmpc_optio
   P->rho_lambda = o->rho_lambda; P->z_div = o->z_div; P->sigma_cap = o->sigma_cap; P->refine_rel = o->refine_rel;
   P->refine_abs = o->refine_abs; P->max_iter = o->max_iter; P->filter_cap = o->filter_cap > 8 ? 8 : o->filter_cap;
   P->max_refine = o->max_refine;
-  for (int k = 0; k < 2; k++) {  // slots: X 4 | U 2 | lambda C | friction 2 | velocity 2 | distance 1
+  for (int k = 0; k < 2; k++) {  // slots: X 4 | U 2 | lambda C | QP: friction 2 ; NLP: velocity 2 | distance 1 | friction 2
     const int C = k == 0 ? 4 : 2;
     for (int s = 0; s < 16; s++) {
-      double lo = 0.0, hi = 0.0;
-      if (s < 6) { lo = -P->box; hi = P->box; }
-      else if (s < 6 + C) { lo = 0.0; hi = 1.0; }
-      else if (s < 8 + C) { lo = -P->fb; hi = P->fb; }
-      else if (s < 10 + C) { lo = -P->vmax; hi = P->vmax; }
-      else if (s < 11 + C) { lo = P->eps; hi = 0.0; }
-      P->slot_lo[k][s] = lo; P->slot_hi[k][s] = hi;
+      double lo = 0.0, hi = 0.0, lon = 0.0, hin = 0.0;
+      if (s < 6) { lo = lon = -P->box; hi = hin = P->box; }
+      else if (s < 6 + C) { lo = lon = 0.0; hi = hin = 1.0; }
+      if (s >= 6 + C && s < 8 + C) { lo = -P->fb; hi = P->fb; lon = -P->vmax; hin = P->vmax; }
+      if (s == 8 + C) { lon = P->eps; hin = 0.0; }
+      if (s >= 9 + C && s < 11 + C) { lon = -P->fb; hin = P->fb; }
+      P->slot_lo[0][k][s] = lo; P->slot_hi[0][k][s] = hi;
+      P->slot_lo[1][k][s] = lon; P->slot_hi[1][k][s] = hin;
     }
   }
 }

@@ -74,7 +74,9 @@ template <int C>
 struct LaneDims {
   static constexpr int NW = C - 1, NR = NW * (NW + 1) / 2, MQP = 60 + 8 * C;
   // two-sided slots of one lane
-  static constexpr int SX = 0, SU = 4, SL = 6, SF = 6 + C, SV = 8 + C, SD = 10 + C, NS = 11 + C, NSQP = 8 + C;
+  // slot order: X 4 | U 2 | lambda C | then QP stage: friction 2;  NLP stage: velocity 2 | distance 1 | friction 2.
+  // The friction slots come last so that lane 0 (which has none: x_0 is fixed) simply runs shorter slot loops.
+  static constexpr int SX = 0, SU = 4, SL = 6, SFQ = 6 + C, NSQP = 8 + C, SV = 6 + C, SD = 8 + C, SFN = 9 + C, NS = 11 + C;
   // thread-private shared-memory fields.  QP stage: 12 per slot, stride NSQP; NLP stage: 11 per slot, stride NS (the two
   // stages never overlap); then the border vectors and the filter.
   static constexpr int Q_SLO = 0, Q_SHI = NSQP, Q_ZLO = 2 * NSQP, Q_ZHI = 3 * NSQP, Q_A = 4 * NSQP, Q_B = 5 * NSQP, Q_C = 6 * NSQP,
@@ -545,9 +547,9 @@ LDEV void l_kkt_solve_border(const Grp& g, const KParams& P, const LaneConst& c,
 #define LPRAGMA_(x) _Pragma(#x)
 #define LPRAGMA(x) LPRAGMA_(x)
 #define LSLOTS LPRAGMA(unroll LSLOT_UNROLL)
-template <int C> LDEV bool l_slot_valid(int s, const Grp& g) { typedef LaneDims<C> d; return (s >= d::SF && s < d::SF + 2) ? (g.j > 0) : true; }
-template <int C> LDEV double l_slot_lo(const KParams& P, int s) { return P.slot_lo[C == 4 ? 0 : 1][s]; }
-template <int C> LDEV double l_slot_hi(const KParams& P, int s) { return P.slot_hi[C == 4 ? 0 : 1][s]; }
+template <int C, bool NL> LDEV int l_nslots(const Grp& g) { typedef LaneDims<C> d; return (NL ? d::NS : d::NSQP) - (g.j == 0 ? 2 : 0); }
+template <int C, bool NL> LDEV double l_slot_lo(const KParams& P, int s) { return P.slot_lo[NL ? 1 : 0][C == 4 ? 0 : 1][s]; }
+template <int C, bool NL> LDEV double l_slot_hi(const KParams& P, int s) { return P.slot_hi[NL ? 1 : 0][C == 4 ? 0 : 1][s]; }
 // e = J v of the linear slots -> field fld (stride-1 slot index); v = lane vector, vp = previous lane's xs (x_j).
 // The distance slot (NLP) is written by the caller.
 template <int C, bool NL>
@@ -556,7 +558,8 @@ LDEV void l_scatter(const Grp& g, const Priv& pr, int fld, const KV& v, const do
   LUNR for (int i = 0; i < 4; i++) pr(fld + d::SX + i) = v.xs[i];
   LUNR for (int a = 0; a < 2; a++) pr(fld + d::SU + a) = v.us[a];
   LUNR for (int i = 0; i < C; i++) pr(fld + d::SL + i) = v.lm[i];
-  LUNR for (int a = 0; a < 2; a++) pr(fld + d::SF + a) = vp[2 * a] - v.us[a];
+  constexpr int SF = NL ? d::SFN : d::SFQ;
+  LUNR for (int a = 0; a < 2; a++) pr(fld + SF + a) = vp[2 * a] - v.us[a];
   if (NL) { LUNR for (int a = 0; a < 2; a++) pr(fld + d::SV + a) = v.xs[2 * a + 1]; }
 }
 // acc.(xs,us,lm) = J'w for the per-slot weights w in field fld (weight of +grad e; 0 in the invalid slots);
@@ -564,7 +567,8 @@ LDEV void l_scatter(const Grp& g, const Priv& pr, int fld, const KV& v, const do
 template <int C, bool NL>
 LDEV void l_gather(const Grp& g, const Priv& pr, int fld, const double* gv, KV& acc, double& wd) {
   typedef LaneDims<C> d;
-  const double wf0 = pr(fld + d::SF), wf1 = pr(fld + d::SF + 1);
+  constexpr int SF = NL ? d::SFN : d::SFQ;
+  const double wf0 = (g.j > 0) ? pr(fld + SF) : 0.0, wf1 = (g.j > 0) ? pr(fld + SF + 1) : 0.0;
   LUNR for (int i = 0; i < 4; i++) acc.xs[i] = pr(fld + d::SX + i);
   acc.us[0] = pr(fld + d::SU) - wf0; acc.us[1] = pr(fld + d::SU + 1) - wf1;
   LUNR for (int i = 0; i < 4; i++) acc.lm[i] = (i < C) ? pr(fld + d::SL + i) : 0.0;
@@ -583,7 +587,7 @@ LDEV void l_assemble(const Grp& g, const KParams& P, const LaneConst& c, const P
   typedef LaneDims<C> d;
   LUNR for (int i = 0; i < 4; i++) H.hx[i] = c.qw + pr(fld + d::SX + i);
   LUNR for (int a = 0; a < 2; a++) {
-    const double sf = pr(fld + d::SF + a);
+    const double sf = (g.j > 0) ? pr(fld + (NL ? d::SFN : d::SFQ) + a) : 0.0;
     H.hu[a] = P.Rw + pr(fld + d::SU + a) + sf;
     H.hxu[a] = -sf;
     const double t = g_down(g, sf);
@@ -612,6 +616,7 @@ struct LaneSolver {
   LaneHess H;
   LaneFact f;
   LaneInfo info;
+  int nsq, nsn;    // slot-loop lengths of this lane in the QP / NLP stage (lane 0 has no friction slots)
 
   LMEM void prev_state(const KV& v, bool homogeneous, double* xp) const {  // x_j: previous lane's xs; lane 0: measured state
     LUNR for (int i = 0; i < 4; i++) { const double t = g_up(g, v.xs[i]); xp[i] = (g.j > 0) ? t : (homogeneous ? 0.0 : c.xin[i]); }
@@ -646,10 +651,10 @@ struct LaneSolver {
   // initial point.  Returns true when the stage is already finished (factorisation failure).
   LMEM bool qp_init(const KParams& P) {
     // W = I, rhs [-c; b; h]
-    LSLOTS for (int s = 0; s < d::NSQP; s++) {
-      const bool act = l_slot_valid<C>(s, g);
+    LSLOTS for (int s = 0; s < nsq; s++) {
+      const bool act = true;
       pr(d::Q_E + s) = act ? 2.0 : 0.0;
-      pr(d::Q_G + s) = act ? l_slot_hi<C>(P, s) + l_slot_lo<C>(P, s) : 0.0;
+      pr(d::Q_G + s) = act ? l_slot_hi<C, false>(P, s) + l_slot_lo<C, false>(P, s) : 0.0;
     }
     LUNR for (int i = 0; i < 4; i++) { x.xs[i] = 0.0; x.lm[i] = 0.0; x.pi[i] = 0.0; }
     x.us[0] = x.us[1] = 0.0; x.dl = 0.0; x.nu[0] = x.nu[1] = 0.0; x.eta = 0.0;
@@ -675,19 +680,19 @@ struct LaneSolver {
     double xp[4]; prev_state(x, false, xp);
     l_scatter<C, false>(g, pr, d::Q_EV, x, xp);
     double rmin = 1e300, rmax = -1e300;
-    LSLOTS for (int s = 0; s < d::NSQP; s++) {
-      if (l_slot_valid<C>(s, g)) {
+    LSLOTS for (int s = 0; s < nsq; s++) {
+      {
         const double e = pr(d::Q_EV + s);
-        const double rl = e - l_slot_lo<C>(P, s), rh = l_slot_hi<C>(P, s) - e;
+        const double rl = e - l_slot_lo<C, false>(P, s), rh = l_slot_hi<C, false>(P, s) - e;
         rmin = fmin(rmin, fmin(rl, rh)); rmax = fmax(rmax, fmax(rl, rh));
       }
     }
     rmin = g_min(g, rmin); rmax = g_max(g, rmax);
     const double ap = -rmin, ad = rmax;
-    LSLOTS for (int s = 0; s < d::NSQP; s++) {
-      const bool act = l_slot_valid<C>(s, g);
+    LSLOTS for (int s = 0; s < nsq; s++) {
+      const bool act = true;
       const double e = pr(d::Q_EV + s);
-      const double rl = e - l_slot_lo<C>(P, s), rh = l_slot_hi<C>(P, s) - e;
+      const double rl = e - l_slot_lo<C, false>(P, s), rh = l_slot_hi<C, false>(P, s) - e;
       pr(d::Q_SLO + s) = act ? ((ap < 0) ? rl : rl + (1.0 + ap)) : 1.0;
       pr(d::Q_SHI + s) = act ? ((ap < 0) ? rh : rh + (1.0 + ap)) : 1.0;
       pr(d::Q_ZLO + s) = act ? ((ad < 0) ? -rl : -rl + (1.0 + ad)) : 0.0;
@@ -698,27 +703,33 @@ struct LaneSolver {
   }
 
   // one Mehrotra predictor-corrector iteration (Prime.c:138-218).  Returns true when the stage is finished.
+  // Slot passes: A (residuals, reciprocals, predictor weights), B (affine step statistics), C (corrector right-hand side),
+  // D (final step and step lengths), E (update).  One instance of the KKT solve serves predictor and corrector.
   LMEM bool qp_iter(const KParams& P) {
     if (qp_it >= P.qp_maxit) return true;
     double xp[4], pin[4];
     prev_state(x, false, xp); next_pi(x, pin);
     l_scatter<C, false>(g, pr, d::Q_EV, x, xp);
-    // ---- residuals (computeresiduals, Auxilary.c:524-553)
+    // ---- pass A: residuals (computeresiduals, Auxilary.c:524-553); 1/s -> A, B ; 1/z -> C, D ; predictor: Sigma -> E, rhs -> G
     KV rx;  // rx.(xs,us,lm,dl) = -(Px + G'z + A'y + c), rx.(pi,nu,eta) = b - Ax
     double sz, mu;
+    const bool predictor = sigma > 0.0;
     {
       double acc_rz = 0.0, acc_sz = 0.0;
-      LSLOTS for (int s = 0; s < d::NSQP; s++) {
-        double wz = 0.0;
-        if (l_slot_valid<C>(s, g)) {
-          const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s);
-          const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
-          const double rzh = hi - shi - e, rzl = -lo - slo + e;
-          acc_rz += rzh * rzh + rzl * rzl;
-          acc_sz += slo * zlo + shi * zhi;
-          wz = zlo - zhi;
-        }
-        pr(d::Q_DE + s) = wz;
+      LSLOTS for (int s = 0; s < nsq; s++) {
+        const double lo = l_slot_lo<C, false>(P, s), hi = l_slot_hi<C, false>(P, s), e = pr(d::Q_EV + s);
+        const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
+        const double rzh = hi - shi - e, rzl = -lo - slo + e;
+        acc_rz += rzh * rzh + rzl * rzl;
+        acc_sz += slo * zlo + shi * zhi;
+        pr(d::Q_DE + s) = zlo - zhi;
+        const double isl = l_rcp(slo), ish = l_rcp(shi);
+        pr(d::Q_A + s) = isl; pr(d::Q_B + s) = ish;
+        pr(d::Q_C + s) = l_rcp(zlo); pr(d::Q_D + s) = l_rcp(zhi);
+        // predictor: W = s/z, ds = -s z, rhs3 = rz - ds/z = rz + s
+        const double wl = zlo * isl, wh = zhi * ish;
+        pr(d::Q_E + s) = predictor ? wl + wh : 0.0;
+        pr(d::Q_G + s) = predictor ? wh * (rzh + shi) - wl * (rzl + slo) : 0.0;
       }
       double acc_rx, acc_ry;
       qp_dual_eq(P, xp, pin, rx, acc_rx, acc_ry);
@@ -729,124 +740,85 @@ struct LaneSolver {
       if (sqrt(nrx) < lim && sqrt(nrz) < lim && sqrt(nry) < lim && sz / d::MQP < P.qp_abstol) { info.qp_flag = 0; return true; }
       mu = sz / d::MQP;
     }
-    // ---- reciprocals, once per iteration: 1/s -> A, B ; 1/z -> C, D ; predictor weights: Sigma -> E, rhs -> G
-    const bool predictor = sigma > 0.0;
-    LSLOTS for (int s = 0; s < d::NSQP; s++) {
-      double sa = 0.0, sb = 0.0;
-      if (l_slot_valid<C>(s, g)) {
-        const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
-        const double isl = l_rcp(slo), ish = l_rcp(shi);
-        pr(d::Q_A + s) = isl; pr(d::Q_B + s) = ish;
-        pr(d::Q_C + s) = l_rcp(zlo); pr(d::Q_D + s) = l_rcp(zhi);
-        if (predictor) {  // W = s/z, ds = -s z, rhs3 = rz - ds/z = rz + s
-          const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s);
-          const double wl = zlo * isl, wh = zhi * ish;
-          const double rzh = hi - shi - e, rzl = -lo - slo + e;
-          sa = wl + wh;
-          sb = wh * (rzh + shi) - wl * (rzl + slo);
-        }
-      }
-      pr(d::Q_E + s) = sa; pr(d::Q_G + s) = sb;
-    }
-    KV r, dd;
     if (predictor) {
       l_assemble<C, false>(g, P, c, pr, d::Q_E, 0.0, 0.0, H);
-      double wd;
-      l_gather<C, false>(g, pr, d::Q_G, H.gv, r, wd);
-      LUNR for (int i = 0; i < 4; i++) { r.xs[i] += rx.xs[i]; r.lm[i] += rx.lm[i]; r.pi[i] = rx.pi[i]; }
-      LUNR for (int a = 0; a < 2; a++) { r.us[a] += rx.us[a]; r.nu[a] = rx.nu[a]; }
-      r.dl = rx.dl; r.eta = rx.eta;
       info.n_fact++;
       if (!l_riccati<C, true>(g, P, c, H, 0.0, f)) { info.qp_flag = 1; return true; }
-      l_kkt_solve_plain<C>(g, P, c, H, f, 0.0, r, dd);
-      // affine step: max step lengths (findsteplength, Auxilary.c:271-294) and rho (Auxilary.c:600-609)
-      double dxp[4]; prev_state(dd, true, dxp);
-      l_scatter<C, false>(g, pr, d::Q_DE, dd, dxp);
-      double rp = 0.0, rdm = 0.0, s_dsz = 0.0, s_sdz = 0.0, s_dsdz = 0.0;
-      LSLOTS for (int s = 0; s < d::NSQP; s++) {
-        if (l_slot_valid<C>(s, g)) {
-          const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s), de = pr(d::Q_DE + s);
-          const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
-          const double isl = pr(d::Q_A + s), ish = pr(d::Q_B + s), izl = pr(d::Q_C + s), izh = pr(d::Q_D + s);
-          const double wl = zlo * isl, wh = zhi * ish;
-          const double rzh = hi - shi - e, rzl = -lo - slo + e;
-          const double dzh = wh * (de - (rzh + shi)), dzl = wl * (-de - (rzl + slo));
-          const double dsh = (-shi * zhi - shi * dzh) * izh, dsl = (-slo * zlo - slo * dzl) * izl;
-          rp = fmax(rp, fmax(-dsh * ish, -dsl * isl));
-          rdm = fmax(rdm, fmax(-dzh * izh, -dzl * izl));
-          s_dsz += dsl * zlo + dsh * zhi; s_sdz += slo * dzl + shi * dzh; s_dsdz += dsl * dzl + dsh * dzh;
-          pr(d::Q_E + s) = dsl * dzl; pr(d::Q_G + s) = dsh * dzh;
-        }
-      }
-      rp = g_max(g, rp); rdm = g_max(g, rdm);
-      const double ap = (rp > 0.0) ? 1.0 / rp : 1.0, ad = (rdm > 0.0) ? 1.0 / rdm : 1.0;
-      // sum (s + ap ds)(z + ad dz) = s'z + ap ds'z + ad s'dz + ap ad ds'dz
-      const double num = sz + g_sum(g, ap * s_dsz + ad * s_sdz + (ap * ad) * s_dsdz);
-      const double rho = num / sz, mr = rho < 1.0 ? rho : 1.0;
-      sigma = mr * mr * mr;
-      if (sigma < 0.0) sigma = 0.0;
     } else {
-      sigma = 0.0;  // E, G already hold zeros
+      sigma = 0.0;  // E, G hold zeros: pure corrector with the previous factor
     }
-    // ---- corrector solve with the same factor: ds = -s z - ds_aff dz_aff + sigma mu (form_ds, Auxilary.c:250-267)
-    {
+    double ap = 1.0, ad = 1.0;
+    KV dd;
+    for (int ph = predictor ? 0 : 1; ph < 2; ph++) {
       const double sm = sigma * mu;
-      LSLOTS for (int s = 0; s < d::NSQP; s++) {
-        double sb = 0.0;
-        if (l_slot_valid<C>(s, g)) {
-          const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s);
+      if (ph == 1) {
+        // ---- pass C: corrector right-hand side, ds = -s z - ds_aff dz_aff + sigma mu (form_ds, Auxilary.c:250-267) -> DE
+        LSLOTS for (int s = 0; s < nsq; s++) {
+          const double lo = l_slot_lo<C, false>(P, s), hi = l_slot_hi<C, false>(P, s), e = pr(d::Q_EV + s);
           const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
           const double wl = zlo * pr(d::Q_A + s), wh = zhi * pr(d::Q_B + s);
           const double rzh = hi - shi - e, rzl = -lo - slo + e;
           const double cdl = -slo * zlo - pr(d::Q_E + s) + sm, cdh = -shi * zhi - pr(d::Q_G + s) + sm;
           const double r3l = rzl - cdl * pr(d::Q_C + s), r3h = rzh - cdh * pr(d::Q_D + s);
-          sb = wh * r3h - wl * r3l;
+          pr(d::Q_DE + s) = wh * r3h - wl * r3l;
         }
-        pr(d::Q_DE + s) = sb;
       }
-      double wd;
-      l_gather<C, false>(g, pr, d::Q_DE, H.gv, r, wd);
+      KV r; double wd;
+      l_gather<C, false>(g, pr, ph == 0 ? d::Q_G : d::Q_DE, H.gv, r, wd);
       LUNR for (int i = 0; i < 4; i++) { r.xs[i] += rx.xs[i]; r.lm[i] += rx.lm[i]; r.pi[i] = rx.pi[i]; }
       LUNR for (int a = 0; a < 2; a++) { r.us[a] += rx.us[a]; r.nu[a] = rx.nu[a]; }
       r.dl = rx.dl; r.eta = rx.eta;
-    }
-    l_kkt_solve_plain<C>(g, P, c, H, f, 0.0, r, dd);
-    double ap, ad;
-    {
+      l_kkt_solve_plain<C>(g, P, c, H, f, 0.0, r, dd);
       double dxp[4]; prev_state(dd, true, dxp);
       l_scatter<C, false>(g, pr, d::Q_DE, dd, dxp);
-      const double sm = sigma * mu;
-      double rp = 0.0, rdm = 0.0;
-      LSLOTS for (int s = 0; s < d::NSQP; s++) {
-        if (l_slot_valid<C>(s, g)) {
-          const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s), de = pr(d::Q_DE + s);
-          const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
-          const double isl = pr(d::Q_A + s), ish = pr(d::Q_B + s), izl = pr(d::Q_C + s), izh = pr(d::Q_D + s);
-          const double wl = zlo * isl, wh = zhi * ish;
-          const double rzh = hi - shi - e, rzl = -lo - slo + e;
+      // ---- pass B (affine: max step lengths, findsteplength Auxilary.c:271-294, and rho, Auxilary.c:600-609)
+      //      or pass D (final step: ds -> A, B ; dz -> C, D)
+      double rp = 0.0, rdm = 0.0, s_dsz = 0.0, s_sdz = 0.0, s_dsdz = 0.0;
+      const bool aff = ph == 0;
+      LSLOTS for (int s = 0; s < nsq; s++) {
+        const double lo = l_slot_lo<C, false>(P, s), hi = l_slot_hi<C, false>(P, s), e = pr(d::Q_EV + s), de = pr(d::Q_DE + s);
+        const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
+        const double isl = pr(d::Q_A + s), ish = pr(d::Q_B + s), izl = pr(d::Q_C + s), izh = pr(d::Q_D + s);
+        const double wl = zlo * isl, wh = zhi * ish;
+        const double rzh = hi - shi - e, rzl = -lo - slo + e;
+        double dzh, dzl, dsh, dsl;
+        if (aff) {
+          dzh = wh * (de - (rzh + shi)); dzl = wl * (-de - (rzl + slo));
+          dsh = (-shi * zhi - shi * dzh) * izh; dsl = (-slo * zlo - slo * dzl) * izl;
+        } else {
           const double cdl = -slo * zlo - pr(d::Q_E + s) + sm, cdh = -shi * zhi - pr(d::Q_G + s) + sm;
           const double r3l = rzl - cdl * izl, r3h = rzh - cdh * izh;
-          const double dzh = wh * (de - r3h), dzl = wl * (-de - r3l);
-          const double dsh = (cdh - shi * dzh) * izh, dsl = (cdl - slo * dzl) * izl;
-          rp = fmax(rp, fmax(-dsh * ish, -dsl * isl));
-          rdm = fmax(rdm, fmax(-dzh * izh, -dzl * izl));
+          dzh = wh * (de - r3h); dzl = wl * (-de - r3l);
+          dsh = (cdh - shi * dzh) * izh; dsl = (cdl - slo * dzl) * izl;
+        }
+        rp = fmax(rp, fmax(-dsh * ish, -dsl * isl));
+        rdm = fmax(rdm, fmax(-dzh * izh, -dzl * izl));
+        if (aff) {
+          s_dsz += dsl * zlo + dsh * zhi; s_sdz += slo * dzl + shi * dzh; s_dsdz += dsl * dzl + dsh * dzh;
+          pr(d::Q_E + s) = dsl * dzl; pr(d::Q_G + s) = dsh * dzh;
+        } else {
           pr(d::Q_A + s) = dsl; pr(d::Q_B + s) = dsh; pr(d::Q_C + s) = dzl; pr(d::Q_D + s) = dzh;
         }
       }
       rp = g_max(g, rp); rdm = g_max(g, rdm);
       ap = (rp > 0.0) ? 1.0 / rp : 1.0; ad = (rdm > 0.0) ? 1.0 / rdm : 1.0;
-      ap = fmin(0.99 * ap, 1.0); ad = fmin(0.99 * ad, 1.0);
-      LANE_DBG("      ap %.3e ad %.3e dlm %.3e %.3e %.3e %.3e\n", ap, ad, dd.lm[0], dd.lm[1], dd.lm[2], dd.lm[3]);
+      if (aff) {
+        // sum (s + ap ds)(z + ad dz) = s'z + ap ds'z + ad s'dz + ap ad ds'dz
+        const double num = sz + g_sum(g, ap * s_dsz + ad * s_sdz + (ap * ad) * s_dsdz);
+        const double rho = num / sz, mr = rho < 1.0 ? rho : 1.0;
+        sigma = mr * mr * mr;
+        if (sigma < 0.0) sigma = 0.0;
+      }
     }
+    ap = fmin(0.99 * ap, 1.0); ad = fmin(0.99 * ad, 1.0);
     LUNR for (int i = 0; i < 4; i++) { x.xs[i] += ap * dd.xs[i]; x.pi[i] += ad * dd.pi[i]; }
     LUNR for (int i = 0; i < C; i++) x.lm[i] += ap * dd.lm[i];
     LUNR for (int a = 0; a < 2; a++) { x.us[a] += ap * dd.us[a]; x.nu[a] += ad * dd.nu[a]; }
     x.dl += ap * dd.dl; x.eta += ad * dd.eta;
-    LSLOTS for (int s = 0; s < d::NSQP; s++) {
-      if (l_slot_valid<C>(s, g)) {
-        pr(d::Q_SLO + s) += ap * pr(d::Q_A + s); pr(d::Q_SHI + s) += ap * pr(d::Q_B + s);
-        pr(d::Q_ZLO + s) += ad * pr(d::Q_C + s); pr(d::Q_ZHI + s) += ad * pr(d::Q_D + s);
-      }
+    // ---- pass E
+    LSLOTS for (int s = 0; s < nsq; s++) {
+      pr(d::Q_SLO + s) += ap * pr(d::Q_A + s); pr(d::Q_SHI + s) += ap * pr(d::Q_B + s);
+      pr(d::Q_ZLO + s) += ad * pr(d::Q_C + s); pr(d::Q_ZHI + s) += ad * pr(d::Q_D + s);
     }
     qp_it++;
     info.qp_iters = qp_it;
@@ -859,10 +831,10 @@ struct LaneSolver {
     prev_state(x, false, xp); next_pi(x, pin);
     l_scatter<C, false>(g, pr, d::Q_EV, x, xp);
     double ec = 0.0, ep = 0.0;
-    LSLOTS for (int s = 0; s < d::NSQP; s++) {
+    LSLOTS for (int s = 0; s < nsq; s++) {
       double wz = 0.0;
-      if (l_slot_valid<C>(s, g)) {
-        const double lo = l_slot_lo<C>(P, s), hi = l_slot_hi<C>(P, s), e = pr(d::Q_EV + s);
+      {
+        const double lo = l_slot_lo<C, false>(P, s), hi = l_slot_hi<C, false>(P, s), e = pr(d::Q_EV + s);
         const double slo = pr(d::Q_SLO + s), shi = pr(d::Q_SHI + s), zlo = pr(d::Q_ZLO + s), zhi = pr(d::Q_ZHI + s);
         wz = zlo - zhi;
         ec = fmax(ec, fmax(fabs(slo * zlo), fabs(shi * zhi)));
@@ -886,7 +858,7 @@ struct LaneSolver {
   //                          G, EV = scratch weights (e(x) at the top of the iteration; refinement)
   // The distance slot SD is one-sided: its "hi" half is inert (s_hi = 1, z_hi = 0, never updated).
   // =============================================================================================================
-  double mu, tau, dw_last, theta_max, theta_min; int nl_it, nfilt; bool first_ic;
+  double mu, tau, dw_last, theta_max, theta_min, ad_prev; int nl_it, nfilt; bool first_ic;
 
   // e(x) of every slot -> field fld
   LMEM void nlp_scatter_e(int fld, const double* xp) {
@@ -921,12 +893,12 @@ struct LaneSolver {
     LUNR for (int i = 0; i < 4; i++) x.pi[i] = 0.0;
     x.nu[0] = x.nu[1] = 0.0; x.eta = 0.0;
     LUNR for (int t = 0; t < 16; t++) pr(d::F_FILT + t) = 0.0;
-    mu = P.mu_init; tau = fmax(P.tau_min, 1.0 - mu); dw_last = 0.0; first_ic = true; nfilt = 0; nl_it = 0;
+    mu = P.mu_init; tau = fmax(P.tau_min, 1.0 - mu); dw_last = 0.0; first_ic = true; nfilt = 0; nl_it = 0; ad_prev = 0.0;
     nlp_scatter_e(d::N_EV, xp);
-    LSLOTS for (int s = 0; s < d::NS; s++) {
-      const bool v = l_slot_valid<C>(s, g), vhi = v && s != d::SD;
+    LSLOTS for (int s = 0; s < nsn; s++) {
+      const bool v = true, vhi = s != d::SD;
       const double e = pr(d::N_EV + s);
-      const double slo = v ? e - l_slot_lo<C>(P, s) : 1.0, shi = vhi ? l_slot_hi<C>(P, s) - e : 1.0;
+      const double slo = v ? e - l_slot_lo<C, true>(P, s) : 1.0, shi = vhi ? l_slot_hi<C, true>(P, s) - e : 1.0;
       pr(d::N_SLO + s) = slo; pr(d::N_SHI + s) = shi;
       pr(d::N_ZLO + s) = v ? mu * l_rcp(slo) : 0.0; pr(d::N_ZHI + s) = vhi ? mu * l_rcp(shi) : 0.0;
     }
@@ -942,36 +914,44 @@ struct LaneSolver {
   }
 
   // one IPM-F iteration.  Returns true when the stage is finished (info.status set).
+  // Slot passes per iteration: A (slacks, pending multiplier step + reset, reciprocals, weights), B (multiplier steps and
+  // the residual weights of the unreduced Newton system; B' after a refinement solve), C (step bounds, barrier terms),
+  // D (one per line-search trial).  The bordered KKT solve is instantiated once and shared by the main solve and the
+  // refinement solves (code footprint: DESIGN.md section 5).
   LMEM bool nlp_iter(const KParams& P) {
     const int it = nl_it;
     double xp[4], pin[4];
     prev_state(x, false, xp); next_pi(x, pin);
-    // ---- slots at x: s = c(x) (feasible IPM), multiplier safeguard, gradient of the distance row
-    KV gfy; double re_pi[4], re_nu[2], re_eta, e_d, e_p, th, zd;
+    // ---- pass A
+    KV gfy; double re_pi[4], re_nu[2], re_eta, e_d, e_p, th, zd, szmin, szmax;
     {
       double e_c = 0.0, zmax = 0.0, smin = 1e300;
-      const double iks = 1.0 / P.kappa_sigma;
+      szmin = 1e300; szmax = 0.0;
+      const double iks = 1.0 / P.kappa_sigma, adp = ad_prev;
       nlp_scatter_e(d::N_EV, xp);
-      LSLOTS for (int s = 0; s < d::NS; s++) {
-        double wz = 0.0;
-        if (l_slot_valid<C>(s, g)) {
-          const bool vhi = s != d::SD;
-          const double e = pr(d::N_EV + s);
-          const double slo = e - l_slot_lo<C>(P, s), shi = vhi ? l_slot_hi<C>(P, s) - e : 1.0;
-          double zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
-          smin = fmin(smin, fmin(slo, shi));
-          if (it > 0) {  // z reset (Ipopt eq. 16) with the mu of the step just taken
-            const double mr_lo = mu * l_rcp(slo), mr_hi = mu * l_rcp(shi);
-            zlo = fmin(fmax(zlo, mr_lo * iks), P.kappa_sigma * mr_lo);
-            if (vhi) zhi = fmin(fmax(zhi, mr_hi * iks), P.kappa_sigma * mr_hi);
-            pr(d::N_ZLO + s) = zlo; pr(d::N_ZHI + s) = zhi;
-          }
-          pr(d::N_SLO + s) = slo; pr(d::N_SHI + s) = shi;
-          e_c = fmax(e_c, fmax(fabs(slo * zlo), fabs(shi * zhi)));
-          zmax = fmax(zmax, fmax(zlo, zhi));
-          wz = zlo - zhi;
+      LSLOTS for (int s = 0; s < nsn; s++) {
+        const bool vhi = s != d::SD;
+        const double e = pr(d::N_EV + s);
+        const double slo = e - l_slot_lo<C, true>(P, s), shi = vhi ? l_slot_hi<C, true>(P, s) - e : 1.0;
+        const double rlo = l_rcp(slo), rhi = l_rcp(shi);
+        double zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
+        smin = fmin(smin, fmin(slo, shi));
+        if (it > 0) {  // multiplier step of the previous iteration, then the z reset (Ipopt eq. 16) with that iteration's mu
+          zlo += adp * pr(d::N_D + s);
+          if (vhi) zhi += adp * pr(d::N_E + s);
+          const double mr_lo = mu * rlo, mr_hi = mu * rhi;
+          zlo = fmin(fmax(zlo, mr_lo * iks), P.kappa_sigma * mr_lo);
+          if (vhi) zhi = fmin(fmax(zhi, mr_hi * iks), P.kappa_sigma * mr_hi);
+          pr(d::N_ZLO + s) = zlo; pr(d::N_ZHI + s) = zhi;
         }
-        pr(d::N_G + s) = wz;
+        pr(d::N_SLO + s) = slo; pr(d::N_SHI + s) = shi; pr(d::N_A + s) = rlo; pr(d::N_B + s) = rhi;
+        const double szl = slo * zlo, szh = shi * zhi;
+        e_c = fmax(e_c, fmax(fabs(szl), fabs(szh)));
+        szmin = fmin(szmin, vhi ? fmin(szl, szh) : szl); szmax = fmax(szmax, vhi ? fmax(szl, szh) : szl);
+        zmax = fmax(zmax, fmax(zlo, zhi));
+        pr(d::N_G + s) = zlo - zhi;                    // J'z weights
+        pr(d::N_C + s) = zlo * rlo + zhi * rhi;        // Sigma
+        pr(d::N_D + s) = rlo - (vhi ? rhi : 0.0);      // barrier gradient weights / mu
       }
       H.gv[0] = 2.0 * (x.xs[0] - c.ox); H.gv[1] = 2.0 * (x.xs[2] - c.oy);
       zd = pr(d::N_ZLO + d::SD);
@@ -988,6 +968,7 @@ struct LaneSolver {
       LUNR for (int i = 0; i < 4; i++) { rem = fmax(rem, fabs(re_pi[i])); res += fabs(re_pi[i]); }
       LUNR for (int a = 0; a < 2; a++) { rem = fmax(rem, fabs(re_nu[a])); res += fabs(re_nu[a]); }
       e_d = g_max(g, rdm); e_p = g_max(g, rem); e_c = g_max(g, e_c); zmax = g_max(g, zmax);
+      szmin = g_min(g, szmin); szmax = g_max(g, szmax);
       th = g_sum(g, res);
       const bool nan_seen = g_any(g, !(rdm == rdm) || !(rem == rem) || !(e_c == e_c) || !(zmax == zmax));
       const double E0 = nan_seen ? 1e300 : fmax(e_d, fmax(e_p, e_c));
@@ -998,47 +979,27 @@ struct LaneSolver {
       if (it == P.max_iter) { info.status = 1; return true; }
       if (!(zmax < P.z_div) || !(E0 < 1e300) || g_any(g, !(smin > 0.0))) { info.status = 2; return true; }
     }
-    // ---- barrier update (Ipopt eq. 7)
+    // ---- barrier update (Ipopt eq. 7): max_i |s_i z_i - mu| from the extreme products
     for (;;) {
-      double emu = 0.0;
-      LSLOTS for (int s = 0; s < d::NS; s++) {
-        if (l_slot_valid<C>(s, g)) {
-          emu = fmax(emu, fabs(pr(d::N_SLO + s) * pr(d::N_ZLO + s) - mu));
-          if (s != d::SD) emu = fmax(emu, fabs(pr(d::N_SHI + s) * pr(d::N_ZHI + s) - mu));
-        }
-      }
-      emu = fmax(g_max(g, emu), fmax(e_d, e_p));
+      const double emu = fmax(fmax(szmax - mu, mu - szmin), fmax(e_d, e_p));
       if (emu <= P.kappa_eps * mu && mu > P.tol / 10.0) {
         mu = fmax(P.tol / 10.0, fmin(P.kappa_mu * mu, mu * sqrt(mu)));
         tau = fmax(P.tau_min, 1.0 - mu);
         nfilt = 0;
       } else break;
     }
-    // ---- slot weights: Sigma -> C, mu/s_lo - mu/s_hi -> D; distance row: capped split.  1/s -> A, B
+    // ---- Hessian blocks and right-hand side (distance row: capped split)
     KV r;
     {
-      LSLOTS for (int s = 0; s < d::NS; s++) {
-        double sa = 0.0, sb = 0.0;
-        if (l_slot_valid<C>(s, g)) {
-          const bool vhi = s != d::SD;
-          const double rlo = l_rcp(pr(d::N_SLO + s)), rhi = l_rcp(pr(d::N_SHI + s));
-          pr(d::N_A + s) = rlo; pr(d::N_B + s) = rhi;
-          sa = pr(d::N_ZLO + s) * rlo + pr(d::N_ZHI + s) * rhi;
-          sb = mu * rlo - (vhi ? mu * rhi : 0.0);
-        }
-        pr(d::N_C + s) = sa; pr(d::N_D + s) = sb;
-      }
-      {
-        const double sg = pr(d::N_C + d::SD);
-        const bool cap = sg > P.sigma_cap;
-        H.sc = fmin(sg, P.sigma_cap); H.capped = cap ? 1 : 0; H.srinv = cap ? l_rcp(sg - H.sc) : 0.0;
-      }
+      const double sg = pr(d::N_C + d::SD);
+      const bool cap = sg > P.sigma_cap;
+      H.sc = fmin(sg, P.sigma_cap); H.capped = cap ? 1 : 0; H.srinv = cap ? l_rcp(sg - H.sc) : 0.0;
       l_assemble<C, true>(g, P, c, pr, d::N_C, P.rho_lambda, zd, H);
       double wd;
       l_gather<C, true>(g, pr, d::N_D, H.gv, r, wd);
-      LUNR for (int i = 0; i < 4; i++) { r.xs[i] -= gfy.xs[i]; r.lm[i] = (i < C) ? r.lm[i] - gfy.lm[i] : 0.0; r.pi[i] = -re_pi[i]; }
-      LUNR for (int a = 0; a < 2; a++) { r.us[a] -= gfy.us[a]; r.nu[a] = -re_nu[a]; }
-      r.dl = wd - gfy.dl; r.eta = -re_eta;
+      LUNR for (int i = 0; i < 4; i++) { r.xs[i] = mu * r.xs[i] - gfy.xs[i]; r.lm[i] = (i < C) ? mu * r.lm[i] - gfy.lm[i] : 0.0; r.pi[i] = -re_pi[i]; }
+      LUNR for (int a = 0; a < 2; a++) { r.us[a] = mu * r.us[a] - gfy.us[a]; r.nu[a] = -re_nu[a]; }
+      r.dl = mu * wd - gfy.dl; r.eta = -re_eta;
     }
     // ---- factorisation with inertia correction (Ipopt algorithm IC)
     double dw = 0.0;
@@ -1057,66 +1018,77 @@ struct LaneSolver {
       if (!ok) { info.status = 3; return true; }
       if (dw > 0.0) { dw_last = dw; first_ic = false; }
     }
-    KV dd; double tb[4];
-    l_kkt_solve_border<C>(g, P, c, H, f, dw, pr, bf, r, dd, tb);
-    // ---- slot steps: de -> C, dz_lo -> D, dz_hi -> E
-    double quad;
-    {
-      double dxp[4]; prev_state(dd, true, dxp);
-      nlp_scatter_de(d::N_C, dd, dxp);
-      const double tbj = l_sel4(tb, g.j);
-      LSLOTS for (int s = 0; s < d::NS; s++) {
-        if (l_slot_valid<C>(s, g)) {
-          const bool vhi = s != d::SD;
-          const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
-          const double rlo = pr(d::N_A + s), rhi = pr(d::N_B + s), de = pr(d::N_C + s);
-          double dzl = (mu - slo * zlo) * rlo - zlo * rlo * de;
-          const double dzh = vhi ? (mu - shi * zhi) * rhi + zhi * rhi * de : 0.0;
+    // ---- solve, then iterative refinement on the unreduced Newton system (one instance of the solve for both)
+    KV dd;
+    for (int rf = 0;; rf++) {
+      KV d2; double tb2[4];
+      l_kkt_solve_border<C>(g, P, c, H, f, dw, pr, bf, r, d2, tb2);
+      double d2p[4]; prev_state(d2, true, d2p);
+      const double tbj = l_sel4(tb2, g.j);
+      if (rf == 0) {
+        dd = d2;
+        nlp_scatter_de(d::N_C, d2, d2p);
+      } else {
+        nlp_scatter_de(d::N_G, d2, d2p);
+        LUNR for (int i = 0; i < 4; i++) { dd.xs[i] += d2.xs[i]; dd.lm[i] += d2.lm[i]; dd.pi[i] += d2.pi[i]; }
+        LUNR for (int a = 0; a < 2; a++) { dd.us[a] += d2.us[a]; dd.nu[a] += d2.nu[a]; }
+        dd.dl += d2.dl; dd.eta += d2.eta;
+      }
+      // pass B: slot steps de -> C, dz_lo -> D, dz_hi -> E (rf = 0: from scratch; later: corrections), then the residual
+      // weights of the complementarity rows: J'(z + dz) weights -> G, rc / s weights -> EV
+      const bool first = rf == 0;
+      LSLOTS for (int s = 0; s < nsn; s++) {
+        const bool vhi = s != d::SD;
+        const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
+        const double rlo = pr(d::N_A + s), rhi = pr(d::N_B + s);
+        double de, dzl, dzh;
+        if (first) {
+          de = pr(d::N_C + s);
+          dzl = (mu - slo * zlo) * rlo - zlo * rlo * de;
+          dzh = vhi ? (mu - shi * zhi) * rhi + zhi * rhi * de : 0.0;
           if (s == d::SD && H.capped) dzl = (mu - slo * zlo) * rlo - H.sc * de - tbj;
-          pr(d::N_D + s) = dzl; pr(d::N_E + s) = dzh;
+        } else {
+          de = pr(d::N_C + s); dzl = pr(d::N_D + s); dzh = pr(d::N_E + s);
+          const double dde = pr(d::N_G + s);
+          const double rcl0 = (mu - slo * zlo) - (slo * dzl + zlo * de);
+          const double rch0 = vhi ? (mu - shi * zhi) - (shi * dzh - zhi * de) : 0.0;
+          double cl = rcl0 * rlo - zlo * rlo * dde;
+          const double ch = vhi ? rch0 * rhi + zhi * rhi * dde : 0.0;
+          if (s == d::SD && H.capped) cl = rcl0 * rlo - H.sc * dde - tbj;
+          de += dde; dzl += cl; dzh += ch;
+          pr(d::N_C + s) = de;
         }
+        pr(d::N_D + s) = dzl; pr(d::N_E + s) = dzh;
+        const double rcl = (mu - slo * zlo) - (slo * dzl + zlo * de);
+        const double rch = vhi ? (mu - shi * zhi) - (shi * dzh - zhi * de) : 0.0;
+        pr(d::N_G + s) = (zlo + dzl) - (zhi + dzh);
+        pr(d::N_EV + s) = rcl * rlo - rch * rhi;
       }
-      quad = dd.xs[0] * dd.xs[0] + dd.xs[2] * dd.xs[2];
-    }
-    // ---- iterative refinement on the unreduced Newton system
-    for (int rf = 0; rf < P.max_refine; rf++) {
-      LSLOTS for (int s = 0; s < d::NS; s++) {
-        double sa2 = 0.0, sb2 = 0.0;
-        if (l_slot_valid<C>(s, g)) {
-          const bool vhi = s != d::SD;
-          const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
-          const double de = pr(d::N_C + s), dzl = pr(d::N_D + s), dzh = pr(d::N_E + s);
-          const double rcl = (mu - slo * zlo) - (slo * dzl + zlo * de);
-          const double rch = vhi ? (mu - shi * zhi) - (shi * dzh - zhi * de) : 0.0;
-          sa2 = (zlo + dzl) - (zhi + dzh);
-          sb2 = rcl * pr(d::N_A + s) - rch * pr(d::N_B + s);
-        }
-        pr(d::N_G + s) = sa2; pr(d::N_EV + s) = sb2;
-      }
+      if (rf >= P.max_refine) break;
       // rho1 = -(grad f + A'(y+dy) + Htilde dx - J'(z+dz)),  rho2 = -(A (x+dx) - b)
-      KV gd, jz2, rr; double wd2, dpin[4], dxp[4];
+      KV gd, jz2; double wd2, dpin[4], dxp[4];
       next_pi(dd, dpin); prev_state(dd, true, dxp);
       l_grad_Aty<C>(P, c, dd, dd, dpin, false, gd);
       l_gather<C, true>(g, pr, d::N_G, H.gv, jz2, wd2);
       double nres = 0.0;
       LUNR for (int i = 0; i < 4; i++) {
         const double ht = c.qw + dw - ((i & 1) ? 0.0 : 2.0 * zd);
-        rr.xs[i] = -(gfy.xs[i] + gd.xs[i] + ht * dd.xs[i] - jz2.xs[i]);
-        nres = fmax(nres, fabs(rr.xs[i]));
+        r.xs[i] = -(gfy.xs[i] + gd.xs[i] + ht * dd.xs[i] - jz2.xs[i]);
+        nres = fmax(nres, fabs(r.xs[i]));
       }
-      LUNR for (int a = 0; a < 2; a++) { rr.us[a] = -(gfy.us[a] + gd.us[a] + (P.Rw + dw) * dd.us[a] - jz2.us[a]); nres = fmax(nres, fabs(rr.us[a])); }
+      LUNR for (int a = 0; a < 2; a++) { r.us[a] = -(gfy.us[a] + gd.us[a] + (P.Rw + dw) * dd.us[a] - jz2.us[a]); nres = fmax(nres, fabs(r.us[a])); }
       LUNR for (int i = 0; i < 4; i++) {
-        rr.lm[i] = (i < C) ? -(gfy.lm[i] + gd.lm[i] + (dw + P.rho_lambda) * dd.lm[i] - jz2.lm[i]) : 0.0;
-        nres = fmax(nres, fabs(rr.lm[i]));
+        r.lm[i] = (i < C) ? -(gfy.lm[i] + gd.lm[i] + (dw + P.rho_lambda) * dd.lm[i] - jz2.lm[i]) : 0.0;
+        nres = fmax(nres, fabs(r.lm[i]));
       }
-      rr.dl = -(gfy.dl + (P.slw + dw) * dd.dl - wd2);
-      nres = fmax(nres, fabs(rr.dl));
+      r.dl = -(gfy.dl + (P.slw + dw) * dd.dl - wd2);
+      nres = fmax(nres, fabs(r.dl));
       {
         double hp[4], hn[2], he;
         l_eq_residual<C>(P, c, dd, dxp, true, hp, hn, he);
-        LUNR for (int i = 0; i < 4; i++) { rr.pi[i] = -(re_pi[i] + hp[i]); nres = fmax(nres, fabs(rr.pi[i])); }
-        LUNR for (int a = 0; a < 2; a++) { rr.nu[a] = -(re_nu[a] + hn[a]); nres = fmax(nres, fabs(rr.nu[a])); }
-        rr.eta = -(re_eta + he); nres = fmax(nres, fabs(rr.eta));
+        LUNR for (int i = 0; i < 4; i++) { r.pi[i] = -(re_pi[i] + hp[i]); nres = fmax(nres, fabs(r.pi[i])); }
+        LUNR for (int a = 0; a < 2; a++) { r.nu[a] = -(re_nu[a] + hn[a]); nres = fmax(nres, fabs(r.nu[a])); }
+        r.eta = -(re_eta + he); nres = fmax(nres, fabs(r.eta));
       }
       nres = g_max(g, nres);
       const double nrhs = fmax(e_d, e_p);
@@ -1125,52 +1097,28 @@ struct LaneSolver {
       {
         KV jb; double wdb;
         l_gather<C, true>(g, pr, d::N_EV, H.gv, jb, wdb);
-        LUNR for (int i = 0; i < 4; i++) { rr.xs[i] += jb.xs[i]; rr.lm[i] += jb.lm[i]; }
-        LUNR for (int a = 0; a < 2; a++) rr.us[a] += jb.us[a];
-        rr.dl += wdb;
+        LUNR for (int i = 0; i < 4; i++) { r.xs[i] += jb.xs[i]; r.lm[i] += jb.lm[i]; }
+        LUNR for (int a = 0; a < 2; a++) r.us[a] += jb.us[a];
+        r.dl += wdb;
       }
-      KV d2; double tb2[4];
-      l_kkt_solve_border<C>(g, P, c, H, f, dw, pr, bf, rr, d2, tb2);
-      double d2p[4]; prev_state(d2, true, d2p);
-      nlp_scatter_de(d::N_G, d2, d2p);
-      const double tbj = l_sel4(tb2, g.j);
-      LSLOTS for (int s = 0; s < d::NS; s++) {
-        if (l_slot_valid<C>(s, g)) {
-          const bool vhi = s != d::SD;
-          const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
-          const double rlo = pr(d::N_A + s), rhi = pr(d::N_B + s);
-          const double de = pr(d::N_C + s), dzl = pr(d::N_D + s), dzh = pr(d::N_E + s), dde = pr(d::N_G + s);
-          const double rcl = (mu - slo * zlo) - (slo * dzl + zlo * de);
-          const double rch = vhi ? (mu - shi * zhi) - (shi * dzh - zhi * de) : 0.0;
-          double cl = rcl * rlo - zlo * rlo * dde;
-          const double ch = vhi ? rch * rhi + zhi * rhi * dde : 0.0;
-          if (s == d::SD && H.capped) cl = rcl * rlo - H.sc * dde - tbj;
-          pr(d::N_C + s) = de + dde; pr(d::N_D + s) = dzl + cl; pr(d::N_E + s) = dzh + ch;
-        }
-      }
-      LUNR for (int i = 0; i < 4; i++) { dd.xs[i] += d2.xs[i]; dd.lm[i] += d2.lm[i]; dd.pi[i] += d2.pi[i]; }
-      LUNR for (int a = 0; a < 2; a++) { dd.us[a] += d2.us[a]; dd.nu[a] += d2.nu[a]; }
-      dd.dl += d2.dl; dd.eta += d2.eta;
-      quad = dd.xs[0] * dd.xs[0] + dd.xs[2] * dd.xs[2];
     }
-    // ---- fraction to the boundary (alpha_max = min(1, tau / max_i(-ds_i / s_i))) and the line-search constants
+    const double quad = dd.xs[0] * dd.xs[0] + dd.xs[2] * dd.xs[2];
+    // ---- pass C: fraction to the boundary (alpha_max = min(1, tau / max_i(-ds_i / s_i))) and the line-search constants
     //      phi = f - mu sum log s, its directional derivative, sum of slack products (for log)
     double a_pmax, a_dmax, ph, dphi, dQd, gdx;
     {
       double rp = 0.0, rdm = 0.0, prod = 1.0, prod2 = 1.0, dsum = 0.0;
-      LSLOTS for (int s = 0; s < d::NS; s++) {
-        if (l_slot_valid<C>(s, g)) {
-          const bool vhi = s != d::SD;
-          const double de = pr(d::N_C + s), rlo = pr(d::N_A + s), rhi = pr(d::N_B + s);
-          rp = fmax(rp, -de * rlo);
-          if (vhi) rp = fmax(rp, de * rhi);
-          double zq = -pr(d::N_D + s) * l_rcp(pr(d::N_ZLO + s));
-          if (vhi) zq = fmax(zq, -pr(d::N_E + s) * l_rcp(pr(d::N_ZHI + s)));
-          rdm = fmax(rdm, zq);
-          const double ss = pr(d::N_SLO + s) * pr(d::N_SHI + s);
-          if (s & 1) prod *= ss; else prod2 *= ss;
-          dsum += de * rlo - (vhi ? de * rhi : 0.0);
-        }
+      LSLOTS for (int s = 0; s < nsn; s++) {
+        const bool vhi = s != d::SD;
+        const double de = pr(d::N_C + s), rlo = pr(d::N_A + s), rhi = pr(d::N_B + s);
+        rp = fmax(rp, -de * rlo);
+        if (vhi) rp = fmax(rp, de * rhi);
+        double zq = -pr(d::N_D + s) * l_rcp(pr(d::N_ZLO + s));
+        if (vhi) zq = fmax(zq, -pr(d::N_E + s) * l_rcp(pr(d::N_ZHI + s)));
+        rdm = fmax(rdm, zq);
+        const double ss = pr(d::N_SLO + s) * pr(d::N_SHI + s);
+        if (s & 1) prod *= ss; else prod2 *= ss;
+        dsum += de * rlo - (vhi ? de * rhi : 0.0);
       }
       rp = g_max(g, rp); rdm = g_max(g, rdm);
       a_pmax = (rp > tau) ? tau / rp : 1.0; a_dmax = (rdm > tau) ? tau / rdm : 1.0;
@@ -1189,7 +1137,7 @@ struct LaneSolver {
       dphi = gdx - mu * g_sum(g, dsum);
       dQd = g_sum(g, qd);
     }
-    // ---- filter line search (theta = ||A x - b||_1 shrinks by (1 - alpha))
+    // ---- filter line search (theta = ||A x - b||_1 shrinks by (1 - alpha)); pass D per trial
     double alpha = a_pmax;
     bool accepted = false, ftype = false;
     while (alpha >= P.alpha_min) {
@@ -1197,15 +1145,13 @@ struct LaneSolver {
       double prod = 1.0, prod2 = 1.0;
       bool pos = true;
       const double aq = alpha * alpha * quad;
-      LSLOTS for (int s = 0; s < d::NS; s++) {
-        if (l_slot_valid<C>(s, g)) {
-          const bool vhi = s != d::SD;
-          const double et = alpha * pr(d::N_C + s) + ((s == d::SD) ? aq : 0.0);
-          const double sl = pr(d::N_SLO + s) + et, sh = vhi ? pr(d::N_SHI + s) - et : 1.0;
-          pos = pos && (sl > 0.0) && (sh > 0.0);
-          const double t = (sl * pr(d::N_A + s)) * (vhi ? sh * pr(d::N_B + s) : 1.0);
-          if (s & 1) prod *= t; else prod2 *= t;
-        }
+      LSLOTS for (int s = 0; s < nsn; s++) {
+        const bool vhi = s != d::SD;
+        const double et = alpha * pr(d::N_C + s) + ((s == d::SD) ? aq : 0.0);
+        const double sl = pr(d::N_SLO + s) + et, sh = vhi ? pr(d::N_SHI + s) - et : 1.0;
+        pos = pos && (sl > 0.0) && (sh > 0.0);
+        const double t = (sl * pr(d::N_A + s)) * (vhi ? sh * pr(d::N_B + s) : 1.0);
+        if (s & 1) prod *= t; else prod2 *= t;
       }
       const bool allpos = g_all(g, pos);
       const double dlog = g_sum(g, allpos ? log(prod) + log(prod2) : 0.0);
@@ -1239,14 +1185,12 @@ struct LaneSolver {
       pr(d::F_FILT + 2 * nfilt) = (1.0 - P.gamma_theta) * th; pr(d::F_FILT + 2 * nfilt + 1) = ph - P.gamma_phi * th;
       nfilt++;
     }
-    // ---- update
+    // ---- update (the multiplier step z += a_dmax dz is applied by pass A of the next iteration)
     LUNR for (int i = 0; i < 4; i++) { x.xs[i] += alpha * dd.xs[i]; x.pi[i] += alpha * dd.pi[i]; }
     LUNR for (int i = 0; i < C; i++) x.lm[i] += alpha * dd.lm[i];
     LUNR for (int a = 0; a < 2; a++) { x.us[a] += alpha * dd.us[a]; x.nu[a] += alpha * dd.nu[a]; }
     x.dl += alpha * dd.dl; x.eta += alpha * dd.eta;
-    LSLOTS for (int s = 0; s < d::NS; s++) {
-      if (l_slot_valid<C>(s, g)) { pr(d::N_ZLO + s) += a_dmax * pr(d::N_D + s); if (s != d::SD) pr(d::N_ZHI + s) += a_dmax * pr(d::N_E + s); }
-    }
+    ad_prev = a_dmax;
     nl_it = it + 1;
     return false;
   }
@@ -1262,6 +1206,7 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
   constexpr int NW = d::NW;
   LaneSolver<C> S;
   S.g = grp_make(); S.pr = pr;
+  S.nsq = l_nslots<C, false>(S.g); S.nsn = l_nslots<C, true>(S.g);
   const Grp& g = S.g;
   const int j = g.j;
   const size_t B = (size_t)io.B;
@@ -1361,18 +1306,19 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
   unsigned w[4] = {0u, 0u, 0u, 0u};
   {
     const bool nlp = io.mode == 1;
+    const int st = nlp ? d::NS : d::NSQP;  // field stride, and slot order, of the stage that ran last
+    const int SF = nlp ? d::SFN : d::SFQ;
     LUNR for (int s = 0; s < d::NS; s++) {
-      if (l_slot_valid<C>(s, g) && (s < d::NSQP || nlp)) {
+      if (s < st && !(j == 0 && s >= SF && s < SF + 2)) {
         int rlo = -1, rhi = -1;
         if (s < d::SU) { rhi = 12 + 4 * j + s; rlo = 28 + 4 * j + s; }
         else if (s < d::SL) { rhi = 44 + 2 * j + (s - d::SU); rlo = 52 + 2 * j + (s - d::SU); }
-        else if (s < d::SF) { rlo = 60 + C * j + (s - d::SL); rhi = 60 + 4 * C + C * j + (s - d::SL); }
-        else if (s < d::SV) { rhi = 2 * (j - 1) + (s - d::SF); rlo = 6 + rhi; }
+        else if (s < d::SL + C) { rlo = 60 + C * j + (s - d::SL); rhi = 60 + 4 * C + C * j + (s - d::SL); }
+        else if (s >= SF) { rhi = 2 * (j - 1) + (s - SF); rlo = 6 + rhi; }
         else if (s < d::SD) { const int q = (s - d::SV) ? 4 + j : j; rhi = d::MQP + 4 + q; rlo = d::MQP + 12 + q; }
         else { rlo = d::MQP + j; }
-        const int st = nlp ? d::NS : d::NSQP;  // field stride of the stage that ran last
         if (rlo >= 0 && pr(2 * st + s) > pr(s)) w[rlo >> 5] |= 1u << (rlo & 31);
-        if (rhi >= 0 && s != d::SD && pr(3 * st + s) > pr(st + s)) w[rhi >> 5] |= 1u << (rhi & 31);
+        if (rhi >= 0 && !(nlp && s == d::SD) && pr(3 * st + s) > pr(st + s)) w[rhi >> 5] |= 1u << (rhi & 31);
       }
     }
     LUNR for (int k = 0; k < 4; k++) w[k] = g_or(g, w[k]);

@@ -30,7 +30,11 @@ LDEV unsigned g_bits(const Grp& g, bool p) { return (__ballot_sync(g.mask, p) >>
 LDEV bool g_any(const Grp& g, bool p) { return (__ballot_sync(g.mask, p) & g.mask) != 0u; }
 LDEV bool g_all(const Grp& g, bool p) { return (__ballot_sync(g.mask, p) & g.mask) == g.mask; }
 // warp-wide vote used only for loop control ("does any group of this warp still iterate"); all 32 lanes converge here
+#if defined(LANE_NT) && LANE_NT > 32  // several warps per CTA kept within one solver iteration of each other (shared i-cache lines)
+LDEV bool w_any(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
+#else
 LDEV bool w_any(bool p) { return __any_sync(LFULL, p); }
+#endif
 LDEV double l_rcp(double v) {  // 1/v: MUFU.RCP64H seed + two Newton steps (~1 ulp for normal operands)
 #if defined(CBF_EXACT_DIV) || defined(CBF_EXACT_RCP)
   return 1.0 / v;
