@@ -251,7 +251,8 @@ def main():
         except Exception: pass
         ach_gbs = (bi + bo) * B / (kern_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms_per_step, "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config,
                 "converged_fraction": conv_all / inst_all, "instances": int(inst_all), "kkt_max_converged": float(kkt[status == 0].max()) if conv else None,
                 "mean_iters": {"qp": float(qp_it.mean()), "nlp": float(nl_it[status == 0].mean()) if conv else None},
