@@ -59,3 +59,86 @@ def test_cfg3_1024_parity(pkg, solver):
     # Bezier epilogue and QP stage
     assert np.abs(out["alpha"].T - ref["alpha"])[both].max() < 1e-6
     assert np.abs(out["x_qp"].T - ref["x_qp"][:, :24]).max() < 1e-8
+
+
+def _check_against_oracle(out, ref, n_active=200):
+    c = H.compare(out, ref, 1e-6)
+    both = c["both"]
+    bad = np.nonzero(both & ((c["ex"] > 1e-6) | (c["eu"] > 1e-6) | (c["es"] > 1e-6)))[0]
+    assert len(bad) == 0, (bad[:10], c["worst"])
+    assert out["kkt"][0][both].max() < 1e-8
+    mism = 0
+    for i in np.nonzero(both)[0][:n_active]:
+        cc = int(ref["c"][i])
+        mism += H.active_rows_oracle(ref, i, cc) != H.active_rows_mask(out, i, cc)
+    assert mism == 0, mism
+    return c
+
+
+def test_cfg3_full_size_4096_against_oracle(pkg, solver):
+    """BASELINE config 3 at its full size, every instance against the oracle (primal 1e-6 relative, KKT < 1e-8, same
+    active set, same set of instances without interior)."""
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    insts = S.cfg3_instances(4096, seed=20251018 + 3000)   # the bench workload
+    out = solver.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP_NLP)
+    ref = H.oracle_batch(insts, mode=1, nthreads=16)
+    c = _check_against_oracle(out, ref, n_active=4096)
+    assert c["status_equal"].mean() > 0.998, np.nonzero(~c["status_equal"])[0][:20]
+    assert c["both"].sum() > 3800
+    assert out["nlp_iters"][0].max() <= 40          # no wandering instance (DESIGN.md section 4)
+    # QP stage: status and answer of every instance (iSWIFT restated); the iteration count may differ by one on a handful
+    outq = solver.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP)
+    refq = H.oracle_batch(insts, mode=0, nthreads=16)
+    assert (outq["status"][0] == 0).all() and (refq["status"] == 0).all()
+    assert (outq["qp_iters"][0] != refq["qp_iters"]).sum() <= 4
+    same = outq["qp_iters"][0] == refq["qp_iters"]
+    assert np.abs(outq["X"].T - refq["X"])[same].max() < 1e-8
+    assert np.abs(outq["X"].T - refq["X"]).max() < 1e-5      # reltol of the QP stage is 1e-6 (GlobalOptions.h:23-26)
+
+
+def test_results_do_not_depend_on_batch_order_or_size(pkg):
+    """Size-independent property: an instance's answer is bit-identical whatever batch it travels in (permuted batch, batch
+    of one, batch padded with other instances) -- instances are independent and the class sort is only a schedule."""
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    insts = S.cfg3_instances(1500)
+    s = pkg.BatchSolver(device=0, max_batch=2048, max_obs=20)
+    base = s.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP_NLP)
+    perm = np.random.default_rng(7).permutation(len(insts))
+    outp = s.solve_host(capi.soa_from_instances([insts[i] for i in perm]), mode=capi.MODE_QP_NLP)
+    for k in ("X", "U", "lam", "slack", "alpha", "kkt", "status", "nlp_iters", "qp_iters", "active"):
+        assert (outp[k] == base[k][:, perm]).all(), k
+    for i in (0, 1, 777, 1499):
+        one = s.solve_host(capi.soa_from_instances([insts[i]]), mode=capi.MODE_QP_NLP)
+        for k in ("X", "U", "slack", "kkt", "status"):
+            assert (one[k][:, 0] == base[k][:, i]).all(), (k, i)
+    s.close()
+
+
+def test_cfg4_size_65536_instances(pkg):
+    """BASELINE config 4's instance count (65536; reference-faithful mode: the agents of a team are independent NLPs) in one
+    launch on one GPU, checked against the oracle on every instance."""
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    B = 65536
+    insts = S.cfg3_instances(B, seed=20251018 + 4000)
+    s = pkg.BatchSolver(device=0, max_batch=B, max_obs=20)
+    out = s.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP_NLP)
+    ref = H.oracle_batch(insts, mode=1, nthreads=16)
+    c = _check_against_oracle(out, ref, n_active=500)
+    assert c["status_equal"].mean() > 0.998
+    assert (out["status"][0] == 1).sum() == 0      # nobody runs into the iteration limit
+    s.close()
+
+
+def test_bezier_chain_and_alpha_buffer_handoff(pkg, solver):
+    """Consecutive cycles: alpha_buf_next of cycle k is the alpha_buf of cycle k+1 (MPC_dist.cpp:792-798); the first Bezier
+    coefficient of every state row then equals the last grid point of the previous cycle."""
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    insts = S.cfg3_instances(64)
+    d = capi.soa_from_instances(insts)
+    o1 = solver.solve_host(d, mode=capi.MODE_QP_NLP)
+    d2 = dict(d); d2["alpha_buf"] = np.ascontiguousarray(o1["alpha_buf_next"])
+    o2 = solver.solve_host(d2, mode=capi.MODE_QP_NLP)
+    assert np.abs(o1["alpha_buf_next"] - o1["X"][12:16]).max() == 0.0
+    a2 = o2["alpha"].reshape(4, 5, -1)
+    assert np.abs(a2[:, 0, :] - o1["X"][12:16]).max() < 1e-9     # curve starts at the buffer
+    assert np.abs(a2[:, 4, :] - o2["X"][12:16]).max() < 1e-9     # and ends at x_4
