@@ -11,6 +11,9 @@
  *                                    src/MPC_dist.cpp:1195-1202, 81-454; include/MPC_dist.hpp:178-181
  *   cbfnmpc_solve_batch_host      <- same, host buffers (copies inside): the call LocoWrapper-side code makes   src/A1_Sim.cpp:227-244
  *   cbfnmpc_solve_dense_nlptuple  <- the nlpTuple boundary type                 include/pack_nlp_data.h:11-29, src/MPC_dist.cpp:403-421
+ *   cbfnmpc_pack_inputs           <- MPC_dist::updateState + copPlanner_eventbase + footholdsPlanner, B agents at once
+ *                                    src/MPC_dist.cpp:1195-1202, 702-782, 1204-1266
+ *   cbfnmpc_run_cycle             <- updateState + run_NMPC from the raw per-cycle inputs (pack, then solve)
  *
  * Plain pointers and sizes only.  All floating point is IEEE FP64.  No CPU fallback exists: every solve runs in
  * the CUDA kernels of libcbfnmpc.so, and every call returns a negative code when no CUDA device is usable.
@@ -114,6 +117,39 @@ int cbfnmpc_solve_dense_nlptuple(cbfnmpc_ctx *ctx, int nv, int p, int mi, const 
                                  const double *Aeq, const double *beq, const double *G, const double *h,
                                  const double *x0_start, const double obs[2], int mode_nlp, double *x_out, int *status,
                                  double *kkt);
+
+/* Raw per-cycle inputs, exactly what MPC_dist::updateState receives plus the object's own state, for B agents.
+ * Structure-of-arrays, batch index fastest; device pointers.
+ *   q, dq        [nq][B]   generalised coordinates / velocities (nq = 18 in the reference; rows 0 and 1 are read)   MPC_dist.cpp:226-229
+ *   contact      [4][B]    contactInd                                                                               :1198
+ *   toe_pos      [12][B]   toePos as Eigen::Matrix<double,3,4> column-major: element (r, foot) at row r + 3*foot    :1199
+ *   gait_domain  [B]       gaitDomain_ (selects the reference columns and the nominal-stance rule)                   :716, :1211
+ *   agent_id     [B]       agent_id_ (rows 2*id, 2*id+1 of the reference trajectory)                                :715-718
+ *   team         [B]       index into the per-team arrays below
+ *   agent_initial[2][B]    agent_Initial_ (set by setPstart)                                                        :1106-1112
+ *   Pr_refined, Prd_refined  [n_teams] matrices 8 x ref_cols, column-major (Eigen::Matrix<double,8,2500>)            MPC_dist.hpp, :930-1104
+ *   Pobs_real    [n_teams] matrices 2 x n_obs, column-major                                                         :1124, :371-396
+ * The reference reads columns [4*gait_domain, 4*gait_domain+4) of the trajectory without a bound check; here a column
+ * index past ref_cols-1 is clamped to the last column. */
+typedef struct {
+  const double *q, *dq;
+  int nq;
+  const int32_t *contact;
+  const double *toe_pos;
+  const int32_t *gait_domain, *agent_id, *team;
+  const double *agent_initial;
+  const double *Pr_refined, *Prd_refined;
+  int ref_cols, n_teams;
+  const double *Pobs_real;
+  int n_obs;
+} cbfnmpc_raw_in;
+
+/* fills packed->x0, xdes, feet_xy, contact, obs_xy (device arrays of the sizes cbfnmpc_in documents; packed->n_obs is ignored,
+ * raw->n_obs columns are written); asynchronous on `cuda_stream` */
+int cbfnmpc_pack_inputs(cbfnmpc_ctx *ctx, int B, const cbfnmpc_raw_in *raw, const cbfnmpc_in *packed, void *cuda_stream);
+/* pack into the context's own staging buffers (B <= max_batch, raw->n_obs <= max_obs), then solve; alpha_buf [4][B] device */
+int cbfnmpc_run_cycle(cbfnmpc_ctx *ctx, int B, int mode, const cbfnmpc_raw_in *raw, const double *alpha_buf,
+                      const cbfnmpc_out *out, void *cuda_stream);
 
 /* FP64 DFMA peak microbenchmark (TFLOP/s) used as the roofline denominator by bench.py */
 int cbfnmpc_measure_fp64_peak(cbfnmpc_ctx *ctx, double *tflops);

@@ -141,6 +141,31 @@ void orc_pack_dense(const orc_gains *g, const double *x0, const double *xdes, co
 #undef GG
 }
 
+/* copPlanner_eventbase (src/MPC_dist.cpp:702-782, effective semantics: use_bezier is false): columns [N g, N g + N) of rows
+ * 2a, 2a+1 of Pr_refined_ / Prd_refined_ (8 x ref_cols, column-major) -> com_desired_Traj_vec_eventbased_ ([x,xd,y,yd] x N).
+ * Columns past the end are clamped (the reference has no bound check). */
+void orc_cop_planner(const double *Pr, const double *Prd, int ref_cols, int agent_id, int gait_domain, double *xdes16) {
+  for (int k = 0; k < 4; k++) {
+    int col = 4 * gait_domain + k;
+    if (col > ref_cols - 1) col = ref_cols - 1;
+    if (col < 0) col = 0;
+    xdes16[4 * k + 0] = Pr[2 * agent_id + 8 * (size_t)col];      /* :715 */
+    xdes16[4 * k + 1] = Prd[2 * agent_id + 8 * (size_t)col];     /* :716 */
+    xdes16[4 * k + 2] = Pr[2 * agent_id + 1 + 8 * (size_t)col];  /* :717 */
+    xdes16[4 * k + 3] = Prd[2 * agent_id + 1 + 8 * (size_t)col]; /* :718 */
+  }
+}
+
+/* footholdsPlanner, first part (src/MPC_dist.cpp:1204-1216): toePos (3x4 column-major) -> feet_xy (x of FR,FL,RR,RL then y);
+ * during the first two gait domains the nominal footprint about agent_Initial_ replaces the measured toes. */
+void orc_footholds(const double *toe_pos12, int gait_domain, const double *agent_initial, double *feet_xy8) {
+  static const double fp[4][2] = {{0.2188, -0.1320}, {0.2188, 0.1320}, {-0.1472, -0.1320}, {-0.1472, 0.1320}}; /* :1206-1209 */
+  for (int i = 0; i < 4; i++) {
+    feet_xy8[i] = (gait_domain <= 1) ? fp[i][0] + agent_initial[0] : toe_pos12[3 * i];
+    feet_xy8[4 + i] = (gait_domain <= 1) ? fp[i][1] + agent_initial[1] : toe_pos12[3 * i + 1];
+  }
+}
+
 int orc_closest_obstacle(const double *pos, const double *obs_xy, int K, double *out) {
   double min_dist = 1000; /* src/MPC_dist.cpp:371 */
   int min_i = 0;

@@ -66,6 +66,8 @@ def lib():
         _lib.orc_stance_matrix.argtypes = [dp, ip, dp]
         _lib.orc_pack_dense.argtypes = [C.POINTER(Gains), dp, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp]
         _lib.orc_closest_obstacle.argtypes = [dp, dp, C.c_int, dp]
+        _lib.orc_cop_planner.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, dp]
+        _lib.orc_footholds.argtypes = [dp, C.c_int, dp, dp]
         _lib.orc_bezier_fit.argtypes = [dp, dp, dp, dp]
         _lib.orc_qp_mehrotra.argtypes = [C.c_int] * 3 + [dp] * 6 + [C.c_double, C.c_double, C.c_int, C.c_double] + [dp] * 4 + [C.POINTER(C.c_int)]
         _lib.orc_nlp_ipm.argtypes = [C.c_int, C.c_int] + [dp] * 6 + [dp, dp, C.c_int, C.POINTER(Gains), C.POINTER(Options), C.POINTER(Result)]
@@ -98,6 +100,22 @@ def default_gains():
 
 def _f(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def cop_planner(Pr, Prd, agent_id, gait_domain):
+    """Pr, Prd: 8 x ref_cols (any layout; passed column-major like Eigen).  Returns xdes (16)."""
+    Prc = np.ascontiguousarray(np.asarray(Pr, float).T); Prdc = np.ascontiguousarray(np.asarray(Prd, float).T)
+    out = np.zeros(16)
+    lib().orc_cop_planner(Prc.reshape(-1), Prdc.reshape(-1), Prc.shape[0], int(agent_id), int(gait_domain), out)
+    return out
+
+
+def footholds(toe_pos, gait_domain, agent_initial):
+    """toe_pos 3 x 4.  Returns feet_xy (8): x of FR,FL,RR,RL then y."""
+    tp = np.ascontiguousarray(np.asarray(toe_pos, float).T).reshape(-1)  # column-major 3x4
+    out = np.zeros(8)
+    lib().orc_footholds(tp, int(gait_domain), _f(agent_initial), out)
+    return out
 
 
 def lip_discrete(g=None):

@@ -36,6 +36,8 @@ def load():
     L.cbfnmpc_set_options.argtypes = [C.c_void_p, C.POINTER(capi.Options)]
     L.cbfnmpc_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.In), C.POINTER(capi.Out), C.c_void_p]
     L.cbfnmpc_solve_batch_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.In), C.POINTER(capi.Out)]
+    L.cbfnmpc_pack_inputs.argtypes = [C.c_void_p, C.c_int, C.POINTER(capi.RawIn), C.POINTER(capi.In), C.c_void_p]
+    L.cbfnmpc_run_cycle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.RawIn), C.c_void_p, C.POINTER(capi.Out), C.c_void_p]
     L.cbfnmpc_launch_count.argtypes = [C.c_void_p]
     L.cbfnmpc_launch_count.restype = C.c_longlong
     L.cbfnmpc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -47,7 +49,8 @@ def load():
 
 EXPORTS = ["cbfnmpc_version", "cbfnmpc_last_error", "cbfnmpc_default_gains", "cbfnmpc_default_options", "cbfnmpc_create",
            "cbfnmpc_destroy", "cbfnmpc_set_gains", "cbfnmpc_set_options", "cbfnmpc_solve_batch", "cbfnmpc_solve_batch_host",
-           "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak"]
+           "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak",
+           "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle"]
 
 
 def default_gains():
@@ -109,6 +112,31 @@ class BatchSolver:
         for k, _ in capi.Out._fields_:
             setattr(so, k, out_ptrs.get(k))
         self._ck(self.L.cbfnmpc_solve_batch(self.ctx, B, mode, C.byref(si), C.byref(so), stream))
+
+    # ---- raw per-cycle inputs (what MPC_dist::updateState receives), device pointers
+    @staticmethod
+    def _raw_struct(raw):
+        r = capi.RawIn()
+        for k, _ in capi.RawIn._fields_:
+            setattr(r, k, raw[k])
+        return r
+
+    def pack_inputs(self, B, raw, packed_ptrs, stream=None):
+        """updateState + copPlanner_eventbase + footholdsPlanner for B agents on the device (cbfnmpc_pack_inputs)."""
+        si = capi.In()
+        for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy"):
+            setattr(si, k, packed_ptrs[k])
+        si.n_obs = raw["n_obs"]
+        r = self._raw_struct(raw)
+        self._ck(self.L.cbfnmpc_pack_inputs(self.ctx, B, C.byref(r), C.byref(si), stream))
+
+    def run_cycle(self, B, raw, alpha_buf_ptr, out_ptrs, mode=capi.MODE_QP_NLP, stream=None):
+        """updateState + run_NMPC from the raw inputs: pack kernel, class sort, solve kernel (cbfnmpc_run_cycle)."""
+        so = capi.Out()
+        for k, _ in capi.Out._fields_:
+            setattr(so, k, out_ptrs.get(k))
+        r = self._raw_struct(raw)
+        self._ck(self.L.cbfnmpc_run_cycle(self.ctx, B, mode, C.byref(r), alpha_buf_ptr, C.byref(so), stream))
 
     def launch_count(self):
         return int(self.L.cbfnmpc_launch_count(self.ctx))

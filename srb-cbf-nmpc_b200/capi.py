@@ -30,6 +30,14 @@ class Out(C.Structure):
                                           "status", "qp_iters", "nlp_iters", "n_fact", "active")]
 
 
+class RawIn(C.Structure):
+    """cbfnmpc_raw_in (include/cbfnmpc.h): device pointers."""
+    _fields_ = [("q", C.c_void_p), ("dq", C.c_void_p), ("nq", C.c_int), ("contact", C.c_void_p), ("toe_pos", C.c_void_p),
+                ("gait_domain", C.c_void_p), ("agent_id", C.c_void_p), ("team", C.c_void_p), ("agent_initial", C.c_void_p),
+                ("Pr_refined", C.c_void_p), ("Prd_refined", C.c_void_p), ("ref_cols", C.c_int), ("n_teams", C.c_int),
+                ("Pobs_real", C.c_void_p), ("n_obs", C.c_int)]
+
+
 OUT_F64 = dict(X=16, U=8, lam=16, slack=1, x_qp=24, alpha=20, alpha_buf_next=4, kkt=1)
 OUT_I32 = dict(status=1, qp_iters=1, nlp_iters=1, n_fact=1)
 IN_F64 = dict(x0=4, xdes=16, feet_xy=8, alpha_buf=4)  # + obs_xy 2K, contact (int32) 4

@@ -68,6 +68,55 @@ __global__ void __launch_bounds__(LANE_NT, 1) cbfnmpc_lane_kernel(const __grid_c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Input packing: updateState + copPlanner_eventbase + footholdsPlanner for B agents, one thread per
+// agent.  Pure data movement (HBM-bound, ~0.9 KB per agent); every store is coalesced (batch index fastest).
+// ---------------------------------------------------------------------------------------------------------
+struct PackIO {
+  cbfnmpc_raw_in r;
+  double *x0, *xdes, *feet, *obs;
+  int* contact;
+  int B;
+};
+__global__ void __launch_bounds__(256) cbfnmpc_pack_kernel(const __grid_constant__ PackIO io) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= io.B) return;
+  const size_t B = (size_t)io.B;
+  const cbfnmpc_raw_in& r = io.r;
+  // measured LIP state (q[0], dq[0], q[1], dq[1])                                      src/MPC_dist.cpp:226-229
+  io.x0[b] = r.q[b]; io.x0[B + b] = r.dq[b]; io.x0[2 * B + b] = r.q[B + b]; io.x0[3 * B + b] = r.dq[B + b];
+  const int g = r.gait_domain[b], a = r.agent_id[b], t = r.team[b];
+  // desired trajectory: columns [4 g, 4 g + 4) of rows 2a, 2a+1 of Pr_refined_ / Prd_refined_, vectorised column-major
+  // as [x, xd, y, yd] x 4                                                               :713-718, :766-780
+  const double* Pr = r.Pr_refined + (size_t)t * 8 * r.ref_cols;
+  const double* Prd = r.Prd_refined + (size_t)t * 8 * r.ref_cols;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int col = 4 * g + k;
+    col = col < r.ref_cols ? col : r.ref_cols - 1;
+    col = col < 0 ? 0 : col;
+    io.xdes[(size_t)(4 * k + 0) * B + b] = Pr[2 * a + 8 * (size_t)col];
+    io.xdes[(size_t)(4 * k + 1) * B + b] = Prd[2 * a + 8 * (size_t)col];
+    io.xdes[(size_t)(4 * k + 2) * B + b] = Pr[2 * a + 1 + 8 * (size_t)col];
+    io.xdes[(size_t)(4 * k + 3) * B + b] = Prd[2 * a + 1 + 8 * (size_t)col];
+  }
+  // stance feet: nominal footprint about agent_Initial_ during the first two domains, measured toes afterwards   :1204-1216
+  const double fpx[4] = {0.2188, 0.2188, -0.1472, -0.1472}, fpy[4] = {-0.1320, 0.1320, -0.1320, 0.1320};
+  const double ax = r.agent_initial[b], ay = r.agent_initial[B + b];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    io.feet[(size_t)i * B + b] = (g <= 1) ? fpx[i] + ax : r.toe_pos[(size_t)(3 * i) * B + b];
+    io.feet[(size_t)(4 + i) * B + b] = (g <= 1) ? fpy[i] + ay : r.toe_pos[(size_t)(3 * i + 1) * B + b];
+    io.contact[(size_t)i * B + b] = r.contact[(size_t)i * B + b];
+  }
+  // real obstacles of the agent's team (Pobs_real, 2 x n_obs column-major) -> x of all obstacles, then y          :371-396
+  const double* Po = r.Pobs_real + (size_t)t * 2 * r.n_obs;
+  for (int k = 0; k < r.n_obs; k++) {
+    io.obs[(size_t)k * B + b] = Po[2 * k];
+    io.obs[(size_t)(r.n_obs + k) * B + b] = Po[2 * k + 1];
+  }
+}
+
 // FP64 pipe microbenchmark: 8 independent DFMA chains per thread.
 __global__ void cbfnmpc_dfma_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -285,6 +334,45 @@ int cbfnmpc_debug_read4(double* out, int reset) {  // debug builds only
   return n[0];
 }
 #endif
+
+static int check_raw(const cbfnmpc_raw_in* r) {
+  if (!r->q || !r->dq || !r->contact || !r->toe_pos || !r->gait_domain || !r->agent_id || !r->team || !r->agent_initial ||
+      !r->Pr_refined || !r->Prd_refined || !r->Pobs_real)
+    return fail(CBFNMPC_ERR_ARG, "cbfnmpc_raw_in: missing array");
+  if (r->nq < 2 || r->ref_cols < 1 || r->n_teams < 1 || r->n_obs < 1) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_raw_in: bad size");
+  return CBFNMPC_OK;
+}
+
+int cbfnmpc_pack_inputs(cbfnmpc_ctx* c, int B, const cbfnmpc_raw_in* raw, const cbfnmpc_in* packed, void* cuda_stream) {
+  if (!c || !raw || !packed || B < 1) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_pack_inputs: bad argument");
+  if (!packed->x0 || !packed->xdes || !packed->feet_xy || !packed->contact || !packed->obs_xy) return fail(CBFNMPC_ERR_ARG, "missing output array");
+  int rc = check_raw(raw);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  PackIO io;
+  io.r = *raw; io.B = B;
+  io.x0 = (double*)packed->x0; io.xdes = (double*)packed->xdes; io.feet = (double*)packed->feet_xy; io.obs = (double*)packed->obs_xy;
+  io.contact = (int*)packed->contact;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  cbfnmpc_pack_kernel<<<(B + 255) / 256, 256, 0, st>>>(io);
+  CK(cudaGetLastError());
+  c->launches++;
+  return CBFNMPC_OK;
+}
+
+int cbfnmpc_run_cycle(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_raw_in* raw, const double* alpha_buf, const cbfnmpc_out* out,
+                      void* cuda_stream) {
+  if (!c || !raw || !out || B < 1) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_run_cycle: bad argument");
+  if (B > c->max_batch) return fail(CBFNMPC_ERR_ARG, "batch larger than max_batch");
+  if (raw->n_obs > c->max_obs) return fail(CBFNMPC_ERR_ARG, "more obstacles than max_obs");
+  if (mode != CBFNMPC_MODE_QP && mode != CBFNMPC_MODE_QP_NLP) return fail(CBFNMPC_ERR_ARG, "bad mode");
+  const size_t Bs = (size_t)B;
+  double* d = c->d_in;  // staging layout of cbfnmpc_solve_batch_host: x0 4 | xdes 16 | feet 8 | alpha_buf 4 | obs 2K
+  cbfnmpc_in din = {d, d + 4 * Bs, d + 20 * Bs, c->d_contact, d + 32 * Bs, raw->n_obs, alpha_buf};
+  int rc = cbfnmpc_pack_inputs(c, B, raw, &din, cuda_stream);
+  if (rc) return rc;
+  return launch(c, B, mode, &din, out, nullptr, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
 
 long long cbfnmpc_launch_count(const cbfnmpc_ctx* c) { return c ? c->launches : 0; }
 

@@ -142,3 +142,58 @@ def test_bezier_chain_and_alpha_buffer_handoff(pkg, solver):
     a2 = o2["alpha"].reshape(4, 5, -1)
     assert np.abs(a2[:, 0, :] - o1["X"][12:16]).max() < 1e-9     # curve starts at the buffer
     assert np.abs(a2[:, 4, :] - o2["X"][12:16]).max() < 1e-9     # and ends at x_4
+
+
+def test_raw_input_packing_and_run_cycle(pkg):
+    """the device pre-kernel (updateState + copPlanner_eventbase + footholdsPlanner for B agents) against the
+    oracle restatement, bit for bit; then cbfnmpc_run_cycle == pack + solve."""
+    import torch
+    import oracle as O
+    from srb_cbf_nmpc_b200 import capi
+    rng = np.random.default_rng(11)
+    T, A, ref_cols, K, nq = 37, 4, 200, 20, 18
+    B = T * A
+    Pr = rng.uniform(-1, 9, size=(T, 8, ref_cols)); Prd = rng.uniform(-0.3, 0.3, size=(T, 8, ref_cols))
+    Pobs = rng.uniform(0, 9, size=(T, 2, K))
+    team = np.repeat(np.arange(T), A).astype(np.int32); agent = np.tile(np.arange(A), T).astype(np.int32)
+    gait = rng.integers(0, 45, size=B).astype(np.int32)
+    ainit = rng.uniform(-1, 1, size=(2, B))
+    q = rng.normal(size=(nq, B)); dq = rng.normal(size=(nq, B)) * 0.2
+    contact = np.array([[1, 1, 1, 1], [0, 1, 1, 0], [1, 0, 0, 1]], np.int32)[rng.integers(0, 3, size=B)].T.copy()
+    toe = rng.normal(size=(12, B))
+    dev = torch.device("cuda", 0)
+    cm = lambda a: np.ascontiguousarray(np.transpose(a, (0, 2, 1)))      # per-team column-major matrices
+    tens = dict(q=q, dq=dq, contact=contact, toe_pos=toe, gait_domain=gait, agent_id=agent, team=team, agent_initial=ainit,
+                Pr_refined=cm(Pr), Prd_refined=cm(Prd), Pobs_real=cm(Pobs))
+    dten = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in tens.items()}
+    raw = {k: v.data_ptr() for k, v in dten.items()}
+    raw.update(nq=nq, ref_cols=ref_cols, n_teams=T, n_obs=K)
+    s = pkg.BatchSolver(device=0, max_batch=B, max_obs=K)
+    packed = {"x0": torch.zeros((4, B), dtype=torch.float64, device=dev), "xdes": torch.zeros((16, B), dtype=torch.float64, device=dev),
+              "feet_xy": torch.zeros((8, B), dtype=torch.float64, device=dev), "contact": torch.zeros((4, B), dtype=torch.int32, device=dev),
+              "obs_xy": torch.zeros((2 * K, B), dtype=torch.float64, device=dev)}
+    s.pack_inputs(B, raw, {k: v.data_ptr() for k, v in packed.items()})
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in packed.items()}
+    for b in range(B):
+        assert np.array_equal(got["x0"][:, b], [q[0, b], dq[0, b], q[1, b], dq[1, b]])
+        assert np.array_equal(got["xdes"][:, b], O.cop_planner(Pr[team[b]], Prd[team[b]], agent[b], gait[b]))
+        assert np.array_equal(got["feet_xy"][:, b], O.footholds(toe[:, b].reshape(4, 3).T, gait[b], ainit[:, b]))
+        assert np.array_equal(got["obs_xy"][:, b], Pobs[team[b]].reshape(-1))
+    assert np.array_equal(got["contact"], contact)
+    # run_cycle: same answers as solving the packed arrays
+    abuf = torch.from_numpy(np.stack([q[0], 0 * q[0], q[1], 0 * q[0]])).to(dev)
+    def outs():
+        o = {k: torch.zeros((n, B), dtype=torch.float64, device=dev) for k, n in capi.OUT_F64.items()}
+        o.update({k: torch.zeros((n, B), dtype=torch.int32, device=dev) for k, n in capi.OUT_I32.items()})
+        o["active"] = torch.zeros((2, B), dtype=torch.int64, device=dev)
+        return o
+    o1, o2 = outs(), outs()
+    s.run_cycle(B, raw, abuf.data_ptr(), {k: v.data_ptr() for k, v in o1.items()}, mode=capi.MODE_QP)
+    ip = {k: v.data_ptr() for k, v in packed.items()}; ip["alpha_buf"] = abuf.data_ptr()
+    s.solve_device(B, ip, {k: v.data_ptr() for k, v in o2.items()}, K, mode=capi.MODE_QP)
+    torch.cuda.synchronize()
+    for k in o1:
+        assert torch.equal(o1[k], o2[k]), k
+    assert (o1["status"] != 4).all()
+    s.close()

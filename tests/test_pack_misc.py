@@ -52,3 +52,33 @@ def test_scenarios_are_seeded():
     for u, v, w in zip(a, b, c):
         assert all(np.array_equal(np.asarray(p), np.asarray(q)) for p, q in zip(u, v))
         assert all(np.array_equal(np.asarray(p), np.asarray(q)) for p, q in zip(u, w))
+
+
+class _NoSolver:  # the mirror's planners are pure host logic; no GPU needed for them
+    pass
+
+
+def _random_team(rng, n_agents=4, ref_cols=60, n_obs=20):
+    Pr = rng.normal(size=(8, ref_cols)); Prd = rng.normal(size=(8, ref_cols))
+    pstart = rng.normal(size=2 * n_agents)
+    obs = rng.uniform(-3, 9, size=(2, n_obs))
+    return Pr, Prd, pstart, obs
+
+
+def test_planner_restatement_matches_the_mirror():
+    """oracle/: copPlanner_eventbase + footholdsPlanner (MPC_dist.cpp:702-782, 1204-1216) against the host mirror class."""
+    from srb_cbf_nmpc_b200.mpc_dist import MPC_dist
+    rng = np.random.default_rng(5)
+    Pr, Prd, pstart, obs = _random_team(rng)
+    for agent in range(4):
+        for g in (0, 1, 2, 7, 14):
+            m = MPC_dist(solver=_NoSolver())
+            m.setAgentID(agent); m.setPstart(pstart); m.setPobs_real(obs); m.setReferenceTrajectory(Pr, Prd)
+            m.gaitDomain_ = g
+            toe = rng.normal(size=(3, 4))
+            m.updateState(rng.normal(size=18), rng.normal(size=18), [1, 0, 0, 1], toe, np.zeros(4))
+            x0, xdes, feet, contact, o = m._instance()
+            assert np.array_equal(O.cop_planner(Pr, Prd, agent, g), xdes)
+            assert np.array_equal(O.footholds(toe, g, pstart[2 * agent:2 * agent + 2]), np.asarray(feet).reshape(-1))
+    # columns past the end are clamped to the last one
+    assert np.array_equal(O.cop_planner(Pr, Prd, 0, 1000)[:4], [Pr[0, -1], Prd[0, -1], Pr[1, -1], Prd[1, -1]])
