@@ -14,6 +14,8 @@
  *   cbfnmpc_pack_inputs           <- MPC_dist::updateState + copPlanner_eventbase + footholdsPlanner, B agents at once
  *                                    src/MPC_dist.cpp:1195-1202, 702-782, 1204-1266
  *   cbfnmpc_run_cycle             <- updateState + run_NMPC from the raw per-cycle inputs (pack, then solve)
+ *   cbfnmpc_closed_loop           <- the receding-horizon loop of src/A1_Sim.cpp:983-1266 on the LIP template (no RaiSim): run_NMPC once
+ *                                    per gait domain, state rolled to the end of the domain, MPC_dist::updateDistance_to_fail (:21-40)
  *
  * Plain pointers and sizes only.  All floating point is IEEE FP64.  No CPU fallback exists: every solve runs in
  * the CUDA kernels of libcbfnmpc.so, and every call returns a negative code when no CUDA device is usable.
@@ -150,6 +152,28 @@ int cbfnmpc_pack_inputs(cbfnmpc_ctx *ctx, int B, const cbfnmpc_raw_in *raw, cons
 /* pack into the context's own staging buffers (B <= max_batch, raw->n_obs <= max_obs), then solve; alpha_buf [4][B] device */
 int cbfnmpc_run_cycle(cbfnmpc_ctx *ctx, int B, int mode, const cbfnmpc_raw_in *raw, const double *alpha_buf,
                       const cbfnmpc_out *out, void *cuda_stream);
+
+/* Closed-loop worlds.  One world = one agent whose raw inputs are the arrays of a cbfnmpc_raw_in; after every
+ * cycle the world is advanced ON THE DEVICE: state <- x_4 of the solution (the end of the gait domain under perfect tracking
+ * of the template), gait_domain += 1, alpha_buf <- alpha_buf_next (MPC_dist.cpp:798, :452), stance feet = nominal footprint
+ * about the new position, contact pattern = 4 feet during the first two domains, then the alternating diagonal pairs of
+ * the trot; success/distance_to_fail follow MPC_dist::updateDistance_to_fail (MPC_dist.cpp:21-40) evaluated at the 4 grid
+ * points of the domain: the first time an obstacle is closer than fail_radius (0.5 in the reference) the world fails and
+ * records its distance from the origin.  The solver status is recorded but, as in the reference, not acted upon.
+ * All pointers are device pointers; q, dq, contact, toe_pos, gait_domain are the SAME arrays as in `raw` (updated in place). */
+typedef struct {
+  double *q, *dq;              /* [nq][B] */
+  int32_t *contact;            /* [4][B] */
+  double *toe_pos;             /* [12][B] */
+  int32_t *gait_domain;        /* [B] */
+  double *alpha_buf;           /* [4][B] */
+  int32_t *success;            /* [B]  1 = no obstacle came within fail_radius so far (initialise to 1) */
+  double *distance_to_fail;    /* [B]  (initialise to the reference's default 10) */
+  int32_t *n_not_converged;    /* [B]  cycles whose solver status was not CBFNMPC_ST_CONVERGED (initialise to 0) */
+  double *traj;                /* optional [n_cycles][4][B]: (x, xd, y, yd) at the end of every cycle */
+} cbfnmpc_world_state;
+int cbfnmpc_closed_loop(cbfnmpc_ctx *ctx, int B, int n_cycles, int mode, const cbfnmpc_raw_in *raw, const cbfnmpc_world_state *w,
+                        double fail_radius, void *cuda_stream);
 
 /* FP64 DFMA peak microbenchmark (TFLOP/s) used as the roofline denominator by bench.py */
 int cbfnmpc_measure_fp64_peak(cbfnmpc_ctx *ctx, double *tflops);

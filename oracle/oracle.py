@@ -205,3 +205,47 @@ def solve_batch(x0, xdes, feet, contact, obs, alpha_buf, mode=1, nthreads=1, g=N
         out["nlp_iters"][i] = r.nlp_iters; out["n_fact"][i] = r.n_fact; out["n_ls"][i] = r.n_ls; out["c"][i] = c
         out["obs"][i] = r.obs[:]; out["z"][i] = r.z[:]; out["s"][i] = r.s[:]; out["y"][i] = r.y[:]
     return out
+
+
+def closed_loop(world, n_cycles, mode=1, fail_radius=0.5, nthreads=8):
+    """CPU restatement of cbfnmpc_closed_loop: per cycle the planners (orc_cop_planner, orc_footholds), one
+    solve per world (orc_solve_batch), MPC_dist::updateDistance_to_fail (src/MPC_dist.cpp:21-40) at the 4 grid points, and the
+    world update (state <- x_4, gaitDomain_ += 1, alpha buffer, nominal footprint about the new position, trot contacts).
+    `world`: host arrays in the layout of scenarios.mc_worlds; updated in place; returns the trajectory [n_cycles][4][B]."""
+    w = world
+    B = w["q"].shape[1]; K = w["n_obs"]
+    fp = np.array([[0.2188, 0.2188, -0.1472, -0.1472], [-0.1320, 0.1320, -0.1320, 0.1320]])   # src/MPC_dist.cpp:1206-1209
+    traj = np.zeros((n_cycles, 4, B))
+    for cyc in range(n_cycles):
+        x0 = np.stack([w["q"][0], w["dq"][0], w["q"][1], w["dq"][1]], 1)
+        xdes = np.zeros((B, 16)); feet = np.zeros((B, 2, 4)); obs = np.zeros((B, 2, K))
+        for b in range(B):
+            t = int(w["team"][b])
+            xdes[b] = cop_planner(w["Pr_refined"][t].T, w["Prd_refined"][t].T, int(w["agent_id"][b]), int(w["gait_domain"][b]))
+            feet[b] = footholds(w["toe_pos"][:, b].reshape(4, 3).T, int(w["gait_domain"][b]), w["agent_initial"][:, b]).reshape(2, 4)
+            obs[b] = w["Pobs_real"][t].T
+        r = solve_batch(x0, xdes, feet, np.ascontiguousarray(w["contact"].T), obs, np.ascontiguousarray(w["alpha_buf"].T), mode=mode,
+                        nthreads=nthreads)
+        X = r["X"]
+        w["n_not_converged"] += (r["status"] != 0).astype(np.int32)
+        for b in range(B):
+            if w["success"][b]:
+                done = False
+                for k in range(4):
+                    px, py = X[b, 4 * k], X[b, 4 * k + 2]
+                    for i in range(K):
+                        dx, dy = px - obs[b, 0, i], py - obs[b, 1, i]
+                        if np.sqrt(dx * dx + dy * dy) < fail_radius:
+                            w["success"][b] = 0; w["distance_to_fail"][b] = np.sqrt(px * px + py * py); done = True
+                            break
+                    if done: break
+        w["q"][0] = X[:, 12]; w["dq"][0] = X[:, 13]; w["q"][1] = X[:, 14]; w["dq"][1] = X[:, 15]
+        traj[cyc] = X[:, 12:16].T
+        w["alpha_buf"][:] = r["alpha_buf_next"].T
+        w["gait_domain"] += 1
+        g = w["gait_domain"]
+        for i in range(4):
+            w["toe_pos"][3 * i] = w["q"][0] + fp[0, i]; w["toe_pos"][3 * i + 1] = w["q"][1] + fp[1, i]; w["toe_pos"][3 * i + 2] = 0.0
+            diag = 1 if i in (0, 3) else 0
+            w["contact"][i] = np.where(g <= 1, 1, np.where(g & 1, diag, 1 - diag))
+    return traj

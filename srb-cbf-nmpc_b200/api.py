@@ -38,6 +38,7 @@ def load():
     L.cbfnmpc_solve_batch_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.In), C.POINTER(capi.Out)]
     L.cbfnmpc_pack_inputs.argtypes = [C.c_void_p, C.c_int, C.POINTER(capi.RawIn), C.POINTER(capi.In), C.c_void_p]
     L.cbfnmpc_run_cycle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.RawIn), C.c_void_p, C.POINTER(capi.Out), C.c_void_p]
+    L.cbfnmpc_closed_loop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(capi.RawIn), C.POINTER(capi.WorldState), C.c_double, C.c_void_p]
     L.cbfnmpc_launch_count.argtypes = [C.c_void_p]
     L.cbfnmpc_launch_count.restype = C.c_longlong
     L.cbfnmpc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -50,7 +51,7 @@ def load():
 EXPORTS = ["cbfnmpc_version", "cbfnmpc_last_error", "cbfnmpc_default_gains", "cbfnmpc_default_options", "cbfnmpc_create",
            "cbfnmpc_destroy", "cbfnmpc_set_gains", "cbfnmpc_set_options", "cbfnmpc_solve_batch", "cbfnmpc_solve_batch_host",
            "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak",
-           "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle"]
+           "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle", "cbfnmpc_closed_loop"]
 
 
 def default_gains():
@@ -137,6 +138,15 @@ class BatchSolver:
             setattr(so, k, out_ptrs.get(k))
         r = self._raw_struct(raw)
         self._ck(self.L.cbfnmpc_run_cycle(self.ctx, B, mode, C.byref(r), alpha_buf_ptr, C.byref(so), stream))
+
+    def closed_loop(self, B, n_cycles, raw, world, mode=capi.MODE_QP_NLP, fail_radius=0.5, stream=None):
+        """n_cycles receding-horizon cycles of B worlds, entirely on the device (cbfnmpc_closed_loop).  `world`: dict of
+        device pointers (q, dq, contact, toe_pos, gait_domain must be the arrays of `raw`)."""
+        w = capi.WorldState()
+        for k, _ in capi.WorldState._fields_:
+            setattr(w, k, world.get(k))
+        r = self._raw_struct(raw)
+        self._ck(self.L.cbfnmpc_closed_loop(self.ctx, B, n_cycles, mode, C.byref(r), C.byref(w), fail_radius, stream))
 
     def launch_count(self):
         return int(self.L.cbfnmpc_launch_count(self.ctx))

@@ -38,6 +38,12 @@ class RawIn(C.Structure):
                 ("Pobs_real", C.c_void_p), ("n_obs", C.c_int)]
 
 
+class WorldState(C.Structure):
+    """cbfnmpc_world_state (include/cbfnmpc.h): device pointers."""
+    _fields_ = [(k, C.c_void_p) for k in ("q", "dq", "contact", "toe_pos", "gait_domain", "alpha_buf", "success", "distance_to_fail",
+                                          "n_not_converged", "traj")]
+
+
 OUT_F64 = dict(X=16, U=8, lam=16, slack=1, x_qp=24, alpha=20, alpha_buf_next=4, kkt=1)
 OUT_I32 = dict(status=1, qp_iters=1, nlp_iters=1, n_fact=1)
 IN_F64 = dict(x0=4, xdes=16, feet_xy=8, alpha_buf=4)  # + obs_xy 2K, contact (int32) 4

@@ -117,6 +117,61 @@ __global__ void __launch_bounds__(256) cbfnmpc_pack_kernel(const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// World update of the closed loop: one thread per world.
+// ---------------------------------------------------------------------------------------------------------
+struct RollIO {
+  cbfnmpc_world_state w;
+  const double *X, *abuf_next, *agent_initial, *Pobs_real;
+  const int *status, *team;
+  int B, n_obs, cycle;
+  double fail_radius;
+};
+__global__ void __launch_bounds__(256) cbfnmpc_rollout_kernel(const __grid_constant__ RollIO io) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= io.B) return;
+  const size_t B = (size_t)io.B;
+  if (io.status[b] != CBFNMPC_ST_CONVERGED) io.w.n_not_converged[b] += 1;
+  // updateDistance_to_fail (src/MPC_dist.cpp:21-40) at the 4 grid points of this domain
+  if (io.w.success[b]) {
+    const double* Po = io.Pobs_real + (size_t)io.team[b] * 2 * io.n_obs;
+    bool failed = false;
+    for (int k = 0; k < 4 && !failed; k++) {
+      const double px = io.X[(size_t)(4 * k) * B + b], py = io.X[(size_t)(4 * k + 2) * B + b];
+      for (int i = 0; i < io.n_obs; i++) {
+        const double dx = px - Po[2 * i], dy = py - Po[2 * i + 1];
+        if (sqrt(dx * dx + dy * dy) < io.fail_radius) {
+          failed = true;
+          io.w.success[b] = 0;
+          io.w.distance_to_fail[b] = sqrt(px * px + py * py);
+          break;
+        }
+      }
+    }
+  }
+  // next measured state = x_4 (end of the gait domain)
+  const double x = io.X[12 * B + b], xd = io.X[13 * B + b], y = io.X[14 * B + b], yd = io.X[15 * B + b];
+  io.w.q[b] = x; io.w.dq[b] = xd; io.w.q[B + b] = y; io.w.dq[B + b] = yd;
+  if (io.w.traj) {
+    double* t = io.w.traj + (size_t)io.cycle * 4 * B;
+    t[b] = x; t[B + b] = xd; t[2 * B + b] = y; t[3 * B + b] = yd;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) io.w.alpha_buf[(size_t)i * B + b] = io.abuf_next[(size_t)i * B + b];  // src/MPC_dist.cpp:798
+  const int g = io.w.gait_domain[b] + 1;                                                              // :452
+  io.w.gait_domain[b] = g;
+  // stance feet under the body, trot contact sequence
+  const double fpx[4] = {0.2188, 0.2188, -0.1472, -0.1472}, fpy[4] = {-0.1320, 0.1320, -0.1320, 0.1320};  // :1206-1209
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    io.w.toe_pos[(size_t)(3 * i) * B + b] = x + fpx[i];
+    io.w.toe_pos[(size_t)(3 * i + 1) * B + b] = y + fpy[i];
+    io.w.toe_pos[(size_t)(3 * i + 2) * B + b] = 0.0;
+    const int diag = (i == 0 || i == 3) ? 1 : 0;       // FR, RL
+    io.w.contact[(size_t)i * B + b] = (g <= 1) ? 1 : ((g & 1) ? diag : 1 - diag);
+  }
+}
+
 // FP64 pipe microbenchmark: 8 independent DFMA chains per thread.
 __global__ void cbfnmpc_dfma_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -372,6 +427,35 @@ int cbfnmpc_run_cycle(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_raw_in* raw
   int rc = cbfnmpc_pack_inputs(c, B, raw, &din, cuda_stream);
   if (rc) return rc;
   return launch(c, B, mode, &din, out, nullptr, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
+
+int cbfnmpc_closed_loop(cbfnmpc_ctx* c, int B, int n_cycles, int mode, const cbfnmpc_raw_in* raw, const cbfnmpc_world_state* w,
+                        double fail_radius, void* cuda_stream) {
+  if (!c || !raw || !w || B < 1 || n_cycles < 1) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_closed_loop: bad argument");
+  if (!w->q || !w->dq || !w->contact || !w->toe_pos || !w->gait_domain || !w->alpha_buf || !w->success || !w->distance_to_fail ||
+      !w->n_not_converged)
+    return fail(CBFNMPC_ERR_ARG, "cbfnmpc_world_state: missing array");
+  if (w->q != raw->q || w->dq != raw->dq || w->contact != raw->contact || w->toe_pos != raw->toe_pos || w->gait_domain != raw->gait_domain)
+    return fail(CBFNMPC_ERR_ARG, "cbfnmpc_world_state must alias the arrays of cbfnmpc_raw_in");
+  if (B > c->max_batch) return fail(CBFNMPC_ERR_ARG, "batch larger than max_batch");
+  if (!(fail_radius > 0.0)) return fail(CBFNMPC_ERR_ARG, "fail_radius must be positive");
+  const size_t Bs = (size_t)B;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  double* o = c->d_out;  // staging layout of cbfnmpc_solve_batch_host
+  cbfnmpc_out dout;
+  memset(&dout, 0, sizeof(dout));
+  dout.X = o; dout.U = o + 16 * Bs; dout.alpha_buf_next = o + 85 * Bs; dout.kkt = o + 89 * Bs; dout.status = c->d_outi;
+  for (int cyc = 0; cyc < n_cycles; cyc++) {
+    int rc = cbfnmpc_run_cycle(c, B, mode, raw, w->alpha_buf, &dout, st);
+    if (rc) return rc;
+    RollIO io;
+    io.w = *w; io.X = dout.X; io.abuf_next = dout.alpha_buf_next; io.agent_initial = raw->agent_initial; io.Pobs_real = raw->Pobs_real;
+    io.status = dout.status; io.team = raw->team; io.B = B; io.n_obs = raw->n_obs; io.cycle = cyc; io.fail_radius = fail_radius;
+    cbfnmpc_rollout_kernel<<<(B + 255) / 256, 256, 0, st>>>(io);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  return CBFNMPC_OK;
 }
 
 long long cbfnmpc_launch_count(const cbfnmpc_ctx* c) { return c ? c->launches : 0; }

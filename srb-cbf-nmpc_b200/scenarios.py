@@ -60,3 +60,31 @@ def cfg2_team():
         feet = p0[:, None] + NOMINAL_FEET
         out.append((x0, xdes, feet, [1, 1, 1, 1], obs.copy()))
     return out
+
+
+def mc_worlds(B, n_cycles, seed=20251018 + 6000, n_obs=20, v_ref=0.2):
+    """Closed-loop Monte-Carlo worlds (the reference's series of randomised runs, src/A1_Sim.cpp:944-1266, on the
+    LIP template): one agent per world, start near the origin at rest, goal (10, 0), a straight-line reference at v_ref and
+    n_obs obstacles scattered along the way (x ~ U(0.8, 4), y ~ U(-1, 1) about the line).  Returns host arrays in the layout of
+    cbfnmpc_raw_in / cbfnmpc_world_state (SoA, per-world matrices column-major)."""
+    rng = np.random.default_rng(seed)
+    ref_cols = 4 * (n_cycles + 2)
+    p0 = np.stack([rng.uniform(-0.2, 0.2, B), rng.uniform(-0.5, 0.5, B)])             # 2 x B
+    goal = np.array([[10.0], [0.0]])
+    dirv = (goal - p0) / np.linalg.norm(goal - p0, axis=0)
+    v = v_ref * dirv                                                                  # 2 x B
+    t = (np.arange(ref_cols) + 1) * TS
+    Pr = np.zeros((B, ref_cols, 8)); Prd = np.zeros((B, ref_cols, 8))                 # [team][col][row] = column-major 8 x ref_cols
+    Pr[:, :, 0] = p0[0][:, None] + v[0][:, None] * t[None, :]; Pr[:, :, 1] = p0[1][:, None] + v[1][:, None] * t[None, :]
+    Prd[:, :, 0] = v[0][:, None]; Prd[:, :, 1] = v[1][:, None]
+    obs = np.stack([rng.uniform(0.8, 4.0, (B, n_obs)), rng.uniform(-1.0, 1.0, (B, n_obs))], axis=2)  # [team][k][xy] = column-major 2 x K
+    q = np.zeros((18, B)); dq = np.zeros((18, B))
+    q[0] = p0[0]; q[1] = p0[1]
+    toe = np.zeros((12, B))
+    for i in range(4):
+        toe[3 * i] = p0[0] + NOMINAL_FEET[0, i]; toe[3 * i + 1] = p0[1] + NOMINAL_FEET[1, i]
+    return dict(q=q, dq=dq, nq=18, contact=np.ones((4, B), np.int32), toe_pos=toe, gait_domain=np.zeros(B, np.int32),
+                agent_id=np.zeros(B, np.int32), team=np.arange(B, dtype=np.int32), agent_initial=p0.copy(),
+                Pr_refined=Pr, Prd_refined=Prd, ref_cols=ref_cols, n_teams=B, Pobs_real=obs, n_obs=n_obs,
+                alpha_buf=np.stack([p0[0], 0 * p0[0], p0[1], 0 * p0[0]]),
+                success=np.ones(B, np.int32), distance_to_fail=np.full(B, 10.0), n_not_converged=np.zeros(B, np.int32))

@@ -197,3 +197,50 @@ def test_raw_input_packing_and_run_cycle(pkg):
         assert torch.equal(o1[k], o2[k]), k
     assert (o1["status"] != 4).all()
     s.close()
+
+
+def _world_to_device(w, torch, dev):
+    keys = ("q", "dq", "contact", "toe_pos", "gait_domain", "agent_id", "team", "agent_initial", "Pr_refined", "Prd_refined", "Pobs_real",
+            "alpha_buf", "success", "distance_to_fail", "n_not_converged")
+    t = {k: torch.from_numpy(np.ascontiguousarray(w[k])).to(dev) for k in keys}
+    raw = {k: t[k].data_ptr() for k in ("q", "dq", "contact", "toe_pos", "gait_domain", "agent_id", "team", "agent_initial", "Pr_refined",
+                                        "Prd_refined", "Pobs_real")}
+    raw.update(nq=w["nq"], ref_cols=w["ref_cols"], n_teams=w["n_teams"], n_obs=w["n_obs"])
+    world = {k: t[k].data_ptr() for k in ("q", "dq", "contact", "toe_pos", "gait_domain", "alpha_buf", "success", "distance_to_fail",
+                                          "n_not_converged")}
+    return t, raw, world
+
+
+def test_closed_loop_worlds_against_the_oracle(pkg):
+    """receding-horizon Monte-Carlo on the device against the CPU restatement: same trajectories, same failing
+    worlds and failing distances; and the reference's A/B finding (src/A1_Sim.cpp:983-1266): with the NLP stage no world
+    that the QP-only planner keeps safe is lost, and worlds the QP-only planner loses are saved."""
+    import torch
+    import copy
+    import oracle as O
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    dev = torch.device("cuda", 0)
+    B, n_cycles = 96, 14
+    res = {}
+    for mode in (capi.MODE_QP, capi.MODE_QP_NLP):
+        w = S.mc_worlds(B, n_cycles)
+        wref = copy.deepcopy(w)
+        t, raw, world = _world_to_device(w, torch, dev)
+        traj = torch.zeros((n_cycles, 4, B), dtype=torch.float64, device=dev); world["traj"] = traj.data_ptr()
+        s = pkg.BatchSolver(device=0, max_batch=B, max_obs=w["n_obs"])
+        s.closed_loop(B, n_cycles, raw, world, mode=mode)
+        torch.cuda.synchronize()
+        tr_ref = O.closed_loop(wref, n_cycles, mode=mode)
+        succ = t["success"].cpu().numpy(); dtf = t["distance_to_fail"].cpu().numpy(); nnc = t["n_not_converged"].cpu().numpy()
+        ok = (nnc == 0) & (wref["n_not_converged"] == 0)     # worlds whose every cycle converged in both implementations
+        assert ok.sum() > 0.5 * B
+        assert (nnc == wref["n_not_converged"]).mean() > 0.97
+        assert np.abs(traj.cpu().numpy() - tr_ref)[:, :, ok].max() < 1e-5
+        assert (succ[ok] == wref["success"][ok]).all()
+        assert np.abs(dtf - wref["distance_to_fail"])[ok].max() < 1e-5
+        assert (t["gait_domain"].cpu().numpy() == n_cycles).all()
+        res[mode] = (succ.copy(), ok.copy())
+        s.close()
+    qp_s, _ = res[capi.MODE_QP]; nl_s, nl_ok = res[capi.MODE_QP_NLP]
+    assert qp_s.sum() < B                               # the obstacle-blind QP planner walks into obstacles in some worlds
+    assert nl_s[nl_ok].mean() > qp_s[nl_ok].mean()      # the NLP stage avoids them

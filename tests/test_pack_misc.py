@@ -82,3 +82,23 @@ def test_planner_restatement_matches_the_mirror():
             assert np.array_equal(O.footholds(toe, g, pstart[2 * agent:2 * agent + 2]), np.asarray(feet).reshape(-1))
     # columns past the end are clamped to the last one
     assert np.array_equal(O.cop_planner(Pr, Prd, 0, 1000)[:4], [Pr[0, -1], Prd[0, -1], Pr[1, -1], Prd[1, -1]])
+
+
+def test_oracle_closed_loop_small():
+    """oracle/: receding-horizon loop on the template: the state follows the straight-line reference, the
+    obstacle-blind QP planner fails in a world whose reference line passes an obstacle, the failing distance is the distance
+    from the origin at the first grid point within 0.5 m (src/MPC_dist.cpp:21-40)."""
+    w = S.mc_worlds(6, 8)
+    w["Pobs_real"][:] = 100.0                      # all obstacles far away ...
+    w["Pobs_real"][0, 0] = [1.0 * 0.6, 0.0]        # ... except one on world 0's path, 0.6 m from the origin line start
+    w["q"][0, 0] = 0.0; w["q"][1, 0] = 0.0; w["agent_initial"][:, 0] = 0.0; w["alpha_buf"][:, 0] = 0.0
+    w["Pr_refined"][0, :, 0] = 0.2 * (np.arange(w["ref_cols"]) + 1) * S.TS; w["Pr_refined"][0, :, 1] = 0.0
+    w["Prd_refined"][0, :, 0] = 0.2; w["Prd_refined"][0, :, 1] = 0.0
+    for i in range(4):
+        w["toe_pos"][3 * i, 0] = S.NOMINAL_FEET[0, i]; w["toe_pos"][3 * i + 1, 0] = S.NOMINAL_FEET[1, i]
+    traj = O.closed_loop(w, 8, mode=0)
+    assert (w["gait_domain"] == 8).all() and (w["n_not_converged"] == 0).all()
+    assert w["success"][0] == 0 and (w["success"][1:] == 1).all()
+    assert 0.09 < w["distance_to_fail"][0] < 0.6 and (w["distance_to_fail"][1:] == 10.0).all()
+    t_end = 8 * 4 * S.TS
+    assert np.abs(traj[-1, 0, 1:] - (w["agent_initial"][0, 1:] + w["Prd_refined"][1:, 0, 0] * t_end)).max() < 0.05   # tracks the reference
