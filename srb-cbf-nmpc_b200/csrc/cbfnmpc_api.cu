@@ -6,7 +6,7 @@
 #include <vector>
 #include "cbfnmpc_host.h"
 #ifndef LANE_NT
-#define LANE_NT 128  // 4 warps (32 instances, one stance class) per CTA, one CTA per SM; the warps re-synchronise every solver iteration
+#define LANE_NT 64  // 2 warps (16 instances, one stance class) per CTA, 2 CTAs per SM; the warps of a CTA re-synchronise every solver iteration
 #endif
 #include "cbfnmpc_lane.h"
 

@@ -542,7 +542,7 @@ LDEV void l_kkt_solve_border(const Grp& g, const KParams& P, const LaneConst& c,
 // only the maps between slots and variables (l_scatter: e = J v, l_gather: J'w, l_assemble) are unrolled.
 // ===============================================================================================================
 #ifndef LSLOT_UNROLL
-#define LSLOT_UNROLL 3
+#define LSLOT_UNROLL 2
 #endif
 #define LPRAGMA_(x) _Pragma(#x)
 #define LPRAGMA(x) LPRAGMA_(x)
