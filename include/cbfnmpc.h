@@ -14,6 +14,7 @@
  *   cbfnmpc_pack_inputs           <- MPC_dist::updateState + copPlanner_eventbase + footholdsPlanner, B agents at once
  *                                    src/MPC_dist.cpp:1195-1202, 702-782, 1204-1266
  *   cbfnmpc_run_cycle             <- updateState + run_NMPC from the raw per-cycle inputs (pack, then solve)
+ *   cbfnmpc_generate_reference    <- MPC_dist::generateReferenceTrajectory (offline, once per scenario), T teams at once   src/MPC_dist.cpp:930-1062
  *   cbfnmpc_closed_loop           <- the receding-horizon loop of src/A1_Sim.cpp:983-1266 on the LIP template (no RaiSim): run_NMPC once
  *                                    per gait domain, state rolled to the end of the domain, MPC_dist::updateDistance_to_fail (:21-40)
  *
@@ -174,6 +175,16 @@ typedef struct {
 } cbfnmpc_world_state;
 int cbfnmpc_closed_loop(cbfnmpc_ctx *ctx, int B, int n_cycles, int mode, const cbfnmpc_raw_in *raw, const cbfnmpc_world_state *w,
                         double fail_radius, void *cuda_stream);
+
+/* generateReferenceTrajectory for n_teams teams of 4 agents: potential field toward (goal_x, goal_y), obstacle
+ * repulsion (the PLANNING obstacles of setPobs), Lennard-Jones forces between team mates; `loop` steps (100000 in the reference),
+ * decimated by 40.  Device pointers:
+ *   Pstart [n_teams][8]   (x, y of the 4 agents, as setPstart receives it)
+ *   Pobs   [n_teams] matrices 2 x n_obs column-major
+ *   Pr_refined, Prd_refined (out) [n_teams] matrices 8 x (loop / 40) column-major -- the layout cbfnmpc_raw_in expects.
+ * The reference's column quirk is kept: the last two output columns are the undecimated steps loop/40 and loop/40 + 1. */
+int cbfnmpc_generate_reference(cbfnmpc_ctx *ctx, int n_teams, const double *Pstart, const double *Pobs, int n_obs, double goal_x,
+                               double goal_y, int loop, double *Pr_refined, double *Prd_refined, void *cuda_stream);
 
 /* FP64 DFMA peak microbenchmark (TFLOP/s) used as the roofline denominator by bench.py */
 int cbfnmpc_measure_fp64_peak(cbfnmpc_ctx *ctx, double *tflops);

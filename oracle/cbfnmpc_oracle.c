@@ -141,6 +141,69 @@ void orc_pack_dense(const orc_gains *g, const double *x0, const double *xdes, co
 #undef GG
 }
 
+/* generateReferenceTrajectory (src/MPC_dist.cpp:930-1062): potential-field + Lennard-Jones recurrence for the 4 agents of one
+ * team, `loop` (100000) steps of the hard-coded discrete double integrator, force ramp over the first 1000 steps, decimation
+ * by 40.  Pstart: 8 (x,y of the 4 agents); Pobs: 2 x n_obs column-major (the PLANNING obstacles, setPobs); outputs Pr, Prd:
+ * 8 x ncols column-major with ncols = loop / 40.  Column c of the outputs is column c+2 of the decimated state history
+ * (:1044-1047); the decimation overwrites only the first ncols columns of the history (:1034-1037), so the last two output
+ * columns are the UNdecimated steps ncols and ncols+1 -- kept, since that is what the reference produces. */
+void orc_generate_reference(const double *Pstart, const double *Pobs, int n_obs, double goal_x, double goal_y, int loop,
+                            double *Pr, double *Prd) {
+  const double alpha = 150.0, eta = 400.0, dmin = 1.0, epsilon = 60, sigma = 1.0;               /* :932-933 */
+  const double a13 = 0.001025061239872, a33 = 0.929527039758809;                                /* Ad, :942-945 */
+  const double b1 = 0.000000068070472960, b3 = 0.000128132654983983;                            /* Bd, :957-960 */
+  const int ramp = 1000, dec = 40, ncols = loop / dec;
+  double q[16];
+  double *hist = (double *)malloc(sizeof(double) * 16 * (size_t)(ncols + 2));  /* decimated history, columns 0 .. ncols+1 */
+  for (int k = 0; k < 4; k++) { q[4 * k] = Pstart[2 * k]; q[4 * k + 1] = Pstart[2 * k + 1]; q[4 * k + 2] = 0; q[4 * k + 3] = 0; }
+  for (int i = 0; i <= loop; i++) {
+    /* record: column c of the decimated history is step 40 c for c < ncols, step c for c = ncols, ncols + 1 */
+    if (i % dec == 0 && i / dec < ncols) memcpy(hist + 16 * (size_t)(i / dec), q, sizeof(q));
+    if (i == ncols || i == ncols + 1) memcpy(hist + 16 * (size_t)i, q, sizeof(q));
+    if (i == loop) break;
+    double F[8];
+    for (int k = 0; k < 4; k++) {
+      const double px = q[4 * k], py = q[4 * k + 1];
+      const double gx = px - goal_x, gy = py - goal_y;
+      const double d_goal = sqrt(gx * gx + gy * gy);
+      double fx = -alpha * (gx / d_goal), fy = -alpha * (gy / d_goal);                           /* F_att, :1000 */
+      double rx = 0, ry = 0;
+      for (int j = 0; j < n_obs; j++) {                                                          /* F_rep, :1003-1017 */
+        const double ox = px - Pobs[2 * j], oy = py - Pobs[2 * j + 1];
+        const double d = sqrt(ox * ox + oy * oy);
+        if (d < dmin) {
+          const double w = eta * (1 / d - 1 / dmin) * (1 / pow(d, 2));
+          rx += w * (ox / d); ry += w * (oy / d);
+        }
+      }
+      double ax = 0, ay = 0;
+      for (int j = 0; j < 4; j++) {                                                              /* Lennard-Jones, :1019-1029 */
+        if (j == k) continue;
+        const double ox = px - q[4 * j], oy = py - q[4 * j + 1];
+        const double d = sqrt(ox * ox + oy * oy);
+        const double w = 4 * epsilon * ((6 * pow(sigma, 6)) / pow(d, 7) - (12 * pow(sigma, 12)) / pow(d, 13));
+        ax = ax - w * (ox / d); ay = ay - w * (oy / d);
+      }
+      F[2 * k] = fx + rx + ax; F[2 * k + 1] = fy + ry + ay;
+      if (d_goal < 0.001) { F[2 * k] = 0; F[2 * k + 1] = 0; }                                    /* :1033-1036 */
+    }
+    const double scale = (i < ramp) ? ((double)i / ramp) : 1.0;                                  /* :1039 */
+    for (int k = 0; k < 4; k++) {                                                                /* q+ = Ae q + Be F scale, :1041 */
+      const double x = q[4 * k], y = q[4 * k + 1], vx = q[4 * k + 2], vy = q[4 * k + 3];
+      const double ux = F[2 * k] * scale, uy = F[2 * k + 1] * scale;
+      q[4 * k] = x + a13 * vx + b1 * ux; q[4 * k + 1] = y + a13 * vy + b1 * uy;
+      q[4 * k + 2] = a33 * vx + b3 * ux; q[4 * k + 3] = a33 * vy + b3 * uy;
+    }
+  }
+  for (int c = 0; c < ncols; c++)
+    for (int k = 0; k < 4; k++) {
+      const double *h = hist + 16 * (size_t)(c + 2) + 4 * k;
+      Pr[2 * k + 8 * (size_t)c] = h[0]; Pr[2 * k + 1 + 8 * (size_t)c] = h[1];
+      Prd[2 * k + 8 * (size_t)c] = h[2]; Prd[2 * k + 1 + 8 * (size_t)c] = h[3];
+    }
+  free(hist);
+}
+
 /* copPlanner_eventbase (src/MPC_dist.cpp:702-782, effective semantics: use_bezier is false): columns [N g, N g + N) of rows
  * 2a, 2a+1 of Pr_refined_ / Prd_refined_ (8 x ref_cols, column-major) -> com_desired_Traj_vec_eventbased_ ([x,xd,y,yd] x N).
  * Columns past the end are clamped (the reference has no bound check). */

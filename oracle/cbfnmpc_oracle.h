@@ -69,6 +69,8 @@ void orc_pack_dense(const orc_gains *g, const double *x0, const double *xdes, co
                     double *Q, double *f, double *Aeq, double *beq, double *G, double *h);
 
 /* src/MPC_dist.cpp:371-396.  obs_xy is 2 x K row-major */
+void orc_generate_reference(const double *Pstart, const double *Pobs, int n_obs, double goal_x, double goal_y, int loop,
+                            double *Pr, double *Prd);
 void orc_cop_planner(const double *Pr, const double *Prd, int ref_cols, int agent_id, int gait_domain, double *xdes16);
 void orc_footholds(const double *toe_pos12, int gait_domain, const double *agent_initial, double *feet_xy8);
 int orc_closest_obstacle(const double *pos, const double *obs_xy, int K, double *out);

@@ -66,6 +66,7 @@ def lib():
         _lib.orc_stance_matrix.argtypes = [dp, ip, dp]
         _lib.orc_pack_dense.argtypes = [C.POINTER(Gains), dp, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp]
         _lib.orc_closest_obstacle.argtypes = [dp, dp, C.c_int, dp]
+        _lib.orc_generate_reference.argtypes = [dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, dp, dp]
         _lib.orc_cop_planner.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, dp]
         _lib.orc_footholds.argtypes = [dp, C.c_int, dp, dp]
         _lib.orc_bezier_fit.argtypes = [dp, dp, dp, dp]
@@ -100,6 +101,15 @@ def default_gains():
 
 def _f(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def generate_reference(Pstart, Pobs, goal=(10.0, 0.0), loop=100000):
+    """generateReferenceTrajectory (src/MPC_dist.cpp:930-1062).  Pstart (8), Pobs 2 x K.  Returns Pr, Prd (8 x loop/40)."""
+    Pobs = np.asarray(Pobs, float)
+    ncols = loop // 40
+    Pr = np.zeros(8 * ncols); Prd = np.zeros(8 * ncols)
+    lib().orc_generate_reference(_f(Pstart), np.ascontiguousarray(Pobs.T).reshape(-1), Pobs.shape[1], goal[0], goal[1], loop, Pr, Prd)
+    return Pr.reshape(ncols, 8).T.copy(), Prd.reshape(ncols, 8).T.copy()
 
 
 def cop_planner(Pr, Prd, agent_id, gait_domain):

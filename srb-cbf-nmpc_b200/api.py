@@ -38,6 +38,8 @@ def load():
     L.cbfnmpc_solve_batch_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.In), C.POINTER(capi.Out)]
     L.cbfnmpc_pack_inputs.argtypes = [C.c_void_p, C.c_int, C.POINTER(capi.RawIn), C.POINTER(capi.In), C.c_void_p]
     L.cbfnmpc_run_cycle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.RawIn), C.c_void_p, C.POINTER(capi.Out), C.c_void_p]
+    L.cbfnmpc_generate_reference.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
     L.cbfnmpc_closed_loop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(capi.RawIn), C.POINTER(capi.WorldState), C.c_double, C.c_void_p]
     L.cbfnmpc_launch_count.argtypes = [C.c_void_p]
     L.cbfnmpc_launch_count.restype = C.c_longlong
@@ -51,7 +53,7 @@ def load():
 EXPORTS = ["cbfnmpc_version", "cbfnmpc_last_error", "cbfnmpc_default_gains", "cbfnmpc_default_options", "cbfnmpc_create",
            "cbfnmpc_destroy", "cbfnmpc_set_gains", "cbfnmpc_set_options", "cbfnmpc_solve_batch", "cbfnmpc_solve_batch_host",
            "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak",
-           "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle", "cbfnmpc_closed_loop"]
+           "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle", "cbfnmpc_closed_loop", "cbfnmpc_generate_reference"]
 
 
 def default_gains():
@@ -138,6 +140,10 @@ class BatchSolver:
             setattr(so, k, out_ptrs.get(k))
         r = self._raw_struct(raw)
         self._ck(self.L.cbfnmpc_run_cycle(self.ctx, B, mode, C.byref(r), alpha_buf_ptr, C.byref(so), stream))
+
+    def generate_reference(self, n_teams, pstart_ptr, pobs_ptr, n_obs, pr_ptr, prd_ptr, goal=(10.0, 0.0), loop=100000, stream=None):
+        """generateReferenceTrajectory for n_teams teams on the device (cbfnmpc_generate_reference)."""
+        self._ck(self.L.cbfnmpc_generate_reference(self.ctx, n_teams, pstart_ptr, pobs_ptr, n_obs, goal[0], goal[1], loop, pr_ptr, prd_ptr, stream))
 
     def closed_loop(self, B, n_cycles, raw, world, mode=capi.MODE_QP_NLP, fail_radius=0.5, stream=None):
         """n_cycles receding-horizon cycles of B worlds, entirely on the device (cbfnmpc_closed_loop).  `world`: dict of

@@ -172,6 +172,68 @@ __global__ void __launch_bounds__(256) cbfnmpc_rollout_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// generateReferenceTrajectory (src/MPC_dist.cpp:930-1062), SURVEY.md 8f.4: sequential in time, parallel over teams.
+// One team = 4 adjacent lanes (lane k = agent k); team mates' positions travel by width-4 shuffles; all lanes of a warp run
+// the same `loop` steps, so full-mask shuffles are legal.  Obstacles of the CTA's teams sit in shared memory.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) cbfnmpc_refgen_kernel(int n_teams, const double* __restrict__ Pstart, const double* __restrict__ Pobs,
+                                                             int n_obs, double goal_x, double goal_y, int loop, double* __restrict__ Pr,
+                                                             double* __restrict__ Prd) {
+  extern __shared__ double s_obs[];  // [32 teams][2 n_obs]
+  const int tl = threadIdx.x >> 2, k = threadIdx.x & 3;
+  const int team = blockIdx.x * 32 + tl;
+  const bool valid = team < n_teams;
+  const int tc = valid ? team : n_teams - 1;   // idle lanes shadow the last team (they must execute the shuffles)
+  for (int i = k; i < 2 * n_obs; i += 4) s_obs[tl * 2 * n_obs + i] = Pobs[(size_t)tc * 2 * n_obs + i];
+  __syncthreads();
+  const double* ob = s_obs + tl * 2 * n_obs;
+  const double alpha = 150.0, eta = 400.0, dmin = 1.0, epsilon = 60.0;                          // :932-933 (sigma = 1)
+  const double a13 = 0.001025061239872, a33 = 0.929527039758809;                                // Ad, :942-945
+  const double b1 = 0.000000068070472960, b3 = 0.000128132654983983;                            // Bd, :957-960
+  const int ramp = 1000, dec = 40, ncols = loop / dec;
+  double x = Pstart[(size_t)tc * 8 + 2 * k], y = Pstart[(size_t)tc * 8 + 2 * k + 1], vx = 0.0, vy = 0.0;
+  double* pr = Pr + (size_t)tc * 8 * ncols + 2 * k;
+  double* prd = Prd + (size_t)tc * 8 * ncols + 2 * k;
+  for (int i = 0; i <= loop; i++) {
+    // output column c holds column c + 2 of the decimated history: step 40 (c + 2) for c + 2 < ncols, else step c + 2
+    int c = -1;
+    if (i % dec == 0 && i / dec < ncols) c = i / dec - 2;
+    if (i == ncols || i == ncols + 1) c = i - 2;
+    if (valid && c >= 0 && c < ncols) {
+      pr[8 * (size_t)c] = x; pr[8 * (size_t)c + 1] = y; prd[8 * (size_t)c] = vx; prd[8 * (size_t)c + 1] = vy;
+    }
+    if (i == loop) break;
+    const double gx = x - goal_x, gy = y - goal_y;
+    const double d_goal = sqrt(gx * gx + gy * gy);
+    double fx = -alpha * (gx / d_goal), fy = -alpha * (gy / d_goal);                             // F_att, :1000
+    double rx = 0.0, ry = 0.0;
+    for (int j = 0; j < n_obs; j++) {                                                            // F_rep, :1003-1017
+      const double ox = x - ob[2 * j], oy = y - ob[2 * j + 1];
+      const double d = sqrt(ox * ox + oy * oy);
+      if (d < dmin) {
+        const double w = eta * (1.0 / d - 1.0 / dmin) * (1.0 / (d * d));
+        rx += w * (ox / d); ry += w * (oy / d);
+      }
+    }
+    double ax = 0.0, ay = 0.0;
+#pragma unroll
+    for (int m = 1; m < 4; m++) {                                                                // Lennard-Jones, :1019-1029
+      const double qx = __shfl_xor_sync(0xffffffffu, x, m, 4), qy = __shfl_xor_sync(0xffffffffu, y, m, 4);
+      const double ox = x - qx, oy = y - qy;
+      const double d2 = ox * ox + oy * oy, d = sqrt(d2), d4 = d2 * d2, d6 = d4 * d2;
+      const double w = 4.0 * epsilon * (6.0 / (d6 * d) - 12.0 / (d6 * d6 * d));
+      ax = ax - w * (ox / d); ay = ay - w * (oy / d);
+    }
+    fx += rx + ax; fy += ry + ay;
+    if (d_goal < 0.001) { fx = 0.0; fy = 0.0; }                                                  // :1033-1036
+    const double scale = (i < ramp) ? ((double)i / ramp) : 1.0;                                  // :1039
+    const double ux = fx * scale, uy = fy * scale;
+    x = x + a13 * vx + b1 * ux; y = y + a13 * vy + b1 * uy;                                      // q+ = Ae q + Be F scale, :1041
+    vx = a33 * vx + b3 * ux; vy = a33 * vy + b3 * uy;
+  }
+}
+
 // FP64 pipe microbenchmark: 8 independent DFMA chains per thread.
 __global__ void cbfnmpc_dfma_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -427,6 +489,18 @@ int cbfnmpc_run_cycle(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_raw_in* raw
   int rc = cbfnmpc_pack_inputs(c, B, raw, &din, cuda_stream);
   if (rc) return rc;
   return launch(c, B, mode, &din, out, nullptr, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
+
+int cbfnmpc_generate_reference(cbfnmpc_ctx* c, int n_teams, const double* Pstart, const double* Pobs, int n_obs, double goal_x, double goal_y,
+                               int loop, double* Pr, double* Prd, void* cuda_stream) {
+  if (!c || !Pstart || !Pobs || !Pr || !Prd || n_teams < 1 || n_obs < 1 || n_obs > 512 || loop < 120)
+    return fail(CBFNMPC_ERR_ARG, "cbfnmpc_generate_reference: bad argument");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  cbfnmpc_refgen_kernel<<<(n_teams + 31) / 32, 128, sizeof(double) * 64 * (size_t)n_obs, st>>>(n_teams, Pstart, Pobs, n_obs, goal_x, goal_y, loop, Pr, Prd);
+  CK(cudaGetLastError());
+  c->launches++;
+  return CBFNMPC_OK;
 }
 
 int cbfnmpc_closed_loop(cbfnmpc_ctx* c, int B, int n_cycles, int mode, const cbfnmpc_raw_in* raw, const cbfnmpc_world_state* w,

@@ -244,3 +244,60 @@ def test_closed_loop_worlds_against_the_oracle(pkg):
     qp_s, _ = res[capi.MODE_QP]; nl_s, nl_ok = res[capi.MODE_QP_NLP]
     assert qp_s.sum() < B                               # the obstacle-blind QP planner walks into obstacles in some worlds
     assert nl_s[nl_ok].mean() > qp_s[nl_ok].mean()      # the NLP stage avoids them
+
+
+def test_reference_generator_on_device(pkg):
+    """generateReferenceTrajectory for many teams on the device against the oracle restatement, then the whole
+    chain of BASELINE config 2 (4-agent team of A1_Sim_4_agents: generator -> planners -> one cycle per agent)."""
+    import torch
+    import oracle as O
+    from srb_cbf_nmpc_b200 import capi
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    T, K, loop = 70, 9, 20000
+    ncols = loop // 40
+    base_start = np.array([0.0, 0.0, 0.0, -0.9, -1, 0, -1, -0.9])
+    base_obs = np.array([[2.2, 1, 0.85, 1, 1, 3, 3.0, 3, -100], [0.9, 1.2, -0.65, 2, -1.75, 0.2, -0.70, -2.2, -0.5 + 100]])   # SIM4:872-873
+    Pstart = base_start[None, :] + rng.uniform(-0.1, 0.1, size=(T, 8)); Pstart[0] = base_start
+    Pobs = base_obs[None] + rng.uniform(-0.3, 0.3, size=(T, 2, K)); Pobs[0] = base_obs
+    d_ps = torch.from_numpy(Pstart).to(dev); d_po = torch.from_numpy(np.ascontiguousarray(np.transpose(Pobs, (0, 2, 1)))).to(dev)
+    d_pr = torch.zeros((T, ncols, 8), dtype=torch.float64, device=dev); d_prd = torch.zeros_like(d_pr)
+    s = pkg.BatchSolver(device=0, max_batch=4 * T, max_obs=K)
+    s.generate_reference(T, d_ps.data_ptr(), d_po.data_ptr(), K, d_pr.data_ptr(), d_prd.data_ptr(), loop=loop)
+    torch.cuda.synchronize()
+    pr = d_pr.cpu().numpy(); prd = d_prd.cpu().numpy()
+    worst = 0.0
+    for t in range(T):
+        Pr, Prd = O.generate_reference(Pstart[t], Pobs[t], loop=loop)
+        worst = max(worst, np.abs(pr[t].T - Pr).max(), np.abs(prd[t].T - Prd).max())
+    assert worst < 1e-7, worst       # pow() vs repeated products: a few ulp per step on a contracting recurrence
+    # BASELINE config 2: one cycle per agent of team 0 from the generated reference (gait domain 2: measured toes are used)
+    B = 4 * T
+    team = np.repeat(np.arange(T), 4).astype(np.int32); agent = np.tile(np.arange(4), T).astype(np.int32)
+    p0 = Pstart.reshape(T, 4, 2)
+    q = np.zeros((18, B)); q[0] = p0[:, :, 0].reshape(-1); q[1] = p0[:, :, 1].reshape(-1)
+    fp = np.array([[0.2188, 0.2188, -0.1472, -0.1472], [-0.1320, 0.1320, -0.1320, 0.1320]])
+    toe = np.zeros((12, B))
+    for i in range(4):
+        toe[3 * i] = q[0] + fp[0, i]; toe[3 * i + 1] = q[1] + fp[1, i]
+    tens = dict(q=q, dq=np.zeros((18, B)), contact=np.ones((4, B), np.int32), toe_pos=toe, gait_domain=np.full(B, 2, np.int32), agent_id=agent,
+                team=team, agent_initial=np.stack([q[0], q[1]]))
+    dten = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in tens.items()}
+    raw = {k: v.data_ptr() for k, v in dten.items()}
+    raw.update(Pr_refined=d_pr.data_ptr(), Prd_refined=d_prd.data_ptr(), Pobs_real=d_po.data_ptr(), nq=18, ref_cols=ncols, n_teams=T, n_obs=K)
+    abuf = torch.from_numpy(np.stack([q[0], 0 * q[0], q[1], 0 * q[0]])).to(dev)
+    o = {k: torch.zeros((n, B), dtype=torch.float64, device=dev) for k, n in capi.OUT_F64.items()}
+    o.update({k: torch.zeros((n, B), dtype=torch.int32, device=dev) for k, n in capi.OUT_I32.items()})
+    s.run_cycle(B, raw, abuf.data_ptr(), {k: v.data_ptr() for k, v in o.items()}, mode=capi.MODE_QP_NLP)
+    torch.cuda.synchronize()
+    st = o["status"][0].cpu().numpy(); X = o["X"].cpu().numpy()
+    assert (st[:4] == 0).all(), st[:4]                     # the 4 agents of the reference's own scenario converge
+    assert (st == 0).mean() > 0.9
+    Pr0, Prd0 = O.generate_reference(Pstart[0], Pobs[0], loop=loop)
+    for a in range(4):                                     # ... to the oracle's answer for the same chain on the CPU
+        xdes = O.cop_planner(Pr0, Prd0, a, 2)
+        feet = O.footholds(toe[:, a].reshape(4, 3).T, 2, [q[0, a], q[1, a]]).reshape(2, 4)
+        r = O.solve_batch(np.array([[q[0, a], 0.0, q[1, a], 0.0]]), xdes[None], feet[None], np.ones((1, 4), np.int32), Pobs[0][None],
+                          np.array([[q[0, a], 0.0, q[1, a], 0.0]]), mode=1, nthreads=1)
+        assert r["status"][0] == 0 and np.abs(X[:, a] - r["X"][0]).max() < 1e-6
+    s.close()

@@ -102,3 +102,21 @@ def test_oracle_closed_loop_small():
     assert 0.09 < w["distance_to_fail"][0] < 0.6 and (w["distance_to_fail"][1:] == 10.0).all()
     t_end = 8 * 4 * S.TS
     assert np.abs(traj[-1, 0, 1:] - (w["agent_initial"][0, 1:] + w["Prd_refined"][1:, 0, 0] * t_end)).max() < 0.05   # tracks the reference
+
+
+def test_reference_generator_restatement():
+    """oracle/: generateReferenceTrajectory (src/MPC_dist.cpp:930-1062) on the 4-agent scenario of src/A1_Sim.cpp:1013 /
+    A1_Sim_4_agents.cpp:872-873: shapes, start, goal, the decimation quirk of the last two columns, determinism."""
+    Pstart = [0.0, 0.0, 0.0, -0.9, -1, 0, -1, -0.9]
+    obs = np.array([[2.2, 1, 0.85, 1, 1, 3, 3.0, 3, -100], [0.9, 1.2, -0.65, 2, -1.75, 0.2, -0.70, -2.2, -0.5 + 100]])
+    Pr, Prd = O.generate_reference(Pstart, obs, loop=20000)
+    assert Pr.shape == (8, 500) and Prd.shape == (8, 500)
+    assert np.abs(Pr[:, 0] - np.array(Pstart)).max() < 0.05            # column 0 = step 80: still next to the start (force ramp)
+    assert np.all(np.diff(Pr[0, :498]) > -1e-3)                        # agent 0 advances toward the goal (10, 0)
+    assert np.abs(Pr[:, 498] - Pr[:, 11]).max() < 0.02                 # quirk: the last two columns are undecimated steps 500, 501
+    Pr2, _ = O.generate_reference(Pstart, obs, loop=20000)
+    assert np.array_equal(Pr, Pr2)
+    # no obstacles, one agent far from the others: pure attraction, speed settles at b3 alpha / (1 - a33) per step / a13-scaled
+    Pr3, Prd3 = O.generate_reference([0, 0, 0, -50, 0, 50, 0, 100], np.array([[1e3], [1e3]]), loop=20000)
+    v_inf = 0.000128132654983983 * 150.0 / (1 - 0.929527039758809)
+    assert abs(Prd3[0, 300] - v_inf) < 1e-3 * v_inf
