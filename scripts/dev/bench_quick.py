@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 import srb_cbf_nmpc_b200 as m
 from srb_cbf_nmpc_b200 import capi, scenarios as S
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096

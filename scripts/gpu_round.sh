@@ -11,7 +11,7 @@ python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_$TAG.l
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_launch_$TAG.log
-python bench_quick.py 4096 > gpurun_out/plainq_$TAG.log 2>&1 && \
+python scripts/dev/bench_quick.py 4096 > gpurun_out/plainq_$TAG.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:cbfnmpc_lane -s 5 -c 1 -f -o gpurun_out/prof_$TAG \
-    python bench_quick.py 4096 > gpurun_out/ncu_full_$TAG.log 2>&1
+    python scripts/dev/bench_quick.py 4096 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_full_$TAG.log

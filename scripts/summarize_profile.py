@@ -51,7 +51,7 @@ if os.path.exists(rep):
             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__average_warp_latency_per_inst_issued.ratio",
             "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
             "sm__icc_request_hit_rate.pct", "sm__cycles_active.avg"]
-    out_md.append("## `ncu --set full --clock-control none` of one `cbfnmpc_lane_kernel` launch (4096 cfg-3 instances, `bench_quick.py 4096`)\n")
+    out_md.append("## `ncu --set full --clock-control none` of one `cbfnmpc_lane_kernel` launch (4096 cfg-3 instances, `scripts/dev/bench_quick.py 4096`)\n")
     out_md.append("| metric | value | unit |\n|---|---|---|")
     summary["metrics"] = {}
     for k in keys:
