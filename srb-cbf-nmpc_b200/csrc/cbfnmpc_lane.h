@@ -32,9 +32,9 @@
 struct KV { double xs[4], us[2], lm[4], dl, pi[4], nu[2], eta; };
 
 struct LaneConst {       // per-instance constants of this lane
-  double xdes[4];        // desired x_{j+1}                                   (MPC_dist.cpp:702-782)
-  double xin[4];         // lane 0: measured state x_0 (MPC_dist.cpp:226-229); other lanes: unused
-  double F[8];           // stance feet, F[4 a + i] = axis a of foot i         (MPC_dist.cpp:1238-1252)
+  // (the desired x_{j+1}, MPC_dist.cpp:702-782, and the measured state x_0, :226-229, live in the private columns F_XDES / F_XIN:
+  //  they are read two or three times per iteration and would otherwise be spilled)
+  double Fl[2];          // last stance foot (column C-1 of the stance matrix F)  (MPC_dist.cpp:1238-1252); F[a][i] = D[a][i] + Fl[a]
   double D[6];           // D = F E, D[c * NW + a] = F[c][a] - F[c][C-1]
   double ox, oy;         // closest obstacle                                   (MPC_dist.cpp:371-396)
   double qw;             // state weight of this stage (Pw at the last stage)
@@ -52,7 +52,7 @@ struct LaneHess {        // stage blocks of H = W + dw I + J' Sigma J  (dw is ad
 
 struct LaneFact {        // Riccati factors of stage j
   double Pn[10];         // P_{j+1}, packed lower (i >= k: i (i + 1) / 2 + k)
-  double K[12], St[12];  // K_j = R~^-1 S~_j, S~_j: [a * 4 + k]
+  double K[12];          // K_j = R~^-1 S~_j: [a * 4 + k]  (S~_j itself is not kept: S~'R~^-1 v = K'v in the substitutions)
   double Lc[6];          // chol(R~_j): (1/l00, l10, 1/l11, l20, l21, 1/l22)
 };
 
@@ -86,7 +86,9 @@ struct LaneDims {
   static constexpr int F_PVB = Q_END > N_END ? Q_END : N_END;  // 4 border columns x 4
   static constexpr int F_KVB = F_PVB + 16;     // 4 border columns x NW (3)
   static constexpr int F_FILT = F_KVB + 12;    // 8 filter entries x 2
-  static constexpr int NPRIV = F_FILT + 16;
+  static constexpr int F_XDES = F_FILT + 16;   // desired state of this lane's stage (4)
+  static constexpr int F_XIN = F_XDES + 4;     // measured state x_0 (4; used by lane 0)
+  static constexpr int NPRIV = F_XIN + 4;
 };
 constexpr int LANE_NPRIV = LaneDims<4>::NPRIV;
 
@@ -192,7 +194,11 @@ LDEV void l_eq_residual(const KParams& P, const LaneConst& c, const KV& v, const
   }
   LUNR for (int a = 0; a < 2; a++) {
     double s = v.us[a];
-    LUNR for (int i = 0; i < C; i++) s -= c.F[4 * a + i] * v.lm[i];
+    // F lambda = D lambda_{0..C-2} + Fl 1'lambda
+    double sl = 0.0;
+    LUNR for (int i = 0; i < C; i++) sl += v.lm[i];
+    LUNR for (int i = 0; i < C - 1; i++) s -= c.D[a * (C - 1) + i] * v.lm[i];
+    s -= c.Fl[a] * sl;
     rnu[a] = s;
   }
   double s = homogeneous ? 0.0 : -1.0;
@@ -202,12 +208,12 @@ LDEV void l_eq_residual(const KParams& P, const LaneConst& c, const KV& v, const
 
 // grad f(x) + A' y restricted to this lane's variables; pin = pi of lane j+1 (0 at lane 3)
 template <int C>
-LDEV void l_grad_Aty(const KParams& P, const LaneConst& c, const KV& x, const KV& y, const double* pin, bool with_grad, KV& g) {
+LDEV void l_grad_Aty(const KParams& P, const LaneConst& c, const Priv& pr, const KV& x, const KV& y, const double* pin, bool with_grad, KV& g) {
   double at[4];
   l_ATx(P, pin, at);
   LUNR for (int i = 0; i < 4; i++) {
     double t = at[i] - y.pi[i];
-    if (with_grad) t += c.qw * (x.xs[i] - c.xdes[i]);
+    if (with_grad) t += c.qw * (x.xs[i] - pr(LaneDims<C>::F_XDES + i));
     g.xs[i] = t;
   }
   LUNR for (int a = 0; a < 2; a++) {
@@ -215,7 +221,11 @@ LDEV void l_grad_Aty(const KParams& P, const LaneConst& c, const KV& x, const KV
     if (with_grad) t += P.Rw * x.us[a];
     g.us[a] = t;
   }
-  LUNR for (int i = 0; i < C; i++) g.lm[i] = -(c.F[i] * y.nu[0] + c.F[4 + i] * y.nu[1]) + y.eta;
+  {
+    const double gl = -(c.Fl[0] * y.nu[0] + c.Fl[1] * y.nu[1]) + y.eta;   // foot C-1
+    LUNR for (int i = 0; i < C - 1; i++) g.lm[i] = gl - (c.D[i] * y.nu[0] + c.D[(C - 1) + i] * y.nu[1]);
+    g.lm[C - 1] = gl;
+  }
   g.dl = with_grad ? P.slw * x.dl : 0.0;
 }
 
@@ -291,11 +301,12 @@ LDEV bool l_riccati(const Grp& g, const KParams& P, const LaneConst& c, const La
     // S~ = D' (GA + hxu on the position columns)
     GA[0] += H.hxu[0]; GA[4 + 2] += H.hxu[1];
     double Y[12];
-    LUNR for (int a = 0; a < NW; a++) LUNR for (int k = 0; k < 4; k++) f.St[4 * a + k] = c.D[a] * GA[k] + c.D[NW + a] * GA[4 + k];
+    double St[12];
+    LUNR for (int a = 0; a < NW; a++) LUNR for (int k = 0; k < 4; k++) St[4 * a + k] = c.D[a] * GA[k] + c.D[NW + a] * GA[4 + k];
     // Y = L^-1 S~, K = L^-T Y, column by column
     LUNR for (int k = 0; k < 4; k++) {
       double col[3] = {0.0, 0.0, 0.0};
-      LUNR for (int a = 0; a < NW; a++) col[a] = f.St[4 * a + k];
+      LUNR for (int a = 0; a < NW; a++) col[a] = St[4 * a + k];
       l_chol_fwd<NW>(f.Lc, col);
       LUNR for (int a = 0; a < NW; a++) Y[4 * a + k] = col[a];
       l_chol_bwd<NW>(f.Lc, col);
@@ -345,14 +356,14 @@ LDEV void l_backward(const Grp& g, const KParams& P, const LaneConst& c, const L
         q[i] = s;
       }
       const double g0 = P.bp * q[0] + P.bv * q[1], g1 = P.bp * q[2] + P.bv * q[3];
-      double k[3] = {0.0, 0.0, 0.0};
-      LUNR for (int a = 0; a < NW; a++) k[a] = (is_main ? m.rw[a] : 0.0) - (c.D[a] * g0 + c.D[NW + a] * g1);
+      double k[3] = {0.0, 0.0, 0.0}, kr[3] = {0.0, 0.0, 0.0};
+      LUNR for (int a = 0; a < NW; a++) { kr[a] = (is_main ? m.rw[a] : 0.0) - (c.D[a] * g0 + c.D[NW + a] * g1); k[a] = kr[a]; }
       l_chol_solve<NW>(f.Lc, k);
       double aq[4];
       l_ATx(P, q, aq);
-      LUNR for (int i = 0; i < 4; i++) {
+      LUNR for (int i = 0; i < 4; i++) {  // -A'q - S~'R~^-1 kr = -A'q - K'kr
         double s = -aq[i];
-        LUNR for (int a = 0; a < NW; a++) s -= f.St[4 * a + i] * k[a];
+        LUNR for (int a = 0; a < NW; a++) s -= f.K[4 * a + i] * kr[a];
         out[r][i] = s;
       }
       if (is_main) { LUNR for (int i = 0; i < 4; i++) m.pv[i] = pn[i]; LUNR for (int a = 0; a < NW; a++) m.kv[a] = k[a]; }
@@ -411,7 +422,7 @@ template <int C>
 LDEV void l_stage_eliminate(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, double dw, const KV& r, LaneMain& m, double* d0) {
   constexpr int NW = LaneDims<C>::NW;
   const double e0 = r.eta;
-  LUNR for (int a = 0; a < 2; a++) d0[a] = c.F[4 * a + C - 1] * e0 + r.nu[a];
+  LUNR for (int a = 0; a < 2; a++) d0[a] = c.Fl[a] * e0 + r.nu[a];
   const double last = r.lm[C - 1] - (H.hl[C - 1] + dw) * e0;
   const double ru0 = r.us[0] - (H.hu[0] + dw) * d0[0], ru1 = r.us[1] - (H.hu[1] + dw) * d0[1];
   LUNR for (int a = 0; a < 3; a++) m.rw[a] = 0.0;
@@ -445,7 +456,7 @@ LDEV void l_recover(const Grp& g, const KParams& P, const LaneConst& c, const La
   const double xpp[2] = {(g.j > 0) ? xp0 : 0.0, (g.j > 0) ? xp2 : 0.0};
   LUNR for (int a = 0; a < 2; a++)
     d.nu[a] = r.us[a] - (H.hu[a] + dw) * du[a] - (P.bp * d.pi[2 * a] + P.bv * d.pi[2 * a + 1]) - H.hxu[a] * xpp[a];
-  d.eta = r.lm[C - 1] - (H.hl[C - 1] + dw) * dll + c.F[C - 1] * d.nu[0] + c.F[4 + C - 1] * d.nu[1];
+  d.eta = r.lm[C - 1] - (H.hl[C - 1] + dw) * dll + c.Fl[0] * d.nu[0] + c.Fl[1] * d.nu[1];
   d.dl = ddl;
 }
 
@@ -619,7 +630,7 @@ struct LaneSolver {
   int nsq, nsn;    // slot-loop lengths of this lane in the QP / NLP stage (lane 0 has no friction slots)
 
   LMEM void prev_state(const KV& v, bool homogeneous, double* xp) const {  // x_j: previous lane's xs; lane 0: measured state
-    LUNR for (int i = 0; i < 4; i++) { const double t = g_up(g, v.xs[i]); xp[i] = (g.j > 0) ? t : (homogeneous ? 0.0 : c.xin[i]); }
+    LUNR for (int i = 0; i < 4; i++) { const double t = g_up(g, v.xs[i]); xp[i] = (g.j > 0) ? t : (homogeneous ? 0.0 : pr(d::F_XIN + i)); }
   }
   LMEM void next_pi(const KV& v, double* pin) const { l_from_next(g, v.pi, pin); }
 
@@ -633,7 +644,7 @@ struct LaneSolver {
   // residual parts shared by qp_iter and qp_final_kkt: -(Px + c + A'y + G'z) and b - Ax; z-weights must be in Q_DE
   LMEM void qp_dual_eq(const KParams& P, const double* xp, const double* pin, KV& rx, double& acc_rx, double& acc_ry) {
     KV gfy, jz; double wd;
-    l_grad_Aty<C>(P, c, x, x, pin, true, gfy);
+    l_grad_Aty<C>(P, c, pr, x, x, pin, true, gfy);
     l_gather<C, false>(g, pr, d::Q_DE, H.gv, jz, wd);
     acc_rx = 0.0; acc_ry = 0.0;
     LUNR for (int i = 0; i < 4; i++) { rx.xs[i] = -(gfy.xs[i] - jz.xs[i]); acc_rx += rx.xs[i] * rx.xs[i]; }
@@ -662,7 +673,7 @@ struct LaneSolver {
     l_assemble<C, false>(g, P, c, pr, d::Q_E, 0.0, 0.0, H);
     KV r, dd; double wd;
     l_gather<C, false>(g, pr, d::Q_G, H.gv, r, wd);
-    LUNR for (int i = 0; i < 4; i++) r.xs[i] += c.qw * c.xdes[i];
+    LUNR for (int i = 0; i < 4; i++) r.xs[i] += c.qw * pr(d::F_XDES + i);
     r.dl = 0.0;
     {
       double xp[4]; prev_state(x, false, xp);
@@ -957,7 +968,7 @@ struct LaneSolver {
       zd = pr(d::N_ZLO + d::SD);
       // ---- KKT error
       KV jz; double wd;
-      l_grad_Aty<C>(P, c, x, x, pin, true, gfy);
+      l_grad_Aty<C>(P, c, pr, x, x, pin, true, gfy);
       l_gather<C, true>(g, pr, d::N_G, H.gv, jz, wd);
       double rdm = fabs(gfy.dl - wd);
       LUNR for (int i = 0; i < 4; i++) rdm = fmax(rdm, fabs(gfy.xs[i] - jz.xs[i]));
@@ -1068,7 +1079,7 @@ struct LaneSolver {
       // rho1 = -(grad f + A'(y+dy) + Htilde dx - J'(z+dz)),  rho2 = -(A (x+dx) - b)
       KV gd, jz2; double wd2, dpin[4], dxp[4];
       next_pi(dd, dpin); prev_state(dd, true, dxp);
-      l_grad_Aty<C>(P, c, dd, dd, dpin, false, gd);
+      l_grad_Aty<C>(P, c, pr, dd, dd, dpin, false, gd);
       l_gather<C, true>(g, pr, d::N_G, H.gv, jz2, wd2);
       double nres = 0.0;
       LUNR for (int i = 0; i < 4; i++) {
@@ -1127,7 +1138,7 @@ struct LaneSolver {
       // f(x) = sum_j x_j (1/2 Q_jj x_j + f_j)   (DV:423-428)
       double f0 = 0.0, gd = 0.0, qd = 0.0;
       LUNR for (int i = 0; i < 4; i++) {
-        const double xv = x.xs[i], dv = dd.xs[i], fv = -c.qw * c.xdes[i];
+        const double xv = x.xs[i], dv = dd.xs[i], fv = -c.qw * pr(d::F_XDES + i);
         f0 += xv * (0.5 * c.qw * xv + fv); gd += (c.qw * xv + fv) * dv; qd += c.qw * dv * dv;
       }
       LUNR for (int a = 0; a < 2; a++) { const double xv = x.us[a], dv = dd.us[a]; f0 += xv * (0.5 * P.Rw * xv); gd += P.Rw * xv * dv; qd += P.Rw * dv * dv; }
@@ -1215,26 +1226,28 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
   bool qp_done = true;
   if (valid) {
     // ---- load (SoA, one instance; lane j takes stage j)
-    LUNR for (int i = 0; i < 4; i++) { S.c.xdes[i] = io.xdes[(size_t)(4 * j + i) * B + b]; S.c.xin[i] = io.x0[(size_t)i * B + b]; }
+    LUNR for (int i = 0; i < 4; i++) { pr(d::F_XDES + i) = io.xdes[(size_t)(4 * j + i) * B + b]; pr(d::F_XIN + i) = io.x0[(size_t)i * B + b]; }
     abuf_j = io.abuf ? io.abuf[(size_t)j * B + b] : 0.0;
     double feet[8];
     LUNR for (int t = 0; t < 8; t++) feet[t] = io.feet[(size_t)t * B + b];
     const int c0 = io.contact[b];
     // stance matrix (MPC_dist.cpp:1238-1252)
+    double F[8];
     LUNR for (int a = 0; a < 2; a++) {
-      if (C == 4) { LUNR for (int i = 0; i < 4; i++) S.c.F[4 * a + i] = feet[4 * a + i]; }
+      if (C == 4) { LUNR for (int i = 0; i < 4; i++) F[4 * a + i] = feet[4 * a + i]; }
       else {
-        S.c.F[4 * a] = (c0 == 0) ? feet[4 * a + 1] : feet[4 * a]; S.c.F[4 * a + 1] = (c0 == 0) ? feet[4 * a + 2] : feet[4 * a + 3];
-        S.c.F[4 * a + 2] = 0.0; S.c.F[4 * a + 3] = 0.0;
+        F[4 * a] = (c0 == 0) ? feet[4 * a + 1] : feet[4 * a]; F[4 * a + 1] = (c0 == 0) ? feet[4 * a + 2] : feet[4 * a + 3];
+        F[4 * a + 2] = 0.0; F[4 * a + 3] = 0.0;
       }
+      S.c.Fl[a] = F[4 * a + C - 1];
     }
     LUNR for (int t = 0; t < 6; t++) S.c.D[t] = 0.0;
-    LUNR for (int k = 0; k < 2; k++) LUNR for (int a = 0; a < NW; a++) S.c.D[k * NW + a] = S.c.F[4 * k + a] - S.c.F[4 * k + C - 1];
+    LUNR for (int k = 0; k < 2; k++) LUNR for (int a = 0; a < NW; a++) S.c.D[k * NW + a] = F[4 * k + a] - F[4 * k + C - 1];
     S.c.qw = (j == 3) ? P.Pw : P.Qw;
     // closest obstacle to the current position: first strict minimum of the Euclidean distance (MPC_dist.cpp:371-396)
     S.c.ox = 0.0; S.c.oy = 0.0;
     if (io.mode == 1) {
-      const double px = S.c.xin[0], py = S.c.xin[2];
+      const double px = pr(d::F_XIN + 0), py = pr(d::F_XIN + 2);
       double best = 1000.0; int bi = 0x7fffffff;
       for (int k = j; k < io.n_obs; k += 4) {
         const double dx = px - io.obs[(size_t)k * B + b], dy = py - io.obs[(size_t)(io.n_obs + k) * B + b];
