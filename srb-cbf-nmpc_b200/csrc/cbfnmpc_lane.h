@@ -85,8 +85,10 @@ struct LaneDims {
                        N_E = 8 * NS, N_G = 9 * NS, N_EV = 10 * NS, N_END = 11 * NS;
   static constexpr int F_PVB = Q_END > N_END ? Q_END : N_END;  // 4 border columns x 4
   static constexpr int F_KVB = F_PVB + 16;     // 4 border columns x NW (3)
-  static constexpr int F_FILT = F_KVB + 12;    // 8 filter entries x 2
-  static constexpr int F_XDES = F_FILT + 16;   // desired state of this lane's stage (4)
+  static constexpr int F_FILT = F_KVB + 12;    // this lane's share of the filter: entries p = 4 q + j (q = 0, 1), (theta, phi) each
+  static constexpr int F_GFY = F_FILT + 4;     // grad f + A'y of the iterate (11) and its dynamics residual (4), parked here between
+  static constexpr int F_REP = F_GFY + 11;     // the right-hand side and the refinement check instead of being spilled
+  static constexpr int F_XDES = F_REP + 4;     // desired state of this lane's stage (4)
   static constexpr int F_XIN = F_XDES + 4;     // measured state x_0 (4; used by lane 0)
   static constexpr int NPRIV = F_XIN + 4;
 };
@@ -883,6 +885,25 @@ struct LaneSolver {
     pr(fld + d::SD) = H.gv[0] * dv.xs[0] + H.gv[1] * dv.xs[2] + dv.dl;
   }
 
+  // The filter is a ring of P.filter_cap (theta, phi) pairs shared by the group: pair p lives in lane p & 3, slot p >> 2.  Empty
+  // slots hold theta = +inf, which never blocks a trial point, so the acceptance test needs no count.
+  LMEM void filter_reset() {
+    LUNR for (int q = 0; q < 2; q++) { pr(d::F_FILT + 2 * q) = CBF_INF; pr(d::F_FILT + 2 * q + 1) = CBF_INF; }
+    nfilt = 0;
+  }
+  LMEM void filter_add(const KParams& P, double th_f, double ph_f) {  // overwrites the oldest pair once the ring is full
+    const int p = nfilt % P.filter_cap;
+    if ((p & 3) == g.j) {
+      if (p >> 2) { pr(d::F_FILT + 2) = th_f; pr(d::F_FILT + 3) = ph_f; } else { pr(d::F_FILT) = th_f; pr(d::F_FILT + 1) = ph_f; }
+    }
+    nfilt++;
+  }
+  LMEM bool filter_ok(double tht, double pht) const {
+    bool okl = true;
+    LUNR for (int q = 0; q < 2; q++) okl = okl && !(tht >= pr(d::F_FILT + 2 * q) && pht >= pr(d::F_FILT + 2 * q + 1));
+    return g_all(g, okl);
+  }
+
   LMEM void nlp_init(const KParams& P) {
     // ---- step 0: strictly interior start (X, then U against friction, then lambda, then the slack variable)
     LUNR for (int i = 0; i < 4; i++) {
@@ -903,7 +924,7 @@ struct LaneSolver {
     }
     LUNR for (int i = 0; i < 4; i++) x.pi[i] = 0.0;
     x.nu[0] = x.nu[1] = 0.0; x.eta = 0.0;
-    LUNR for (int t = 0; t < 16; t++) pr(d::F_FILT + t) = 0.0;
+    filter_reset();
     mu = P.mu_init; tau = fmax(P.tau_min, 1.0 - mu); dw_last = 0.0; first_ic = true; nfilt = 0; nl_it = 0; ad_prev = 0.0;
     nlp_scatter_e(d::N_EV, xp);
     LSLOTS for (int s = 0; s < nsn; s++) {
@@ -981,6 +1002,8 @@ struct LaneSolver {
       e_d = g_max(g, rdm); e_p = g_max(g, rem); e_c = g_max(g, e_c); zmax = g_max(g, zmax);
       szmin = g_min(g, szmin); szmax = g_max(g, szmax);
       th = g_sum(g, res);
+      LUNR for (int i = 0; i < 4; i++) { pr(d::F_GFY + i) = gfy.xs[i]; pr(d::F_GFY + 6 + i) = gfy.lm[i]; pr(d::F_REP + i) = re_pi[i]; }
+      pr(d::F_GFY + 4) = gfy.us[0]; pr(d::F_GFY + 5) = gfy.us[1]; pr(d::F_GFY + 10) = gfy.dl;
       const bool nan_seen = g_any(g, !(rdm == rdm) || !(rem == rem) || !(e_c == e_c) || !(zmax == zmax));
       const double E0 = nan_seen ? 1e300 : fmax(e_d, fmax(e_p, e_c));
       info.kkt = E0; info.nlp_iters = it;
@@ -996,7 +1019,7 @@ struct LaneSolver {
       if (emu <= P.kappa_eps * mu && mu > P.tol / 10.0) {
         mu = fmax(P.tol / 10.0, fmin(P.kappa_mu * mu, mu * sqrt(mu)));
         tau = fmax(P.tau_min, 1.0 - mu);
-        nfilt = 0;
+        filter_reset();
       } else break;
     }
     // ---- Hessian blocks and right-hand side (distance row: capped split)
@@ -1080,24 +1103,27 @@ struct LaneSolver {
       KV gd, jz2; double wd2, dpin[4], dxp[4];
       next_pi(dd, dpin); prev_state(dd, true, dxp);
       l_grad_Aty<C>(P, c, pr, dd, dd, dpin, false, gd);
+      KV gf; double rp_[4];   // parked by pass A
+      LUNR for (int i = 0; i < 4; i++) { gf.xs[i] = pr(d::F_GFY + i); gf.lm[i] = pr(d::F_GFY + 6 + i); rp_[i] = pr(d::F_REP + i); }
+      gf.us[0] = pr(d::F_GFY + 4); gf.us[1] = pr(d::F_GFY + 5); gf.dl = pr(d::F_GFY + 10);
       l_gather<C, true>(g, pr, d::N_G, H.gv, jz2, wd2);
       double nres = 0.0;
       LUNR for (int i = 0; i < 4; i++) {
         const double ht = c.qw + dw - ((i & 1) ? 0.0 : 2.0 * zd);
-        r.xs[i] = -(gfy.xs[i] + gd.xs[i] + ht * dd.xs[i] - jz2.xs[i]);
+        r.xs[i] = -(gf.xs[i] + gd.xs[i] + ht * dd.xs[i] - jz2.xs[i]);
         nres = fmax(nres, fabs(r.xs[i]));
       }
-      LUNR for (int a = 0; a < 2; a++) { r.us[a] = -(gfy.us[a] + gd.us[a] + (P.Rw + dw) * dd.us[a] - jz2.us[a]); nres = fmax(nres, fabs(r.us[a])); }
+      LUNR for (int a = 0; a < 2; a++) { r.us[a] = -(gf.us[a] + gd.us[a] + (P.Rw + dw) * dd.us[a] - jz2.us[a]); nres = fmax(nres, fabs(r.us[a])); }
       LUNR for (int i = 0; i < 4; i++) {
-        r.lm[i] = (i < C) ? -(gfy.lm[i] + gd.lm[i] + (dw + P.rho_lambda) * dd.lm[i] - jz2.lm[i]) : 0.0;
+        r.lm[i] = (i < C) ? -(gf.lm[i] + gd.lm[i] + (dw + P.rho_lambda) * dd.lm[i] - jz2.lm[i]) : 0.0;
         nres = fmax(nres, fabs(r.lm[i]));
       }
-      r.dl = -(gfy.dl + (P.slw + dw) * dd.dl - wd2);
+      r.dl = -(gf.dl + (P.slw + dw) * dd.dl - wd2);
       nres = fmax(nres, fabs(r.dl));
       {
         double hp[4], hn[2], he;
         l_eq_residual<C>(P, c, dd, dxp, true, hp, hn, he);
-        LUNR for (int i = 0; i < 4; i++) { r.pi[i] = -(re_pi[i] + hp[i]); nres = fmax(nres, fabs(r.pi[i])); }
+        LUNR for (int i = 0; i < 4; i++) { r.pi[i] = -(rp_[i] + hp[i]); nres = fmax(nres, fabs(r.pi[i])); }
         LUNR for (int a = 0; a < 2; a++) { r.nu[a] = -(re_nu[a] + hn[a]); nres = fmax(nres, fabs(r.nu[a])); }
         r.eta = -(re_eta + he); nres = fmax(nres, fabs(r.eta));
       }
@@ -1170,10 +1196,7 @@ struct LaneSolver {
         const double tht = (1.0 - alpha) * th;
         const double dph = alpha * gdx + 0.5 * alpha * alpha * dQd - mu * dlog;
         const double pht = ph + dph;
-        bool okf = tht <= theta_max;
-        for (int fi = 0; fi < nfilt && okf; fi++)
-          if (tht >= pr(d::F_FILT + 2 * fi) && pht >= pr(d::F_FILT + 2 * fi + 1)) okf = false;
-        if (okf) {
+        if (tht <= theta_max && filter_ok(tht, pht)) {
           const bool sw = dphi < 0.0 && alpha * (dphi * dphi) > th;  // switching condition, s_phi = 2, s_theta = 1, delta = 1
           if (th <= theta_min && sw) {
             if (dph - 10.0 * CBF_EPSM * fabs(ph) <= P.eta_phi * alpha * dphi) { accepted = true; ftype = true; }
@@ -1188,14 +1211,7 @@ struct LaneSolver {
     LANE_LOG(alpha); LANE_LOG(ph); LANE_LOG(dphi);
     LANE_DBG("   alpha %.3e acc %d ftype %d ph %.10e dphi %.3e\n", alpha, (int)accepted, (int)ftype, ph, dphi);
     if (!accepted) { info.status = 2; return true; }
-    if (!ftype) {
-      if (nfilt >= P.filter_cap) {
-        for (int t = 0; t < 2 * (P.filter_cap - 1); t++) pr(d::F_FILT + t) = pr(d::F_FILT + t + 2);
-        nfilt--;
-      }
-      pr(d::F_FILT + 2 * nfilt) = (1.0 - P.gamma_theta) * th; pr(d::F_FILT + 2 * nfilt + 1) = ph - P.gamma_phi * th;
-      nfilt++;
-    }
+    if (!ftype) filter_add(P, (1.0 - P.gamma_theta) * th, ph - P.gamma_phi * th);
     // ---- update (the multiplier step z += a_dmax dz is applied by pass A of the next iteration)
     LUNR for (int i = 0; i < 4; i++) { x.xs[i] += alpha * dd.xs[i]; x.pi[i] += alpha * dd.pi[i]; }
     LUNR for (int i = 0; i < C; i++) x.lm[i] += alpha * dd.lm[i];

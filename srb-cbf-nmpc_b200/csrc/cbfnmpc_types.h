@@ -14,6 +14,7 @@ struct KParams {
 };
 
 #define CBF_EPSM 2.220446049250313e-16
+#define CBF_INF (__builtin_huge_val())
 
 struct BatchIO {
   // inputs, SoA [field][B]
