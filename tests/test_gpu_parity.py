@@ -301,3 +301,21 @@ def test_reference_generator_on_device(pkg):
                           np.array([[q[0, a], 0.0, q[1, a], 0.0]]), mode=1, nthreads=1)
         assert r["status"][0] == 0 and np.abs(X[:, a] - r["X"][0]).max() < 1e-6
     s.close()
+
+
+def test_host_call_pinned_and_pageable_buffers_agree(pkg, solver):
+    """cbfnmpc_solve_batch_host with pinned (one merged copy per direction) and with pageable host buffers: bit-identical."""
+    import torch
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    insts = S.cfg3_instances(700)
+    d = capi.soa_from_instances(insts); B = 700; K = int(d["n_obs"])
+    ref = solver.solve_host(d, mode=capi.MODE_QP_NLP)                      # pageable numpy arrays
+    pin = {k: torch.from_numpy(d[k].copy()).pin_memory() for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy", "alpha_buf")}
+    dp = {k: v.numpy() for k, v in pin.items()}; dp["n_obs"] = K
+    outp = {k: torch.zeros((n, B), dtype=torch.float64).pin_memory() for k, n in capi.OUT_F64.items()}
+    outp.update({k: torch.zeros((n, B), dtype=torch.int32).pin_memory() for k, n in capi.OUT_I32.items()})
+    outp["active"] = torch.zeros((2, B), dtype=torch.int64).pin_memory()
+    on = {k: v.numpy() for k, v in outp.items()}; on["active"] = on["active"].view(np.uint64)
+    solver.solve_host(dp, mode=capi.MODE_QP_NLP, out=on)
+    for k in ref:
+        assert np.array_equal(on[k], ref[k]), k
