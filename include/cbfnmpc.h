@@ -63,6 +63,7 @@ typedef struct {
   double dw_first, dw_min, kw_minus, kw_plus, kw_plus_first, dw_max, rho_lambda, z_div;
   double sigma_cap, refine_rel, refine_abs;
   int max_iter, filter_cap, max_refine;
+  double acc_tol;  /* acceptable KKT error once the barrier parameter has reached its floor tol/10 (Ipopt's acceptable_tol) */
 } cbfnmpc_options;
 
 /* Structure-of-arrays batch inputs: field-major, batch index fastest ( a[f * B + b] ).

@@ -17,7 +17,7 @@ void orc_default_options(orc_options *o) {
   o->push = 1e-2; o->gamma_theta = 1e-5; o->gamma_phi = 1e-5; o->delta = 1.0; o->s_theta = 1.1; o->s_phi = 2.3;
   o->eta_phi = 1e-4; o->kappa_sigma = 1e10; o->alpha_min = 1e-10;
   o->dw_first = 1e-4; o->dw_min = 1e-20; o->kw_minus = 1.0 / 3.0; o->kw_plus = 8.0; o->kw_plus_first = 100.0;
-  o->dw_max = 1e40; o->rho_lambda = 1e-6; o->z_div = 1e13;
+  o->dw_max = 1e40; o->rho_lambda = 1e-6; o->z_div = 1e13; o->acc_tol = 9e-9;
   o->max_iter = 200; o->filter_cap = 8;
 }
 
@@ -713,7 +713,7 @@ int orc_nlp_ipm(int nv, int mi, const double *Q, const double *f, const double *
     }
     for (int r = 0; r < m; r++) e_c = fmax(e_c, fabs(s[r] * z[r]));
     E0 = fmax(e_d, fmax(e_p, e_c));
-    if (E0 <= o->tol) { status = 0; break; }
+    if (E0 <= o->tol || (mu <= o->tol / 10 && E0 <= o->acc_tol)) { status = 0; break; }
     if (it == o->max_iter) break;
     double zmax = 0;
     for (int r = 0; r < m; r++) zmax = fmax(zmax, z[r]);

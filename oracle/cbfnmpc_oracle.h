@@ -33,6 +33,7 @@ typedef struct {
   double gamma_theta, gamma_phi, delta, s_theta, s_phi, eta_phi, kappa_sigma, alpha_min;
   double dw_first, dw_min, kw_minus, kw_plus, kw_plus_first, dw_max, rho_lambda, z_div;
   int max_iter, filter_cap;
+  double acc_tol; /* acceptable KKT error once mu has reached tol/10 */
 } orc_options;
 
 typedef struct {

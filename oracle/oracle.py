@@ -19,7 +19,7 @@ class Options(C.Structure):
                 ("kappa_sigma", C.c_double), ("alpha_min", C.c_double),
                 ("dw_first", C.c_double), ("dw_min", C.c_double), ("kw_minus", C.c_double), ("kw_plus", C.c_double),
                 ("kw_plus_first", C.c_double), ("dw_max", C.c_double), ("rho_lambda", C.c_double), ("z_div", C.c_double),
-                ("max_iter", C.c_int), ("filter_cap", C.c_int)]
+                ("max_iter", C.c_int), ("filter_cap", C.c_int), ("acc_tol", C.c_double)]
 
 
 class Gains(C.Structure):

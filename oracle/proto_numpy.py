@@ -345,7 +345,7 @@ def nlp_ipm(prob, x_start, opts=None, verbose=False, direction_fn=None, compare=
         info.update(iters=it, kkt=E0, mu=mu)
         if verbose:
             print(f"it {it:3d} mu {mu:.2e} E0 {E0:.3e} ed {e_d:.2e} ep {e_p:.2e} obj {prob.obj(x):.8f} dw {dw_last:.1e} slack {x[-1]:.5f}")
-        if E0 <= o['tol']:
+        if E0 <= o['tol'] or (mu <= o['tol'] / 10 and E0 <= o.get('acc_tol', 9e-9)):
             info['status'] = 0
             break
         if it == o['max_iter']:

@@ -4,7 +4,7 @@ sys.path.insert(0, '.')
 import srb_cbf_nmpc_b200 as m
 from srb_cbf_nmpc_b200 import capi, scenarios as S
 i = int(sys.argv[1])
-inst = S.cfg3_instances(4096)[i]
+inst = S.cfg3_instances(32768)[i]
 s = m.BatchSolver(max_batch=8)
 L = m.load()
 buf = np.zeros(8192)

@@ -17,7 +17,7 @@ class Options(C.Structure):
                 ("dw_first", C.c_double), ("dw_min", C.c_double), ("kw_minus", C.c_double), ("kw_plus", C.c_double),
                 ("kw_plus_first", C.c_double), ("dw_max", C.c_double), ("rho_lambda", C.c_double), ("z_div", C.c_double),
                 ("sigma_cap", C.c_double), ("refine_rel", C.c_double), ("refine_abs", C.c_double),
-                ("max_iter", C.c_int), ("filter_cap", C.c_int), ("max_refine", C.c_int)]
+                ("max_iter", C.c_int), ("filter_cap", C.c_int), ("max_refine", C.c_int), ("acc_tol", C.c_double)]
 
 
 class In(C.Structure):

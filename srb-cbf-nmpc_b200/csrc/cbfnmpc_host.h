@@ -22,6 +22,7 @@ static inline void host_default_options(cbfnmpc_options* o) {
   o->dw_max = 1e40; o->rho_lambda = 1e-6; o->z_div = 1e13;
   o->sigma_cap = 1e8; o->refine_rel = 1e-4; o->refine_abs = 1e-11;
   o->max_iter = 200; o->filter_cap = 8; o->max_refine = 2;
+  o->acc_tol = 9e-9;  // BASELINE bar: KKT residual below 1e-8; see DESIGN.md 4
 }
 
 // LIP discretisation exactly as src/MPC_dist.cpp:117-127 (3rd-order Taylor of exp(A Ts); Bd = A^-1 (Ad - I) B)
@@ -72,7 +73,7 @@ static inline void host_fill_kparams(const cbfnmpc_gains* g, const cbfnmpc_optio
   P->kw_minus = o->kw_minus; P->kw_plus = o->kw_plus; P->kw_plus_first = o->kw_plus_first; P->dw_max = o->dw_max;
   P->rho_lambda = o->rho_lambda; P->z_div = o->z_div; P->sigma_cap = o->sigma_cap; P->refine_rel = o->refine_rel;
   P->refine_abs = o->refine_abs; P->max_iter = o->max_iter; P->filter_cap = o->filter_cap > 8 ? 8 : o->filter_cap;
-  P->max_refine = o->max_refine;
+  P->max_refine = o->max_refine; P->acc_tol = o->acc_tol > o->tol ? o->acc_tol : o->tol;
   for (int k = 0; k < 2; k++) {  // slots: X 4 | U 2 | lambda C | QP: friction 2 ; NLP: velocity 2 | distance 1 | friction 2
     const int C = k == 0 ? 4 : 2;
     for (int s = 0; s < 16; s++) {

@@ -104,7 +104,7 @@ constexpr int LANE_NPRIV = LaneDims<4>::NPRIV;
 // in the QP stage (FLOOR; this only damps the motion of lambda inside its optimal face).  The NLP stage reports every
 // non-positive pivot instead and lets the inertia correction add dw I, which is what keeps its line search well scaled.  iSWIFT's LDL' / the oracle's Bunch-Kaufman work on the
 // unreduced KKT matrix and do not meet this cancellation (Auxilary.c:332-420).
-#define CHOL_FLOOR 1e-10
+#define CHOL_FLOOR 1e-12
 #define CHOL_NOISE 1e-9
 template <bool FLOOR>
 LDEV double l_pivot(double d, double diag, bool& ok) {
@@ -1009,7 +1009,9 @@ struct LaneSolver {
       info.kkt = E0; info.nlp_iters = it;
       LANE_LOG(1000.0 + it); LANE_LOG(mu); LANE_LOG(E0); LANE_LOG(e_d); LANE_LOG(e_p); LANE_LOG(e_c); LANE_LOG(th);
       LANE_DBG("it %d mu %.2e E0 %.3e ed %.2e ep %.2e ec %.2e zmax %.2e th %.2e\n", it, mu, E0, e_d, e_p, e_c, zmax, th);
-      if (E0 <= P.tol) { info.status = 0; return true; }
+      // converged: KKT error <= tol, or <= acc_tol once the barrier parameter sits at its floor (there the dual residual is at
+      // its FP64 noise level, s = mu / z ~ 1e-13 for active rows, and may hover just above tol for many iterations)
+      if (E0 <= P.tol || (mu <= P.tol / 10.0 && E0 <= P.acc_tol)) { info.status = 0; return true; }
       if (it == P.max_iter) { info.status = 1; return true; }
       if (!(zmax < P.z_div) || !(E0 < 1e300) || g_any(g, !(smin > 0.0))) { info.status = 2; return true; }
     }

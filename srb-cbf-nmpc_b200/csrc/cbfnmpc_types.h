@@ -9,6 +9,7 @@ struct KParams {
   double tol, mu_init, kappa_eps, kappa_mu, tau_min, push, gamma_theta, gamma_phi, eta_phi, kappa_sigma, alpha_min;
   double dw_first, dw_min, kw_minus, kw_plus, kw_plus_first, dw_max, rho_lambda, z_div, sigma_cap, refine_rel, refine_abs;
   int qp_maxit, max_iter, filter_cap, max_refine;
+  double acc_tol;
   // slot bounds by [stage: 0 QP, 1 NLP][class: 0 = 4 stance feet, 1 = 2][slot] (slot order of cbfnmpc_lane.h, LaneDims)
   double slot_lo[2][2][16], slot_hi[2][2][16];
 };
