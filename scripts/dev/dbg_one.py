@@ -14,8 +14,3 @@ o = s.solve_host(capi.soa_from_instances([inst]), mode=1)
 n = L.cbfnmpc_debug_read(buf.ctypes.data, 1)
 print("status", o["status"][0], "nlp", o["nlp_iters"][0], "log entries", n)
 np.save("gpurun_out/dbg_%d.npy" % i, buf[:n])
-if 0: buf4 = np.zeros((4, 8192))
-#L.cbfnmpc_debug_read4.argtypes = [C.c_void_p, C.c_int]
-#n4 = L.cbfnmpc_debug_read4(buf4.ctypes.data, 1)
-#np.save("gpurun_out/dbg4_%d.npy" % i, buf4[:, :n4])
-#print("log4 entries", n4)

@@ -441,17 +441,6 @@ int cbfnmpc_debug_read(double* out, int reset) {  // debug builds only
 }
 #endif
 
-#ifdef CBF_DBGBUF
-int cbfnmpc_debug_read4(double* out, int reset) {  // debug builds only
-  int n[4] = {0, 0, 0, 0};
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(n, g_dbg4_n, sizeof(n));
-  cudaMemcpyFromSymbol(out, g_dbg4, sizeof(double) * 4 * 8192);
-  if (reset) { int z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_dbg4_n, z, sizeof(z)); }
-  return n[0];
-}
-#endif
-
 static int check_raw(const cbfnmpc_raw_in* r) {
   if (!r->q || !r->dq || !r->contact || !r->toe_pos || !r->gait_domain || !r->agent_id || !r->team || !r->agent_initial ||
       !r->Pr_refined || !r->Prd_refined || !r->Pobs_real)

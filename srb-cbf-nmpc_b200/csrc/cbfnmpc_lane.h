@@ -247,7 +247,7 @@ LDEV void l_from_next(const Grp& g, const double* v, double* out) {
 // ---------------------------------------------------------------------------------------------------------------
 template <int C, bool FLOOR>
 LDEV bool l_riccati(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, double dw, LaneFact& f) {
-  constexpr int NW = LaneDims<C>::NW, NR = LaneDims<C>::NR;
+  constexpr int NW = LaneDims<C>::NW;
   // cost on x_j (previous lane's hx, hxy), needed by stage j
   double hxp[4], hxyp;
   LUNR for (int i = 0; i < 4; i++) hxp[i] = g_up(g, H.hx[i]);
@@ -298,8 +298,6 @@ LDEV bool l_riccati(const Grp& g, const KParams& P, const LaneConst& c, const La
       }
     }
     const bool okc = l_chol<NW, FLOOR>(Rt, f.Lc);
-    if (!okc && step == 3) LANE_DBGA("   riccati: stage-%d block not PD: Rt %.6e %.6e %.6e %.6e %.6e %.6e\n", g.j, Rt[0], Rt[1], Rt[2], Rt[3], Rt[4], Rt[5]);
-    if (!okc && step == 3 && g.j == 3) LANE_DBGA("   N2 %.6e %.6e %.6e hl %.6e %.6e %.6e %.6e D %.4f %.4f %.4f %.4f %.4f %.4f dw %.3e Pn %.4e %.4e %.4e %.4e\n", N2[0], N2[1], N2[2], H.hl[0], H.hl[1], H.hl[2], H.hl[3], c.D[0], c.D[1], c.D[2], c.D[3], c.D[4], c.D[5], dw, Pn[0], Pn[2], Pn[5], Pn[9]);
     // S~ = D' (GA + hxu on the position columns)
     GA[0] += H.hxu[0]; GA[4 + 2] += H.hxu[1];
     double Y[12];

@@ -61,21 +61,15 @@ LDEV double l_add_rn(double a, double b) { return __dadd_rn(a, b); }
 #ifdef CBF_DBGBUF  // debug builds only: group 0 of warp 0 logs numbers into a device buffer (lighter than printf)
 __device__ double g_dbg[8192];
 __device__ int g_dbg_n;
-__device__ double g_dbg4[4][8192];
-__device__ int g_dbg4_n[4];
 #define LANE_LOG(v) do { if (blockIdx.x == 0 && threadIdx.x == 0 && g_dbg_n < 8192) g_dbg[g_dbg_n++] = (v); } while (0)
-#define LANE_LOG4(v) do { if (blockIdx.x == 0 && threadIdx.x < 4 && g_dbg4_n[threadIdx.x] < 8192) g_dbg4[threadIdx.x][g_dbg4_n[threadIdx.x]++] = (v); } while (0)
 #else
 #define LANE_LOG(v) do { } while (0)
-#define LANE_LOG4(v) do { } while (0)
 #endif
-#ifdef CBF_TRACE  // debug builds only (scripts/trace_instance.sh): group 0 of warp 0 narrates
+#ifdef CBF_TRACE  // debug builds only (scripts/dev/README.md): group 0 of warp 0 narrates
 #include <stdio.h>
 #define LANE_DBG(...) do { if (blockIdx.x == 0 && threadIdx.x == 0) printf(__VA_ARGS__); } while (0)
-#define LANE_DBGA(...) do { if (blockIdx.x == 0 && threadIdx.x < 4) printf(__VA_ARGS__); } while (0)
 #else
 #define LANE_DBG(...) do { } while (0)
-#define LANE_DBGA(...) do { } while (0)
 #endif
 
 #else
@@ -132,19 +126,15 @@ LDEV double l_rsq(double v) { return 1.0 / sqrt(v); }
 LDEV double l_mul_rn(double a, double b) { volatile double r = a * b; return r; }
 LDEV double l_add_rn(double a, double b) { volatile double r = a + b; return r; }
 #ifdef CBF_DBGBUF
-extern double g_dbg[8192]; extern int g_dbg_n; extern double g_dbg4[4][8192]; extern int g_dbg4_n[4];
+extern double g_dbg[8192]; extern int g_dbg_n;
 #define LANE_LOG(v) do { if (lemu::g_grp.cur == 0 && g_dbg_n < 8192) g_dbg[g_dbg_n++] = (v); } while (0)
-#define LANE_LOG4(v) do { if (g_dbg4_n[lemu::g_grp.cur] < 8192) g_dbg4[lemu::g_grp.cur][g_dbg4_n[lemu::g_grp.cur]++] = (v); } while (0)
 #else
 #define LANE_LOG(v) do { } while (0)
-#define LANE_LOG4(v) do { } while (0)
 #endif
 #ifdef CBF_TRACE
 #define LANE_DBG(...) do { if (lemu::g_grp.cur == 0) fprintf(stderr, __VA_ARGS__); } while (0)
-#define LANE_DBGA(...) fprintf(stderr, __VA_ARGS__)
 #else
 #define LANE_DBG(...) do { } while (0)
-#define LANE_DBGA(...) do { } while (0)
 #endif
 #endif
 

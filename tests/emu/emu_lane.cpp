@@ -12,8 +12,7 @@
 #include "../../srb-cbf-nmpc_b200/csrc/cbfnmpc_host.h"
 
 #ifdef CBF_DBGBUF
-double g_dbg[8192]; int g_dbg_n; double g_dbg4[4][8192]; int g_dbg4_n[4];
-extern "C" int emu_debug_read4(double* out, int reset) { int n = g_dbg4_n[0]; memcpy(out, g_dbg4, sizeof(g_dbg4)); if (reset) memset(g_dbg4_n, 0, sizeof(g_dbg4_n)); return n; }
+double g_dbg[8192]; int g_dbg_n;
 extern "C" int emu_debug_read(double* out, int reset) { int n = g_dbg_n; memcpy(out, g_dbg, sizeof(g_dbg)); if (reset) g_dbg_n = 0; return n; }
 #endif
 namespace lemu {
