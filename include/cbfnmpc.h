@@ -43,7 +43,8 @@ extern "C" {
 #define CBFNMPC_ST_MAXITER 1
 #define CBFNMPC_ST_INFEASIBLE 2  /* line search / multiplier divergence: NLP has no interior */
 #define CBFNMPC_ST_NUMERICAL 3   /* inertia correction exhausted */
-#define CBFNMPC_ST_BADINPUT 4    /* contact pattern other than 4 feet or a diagonal pair (src/MPC_dist.cpp:1238-1252) */
+#define CBFNMPC_ST_BADINPUT 4    /* number of stance feet other than 4 or 2 (src/MPC_dist.cpp:1238-1252; with 2 the reference picks
+                                    FL,RR when contactInd[0] == 0 and FR,RL otherwise, whatever the other flags say -- so does this) */
 
 #define CBFNMPC_MODE_QP 0      /* use_snopt == false: the iSWIFT-equivalent QP optimum is the answer (MPC_dist.hpp:139) */
 #define CBFNMPC_MODE_QP_NLP 1  /* use_snopt == true : QP optimum -> NLP (src/MPC_dist.cpp:348 -> 402-427)              */

@@ -319,3 +319,70 @@ def test_host_call_pinned_and_pageable_buffers_agree(pkg, solver):
     solver.solve_host(dp, mode=capi.MODE_QP_NLP, out=on)
     for k in ref:
         assert np.array_equal(on[k], ref[k]), k
+
+
+def test_ragged_batch_sizes_and_edge_inputs(pkg):
+    """Batch sizes around the group / warp / CTA granularities (8 instances per warp, 16 per CTA, two stance classes), a batch
+    made only of bad contact patterns, a single obstacle column, and far-away obstacles (first-minimum rule with the
+    reference's 1000 m start value, MPC_dist.cpp:371-396)."""
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    allinst = S.cfg3_instances(80)
+    s = pkg.BatchSolver(device=0, max_batch=128, max_obs=20)
+    for B in (1, 2, 7, 8, 9, 15, 16, 17, 31, 33, 64, 65, 80):
+        insts = allinst[:B]
+        out = s.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP_NLP)
+        ref = H.oracle_batch(insts, mode=1)
+        c = H.compare(out, ref)
+        assert c["status_equal"].all(), (B, out["status"][0], ref["status"])
+        assert c["worst"] < 1e-6, (B, c["worst"])
+    bad = []
+    for k, pat in enumerate(([1, 1, 1, 0], [0, 0, 0, 0], [1, 0, 0, 0], [0, 1, 1, 1], [0, 0, 1, 0])):   # 3, 0 or 1 stance feet
+        i = list(allinst[k]); i[3] = pat; bad.append(tuple(i))
+    out = s.solve_host(capi.soa_from_instances(bad), mode=capi.MODE_QP_NLP)
+    assert (out["status"][0] == capi.ST_BADINPUT).all()
+    # two feet that are not a diagonal pair: the reference looks only at the count and at contactInd[0] (MPC_dist.cpp:1243-1252)
+    odd = []
+    for k, pat in enumerate(([1, 1, 0, 0], [0, 1, 0, 1], [1, 0, 1, 0])):
+        i = list(allinst[10 + k]); i[3] = pat; odd.append(tuple(i))
+    out = s.solve_host(capi.soa_from_instances(odd), mode=capi.MODE_QP_NLP)
+    ref = H.oracle_batch(odd, mode=1)
+    assert (out["status"][0] == ref["status"]).all() and (ref["c"] == 2).all() and H.compare(out, ref)["worst"] < 1e-6
+    mixed = bad[:2] + allinst[:3]
+    out = s.solve_host(capi.soa_from_instances(mixed), mode=capi.MODE_QP_NLP)
+    ref = H.oracle_batch(mixed, mode=1)
+    assert (out["status"][0] == ref["status"]).all() and (out["status"][0][:2] == 4).all()
+    one = [(a, b, c_, d, e[:, :1].copy()) for a, b, c_, d, e in allinst[:9]]            # K = 1
+    out = s.solve_host(capi.soa_from_instances(one), mode=capi.MODE_QP_NLP)
+    ref = H.oracle_batch(one, mode=1)
+    assert H.compare(out, ref)["worst"] < 1e-6 and (out["status"][0] == ref["status"]).all()
+    far = [(a, b, c_, d, e + 5000.0) for a, b, c_, d, e in allinst[:9]]                 # nothing within 1000 m: column 0 is used
+    out = s.solve_host(capi.soa_from_instances(far), mode=capi.MODE_QP_NLP)
+    ref = H.oracle_batch(far, mode=1)
+    assert H.compare(out, ref)["worst"] < 1e-6 and (out["status"][0] == ref["status"]).all()
+    s.close()
+
+
+def test_non_default_gains_and_options(pkg):
+    """cbfnmpc_set_gains / cbfnmpc_set_options: other weights, friction, height, grid time, distance threshold, velocity limit,
+    tolerances and iteration limits give the oracle's answers for the same settings."""
+    import oracle as O
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    insts = S.cfg3_instances(48)
+    gains = dict(Qw=150.0, Rw=0.5, Pw=900.0, slack_w=1500.0, mu_fric=0.5, h_com=0.31, Ts=0.05, eps_dist=1.2, v_max=0.45)
+    s = pkg.BatchSolver(device=0, max_batch=64, max_obs=20, gains=gains, options=dict(tol=1e-8, acc_tol=1e-8))
+    out = s.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP_NLP)
+    g = O.default_gains(); o = O.default_options()
+    for k, v in gains.items(): setattr(g, k, v)
+    o.tol = 1e-8; o.acc_tol = 1e-8
+    x0 = np.array([i[0] for i in insts]); xd = np.array([i[1] for i in insts]); ft = np.array([np.asarray(i[2]).reshape(2, 4) for i in insts])
+    ct = np.array([i[3] for i in insts], np.int32); ob = np.array([i[4] for i in insts])
+    ab = np.stack([x0[:, 0], 0 * x0[:, 0], x0[:, 2], 0 * x0[:, 0]], 1)
+    ref = O.solve_batch(x0, xd, ft, ct, ob, ab, mode=1, nthreads=8, g=g, o=o)
+    c = H.compare(out, ref)
+    assert c["status_equal"].all() and c["both"].sum() >= 30 and c["worst"] < 1e-6, c["worst"]
+    assert np.abs(out["x_qp"].T - ref["x_qp"][:, :24])[c["both"]].max() < 1e-7
+    # iteration limits are honoured: status 1 (max-iter) everywhere with 3 NLP iterations
+    s.set_options(max_iter=3)
+    out = s.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP_NLP)
+    assert ((out["status"][0] == capi.ST_MAXITER) | (out["status"][0] == capi.ST_INFEASIBLE)).all() and out["nlp_iters"][0].max() <= 3
+    s.close()
