@@ -253,12 +253,14 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     if (e_ != cudaSuccess) return fail(CBFNMPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+#define CBF_MAX_CHUNKS 4
 struct cbfnmpc_ctx {
   int device, max_batch, max_obs;
   cbfnmpc_gains gains;
   cbfnmpc_options opts;
   KParams kp;
   cudaStream_t stream;
+  cudaStream_t cstream[CBF_MAX_CHUNKS];  // host-buffer calls: chunk k of the batch travels on cstream[k] (cstream[0] == stream)
   cudaEvent_t ev0, ev1;
   bool timed;
   long long launches;
@@ -293,6 +295,8 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
   host_default_gains(&c->gains); host_default_options(&c->opts);
   host_fill_kparams(&c->gains, &c->opts, &c->kp);
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->cstream[0] = c->stream;
+  for (int k = 1; k < CBF_MAX_CHUNKS; k++) CK(cudaStreamCreateWithFlags(&c->cstream[k], cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
   CK(cudaMalloc(&c->d_in, sizeof(double) * (size_t)(32 + 2 * max_obs) * max_batch));
   CK(cudaMalloc(&c->d_contact, sizeof(int) * 4 * (size_t)max_batch));
@@ -300,7 +304,7 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
   CK(cudaMalloc(&c->d_outi, sizeof(int) * 4 * (size_t)max_batch));
   CK(cudaMalloc(&c->d_active, sizeof(unsigned long long) * 2 * (size_t)max_batch));
   CK(cudaMalloc(&c->d_xstart, sizeof(double) * 41));
-  CK(cudaMalloc(&c->d_perm, sizeof(int) * (2 * (size_t)max_batch + 2)));
+  CK(cudaMalloc(&c->d_perm, sizeof(int) * (2 * (size_t)max_batch + 2 * CBF_MAX_CHUNKS)));
   c->perm_cap = max_batch;
   CK(cudaFuncSetAttribute(cbfnmpc_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LANE_NPRIV * LANE_NT * sizeof(double))));
   *out = c;
@@ -313,6 +317,7 @@ void cbfnmpc_destroy(cbfnmpc_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_in); cudaFree(c->d_contact); cudaFree(c->d_out); cudaFree(c->d_outi); cudaFree(c->d_active); cudaFree(c->d_xstart); cudaFree(c->d_perm);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  for (int k = 1; k < CBF_MAX_CHUNKS; k++) cudaStreamDestroy(c->cstream[k]);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -335,32 +340,37 @@ int cbfnmpc_set_options(cbfnmpc_ctx* c, const cbfnmpc_options* o) {
   return CBFNMPC_OK;
 }
 
-static int launch(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const cbfnmpc_out* out, const double* xstart,
-                  cudaStream_t st) {
+// B instances whose arrays have pitch ld; perm = this launch's class lists (2 B + 2 ints)
+static int launch_on(cbfnmpc_ctx* c, int B, int ld, int mode, const cbfnmpc_in* in, const cbfnmpc_out* out, const double* xstart,
+                     cudaStream_t st, int* perm, bool timed = true) {
   BatchIO io;
   io.x0 = in->x0; io.xdes = in->xdes; io.feet = in->feet_xy; io.contact = in->contact; io.obs = in->obs_xy; io.n_obs = in->n_obs;
   io.abuf = in->alpha_buf; io.xstart = xstart;
   io.X = out->X; io.U = out->U; io.lam = out->lam; io.slack = out->slack; io.xqp = out->x_qp; io.alpha = out->alpha;
   io.abuf_next = out->alpha_buf_next; io.kkt = out->kkt; io.status = out->status; io.qp_iters = out->qp_iters;
   io.nlp_iters = out->nlp_iters; io.n_fact = out->n_fact; io.active = (unsigned long long*)out->active;
-  io.B = B; io.mode = mode;
+  io.B = B; io.ld = ld; io.mode = mode;
+  int* counts = perm + 2 * (size_t)B;
+  const int ipc = LANE_NT / 4;
+  cbfnmpc_classify_kernel<<<1, 1024, 0, st>>>(io, perm, counts);
+  CK(cudaGetLastError());
+  if (timed) CK(cudaEventRecord(c->ev0, st));  // the event pair brackets the solve kernel alone
+  cbfnmpc_lane_kernel<<<(B + ipc - 1) / ipc + 1, LANE_NT, LANE_NPRIV * LANE_NT * sizeof(double), st>>>(c->kp, io, perm, counts);
+  CK(cudaGetLastError());
+  if (timed) { CK(cudaEventRecord(c->ev1, st)); c->timed = true; }
+  c->launches += 2;
+  return CBFNMPC_OK;
+}
+
+static int launch(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const cbfnmpc_out* out, const double* xstart,
+                  cudaStream_t st) {
   if (B > c->perm_cap) {  // device-pointer batches larger than max_batch: grow the class lists
     CK(cudaStreamSynchronize(st));
     CK(cudaFree(c->d_perm));
-    CK(cudaMalloc(&c->d_perm, sizeof(int) * (2 * (size_t)B + 2)));
+    CK(cudaMalloc(&c->d_perm, sizeof(int) * (2 * (size_t)B + 2 * CBF_MAX_CHUNKS)));
     c->perm_cap = B;
   }
-  int* counts = c->d_perm + 2 * (size_t)c->perm_cap;
-  const int ipc = LANE_NT / 4;
-  cbfnmpc_classify_kernel<<<1, 1024, 0, st>>>(io, c->d_perm, counts);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(c->ev0, st));  // the event pair brackets the solve kernel alone
-  cbfnmpc_lane_kernel<<<(B + ipc - 1) / ipc + 1, LANE_NT, LANE_NPRIV * LANE_NT * sizeof(double), st>>>(c->kp, io, c->d_perm, counts);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(c->ev1, st));
-  c->timed = true;
-  c->launches += 2;
-  return CBFNMPC_OK;
+  return launch_on(c, B, B, mode, in, out, xstart, st, c->d_perm);
 }
 
 int cbfnmpc_solve_batch(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const cbfnmpc_out* out, void* cuda_stream) {
@@ -380,53 +390,70 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
   const int K = (mode == CBFNMPC_MODE_QP_NLP) ? in->n_obs : 0;
   if (mode == CBFNMPC_MODE_QP_NLP && (!in->obs_xy || K < 1 || K > c->max_obs)) return fail(CBFNMPC_ERR_ARG, "NLP mode needs 1..max_obs obstacles");
   CK(cudaSetDevice(c->device));
-  cudaStream_t st = c->stream;
   const size_t Bs = (size_t)B;
-  // device staging layout (doubles): x0 4 | xdes 16 | feet 8 | alpha_buf 4 | obs 2K
+  // Large batches are cut into equal column ranges, each on its own stream: the upload of one range overlaps the solves of
+  // the earlier ones and the downloads of the earlier ones overlap the solves of the later ones.  A range's kernel does not
+  // get faster with fewer instances (it is latency-bound), so the kernels simply run side by side; what stays on the critical
+  // path is the upload of everything, one kernel and the download of the last range.  All uploads and launches are enqueued
+  // before any download.  Measured on B200 with 4096 instances: 1 / 2 / 4 / 8 ranges -> 0.932 / 0.890 / 0.880 / 0.903 ms.
+  // Device staging (pitch B): x0 4 | xdes 16 | feet 8 | alpha_buf 4 | obs 2K rows of doubles; outputs X 16 | U 8 | lam 16 |
+  // slack 1 | x_qp 24 | alpha 20 | abuf_next 4 | kkt 1.
+  const int nch = B >= 4096 ? 4 : (B >= 1024 ? 2 : 1);
+  size_t cut[CBF_MAX_CHUNKS + 1];
+  for (int k = 0; k <= nch; k++) cut[k] = Bs * k / nch;
   double* d = c->d_in;
-  struct Seg { const double* h; size_t off, n; };
-  Seg segs[5] = {{in->x0, 0, 4 * Bs}, {in->xdes, 4 * Bs, 16 * Bs}, {in->feet_xy, 20 * Bs, 8 * Bs}, {in->alpha_buf, 28 * Bs, 4 * Bs},
-                 {in->obs_xy, 32 * Bs, 2 * (size_t)K * Bs}};
-  // adjacent host arrays (one pinned block, as the Python binding allocates) are merged into a single copy
-  for (int i = 0; i < 5;) {
-    if (!segs[i].h || segs[i].n == 0) { i++; continue; }
-    int j = i; size_t n = segs[i].n;
-    while (j + 1 < 5 && segs[j + 1].h == segs[j].h + segs[j].n && segs[j + 1].n > 0) { j++; n += segs[j].n; }
-    CK(cudaMemcpyAsync(d + segs[i].off, segs[i].h, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    i = j + 1;
-  }
-  if (!in->alpha_buf) CK(cudaMemsetAsync(d + 28 * Bs, 0, sizeof(double) * 4 * Bs, st));
-  CK(cudaMemcpyAsync(c->d_contact, in->contact, sizeof(int) * 4 * Bs, cudaMemcpyHostToDevice, st));
-  cbfnmpc_in din = {d, d + 4 * Bs, d + 20 * Bs, c->d_contact, d + 32 * Bs, K, d + 28 * Bs};
-  // device output layout (doubles): X 16 | U 8 | lam 16 | slack 1 | x_qp 24 | alpha 20 | abuf_next 4 | kkt 1
   double* o = c->d_out;
-  cbfnmpc_out dout;
-  dout.X = o; dout.U = o + 16 * Bs; dout.lam = o + 24 * Bs; dout.slack = o + 40 * Bs; dout.x_qp = o + 41 * Bs;
-  dout.alpha = o + 65 * Bs; dout.alpha_buf_next = o + 85 * Bs; dout.kkt = o + 89 * Bs;
-  dout.status = c->d_outi; dout.qp_iters = c->d_outi + Bs; dout.nlp_iters = c->d_outi + 2 * Bs; dout.n_fact = c->d_outi + 3 * Bs;
-  dout.active = (uint64_t*)c->d_active;
-  int rc = launch(c, B, mode, &din, &dout, nullptr, st);
-  if (rc) return rc;
-  struct OSeg { double* h; size_t off, n; };
-  OSeg os[8] = {{out->X, 0, 16 * Bs}, {out->U, 16 * Bs, 8 * Bs}, {out->lam, 24 * Bs, 16 * Bs}, {out->slack, 40 * Bs, Bs},
-                {out->x_qp, 41 * Bs, 24 * Bs}, {out->alpha, 65 * Bs, 20 * Bs}, {out->alpha_buf_next, 85 * Bs, 4 * Bs}, {out->kkt, 89 * Bs, Bs}};
-  for (int i = 0; i < 8;) {
-    if (!os[i].h) { i++; continue; }
-    int j = i; size_t n = os[i].n;
-    while (j + 1 < 8 && os[j + 1].h == os[j].h + os[j].n) { j++; n += os[j].n; }
-    CK(cudaMemcpyAsync(os[i].h, o + os[i].off, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-    i = j + 1;
+  struct Seg { const double* h; size_t row, rows; };
+  const Seg segs[5] = {{in->x0, 0, 4}, {in->xdes, 4, 16}, {in->feet_xy, 20, 8}, {in->alpha_buf, 28, 4}, {in->obs_xy, 32, 2 * (size_t)K}};
+  struct OSeg { double* h; size_t row, rows; };
+  const OSeg os[8] = {{out->X, 0, 16}, {out->U, 16, 8}, {out->lam, 24, 16}, {out->slack, 40, 1}, {out->x_qp, 41, 24}, {out->alpha, 65, 20},
+                      {out->alpha_buf_next, 85, 4}, {out->kkt, 89, 1}};
+  int32_t* const oi[4] = {out->status, out->qp_iters, out->nlp_iters, out->n_fact};
+  const size_t pitch = sizeof(double) * Bs;
+  for (int k = 0; k < nch; k++) {
+    const size_t b0 = cut[k], n = cut[k + 1] - b0;
+    cudaStream_t st = c->cstream[k];
+    // adjacent host arrays (one pinned block, as bench.py allocates) are merged into a single 2-D copy
+    for (int i = 0; i < 5;) {
+      if (!segs[i].h || segs[i].rows == 0) { i++; continue; }
+      int j = i; size_t rows = segs[i].rows;
+      while (j + 1 < 5 && segs[j + 1].h == segs[j].h + segs[j].rows * Bs && segs[j + 1].rows > 0) { j++; rows += segs[j].rows; }
+      CK(cudaMemcpy2DAsync(d + segs[i].row * Bs + b0, pitch, segs[i].h + b0, pitch, sizeof(double) * n, rows, cudaMemcpyHostToDevice, st));
+      i = j + 1;
+    }
+    if (!in->alpha_buf) CK(cudaMemset2DAsync(d + 28 * Bs + b0, pitch, 0, sizeof(double) * n, 4, st));
+    CK(cudaMemcpy2DAsync(c->d_contact + b0, sizeof(int) * Bs, in->contact + b0, sizeof(int) * Bs, sizeof(int) * n, 4, cudaMemcpyHostToDevice, st));
+    cbfnmpc_in din = {d + b0, d + 4 * Bs + b0, d + 20 * Bs + b0, c->d_contact + b0, d + 32 * Bs + b0, K, d + 28 * Bs + b0};
+    cbfnmpc_out dout;
+    dout.X = o + b0; dout.U = o + 16 * Bs + b0; dout.lam = o + 24 * Bs + b0; dout.slack = o + 40 * Bs + b0; dout.x_qp = o + 41 * Bs + b0;
+    dout.alpha = o + 65 * Bs + b0; dout.alpha_buf_next = o + 85 * Bs + b0; dout.kkt = o + 89 * Bs + b0;
+    dout.status = c->d_outi + b0; dout.qp_iters = c->d_outi + Bs + b0; dout.nlp_iters = c->d_outi + 2 * Bs + b0;
+    dout.n_fact = c->d_outi + 3 * Bs + b0;
+    dout.active = (uint64_t*)c->d_active + b0;
+    int rc = launch_on(c, (int)n, B, mode, &din, &dout, nullptr, st, c->d_perm + 2 * b0 + 2 * k, k == 0);
+    if (rc) return rc;
   }
-  int32_t* oi[4] = {out->status, out->qp_iters, out->nlp_iters, out->n_fact};
-  for (int i = 0; i < 4;) {
-    if (!oi[i]) { i++; continue; }
-    int j = i; size_t n = Bs;
-    while (j + 1 < 4 && oi[j + 1] == oi[j] + Bs) { j++; n += Bs; }
-    CK(cudaMemcpyAsync(oi[i], c->d_outi + (size_t)i * Bs, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-    i = j + 1;
+  for (int k = 0; k < nch; k++) {
+    const size_t b0 = cut[k], n = cut[k + 1] - b0;
+    cudaStream_t st = c->cstream[k];
+    for (int i = 0; i < 8;) {
+      if (!os[i].h) { i++; continue; }
+      int j = i; size_t rows = os[i].rows;
+      while (j + 1 < 8 && os[j + 1].h == os[j].h + os[j].rows * Bs) { j++; rows += os[j].rows; }
+      CK(cudaMemcpy2DAsync(os[i].h + b0, pitch, o + os[i].row * Bs + b0, pitch, sizeof(double) * n, rows, cudaMemcpyDeviceToHost, st));
+      i = j + 1;
+    }
+    for (int i = 0; i < 4;) {
+      if (!oi[i]) { i++; continue; }
+      int j = i; size_t rows = 1;
+      while (j + 1 < 4 && oi[j + 1] == oi[j] + Bs) { j++; rows++; }
+      CK(cudaMemcpy2DAsync(oi[i] + b0, sizeof(int) * Bs, c->d_outi + (size_t)i * Bs + b0, sizeof(int) * Bs, sizeof(int) * n, rows, cudaMemcpyDeviceToHost, st));
+      i = j + 1;
+    }
+    if (out->active)
+      CK(cudaMemcpy2DAsync(out->active + b0, sizeof(uint64_t) * Bs, c->d_active + b0, sizeof(uint64_t) * Bs, sizeof(uint64_t) * n, 2, cudaMemcpyDeviceToHost, st));
   }
-  if (out->active) CK(cudaMemcpyAsync(out->active, c->d_active, sizeof(unsigned long long) * 2 * Bs, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  for (int k = 0; k < nch; k++) CK(cudaStreamSynchronize(c->cstream[k]));
   return CBFNMPC_OK;
 }
 

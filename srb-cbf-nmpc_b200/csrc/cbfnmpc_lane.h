@@ -1236,7 +1236,7 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
   S.nsq = l_nslots<C, false>(S.g); S.nsn = l_nslots<C, true>(S.g);
   const Grp& g = S.g;
   const int j = g.j;
-  const size_t B = (size_t)io.B;
+  const size_t B = (size_t)io.ld;  // array pitch
   S.info.status = 1; S.info.qp_iters = 0; S.info.qp_flag = 3; S.info.nlp_iters = 0; S.info.n_fact = 0; S.info.kkt = 0.0;
   double abuf_j = 0.0;
   bool qp_done = true;
@@ -1368,7 +1368,7 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
 
 // contact pattern -> number of stance feet: 4, 2 (a diagonal pair) or -1 (MPC_dist.cpp:1238-1252)
 LDEV int lane_classify(const BatchIO& io, int b) {
-  const size_t B = (size_t)io.B;
+  const size_t B = (size_t)io.ld;  // array pitch
   const int c0 = io.contact[b], c1 = io.contact[B + b], c2 = io.contact[2 * B + b], c3 = io.contact[3 * B + b];
   const int csum = c0 + c1 + c2 + c3;
   if (csum == 4) return 4;
@@ -1376,7 +1376,7 @@ LDEV int lane_classify(const BatchIO& io, int b) {
   return -1;
 }
 LDEV void lane_store_bad(const BatchIO& io, int b) {
-  const size_t B = (size_t)io.B;
+  const size_t B = (size_t)io.ld;  // array pitch
   if (io.status) io.status[b] = 4;
   if (io.kkt) io.kkt[b] = 0.0;
   if (io.qp_iters) io.qp_iters[b] = 0;

@@ -26,4 +26,5 @@ struct BatchIO {
   int *status, *qp_iters, *nlp_iters, *n_fact;
   unsigned long long* active;
   int B, mode;
+  int ld;  // leading dimension of every array (>= B; > B when the batch is a column range of a larger SoA block)
 };

@@ -89,7 +89,7 @@ int emu_solve_batch_host(const cbfnmpc_gains* g, const cbfnmpc_options* o, int B
   io.X = out->X; io.U = out->U; io.lam = out->lam; io.slack = out->slack; io.xqp = out->x_qp; io.alpha = out->alpha;
   io.abuf_next = out->alpha_buf_next; io.kkt = out->kkt; io.status = out->status; io.qp_iters = out->qp_iters;
   io.nlp_iters = out->nlp_iters; io.n_fact = out->n_fact; io.active = (unsigned long long*)out->active;
-  io.B = B; io.mode = mode;
+  io.B = B; io.ld = B; io.mode = mode;
   for (int b = 0; b < B; b++) {
     lemu::g_grp.cur = 0;
     const int C = lane_classify(io, b);
