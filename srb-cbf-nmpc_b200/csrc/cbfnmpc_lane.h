@@ -955,7 +955,8 @@ struct LaneSolver {
     // ---- pass A
     KV gfy; double re_pi[4], re_nu[2], re_eta, e_d, e_p, th, zd, szmin, szmax;
     {
-      double e_c = 0.0, zmax = 0.0, smin = 1e300;
+      int zhw = 0;          // running maximum of the multipliers' high words (z >= 0; a NaN shows up as a huge value)
+      bool spos = true;     // every slack positive
       szmin = 1e300; szmax = 0.0;
       const double iks = 1.0 / P.kappa_sigma, adp = ad_prev;
       nlp_scatter_e(d::N_EV, xp);
@@ -965,20 +966,21 @@ struct LaneSolver {
         const double slo = e - l_slot_lo<C, true>(P, s), shi = vhi ? l_slot_hi<C, true>(P, s) - e : 1.0;
         const double rlo = l_rcp(slo), rhi = l_rcp(shi);
         double zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
-        smin = fmin(smin, fmin(slo, shi));
+        spos = spos && (slo > 0.0) && (shi > 0.0);
         if (it > 0) {  // multiplier step of the previous iteration, then the z reset (Ipopt eq. 16) with that iteration's mu
           zlo += adp * pr(d::N_D + s);
           if (vhi) zhi += adp * pr(d::N_E + s);
-          const double mr_lo = mu * rlo, mr_hi = mu * rhi;
-          zlo = fmin(fmax(zlo, mr_lo * iks), P.kappa_sigma * mr_lo);
-          if (vhi) zhi = fmin(fmax(zhi, mr_hi * iks), P.kappa_sigma * mr_hi);
+          // z in [mu / (kappa s), kappa mu / s] <=> s z in [mu / kappa, kappa mu]: with kappa = 1e10 the clamp is almost never active
+          const double pl = slo * zlo, ph_ = shi * zhi;
+          if (!(pl >= mu * iks && pl <= P.kappa_sigma * mu)) { const double mr_lo = mu * rlo; zlo = fmin(fmax(zlo, mr_lo * iks), P.kappa_sigma * mr_lo); }
+          if (vhi && !(ph_ >= mu * iks && ph_ <= P.kappa_sigma * mu)) { const double mr_hi = mu * rhi; zhi = fmin(fmax(zhi, mr_hi * iks), P.kappa_sigma * mr_hi); }
           pr(d::N_ZLO + s) = zlo; pr(d::N_ZHI + s) = zhi;
         }
         pr(d::N_SLO + s) = slo; pr(d::N_SHI + s) = shi; pr(d::N_A + s) = rlo; pr(d::N_B + s) = rhi;
         const double szl = slo * zlo, szh = shi * zhi;
-        e_c = fmax(e_c, fmax(fabs(szl), fabs(szh)));
-        szmin = fmin(szmin, vhi ? fmin(szl, szh) : szl); szmax = fmax(szmax, vhi ? fmax(szl, szh) : szl);
-        zmax = fmax(zmax, fmax(zlo, zhi));
+        const double szh_ = vhi ? szh : szl;   // the distance slot has no upper half
+        szmin = fmin(szmin, fmin(szl, szh_)); szmax = fmax(szmax, fmax(szl, szh_));
+        zhw = l_imax(zhw, l_imax(l_hiword(zlo), l_hiword(zhi)));
         pr(d::N_G + s) = zlo - zhi;                    // J'z weights
         pr(d::N_C + s) = zlo * rlo + zhi * rhi;        // Sigma
         pr(d::N_D + s) = rlo - (vhi ? rhi : 0.0);      // barrier gradient weights / mu
@@ -997,8 +999,10 @@ struct LaneSolver {
       double rem = fabs(re_eta), res = fabs(re_eta);
       LUNR for (int i = 0; i < 4; i++) { rem = fmax(rem, fabs(re_pi[i])); res += fabs(re_pi[i]); }
       LUNR for (int a = 0; a < 2; a++) { rem = fmax(rem, fabs(re_nu[a])); res += fabs(re_nu[a]); }
-      e_d = g_max(g, rdm); e_p = g_max(g, rem); e_c = g_max(g, e_c); zmax = g_max(g, zmax);
+      e_d = g_max(g, rdm); e_p = g_max(g, rem);
       szmin = g_min(g, szmin); szmax = g_max(g, szmax);
+      const double e_c = szmax;                                  // complementarity error max_i s_i z_i (s, z > 0)
+      const double zmax = g_max(g, l_from_hiword(zhw));          // to 2^-20 relative: only compared with z_div
       th = g_sum(g, res);
       LUNR for (int i = 0; i < 4; i++) { pr(d::F_GFY + i) = gfy.xs[i]; pr(d::F_GFY + 6 + i) = gfy.lm[i]; pr(d::F_REP + i) = re_pi[i]; }
       pr(d::F_GFY + 4) = gfy.us[0]; pr(d::F_GFY + 5) = gfy.us[1]; pr(d::F_GFY + 10) = gfy.dl;
@@ -1011,7 +1015,7 @@ struct LaneSolver {
       // its FP64 noise level, s = mu / z ~ 1e-13 for active rows, and may hover just above tol for many iterations)
       if (E0 <= P.tol || (mu <= P.tol / 10.0 && E0 <= P.acc_tol)) { info.status = 0; return true; }
       if (it == P.max_iter) { info.status = 1; return true; }
-      if (!(zmax < P.z_div) || !(E0 < 1e300) || g_any(g, !(smin > 0.0))) { info.status = 2; return true; }
+      if (!(zmax < P.z_div) || !(E0 < 1e300) || g_any(g, !spos)) { info.status = 2; return true; }
     }
     // ---- barrier update (Ipopt eq. 7): max_i |s_i z_i - mu| from the extreme products
     for (;;) {

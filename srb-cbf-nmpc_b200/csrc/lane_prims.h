@@ -58,6 +58,10 @@ LDEV double l_rsq(double v) {  // 1/sqrt(v)
 }
 LDEV double l_mul_rn(double a, double b) { return __dmul_rn(a, b); }
 LDEV double l_add_rn(double a, double b) { return __dadd_rn(a, b); }
+// high word of a double / double from a high word: non-negative doubles order like their high words, which makes a 1-instruction
+// (integer) running maximum good to 2^-20 relative -- enough for threshold tests
+LDEV int l_hiword(double v) { return __double2hiint(v); }
+LDEV double l_from_hiword(int h) { return __hiloint2double(h, 0); }
 #ifdef CBF_DBGBUF  // debug builds only: group 0 of warp 0 logs numbers into a device buffer (lighter than printf)
 __device__ double g_dbg[8192];
 __device__ int g_dbg_n;
@@ -123,6 +127,8 @@ LDEV double l_rsq(double v) { double r = (double)(float)(1.0 / sqrt(v)); const d
 LDEV double l_rcp(double v) { return 1.0 / v; }
 LDEV double l_rsq(double v) { return 1.0 / sqrt(v); }
 #endif
+LDEV int l_hiword(double v) { uint64_t u; memcpy(&u, &v, 8); return (int)(u >> 32); }
+LDEV double l_from_hiword(int h) { uint64_t u = (uint64_t)(uint32_t)h << 32; double v; memcpy(&v, &u, 8); return v; }
 LDEV double l_mul_rn(double a, double b) { volatile double r = a * b; return r; }
 LDEV double l_add_rn(double a, double b) { volatile double r = a + b; return r; }
 #ifdef CBF_DBGBUF
@@ -138,6 +144,7 @@ extern double g_dbg[8192]; extern int g_dbg_n;
 #endif
 #endif
 
+LDEV int l_imax(int a, int b) { return a > b ? a : b; }
 // ------------------------------------------------------------------------------------------ group reductions
 LDEV double g_sum(const Grp& g, double v) { v += g_xor(g, v, 1); v += g_xor(g, v, 2); return v; }
 LDEV double g_max(const Grp& g, double v) { v = fmax(v, g_xor(g, v, 1)); v = fmax(v, g_xor(g, v, 2)); return v; }
