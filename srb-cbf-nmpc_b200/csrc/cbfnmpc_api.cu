@@ -11,7 +11,7 @@
 #include "cbfnmpc_lane.h"
 
 // ---------------------------------------------------------------------------------------------------------
-// The solver (cbfnmpc_lane.h): one instance = 4 adjacent lanes, 8 instances per warp, one warp per CTA.
+// The solver (cbfnmpc_lane.h): one instance = 4 adjacent lanes, 8 instances per warp, LANE_NT / 32 warps per CTA.
 // A pre-pass sorts the instances by stance class (4 feet / diagonal pair) so that every warp runs one template
 // instantiation; the order inside a class is the batch order (deterministic).
 // ---------------------------------------------------------------------------------------------------------

@@ -13,15 +13,16 @@
 // recursion over the horizon as a chain lane 3 -> 2 -> 1 -> 0 (each lane keeps its stage's factors in registers);
 // 5x5 Schur complement for the global slack variable and the (capped) distance rows.
 //
-// Everything a lane touches is addressed with compile-time indices: the iterate, the Hessian blocks and the Riccati
-// factors live in registers; per-row state (slacks, multipliers, reciprocals) lives in thread-private columns of shared
-// memory (element f of thread t at priv[f * LANE_NT + t]: conflict-free, immediate offsets).
+// The iterate, the Hessian blocks and the Riccati factors live in registers (compile-time indices only); per-row state
+// (slacks, multipliers, reciprocals, steps) and a few vectors that would otherwise be spilled live in thread-private
+// columns of shared memory (element f of thread t at priv[f * LANE_NT + t]: conflict-free).  Formulas that are the same for
+// every row run as rolled loops over those columns: the kernel is sensitive to its instruction footprint.
 #pragma once
 #include "cbfnmpc_types.h"
 #include "lane_prims.h"
 
 #ifndef LANE_NT
-#define LANE_NT 128  // threads per CTA = stride of the thread-private shared-memory columns
+#define LANE_NT 64  // threads per CTA = stride of the thread-private shared-memory columns (set by cbfnmpc_api.cu)
 #endif
 #define LUNR _Pragma("unroll")
 
