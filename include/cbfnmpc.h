@@ -109,11 +109,13 @@ int cbfnmpc_set_options(cbfnmpc_ctx *ctx, const cbfnmpc_options *o);
 
 /* device pointers; asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream) */
 int cbfnmpc_solve_batch(cbfnmpc_ctx *ctx, int B, int mode, const cbfnmpc_in *in, const cbfnmpc_out *out, void *cuda_stream);
-/* host pointers; copies in, solves, copies out, synchronises */
+/* host pointers; copies in, solves, copies out, synchronises.  Batches of >= 1024 instances travel as 2-4 column ranges on
+ * separate streams so that copies overlap solves; pinned buffers laid out back to back need one copy per range and direction. */
 int cbfnmpc_solve_batch_host(cbfnmpc_ctx *ctx, int B, int mode, const cbfnmpc_in *in, const cbfnmpc_out *out);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 long long cbfnmpc_launch_count(const cbfnmpc_ctx *ctx);
-/* last solve kernel's duration in ms measured with CUDA events on the launch stream (synchronises) */
+/* last solve kernel's duration in ms measured with CUDA events on the launch stream (synchronises).  A host-buffer call on a
+ * large batch launches one kernel per column range (see cbfnmpc_solve_batch_host); the first range's kernel is the one timed. */
 int cbfnmpc_last_kernel_ms(cbfnmpc_ctx *ctx, float *ms);
 
 /* One instance in the reference's own dense layout (column-major Eigen matrices of pack_nlp_data.h:11-29).
