@@ -14,6 +14,8 @@
  *   cbfnmpc_pack_inputs           <- MPC_dist::updateState + copPlanner_eventbase + footholdsPlanner, B agents at once
  *                                    src/MPC_dist.cpp:1195-1202, 702-782, 1204-1266
  *   cbfnmpc_run_cycle             <- updateState + run_NMPC from the raw per-cycle inputs (pack, then solve)
+ *   cbfnmpc_qp_dense_batch        <- iswiftQp_e on a QP without stage structure (the low-level controller's, src/LowLevelCtrl.cpp:18-52),
+ *                                    B problems at once                                   optimization/iSWIFT/src/iswift_qp.cpp:44-210
  *   cbfnmpc_generate_reference    <- MPC_dist::generateReferenceTrajectory (offline, once per scenario), T teams at once   src/MPC_dist.cpp:930-1062
  *   cbfnmpc_closed_loop           <- the receding-horizon loop of src/A1_Sim.cpp:983-1266 on the LIP template (no RaiSim): run_NMPC once
  *                                    per gait domain, state rolled to the end of the domain, MPC_dist::updateDistance_to_fail (:21-40)
@@ -189,6 +191,15 @@ int cbfnmpc_closed_loop(cbfnmpc_ctx *ctx, int B, int n_cycles, int mode, const c
  * The reference's column quirk is kept: the last two output columns are the undecimated steps loop/40 and loop/40 + 1. */
 int cbfnmpc_generate_reference(cbfnmpc_ctx *ctx, int n_teams, const double *Pstart, const double *Pobs, int n_obs, double goal_x,
                                double goal_y, int loop, double *Pr_refined, double *Prd_refined, void *cuda_stream);
+
+/* B dense convex QPs of identical dimensions, iSWIFT's algorithm and the context's qp_* options, one warp per problem:
+ *     min 1/2 x'Px + c'x   s.t.  A x = b,  G x <= h          n <= 32, p <= 24 (may be 0), 1 <= m <= 64
+ * Device pointers; problem q's data is contiguous: P + q n n (n x n), A + q p n (p x n), G + q m n (m x n), all column-major
+ * like the Eigen matrices iswiftQp_e receives; c + q n, b + q p, h + q m.  Outputs x [B][n]; y [B][p], z [B][m] optional (NULL);
+ * status [B]: 0 converged, 1 factorisation failed (P + G'WG not positive definite), 2 iteration limit; iters [B]. */
+int cbfnmpc_qp_dense_batch(cbfnmpc_ctx *ctx, int B, int n, int p, int m, const double *P, const double *c, const double *A,
+                           const double *b, const double *G, const double *h, double *x, double *y, double *z, int32_t *status,
+                           int32_t *iters, void *cuda_stream);
 
 /* FP64 DFMA peak microbenchmark (TFLOP/s) used as the roofline denominator by bench.py */
 int cbfnmpc_measure_fp64_peak(cbfnmpc_ctx *ctx, double *tflops);

@@ -40,6 +40,7 @@ def load():
     L.cbfnmpc_run_cycle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.RawIn), C.c_void_p, C.POINTER(capi.Out), C.c_void_p]
     L.cbfnmpc_generate_reference.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cbfnmpc_qp_dense_batch.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 11 + [C.c_void_p]
     L.cbfnmpc_closed_loop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(capi.RawIn), C.POINTER(capi.WorldState), C.c_double, C.c_void_p]
     L.cbfnmpc_launch_count.argtypes = [C.c_void_p]
     L.cbfnmpc_launch_count.restype = C.c_longlong
@@ -53,7 +54,7 @@ def load():
 EXPORTS = ["cbfnmpc_version", "cbfnmpc_last_error", "cbfnmpc_default_gains", "cbfnmpc_default_options", "cbfnmpc_create",
            "cbfnmpc_destroy", "cbfnmpc_set_gains", "cbfnmpc_set_options", "cbfnmpc_solve_batch", "cbfnmpc_solve_batch_host",
            "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak",
-           "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle", "cbfnmpc_closed_loop", "cbfnmpc_generate_reference"]
+           "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle", "cbfnmpc_closed_loop", "cbfnmpc_generate_reference", "cbfnmpc_qp_dense_batch"]
 
 
 def default_gains():
@@ -144,6 +145,12 @@ class BatchSolver:
     def generate_reference(self, n_teams, pstart_ptr, pobs_ptr, n_obs, pr_ptr, prd_ptr, goal=(10.0, 0.0), loop=100000, stream=None):
         """generateReferenceTrajectory for n_teams teams on the device (cbfnmpc_generate_reference)."""
         self._ck(self.L.cbfnmpc_generate_reference(self.ctx, n_teams, pstart_ptr, pobs_ptr, n_obs, goal[0], goal[1], loop, pr_ptr, prd_ptr, stream))
+
+    def qp_dense_batch(self, B, n, p, m, ptrs, stream=None):
+        """B dense QPs (iSWIFT's algorithm, one warp each; cbfnmpc_qp_dense_batch).  ptrs: device pointers P, c, A, b, G, h, x, y, z,
+        status, iters (A, b, y, z may be None)."""
+        a = [ptrs.get(k) for k in ("P", "c", "A", "b", "G", "h", "x", "y", "z", "status", "iters")]
+        self._ck(self.L.cbfnmpc_qp_dense_batch(self.ctx, B, n, p, m, *a, stream))
 
     def closed_loop(self, B, n_cycles, raw, world, mode=capi.MODE_QP_NLP, fail_radius=0.5, stream=None):
         """n_cycles receding-horizon cycles of B worlds, entirely on the device (cbfnmpc_closed_loop).  `world`: dict of

@@ -9,6 +9,7 @@
 #define LANE_NT 64  // 2 warps (16 instances, one stance class) per CTA, 2 CTAs per SM; the warps of a CTA re-synchronise every solver iteration
 #endif
 #include "cbfnmpc_lane.h"
+#include "cbfnmpc_qpdense.h"
 
 // ---------------------------------------------------------------------------------------------------------
 // The solver (cbfnmpc_lane.h): one instance = 4 adjacent lanes, 8 instances per warp, LANE_NT / 32 warps per CTA.
@@ -232,6 +233,16 @@ __global__ void __launch_bounds__(128) cbfnmpc_refgen_kernel(int n_teams, const 
     x = x + a13 * vx + b1 * ux; y = y + a13 * vy + b1 * uy;                                      // q+ = Ae q + Be F scale, :1041
     vx = a33 * vx + b3 * ux; vy = a33 * vy + b3 * uy;
   }
+}
+
+// Dense batched QP (cbfnmpc_qpdense.h): one warp per problem, 3 problems per CTA (58 KB of shared memory each).
+#define QD_WARPS 3
+__global__ void __launch_bounds__(32 * QD_WARPS, 1) cbfnmpc_qpdense_kernel(const __grid_constant__ QDenseIO io) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  QDenseWS* ws = reinterpret_cast<QDenseWS*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * QD_WARPS + warp;
+  if (q < io.B) qdense_solve_warp(ws[warp], io, q);
 }
 
 // FP64 pipe microbenchmark: 8 independent DFMA chains per thread.
@@ -505,6 +516,25 @@ int cbfnmpc_run_cycle(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_raw_in* raw
   int rc = cbfnmpc_pack_inputs(c, B, raw, &din, cuda_stream);
   if (rc) return rc;
   return launch(c, B, mode, &din, out, nullptr, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
+
+int cbfnmpc_qp_dense_batch(cbfnmpc_ctx* c, int B, int n, int p, int m, const double* P, const double* cv, const double* A, const double* b,
+                           const double* G, const double* h, double* x, double* y, double* z, int32_t* status, int32_t* iters, void* cuda_stream) {
+  if (!c || B < 1 || !P || !cv || !G || !h || !x || !status || !iters) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_qp_dense_batch: bad argument");
+  if (n < 1 || n > QD_NMAX || p < 0 || p > QD_PMAX || m < 1 || m > QD_MMAX) return fail(CBFNMPC_ERR_ARG, "dimensions outside n <= 32, p <= 24, 1 <= m <= 64");
+  if (p > 0 && (!A || !b)) return fail(CBFNMPC_ERR_ARG, "equality data missing");
+  CK(cudaSetDevice(c->device));
+  static bool attr_set = false;
+  if (!attr_set) { CK(cudaFuncSetAttribute(cbfnmpc_qpdense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QD_WARPS * sizeof(QDenseWS)))); attr_set = true; }
+  QDenseIO io;
+  io.B = B; io.n = n; io.p = p; io.m = m; io.P = P; io.c = cv; io.A = A; io.b = b; io.G = G; io.h = h;
+  io.reltol = c->opts.qp_reltol; io.abstol = c->opts.qp_abstol; io.maxit = c->opts.qp_maxit;
+  io.x = x; io.y = y; io.z = z; io.status = status; io.iters = iters;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  cbfnmpc_qpdense_kernel<<<(B + QD_WARPS - 1) / QD_WARPS, 32 * QD_WARPS, QD_WARPS * sizeof(QDenseWS), st>>>(io);
+  CK(cudaGetLastError());
+  c->launches++;
+  return CBFNMPC_OK;
 }
 
 int cbfnmpc_generate_reference(cbfnmpc_ctx* c, int n_teams, const double* Pstart, const double* Pobs, int n_obs, double goal_x, double goal_y,

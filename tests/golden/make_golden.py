@@ -90,6 +90,17 @@ def main():
         else:
             print("nv", nv, "status", r["status"], "(no scipy run)")
     np.savez(os.path.join(HERE, "mpc_golden.npz"), **{k: np.array(v) for k, v in recs.items()})
+    # ---- 4. dense QPs of the low-level controller's size (src/LowLevelCtrl.cpp:18-52: 31 variables, 18 equalities, 45 inequalities
+    #         at 4 stance feet) through the reference's own iSWIFT core
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from qp_cases import lowlevel_like_qps
+    qps = lowlevel_like_qps(12, seed=20251018 + 7000)
+    sol = dict(x=[], iters=[], flag=[])
+    for (Pq, cq, Aq, bq, Gq, hq) in qps:
+        xr, yr, zr, sr, itr, fl, _, _ = O.iswift_ref_dense(Pq, cq, Aq, bq, Gq, hq)
+        sol["x"].append(xr); sol["iters"].append(itr); sol["flag"].append(fl)
+    print("low-level-size QPs through the reference core: flags", sol["flag"], "iterations", sol["iters"])
+    np.savez(os.path.join(HERE, "lowlevel_qp_golden.npz"), x=np.array(sol["x"]), iters=np.array(sol["iters"]), flag=np.array(sol["flag"]))
 
 
 if __name__ == "__main__":

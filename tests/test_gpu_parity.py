@@ -386,3 +386,54 @@ def test_non_default_gains_and_options(pkg):
     out = s.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP_NLP)
     assert ((out["status"][0] == capi.ST_MAXITER) | (out["status"][0] == capi.ST_INFEASIBLE)).all() and out["nlp_iters"][0].max() <= 3
     s.close()
+
+
+def test_dense_qp_batch_against_iswift(pkg):
+    """cbfnmpc_qp_dense_batch (one warp per dense QP, iSWIFT's algorithm): the reference's canned QP
+    (optimization/iSWIFT/include/Matrices_small.h: 30 variables, 18 equalities, 24 inequalities, known answer from the
+    reference's own core), low-level-controller-size QPs against the reference core's answers, and a batch of 300 against the
+    oracle."""
+    import os
+    import torch
+    import oracle as O
+    import qp_cases
+    dev = torch.device("cuda", 0)
+    s = pkg.BatchSolver(device=0, max_batch=8, max_obs=20)
+
+    def run(qps):
+        B = len(qps); n = qps[0][0].shape[0]; p = qps[0][2].shape[0]; m = qps[0][4].shape[0]
+        cm = lambda k: torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(q[k], float).T for q in qps]))).to(dev)   # column-major per problem
+        vec = lambda k: torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(q[k], float) for q in qps]))).to(dev)
+        t = dict(P=cm(0), c=vec(1), A=cm(2), b=vec(3), G=cm(4), h=vec(5), x=torch.zeros((B, n), dtype=torch.float64, device=dev),
+                 y=torch.zeros((B, max(p, 1)), dtype=torch.float64, device=dev), z=torch.zeros((B, m), dtype=torch.float64, device=dev),
+                 status=torch.zeros(B, dtype=torch.int32, device=dev), iters=torch.zeros(B, dtype=torch.int32, device=dev))
+        s.qp_dense_batch(B, n, p, m, {k: v.data_ptr() for k, v in t.items()})
+        torch.cuda.synchronize()
+        return {k: t[k].cpu().numpy() for k in ("x", "y", "z", "status", "iters")}
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "iswift_small.npz"))
+    r = run([(g["P"], g["c"], g["A"], g["b"], g["G"], g["h"])])
+    assert r["status"][0] == 0 and r["iters"][0] == int(g["iters"])
+    assert np.abs(r["x"][0] - g["x"]).max() < 1e-8 * np.abs(g["x"]).max()
+    gl = np.load(os.path.join(os.path.dirname(__file__), "golden", "lowlevel_qp_golden.npz"))
+    qps = qp_cases.lowlevel_like_qps(12)
+    r = run(qps)
+    assert (r["status"] == 0).all() and (r["iters"] == gl["iters"]).all()
+    assert np.abs(r["x"] - gl["x"]).max() < 1e-8 * np.abs(gl["x"]).max()
+    many = qp_cases.lowlevel_like_qps(300, seed=99)
+    r = run(many)
+    worst = 0.0
+    for k, q in enumerate(many):
+        x, y, z, sl, it, flag = O.qp_mehrotra(*q)
+        assert flag == 0 and r["status"][k] == 0 and abs(int(r["iters"][k]) - it) <= 1
+        if r["iters"][k] == it: worst = max(worst, np.abs(r["x"][k] - x).max() / max(1.0, np.abs(x).max()))
+    assert worst < 1e-8, worst
+    # no equalities, and a problem whose reduced Hessian is not positive definite (status 1)
+    noeq = [(q[0], q[1], np.zeros((0, 31)), np.zeros(0), q[4], q[5]) for q in many[:5]]
+    r = run(noeq)
+    for k, q in enumerate(noeq):
+        x, y, z, sl, it, flag = O.qp_mehrotra(*q)
+        assert r["status"][k] == 0 and np.abs(r["x"][k] - x).max() < 1e-7 * max(1.0, np.abs(x).max())
+    bad = [(-np.eye(31), many[0][1], many[0][2], many[0][3], many[0][4], many[0][5])]
+    assert run(bad)["status"][0] == 1
+    s.close()

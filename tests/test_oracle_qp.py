@@ -56,3 +56,17 @@ def test_mpc_qp_against_live_reference_core():
         # numpy prototype follows the same path
         xn = P.mehrotra_qp(Q, f, A, b, G, h)
         assert xn[4] == xo[4] and np.abs(xn[0] - xo[0]).max() < 1e-9
+
+
+def test_lowlevel_size_qps_against_the_reference_core():
+    """Dense QPs with the low-level controller's dimensions (tests/qp_cases.py): the oracle's Mehrotra restatement against
+    the answers of the reference's own iSWIFT core (tests/golden/lowlevel_qp_golden.npz): same iteration counts, same x."""
+    import os
+    import qp_cases
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lowlevel_qp_golden.npz"))
+    qps = qp_cases.lowlevel_like_qps(12)
+    for k, (P_, c_, A_, b_, G_, h_) in enumerate(qps):
+        x, y, z, s, it, flag = O.qp_mehrotra(P_, c_, A_, b_, G_, h_)
+        assert flag == 0 and g["flag"][k] == 0
+        assert it == g["iters"][k]
+        assert np.abs(x - g["x"][k]).max() < 1e-8 * max(1.0, np.abs(g["x"][k]).max())
