@@ -50,20 +50,30 @@ __global__ void __launch_bounds__(1024, 1) cbfnmpc_classify_kernel(const __grid_
 }
 
 __global__ void __launch_bounds__(LANE_NT, 1) cbfnmpc_lane_kernel(const __grid_constant__ KParams P, const __grid_constant__ BatchIO io,
-                                                                  const int* __restrict__ perm, const int* __restrict__ counts) {
+                                                                  const int* __restrict__ perm, const int* __restrict__ counts, int sm_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Priv pr; pr.base = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
   constexpr int IPC = LANE_NT / 4;  // instances per CTA; a CTA runs one stance class
   const int grp = threadIdx.x >> 2;
   const int n4 = counts[0], n2 = counts[1];
   const int c4 = (n4 + IPC - 1) / IPC;
-  if ((int)blockIdx.x < c4) {
-    const int slot = blockIdx.x * IPC + grp;
+  // The first 2 x (number of SMs) CTAs are resident at once and are handed out breadth-first over the SMs, so blockIdx b and
+  // b + nsm share SM b: give those two the neighbouring work items 2b, 2b + 1 (same stance class except at the class boundary)
+  // so that the two CTAs of an SM share instruction-cache lines.  SMs that get a single CTA take the items after the pairs.
+  int cta = blockIdx.x;
+  {
+    const int nsm = sm_count, total = (int)gridDim.x, first = total < 2 * nsm ? total : 2 * nsm;
+    const int npair = first > nsm ? first - nsm : 0;
+    if (cta < nsm) cta = (cta < npair) ? 2 * cta : 2 * npair + (cta - npair);
+    else if (cta < first) cta = 2 * (cta - nsm) + 1;
+  }
+  if (cta < c4) {
+    const int slot = cta * IPC + grp;
     const bool valid = slot < n4;
     lane_run_group<4>(P, io, valid ? perm[slot] : 0, valid, pr);
   } else {
-    const int slot = (blockIdx.x - c4) * IPC + grp;
-    if ((int)(blockIdx.x - c4) * IPC >= n2) return;
+    const int slot = (cta - c4) * IPC + grp;
+    if ((cta - c4) * IPC >= n2) return;
     const bool valid = slot < n2;
     lane_run_group<2>(P, io, valid ? perm[io.B + slot] : 0, valid, pr);
   }
@@ -274,6 +284,7 @@ struct cbfnmpc_ctx {
   cudaStream_t cstream[CBF_MAX_CHUNKS];  // host-buffer calls: chunk k of the batch travels on cstream[k] (cstream[0] == stream)
   cudaEvent_t ev0, ev1;
   bool timed;
+  int sm_count;
   long long launches;
   // staging for the host-pointer entry points
   double* d_in;   // (32 + 2 max_obs) * max_batch
@@ -303,6 +314,7 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
   CK(cudaSetDevice(device));
   cbfnmpc_ctx* c = new cbfnmpc_ctx();
   c->device = device; c->max_batch = max_batch; c->max_obs = max_obs; c->launches = 0; c->timed = false;
+  { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); c->sm_count = prop.multiProcessorCount; }
   host_default_gains(&c->gains); host_default_options(&c->opts);
   host_fill_kparams(&c->gains, &c->opts, &c->kp);
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -366,7 +378,7 @@ static int launch_on(cbfnmpc_ctx* c, int B, int ld, int mode, const cbfnmpc_in* 
   cbfnmpc_classify_kernel<<<1, 1024, 0, st>>>(io, perm, counts);
   CK(cudaGetLastError());
   if (timed) CK(cudaEventRecord(c->ev0, st));  // the event pair brackets the solve kernel alone
-  cbfnmpc_lane_kernel<<<(B + ipc - 1) / ipc + 1, LANE_NT, LANE_NPRIV * LANE_NT * sizeof(double), st>>>(c->kp, io, perm, counts);
+  cbfnmpc_lane_kernel<<<(B + ipc - 1) / ipc + 1, LANE_NT, LANE_NPRIV * LANE_NT * sizeof(double), st>>>(c->kp, io, perm, counts, c->sm_count);
   CK(cudaGetLastError());
   if (timed) { CK(cudaEventRecord(c->ev1, st)); c->timed = true; }
   c->launches += 2;
