@@ -4,6 +4,7 @@ sys.path.insert(0, '.')  # run from the repo root
 import srb_cbf_nmpc_b200 as m
 from srb_cbf_nmpc_b200 import capi, scenarios as S
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+MODES = [int(a) for a in sys.argv[2:]] or [0, 1]  # 0 = QP only, 1 = QP -> NLP
 insts = S.cfg3_instances(B)
 d = capi.soa_from_instances(insts); K = int(d["n_obs"])
 s = m.BatchSolver(max_batch=B)
@@ -13,7 +14,7 @@ tout = {k: torch.zeros((n, B), dtype=torch.float64, device=dev) for k, n in capi
 tout.update({k: torch.zeros((n, B), dtype=torch.int32, device=dev) for k, n in capi.OUT_I32.items()})
 tout["active"] = torch.zeros((2, B), dtype=torch.int64, device=dev)
 ip = {k: v.data_ptr() for k, v in tin.items()}; op = {k: v.data_ptr() for k, v in tout.items()}
-for mode in (0, 1):
+for mode in MODES:
     for it in range(4):
         s.solve_device(B, ip, op, K, mode=mode); torch.cuda.synchronize()
         km = s.last_kernel_ms()

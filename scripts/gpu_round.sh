@@ -1,4 +1,5 @@
 #!/bin/bash
+# (the full capture is launch #5 of `bench_quick.py 4096 1`: the second device-resident QP->NLP launch over 4096 instances)
 # One GPU session: parity tests, bench line, ncu launch list and one full capture of the solve kernel.
 # usage: bash scripts/gpu_round.sh <tag>
 TAG=${1:-r01}
@@ -11,7 +12,7 @@ python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_$TAG.l
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_launch_$TAG.log
-python scripts/dev/bench_quick.py 4096 > gpurun_out/plainq_$TAG.log 2>&1 && \
+python scripts/dev/bench_quick.py 4096 1 > gpurun_out/plainq_$TAG.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:cbfnmpc_lane -s 5 -c 1 -f -o gpurun_out/prof_$TAG \
-    python scripts/dev/bench_quick.py 4096 > gpurun_out/ncu_full_$TAG.log 2>&1
+    python scripts/dev/bench_quick.py 4096 1 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_full_$TAG.log

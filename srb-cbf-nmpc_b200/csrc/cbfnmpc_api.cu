@@ -295,7 +295,16 @@ struct cbfnmpc_ctx {
   double* d_xstart;              // 41 (dense entry point)
   int* d_perm;                   // 2 * max_batch + 2: class lists + counts (grown on demand for device-pointer batches)
   int perm_cap;
+  // small host-buffer batches (<= small_cap instances): one pinned block up, one down (see solve_small)
+  int small_cap;
+  unsigned char *h_sin, *h_sout, *d_sin, *d_sout;
 };
+
+// Small host-buffer batches: inputs  = (32 + 2K) B doubles | contact 4B ints | class lists 2B ints | counts 2 ints (+ pad),
+//                             outputs = 90 B doubles | active 2B u64 | status, qp_iters, nlp_iters, n_fact 4B ints.
+#define CBF_SMALL_BATCH 64
+static size_t small_in_bytes(int B, int K) { return sizeof(double) * (size_t)(32 + 2 * K) * B + sizeof(int) * ((size_t)6 * B + 4); }
+static size_t small_out_bytes(int B) { return sizeof(double) * (size_t)92 * B + sizeof(int) * (size_t)4 * B; }
 
 extern "C" {
 
@@ -329,6 +338,12 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
   CK(cudaMalloc(&c->d_xstart, sizeof(double) * 41));
   CK(cudaMalloc(&c->d_perm, sizeof(int) * (2 * (size_t)max_batch + 2 * CBF_MAX_CHUNKS)));
   c->perm_cap = max_batch;
+  c->small_cap = max_batch < CBF_SMALL_BATCH ? max_batch : CBF_SMALL_BATCH;
+  {
+    const size_t nin = small_in_bytes(c->small_cap, max_obs), nout = small_out_bytes(c->small_cap);
+    CK(cudaMalloc(&c->d_sin, nin)); CK(cudaMalloc(&c->d_sout, nout));
+    CK(cudaHostAlloc(&c->h_sin, nin, cudaHostAllocDefault)); CK(cudaHostAlloc(&c->h_sout, nout, cudaHostAllocDefault));
+  }
   CK(cudaFuncSetAttribute(cbfnmpc_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LANE_NPRIV * LANE_NT * sizeof(double))));
   *out = c;
   return CBFNMPC_OK;
@@ -339,6 +354,7 @@ void cbfnmpc_destroy(cbfnmpc_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_in); cudaFree(c->d_contact); cudaFree(c->d_out); cudaFree(c->d_outi); cudaFree(c->d_active); cudaFree(c->d_xstart); cudaFree(c->d_perm);
+  cudaFree(c->d_sin); cudaFree(c->d_sout); cudaFreeHost(c->h_sin); cudaFreeHost(c->h_sout);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   for (int k = 1; k < CBF_MAX_CHUNKS; k++) cudaStreamDestroy(c->cstream[k]);
   cudaStreamDestroy(c->stream);
@@ -365,7 +381,7 @@ int cbfnmpc_set_options(cbfnmpc_ctx* c, const cbfnmpc_options* o) {
 
 // B instances whose arrays have pitch ld; perm = this launch's class lists (2 B + 2 ints)
 static int launch_on(cbfnmpc_ctx* c, int B, int ld, int mode, const cbfnmpc_in* in, const cbfnmpc_out* out, const double* xstart,
-                     cudaStream_t st, int* perm, bool timed = true) {
+                     cudaStream_t st, int* perm, bool timed = true, bool classify = true) {
   BatchIO io;
   io.x0 = in->x0; io.xdes = in->xdes; io.feet = in->feet_xy; io.contact = in->contact; io.obs = in->obs_xy; io.n_obs = in->n_obs;
   io.abuf = in->alpha_buf; io.xstart = xstart;
@@ -375,13 +391,74 @@ static int launch_on(cbfnmpc_ctx* c, int B, int ld, int mode, const cbfnmpc_in* 
   io.B = B; io.ld = ld; io.mode = mode;
   int* counts = perm + 2 * (size_t)B;
   const int ipc = LANE_NT / 4;
-  cbfnmpc_classify_kernel<<<1, 1024, 0, st>>>(io, perm, counts);
-  CK(cudaGetLastError());
+  if (classify) {
+    cbfnmpc_classify_kernel<<<1, 1024, 0, st>>>(io, perm, counts);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
   if (timed) CK(cudaEventRecord(c->ev0, st));  // the event pair brackets the solve kernel alone
   cbfnmpc_lane_kernel<<<(B + ipc - 1) / ipc + 1, LANE_NT, LANE_NPRIV * LANE_NT * sizeof(double), st>>>(c->kp, io, perm, counts, c->sm_count);
   CK(cudaGetLastError());
   if (timed) { CK(cudaEventRecord(c->ev1, st)); c->timed = true; }
-  c->launches += 2;
+  c->launches++;
+  return CBFNMPC_OK;
+}
+
+// A batch of at most small_cap instances in host memory: the latency of such a call is the driver's per-copy cost, not
+// bandwidth, so everything goes up in ONE copy from a pinned block (the class lists included: the stance classes are sorted on
+// the host, which has the contact flags, instead of by cbfnmpc_classify_kernel) and comes back in ONE copy.
+static int solve_small(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const cbfnmpc_out* out, int K) {
+  const size_t Bs = (size_t)B;
+  double* hd = (double*)c->h_sin;
+  const size_t nd = (size_t)(32 + 2 * K) * Bs;
+  memcpy(hd, in->x0, sizeof(double) * 4 * Bs);
+  memcpy(hd + 4 * Bs, in->xdes, sizeof(double) * 16 * Bs);
+  memcpy(hd + 20 * Bs, in->feet_xy, sizeof(double) * 8 * Bs);
+  if (in->alpha_buf) memcpy(hd + 28 * Bs, in->alpha_buf, sizeof(double) * 4 * Bs); else memset(hd + 28 * Bs, 0, sizeof(double) * 4 * Bs);
+  if (K > 0) memcpy(hd + 32 * Bs, in->obs_xy, sizeof(double) * 2 * (size_t)K * Bs);
+  int* hi = (int*)(hd + nd);
+  memcpy(hi, in->contact, sizeof(int) * 4 * Bs);
+  int* hperm = hi + 4 * Bs;
+  int n4 = 0, n2 = 0, nbad = 0;
+  int bad[CBF_SMALL_BATCH];
+  for (int b = 0; b < B; b++) {  // lane_classify, stable within a class like the kernel's scan
+    const int c0 = hi[b], csum = c0 + hi[Bs + b] + hi[2 * Bs + b] + hi[3 * Bs + b];
+    if (csum == 4) hperm[n4++] = b;
+    else if (csum == 2 && (c0 == 0 || c0 == 1)) hperm[Bs + n2++] = b;
+    else bad[nbad++] = b;
+  }
+  hperm[2 * Bs] = n4; hperm[2 * Bs + 1] = n2;
+  cudaStream_t st = c->stream;
+  CK(cudaMemcpyAsync(c->d_sin, c->h_sin, small_in_bytes(B, K), cudaMemcpyHostToDevice, st));
+  double* d = (double*)c->d_sin;
+  int* di = (int*)(d + nd);
+  cbfnmpc_in din = {d, d + 4 * Bs, d + 20 * Bs, di, d + 32 * Bs, K, d + 28 * Bs};
+  double* o = (double*)c->d_sout;
+  cbfnmpc_out dout;
+  dout.X = o; dout.U = o + 16 * Bs; dout.lam = o + 24 * Bs; dout.slack = o + 40 * Bs; dout.x_qp = o + 41 * Bs;
+  dout.alpha = o + 65 * Bs; dout.alpha_buf_next = o + 85 * Bs; dout.kkt = o + 89 * Bs;
+  dout.active = (uint64_t*)(o + 90 * Bs);
+  int32_t* doi = (int32_t*)(o + 92 * Bs);
+  dout.status = doi; dout.qp_iters = doi + Bs; dout.nlp_iters = doi + 2 * Bs; dout.n_fact = doi + 3 * Bs;
+  int rc = launch_on(c, B, B, mode, &din, &dout, nullptr, st, di + 4 * Bs, true, false);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(c->h_sout, c->d_sout, small_out_bytes(B), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  double* ho = (double*)c->h_sout;
+  uint64_t* ha = (uint64_t*)(ho + 90 * Bs);
+  int32_t* hoi = (int32_t*)(ho + 92 * Bs);
+  for (int k = 0; k < nbad; k++) {  // lane_store_bad
+    const int b = bad[k];
+    hoi[b] = 4; hoi[Bs + b] = 0; hoi[2 * Bs + b] = 0; hoi[3 * Bs + b] = 0; ho[89 * Bs + b] = 0.0; ho[40 * Bs + b] = 0.0;
+    ha[b] = 0; ha[Bs + b] = 0;
+  }
+  struct OSeg { double* h; size_t row, rows; };
+  const OSeg os[8] = {{out->X, 0, 16}, {out->U, 16, 8}, {out->lam, 24, 16}, {out->slack, 40, 1}, {out->x_qp, 41, 24}, {out->alpha, 65, 20},
+                      {out->alpha_buf_next, 85, 4}, {out->kkt, 89, 1}};
+  for (int i = 0; i < 8; i++) if (os[i].h) memcpy(os[i].h, ho + os[i].row * Bs, sizeof(double) * os[i].rows * Bs);
+  int32_t* const oi[4] = {out->status, out->qp_iters, out->nlp_iters, out->n_fact};
+  for (int i = 0; i < 4; i++) if (oi[i]) memcpy(oi[i], hoi + (size_t)i * Bs, sizeof(int32_t) * Bs);
+  if (out->active) memcpy(out->active, ha, sizeof(uint64_t) * 2 * Bs);
   return CBFNMPC_OK;
 }
 
@@ -413,6 +490,7 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
   const int K = (mode == CBFNMPC_MODE_QP_NLP) ? in->n_obs : 0;
   if (mode == CBFNMPC_MODE_QP_NLP && (!in->obs_xy || K < 1 || K > c->max_obs)) return fail(CBFNMPC_ERR_ARG, "NLP mode needs 1..max_obs obstacles");
   CK(cudaSetDevice(c->device));
+  if (B <= c->small_cap) return solve_small(c, B, mode, in, out, K);
   const size_t Bs = (size_t)B;
   // Large batches are cut into equal column ranges, each on its own stream: the upload of one range overlaps the solves of
   // the earlier ones and the downloads of the earlier ones overlap the solves of the later ones.  A range's kernel does not

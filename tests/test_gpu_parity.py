@@ -111,6 +111,15 @@ def test_results_do_not_depend_on_batch_order_or_size(pkg):
         one = s.solve_host(capi.soa_from_instances([insts[i]]), mode=capi.MODE_QP_NLP)
         for k in ("X", "U", "slack", "kkt", "status"):
             assert (one[k][:, 0] == base[k][:, i]).all(), (k, i)
+    # batches of <= 64 instances take the single-copy host path (classes sorted on the host): same bits, both modes
+    for n in (5, 64):
+        small = s.solve_host(capi.soa_from_instances(insts[:n]), mode=capi.MODE_QP_NLP)
+        for k in base:
+            assert (small[k] == base[k][:, :n]).all(), (k, n)
+    big = s.solve_host(capi.soa_from_instances(insts[:70]), mode=capi.MODE_QP)
+    small = s.solve_host(capi.soa_from_instances(insts[:33]), mode=capi.MODE_QP)
+    for k in ("X", "U", "lam", "x_qp", "alpha", "kkt", "status", "qp_iters"):
+        assert (small[k] == big[k][:, :33]).all(), k
     s.close()
 
 
