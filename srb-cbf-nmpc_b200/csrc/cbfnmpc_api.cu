@@ -52,9 +52,12 @@ __global__ void __launch_bounds__(1024, 1) cbfnmpc_classify_kernel(const __grid_
 __global__ void __launch_bounds__(LANE_NT, 1) cbfnmpc_lane_kernel(const __grid_constant__ KParams P, const __grid_constant__ BatchIO io,
                                                                   const int* __restrict__ perm, const int* __restrict__ counts, int sm_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Priv pr; pr.base = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
+  const int tid = l_tid();
+  Priv pr; pr.base = reinterpret_cast<double*>(smem_raw) + tid;
   constexpr int IPC = LANE_NT / 4;  // instances per CTA; a CTA runs one stance class
-  const int grp = threadIdx.x >> 2;
+  __shared__ unsigned long long pace_bar[2];
+  __shared__ int pace_flag[2 * ((LANE_NT + 31) / 32)];
+  const int grp = tid >> 2;
   const int n4 = counts[0], n2 = counts[1];
   const int c4 = (n4 + IPC - 1) / IPC;
   // The first 2 x (number of SMs) CTAs are resident at once and are handed out breadth-first over the SMs, so blockIdx b and
@@ -70,12 +73,12 @@ __global__ void __launch_bounds__(LANE_NT, 1) cbfnmpc_lane_kernel(const __grid_c
   if (cta < c4) {
     const int slot = cta * IPC + grp;
     const bool valid = slot < n4;
-    lane_run_group<4>(P, io, valid ? perm[slot] : 0, valid, pr);
+    lane_run_group<4>(P, io, valid ? perm[slot] : 0, valid, pr, pace_make(pace_bar, pace_flag));
   } else {
     const int slot = (cta - c4) * IPC + grp;
     if ((cta - c4) * IPC >= n2) return;
     const bool valid = slot < n2;
-    lane_run_group<2>(P, io, valid ? perm[io.B + slot] : 0, valid, pr);
+    lane_run_group<2>(P, io, valid ? perm[io.B + slot] : 0, valid, pr, pace_make(pace_bar, pace_flag));
   }
 }
 

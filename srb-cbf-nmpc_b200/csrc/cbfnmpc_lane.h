@@ -1233,7 +1233,7 @@ struct LaneSolver {
 // Bezier epilogue, store.  Shared by the CUDA kernel and the tests/emu harness.
 // ===============================================================================================================
 template <int C>
-LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid, Priv pr) {
+LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid, Priv pr, Pace pace = Pace()) {
   typedef LaneDims<C> d;
   constexpr int NW = d::NW;
   LaneSolver<C> S;
@@ -1291,10 +1291,10 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
       S.info.qp_flag = 0;
     }
   }
-  // ---- QP stage: the groups of a warp iterate together until the last one has finished
+  // ---- QP stage: the groups of a CTA iterate together (pace_go) until the last one has finished
   for (;;) {
     const bool act = valid && !qp_done;
-    if (!w_any(act)) break;
+    if (!pace_go(pace, act)) break;
     if (act) qp_done = S.qp_iter(P);
   }
   bool nl_done = true;
@@ -1309,7 +1309,7 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
   // ---- NLP stage
   for (;;) {
     const bool act = valid && !nl_done;
-    if (!w_any(act)) break;
+    if (!pace_go(pace, act)) break;
     if (act) nl_done = S.nlp_iter(P);
   }
   if (!valid) return;

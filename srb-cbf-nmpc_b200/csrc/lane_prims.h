@@ -18,7 +18,10 @@ struct Grp {
   unsigned mask;  // the 4 lanes of this group
   int j;          // stage owned by this lane (0..3)
 };
-LDEV Grp grp_make() { Grp g; const int lane = threadIdx.x & 31; g.j = lane & 3; g.mask = 0xFu << (lane & ~3); return g; }
+// (Making the thread index opaque to stop ptxas from re-reading SR_TID wherever it needs the mask again was tried: the registers
+// it then holds cost more in spills than the S2R latency -- 0.746 instead of 0.72 ms per 4096 solves.)
+LDEV int l_tid() { return (int)threadIdx.x; }
+LDEV Grp grp_make() { Grp g; const int lane = l_tid() & 31; g.j = lane & 3; g.mask = 0xFu << (lane & ~3); return g; }
 LDEV double g_idx(const Grp& g, double v, int src) { return __shfl_sync(g.mask, v, src, 4); }
 LDEV double g_up(const Grp& g, double v) { return __shfl_up_sync(g.mask, v, 1, 4); }      // from lane j-1 (lane 0: own value)
 LDEV double g_down(const Grp& g, double v) { return __shfl_down_sync(g.mask, v, 1, 4); }  // from lane j+1 (lane 3: own value)
@@ -29,11 +32,61 @@ LDEV unsigned g_xor_u(const Grp& g, unsigned v, int m) { return __shfl_xor_sync(
 LDEV unsigned g_bits(const Grp& g, bool p) { return (__ballot_sync(g.mask, p) >> ((threadIdx.x & 31) & ~3)) & 0xFu; }
 LDEV bool g_any(const Grp& g, bool p) { return (__ballot_sync(g.mask, p) & g.mask) != 0u; }
 LDEV bool g_all(const Grp& g, bool p) { return (__ballot_sync(g.mask, p) & g.mask) == g.mask; }
-// warp-wide vote used only for loop control ("does any group of this warp still iterate"); all 32 lanes converge here
-#if defined(LANE_NT) && LANE_NT > 32  // several warps per CTA kept within one solver iteration of each other (shared i-cache lines)
-LDEV bool w_any(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
+// Loop control ("does any group of this CTA still iterate").  The warps of a CTA are kept within ONE solver iteration of each
+// other so that they fetch the same instruction-cache lines, but they do not wait for each other every iteration: round r ends
+// with an arrival on mbarrier r & 1 and a wait for round r - 1 only.  A warp whose own groups have all finished has nothing to
+// run, so it waits for round r itself and reads the other warps' flags of that round; all warps leave in the same round.
+struct Pace {
+#if defined(LANE_NT) && LANE_NT > 32
+  unsigned bar, flg;  // shared-space addresses: 2 mbarriers (arrival count = warps per CTA), int flag[2][warps]
+  int r, me;          // round counter, thread index
+#endif
+};
+#if defined(LANE_NT) && LANE_NT > 32
+LDEV void pace_wait(unsigned bar, int parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "PACE_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra PACE_DONE;\n\t"
+      "bra PACE_WAIT;\n\t"
+      "PACE_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// all threads of the CTA, once, before the first pace_go
+LDEV Pace pace_make(unsigned long long* bars, int* flags) {
+  Pace p;
+  p.bar = (unsigned)__cvta_generic_to_shared(bars); p.flg = (unsigned)__cvta_generic_to_shared(flags); p.r = 0; p.me = l_tid();
+  if (p.me == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(p.bar), "r"(LANE_NT / 32) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(p.bar + 8), "r"(LANE_NT / 32) : "memory");
+  }
+  __syncthreads();
+  return p;
+}
+LDEV bool pace_go(Pace& p, bool act) {
+  constexpr int NWARP = LANE_NT / 32;
+  const bool mine = __any_sync(LFULL, act);
+  const int r = p.r, k = r & 1;
+  if (r > 0) pace_wait(p.bar + 8 * (k ^ 1), ((r - 1) >> 1) & 1);  // everybody has finished round r - 1
+  if ((p.me & 31) == 0) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(p.flg + 4 * (k * NWARP + (p.me >> 5))), "r"(mine ? 1 : 0) : "memory");
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(p.bar + 8 * k) : "memory");
+  }
+  p.r = r + 1;
+  if (mine) return true;
+  pace_wait(p.bar + 8 * k, (r >> 1) & 1);
+  int any = 0;
+#pragma unroll
+  for (int w = 0; w < NWARP; w++) {
+    int f;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(f) : "r"(p.flg + 4 * (k * NWARP + w)) : "memory");
+    any |= f;
+  }
+  return any != 0;
+}
 #else
-LDEV bool w_any(bool p) { return __any_sync(LFULL, p); }
+LDEV Pace pace_make(unsigned long long*, int*) { return Pace(); }
+LDEV bool pace_go(Pace&, bool act) { return __any_sync(LFULL, act); }
 #endif
 LDEV double l_rcp(double v) {  // 1/v: MUFU.RCP64H seed + two Newton steps (~1 ulp for normal operands)
 #if defined(CBF_EXACT_DIV) || defined(CBF_EXACT_RCP)
@@ -119,7 +172,8 @@ LDEV unsigned g_bits(const Grp& g, bool p) {
   unsigned r = (unsigned)(lemu::g_grp.xi[0] | (lemu::g_grp.xi[1] << 1) | (lemu::g_grp.xi[2] << 2) | (lemu::g_grp.xi[3] << 3)); lemu::barrier();
   return r;
 }
-LDEV bool w_any(bool p) { Grp g = grp_make(); return g_any(g, p); }  // the emulated warp is one group
+struct Pace {};
+LDEV bool pace_go(Pace&, bool act) { Grp g = grp_make(); return g_any(g, act); }  // the emulated CTA is one group
 #ifdef CBF_EMU_GPUMATH  // mimic the CUDA build's rounding: low-precision seed + two Newton steps (not correctly rounded)
 LDEV double l_rcp(double v) { double r = (double)(float)(1.0 / v); r = fma(fma(-v, r, 1.0), r, r); r = fma(fma(-v, r, 1.0), r, r); return r; }
 LDEV double l_rsq(double v) { double r = (double)(float)(1.0 / sqrt(v)); const double h = 0.5 * v; r = fma(fma(-h * r, r, 0.5), r, r); r = fma(fma(-h * r, r, 0.5), r, r); return r; }
