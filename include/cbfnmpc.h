@@ -46,7 +46,9 @@ extern "C" {
 #define CBFNMPC_ST_INFEASIBLE 2  /* line search / multiplier divergence: NLP has no interior */
 #define CBFNMPC_ST_NUMERICAL 3   /* inertia correction exhausted */
 #define CBFNMPC_ST_BADINPUT 4    /* number of stance feet other than 4 or 2 (src/MPC_dist.cpp:1238-1252; with 2 the reference picks
-                                    FL,RR when contactInd[0] == 0 and FR,RL otherwise, whatever the other flags say -- so does this) */
+                                    FL,RR when contactInd[0] == 0 and FR,RL otherwise, whatever the other flags say -- so does this),
+                                    or non-finite data (measured state, reference columns, stance feet, closest obstacle; the
+                                    reference hands those to its solvers unchecked).  X, U, ... are not written for status 4. */
 
 #define CBFNMPC_MODE_QP 0      /* use_snopt == false: the iSWIFT-equivalent QP optimum is the answer (MPC_dist.hpp:139) */
 #define CBFNMPC_MODE_QP_NLP 1  /* use_snopt == true : QP optimum -> NLP (src/MPC_dist.cpp:348 -> 402-427)              */

@@ -905,6 +905,16 @@ int orc_solve_instance(const orc_gains *g, const orc_options *o, const double *x
   memset(res, 0, sizeof(*res));
   int c = orc_stance_matrix(feet_xy, contact, F);
   if (c < 0) { res->status = 4; return 4; }
+  {
+    /* non-finite data are bad input too (the reference would hand NaN to its solvers) */
+    double obs0[2] = {0, 0}, chk = 0.0;
+    if (mode == 1) { double pos[2] = {x0[0], x0[2]}; orc_closest_obstacle(pos, obs_xy, K, obs0); }
+    for (int i = 0; i < 4; i++) chk += 0.0 * x0[i];
+    for (int i = 0; i < 16; i++) chk += 0.0 * xdes[i];
+    for (int i = 0; i < 2 * c; i++) chk += 0.0 * F[i];
+    chk += 0.0 * obs0[0] + 0.0 * obs0[1];
+    if (!(chk == 0.0)) { res->status = 4; res->c = c; return 4; }
+  }
   const int nv = 25 + 4 * c, p = ORC_NEQ, mi = 60 + 8 * c;
   double *buf = (double *)malloc(sizeof(double) * ((size_t)nv * nv + nv + (size_t)p * nv + p + (size_t)mi * nv + mi + 2 * nv + p + 2 * mi));
   double *Q = buf, *f = Q + (size_t)nv * nv, *A = f + nv, *b = A + (size_t)p * nv, *G = b + p, *h = G + (size_t)mi * nv;

@@ -903,7 +903,12 @@ struct LaneSolver {
     return g_all(g, okl);
   }
 
-  LMEM void nlp_init(const KParams& P) {
+  // Returns true when the stage is finished already: data that leave some row without an interior start (non-finite inputs)
+  // are answered with status 4, like the oracle does.
+  LMEM bool nlp_init(const KParams& P) {
+    double chk = 0.0 * x.dl + 0.0 * x.us[0] + 0.0 * x.us[1];  // a QP stage that broke down leaves NaN behind: no start point
+    LUNR for (int i = 0; i < 4; i++) chk += 0.0 * x.xs[i];
+    LUNR for (int i = 0; i < C; i++) chk += 0.0 * x.lm[i];
     // ---- step 0: strictly interior start (X, then U against friction, then lambda, then the slack variable)
     LUNR for (int i = 0; i < 4; i++) {
       const double lim = (i & 1) ? fmin(P.box, P.vmax) : P.box;
@@ -926,10 +931,12 @@ struct LaneSolver {
     filter_reset();
     mu = P.mu_init; tau = fmax(P.tau_min, 1.0 - mu); dw_last = 0.0; first_ic = true; nfilt = 0; nl_it = 0; ad_prev = 0.0;
     nlp_scatter_e(d::N_EV, xp);
+    bool interior = chk == 0.0;
     LSLOTS for (int s = 0; s < nsn; s++) {
       const bool v = true, vhi = s != d::SD;
       const double e = pr(d::N_EV + s);
       const double slo = v ? e - l_slot_lo<C, true>(P, s) : 1.0, shi = vhi ? l_slot_hi<C, true>(P, s) - e : 1.0;
+      interior = interior && (slo > 0.0) && (shi > 0.0);
       pr(d::N_SLO + s) = slo; pr(d::N_SHI + s) = shi;
       pr(d::N_ZLO + s) = v ? mu * l_rcp(slo) : 0.0; pr(d::N_ZHI + s) = vhi ? mu * l_rcp(shi) : 0.0;
     }
@@ -942,6 +949,8 @@ struct LaneSolver {
       theta_max = 1e4 * fmax(1.0, th0); theta_min = 1e-4 * fmax(1.0, th0);
     }
     info.status = 1; info.nlp_iters = 0;
+    if (!g_all(g, interior)) { info.status = 4; info.kkt = CBF_INF; return true; }
+    return false;
   }
 
   // one IPM-F iteration.  Returns true when the stage is finished (info.status set).
@@ -1244,7 +1253,7 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
   const size_t B = (size_t)io.ld;  // array pitch
   S.info.status = 1; S.info.qp_iters = 0; S.info.qp_flag = 3; S.info.nlp_iters = 0; S.info.n_fact = 0; S.info.kkt = 0.0;
   double abuf_j = 0.0;
-  bool qp_done = true;
+  bool qp_done = true, badin = false;
   if (valid) {
     // ---- load (SoA, one instance; lane j takes stage j)
     LUNR for (int i = 0; i < 4; i++) { pr(d::F_XDES + i) = io.xdes[(size_t)(4 * j + i) * B + b]; pr(d::F_XIN + i) = io.x0[(size_t)i * B + b]; }
@@ -1282,7 +1291,14 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
       if (bi == 0x7fffffff) bi = 0;
       S.c.ox = io.obs[(size_t)bi * B + b]; S.c.oy = io.obs[(size_t)(io.n_obs + bi) * B + b];
     }
-    if (io.xstart == nullptr) {
+    // non-finite data (0 * v is 0 only for finite v) are answered with status 4 before anything is solved
+    double chk = 0.0 * S.c.ox + 0.0 * S.c.oy;
+    LUNR for (int i = 0; i < 4; i++) chk += 0.0 * pr(d::F_XDES + i) + 0.0 * pr(d::F_XIN + i);
+    LUNR for (int t = 0; t < 8; t++) chk += 0.0 * F[t];
+    badin = !g_all(g, chk == 0.0);
+    if (badin) {
+      S.info.status = 4;
+    } else if (io.xstart == nullptr) {
       qp_done = S.qp_init(P);
     } else {
       LUNR for (int i = 0; i < 4; i++) { S.x.xs[i] = io.xstart[(size_t)(4 * j + i) * B + b]; S.x.lm[i] = (i < C) ? io.xstart[(size_t)(24 + C * j + i) * B + b] : 0.0; S.x.pi[i] = 0.0; }
@@ -1298,12 +1314,12 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
     if (act) qp_done = S.qp_iter(P);
   }
   bool nl_done = true;
-  if (valid) {
+  if (valid && !badin) {
     if (io.xqp) {
       LUNR for (int i = 0; i < 4; i++) io.xqp[(size_t)(4 * j + i) * B + b] = S.x.xs[i];
       LUNR for (int a = 0; a < 2; a++) io.xqp[(size_t)(16 + 2 * j + a) * B + b] = S.x.us[a];
     }
-    if (io.mode == 1) { S.nlp_init(P); nl_done = false; }
+    if (io.mode == 1) nl_done = S.nlp_init(P);
     else S.qp_final_kkt(P);
   }
   // ---- NLP stage

@@ -17,7 +17,7 @@ def oracle_batch(insts, mode=1, nthreads=8, alpha_buf=None, options=None):
     x0 = np.array([i[0] for i in insts]); xd = np.array([i[1] for i in insts])
     ft = np.array([np.asarray(i[2]).reshape(2, 4) for i in insts]); ct = np.array([i[3] for i in insts], np.int32)
     ob = np.array([i[4] for i in insts])
-    ab = np.stack([x0[:, 0], 0 * x0[:, 0], x0[:, 2], 0 * x0[:, 0]], 1) if alpha_buf is None else np.asarray(alpha_buf, float)
+    ab = np.stack([x0[:, 0], np.zeros(len(x0)), x0[:, 2], np.zeros(len(x0))], 1) if alpha_buf is None else np.asarray(alpha_buf, float)
     o = O.default_options()
     for k, v in (options or {}).items():
         setattr(o, k, v)
@@ -51,3 +51,22 @@ def active_rows_mask(out, i, c):
     lo, hi = int(out["active"][0, i]), int(out["active"][1, i])
     m = lo | (hi << 64)
     return {r for r in rows if (m >> r) & 1}
+
+
+def degenerate_instances(base):
+    """Non-finite and absurd data on top of 6 regular instances: (label, must_be_status_4, instance).  Non-finite measured state,
+    reference column, stance-foot coordinate or closest obstacle -> status 4 (bad input) in the oracle and in the kernel;
+    finite nonsense only has to come back, flagged as not converged, in both."""
+    out = []
+    spec = [("x0", np.nan, True), ("x0", np.inf, True), ("xdes", np.nan, True), ("xdes", -np.inf, True), ("feet", np.nan, True),
+            ("obs", np.nan, True), ("obs", np.inf, True), ("x0", 1e8, False), ("xdes", 1e12, False), ("feet0", 0.0, False), ("x0", 1e300, False)]
+    for k, (what, val, bad) in enumerate(spec):
+        a, b, c, d, e = base[k % len(base)]
+        a = np.array(a, float); b = np.array(b, float); c = np.array(c, float); e = np.array(e, float); d = [1, 1, 1, 1] if what == "feet" else d
+        if what == "x0": a[0] = val
+        if what == "xdes": b.flat[5] = val
+        if what == "feet": c.flat[2] = val
+        if what == "feet0": c[:] = 0.0
+        if what == "obs": e[:] = val
+        out.append(("%s=%g" % (what, val), bad, (a, b, c, d, e)))
+    return out

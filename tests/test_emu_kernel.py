@@ -54,3 +54,19 @@ def test_degenerate_support_weights_qp():
     ref = H.oracle_batch(insts, mode=0)
     assert (out["status"][0] == 0).all() and (ref["status"] == 0).all()
     assert np.abs(out["X"].T - ref["X"]).max() < 1e-8 and np.abs(out["U"].T - ref["U"]).max() < 1e-8
+
+
+def test_non_finite_and_absurd_inputs_come_back_flagged():
+    """NaN / Inf / absurd magnitudes in the inputs: every solve terminates; non-finite data are status 4 in the oracle and in
+    the kernel source, finite nonsense is 'not converged' in both (the reference would hand them to its solvers unchecked)."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("scen", os.path.join(os.path.dirname(__file__), "..", "srb-cbf-nmpc_b200", "scenarios.py"))
+    S = importlib.util.module_from_spec(spec); spec.loader.exec_module(S)
+    cases = H.degenerate_instances(S.cfg3_instances(6))
+    insts = [c[2] for c in cases]
+    for mode in (0, 1):
+        out = emu.solve(insts, mode=mode)
+        ref = H.oracle_batch(insts, mode=mode)
+        for k, (label, bad, _) in enumerate(cases):
+            if bad and (mode == 1 or not label.startswith("obs")): assert out["status"][0][k] == 4 and ref["status"][k] == 4, (label, mode, out["status"][0][k], ref["status"][k])
+            elif mode == 1: assert out["status"][0][k] != 0 and ref["status"][k] != 0, (label, out["status"][0][k], ref["status"][k])

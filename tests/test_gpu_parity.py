@@ -364,6 +364,19 @@ def test_ragged_batch_sizes_and_edge_inputs(pkg):
     out = s.solve_host(capi.soa_from_instances(one), mode=capi.MODE_QP_NLP)
     ref = H.oracle_batch(one, mode=1)
     assert H.compare(out, ref)["worst"] < 1e-6 and (out["status"][0] == ref["status"]).all()
+    # NaN / Inf / absurd magnitudes: the call returns, non-finite data are status 4, finite nonsense is "not converged"; the
+    # regular instances that travel in the same batch are unaffected
+    cases = H.degenerate_instances(allinst[:6])
+    mix = [c[2] for c in cases] + allinst[20:40]
+    out = s.solve_host(capi.soa_from_instances(mix), mode=capi.MODE_QP_NLP)
+    ref = H.oracle_batch(mix, mode=1)
+    for k, (label, isbad, _) in enumerate(cases):
+        if isbad: assert out["status"][0][k] == 4 and ref["status"][k] == 4, (label, out["status"][0][k], ref["status"][k])
+        assert out["status"][0][k] != 0 and ref["status"][k] != 0, label
+    n = len(cases)
+    assert (out["status"][0][n:] == ref["status"][n:]).all()
+    okk = ref["status"][n:] == 0
+    assert np.abs(out["X"].T[n:][okk] - ref["X"][n:][okk]).max() < 1e-6
     far = [(a, b, c_, d, e + 5000.0) for a, b, c_, d, e in allinst[:9]]                 # nothing within 1000 m: column 0 is used
     out = s.solve_host(capi.soa_from_instances(far), mode=capi.MODE_QP_NLP)
     ref = H.oracle_batch(far, mode=1)
