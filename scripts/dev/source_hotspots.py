@@ -2,7 +2,7 @@
 """Dev tool: attribute the executed instructions and stall samples of one `ncu --set full` capture of cbfnmpc_lane_kernel to
 source lines and functions of csrc/cbfnmpc_lane.h.
 
-  python scripts/dev/source_hotspots.py gpurun_out/prof_<tag>.ncu-rep [srb-cbf-nmpc_b200/lib/libcbfnmpc.so]
+  python scripts/dev/source_hotspots.py gpurun_out/prof_<tag>.ncu-rep [srb-cbf-nmpc_b200/lib/libcbfnmpc.so [kernel [header]]]
 
 The report's SASS page has no line numbers; they come from `nvdisasm -g` of the cubin inside the library, joined by instruction
 offset.  The library must be the build that was profiled (the static instruction counts are compared)."""
@@ -17,8 +17,9 @@ from collections import Counter, defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 rep = sys.argv[1]
-lib = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "srb-cbf-nmpc_b200", "lib", "libcbfnmpc.so")
-KERNEL = "cbfnmpc_lane_kernel"
+lib = os.path.abspath(sys.argv[2]) if len(sys.argv) > 2 else os.path.join(ROOT, "srb-cbf-nmpc_b200", "lib", "libcbfnmpc.so")
+KERNEL = sys.argv[3] if len(sys.argv) > 3 else "cbfnmpc_lane_kernel"
+HEADER = sys.argv[4] if len(sys.argv) > 4 else "cbfnmpc_lane.h"
 
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, check=True, capture_output=True)
@@ -50,12 +51,12 @@ if len(rows) != len(lines):
 
 # function ranges of cbfnmpc_lane.h: a definition starts at a line that begins (column 0 or 2) with LDEV / template / struct
 fn_at = []
-hpath = os.path.join(ROOT, "srb-cbf-nmpc_b200", "csrc", "cbfnmpc_lane.h")
+hpath = os.path.join(ROOT, "srb-cbf-nmpc_b200", "csrc", HEADER)
 for n, l in enumerate(open(hpath), 1):
-    m = re.match(r"\s{0,2}(?:template\s*<[^>]*>\s*)?(?:LDEV|LMEM)\s+[\w:<>\s\*&]*?(\w+)\s*\(", l)
+    m = re.match(r"\s{0,2}(?:template\s*<[^>]*>\s*)?(?:LDEV|LMEM|__device__(?:\s+__forceinline__)?)\s+[\w:<>\s\*&]*?(\w+)\s*\(", l)
     if m: fn_at.append((n, m.group(1)))
 def fn_of(f, n):
-    if f != "cbfnmpc_lane.h": return f
+    if f != HEADER: return f
     name = "(top)"
     for a, b in fn_at:
         if a <= n: name = b
@@ -77,7 +78,7 @@ for fn, s in sm_fn.most_common(25):
 src_lines = open(hpath).read().splitlines()
 print("\n| line | samples share | executed share | source |\n|---|---|---|---|")
 for (f, n), s in sm_line.most_common(40):
-    text = src_lines[n - 1].strip()[:110] if f == "cbfnmpc_lane.h" and n <= len(src_lines) else ""
+    text = src_lines[n - 1].strip()[:110] if f == HEADER and n <= len(src_lines) else ""
     print("| %s:%d | %.2f %% | %.2f %% | `%s` |" % (f, n, 100 * s / ts, 100 * ex_line[(f, n)] / te, text))
 
 # inclusive view: every function on the inline chain of an instruction gets its samples; and the call sites inside the two
@@ -89,7 +90,7 @@ for ch, r in zip(chains, rows):
     for f, n in ch:
         fn = fn_of(f, n)
         if fn not in seen: inc_fn[fn] += s; seen.add(fn)
-        if fn in ("qp_iter", "nlp_iter", "nlp_init", "qp_init", "lane_run_group") and f == "cbfnmpc_lane.h": site[(fn, n)] += s; site_ex[(fn, n)] += e
+        if fn in ("qp_iter", "nlp_iter", "nlp_init", "qp_init", "lane_run_group", "qdense_solve_warp", "qd_factor", "qd_solve") and f == HEADER: site[(fn, n)] += s; site_ex[(fn, n)] += e
 print("\n| function (inclusive) | samples share |\n|---|---|")
 for fn, s in inc_fn.most_common(30): print("| %s | %.1f %% |" % (fn, 100 * s / ts))
 print("\n| call site in the iteration bodies (inclusive) | samples share | executed share | source |\n|---|---|---|---|")

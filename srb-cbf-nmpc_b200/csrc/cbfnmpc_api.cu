@@ -248,14 +248,14 @@ __global__ void __launch_bounds__(128) cbfnmpc_refgen_kernel(int n_teams, const 
   }
 }
 
-// Dense batched QP (cbfnmpc_qpdense.h): one warp per problem, 3 problems per CTA (58 KB of shared memory each).
-#define QD_WARPS 3
+// Dense batched QP (cbfnmpc_qpdense.h): one warp per problem, 4 problems per CTA (56.6 KB of shared memory each).
+#define QD_WARPS 4
 __global__ void __launch_bounds__(32 * QD_WARPS, 1) cbfnmpc_qpdense_kernel(const __grid_constant__ QDenseIO io) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   QDenseWS* ws = reinterpret_cast<QDenseWS*>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int q = blockIdx.x * QD_WARPS + warp;
-  if (q < io.B) qdense_solve_warp(ws[warp], io, q);
+  qdense_solve_warp(ws[warp], io, q < io.B ? q : 0, q < io.B);
 }
 
 // FP64 pipe microbenchmark: 8 independent DFMA chains per thread.

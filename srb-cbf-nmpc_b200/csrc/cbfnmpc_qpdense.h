@@ -18,8 +18,9 @@
 #define QD_NMAX 32
 #define QD_PMAX 24
 #define QD_MMAX 64
-#define QD_LDN 33   // leading dimensions of the row-major n x n / p x p matrices: odd, so that "lane i reads row i" is conflict-free
-#define QD_LDP 25
+#define QD_LDN 33   // leading dimensions of the row-major matrices: odd, so that "lane i reads row i" is conflict-free (and
+#define QD_LDP 25   // "lane j reads column j" and broadcast reads are conflict-free anyway)
+#define QD_LDG 33   // G (m x n) and A (p x n); columns n .. 31 are zero-filled so that the register loops can run to 32
 
 struct QDenseIO {
   int B, n, p, m;
@@ -35,15 +36,15 @@ struct QDenseIO {
 
 struct QDenseWS {                       // one warp
   double P[QD_NMAX * QD_LDN], K[QD_NMAX * QD_LDN];         // row-major n x n (K: lower triangle = Cholesky factor)
-  double G[QD_MMAX * QD_NMAX];                             // row-major m x n
-  double A[QD_PMAX * QD_NMAX];                             // row-major p x n
+  double G[QD_MMAX * QD_LDG];                              // row-major m x n
+  double A[QD_PMAX * QD_LDG];                              // row-major p x n
   double V[QD_NMAX * QD_PMAX];                             // L^-1 A'  (n x p, row-major)
   double S[QD_PMAX * QD_LDP];                              // chol(V'V)
   double c[QD_NMAX], b[QD_PMAX], h[QD_MMAX];
   double x[QD_NMAX], y[QD_PMAX], z[QD_MMAX], s[QD_MMAX];
   double rx[QD_NMAX], ry[QD_PMAX], rz[QD_MMAX];
-  double dx[QD_NMAX], dy[QD_PMAX], dz[QD_MMAX], ds[QD_MMAX], dsl[QD_MMAX], r3[QD_MMAX], w[QD_MMAX], iw[QD_MMAX], lam2[QD_MMAX];
-  double t1[QD_NMAX], t2[QD_PMAX];
+  double dx[QD_NMAX], dy[QD_PMAX], dz[QD_MMAX], ds[QD_MMAX], dsl[QD_MMAX], w[QD_MMAX], iw[QD_MMAX];
+  double idK[QD_NMAX], idS[QD_PMAX];                       // 1 / diagonal of the two Cholesky factors
   double rho;
 };
 
@@ -64,128 +65,142 @@ __device__ __forceinline__ double qd_wmin(double v) {
   return v;
 }
 
-// in-place Cholesky of the lower triangle of M (row-major, leading dimension ld), dimension n <= 32: lane i owns row i
-__device__ bool qd_chol(double* M, int n, int ld, int lane) {
+// Cholesky of a symmetric matrix whose row i sits in lane i's registers (row[0 .. NM), entries beyond the dimension n and the
+// strict upper triangle are ignored).  Left-looking: column k needs row k of the factor, which lane k publishes entry by entry
+// in shared memory (M, leading dimension ld) as it is produced, so that everybody reads it by broadcast.  On return M holds
+// the factor (lower triangle), idg the reciprocals of its diagonal, row[] the lane's row of the factor.
+template <int NM>
+__device__ __forceinline__ bool qd_chol_reg(double (&row)[NM], double* M, double* idg, int n, int ld, int lane) {
   bool ok = true;
-  for (int k = 0; k < n; k++) {
-    double v = 0.0;
-    if (lane >= k && lane < n) {
-      v = M[lane * ld + k];
-      _Pragma("unroll 4")
-      for (int j = 0; j < k; j++) v -= M[lane * ld + j] * M[k * ld + j];
+#pragma unroll
+  for (int k = 0; k < NM; k++) {
+    if (k < n) {
+      double v = row[k];
+#pragma unroll
+      for (int j = 0; j < k; j++) v -= row[j] * M[k * ld + j];
+      const double dk = __shfl_sync(QDW, v, k);
+      if (!(dk > 0.0) || !(dk < 1e300)) ok = false;
+      const double ik = rsqrt(dk);
+      const double l = (lane == k) ? dk * ik : v * ik;
+      row[k] = l;
+      if (lane >= k && lane < n) M[lane * ld + k] = l;
+      if (lane == k) idg[k] = ik;
+      __syncwarp();
     }
-    const double dk = __shfl_sync(QDW, v, k);
-    if (!(dk > 0.0) || !(dk < 1e300)) ok = false;
-    const double ik = rsqrt(dk);
-    if (lane >= k && lane < n) M[lane * ld + k] = (lane == k) ? dk * ik : v * ik;
-    __syncwarp();
   }
   return ok;
 }
 // v <- L^-1 v / v <- L^-T v for one vector, entry i in lane i's register (shuffles carry the pivots; no barriers)
-__device__ __forceinline__ double qd_fwd(const double* L, int n, int ld, double v, int lane) {
+__device__ __forceinline__ double qd_fwd(const double* L, const double* idg, int n, int ld, double v, int lane) {
   for (int k = 0; k < n; k++) {
-    const double vk = __shfl_sync(QDW, v, k) / L[k * ld + k];
+    const double vk = __shfl_sync(QDW, v, k) * idg[k];
     if (lane == k) v = vk;
     else if (lane > k && lane < n) v -= L[lane * ld + k] * vk;
   }
   return v;
 }
-__device__ __forceinline__ double qd_bwd(const double* L, int n, int ld, double v, int lane) {
+__device__ __forceinline__ double qd_bwd(const double* L, const double* idg, int n, int ld, double v, int lane) {
   for (int k = n - 1; k >= 0; k--) {
-    const double vk = __shfl_sync(QDW, v, k) / L[k * ld + k];
+    const double vk = __shfl_sync(QDW, v, k) * idg[k];
     if (lane == k) v = vk;
     else if (lane < k) v -= L[k * ld + lane] * vk;
   }
   return v;
 }
 
-// factor [P + G'W^-1 G, A'; A, 0] for the weights w (s/z)
+// factor [P + G'W^-1 G, A'; A, 0] for the weights w (s/z).  Lane i accumulates row i of K = P + G' W^-1 G + rho A'A in
+// registers as a sum of outer products (the rows of G and A are read by broadcast), factorises it there (qd_chol_reg), then
+// lane q substitutes column q of V = L^-1 A' in registers, accumulates row q of V'V the same way and factorises that.
 __device__ bool qd_factor(QDenseWS& ws, int n, int p, int m, int lane) {
   for (int r = lane; r < m; r += 32) ws.iw[r] = 1.0 / ws.w[r];
   __syncwarp();
-  double kd = 0.0, ad = 0.0;   // diagonal of P + G'W^-1 G and of A'A (lane i: entry i)
-  if (lane < n) {
-    for (int j = 0; j <= lane; j++) {
-      double v = ws.P[lane * QD_LDN + j];
-      _Pragma("unroll 4")
-      for (int r = 0; r < m; r++) v += (ws.G[r * QD_NMAX + lane] * ws.iw[r]) * ws.G[r * QD_NMAX + j];
-      ws.K[lane * QD_LDN + j] = v;
-      if (j == lane) kd = v;
-    }
-    for (int q = 0; q < p; q++) ad += ws.A[q * QD_NMAX + lane] * ws.A[q * QD_NMAX + lane];
+  double kr[QD_NMAX];
+#pragma unroll
+  for (int j = 0; j < QD_NMAX; j++) kr[j] = ws.P[lane * QD_LDN + j];   // rows / columns n .. 31 of P are zero-filled at load
+  double kd = ws.P[lane * QD_LDN + lane], ad = 0.0;                      // diagonal entries of P + G'W^-1 G and of A'A
+#pragma unroll 1
+  for (int r = 0; r < m; r++) {
+    const double gl = ws.G[r * QD_LDG + lane], gi = gl * ws.iw[r];
+    kd += gi * gl;
+#pragma unroll
+    for (int j = 0; j < QD_NMAX; j++) kr[j] += gi * ws.G[r * QD_LDG + j];
   }
+  for (int q = 0; q < p; q++) { const double al = ws.A[q * QD_LDG + lane]; ad += al * al; }
   const double skd = qd_wsum(kd), sad = qd_wsum(ad);
   const double rho = (p > 0 && sad > 0.0) ? skd / sad : 0.0;
   if (lane == 0) ws.rho = rho;
-  if (lane < n && p > 0) {
-    for (int j = 0; j <= lane; j++) {
-      double v = 0.0;
-      _Pragma("unroll 4")
-      for (int q = 0; q < p; q++) v += ws.A[q * QD_NMAX + lane] * ws.A[q * QD_NMAX + j];
-      ws.K[lane * QD_LDN + j] += rho * v;
-    }
+#pragma unroll 1
+  for (int q = 0; q < p; q++) {
+    const double ai = rho * ws.A[q * QD_LDG + lane];
+#pragma unroll
+    for (int j = 0; j < QD_NMAX; j++) kr[j] += ai * ws.A[q * QD_LDG + j];
   }
   __syncwarp();
-  bool ok = qd_chol(ws.K, n, QD_LDN, lane);
+  bool ok = qd_chol_reg<QD_NMAX>(kr, ws.K, ws.idK, n, QD_LDN, lane);
   if (p > 0) {
-    // V = L^-1 A': lane q substitutes column q (= row q of A) on its own, no exchange needed
-    if (lane < p) {
-      for (int k = 0; k < n; k++) {
-        double v = ws.A[lane * QD_NMAX + k];
-        _Pragma("unroll 4")
-        for (int j = 0; j < k; j++) v -= ws.K[k * QD_LDN + j] * ws.V[j * QD_PMAX + lane];
-        ws.V[k * QD_PMAX + lane] = v / ws.K[k * QD_LDN + k];
+    // V = L^-1 A': lane q substitutes column q (= row q of A) in registers; rows of L by broadcast
+    double vq[QD_NMAX];
+#pragma unroll
+    for (int k = 0; k < QD_NMAX; k++) {
+      vq[k] = 0.0;
+      if (k < n) {
+        double v = (lane < p) ? ws.A[lane * QD_LDG + k] : 0.0;
+#pragma unroll
+        for (int j = 0; j < k; j++) v -= ws.K[k * QD_LDN + j] * vq[j];
+        vq[k] = v * ws.idK[k];
+        if (lane < p) ws.V[k * QD_PMAX + lane] = vq[k];
       }
     }
     __syncwarp();
-    if (lane < p) {
-      for (int j = 0; j <= lane; j++) {
-        double v = 0.0;
-        _Pragma("unroll 4")
-        for (int i = 0; i < n; i++) v += ws.V[i * QD_PMAX + lane] * ws.V[i * QD_PMAX + j];
-        ws.S[lane * QD_LDP + j] = v;
+    double sr[QD_PMAX];
+#pragma unroll
+    for (int j = 0; j < QD_PMAX; j++) sr[j] = 0.0;
+#pragma unroll
+    for (int i = 0; i < QD_NMAX; i++) {
+      if (i < n) {
+#pragma unroll
+        for (int j = 0; j < QD_PMAX; j++) sr[j] += vq[i] * ws.V[i * QD_PMAX + j];   // columns p .. 23 of V are zero-filled at load
       }
     }
-    __syncwarp();
-    ok = qd_chol(ws.S, p, QD_LDP, lane) && ok;
+    ok = qd_chol_reg<QD_PMAX>(sr, ws.S, ws.idS, p, QD_LDP, lane) && ok;
   }
   return ok;
 }
 
-// solve [P A' G'; A 0 0; G 0 -W][dx; dy; dz] = [r1; r2; r3] with the stored factor
+// solve [P A' G'; A 0 0; G 0 -W][dx; dy; dz] = [r1; r2; r3] with the stored factor.  r3 may be the array dz (entry r is read
+// before it is written, by the same lane); dx and dy double as scratch for L^-1 r and for the multiplier step.
 __device__ void qd_solve(QDenseWS& ws, int n, int p, int m, const double* r1, const double* r2, const double* r3, double* dx, double* dy,
                          double* dz, int lane) {
   double t = 0.0;
   if (lane < n) {
     t = r1[lane];
     _Pragma("unroll 4")
-    for (int r = 0; r < m; r++) t += ws.G[r * QD_NMAX + lane] * (r3[r] * ws.iw[r]);
-    for (int q = 0; q < p; q++) t += ws.rho * ws.A[q * QD_NMAX + lane] * r2[q];
+    for (int r = 0; r < m; r++) t += ws.G[r * QD_LDG + lane] * (r3[r] * ws.iw[r]);
+    for (int q = 0; q < p; q++) t += ws.rho * ws.A[q * QD_LDG + lane] * r2[q];
   }
-  t = qd_fwd(ws.K, n, QD_LDN, t, lane);                  // t = L^-1 r
+  t = qd_fwd(ws.K, ws.idK, n, QD_LDN, t, lane);                  // t = L^-1 r
   if (p > 0) {
-    if (lane < n) ws.t1[lane] = t;
+    if (lane < n) dx[lane] = t;
     __syncwarp();
     double u = 0.0;
     if (lane < p) {
       u = -r2[lane];
       _Pragma("unroll 4")
-      for (int i = 0; i < n; i++) u += ws.V[i * QD_PMAX + lane] * ws.t1[i];   // V't - r2
+      for (int i = 0; i < n; i++) u += ws.V[i * QD_PMAX + lane] * dx[i];   // V't - r2
     }
-    u = qd_fwd(ws.S, p, QD_LDP, u, lane);
-    u = qd_bwd(ws.S, p, QD_LDP, u, lane);                // dy
-    if (lane < p) { dy[lane] = u; ws.t2[lane] = u; }
+    u = qd_fwd(ws.S, ws.idS, p, QD_LDP, u, lane);
+    u = qd_bwd(ws.S, ws.idS, p, QD_LDP, u, lane);                // dy
+    if (lane < p) dy[lane] = u;
     __syncwarp();
-    if (lane < n) for (int q = 0; q < p; q++) t -= ws.V[lane * QD_PMAX + q] * ws.t2[q];
+    if (lane < n) for (int q = 0; q < p; q++) t -= ws.V[lane * QD_PMAX + q] * dy[q];
   }
-  t = qd_bwd(ws.K, n, QD_LDN, t, lane);                  // dx
+  t = qd_bwd(ws.K, ws.idK, n, QD_LDN, t, lane);                  // dx
   if (lane < n) dx[lane] = t;
   __syncwarp();
   for (int r = lane; r < m; r += 32) {
     double v = -r3[r];
     _Pragma("unroll 4")
-    for (int j = 0; j < n; j++) v += ws.G[r * QD_NMAX + j] * dx[j];
+    for (int j = 0; j < n; j++) v += ws.G[r * QD_LDG + j] * dx[j];
     dz[r] = v * ws.iw[r];
   }
   __syncwarp();
@@ -199,106 +214,124 @@ __device__ void qd_steplength(const QDenseWS& ws, const double* dsv, const doubl
   ap = (rp > 0.0) ? 1.0 / rp : 1.0; ad = (rd > 0.0) ? 1.0 / rd : 1.0;
 }
 
-__device__ void qdense_solve_warp(QDenseWS& ws, const QDenseIO& io, int q) {
+// valid == false: a warp without a problem (tail of the batch); it only takes part in the CTA-wide votes
+__device__ void qdense_solve_warp(QDenseWS& ws, const QDenseIO& io, int q, bool valid) {
   const int lane = threadIdx.x & 31, n = io.n, p = io.p, m = io.m;
-  // ---- load (column-major global -> row-major shared)
-  const double* Pg = io.P + (size_t)q * n * n; const double* Ag = io.A + (size_t)q * p * n; const double* Gg = io.G + (size_t)q * m * n;
-  for (int t = lane; t < n * n; t += 32) { const int i = t % n, j = t / n; ws.P[i * QD_LDN + j] = Pg[t]; }
-  for (int t = lane; t < p * n; t += 32) { const int i = t % p, j = t / p; ws.A[i * QD_NMAX + j] = Ag[t]; }
-  for (int t = lane; t < m * n; t += 32) { const int i = t % m, j = t / m; ws.G[i * QD_NMAX + j] = Gg[t]; }
-  for (int t = lane; t < n; t += 32) ws.c[t] = io.c[(size_t)q * n + t];
-  for (int t = lane; t < p; t += 32) ws.b[t] = io.b[(size_t)q * p + t];
-  for (int t = lane; t < m; t += 32) ws.h[t] = io.h[(size_t)q * m + t];
-  __syncwarp();
   int flag = 3, it = 0;
-  // ---- kkt_initialize: W = I, rhs [-c; b; h]
-  for (int r = lane; r < m; r += 32) ws.w[r] = 1.0;
-  if (lane < n) ws.rx[lane] = -ws.c[lane];
-  __syncwarp();
-  bool ok = qd_factor(ws, n, p, m, lane);
-  if (!ok) flag = 1;
-  else {
-    qd_solve(ws, n, p, m, ws.rx, ws.b, ws.h, ws.x, ws.y, ws.dz, lane);
-    double rmin = 1e300, rmax = -1e300;
-    for (int r = lane; r < m; r += 32) {
-      double t = ws.h[r];
-      for (int j = 0; j < n; j++) t -= ws.G[r * QD_NMAX + j] * ws.x[j];
-      ws.rz[r] = t; rmin = fmin(rmin, t); rmax = fmax(rmax, t);
-    }
-    rmin = qd_wmin(rmin); rmax = qd_wmax(rmax);
-    const double ap0 = -rmin, ad0 = rmax;
-    for (int r = lane; r < m; r += 32) {
-      ws.s[r] = (ap0 < 0) ? ws.rz[r] : ws.rz[r] + (1 + ap0);
-      ws.z[r] = (ad0 < 0) ? -ws.rz[r] : -ws.rz[r] + (1 + ad0);
-    }
+  bool run = false;
+  if (valid) {
+    // ---- load (column-major global -> row-major shared, zero-filled up to the register-loop bounds)
+    const double* Pg = io.P + (size_t)q * n * n; const double* Ag = io.A + (size_t)q * p * n; const double* Gg = io.G + (size_t)q * m * n;
+    for (int t = lane; t < QD_NMAX * QD_LDN; t += 32) ws.P[t] = 0.0;
+    for (int t = lane; t < QD_MMAX * QD_LDG; t += 32) ws.G[t] = 0.0;
+    for (int t = lane; t < QD_PMAX * QD_LDG; t += 32) ws.A[t] = 0.0;
+    for (int t = lane; t < QD_NMAX * QD_PMAX; t += 32) ws.V[t] = 0.0;
     __syncwarp();
-    double sigma = 100.0;  // GlobalOptions.h:26
-    flag = 2;
-    for (it = 0; it < io.maxit; it++) {
-      // ---- residuals (computeresiduals, Auxilary.c:524-553)
-      double nrx = 0.0, nry = 0.0, nrz = 0.0, sz = 0.0;
-      if (lane < n) {
-        double t = ws.c[lane];
-        _Pragma("unroll 4")
-        for (int i = 0; i < n; i++) t += ws.P[lane * QD_LDN + i] * ws.x[i];
-        _Pragma("unroll 4")
-        for (int r = 0; r < m; r++) t += ws.G[r * QD_NMAX + lane] * ws.z[r];
-        for (int i = 0; i < p; i++) t += ws.A[i * QD_NMAX + lane] * ws.y[i];
-        ws.rx[lane] = -t; nrx = t * t;
-      }
-      if (lane < p) {
-        double t = ws.b[lane];
-        for (int j = 0; j < n; j++) t -= ws.A[lane * QD_NMAX + j] * ws.x[j];
-        ws.ry[lane] = t; nry = t * t;
-      }
+    for (int t = lane; t < n * n; t += 32) { const int i = t % n, j = t / n; ws.P[i * QD_LDN + j] = Pg[t]; }
+    for (int t = lane; t < p * n; t += 32) { const int i = t % p, j = t / p; ws.A[i * QD_LDG + j] = Ag[t]; }
+    for (int t = lane; t < m * n; t += 32) { const int i = t % m, j = t / m; ws.G[i * QD_LDG + j] = Gg[t]; }
+    for (int t = lane; t < n; t += 32) ws.c[t] = io.c[(size_t)q * n + t];
+    for (int t = lane; t < p; t += 32) ws.b[t] = io.b[(size_t)q * p + t];
+    for (int t = lane; t < m; t += 32) ws.h[t] = io.h[(size_t)q * m + t];
+    __syncwarp();
+    // ---- kkt_initialize: W = I, rhs [-c; b; h]
+    for (int r = lane; r < m; r += 32) ws.w[r] = 1.0;
+    if (lane < n) ws.rx[lane] = -ws.c[lane];
+    __syncwarp();
+    if (!qd_factor(ws, n, p, m, lane)) flag = 1;
+    else {
+      qd_solve(ws, n, p, m, ws.rx, ws.b, ws.h, ws.x, ws.y, ws.dz, lane);
+      double rmin = 1e300, rmax = -1e300;
       for (int r = lane; r < m; r += 32) {
-        double t = ws.h[r] - ws.s[r];
-        _Pragma("unroll 4")
-        for (int j = 0; j < n; j++) t -= ws.G[r * QD_NMAX + j] * ws.x[j];
-        ws.rz[r] = t; nrz += t * t; sz += ws.s[r] * ws.z[r];
+        double t = ws.h[r];
+        for (int j = 0; j < n; j++) t -= ws.G[r * QD_LDG + j] * ws.x[j];
+        ws.rz[r] = t; rmin = fmin(rmin, t); rmax = fmax(rmax, t);
       }
-      nrx = sqrt(qd_wsum(nrx)); nry = sqrt(qd_wsum(nry)); nrz = sqrt(qd_wsum(nrz)); sz = qd_wsum(sz);
-      const double lim = io.reltol / sqrt(3.0);
-      if (nrx < lim && nrz < lim && (p == 0 || nry < lim) && sz / m < io.abstol) { flag = 0; break; }
-      double mu = 0.0;
-      for (int r = lane; r < m; r += 32) { const double l = sqrt(ws.s[r] * ws.z[r]); ws.lam2[r] = l * l; mu += ws.lam2[r]; }
-      mu = qd_wsum(mu) / m;
-      __syncwarp();
-      if (sigma > 0.0) {
-        for (int r = lane; r < m; r += 32) { ws.w[r] = ws.s[r] / ws.z[r]; ws.ds[r] = -ws.lam2[r]; ws.r3[r] = ws.rz[r] - ws.ds[r] / ws.z[r]; }
-        __syncwarp();
-        if (!qd_factor(ws, n, p, m, lane)) { flag = 1; break; }
-        qd_solve(ws, n, p, m, ws.rx, ws.ry, ws.r3, ws.dx, ws.dy, ws.dz, lane);
-        for (int r = lane; r < m; r += 32) ws.dsl[r] = (ws.ds[r] - ws.s[r] * ws.dz[r]) / ws.z[r];
-        __syncwarp();
-        double ap, ad;
-        qd_steplength(ws, ws.dsl, ws.dz, m, lane, ap, ad);
-        double num = 0.0;
-        for (int r = lane; r < m; r += 32) num += (ws.s[r] + ap * ws.dsl[r]) * (ws.z[r] + ad * ws.dz[r]);
-        num = qd_wsum(num);
-        const double rho = num / sz, mr = rho < 1.0 ? rho : 1.0;
-        sigma = mr * mr * mr;
-        if (sigma < 0.0) sigma = 0.0;
-        for (int r = lane; r < m; r += 32) ws.ds[r] = -ws.lam2[r] - ws.dsl[r] * ws.dz[r] + sigma * mu;
-      } else {
-        sigma = 0.0;
-        for (int r = lane; r < m; r += 32) ws.ds[r] = -ws.lam2[r] + sigma * mu;
+      rmin = qd_wmin(rmin); rmax = qd_wmax(rmax);
+      const double ap0 = -rmin, ad0 = rmax;
+      for (int r = lane; r < m; r += 32) {
+        ws.s[r] = (ap0 < 0) ? ws.rz[r] : ws.rz[r] + (1 + ap0);
+        ws.z[r] = (ad0 < 0) ? -ws.rz[r] : -ws.rz[r] + (1 + ad0);
       }
       __syncwarp();
-      for (int r = lane; r < m; r += 32) ws.r3[r] = ws.rz[r] - ws.ds[r] / ws.z[r];
+      flag = 2; run = true;
+    }
+  }
+  double sigma = 100.0;  // GlobalOptions.h:26
+  // The warps of a CTA start every iteration together, so that they fetch the same instruction-cache lines (the unrolled
+  // register loops of qd_factor are 0.4 MB of code).
+  for (;;) {
+    const bool act = run && it < io.maxit;
+    if (!__syncthreads_or(act ? 1 : 0)) break;
+    if (!act) continue;
+    // ---- residuals (computeresiduals, Auxilary.c:524-553)
+    double nrx = 0.0, nry = 0.0, nrz = 0.0, sz = 0.0;
+    if (lane < n) {
+      double t = ws.c[lane];
+      _Pragma("unroll 4")
+      for (int i = 0; i < n; i++) t += ws.P[lane * QD_LDN + i] * ws.x[i];
+      _Pragma("unroll 4")
+      for (int r = 0; r < m; r++) t += ws.G[r * QD_LDG + lane] * ws.z[r];
+      for (int i = 0; i < p; i++) t += ws.A[i * QD_LDG + lane] * ws.y[i];
+      ws.rx[lane] = -t; nrx = t * t;
+    }
+    if (lane < p) {
+      double t = ws.b[lane];
+      for (int j = 0; j < n; j++) t -= ws.A[lane * QD_LDG + j] * ws.x[j];
+      ws.ry[lane] = t; nry = t * t;
+    }
+    for (int r = lane; r < m; r += 32) {
+      double t = ws.h[r] - ws.s[r];
+      _Pragma("unroll 4")
+      for (int j = 0; j < n; j++) t -= ws.G[r * QD_LDG + j] * ws.x[j];
+      ws.rz[r] = t; nrz += t * t; sz += ws.s[r] * ws.z[r];
+    }
+    nrx = sqrt(qd_wsum(nrx)); nry = sqrt(qd_wsum(nry)); nrz = sqrt(qd_wsum(nrz)); sz = qd_wsum(sz);
+    const double lim = io.reltol / sqrt(3.0);
+    if (nrx < lim && nrz < lim && (p == 0 || nry < lim) && sz / m < io.abstol) { flag = 0; run = false; continue; }
+    // lambda^2 = (sqrt(s z))^2 as iSWIFT forms it; entry r belongs to lane r % 32 throughout
+    double mu = 0.0;
+    for (int r = lane; r < m; r += 32) { const double l = sqrt(ws.s[r] * ws.z[r]); mu += l * l; }
+    mu = qd_wsum(mu) / m;
+    if (sigma > 0.0) {
+      for (int r = lane; r < m; r += 32) {
+        const double l = sqrt(ws.s[r] * ws.z[r]);
+        ws.w[r] = ws.s[r] / ws.z[r]; ws.ds[r] = -(l * l); ws.dz[r] = ws.rz[r] - ws.ds[r] / ws.z[r];
+      }
       __syncwarp();
-      qd_solve(ws, n, p, m, ws.rx, ws.ry, ws.r3, ws.dx, ws.dy, ws.dz, lane);
+      if (!qd_factor(ws, n, p, m, lane)) { flag = 1; run = false; continue; }
+      qd_solve(ws, n, p, m, ws.rx, ws.ry, ws.dz, ws.dx, ws.dy, ws.dz, lane);
       for (int r = lane; r < m; r += 32) ws.dsl[r] = (ws.ds[r] - ws.s[r] * ws.dz[r]) / ws.z[r];
       __syncwarp();
       double ap, ad;
       qd_steplength(ws, ws.dsl, ws.dz, m, lane, ap, ad);
-      ap = fmin(0.99 * ap, 1.0); ad = fmin(0.99 * ad, 1.0);
-      if (lane < n) ws.x[lane] += ap * ws.dx[lane];
-      if (lane < p) ws.y[lane] += ad * ws.dy[lane];
-      for (int r = lane; r < m; r += 32) { ws.s[r] += ap * ws.dsl[r]; ws.z[r] += ad * ws.dz[r]; }
-      __syncwarp();
+      double num = 0.0;
+      for (int r = lane; r < m; r += 32) num += (ws.s[r] + ap * ws.dsl[r]) * (ws.z[r] + ad * ws.dz[r]);
+      num = qd_wsum(num);
+      const double rho = num / sz, mr = rho < 1.0 ? rho : 1.0;
+      sigma = mr * mr * mr;
+      if (sigma < 0.0) sigma = 0.0;
+      for (int r = lane; r < m; r += 32) { const double l = sqrt(ws.s[r] * ws.z[r]); ws.ds[r] = -(l * l) - ws.dsl[r] * ws.dz[r] + sigma * mu; }
+    } else {
+      sigma = 0.0;
+      for (int r = lane; r < m; r += 32) { const double l = sqrt(ws.s[r] * ws.z[r]); ws.ds[r] = -(l * l) + sigma * mu; }
     }
+    __syncwarp();
+    for (int r = lane; r < m; r += 32) ws.dz[r] = ws.rz[r] - ws.ds[r] / ws.z[r];
+    __syncwarp();
+    qd_solve(ws, n, p, m, ws.rx, ws.ry, ws.dz, ws.dx, ws.dy, ws.dz, lane);
+    for (int r = lane; r < m; r += 32) ws.dsl[r] = (ws.ds[r] - ws.s[r] * ws.dz[r]) / ws.z[r];
+    __syncwarp();
+    double ap, ad;
+    qd_steplength(ws, ws.dsl, ws.dz, m, lane, ap, ad);
+    ap = fmin(0.99 * ap, 1.0); ad = fmin(0.99 * ad, 1.0);
+    if (lane < n) ws.x[lane] += ap * ws.dx[lane];
+    if (lane < p) ws.y[lane] += ad * ws.dy[lane];
+    for (int r = lane; r < m; r += 32) { ws.s[r] += ap * ws.dsl[r]; ws.z[r] += ad * ws.dz[r]; }
+    __syncwarp();
+    it++;
   }
+  if (!valid) return;
   // ---- store
   for (int t = lane; t < n; t += 32) io.x[(size_t)q * n + t] = ws.x[t];
   if (io.y) for (int t = lane; t < p; t += 32) io.y[(size_t)q * p + t] = ws.y[t];
