@@ -111,7 +111,7 @@ __device__ __forceinline__ double qd_bwd(const double* L, const double* idg, int
 // factor [P + G'W^-1 G, A'; A, 0] for the weights w (s/z).  Lane i accumulates row i of K = P + G' W^-1 G + rho A'A in
 // registers as a sum of outer products (the rows of G and A are read by broadcast), factorises it there (qd_chol_reg), then
 // lane q substitutes column q of V = L^-1 A' in registers, accumulates row q of V'V the same way and factorises that.
-__device__ bool qd_factor(QDenseWS& ws, int n, int p, int m, int lane) {
+__device__ __noinline__ bool qd_factor(QDenseWS& ws, int n, int p, int m, int lane) {  // one copy: 70 KB of unrolled code
   for (int r = lane; r < m; r += 32) ws.iw[r] = 1.0 / ws.w[r];
   __syncwarp();
   double kr[QD_NMAX];
@@ -169,7 +169,7 @@ __device__ bool qd_factor(QDenseWS& ws, int n, int p, int m, int lane) {
 
 // solve [P A' G'; A 0 0; G 0 -W][dx; dy; dz] = [r1; r2; r3] with the stored factor.  r3 may be the array dz (entry r is read
 // before it is written, by the same lane); dx and dy double as scratch for L^-1 r and for the multiplier step.
-__device__ void qd_solve(QDenseWS& ws, int n, int p, int m, const double* r1, const double* r2, const double* r3, double* dx, double* dy,
+__device__ __noinline__ void qd_solve(QDenseWS& ws, int n, int p, int m, const double* r1, const double* r2, const double* r3, double* dx, double* dy,
                          double* dz, int lane) {
   double t = 0.0;
   if (lane < n) {
