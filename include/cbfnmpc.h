@@ -140,6 +140,11 @@ int cbfnmpc_solve_dense_nlptuple(cbfnmpc_ctx *ctx, int nv, int p, int mi, const 
  *   agent_initial[2][B]    agent_Initial_ (set by setPstart)                                                        :1106-1112
  *   Pr_refined, Prd_refined  [n_teams] matrices 8 x ref_cols, column-major (Eigen::Matrix<double,8,2500>)            MPC_dist.hpp, :930-1104
  *   Pobs_real    [n_teams] matrices 2 x n_obs, column-major                                                         :1124, :371-396
+ *   state_other  [4*n_other][B]  optional (NULL / 0 = the reference as shipped).  The reference carries the other agent's
+ *                (x, y, vx, vy) into run_NMPC (updateState, :1200; nlpTuple) and its disabled rule (:391) makes that agent's
+ *                position extrapolated over the horizon, (x + vx*4*Ts, y + vy*4*Ts), THE obstacle of the distance rows.  With
+ *                n_other > 0 the extrapolated positions of the n_other neighbours (rows 4k .. 4k+3 = neighbour k) compete with
+ *                the real obstacles in the closest-obstacle rule: they are appended as obstacle columns n_obs .. n_obs+n_other-1.
  * The reference reads columns [4*gait_domain, 4*gait_domain+4) of the trajectory without a bound check; here a column
  * index past ref_cols-1 is clamped to the last column. */
 typedef struct {
@@ -153,12 +158,21 @@ typedef struct {
   int ref_cols, n_teams;
   const double *Pobs_real;
   int n_obs;
+  const double *state_other;
+  int n_other;
 } cbfnmpc_raw_in;
 
 /* fills packed->x0, xdes, feet_xy, contact, obs_xy (device arrays of the sizes cbfnmpc_in documents; packed->n_obs is ignored,
- * raw->n_obs columns are written); asynchronous on `cuda_stream` */
+ * raw->n_obs + raw->n_other columns are written); asynchronous on `cuda_stream` */
 int cbfnmpc_pack_inputs(cbfnmpc_ctx *ctx, int B, const cbfnmpc_raw_in *raw, const cbfnmpc_in *packed, void *cuda_stream);
-/* pack into the context's own staging buffers (B <= max_batch, raw->n_obs <= max_obs), then solve; alpha_buf [4][B] device */
+/* state_other for agents stored team by team (team_size consecutive agents form a team, B a multiple of team_size): neighbour k
+ * of agent a is the k-th OTHER member of its team, rows (q[0], q[1], dq[0], dq[1]) of that member.  state_other
+ * [4*(team_size-1)][B], device.  (Agents of a team spread over several GPUs exchange the same rows with an all-gather, see
+ * srb-cbf-nmpc_b200/sharding.py.) */
+int cbfnmpc_team_states(cbfnmpc_ctx *ctx, int B, int team_size, const double *q, const double *dq, double *state_other,
+                        void *cuda_stream);
+/* pack into the context's own staging buffers (B <= max_batch, raw->n_obs + raw->n_other <= max_obs), then solve; alpha_buf
+ * [4][B] device */
 int cbfnmpc_run_cycle(cbfnmpc_ctx *ctx, int B, int mode, const cbfnmpc_raw_in *raw, const double *alpha_buf,
                       const cbfnmpc_out *out, void *cuda_stream);
 

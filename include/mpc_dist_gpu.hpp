@@ -79,6 +79,10 @@ struct Batch {
 class MPC_dist_gpu {
  public:
   bool use_snopt = false;  // MPC_dist.hpp:139
+  // The reference's disabled inter-agent rule (MPC_dist.cpp:391): the other agent, extrapolated over the horizon
+  // (x + vx*4*Ts, y + vy*4*Ts), competes with the real obstacles for the distance rows.  false = the reference as shipped
+  // (state_other is carried and never read).
+  bool use_state_other = false;
 
   // `ctx` may be shared by several agents that are stepped from the same thread (or by a team, below).
   explicit MPC_dist_gpu(Context* ctx) : ctx_(ctx) {
@@ -109,7 +113,7 @@ class MPC_dist_gpu {
 
   // One control cycle of this agent alone (B = 1).  Returns the per-instance status (CBFNMPC_ST_*).
   int run_NMPC() {
-    Batch b(1, n_obs_);
+    Batch b(1, n_obs());
     pack(b, 0);
     cbfnmpc_in in = b.in(); cbfnmpc_out out = b.out();
     int rc = cbfnmpc_solve_batch_host(ctx_->get(), 1, use_snopt ? CBFNMPC_MODE_QP_NLP : CBFNMPC_MODE_QP, &in, &out);
@@ -132,12 +136,12 @@ class MPC_dist_gpu {
   double slack() const { return slack_; }
 
   // ---- used by MPC_dist_gpu_team
-  int n_obs() const { return n_obs_; }
+  int n_obs() const { return n_obs_ + (use_state_other ? 1 : 0); }  // obstacle columns of this agent's instances
   // copPlanner_eventbase (:702-782) + footholdsPlanner (:1204-1266) + state (:226-229) -> column `b` of a batch
   void pack(Batch& bt, int b) {
     const int B = bt.B, N = 4;
     if (Pr_.empty() || 4 * (gaitDomain_ + 1) > ref_cols_) throw Error(CBFNMPC_ERR_ARG, "reference trajectory missing or exhausted");
-    if ((int)Pobs_real_.size() != 2 * bt.K) throw Error(CBFNMPC_ERR_ARG, "obstacle count differs from the batch");
+    if (n_obs() != bt.K || (int)Pobs_real_.size() != 2 * n_obs_) throw Error(CBFNMPC_ERR_ARG, "obstacle count differs from the batch");
     const size_t rows = 2 * NUMBER_OF_AGENTS;
     for (int k = 0; k < N; k++) {
       const size_t col = (size_t)N * gaitDomain_ + k;
@@ -156,7 +160,12 @@ class MPC_dist_gpu {
       bt.contact[(size_t)i * B + b] = contactInd_[i];
     }
     bt.x0[0 * B + b] = q_[0]; bt.x0[1 * B + b] = dq_[0]; bt.x0[2 * B + b] = q_[1]; bt.x0[3 * B + b] = dq_[1];  // :226-229
-    for (int k = 0; k < bt.K; k++) { bt.obs[(size_t)k * B + b] = Pobs_real_[2 * k]; bt.obs[(size_t)(bt.K + k) * B + b] = Pobs_real_[2 * k + 1]; }
+    for (int k = 0; k < n_obs_; k++) { bt.obs[(size_t)k * B + b] = Pobs_real_[2 * k]; bt.obs[(size_t)(bt.K + k) * B + b] = Pobs_real_[2 * k + 1]; }
+    if (use_state_other) {  // :391
+      const double Ts = 43 * 0.001;  // TSOPTTICK * 0.001
+      bt.obs[(size_t)n_obs_ * B + b] = state_other_[0] + (state_other_[2] * 4.0) * Ts;
+      bt.obs[(size_t)(bt.K + n_obs_) * B + b] = state_other_[1] + (state_other_[3] * 4.0) * Ts;
+    }
     for (int i = 0; i < 4; i++) bt.abuf[(size_t)i * B + b] = alpha_buf_[i];
   }
   void consume(const Batch& bt, int b) {

@@ -37,6 +37,7 @@ def load():
     L.cbfnmpc_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.In), C.POINTER(capi.Out), C.c_void_p]
     L.cbfnmpc_solve_batch_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.In), C.POINTER(capi.Out)]
     L.cbfnmpc_pack_inputs.argtypes = [C.c_void_p, C.c_int, C.POINTER(capi.RawIn), C.POINTER(capi.In), C.c_void_p]
+    L.cbfnmpc_team_states.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cbfnmpc_run_cycle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(capi.RawIn), C.c_void_p, C.POINTER(capi.Out), C.c_void_p]
     L.cbfnmpc_generate_reference.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p]
@@ -54,7 +55,8 @@ def load():
 EXPORTS = ["cbfnmpc_version", "cbfnmpc_last_error", "cbfnmpc_default_gains", "cbfnmpc_default_options", "cbfnmpc_create",
            "cbfnmpc_destroy", "cbfnmpc_set_gains", "cbfnmpc_set_options", "cbfnmpc_solve_batch", "cbfnmpc_solve_batch_host",
            "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak",
-           "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle", "cbfnmpc_closed_loop", "cbfnmpc_generate_reference", "cbfnmpc_qp_dense_batch"]
+           "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle", "cbfnmpc_closed_loop", "cbfnmpc_generate_reference", "cbfnmpc_qp_dense_batch",
+           "cbfnmpc_team_states"]
 
 
 def default_gains():
@@ -122,7 +124,10 @@ class BatchSolver:
     def _raw_struct(raw):
         r = capi.RawIn()
         for k, _ in capi.RawIn._fields_:
-            setattr(r, k, raw[k])
+            if k in ("state_other", "n_other"):          # optional: the reference's disabled inter-agent rule
+                setattr(r, k, raw.get(k) or 0)
+            else:
+                setattr(r, k, raw[k])
         return r
 
     def pack_inputs(self, B, raw, packed_ptrs, stream=None):
@@ -130,9 +135,13 @@ class BatchSolver:
         si = capi.In()
         for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy"):
             setattr(si, k, packed_ptrs[k])
-        si.n_obs = raw["n_obs"]
+        si.n_obs = raw["n_obs"] + (raw.get("n_other", 0) if raw.get("state_other") else 0)
         r = self._raw_struct(raw)
         self._ck(self.L.cbfnmpc_pack_inputs(self.ctx, B, C.byref(r), C.byref(si), stream))
+
+    def team_states(self, B, team_size, q_ptr, dq_ptr, state_other_ptr, stream=None):
+        """state_other [4*(team_size-1)][B] of agents stored team by team (cbfnmpc_team_states)."""
+        self._ck(self.L.cbfnmpc_team_states(self.ctx, B, team_size, q_ptr, dq_ptr, state_other_ptr, stream))
 
     def run_cycle(self, B, raw, alpha_buf_ptr, out_ptrs, mode=capi.MODE_QP_NLP, stream=None):
         """updateState + run_NMPC from the raw inputs: pack kernel, class sort, solve kernel (cbfnmpc_run_cycle)."""

@@ -35,7 +35,7 @@ class RawIn(C.Structure):
     _fields_ = [("q", C.c_void_p), ("dq", C.c_void_p), ("nq", C.c_int), ("contact", C.c_void_p), ("toe_pos", C.c_void_p),
                 ("gait_domain", C.c_void_p), ("agent_id", C.c_void_p), ("team", C.c_void_p), ("agent_initial", C.c_void_p),
                 ("Pr_refined", C.c_void_p), ("Prd_refined", C.c_void_p), ("ref_cols", C.c_int), ("n_teams", C.c_int),
-                ("Pobs_real", C.c_void_p), ("n_obs", C.c_int)]
+                ("Pobs_real", C.c_void_p), ("n_obs", C.c_int), ("state_other", C.c_void_p), ("n_other", C.c_int)]
 
 
 class WorldState(C.Structure):

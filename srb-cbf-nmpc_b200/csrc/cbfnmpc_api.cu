@@ -91,6 +91,7 @@ struct PackIO {
   double *x0, *xdes, *feet, *obs;
   int* contact;
   int B;
+  double Ts;
 };
 __global__ void __launch_bounds__(256) cbfnmpc_pack_kernel(const __grid_constant__ PackIO io) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,9 +126,31 @@ __global__ void __launch_bounds__(256) cbfnmpc_pack_kernel(const __grid_constant
   }
   // real obstacles of the agent's team (Pobs_real, 2 x n_obs column-major) -> x of all obstacles, then y          :371-396
   const double* Po = r.Pobs_real + (size_t)t * 2 * r.n_obs;
+  const int no = (r.state_other != nullptr) ? r.n_other : 0, K = r.n_obs + no;
   for (int k = 0; k < r.n_obs; k++) {
     io.obs[(size_t)k * B + b] = Po[2 * k];
-    io.obs[(size_t)(r.n_obs + k) * B + b] = Po[2 * k + 1];
+    io.obs[(size_t)(K + k) * B + b] = Po[2 * k + 1];
+  }
+  // the other agents, extrapolated over the horizon, as obstacle candidates (the reference's disabled rule)            :391
+  for (int k = 0; k < no; k++) {
+    const double* so = r.state_other + (size_t)(4 * k) * B + b;
+    // separately rounded products and sum (no FMA contraction): the same bits as the host-side mirrors
+    io.obs[(size_t)(r.n_obs + k) * B + b] = __dadd_rn(so[0], __dmul_rn(__dmul_rn(so[2 * B], 4.0), io.Ts));
+    io.obs[(size_t)(K + r.n_obs + k) * B + b] = __dadd_rn(so[B], __dmul_rn(__dmul_rn(so[3 * B], 4.0), io.Ts));
+  }
+}
+
+// state_other of team-major batches: neighbour k of agent a = k-th other member of its team
+__global__ void __launch_bounds__(256) cbfnmpc_team_states_kernel(int B, int T, const double* __restrict__ q, const double* __restrict__ dq,
+                                                                  double* __restrict__ so) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const size_t Bs = (size_t)B;
+  const int base = (b / T) * T, me = b - base;
+  for (int k = 0; k < T - 1; k++) {
+    const int o = base + (k < me ? k : k + 1);
+    so[(size_t)(4 * k) * Bs + b] = q[o]; so[(size_t)(4 * k + 1) * Bs + b] = q[Bs + o];
+    so[(size_t)(4 * k + 2) * Bs + b] = dq[o]; so[(size_t)(4 * k + 3) * Bs + b] = dq[Bs + o];
   }
 }
 
@@ -347,7 +370,9 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
     CK(cudaMalloc(&c->d_sin, nin)); CK(cudaMalloc(&c->d_sout, nout));
     CK(cudaHostAlloc(&c->h_sin, nin, cudaHostAllocDefault)); CK(cudaHostAlloc(&c->h_sout, nout, cudaHostAllocDefault));
   }
+  // function attributes are per device: set them for every context, not once per process
   CK(cudaFuncSetAttribute(cbfnmpc_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LANE_NPRIV * LANE_NT * sizeof(double))));
+  CK(cudaFuncSetAttribute(cbfnmpc_qpdense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QD_WARPS * sizeof(QDenseWS))));
   *out = c;
   return CBFNMPC_OK;
 }
@@ -577,6 +602,7 @@ static int check_raw(const cbfnmpc_raw_in* r) {
       !r->Pr_refined || !r->Prd_refined || !r->Pobs_real)
     return fail(CBFNMPC_ERR_ARG, "cbfnmpc_raw_in: missing array");
   if (r->nq < 2 || r->ref_cols < 1 || r->n_teams < 1 || r->n_obs < 1) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_raw_in: bad size");
+  if (r->n_other < 0 || (r->n_other > 0 && !r->state_other)) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_raw_in: n_other without state_other");
   return CBFNMPC_OK;
 }
 
@@ -587,7 +613,7 @@ int cbfnmpc_pack_inputs(cbfnmpc_ctx* c, int B, const cbfnmpc_raw_in* raw, const 
   if (rc) return rc;
   CK(cudaSetDevice(c->device));
   PackIO io;
-  io.r = *raw; io.B = B;
+  io.r = *raw; io.B = B; io.Ts = c->gains.Ts;
   io.x0 = (double*)packed->x0; io.xdes = (double*)packed->xdes; io.feet = (double*)packed->feet_xy; io.obs = (double*)packed->obs_xy;
   io.contact = (int*)packed->contact;
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
@@ -597,15 +623,27 @@ int cbfnmpc_pack_inputs(cbfnmpc_ctx* c, int B, const cbfnmpc_raw_in* raw, const 
   return CBFNMPC_OK;
 }
 
+int cbfnmpc_team_states(cbfnmpc_ctx* c, int B, int team_size, const double* q, const double* dq, double* state_other, void* cuda_stream) {
+  if (!c || !q || !dq || !state_other || B < 1 || team_size < 2 || B % team_size != 0)
+    return fail(CBFNMPC_ERR_ARG, "cbfnmpc_team_states: bad argument (B must be a multiple of team_size >= 2)");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  cbfnmpc_team_states_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, team_size, q, dq, state_other);
+  CK(cudaGetLastError());
+  c->launches++;
+  return CBFNMPC_OK;
+}
+
 int cbfnmpc_run_cycle(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_raw_in* raw, const double* alpha_buf, const cbfnmpc_out* out,
                       void* cuda_stream) {
   if (!c || !raw || !out || B < 1) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_run_cycle: bad argument");
   if (B > c->max_batch) return fail(CBFNMPC_ERR_ARG, "batch larger than max_batch");
-  if (raw->n_obs > c->max_obs) return fail(CBFNMPC_ERR_ARG, "more obstacles than max_obs");
+  const int K = raw->n_obs + (raw->state_other ? raw->n_other : 0);
+  if (K > c->max_obs) return fail(CBFNMPC_ERR_ARG, "more obstacle columns (n_obs + n_other) than max_obs");
   if (mode != CBFNMPC_MODE_QP && mode != CBFNMPC_MODE_QP_NLP) return fail(CBFNMPC_ERR_ARG, "bad mode");
   const size_t Bs = (size_t)B;
   double* d = c->d_in;  // staging layout of cbfnmpc_solve_batch_host: x0 4 | xdes 16 | feet 8 | alpha_buf 4 | obs 2K
-  cbfnmpc_in din = {d, d + 4 * Bs, d + 20 * Bs, c->d_contact, d + 32 * Bs, raw->n_obs, alpha_buf};
+  cbfnmpc_in din = {d, d + 4 * Bs, d + 20 * Bs, c->d_contact, d + 32 * Bs, K, alpha_buf};
   int rc = cbfnmpc_pack_inputs(c, B, raw, &din, cuda_stream);
   if (rc) return rc;
   return launch(c, B, mode, &din, out, nullptr, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
@@ -617,8 +655,6 @@ int cbfnmpc_qp_dense_batch(cbfnmpc_ctx* c, int B, int n, int p, int m, const dou
   if (n < 1 || n > QD_NMAX || p < 0 || p > QD_PMAX || m < 1 || m > QD_MMAX) return fail(CBFNMPC_ERR_ARG, "dimensions outside n <= 32, p <= 24, 1 <= m <= 64");
   if (p > 0 && (!A || !b)) return fail(CBFNMPC_ERR_ARG, "equality data missing");
   CK(cudaSetDevice(c->device));
-  static bool attr_set = false;
-  if (!attr_set) { CK(cudaFuncSetAttribute(cbfnmpc_qpdense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QD_WARPS * sizeof(QDenseWS)))); attr_set = true; }
   QDenseIO io;
   io.B = B; io.n = n; io.p = p; io.m = m; io.P = P; io.c = cv; io.A = A; io.b = b; io.G = G; io.h = h;
   io.reltol = c->opts.qp_reltol; io.abstol = c->opts.qp_abstol; io.maxit = c->opts.qp_maxit;

@@ -10,6 +10,7 @@ from .api import BatchSolver
 NDOMAIN = 4            # include/global_loco_opts.h:9
 NUMBER_OF_AGENTS = 4   # :14
 NUMBER_OF_OBS = 20     # :15
+TS = 43 * 0.001         # TSOPTTICK * 0.001, evaluated like the reference does (not the literal 0.043) (include/global_loco_opts.h:10; MPC_dist.cpp:104)
 INIT_FOOTPRINT = np.array([[0.2188, -0.1320], [0.2188, 0.1320], [-0.1472, -0.1320], [-0.1472, 0.1320]])  # MPC_dist.cpp:1206-1209
 
 
@@ -17,8 +18,11 @@ class MPC_dist:
     """One agent.  Construct with a shared BatchSolver (or let it create one with max_batch=1)."""
 
     def __init__(self, solver=None):
-        self.solver = solver or BatchSolver(max_batch=1, max_obs=NUMBER_OF_OBS)
+        self.solver = solver or BatchSolver(max_batch=1, max_obs=NUMBER_OF_OBS + NUMBER_OF_AGENTS - 1)
         self.use_snopt = False                      # include/MPC_dist.hpp:139
+        # the reference's disabled inter-agent rule (MPC_dist.cpp:391): the other agent, extrapolated over the horizon, competes
+        # with the real obstacles for the distance rows.  False = the reference as shipped (state_other carried, unread).
+        self.use_state_other = False
         self.agent_id_ = 0                          # MPC_dist.cpp:58
         self.gaitDomain_ = 0                        # :55
         self.domain_ = 0                            # :54
@@ -54,7 +58,7 @@ class MPC_dist:
         self.q[:] = np.asarray(qin, float)[:18]; self.dq[:] = np.asarray(dqin, float)[:18]
         self.contactInd[:] = np.asarray(ind, np.int32)[:4]
         self.toePos_ = np.asarray(toePos, float).reshape(3, 4).copy()
-        self.state_other = np.asarray(state_vec, float).reshape(4).copy()
+        self.state_other = np.asarray(state_vec, float).reshape(-1).copy()   # 4 numbers per neighbour
 
     def copPlanner_eventbase(self):  # MPC_dist.cpp:702-782: columns [N*gaitDomain_, +N) of this agent's rows
         N, a, g = 4, self.agent_id_, self.gaitDomain_
@@ -74,7 +78,12 @@ class MPC_dist:
         xdes = self.copPlanner_eventbase()
         feet = self.footholdsPlanner()
         x0 = np.array([self.q[0], self.dq[0], self.q[1], self.dq[1]])  # :226-229
-        return (x0, xdes, feet, self.contactInd.copy(), self.Pobs_real.copy())
+        obs = self.Pobs_real.copy()
+        if self.use_state_other:
+            so = self.state_other.reshape(-1, 4)   # one row (x, y, vx, vy) per neighbour; the reference has one neighbour
+            ext = np.stack([so[:, 0] + so[:, 2] * 4 * TS, so[:, 1] + so[:, 3] * 4 * TS])
+            obs = np.hstack([obs, ext])
+        return (x0, xdes, feet, self.contactInd.copy(), obs)
 
     def _consume(self, out, b):
         self.mpc_state_e_x_eventbased_ = out["X"][:, b].copy()                 # :431-436
@@ -102,8 +111,15 @@ class MPC_dist_team:
 
     def __init__(self, agents, solver=None):
         self.agents = agents
-        self.solver = solver or BatchSolver(max_batch=len(agents), max_obs=NUMBER_OF_OBS)
+        self.solver = solver or BatchSolver(max_batch=len(agents), max_obs=NUMBER_OF_OBS + len(agents) - 1)
         for a in agents: a.solver = self.solver
+
+    def exchange_states(self):
+        """What the simulation loop of the reference does between cycles (state_vec = the other agent's get_lastState()), for a
+        whole team: every agent receives the (x, y, vx, vy) of all the others, in team order."""
+        last = [a.get_lastState() for a in self.agents]
+        for i, a in enumerate(self.agents):
+            a.state_other = np.concatenate([last[k] for k in range(len(self.agents)) if k != i])
 
     def run_NMPC(self):
         insts = [a._instance() for a in self.agents]

@@ -1,6 +1,11 @@
 """Multi-GPU plumbing of the batch path: instances are independent, so ranks own contiguous ranges of the
 global instance set and exchange nothing in the data path; torch.distributed is used only for the barrier and for the
-max-over-ranks / sum-over-ranks reduction of the timing and work counters."""
+max-over-ranks / sum-over-ranks reduction of the timing and work counters.
+
+The one exchange the reference has is `state_other`: every agent receives the other agent's (x, y, vx, vy) once per control
+cycle (MPC_dist::updateState, src/MPC_dist.cpp:1200) -- unused by the shipped run_NMPC, consumed by its disabled inter-agent rule
+(:391).  For batches stored team by team it is a local gather (cbfnmpc_team_states); when the members of a team live on
+different GPUs (rank r holds member r of every team) it is one all-gather per cycle: `exchange_state_other`."""
 import torch
 
 
@@ -43,3 +48,19 @@ def gather_results(dist, local, device):
         dist.all_gather(parts, pad)
         out[k] = torch.cat([p[:int(s)] for p, s in zip(parts, sizes)]).cpu().numpy().T
     return out
+
+
+def exchange_state_other(dist, q, dq, device=None):
+    """Agent-sharded layout: rank r holds member r of every team, team t at local index t on every rank; world size = team size.
+    q, dq: [nq][B_local] tensors (rows 0, 1 are read).  Returns state_other [4*(world-1)][B_local]: rows 4k..4k+3 = (x, y, vx, vy)
+    of the k-th OTHER member of the team (ranks in increasing order, own rank skipped) -- the layout cbfnmpc_raw_in.state_other
+    takes.  One all-gather of 4 x B_local doubles per rank and cycle (NCCL on GPUs, gloo in the CPU tests)."""
+    mine = torch.stack([q[0], q[1], dq[0], dq[1]]).contiguous()
+    if device is not None:
+        mine = mine.to(device)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return mine.new_zeros((0, mine.shape[1]))
+    world, rank = dist.get_world_size(), dist.get_rank()
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return torch.cat([parts[r] for r in range(world) if r != rank]).contiguous()

@@ -208,6 +208,108 @@ def test_raw_input_packing_and_run_cycle(pkg):
     s.close()
 
 
+def test_state_other_as_obstacle_candidate(pkg):
+    """The reference's disabled inter-agent rule (src/MPC_dist.cpp:391): the other agents, extrapolated over the horizon,
+    compete with the real obstacles for the distance rows.  cbfnmpc_team_states against numpy, the packed obstacle columns
+    against numpy, the cycle against the oracle fed with the augmented obstacle list, and the host-side mirror."""
+    import torch
+    import oracle as O
+    from srb_cbf_nmpc_b200 import capi, scenarios as S, mpc_dist as MD
+    rng = np.random.default_rng(5)
+    T, A, ref_cols, K, nq, Ts = 16, 4, 40, 6, 18, 43 * 0.001
+    B = T * A
+    insts = S.cfg3_instances(B, seed=99)
+    # team mates 0.35-0.7 m apart, moving, so that a neighbour is often the closest "obstacle"
+    q = np.zeros((nq, B)); dq = np.zeros((nq, B))
+    for t in range(T):
+        c0 = np.array([insts[4 * t][0][0], insts[4 * t][0][2]])
+        for a in range(A):
+            b = 4 * t + a
+            q[0, b], q[1, b] = c0 + np.array([0.45 * (a // 2), 0.5 * (a % 2)]) + rng.uniform(-0.05, 0.05, 2)
+            dq[0, b], dq[1, b] = rng.uniform(-0.3, 0.3, 2)
+    Pobs = rng.uniform(0, 9, size=(T, 2, K)); Pobs[:, 1] = rng.uniform(-2, 2, size=(T, K))
+    team = np.repeat(np.arange(T), A).astype(np.int32); agent = np.tile(np.arange(A), T).astype(np.int32)
+    gait = np.full(B, 3, np.int32); ainit = np.stack([q[0], q[1]])
+    Pr = np.zeros((T, 8, ref_cols)); Prd = np.zeros((T, 8, ref_cols))
+    for t in range(T):
+        for a in range(A):
+            b = 4 * t + a
+            Pr[t, 2 * a] = q[0, b] + 0.2 * Ts * np.arange(ref_cols); Pr[t, 2 * a + 1] = q[1, b]; Prd[t, 2 * a] = 0.2
+    contact = np.ones((4, B), np.int32)
+    toe = np.zeros((12, B))
+    for i, (fx, fy) in enumerate(MD.INIT_FOOTPRINT):
+        toe[3 * i] = q[0] + fx; toe[3 * i + 1] = q[1] + fy
+    dev = torch.device("cuda", 0)
+    cm = lambda a: np.ascontiguousarray(np.transpose(a, (0, 2, 1)))
+    tens = dict(q=q, dq=dq, contact=contact, toe_pos=toe, gait_domain=gait, agent_id=agent, team=team, agent_initial=ainit,
+                Pr_refined=cm(Pr), Prd_refined=cm(Prd), Pobs_real=cm(Pobs))
+    dten = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in tens.items()}
+    s = pkg.BatchSolver(device=0, max_batch=B, max_obs=K + A - 1)
+    so = torch.zeros((4 * (A - 1), B), dtype=torch.float64, device=dev)
+    s.team_states(B, A, dten["q"].data_ptr(), dten["dq"].data_ptr(), so.data_ptr())
+    torch.cuda.synchronize()
+    so_ref = np.zeros((4 * (A - 1), B))
+    for b in range(B):
+        others = [4 * (b // 4) + k for k in range(A) if k != b % 4]
+        for k, o in enumerate(others):
+            so_ref[4 * k:4 * k + 4, b] = [q[0, o], q[1, o], dq[0, o], dq[1, o]]
+    assert np.array_equal(so.cpu().numpy(), so_ref)
+    raw = {k: v.data_ptr() for k, v in dten.items()}
+    raw.update(nq=nq, ref_cols=ref_cols, n_teams=T, n_obs=K, state_other=so.data_ptr(), n_other=A - 1)
+    KK = K + A - 1
+    packed = {"x0": torch.zeros((4, B), dtype=torch.float64, device=dev), "xdes": torch.zeros((16, B), dtype=torch.float64, device=dev),
+              "feet_xy": torch.zeros((8, B), dtype=torch.float64, device=dev), "contact": torch.zeros((4, B), dtype=torch.int32, device=dev),
+              "obs_xy": torch.zeros((2 * KK, B), dtype=torch.float64, device=dev)}
+    s.pack_inputs(B, raw, {k: v.data_ptr() for k, v in packed.items()})
+    torch.cuda.synchronize()
+    obs_ref = np.zeros((B, 2, KK))
+    for b in range(B):
+        obs_ref[b, :, :K] = Pobs[team[b]]
+        for k in range(A - 1):
+            x, y, vx, vy = so_ref[4 * k:4 * k + 4, b]
+            obs_ref[b, 0, K + k] = x + vx * 4.0 * Ts; obs_ref[b, 1, K + k] = y + vy * 4.0 * Ts
+    assert np.array_equal(packed["obs_xy"].cpu().numpy().T.reshape(B, 2, KK), obs_ref)
+    abuf = torch.from_numpy(np.stack([q[0], 0 * q[0], q[1], 0 * q[0]])).to(dev)
+    o = {k: torch.zeros((n, B), dtype=torch.float64, device=dev) for k, n in capi.OUT_F64.items()}
+    o.update({k: torch.zeros((n, B), dtype=torch.int32, device=dev) for k, n in capi.OUT_I32.items()})
+    o["active"] = torch.zeros((2, B), dtype=torch.int64, device=dev)
+    s.run_cycle(B, raw, abuf.data_ptr(), {k: v.data_ptr() for k, v in o.items()}, mode=capi.MODE_QP_NLP)
+    torch.cuda.synchronize()
+    x0 = np.stack([q[0], dq[0], q[1], dq[1]], 1)
+    xdes = np.stack([O.cop_planner(Pr[team[b]], Prd[team[b]], agent[b], gait[b]) for b in range(B)])
+    feet = np.stack([O.footholds(toe[:, b].reshape(4, 3).T, gait[b], ainit[:, b]).reshape(2, 4) for b in range(B)])
+    ref = O.solve_batch(x0, xdes, feet, contact.T.copy(), obs_ref, abuf.cpu().numpy().T.copy(), mode=1, nthreads=8)
+    st = o["status"][0].cpu().numpy()
+    assert (st == ref["status"]).all()
+    ok = st == 0
+    assert ok.sum() > B // 2
+    assert np.abs(o["X"].cpu().numpy().T - ref["X"])[ok].max() < 1e-6 and np.abs(o["U"].cpu().numpy().T - ref["U"])[ok].max() < 1e-6
+    # a neighbour really is the distance-row centre for some agents, and the rule changes their answers
+    dists = np.linalg.norm(obs_ref - np.stack([q[0], q[1]], 1)[:, :, None], axis=1)
+    assert (dists.argmin(1) >= K).sum() > B // 4
+    raw0 = dict(raw); raw0.pop("state_other"); raw0.pop("n_other")
+    o0 = {k: torch.zeros_like(v) for k, v in o.items()}
+    s.run_cycle(B, raw0, abuf.data_ptr(), {k: v.data_ptr() for k, v in o0.items()}, mode=capi.MODE_QP_NLP)
+    torch.cuda.synchronize()
+    assert (o0["X"] - o["X"]).abs().max().item() > 1e-3
+    # host-side mirror: MPC_dist_team.exchange_states + use_state_other, one team
+    ags = []
+    for a in range(A):
+        m = MD.MPC_dist(solver=s); m.setAgentID(a); m.use_snopt = True; m.use_state_other = True
+        m.setPstart(np.stack([q[0, :A], q[1, :A]], 1).reshape(-1)); m.setPobs_real(Pobs[0]); m.setReferenceTrajectory(Pr[0], Prd[0])
+        m.gaitDomain_ = 3
+        qa = np.zeros(18); dqa = np.zeros(18); qa[:2] = q[:2, a]; dqa[:2] = dq[:2, a]
+        m.updateState(qa, dqa, [1, 1, 1, 1], toe[:, a].reshape(4, 3).T, np.zeros(4))
+        ags.append(m)
+    tm = MD.MPC_dist_team(ags, solver=s)
+    tm.exchange_states()
+    tm.run_NMPC()
+    for a in range(A):
+        assert ags[a].status == st[a]
+        if st[a] == 0: assert np.abs(ags[a].get_MPCsol()[:, 0] - ref["X"][a]).max() < 1e-6
+    s.close()
+
+
 def _world_to_device(w, torch, dev):
     keys = ("q", "dq", "contact", "toe_pos", "gait_domain", "agent_id", "team", "agent_initial", "Pr_refined", "Prd_refined", "Pobs_real",
             "alpha_buf", "success", "distance_to_fail", "n_not_converged")

@@ -58,3 +58,33 @@ def test_shard_ranges_cover_exactly():
             assert rs[0][0] == 0 and rs[-1][1] == n and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
             assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
     assert SH.shard_teams(16384, 4, 3, 8) == (3 * 2048 * 4, 4 * 2048 * 4)
+
+
+def _worker_exchange(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    from srb_cbf_nmpc_b200 import sharding as SH
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    qq = torch.randn((18, 5), generator=g, dtype=torch.float64); dq = torch.randn((18, 5), generator=g, dtype=torch.float64)
+    so = SH.exchange_state_other(dist, qq, dq)
+    q.put((rank, qq[:2].numpy(), dq[:2].numpy(), so.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_state_other_exchange():
+    """Agent-sharded teams (rank r holds member r of every team): one all-gather per cycle hands every agent the other member's
+    (x, y, vx, vy) -- the state_vec of MPC_dist::updateState (src/MPC_dist.cpp:1195-1202)."""
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_exchange, args=(r, world, port, q)) for r in range(world)]
+    for p in ps: p.start()
+    res = sorted((q.get(timeout=120) for _ in ps), key=lambda t: t[0])
+    for p in ps: p.join(timeout=60)
+    assert [p.exitcode for p in ps] == [0, 0]
+    (_, q0, dq0, so0), (_, q1, dq1, so1) = res
+    assert so0.shape == so1.shape == (4, 5)
+    assert np.array_equal(so0, np.vstack([q1, dq1])) and np.array_equal(so1, np.vstack([q0, dq0]))
