@@ -85,6 +85,7 @@ def cpu_baseline(insts, seconds_target=12.0, nthreads=None):
     import oracle as O
     nthreads = nthreads or os.cpu_count() or 1
     O.build()
+    ref_qp = O.use_reference_qp(True)   # QP stage by the reference's own iSWIFT core when oracle/_ref travelled with the repo
 
     def run(sub):
         x0 = np.array([i[0] for i in sub]); xd = np.array([i[1] for i in sub]); ft = np.array([i[2] for i in sub])
@@ -100,10 +101,13 @@ def cpu_baseline(insts, seconds_target=12.0, nthreads=None):
     while dt < seconds_target and passes < 64:
         d1, c1 = run(insts)
         dt += d1; conv += c1; n += len(insts); passes += 1
+    O.use_reference_qp(False)
+    qp_desc = ("QP stage = the reference's own iSWIFT C core compiled from /root/reference (oracle/_ref)" if ref_qp
+               else "QP stage = dense restatement of iSWIFT (oracle/_ref absent)")
     return {"value": conv / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
-            "sample": "%d passes over the %d cfg-3 instances (%d solves, %d converged) in %.1f s wall on %d host threads; "
-                      "oracle/cbfnmpc_oracle.c (dense iSWIFT-restated QP + IPM-F NLP; the reference's ifopt+SNOPT stage cannot be built "
-                      "offline)" % (passes, len(insts), n, conv, dt, nthreads),
+            "sample": "%d passes over the %d cfg-3 instances (%d solves, %d converged) in %.1f s wall on %d host threads; %s, NLP stage = "
+                      "IPM-F restatement of oracle/cbfnmpc_oracle.c (the reference's ifopt+SNOPT stage cannot be built offline)"
+                      % (passes, len(insts), n, conv, dt, nthreads, qp_desc),
             "n": n, "seconds": dt, "converged": conv}
 
 

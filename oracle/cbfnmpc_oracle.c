@@ -898,6 +898,11 @@ void orc_bezier_fit(const double *alpha_buf, const double *X16, double *alpha20,
   }
 }
 
+/* QP stage of orc_solve_instance: the restatement above, or (bench.py's CPU baseline) the reference's own iSWIFT core from
+ * oracle/_ref, handed in as a function pointer with the signature of ref_driver.c's iswift_ref_solve_dense */
+static orc_qp_backend g_qp_backend = 0;
+void orc_set_qp_backend(orc_qp_backend f) { g_qp_backend = f; }
+
 int orc_solve_instance(const orc_gains *g, const orc_options *o, const double *x0, const double *xdes,
                        const double *feet_xy, const int *contact, const double *obs_xy, int K,
                        const double *alpha_buf, int mode, orc_result *res) {
@@ -921,7 +926,9 @@ int orc_solve_instance(const orc_gains *g, const orc_options *o, const double *x
   double *xq = h + mi, *yq = xq + nv, *zq = yq + p, *sq = zq + mi;
   orc_pack_dense(g, x0, xdes, F, c, Q, f, A, b, G, h);
   int qit = 0;
-  int qflag = orc_qp_mehrotra(nv, mi, p, Q, f, A, b, G, h, o->qp_reltol, o->qp_abstol, o->qp_maxit, 0.0, xq, yq, zq, sq, &qit);
+  int qflag;
+  if (g_qp_backend) { double t1 = 0, t2 = 0; qflag = g_qp_backend(nv, mi, p, Q, f, A, b, G, h, xq, yq, zq, sq, &qit, &t1, &t2); }
+  else qflag = orc_qp_mehrotra(nv, mi, p, Q, f, A, b, G, h, o->qp_reltol, o->qp_abstol, o->qp_maxit, 0.0, xq, yq, zq, sq, &qit);
   double obs[2] = {0, 0};
   if (mode == 1) {
     double pos[2] = {x0[0], x0[2]};

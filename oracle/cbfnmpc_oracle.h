@@ -80,6 +80,9 @@ int orc_closest_obstacle(const double *pos, const double *obs_xy, int K, double 
 void orc_bezier_fit(const double *alpha_buf, const double *X16, double *alpha20, double *alpha_buf_next);
 
 /* iSWIFT restated, dense, column-major inputs.  Returns flag (0 optimal, 2 max-iter, 1 KKT failure). */
+typedef int (*orc_qp_backend)(int n, int m, int p, const double *P, const double *c, const double *A, const double *b, const double *G,
+                              const double *h, double *x, double *y, double *z, double *s, int *iters, double *t_setup, double *t_solve);
+void orc_set_qp_backend(orc_qp_backend f); /* NULL = orc_qp_mehrotra */
 int orc_qp_mehrotra(int n, int m, int p, const double *P, const double *c, const double *A, const double *b,
                     const double *G, const double *h, double reltol, double abstol, int maxit, double sigma_d,
                     double *x, double *y, double *z, double *s, int *iters);

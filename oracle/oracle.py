@@ -91,6 +91,20 @@ def ref_lib():
     return _ref
 
 
+def use_reference_qp(on=True):
+    """QP stage of solve_instance / solve_batch by the reference's own iSWIFT C core (oracle/_ref) instead of the restatement.
+    Returns True when the core is available and now in use.  Used by bench.py's CPU baseline only; the parity tests keep the
+    restatement (which they pin against that core separately)."""
+    L = lib()
+    L.orc_set_qp_backend.argtypes = [C.c_void_p]
+    r = ref_lib() if on else None
+    if r is None:
+        L.orc_set_qp_backend(None)
+        return False
+    L.orc_set_qp_backend(C.cast(r.iswift_ref_solve_dense, C.c_void_p))
+    return True
+
+
 def default_options():
     o = Options(); lib().orc_default_options(C.byref(o)); return o
 
