@@ -77,6 +77,31 @@ def test_golden_scipy_agreement():
         assert abs(g["obj_oracle"][i] - g["obj_scipy"][i]) < 1e-3 * max(1.0, abs(g["obj_oracle"][i]) * 1e-4)
 
 
+def test_live_scipy_agreement_on_fresh_instances():
+    """The same cross-check run live on instances outside the fixture: scipy SLSQP (a sequential QP method, like the
+    reference's SNOPT) started at the QP optimum lands on the oracle's local solution on every instance: X, U to 1e-4 and the
+    slack variable to 1e-6 (SLSQP stops where its line search stalls at ftol = 1e-15, up to 1e-7 outside the feasible set),
+    objective to 2e-6 relative."""
+    from scipy.optimize import minimize
+    insts = S.cfg3_instances(40, seed=20251018 + 9000)
+    checked = 0
+    for (x0, xdes, feet, contact, obs) in insts:
+        r = O.solve_instance(x0, xdes, feet, contact, obs)
+        if r["status"] != 0:
+            continue
+        F = P.stance_matrix(feet, contact)
+        Q, f, A, b, G, h = O.pack_dense(x0, xdes, F)
+        prob = P.NlpProblem(Q, f, A, b, G, h, r["obs"])
+        cons = [dict(type="eq", fun=lambda v: A @ v - b, jac=lambda v: A), dict(type="ineq", fun=prob.cons, jac=prob.jac)]
+        res = minimize(prob.obj, r["x_qp"], jac=prob.grad, constraints=cons, method="SLSQP", options=dict(ftol=1e-15, maxiter=500))
+        fo = prob.obj(r["x"])
+        assert prob.cons(res.x).min() > -1e-6
+        assert abs(res.fun - fo) <= 2e-6 * max(1.0, abs(fo)), (res.fun, fo)
+        assert np.abs(res.x[:24] - r["x"][:24]).max() < 1e-4 and abs(res.x[-1] - r["x"][-1]) < 1e-6
+        checked += 1
+    assert checked >= 30
+
+
 def test_numpy_prototype_follows_c_oracle():
     for inst in [S.cfg1_instance(4)] + S.cfg3_instances(6):
         rc = O.solve_instance(*inst)
