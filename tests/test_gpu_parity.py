@@ -123,6 +123,36 @@ def test_results_do_not_depend_on_batch_order_or_size(pkg):
     s.close()
 
 
+def test_reflection_equivariance_at_full_size(pkg):
+    """Size-independent property of the path at BASELINE's batch size: the problem is equivariant under the reflection y -> -y
+    (state, reference, feet and obstacles mirrored together; left and right feet swap).  The solver is not told: the answers
+    must mirror too.  (It is NOT translation-equivariant: the reference's input cost 0.1 |u|^2 penalises the absolute COP
+    position, MPC_dist.cpp:164-175 -- the oracle shows the same 1e-4 shifts.)"""
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    B = 4096
+    insts = S.cfg3_instances(B)
+    s = pkg.BatchSolver(device=0, max_batch=B, max_obs=20)
+    base = s.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP_NLP)
+    swap = [1, 0, 3, 2]   # feet order FR, FL, RR, RL: the mirrored robot's FR is the old FL, ...
+    mirrored = []
+    for x0, xdes, feet, contact, obs in insts:
+        x0m = np.array(x0, float); x0m[2:] *= -1
+        xd = np.array(xdes, float).copy(); xd[2::4] *= -1; xd[3::4] *= -1
+        f = np.asarray(feet, float)[:, swap].copy(); f[1] *= -1
+        o = np.asarray(obs, float).copy(); o[1] *= -1
+        mirrored.append((x0m, xd, f, [contact[k] for k in swap], o))
+    out = s.solve_host(capi.soa_from_instances(mirrored), mode=capi.MODE_QP_NLP)
+    same = out["status"][0] == base["status"][0]
+    assert same.mean() > 0.998
+    ok = same & (base["status"][0] == 0)
+    sgn = np.tile([1.0, 1.0, -1.0, -1.0], 4)[:, None]
+    assert np.abs(out["X"] - sgn * base["X"])[:, ok].max() < 1e-6
+    assert np.abs(out["U"] - np.tile([1.0, -1.0], 4)[:, None] * base["U"])[:, ok].max() < 1e-6
+    assert np.abs(out["slack"] - base["slack"])[:, ok].max() < 1e-6
+    assert (out["nlp_iters"][0][ok] == base["nlp_iters"][0][ok]).mean() > 0.99
+    s.close()
+
+
 def test_cfg4_size_65536_instances(pkg):
     """BASELINE config 4's instance count (65536; reference-faithful mode: the agents of a team are independent NLPs) in one
     launch on one GPU, checked against the oracle on every instance."""
