@@ -552,9 +552,12 @@ done:
 /* NLP stage: IPM-F                                                                                  */
 /* ------------------------------------------------------------------------------------------------ */
 typedef struct {
-  int nv, mi, m, p, c, with_nl;
+  int nv, mi, m, p, c, with_nl;   /* with_nl: the 8 + 8 velocity rows are present */
   const double *Q, *f, *A, *b, *G, *h;
-  double obs[2], eps_dist, v_max;
+  double v_max;
+  int nd;                          /* distance rows: |p_{dstage+1} - dctr|^2 + delta >= deps */
+  int dstage[ORC_ND_MAX];
+  double dctr[ORC_ND_MAX][2], deps[ORC_ND_MAX];
 } nlp_prob;
 
 static void nlp_cons(const nlp_prob *P, const double *x, double *cv) { /* c(x) >= 0, row order [h-Gx | d-eps | vmax-v | vmax+v] */
@@ -566,12 +569,14 @@ static void nlp_cons(const nlp_prob *P, const double *x, double *cv) { /* c(x) >
     }
     cv[r] = t;
   }
+  for (int r = 0; r < P->nd; r++) { /* dec_vars_constr_cost.h:262-265 */
+    const int k = P->dstage[r];
+    cv[P->mi + r] = pow(x[4 * k] - P->dctr[r][0], 2) + pow(x[4 * k + 2] - P->dctr[r][1], 2) * 1 + x[P->nv - 1] - P->deps[r];
+  }
   if (P->with_nl) {
-    for (int k = 0; k < 4; k++) /* dec_vars_constr_cost.h:262-265 */
-      cv[P->mi + k] = pow(x[4 * k] - P->obs[0], 2) + pow(x[4 * k + 2] - P->obs[1], 2) * 1 + x[P->nv - 1] - P->eps_dist;
     for (int r = 0; r < 8; r++) {
-      cv[P->mi + 4 + r] = P->v_max - x[VEL_IDX[r]];
-      cv[P->mi + 12 + r] = P->v_max + x[VEL_IDX[r]];
+      cv[P->mi + P->nd + r] = P->v_max - x[VEL_IDX[r]];
+      cv[P->mi + P->nd + 8 + r] = P->v_max + x[VEL_IDX[r]];
     }
   }
 }
@@ -582,15 +587,16 @@ static void nlp_jac(const nlp_prob *P, const double *x, double *J) {
   memset(J, 0, sizeof(double) * m * nv);
   for (int j = 0; j < nv; j++)
     for (int r = 0; r < P->mi; r++) J[r + (size_t)j * m] = -P->G[r + (size_t)j * P->mi];
+  for (int r = 0; r < P->nd; r++) { /* dec_vars_constr_cost.h:363-377 */
+    const int k = P->dstage[r];
+    J[(P->mi + r) + (size_t)(4 * k) * m] = 2 * (x[4 * k] - P->dctr[r][0]);
+    J[(P->mi + r) + (size_t)(4 * k + 2) * m] = 2 * (x[4 * k + 2] - P->dctr[r][1]);
+    J[(P->mi + r) + (size_t)(nv - 1) * m] = 1.0;
+  }
   if (P->with_nl) {
-    for (int k = 0; k < 4; k++) { /* dec_vars_constr_cost.h:363-377 */
-      J[(P->mi + k) + (size_t)(4 * k) * m] = 2 * (x[4 * k] - P->obs[0]);
-      J[(P->mi + k) + (size_t)(4 * k + 2) * m] = 2 * (x[4 * k + 2] - P->obs[1]);
-      J[(P->mi + k) + (size_t)(nv - 1) * m] = 1.0;
-    }
     for (int r = 0; r < 8; r++) {
-      J[(P->mi + 4 + r) + (size_t)VEL_IDX[r] * m] = -1.0;
-      J[(P->mi + 12 + r) + (size_t)VEL_IDX[r] * m] = 1.0;
+      J[(P->mi + P->nd + r) + (size_t)VEL_IDX[r] * m] = -1.0;
+      J[(P->mi + P->nd + 8 + r) + (size_t)VEL_IDX[r] * m] = 1.0;
     }
   }
 }
@@ -634,10 +640,11 @@ static void interior_start(const nlp_prob *P, const orc_gains *g, double push, d
       x[16 + 2 * k + a] = clampd(x[16 + 2 * k + a], lo, hi);
     }
   for (int j = 24; j < 24 + 4 * c; j++) x[j] = clampd(x[j], push, 1 - push);
-  if (P->with_nl) {
+  if (P->nd > 0) {
     double cmin = 1e300;
-    for (int k = 0; k < 4; k++) {
-      double d = pow(x[4 * k] - P->obs[0], 2) + pow(x[4 * k + 2] - P->obs[1], 2) + x[P->nv - 1] - P->eps_dist;
+    for (int r = 0; r < P->nd; r++) {
+      const int k = P->dstage[r];
+      double d = pow(x[4 * k] - P->dctr[r][0], 2) + pow(x[4 * k + 2] - P->dctr[r][1], 2) + x[P->nv - 1] - P->deps[r];
       if (d < cmin) cmin = d;
     }
     if (cmin < push) x[P->nv - 1] += push - cmin;
@@ -647,10 +654,21 @@ static void interior_start(const nlp_prob *P, const orc_gains *g, double push, d
 int orc_nlp_ipm(int nv, int mi, const double *Q, const double *f, const double *Aeq, const double *beq,
                 const double *G, const double *h, const double *obs, const double *x_start, int with_nl,
                 const orc_gains *g, const orc_options *o, orc_result *res) {
+  int dstage[4] = {0, 1, 2, 3};
+  double dctr[8], deps[4];
+  for (int k = 0; k < 4; k++) { dctr[2 * k] = obs ? obs[0] : 0; dctr[2 * k + 1] = obs ? obs[1] : 0; deps[k] = g->eps_dist; }
+  return orc_nlp_ipm_rows(nv, mi, Q, f, Aeq, beq, G, h, with_nl ? 4 : 0, dstage, dctr, deps, x_start, with_nl, g, o, res);
+}
+
+int orc_nlp_ipm_rows(int nv, int mi, const double *Q, const double *f, const double *Aeq, const double *beq,
+                     const double *G, const double *h, int nd, const int *dstage, const double *dctr, const double *deps,
+                     const double *x_start, int with_nl, const orc_gains *g, const orc_options *o, orc_result *res) {
   nlp_prob P;
-  P.nv = nv; P.mi = mi; P.with_nl = with_nl; P.m = mi + (with_nl ? 20 : 0); P.p = ORC_NEQ; P.c = (nv - 25) / 4;
+  if (nd < 0 || nd > ORC_ND_MAX) { memset(res, 0, sizeof(*res)); res->status = 4; return 4; }
+  P.nv = nv; P.mi = mi; P.with_nl = with_nl; P.nd = nd; P.m = mi + nd + (with_nl ? 16 : 0); P.p = ORC_NEQ; P.c = (nv - 25) / 4;
   P.Q = Q; P.f = f; P.A = Aeq; P.b = beq; P.G = G; P.h = h;
-  P.obs[0] = obs ? obs[0] : 0; P.obs[1] = obs ? obs[1] : 0; P.eps_dist = g->eps_dist; P.v_max = g->v_max;
+  for (int r = 0; r < nd; r++) { P.dstage[r] = dstage[r]; P.dctr[r][0] = dctr[2 * r]; P.dctr[r][1] = dctr[2 * r + 1]; P.deps[r] = deps[r]; }
+  P.v_max = g->v_max;
   const int n = nv, m = P.m, p = P.p;
   /* general (multi-variable) rows stay in the augmented system; single-variable bound rows are condensed */
   int gen[ORC_MROWS_MAX], ng = 0, isgen[ORC_MROWS_MAX];
@@ -658,7 +676,7 @@ int orc_nlp_ipm(int nv, int mi, const double *Q, const double *f, const double *
     int nnz = 0;
     if (r < mi) {
       for (int j = 0; j < n; j++) nnz += (G[r + (size_t)j * mi] != 0.0);
-    } else nnz = (r < mi + 4) ? 3 : 1;
+    } else nnz = (r < mi + nd) ? 3 : 1;
     isgen[r] = nnz > 1;
     if (isgen[r]) gen[ng++] = r;
   }
@@ -740,11 +758,11 @@ int orc_nlp_ipm(int nv, int mi, const double *Q, const double *f, const double *
         K[j + (size_t)j * NK] += dw;
       }
       for (int j = 24; j < n - 1; j++) K[j + (size_t)j * NK] += o->rho_lambda;
-      if (with_nl)
-        for (int k = 0; k < 4; k++) { /* Hessian of the Lagrangian: -2 z_k on the two position diagonals */
-          K[(4 * k) + (size_t)(4 * k) * NK] -= 2 * z[mi + k];
-          K[(4 * k + 2) + (size_t)(4 * k + 2) * NK] -= 2 * z[mi + k];
-        }
+      for (int r = 0; r < nd; r++) { /* Hessian of the Lagrangian: -2 z_r on the two position diagonals of the row's stage */
+        const int k = P.dstage[r];
+        K[(4 * k) + (size_t)(4 * k) * NK] -= 2 * z[mi + r];
+        K[(4 * k + 2) + (size_t)(4 * k + 2) * NK] -= 2 * z[mi + r];
+      }
       for (int r = 0; r < m; r++) {
         if (isgen[r]) continue;
         for (int j = 0; j < n; j++) {

@@ -22,7 +22,8 @@ extern "C" {
 
 #define ORC_NV_MAX 41
 #define ORC_NEQ 28
-#define ORC_MROWS_MAX 112 /* 92 linear + 4 distance + 16 one-sided velocity rows at c = 4 */
+#define ORC_ND_MAX 76     /* distance rows: 4 in the reference (one per stage); up to 19 per stage in the extended form */
+#define ORC_MROWS_MAX 184 /* 92 linear + ORC_ND_MAX distance + 16 one-sided velocity rows at c = 4 */
 
 typedef struct {
   /* QP stage (iSWIFT GlobalOptions.h:23-26) */
@@ -92,6 +93,14 @@ int orc_qp_mehrotra(int n, int m, int p, const double *P, const double *c, const
 int orc_nlp_ipm(int nv, int mi, const double *Q, const double *f, const double *Aeq, const double *beq,
                 const double *G, const double *h, const double *obs, const double *x_start, int with_nl,
                 const orc_gains *g, const orc_options *o, orc_result *res);
+
+/* The same NLP with a general set of distance rows ("extended mode": K obstacles and neighbour rows per
+ * stage; no reference implementation exists, this is the checker the extended kernel will be held against):
+ *   row r:  |p_{dstage[r]+1} - dctr[r]|^2 + delta >= deps[r],   r = 0 .. nd-1,  dstage in 0..3, dctr nd x 2 row-major.
+ * Row order [G rows | nd distance rows | 8 + 8 velocity rows].  orc_nlp_ipm is the case nd = 4, dstage = 0..3, one centre, eps_dist. */
+int orc_nlp_ipm_rows(int nv, int mi, const double *Q, const double *f, const double *Aeq, const double *beq,
+                     const double *G, const double *h, int nd, const int *dstage, const double *dctr, const double *deps,
+                     const double *x_start, int with_vel, const orc_gains *g, const orc_options *o, orc_result *res);
 
 /* One full run_NMPC: pack -> QP -> (mode 1) closest obstacle -> NLP -> Bezier fit. */
 int orc_solve_instance(const orc_gains *g, const orc_options *o, const double *x0, const double *xdes,

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-NV_MAX, NEQ, MROWS_MAX = 41, 28, 112
+NV_MAX, NEQ, MROWS_MAX = 41, 28, 184
 
 
 class Options(C.Structure):
@@ -191,6 +191,38 @@ def nlp_ipm(Q, f, A, b, G, h, obs, x_start, with_nl=True, g=None, o=None):
     lib().orc_nlp_ipm(nv, mi, _f(Q.ravel(order="F")), _f(f), _f(A.ravel(order="F")), _f(b), _f(G.ravel(order="F")), _f(h),
                       _f(obs), _f(x_start), int(with_nl), C.byref(g), C.byref(o), C.byref(r))
     return res_to_dict(r)
+
+
+def nlp_ipm_rows(Q, f, A, b, G, h, dstage, dctr, deps, x_start, with_vel=True, g=None, o=None):
+    """The NLP with a general set of distance rows |p_{dstage[r]+1} - dctr[r]|^2 + delta >= deps[r] (extended mode)."""
+    g = g or default_gains(); o = o or default_options()
+    nv, mi = Q.shape[0], G.shape[0]
+    ds = np.ascontiguousarray(dstage, dtype=np.int32); nd = len(ds)
+    r = Result()
+    L = lib()
+    L.orc_nlp_ipm_rows.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, ip, dp, dp, dp, C.c_int, C.POINTER(Gains),
+                                   C.POINTER(Options), C.POINTER(Result)]
+    L.orc_nlp_ipm_rows(nv, mi, _f(Q.ravel(order="F")), _f(f), _f(A.ravel(order="F")), _f(b), _f(G.ravel(order="F")), _f(h), nd, ds,
+                       _f(np.asarray(dctr, float).reshape(-1)), _f(deps), _f(x_start), int(with_vel), C.byref(g), C.byref(o), C.byref(r))
+    return res_to_dict(r)
+
+
+def solve_instance_ext(x0, xdes, feet, contact, centres, eps, g=None, o=None):
+    """Extended-mode instance: QP stage as in the reference, then the NLP with n_c distance rows per stage.  centres
+    (n_c, 4, 2): centre of row i at stage k (an obstacle: the same point at every stage; a neighbour: its predicted position at
+    that stage); eps (n_c,).  Returns the dict of nlp_ipm_rows plus x_qp."""
+    g = g or default_gains(); o = o or default_options()
+    F = np.zeros(8); c = lib().orc_stance_matrix(_f(np.asarray(feet, float).reshape(-1)), np.ascontiguousarray(contact, dtype=np.int32), F)
+    if c < 0:
+        return dict(status=4)
+    Fm = F[:2 * c].reshape(2, c)
+    Q, f, A, b, G, h = pack_dense(np.asarray(x0, float), np.asarray(xdes, float), Fm, g)
+    xq = qp_mehrotra(Q, f, A, b, G, h, o.qp_reltol, o.qp_abstol, o.qp_maxit)[0]
+    centres = np.asarray(centres, float); n_c = centres.shape[0]
+    dstage = np.tile(np.arange(4), n_c); dctr = centres.reshape(-1, 2); deps = np.repeat(np.asarray(eps, float), 4)
+    r = nlp_ipm_rows(Q, f, A, b, G, h, dstage, dctr, deps, xq, True, g, o)
+    r["x_qp"] = xq
+    return r
 
 
 def solve_instance(x0, xdes, feet, contact, obs, alpha_buf=None, mode=1, g=None, o=None):

@@ -109,3 +109,76 @@ def test_numpy_prototype_follows_c_oracle():
         assert (rc["status"] == 0) == (rn["info"]["status"] == 0)
         if rc["status"] == 0:
             assert np.abs(rc["x"][:24] - rn["x"][:24]).max() < 1e-9
+
+
+def _ext_problem(inst, n_obs=3, n_nbr=2, seed=0):
+    """Extended-mode rows for one instance: the n_obs closest obstacles (one centre for all stages, eps 1.9) and n_nbr
+    neighbours walking beside the robot (a different centre per stage, eps 2.2 = the reference's commented robot-to-robot
+    threshold, dec_vars_constr_cost.h:402)."""
+    x0, xdes, feet, contact, obs = inst
+    rng = np.random.default_rng(seed)
+    d = np.hypot(obs[0] - x0[0], obs[1] - x0[2])
+    centres = [np.tile(obs[:, k], (4, 1)) for k in np.argsort(d)[:n_obs]]
+    for j in range(n_nbr):
+        p = np.array([x0[0], x0[2]]) + rng.uniform(0.6, 1.0) * np.array([np.cos(2.1 * j + 1.0), np.sin(2.1 * j + 1.0)])
+        v = rng.uniform(-0.2, 0.2, 2)
+        centres.append(np.stack([p + v * 0.043 * (k + 1) for k in range(4)]))
+    eps = np.array([1.9] * n_obs + [2.2] * n_nbr)
+    return np.array(centres), eps
+
+
+def test_extended_rows_reduce_to_the_reference_form():
+    """orc_nlp_ipm_rows with the reference's 4 rows (one centre, one per stage) is orc_nlp_ipm, bit for bit."""
+    for inst in S.cfg3_instances(12):
+        x0, xdes, feet, contact, obs = inst
+        r = O.solve_instance(x0, xdes, feet, contact, obs)
+        e = O.solve_instance_ext(x0, xdes, feet, contact, np.tile(r["obs"], (1, 4, 1)), [float(np.float32(1.9))])
+        assert e["status"] == r["status"] and e["nlp_iters"] == r["nlp_iters"]
+        assert np.array_equal(e["x"], r["x"]) and np.array_equal(e["z"], r["z"])
+
+
+def test_extended_rows_give_kkt_points_that_scipy_confirms():
+    """Extended mode (K obstacle rows and neighbour rows per stage; no reference implementation): the oracle's
+    answers satisfy the KKT conditions of the enlarged NLP (independent numpy residual) and scipy SLSQP agrees."""
+    from scipy.optimize import minimize
+    n_ok = 0
+    for k, inst in enumerate(S.cfg3_instances(16, seed=20251018 + 9500)):
+        x0, xdes, feet, contact, obs = inst
+        centres, eps = _ext_problem(inst, seed=k)
+        r = O.solve_instance_ext(x0, xdes, feet, contact, centres, eps)
+        if r["status"] != 0:
+            continue
+        F = P.stance_matrix(feet, contact)
+        Q, f, A, b, G, h = O.pack_dense(x0, xdes, F)
+        nv, mi, n_c = Q.shape[0], G.shape[0], len(eps)
+        x, y, z = r["x"], r["y"], r["z"]
+        vel = [1, 5, 9, 13, 3, 7, 11, 15]
+
+        def cons(v):
+            dist = [(v[4 * s] - centres[i, s, 0]) ** 2 + (v[4 * s + 2] - centres[i, s, 1]) ** 2 + v[-1] - eps[i] for i in range(n_c) for s in range(4)]
+            vm = float(np.float32(0.35))
+            return np.concatenate([h - G @ v, dist, vm - v[vel], vm + v[vel]])
+
+        def jac(v):
+            J = np.zeros((mi + 4 * n_c + 16, nv)); J[:mi] = -G
+            for i in range(n_c):
+                for s in range(4):
+                    J[mi + 4 * i + s, 4 * s] = 2 * (v[4 * s] - centres[i, s, 0]); J[mi + 4 * i + s, 4 * s + 2] = 2 * (v[4 * s + 2] - centres[i, s, 1])
+                    J[mi + 4 * i + s, -1] = 1.0
+            for q, j in enumerate(vel):
+                J[mi + 4 * n_c + q, j] = -1.0; J[mi + 4 * n_c + 8 + q, j] = 1.0
+            return J
+        c = cons(x)
+        assert len(z) == len(c) and c.min() > -1e-9 and z.min() >= 0
+        assert np.abs(Q @ x + f + A.T @ y - jac(x).T @ z).max() < 1e-8          # stationarity
+        assert np.abs(A @ x - b).max() < 1e-8 and np.abs(c * z).max() < 1e-8    # feasibility, complementarity
+        res = minimize(lambda v: 0.5 * v @ Q @ v + f @ v, r["x_qp"], jac=lambda v: Q @ v + f, method="SLSQP",
+                       constraints=[dict(type="eq", fun=lambda v: A @ v - b, jac=lambda v: A), dict(type="ineq", fun=cons, jac=jac)],
+                       options=dict(ftol=1e-15, maxiter=500))
+        fo = 0.5 * x @ Q @ x + f @ x
+        if cons(res.x).min() > -1e-6 and abs(res.fun - fo) <= 2e-6 * max(1.0, abs(fo)):
+            assert np.abs(res.x[:24] - x[:24]).max() < 1e-3   # SLSQP's accuracy on these flatter problems; the objectives agree to 2e-6
+            n_ok += 1
+        else:
+            assert res.fun > fo - 1e-6 * max(1.0, abs(fo)) or cons(res.x).min() < -1e-6   # scipy never finds a better feasible point
+    assert n_ok >= 8
