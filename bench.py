@@ -286,6 +286,16 @@ def main():
             lat[name] = 1e3 * statistics.median(ts[20:])
             lat[name.replace("p50_", "kernel_").replace("_ms", "_kernel_ms")] = s2.last_kernel_ms()
             s2.close()
+        # the same two latencies through the C++ host class (examples/team_cycles --latency; built by __graft_entry__.build())
+        exe = os.path.join(ROOT, "examples", "team_cycles")
+        if os.path.exists(exe):
+            try:
+                import subprocess
+                r = subprocess.run([exe, "--latency", "300"], capture_output=True, text=True, timeout=120)
+                if r.returncode == 0:
+                    lat["cpp_host"] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as e:  # the C++ example is optional for the bench line
+                lat["cpp_host"] = {"error": str(e)[:200]}
         line["latency"] = lat
         print(json.dumps(line))
     if dist is not None:

@@ -6,16 +6,22 @@
 //   build:  g++ -std=c++17 -O2 -Iinclude examples/team_cycles.cpp -Lsrb-cbf-nmpc_b200/lib -lcbfnmpc -Wl,-rpath,'$ORIGIN/../srb-cbf-nmpc_b200/lib' -o examples/team_cycles
 //   run  :  examples/team_cycles [cycles] [use_snopt 0/1]      prints one line per agent and cycle:
 //           cycle agent status kkt slack X[16] alpha[20]
+//           examples/team_cycles --latency [cycles]           one JSON line: p50 / p90 wall time of MPC_dist_gpu::run_NMPC() (one
+//           agent, QP -> NLP) and of MPC_dist_gpu_team::run_NMPC() (4 agents in one launch) over `cycles` receding-horizon cycles
+#include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <memory>
 #include "mpc_dist_gpu.hpp"
 
 int main(int argc, char** argv) {
   using namespace cbfnmpc;
-  const int cycles = argc > 1 ? atoi(argv[1]) : 3;
-  const bool nlp = argc > 2 ? atoi(argv[2]) != 0 : true;
+  const bool latency = argc > 1 && std::strcmp(argv[1], "--latency") == 0;
+  const int cycles = latency ? (argc > 2 ? atoi(argv[2]) : 300) : (argc > 1 ? atoi(argv[1]) : 3);
+  const bool nlp = latency ? true : (argc > 2 ? atoi(argv[2]) != 0 : true);
   const int ncols = 4 * (cycles + 1);
   const double Ts = 0.043, goal[2] = {10.0, 0.0};
   const double Pstart[8] = {0.0, 0.0, 0.0, -0.9, -1.0, 0.0, -1.0, -0.9};            // SIM4:862
@@ -48,6 +54,11 @@ int main(int argc, char** argv) {
       ptrs.push_back(&m);
     }
     MPC_dist_gpu_team team(&ctx, ptrs);
+    std::vector<double> t_one, t_team;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
     for (int c = 0; c < cycles; c++) {
       for (int a = 0; a < 4; a++) {
         int ind[4] = {1, 1, 1, 1};
@@ -59,16 +70,36 @@ int main(int argc, char** argv) {
         agents[a ^ 1]->get_lastState(other);  // pairwise neighbour exchange, shared_structs.hpp:63,94
         agents[a]->updateState(q[a], dq[a], ind, toe, other);
       }
+      if (latency) {  // agent 0 alone (B = 1) on a copy of its state, then the team launch that advances everybody
+        MPC_dist_gpu solo = *agents[0];
+        auto t0 = now(); solo.run_NMPC(); auto t1 = now();
+        t_one.push_back(ms(t0, t1));
+      }
+      auto t0 = now();
       team.run_NMPC();
+      auto t1 = now();
+      t_team.push_back(ms(t0, t1));
       for (int a = 0; a < 4; a++) {
         double X[16], al[20];
         agents[a]->get_MPCsol(X); agents[a]->get_alphaCOM(al);
-        printf("%d %d %d %.3e %.17g", c, a, agents[a]->status(), agents[a]->kkt(), agents[a]->slack());
-        for (int i = 0; i < 16; i++) printf(" %.17g", X[i]);
-        for (int i = 0; i < 20; i++) printf(" %.17g", al[i]);
-        printf("\n");
+        if (!latency) {
+          printf("%d %d %d %.3e %.17g", c, a, agents[a]->status(), agents[a]->kkt(), agents[a]->slack());
+          for (int i = 0; i < 16; i++) printf(" %.17g", X[i]);
+          for (int i = 0; i < 20; i++) printf(" %.17g", al[i]);
+          printf("\n");
+        }
         q[a][0] = X[12]; dq[a][0] = X[13]; q[a][1] = X[14]; dq[a][1] = X[15];  // end of the planned domain
       }
+    }
+    if (latency) {
+      auto pct = [](std::vector<double> v, double p) {
+        if (v.size() > 20) v.erase(v.begin(), v.begin() + 10);  // warm-up cycles
+        std::sort(v.begin(), v.end());
+        return v[(size_t)(p * (v.size() - 1))];
+      };
+      printf("{\"host\": \"C++ (include/mpc_dist_gpu.hpp)\", \"cycles\": %d, \"single_solve_p50_ms\": %.4f, \"single_solve_p90_ms\": %.4f, "
+             "\"team4_cycle_p50_ms\": %.4f, \"team4_cycle_p90_ms\": %.4f}\n",
+             cycles, pct(t_one, 0.5), pct(t_one, 0.9), pct(t_team, 0.5), pct(t_team, 0.9));
     }
   } catch (const Error& e) {
     fprintf(stderr, "cbfnmpc error %d: %s\n", e.code, e.what());
