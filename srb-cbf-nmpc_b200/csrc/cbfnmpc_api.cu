@@ -524,7 +524,8 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
   // the earlier ones and the downloads of the earlier ones overlap the solves of the later ones.  A range's kernel does not
   // get faster with fewer instances (it is latency-bound), so the kernels simply run side by side; what stays on the critical
   // path is the upload of everything, one kernel and the download of the last range.  All uploads and launches are enqueued
-  // before any download.  Measured on B200 with 4096 instances: 1 / 2 / 4 / 8 ranges -> 0.932 / 0.890 / 0.880 / 0.903 ms.
+  // before any download.  Measured on B200 with 4096 instances: 1 / 2 / 4 / 8 ranges -> 0.932 / 0.890 / 0.880 / 0.903 ms
+  // (4 ranges shrinking by 0.556, so that in theory they finish together: 0.874 - 1.0 ms, worse and erratic).
   // Device staging (pitch B): x0 4 | xdes 16 | feet 8 | alpha_buf 4 | obs 2K rows of doubles; outputs X 16 | U 8 | lam 16 |
   // slack 1 | x_qp 24 | alpha 20 | abuf_next 4 | kkt 1.
   const int nch = B >= 4096 ? 4 : (B >= 1024 ? 2 : 1);
