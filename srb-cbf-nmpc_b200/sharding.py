@@ -61,6 +61,12 @@ def exchange_state_other(dist, q, dq, device=None):
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return mine.new_zeros((0, mine.shape[1]))
     world, rank = dist.get_world_size(), dist.get_rank()
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine)
-    return torch.cat([parts[r] for r in range(world) if r != rank]).contiguous()
+    allb = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+    try:
+        dist.all_gather_into_tensor(allb, mine)           # one collective into one buffer
+    except (RuntimeError, NotImplementedError, AttributeError):
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        allb = torch.stack(parts)
+    others = torch.tensor([r for r in range(world) if r != rank], dtype=torch.long, device=mine.device)
+    return allb.index_select(0, others).reshape(4 * (world - 1), mine.shape[1])
