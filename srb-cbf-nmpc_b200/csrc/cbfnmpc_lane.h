@@ -91,7 +91,9 @@ struct LaneDims {
   static constexpr int F_REP = F_GFY + 11;     // the right-hand side and the refinement check instead of being spilled
   static constexpr int F_XDES = F_REP + 4;     // desired state of this lane's stage (4)
   static constexpr int F_XIN = F_XDES + 4;     // measured state x_0 (4; used by lane 0)
-  static constexpr int NPRIV = F_XIN + 4;
+  static constexpr int F_PERS = F_XIN + 4;     // values that live across iterations and are read once or twice per iteration:
+                                               // tau, dw_last, theta_max, theta_min, ad_prev (out of the register file)
+  static constexpr int NPRIV = F_PERS + 5;
 };
 constexpr int LANE_NPRIV = LaneDims<4>::NPRIV;
 
@@ -870,7 +872,13 @@ struct LaneSolver {
   //                          G, EV = scratch weights (e(x) at the top of the iteration; refinement)
   // The distance slot SD is one-sided: its "hi" half is inert (s_hi = 1, z_hi = 0, never updated).
   // =============================================================================================================
-  double mu, tau, dw_last, theta_max, theta_min, ad_prev; int nl_it, nfilt; bool first_ic;
+  double mu; int nl_it, nfilt; bool first_ic;
+  // tau, dw_last, theta_max, theta_min, ad_prev: private columns F_PERS + 0 .. 4
+#define PERS_TAU pr(d::F_PERS + 0)
+#define PERS_DWLAST pr(d::F_PERS + 1)
+#define PERS_THMAX pr(d::F_PERS + 2)
+#define PERS_THMIN pr(d::F_PERS + 3)
+#define PERS_ADPREV pr(d::F_PERS + 4)
 
   // e(x) of every slot -> field fld
   LMEM void nlp_scatter_e(int fld, const double* xp) {
@@ -929,7 +937,7 @@ struct LaneSolver {
     LUNR for (int i = 0; i < 4; i++) x.pi[i] = 0.0;
     x.nu[0] = x.nu[1] = 0.0; x.eta = 0.0;
     filter_reset();
-    mu = P.mu_init; tau = fmax(P.tau_min, 1.0 - mu); dw_last = 0.0; first_ic = true; nfilt = 0; nl_it = 0; ad_prev = 0.0;
+    mu = P.mu_init; PERS_TAU = fmax(P.tau_min, 1.0 - mu); PERS_DWLAST = 0.0; first_ic = true; nfilt = 0; nl_it = 0; PERS_ADPREV = 0.0;
     nlp_scatter_e(d::N_EV, xp);
     bool interior = chk == 0.0;
     LSLOTS for (int s = 0; s < nsn; s++) {
@@ -946,7 +954,7 @@ struct LaneSolver {
       double r = fabs(reta) + fabs(rnu[0]) + fabs(rnu[1]);
       LUNR for (int i = 0; i < 4; i++) r += fabs(rpi[i]);
       const double th0 = g_sum(g, r);
-      theta_max = 1e4 * fmax(1.0, th0); theta_min = 1e-4 * fmax(1.0, th0);
+      PERS_THMAX = 1e4 * fmax(1.0, th0); PERS_THMIN = 1e-4 * fmax(1.0, th0);
     }
     info.status = 1; info.nlp_iters = 0;
     if (!g_all(g, interior)) { info.status = 4; info.kkt = CBF_INF; return true; }
@@ -968,7 +976,7 @@ struct LaneSolver {
       int zhw = 0;          // running maximum of the multipliers' high words (z >= 0; a NaN shows up as a huge value)
       bool spos = true;     // every slack positive
       szmin = 1e300; szmax = 0.0;
-      const double iks = 1.0 / P.kappa_sigma, adp = ad_prev;
+      const double iks = 1.0 / P.kappa_sigma, adp = PERS_ADPREV;
       nlp_scatter_e(d::N_EV, xp);
       LSLOTS for (int s = 0; s < nsn; s++) {
         const bool vhi = s != d::SD;
@@ -1032,7 +1040,7 @@ struct LaneSolver {
       const double emu = fmax(fmax(szmax - mu, mu - szmin), fmax(e_d, e_p));
       if (emu <= P.kappa_eps * mu && mu > P.tol / 10.0) {
         mu = fmax(P.tol / 10.0, fmin(P.kappa_mu * mu, mu * sqrt(mu)));
-        tau = fmax(P.tau_min, 1.0 - mu);
+        PERS_TAU = fmax(P.tau_min, 1.0 - mu);
         filter_reset();
       } else break;
     }
@@ -1053,6 +1061,7 @@ struct LaneSolver {
     double dw = 0.0;
     LaneBorder bf;
     {
+      const double dw_last = PERS_DWLAST;
       bool ok = false;
       for (;;) {
         info.n_fact++;
@@ -1064,7 +1073,7 @@ struct LaneSolver {
         if (dw > P.dw_max) break;
       }
       if (!ok) { info.status = 3; return true; }
-      if (dw > 0.0) { dw_last = dw; first_ic = false; }
+      if (dw > 0.0) { PERS_DWLAST = dw; first_ic = false; }
     }
     // ---- solve, then iterative refinement on the unreduced Newton system (one instance of the solve for both)
     KV dd;
@@ -1172,6 +1181,7 @@ struct LaneSolver {
         dsum += de * rlo - (vhi ? de * rhi : 0.0);
       }
       rp = g_max(g, rp); rdm = g_max(g, rdm);
+      const double tau = PERS_TAU;
       a_pmax = (rp > tau) ? tau / rp : 1.0; a_dmax = (rdm > tau) ? tau / rdm : 1.0;
       LANE_LOG(dw); LANE_LOG(a_pmax); LANE_LOG(a_dmax);
       LANE_DBG("   dw %.1e apmax %.3e admax %.3e ddl %.3e\n", dw, a_pmax, a_dmax, dd.dl);
@@ -1210,9 +1220,9 @@ struct LaneSolver {
         const double tht = (1.0 - alpha) * th;
         const double dph = alpha * gdx + 0.5 * alpha * alpha * dQd - mu * dlog;
         const double pht = ph + dph;
-        if (tht <= theta_max && filter_ok(tht, pht)) {
+        if (tht <= PERS_THMAX && filter_ok(tht, pht)) {
           const bool sw = dphi < 0.0 && alpha * (dphi * dphi) > th;  // switching condition, s_phi = 2, s_theta = 1, delta = 1
-          if (th <= theta_min && sw) {
+          if (th <= PERS_THMIN && sw) {
             if (dph - 10.0 * CBF_EPSM * fabs(ph) <= P.eta_phi * alpha * dphi) { accepted = true; ftype = true; }
           } else if (tht <= (1.0 - P.gamma_theta) * th || dph - 10.0 * CBF_EPSM * fabs(ph) <= -P.gamma_phi * th) {
             accepted = true; ftype = false;
@@ -1231,7 +1241,7 @@ struct LaneSolver {
     LUNR for (int i = 0; i < C; i++) x.lm[i] += alpha * dd.lm[i];
     LUNR for (int a = 0; a < 2; a++) { x.us[a] += alpha * dd.us[a]; x.nu[a] += alpha * dd.nu[a]; }
     x.dl += alpha * dd.dl; x.eta += alpha * dd.eta;
-    ad_prev = a_dmax;
+    PERS_ADPREV = a_dmax;
     nl_it = it + 1;
     return false;
   }
