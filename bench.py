@@ -148,6 +148,17 @@ def main():
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line)); return
 
+    # the CUDA library normally travels prebuilt with the repo; a fresh checkout builds it once (local rank 0), the others wait
+    lib_path = os.path.join(ROOT, "srb-cbf-nmpc_b200", "lib", "libcbfnmpc.so")
+    if not os.path.exists(lib_path):
+        if local == 0:
+            import __graft_entry__ as g
+            g.build()
+        else:
+            t_wait = time.time()
+            while not os.path.exists(lib_path) and time.time() - t_wait < 900:
+                time.sleep(1.0)
+            time.sleep(2.0)
     import torch
     import srb_cbf_nmpc_b200 as pkg
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
