@@ -1029,6 +1029,18 @@ struct LaneSolver {
       info.kkt = E0; info.nlp_iters = it;
       LANE_LOG(1000.0 + it); LANE_LOG(mu); LANE_LOG(E0); LANE_LOG(e_d); LANE_LOG(e_p); LANE_LOG(e_c); LANE_LOG(th);
       LANE_DBG("it %d mu %.2e E0 %.3e ed %.2e ep %.2e ec %.2e zmax %.2e th %.2e\n", it, mu, E0, e_d, e_p, e_c, zmax, th);
+#ifdef CBF_TRACE
+      {
+        double tx = 0, tu = 0, tl = 0, gx = 0, jx = 0, py = 0, ny = 0;
+        LUNR for (int i = 0; i < 4; i++) { tx = fmax(tx, fabs(gfy.xs[i] - jz.xs[i])); gx = fmax(gx, fabs(gfy.xs[i])); jx = fmax(jx, fabs(jz.xs[i])); py = fmax(py, fabs(x.pi[i])); }
+        LUNR for (int a = 0; a < 2; a++) { tu = fmax(tu, fabs(gfy.us[a] - jz.us[a])); ny = fmax(ny, fabs(x.nu[a])); }
+        LUNR for (int i = 0; i < C; i++) tl = fmax(tl, fabs(gfy.lm[i] - jz.lm[i]));
+        tx = g_max(g, tx); tu = g_max(g, tu); tl = g_max(g, tl); gx = g_max(g, gx); jx = g_max(g, jx); py = g_max(g, py); ny = g_max(g, ny);
+        const double ey = g_max(g, fabs(x.eta)), xm = g_max(g, fmax(fabs(x.xs[0]), fabs(x.xs[2])));
+        LANE_DBG("   ed parts: x %.2e u %.2e lam %.2e dl %.2e | |gfy.x| %.2e |jz.x| %.2e |pi| %.2e |nu| %.2e |eta| %.2e |pos| %.2e szmin %.2e szmax %.2e\n",
+                 tx, tu, tl, fabs(gfy.dl - wd), gx, jx, py, ny, ey, xm, szmin, szmax);
+      }
+#endif
       // converged: KKT error <= tol, or <= acc_tol once the barrier parameter sits at its floor (there the dual residual is at
       // its FP64 noise level, s = mu / z ~ 1e-13 for active rows, and may hover just above tol for many iterations)
       if (E0 <= P.tol || (mu <= P.tol / 10.0 && E0 <= P.acc_tol)) { info.status = 0; return true; }
@@ -1205,12 +1217,14 @@ struct LaneSolver {
       // phi(x + alpha dx) - phi(x) = alpha g'dx + 1/2 alpha^2 dx'Q dx - mu sum log(s_t / s)
       double prod = 1.0, prod2 = 1.0;
       bool pos = true;
+      double smin = 1.0;
       const double aq = alpha * alpha * quad;
       LSLOTS for (int s = 0; s < nsn; s++) {
         const bool vhi = s != d::SD;
         const double et = alpha * pr(d::N_C + s) + ((s == d::SD) ? aq : 0.0);
         const double sl = pr(d::N_SLO + s) + et, sh = vhi ? pr(d::N_SHI + s) - et : 1.0;
         pos = pos && (sl > 0.0) && (sh > 0.0);
+        smin = fmin(smin, fmin(sl, sh));
         const double t = (sl * pr(d::N_A + s)) * (vhi ? sh * pr(d::N_B + s) : 1.0);
         if (s & 1) prod *= t; else prod2 *= t;
       }
@@ -1228,6 +1242,25 @@ struct LaneSolver {
             accepted = true; ftype = false;
           }
         }
+      }
+      if (accepted && g_any(g, smin < 1e-12)) {
+        // The test above works on the linearised slacks s + alpha ds.  Late in the run tau = 1 - mu lets an active slack shrink
+        // by a factor mu in one step, to below the rounding (~1e-15) of the O(1) positions it is computed from.  When a trial
+        // slack is that small, the slacks that pass A will compute at x + alpha dx -- by the same expressions, from the same
+        // bits -- must be positive too (the oracle's line search evaluates c(x + alpha dx) itself); otherwise the step is halved.
+        KV xt;
+        LUNR for (int i = 0; i < 4; i++) { xt.xs[i] = x.xs[i] + alpha * dd.xs[i]; xt.lm[i] = (i < C) ? x.lm[i] + alpha * dd.lm[i] : 0.0; }
+        LUNR for (int a = 0; a < 2; a++) xt.us[a] = x.us[a] + alpha * dd.us[a];
+        xt.dl = x.dl + alpha * dd.dl;
+        double xp2[4]; prev_state(xt, false, xp2);
+        l_scatter<C, true>(g, pr, d::N_EV, xt, xp2);
+        { const double a_ = xt.xs[0] - c.ox, b_ = xt.xs[2] - c.oy; pr(d::N_EV + d::SD) = a_ * a_ + b_ * b_ + xt.dl; }
+        bool okp = true;
+        LSLOTS for (int s = 0; s < nsn; s++) {
+          const double e = pr(d::N_EV + s);
+          okp = okp && (e - l_slot_lo<C, true>(P, s) > 0.0) && ((s != d::SD) ? (l_slot_hi<C, true>(P, s) - e > 0.0) : true);
+        }
+        accepted = g_all(g, okp);
       }
       if (accepted) break;
       alpha *= 0.5;

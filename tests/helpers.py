@@ -70,3 +70,33 @@ def degenerate_instances(base):
         if what == "obs": e[:] = val
         out.append(("%s=%g" % (what, val), bad, (a, b, c, d, e)))
     return out
+
+
+def wide_fuzz_instances(n, seed=2025):
+    """Instances well outside the cfg-3 distribution: feet scaled 0.5-1.5 and perturbed by 8 cm, start velocities sometimes
+    outside the velocity box (the NLP then has no interior), reference speeds up to 0.34 m/s in any direction with noisy
+    positions, 1-20 obstacles at 0.2-6 m, sometimes one almost on top of the robot."""
+    rng = np.random.default_rng(seed)
+    nominal = np.array([[0.183, 0.183, -0.183, -0.183], [-0.132, 0.132, -0.132, 0.132]])
+    out = []
+    for _ in range(n):
+        p0 = np.array([rng.uniform(-3, 12), rng.uniform(-4, 4)])
+        v0 = rng.uniform(-0.349, 0.349, 2) if rng.random() < 0.7 else rng.uniform(-0.6, 0.6, 2)
+        x0 = np.array([p0[0], v0[0], p0[1], v0[1]])
+        t = rng.uniform(0, 2 * np.pi)
+        vref = rng.uniform(0.0, 0.34) * np.array([np.cos(t), np.sin(t)])
+        xdes = np.zeros(16)
+        for k in range(4):
+            xdes[4 * k:4 * k + 4] = [p0[0] + vref[0] * 0.043 * (k + 1) + rng.normal(0, 0.02), vref[0],
+                                     p0[1] + vref[1] * 0.043 * (k + 1) + rng.normal(0, 0.02), vref[1]]
+        u = rng.random()
+        contact = [1, 1, 1, 1] if u < 0.4 else ([0, 1, 1, 0] if u < 0.7 else [1, 0, 0, 1])
+        feet = p0[:, None] + nominal * rng.uniform(0.5, 1.5) + rng.uniform(-0.08, 0.08, (2, 4))
+        K = int(rng.integers(1, 21))
+        r = rng.uniform(0.2, 6.0, K); a = rng.uniform(0, 2 * np.pi, K)
+        obs = p0[:, None] + np.stack([r * np.cos(a), r * np.sin(a)])
+        if rng.random() < 0.3:
+            obs[:, 0] = p0 + rng.uniform(-0.3, 0.3, 2)
+        obs = np.hstack([obs, np.repeat(obs[:, -1:], 20 - K, 1)])
+        out.append((x0, xdes, feet, contact, obs))
+    return out

@@ -153,6 +153,29 @@ def test_reflection_equivariance_at_full_size(pkg):
     s.close()
 
 
+def test_wide_fuzz_against_the_oracle(pkg):
+    """Far outside the cfg-3 distribution (helpers.wide_fuzz_instances: scaled and perturbed feet, start velocities outside the
+    velocity box, obstacles on top of the robot, 1-20 obstacle columns): same statuses, same answers."""
+    from srb_cbf_nmpc_b200 import capi
+    insts = H.wide_fuzz_instances(2048, seed=77)
+    s = pkg.BatchSolver(device=0, max_batch=2048, max_obs=20)
+    out = s.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP_NLP)
+    ref = H.oracle_batch(insts, mode=1, nthreads=16)
+    c = H.compare(out, ref)
+    assert c["status_equal"].mean() >= 0.995, (c["status_equal"].mean(), np.bincount(out["status"][0], minlength=5), np.bincount(ref["status"], minlength=5))
+    assert c["worst"] < 1e-6
+    assert (out["status"][0] == 0).sum() > 1000 and (out["status"][0] == 1).sum() == 0
+    outq = s.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP)
+    refq = H.oracle_batch(insts, mode=0, nthreads=16)
+    both = (outq["status"][0] == 0) & (refq["status"] == 0)
+    # QP mode: a few 4-foot instances stall just above iSWIFT's dual-residual limit (DESIGN.md section 3, known limit) and
+    # come back as MAXITER with X right to 1e-6; everything else agrees
+    assert (outq["status"][0] == refq["status"]).mean() >= 0.99 and both.sum() > 1700
+    assert np.abs(outq["X"].T - refq["X"])[both].max() < 1e-7
+    assert np.abs(outq["X"].T - refq["X"])[refq["status"] == 0].max() < 1e-5
+    s.close()
+
+
 def test_cfg4_size_65536_instances(pkg):
     """BASELINE config 4's instance count (65536; reference-faithful mode: the agents of a team are independent NLPs) in one
     launch on one GPU, checked against the oracle on every instance."""
