@@ -85,6 +85,7 @@ def cpu_baseline(insts, seconds_target=12.0, nthreads=None):
     import oracle as O
     nthreads = nthreads or os.cpu_count() or 1
     O.build()
+    built = O.use_native_build(True)    # gcc -O3 -march=native on this host; reference core: -O3 -march=x86-64-v3
     ref_qp = O.use_reference_qp(True)   # QP stage by the reference's own iSWIFT core when oracle/_ref travelled with the repo
 
     def run(sub):
@@ -102,12 +103,13 @@ def cpu_baseline(insts, seconds_target=12.0, nthreads=None):
         d1, c1 = run(insts)
         dt += d1; conv += c1; n += len(insts); passes += 1
     O.use_reference_qp(False)
+    O.use_native_build(False)
     qp_desc = ("QP stage = the reference's own iSWIFT C core compiled from /root/reference (oracle/_ref)" if ref_qp
                else "QP stage = dense restatement of iSWIFT (oracle/_ref absent)")
-    return {"value": conv / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
+    return {"value": conv / dt, "unit": UNIT, "cores": nthreads, "per_core": conv / dt / nthreads, "kind": "port",
             "sample": "%d passes over the %d cfg-3 instances (%d solves, %d converged) in %.1f s wall on %d host threads; %s, NLP stage = "
-                      "IPM-F restatement of oracle/cbfnmpc_oracle.c (the reference's ifopt+SNOPT stage cannot be built offline)"
-                      % (passes, len(insts), n, conv, dt, nthreads, qp_desc),
+                      "IPM-F restatement of oracle/cbfnmpc_oracle.c (the reference's ifopt+SNOPT stage cannot be built offline); builds: %s"
+                      % (passes, len(insts), n, conv, dt, nthreads, qp_desc, json.dumps(built)),
             "n": n, "seconds": dt, "converged": conv}
 
 
@@ -144,7 +146,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * sum(x["seconds"] for x in vals) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "per_core": v / last["cores"], "kind": "port", "sample": last["sample"]},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line)); return
 
@@ -227,28 +229,47 @@ def main():
     # ---- end to end through the host-buffer C-ABI call, pinned host memory
     n_in = sum(capi.IN_F64.values()) + 2 * K_obs
     hin = torch.empty((n_in, B), dtype=torch.float64).pin_memory(); hct = torch.empty((4, B), dtype=torch.int32).pin_memory()
-    hout = torch.empty((90, B), dtype=torch.float64).pin_memory(); houti = torch.empty((4, B), dtype=torch.int32).pin_memory()
-    hact = torch.empty((2, B), dtype=torch.int64).pin_memory()
+    # Outputs of the e2e leg = what a caller of MPC_dist reads every cycle: X (get_MPCsol), U, slack, alpha (get_alphaCOM), the next
+    # alpha buffer, the KKT error, status and the two iteration counts.  lam, x_qp, active and n_fact are diagnostics: NULL here, so
+    # the library does not download them (the kernel still computes them into its staging).
+    E2E_ROWS = 50
+    hout = torch.empty((E2E_ROWS, B), dtype=torch.float64).pin_memory(); houti = torch.empty((3, B), dtype=torch.int32).pin_memory()
     hn, ho = hin.numpy(), hout.numpy()
-    dh = {"x0": hn[0:4], "xdes": hn[4:20], "feet_xy": hn[20:28], "alpha_buf": hn[28:32], "obs_xy": hn[32:32 + 2 * K_obs], "contact": hct.numpy(), "n_obs": K_obs}
+
+    def in_views(hn, hc):
+        return {"x0": hn[0:4], "xdes": hn[4:20], "feet_xy": hn[20:28], "alpha_buf": hn[28:32], "obs_xy": hn[32:32 + 2 * K_obs], "contact": hc, "n_obs": K_obs}
+
+    def out_views(ho, hi):
+        return {"X": ho[0:16], "U": ho[16:24], "slack": ho[24:25], "alpha": ho[25:45], "alpha_buf_next": ho[45:49], "kkt": ho[49:50],
+                "status": hi[0:1], "qp_iters": hi[1:2], "nlp_iters": hi[2:3], "lam": None, "x_qp": None, "n_fact": None, "active": None}
+    dh = in_views(hn, hct.numpy())
     for k in ("x0", "xdes", "feet_xy", "alpha_buf", "obs_xy", "contact"):
         dh[k][...] = d[k]
-    oh = {"X": ho[0:16], "U": ho[16:24], "lam": ho[24:40], "slack": ho[40:41], "x_qp": ho[41:65], "alpha": ho[65:85], "alpha_buf_next": ho[85:89],
-          "kkt": ho[89:90], "status": houti.numpy()[0:1], "qp_iters": houti.numpy()[1:2], "nlp_iters": houti.numpy()[2:3], "n_fact": houti.numpy()[3:4],
-          "active": hact.numpy().view(np.uint64)}
-    for _ in range(3):
-        solver.solve_host(dh, mode=capi.MODE_QP_NLP, out=oh)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        solver.solve_host(dh, mode=capi.MODE_QP_NLP, out=oh)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
+    oh = out_views(ho, houti.numpy())
+
+    def time_host_calls(dh, oh):
+        for _ in range(3):
+            solver.solve_host(dh, mode=capi.MODE_QP_NLP, out=oh)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            solver.solve_host(dh, mode=capi.MODE_QP_NLP, out=oh)
+        torch.cuda.synchronize(dev)
+        return time.perf_counter() - t0
+    e2e_s = time_host_calls(dh, oh)
     conv_e2e = int((oh["status"][0] == 0).sum())
+    # the same call with ordinary (pageable) numpy arrays: what a host program gets when it does not pin its buffers
+    pn, pc = np.empty((n_in, B)), np.empty((4, B), np.int32)
+    dp_ = in_views(pn, pc)
+    for k in ("x0", "xdes", "feet_xy", "alpha_buf", "obs_xy", "contact"):
+        dp_[k][...] = d[k]
+    op_ = out_views(np.empty((E2E_ROWS, B)), np.empty((3, B), np.int32))
+    e2e_pageable_s = time_host_calls(dp_, op_)
+    conv_e2e_p = int((op_["status"][0] == 0).sum())
     clocks = sampler.stop(mark0, None)
     # ---- reduce over ranks: max time, summed work
-    (total_ms_max, e2e_s_max), (conv_all, conv_e2e_all, flops_all, launches_all, inst_all) = SH.reduce_over_ranks(
-        dist, [total_ms, e2e_s], [conv, conv_e2e, flops, launches, B], dev)
+    (total_ms_max, e2e_s_max, e2e_p_s_max), (conv_all, conv_e2e_all, flops_all, launches_all, inst_all, conv_e2e_p_all) = SH.reduce_over_ranks(
+        dist, [total_ms, e2e_s, e2e_pageable_s], [conv, conv_e2e, flops, launches, B, conv_e2e_p], dev)
     fp64_peak = solver.fp64_peak_tflops()
     bi, bo = algorithmic_bytes(K_obs)
     if rank == 0:
@@ -272,7 +293,10 @@ def main():
                 "converged_fraction": conv_all / inst_all, "instances": int(inst_all), "kkt_max_converged": float(kkt[status == 0].max()) if conv else None,
                 "mean_iters": {"qp": float(qp_it.mean()), "nlp": float(nl_it[status == 0].mean()) if conv else None},
                 "e2e": {"value": conv_e2e_all / (e2e_s_max / args.steps), "unit": UNIT, "h2d_bytes_per_step": int((n_in * 8 + 16) * B),
-                        "d2h_bytes_per_step": int((90 * 8 + 16 + 16) * B), "ms_per_step": 1e3 * e2e_s_max / args.steps},
+                        "d2h_bytes_per_step": int((E2E_ROWS * 8 + 12) * B), "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                        "host_memory": "pinned; outputs X, U, slack, alpha, alpha_buf_next, kkt, status, qp_iters, nlp_iters (lam, x_qp, active, n_fact: NULL, not downloaded)"},
+                "e2e_pageable": {"value": conv_e2e_p_all / (e2e_p_s_max / args.steps), "unit": UNIT, "ms_per_step": 1e3 * e2e_p_s_max / args.steps,
+                                 "host_memory": "pageable numpy arrays, same call and outputs"},
                 "gpu_launches": int(launches_all),
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
@@ -284,7 +308,7 @@ def main():
                                   "peak_source": "DFMA microbenchmark run in this process (cbfnmpc_measure_fp64_peak)",
                                   "algorithmic_flops_per_iter": F_ITER}}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(S.cfg3_instances(B, seed=20251018 + 3000)).items() if k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(S.cfg3_instances(B, seed=20251018 + 3000)).items() if k in ("value", "unit", "cores", "per_core", "kind", "sample")}
         # p50 single-solve latency (cfg 1) and one 4-agent team cycle (cfg 2), host-buffer call
         lat = {}
         for name, ins in (("p50_single_solve_ms", [S.cfg1_instance(4)]), ("p50_team4_cycle_ms", S.cfg2_team())):

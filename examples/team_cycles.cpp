@@ -6,6 +6,8 @@
 //   build:  g++ -std=c++17 -O2 -Iinclude examples/team_cycles.cpp -Lsrb-cbf-nmpc_b200/lib -lcbfnmpc -Wl,-rpath,'$ORIGIN/../srb-cbf-nmpc_b200/lib' -o examples/team_cycles
 //   run  :  examples/team_cycles [cycles] [use_snopt 0/1]      prints one line per agent and cycle:
 //           cycle agent status kkt slack X[16] alpha[20]
+//           examples/team_cycles --nlptuple [cycles]          every cycle also solved through the dense nlpTuple boundary
+//                                                             (cbfnmpc_pack_dense + cbfnmpc_solve_dense_nlptuple); one JSON line
 //           examples/team_cycles --latency [cycles]           one JSON line: p50 / p90 wall time of MPC_dist_gpu::run_NMPC() (one
 //           agent, QP -> NLP) and of MPC_dist_gpu_team::run_NMPC() (4 agents in one launch) over `cycles` receding-horizon cycles
 #include <algorithm>
@@ -20,8 +22,11 @@
 int main(int argc, char** argv) {
   using namespace cbfnmpc;
   const bool latency = argc > 1 && std::strcmp(argv[1], "--latency") == 0;
-  const int cycles = latency ? (argc > 2 ? atoi(argv[2]) : 300) : (argc > 1 ? atoi(argv[1]) : 3);
-  const bool nlp = latency ? true : (argc > 2 ? atoi(argv[2]) != 0 : true);
+  const bool check_tuple = argc > 1 && std::strcmp(argv[1], "--nlptuple") == 0;
+  const int cycles = (latency || check_tuple) ? (argc > 2 ? atoi(argv[2]) : (latency ? 300 : 4)) : (argc > 1 ? atoi(argv[1]) : 3);
+  const bool nlp = (latency || check_tuple) ? true : (argc > 2 ? atoi(argv[2]) != 0 : true);
+  double tuple_x[4][41] = {{0}}, tuple_worst = 0.0; int tuple_status[4] = {0}, tuple_status_mismatch = 0;
+  const bool tuple_four[2] = {true, false};  // stance: 4 feet during the first two cycles, a diagonal pair afterwards
   const int ncols = 4 * (cycles + 1);
   const double Ts = 0.043, goal[2] = {10.0, 0.0};
   const double Pstart[8] = {0.0, 0.0, 0.0, -0.9, -1.0, 0.0, -1.0, -0.9};            // SIM4:862
@@ -70,6 +75,12 @@ int main(int argc, char** argv) {
         agents[a ^ 1]->get_lastState(other);  // pairwise neighbour exchange, shared_structs.hpp:63,94
         agents[a]->updateState(q[a], dq[a], ind, toe, other);
       }
+      if (check_tuple) {  // every agent's cycle once more through the dense nlpTuple boundary, before the team launch advances it
+        for (int a = 0; a < 4; a++) {
+          double xt[41]; tuple_status[a] = agents[a]->solve_via_nlptuple(xt);
+          std::memcpy(tuple_x[a], xt, sizeof xt);
+        }
+      }
       if (latency) {  // agent 0 alone (B = 1) on a copy of its state, then the team launch that advances everybody
         MPC_dist_gpu solo = *agents[0];
         auto t0 = now(); solo.run_NMPC(); auto t1 = now();
@@ -82,15 +93,26 @@ int main(int argc, char** argv) {
       for (int a = 0; a < 4; a++) {
         double X[16], al[20];
         agents[a]->get_MPCsol(X); agents[a]->get_alphaCOM(al);
-        if (!latency) {
+        if (!latency && !check_tuple) {
           printf("%d %d %d %.3e %.17g", c, a, agents[a]->status(), agents[a]->kkt(), agents[a]->slack());
           for (int i = 0; i < 16; i++) printf(" %.17g", X[i]);
           for (int i = 0; i < 20; i++) printf(" %.17g", al[i]);
           printf("\n");
         }
+        if (check_tuple) {
+          double Uu[8]; agents[a]->get_MPCinputs(Uu);
+          double dmax = std::fabs(tuple_x[a][24 + 4 * (tuple_four[c >= 2 ? 1 : 0] ? 4 : 2)] - agents[a]->slack());
+          for (int i = 0; i < 16; i++) dmax = std::max(dmax, std::fabs(tuple_x[a][i] - X[i]));
+          for (int i = 0; i < 8; i++) dmax = std::max(dmax, std::fabs(tuple_x[a][16 + i] - Uu[i]));
+          tuple_worst = std::max(tuple_worst, dmax);
+          if (tuple_status[a] != agents[a]->status()) tuple_status_mismatch++;
+        }
         q[a][0] = X[12]; dq[a][0] = X[13]; q[a][1] = X[14]; dq[a][1] = X[15];  // end of the planned domain
       }
     }
+    if (check_tuple)
+      printf("{\"nlptuple_check\": {\"cycles\": %d, \"agents\": 4, \"max_abs_diff_X_U_slack\": %.3e, \"status_mismatches\": %d}}\n", cycles, tuple_worst,
+             tuple_status_mismatch);
     if (latency) {
       auto pct = [](std::vector<double> v, double p) {
         if (v.size() > 20) v.erase(v.begin(), v.begin() + 10);  // warm-up cycles

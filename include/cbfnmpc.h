@@ -129,6 +129,13 @@ int cbfnmpc_solve_dense_nlptuple(cbfnmpc_ctx *ctx, int nv, int p, int mi, const 
                                  const double *x0_start, const double obs[2], int mode_nlp, double *x_out, int *status,
                                  double *kkt);
 
+/* The dense matrices MPC_dist::run_NMPC builds for one agent (src/MPC_dist.cpp:164-321), from the compact inputs and the
+ * context's gains: host code, no device work.  F = stance matrix 2 x c (row-major, leading dimension 4), c in {2, 4};
+ * outputs column-major: Q nv x nv, f nv, Aeq 28 x nv, beq 28, G (60+8c) x nv, h 60+8c, nv = 25 + 4c.  Lets a host program
+ * (or a test) produce an nlpTuple for cbfnmpc_solve_dense_nlptuple without Eigen. */
+int cbfnmpc_pack_dense(const cbfnmpc_ctx *ctx, const double x0[4], const double xdes[16], const double *F, int c, double *Q,
+                       double *f, double *Aeq, double *beq, double *G, double *h);
+
 /* Raw per-cycle inputs, exactly what MPC_dist::updateState receives plus the object's own state, for B agents.
  * Structure-of-arrays, batch index fastest; device pointers.
  *   q, dq        [nq][B]   generalised coordinates / velocities (nq = 18 in the reference; rows 0 and 1 are read)   MPC_dist.cpp:226-229

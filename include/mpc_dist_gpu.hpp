@@ -21,6 +21,7 @@
 // does sequentially).
 #pragma once
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -122,11 +123,54 @@ class MPC_dist_gpu {
     return status_;
   }
 
+  // The same cycle through the reference's dense boundary type (nlpTuple, pack_nlp_data.h:11-29; MPC_dist.cpp:348 and :403-421):
+  // dense Q, f, Aeq, beq, G, h built as MPC_dist.cpp:164-321 does, the QP solved from them (iswiftQp_e's role), the closest
+  // obstacle chosen (:371-396), then the NLP started at the QP optimum.  x_out = the decision vector [X16 | U8 | Lambda 4c | delta].
+  // Does not touch the object's state (no gaitDomain_ increment, no Bezier fit): a cross-check of run_NMPC(), not a second path.
+  int solve_via_nlptuple(double* x_out /* 25 + 4c */, double* kkt_out = nullptr) {
+    Batch b(1, n_obs());
+    const int gd = gaitDomain_;
+    double toe_keep[12]; std::memcpy(toe_keep, toePos_, sizeof toe_keep);
+    pack(b, 0);
+    std::memcpy(toePos_, toe_keep, sizeof toe_keep); gaitDomain_ = gd;
+    int csum = 0; for (int i = 0; i < 4; i++) csum += b.contact[i];
+    const int c = csum == 4 ? 4 : 2, nv = 25 + 4 * c, p = 28, mi = 60 + 8 * c;
+    double F[8] = {0};
+    for (int a = 0; a < 2; a++) {
+      if (c == 4) { for (int i = 0; i < 4; i++) F[4 * a + i] = b.feet[4 * a + i]; }
+      else if (b.contact[0] == 0) { F[4 * a] = b.feet[4 * a + 1]; F[4 * a + 1] = b.feet[4 * a + 2]; }   // MPC_dist.cpp:1238-1252
+      else { F[4 * a] = b.feet[4 * a]; F[4 * a + 1] = b.feet[4 * a + 3]; }
+    }
+    std::vector<double> Q((size_t)nv * nv), f(nv), A((size_t)p * nv), be(p), G((size_t)mi * nv), h(mi), xq(nv), x0s(nv);
+    int rc = cbfnmpc_pack_dense(ctx_->get(), b.x0.data(), b.xdes.data(), F, c, Q.data(), f.data(), A.data(), be.data(), G.data(), h.data());
+    if (rc != CBFNMPC_OK) throw Error(rc, std::string("cbfnmpc_pack_dense: ") + cbfnmpc_last_error());
+    int st = -1; double kk = 0.0;
+    rc = cbfnmpc_solve_dense_nlptuple(ctx_->get(), nv, p, mi, Q.data(), f.data(), A.data(), be.data(), G.data(), h.data(), nullptr, nullptr, 0,
+                                      xq.data(), &st, &kk);
+    if (rc != CBFNMPC_OK) throw Error(rc, std::string("cbfnmpc_solve_dense_nlptuple (QP): ") + cbfnmpc_last_error());
+    if (use_snopt) {
+      double best = 1000.0, obs[2] = {b.obs[0], b.obs[b.K]};   // first strict minimum of the Euclidean distance, :371-396
+      for (int k = 0; k < b.K; k++) {
+        const double dx = b.x0[0] - b.obs[k], dy = b.x0[2] - b.obs[b.K + k], d = std::sqrt(dx * dx + dy * dy);
+        if (d < best) { best = d; obs[0] = b.obs[k]; obs[1] = b.obs[b.K + k]; }
+      }
+      x0s = xq;
+      rc = cbfnmpc_solve_dense_nlptuple(ctx_->get(), nv, p, mi, Q.data(), f.data(), A.data(), be.data(), G.data(), h.data(), x0s.data(), obs, 1,
+                                        xq.data(), &st, &kk);
+      if (rc != CBFNMPC_OK) throw Error(rc, std::string("cbfnmpc_solve_dense_nlptuple (NLP): ") + cbfnmpc_last_error());
+    }
+    std::memcpy(x_out, xq.data(), sizeof(double) * nv);
+    if (kkt_out) *kkt_out = kk;
+    return st;
+  }
+
   void get_alphaCOM(double out[20]) const {  // 4x5, column-major like the Eigen::MatrixXd the reference returns
     for (int r = 0; r < 4; r++) for (int j = 0; j < 5; j++) out[4 * j + r] = alpha_[5 * r + j];
   }
   void get_MPCsol(double out[16]) const { std::memcpy(out, X_, sizeof X_); }
   void get_MPCinputs(double out[8]) const { std::memcpy(out, U_, sizeof U_); }
+  // mpc_state_e_u_eventbased_ (MPC_dist.hpp:63, cpp:438-440): the x-components of the 4 centre-of-pressure inputs only
+  void get_MPCsol_u(double out[4]) const { for (int k = 0; k < 4; k++) out[k] = U_[2 * k]; }
   void get_QPsol(double out[24]) const { std::memcpy(out, xqp_, sizeof xqp_); }
   void get_lastState(double out[4]) const { out[0] = q_[0]; out[1] = q_[1]; out[2] = dq_[0]; out[3] = dq_[1]; }  // :1272-1276
   int getDomain() const { return domain_; }

@@ -42,15 +42,46 @@ def build(force=False):
     stale = (not os.path.exists(lib)) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in src)
     ref = os.path.join(HERE, "_ref", "libiswift_ref.so")
     need_ref = os.path.isdir("/root/reference/optimization/iSWIFT/src") and (
-        force or not os.path.exists(ref) or os.path.getmtime(os.path.join(HERE, "ref_driver.c")) > os.path.getmtime(ref))
+        force or not os.path.exists(ref) or not os.path.exists(ref.replace(".so", "_v3.so"))
+        or os.path.getmtime(os.path.join(HERE, "ref_driver.c")) > os.path.getmtime(ref))
     if force or stale:
         subprocess.check_call(["make", "-s", "-C", HERE, "liborc.so"] + (["-B"] if force else []))
     if need_ref:
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
 
 
+def _cpu_flags():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def build_native():
+    """CPU-baseline build of the oracle for THIS machine: gcc -O3 -march=native, compiled where it runs (the
+    GPU box's host differs from the build container, so this file never travels: _native/ is git- and gpurun-ignored).
+    The parity tests keep liborc.so (-march=x86-64-v2: no FMA contraction, the same bits everywhere).  Returns the path or None."""
+    import hashlib
+    flags = " ".join(sorted(_cpu_flags()))
+    tag = hashlib.sha1(flags.encode()).hexdigest()[:10]
+    out = os.path.join(HERE, "_native", "liborc_native_%s.so" % tag)
+    src = os.path.join(HERE, "cbfnmpc_oracle.c")
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    try:
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-std=gnu99", "-w", "-shared", "-o", out, src, "-lm", "-lpthread"])
+        return out
+    except Exception:
+        return None
+
+
 _lib = None
 _ref = None
+_native = False
 dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
@@ -59,7 +90,11 @@ def lib():
     global _lib
     if _lib is None:
         build()
-        _lib = C.CDLL(os.path.join(HERE, "liborc.so"))
+        path = os.path.join(HERE, "liborc.so")
+        if _native:
+            path = build_native() or path
+        _lib = C.CDLL(path)
+        _lib.build_path = path
         _lib.orc_default_options.argtypes = [C.POINTER(Options)]
         _lib.orc_default_gains.argtypes = [C.POINTER(Gains)]
         _lib.orc_lip_discrete.argtypes = [C.POINTER(Gains), dp, dp]
@@ -83,12 +118,24 @@ def ref_lib():
     if _ref is None:
         build()
         path = os.path.join(HERE, "_ref", "libiswift_ref.so")
+        v3 = os.path.join(HERE, "_ref", "libiswift_ref_v3.so")
+        if _native and os.path.exists(v3) and {"avx2", "fma", "bmi2"} <= _cpu_flags():
+            path = v3   # the reference core built -O3 -march=x86-64-v3 (its sources do not travel, so it cannot be -march=native on the box)
         if not os.path.exists(path):
             return None
         _ref = C.CDLL(path)
         _ref.iswift_ref_solve_dense.argtypes = [C.c_int] * 3 + [dp] * 6 + [dp, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _ref.iswift_ref_solve_ccs.argtypes = [C.c_int] * 3 + [ip, ip, dp] * 3 + [dp, dp, dp, C.c_double, ip, dp, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return _ref
+
+
+def use_native_build(on=True):
+    """bench.py's CPU baseline only: switch this module to the -O3 -march=native build of the oracle (and the -march=x86-64-v3
+    build of the reference core).  Drops the loaded handles; returns a description of what is now in use."""
+    global _lib, _ref, _native
+    _native = bool(on); _lib = None; _ref = None
+    L = lib(); r = ref_lib()
+    return {"oracle": os.path.relpath(L.build_path, HERE), "iswift": os.path.basename(r._name) if r is not None else None}
 
 
 def use_reference_qp(on=True):

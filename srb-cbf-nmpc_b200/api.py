@@ -48,6 +48,7 @@ def load():
     L.cbfnmpc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.cbfnmpc_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.cbfnmpc_solve_dense_nlptuple.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.cbfnmpc_pack_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
     _lib = L
     return L
 
@@ -56,7 +57,7 @@ EXPORTS = ["cbfnmpc_version", "cbfnmpc_last_error", "cbfnmpc_default_gains", "cb
            "cbfnmpc_destroy", "cbfnmpc_set_gains", "cbfnmpc_set_options", "cbfnmpc_solve_batch", "cbfnmpc_solve_batch_host",
            "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak",
            "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle", "cbfnmpc_closed_loop", "cbfnmpc_generate_reference", "cbfnmpc_qp_dense_batch",
-           "cbfnmpc_team_states"]
+           "cbfnmpc_team_states", "cbfnmpc_pack_dense"]
 
 
 def default_gains():
@@ -179,6 +180,18 @@ class BatchSolver:
     def fp64_peak_tflops(self):
         t = C.c_double(0); self._ck(self.L.cbfnmpc_measure_fp64_peak(self.ctx, C.byref(t))); return t.value
 
+    def pack_dense(self, x0, xdes, F):
+        """The dense nlpTuple matrices of MPC_dist.cpp:164-321 for one agent (host code; F = 2 x c stance matrix)."""
+        F = np.asarray(F, float); c = F.shape[1]
+        nv, p, mi = 25 + 4 * c, 28, 60 + 8 * c
+        F4 = np.zeros((2, 4)); F4[:, :c] = F
+        x0 = np.ascontiguousarray(x0, dtype=np.float64); xdes = np.ascontiguousarray(xdes, dtype=np.float64)
+        Q = np.zeros((nv, nv), order="F"); f = np.zeros(nv); A = np.zeros((p, nv), order="F"); b = np.zeros(p)
+        G = np.zeros((mi, nv), order="F"); h = np.zeros(mi)
+        self._ck(self.L.cbfnmpc_pack_dense(self.ctx, x0.ctypes.data, xdes.ctypes.data, F4.ctypes.data, c, Q.ctypes.data, f.ctypes.data,
+                                           A.ctypes.data, b.ctypes.data, G.ctypes.data, h.ctypes.data))
+        return Q, f, A, b, G, h
+
     def solve_dense_nlptuple(self, Q, f, Aeq, beq, G, h, x0_start, obs, mode_nlp=True):
         """Reference layout: Eigen column-major matrices of pack_nlp_data.h:11-29."""
         nv, p, mi = Q.shape[0], Aeq.shape[0], G.shape[0]
@@ -191,5 +204,7 @@ class BatchSolver:
                                                  Gc.ctypes.data, hv.ctypes.data, xs.ctypes.data, ob.ctypes.data, int(mode_nlp),
                                                  xo.ctypes.data, C.byref(st), C.byref(kk))
         if rc != 0:
-            raise CbfNmpcError("cbfnmpc_solve_dense_nlptuple failed (%d): %s" % (rc, self.L.cbfnmpc_last_error().decode()))
+            e = CbfNmpcError("cbfnmpc_solve_dense_nlptuple failed (%d): %s" % (rc, self.L.cbfnmpc_last_error().decode()))
+            e.code = rc
+            raise e
         return xo, st.value, kk.value

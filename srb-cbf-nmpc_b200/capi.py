@@ -73,16 +73,34 @@ def alloc_out(B):
     return o
 
 
+def _check(name, a, dtype, rows, B):
+    """The C ABI reads raw pointers: a wrong dtype, a transposed view or a short array would be read as garbage."""
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("%s must be a C-contiguous numpy array of %s" % (name, np.dtype(dtype).name))
+    if a.size != rows * B:
+        raise ValueError("%s must hold %d x %d elements ([field][B]), has %d" % (name, rows, B, a.size))
+
+
 def in_struct(d):
     s = In()
-    for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy", "alpha_buf"):
+    B = d["x0"].shape[1]; K = int(d["n_obs"])
+    rows = dict(IN_F64, obs_xy=2 * K)
+    for k in ("x0", "xdes", "feet_xy", "obs_xy", "alpha_buf"):
+        _check(k, d[k], np.float64, rows[k], B)
         setattr(s, k, d[k].ctypes.data)
-    s.n_obs = int(d["n_obs"])
+    _check("contact", d["contact"], np.int32, 4, B)
+    s.contact = d["contact"].ctypes.data
+    s.n_obs = K
     return s
 
 
-def out_struct(o):
+def out_struct(o, B=None):
+    """Arrays that are None (or absent) are passed as NULL: the library then skips them (and their download)."""
     s = Out()
-    for k in o:
-        setattr(s, k, o[k].ctypes.data)
+    for k, v in o.items():
+        if v is None:
+            continue
+        dt, rows = (np.float64, OUT_F64[k]) if k in OUT_F64 else ((np.int32, 1) if k in OUT_I32 else (np.uint64, 2))
+        _check(k, v, dt, rows, v.size // rows if B is None else B)
+        setattr(s, k, v.ctypes.data)
     return s

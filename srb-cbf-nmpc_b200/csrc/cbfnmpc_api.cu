@@ -100,7 +100,12 @@ __global__ void __launch_bounds__(256) cbfnmpc_pack_kernel(const __grid_constant
   const cbfnmpc_raw_in& r = io.r;
   // measured LIP state (q[0], dq[0], q[1], dq[1])                                      src/MPC_dist.cpp:226-229
   io.x0[b] = r.q[b]; io.x0[B + b] = r.dq[b]; io.x0[2 * B + b] = r.q[B + b]; io.x0[3 * B + b] = r.dq[B + b];
-  const int g = r.gait_domain[b], a = r.agent_id[b], t = r.team[b];
+  const int g = r.gait_domain[b];
+  int a = r.agent_id[b], t = r.team[b];
+  // a team or agent index outside the arrays is bad input: nothing is read out of bounds and the instance is answered
+  // with status 4 (the contact pattern written below classifies as invalid)
+  const bool bad_index = t < 0 || t >= r.n_teams || a < 0 || a >= 4;
+  if (bad_index) { a = 0; t = 0; }
   // desired trajectory: columns [4 g, 4 g + 4) of rows 2a, 2a+1 of Pr_refined_ / Prd_refined_, vectorised column-major
   // as [x, xd, y, yd] x 4                                                               :713-718, :766-780
   const double* Pr = r.Pr_refined + (size_t)t * 8 * r.ref_cols;
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(256) cbfnmpc_pack_kernel(const __grid_constant
   for (int i = 0; i < 4; i++) {
     io.feet[(size_t)i * B + b] = (g <= 1) ? fpx[i] + ax : r.toe_pos[(size_t)(3 * i) * B + b];
     io.feet[(size_t)(4 + i) * B + b] = (g <= 1) ? fpy[i] + ay : r.toe_pos[(size_t)(3 * i + 1) * B + b];
-    io.contact[(size_t)i * B + b] = r.contact[(size_t)i * B + b];
+    io.contact[(size_t)i * B + b] = bad_index ? -1 : r.contact[(size_t)i * B + b];
   }
   // real obstacles of the agent's team (Pobs_real, 2 x n_obs column-major) -> x of all obstacles, then y          :371-396
   const double* Po = r.Pobs_real + (size_t)t * 2 * r.n_obs;
@@ -161,7 +166,7 @@ struct RollIO {
   cbfnmpc_world_state w;
   const double *X, *abuf_next, *agent_initial, *Pobs_real;
   const int *status, *team;
-  int B, n_obs, cycle;
+  int B, n_obs, cycle, n_teams;
   double fail_radius;
 };
 __global__ void __launch_bounds__(256) cbfnmpc_rollout_kernel(const __grid_constant__ RollIO io) {
@@ -169,9 +174,11 @@ __global__ void __launch_bounds__(256) cbfnmpc_rollout_kernel(const __grid_const
   if (b >= io.B) return;
   const size_t B = (size_t)io.B;
   if (io.status[b] != CBFNMPC_ST_CONVERGED) io.w.n_not_converged[b] += 1;
+  if (io.status[b] == CBFNMPC_ST_BADINPUT) return;  // nothing was solved (X, alpha_buf_next are not written): the world stays where it is
   // updateDistance_to_fail (src/MPC_dist.cpp:21-40) at the 4 grid points of this domain
   if (io.w.success[b]) {
-    const double* Po = io.Pobs_real + (size_t)io.team[b] * 2 * io.n_obs;
+    const int tm = io.team[b] < 0 ? 0 : (io.team[b] >= io.n_teams ? io.n_teams - 1 : io.team[b]);
+    const double* Po = io.Pobs_real + (size_t)tm * 2 * io.n_obs;
     bool failed = false;
     for (int k = 0; k < 4 && !failed; k++) {
       const double px = io.X[(size_t)(4 * k) * B + b], py = io.X[(size_t)(4 * k + 2) * B + b];
@@ -234,11 +241,14 @@ __global__ void __launch_bounds__(128) cbfnmpc_refgen_kernel(int n_teams, const 
   double* prd = Prd + (size_t)tc * 8 * ncols + 2 * k;
   for (int i = 0; i <= loop; i++) {
     // output column c holds column c + 2 of the decimated history: step 40 (c + 2) for c + 2 < ncols, else step c + 2
-    int c = -1;
-    if (i % dec == 0 && i / dec < ncols) c = i / dec - 2;
-    if (i == ncols || i == ncols + 1) c = i - 2;
-    if (valid && c >= 0 && c < ncols) {
-      pr[8 * (size_t)c] = x; pr[8 * (size_t)c + 1] = y; prd[8 * (size_t)c] = vx; prd[8 * (size_t)c + 1] = vy;
+    // (a step can be both: the two stores are independent)
+    const int c1 = (i % dec == 0 && i / dec < ncols) ? i / dec - 2 : -1;
+    const int c2 = (i == ncols || i == ncols + 1) ? i - 2 : -1;
+    if (valid && c1 >= 0 && c1 < ncols) {
+      pr[8 * (size_t)c1] = x; pr[8 * (size_t)c1 + 1] = y; prd[8 * (size_t)c1] = vx; prd[8 * (size_t)c1 + 1] = vy;
+    }
+    if (valid && c2 >= 0 && c2 < ncols) {
+      pr[8 * (size_t)c2] = x; pr[8 * (size_t)c2 + 1] = y; prd[8 * (size_t)c2] = vx; prd[8 * (size_t)c2 + 1] = vy;
     }
     if (i == loop) break;
     const double gx = x - goal_x, gy = y - goal_y;
@@ -301,6 +311,11 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 #define CBF_MAX_CHUNKS 4
+// Rows of the device output staging ([row][B] doubles).  What a caller of MPC_dist reads every cycle (X, U, slack, alpha, next
+// alpha buffer, KKT error) comes first and is contiguous, so that a host block laid out the same way comes back in ONE copy per
+// column range; lam and x_qp (diagnostics) follow and are only downloaded when asked for.
+enum { O_X = 0, O_U = 16, O_SLACK = 24, O_ALPHA = 25, O_ABUF = 45, O_KKT = 49, O_LAM = 50, O_XQP = 66, O_ROWS = 90 };
+#define CBF_REFGEN_MAX_OBS 440
 struct cbfnmpc_ctx {
   int device, max_batch, max_obs;
   cbfnmpc_gains gains;
@@ -309,6 +324,9 @@ struct cbfnmpc_ctx {
   cudaStream_t stream;
   cudaStream_t cstream[CBF_MAX_CHUNKS];  // host-buffer calls: chunk k of the batch travels on cstream[k] (cstream[0] == stream)
   cudaEvent_t ev0, ev1;
+  cudaEvent_t ev_last;       // recorded after the last launch that used the context's class lists / staging buffers
+  cudaStream_t last_stream;  // the stream it was recorded on (a call on another stream waits for it first)
+  bool have_last;
   bool timed;
   int sm_count;
   long long launches;
@@ -356,6 +374,7 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
   c->cstream[0] = c->stream;
   for (int k = 1; k < CBF_MAX_CHUNKS; k++) CK(cudaStreamCreateWithFlags(&c->cstream[k], cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+  CK(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming)); c->have_last = false; c->last_stream = c->stream;
   CK(cudaMalloc(&c->d_in, sizeof(double) * (size_t)(32 + 2 * max_obs) * max_batch));
   CK(cudaMalloc(&c->d_contact, sizeof(int) * 4 * (size_t)max_batch));
   CK(cudaMalloc(&c->d_out, sizeof(double) * 90 * (size_t)max_batch));
@@ -373,6 +392,7 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
   // function attributes are per device: set them for every context, not once per process
   CK(cudaFuncSetAttribute(cbfnmpc_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LANE_NPRIV * LANE_NT * sizeof(double))));
   CK(cudaFuncSetAttribute(cbfnmpc_qpdense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QD_WARPS * sizeof(QDenseWS))));
+  CK(cudaFuncSetAttribute(cbfnmpc_refgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * CBF_REFGEN_MAX_OBS)));
   *out = c;
   return CBFNMPC_OK;
 }
@@ -380,10 +400,11 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
 void cbfnmpc_destroy(cbfnmpc_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  for (int k = 0; k < CBF_MAX_CHUNKS; k++) cudaStreamSynchronize(c->cstream[k]);
+  if (c->have_last) cudaEventSynchronize(c->ev_last);  // the caller's stream of the last call
   cudaFree(c->d_in); cudaFree(c->d_contact); cudaFree(c->d_out); cudaFree(c->d_outi); cudaFree(c->d_active); cudaFree(c->d_xstart); cudaFree(c->d_perm);
   cudaFree(c->d_sin); cudaFree(c->d_sout); cudaFreeHost(c->h_sin); cudaFreeHost(c->h_sout);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_last);
   for (int k = 1; k < CBF_MAX_CHUNKS; k++) cudaStreamDestroy(c->cstream[k]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -404,6 +425,19 @@ int cbfnmpc_set_options(cbfnmpc_ctx* c, const cbfnmpc_options* o) {
     return fail(CBFNMPC_ERR_ARG, "cbfnmpc_set_options: bad option");
   c->opts = *o;
   host_fill_kparams(&c->gains, &c->opts, &c->kp);
+  return CBFNMPC_OK;
+}
+
+// One context owns one set of class lists and staging buffers, so its calls must not overlap each other.  Calls on the same
+// stream are ordered by the stream; a call on a different stream than the previous one first waits for the previous call's work
+// (an event, no host synchronisation).
+static int ctx_enter(cbfnmpc_ctx* c, cudaStream_t st) {
+  if (c->have_last && c->last_stream != st) CK(cudaStreamWaitEvent(st, c->ev_last, 0));
+  return CBFNMPC_OK;
+}
+static int ctx_leave(cbfnmpc_ctx* c, cudaStream_t st) {
+  CK(cudaEventRecord(c->ev_last, st));
+  c->last_stream = st; c->have_last = true;
   return CBFNMPC_OK;
 }
 
@@ -463,8 +497,8 @@ static int solve_small(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, co
   cbfnmpc_in din = {d, d + 4 * Bs, d + 20 * Bs, di, d + 32 * Bs, K, d + 28 * Bs};
   double* o = (double*)c->d_sout;
   cbfnmpc_out dout;
-  dout.X = o; dout.U = o + 16 * Bs; dout.lam = o + 24 * Bs; dout.slack = o + 40 * Bs; dout.x_qp = o + 41 * Bs;
-  dout.alpha = o + 65 * Bs; dout.alpha_buf_next = o + 85 * Bs; dout.kkt = o + 89 * Bs;
+  dout.X = o + O_X * Bs; dout.U = o + O_U * Bs; dout.lam = o + O_LAM * Bs; dout.slack = o + O_SLACK * Bs; dout.x_qp = o + O_XQP * Bs;
+  dout.alpha = o + O_ALPHA * Bs; dout.alpha_buf_next = o + O_ABUF * Bs; dout.kkt = o + O_KKT * Bs;
   dout.active = (uint64_t*)(o + 90 * Bs);
   int32_t* doi = (int32_t*)(o + 92 * Bs);
   dout.status = doi; dout.qp_iters = doi + Bs; dout.nlp_iters = doi + 2 * Bs; dout.n_fact = doi + 3 * Bs;
@@ -477,12 +511,12 @@ static int solve_small(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, co
   int32_t* hoi = (int32_t*)(ho + 92 * Bs);
   for (int k = 0; k < nbad; k++) {  // lane_store_bad
     const int b = bad[k];
-    hoi[b] = 4; hoi[Bs + b] = 0; hoi[2 * Bs + b] = 0; hoi[3 * Bs + b] = 0; ho[89 * Bs + b] = 0.0; ho[40 * Bs + b] = 0.0;
+    hoi[b] = 4; hoi[Bs + b] = 0; hoi[2 * Bs + b] = 0; hoi[3 * Bs + b] = 0; ho[O_KKT * Bs + b] = 0.0; ho[O_SLACK * Bs + b] = 0.0;
     ha[b] = 0; ha[Bs + b] = 0;
   }
   struct OSeg { double* h; size_t row, rows; };
-  const OSeg os[8] = {{out->X, 0, 16}, {out->U, 16, 8}, {out->lam, 24, 16}, {out->slack, 40, 1}, {out->x_qp, 41, 24}, {out->alpha, 65, 20},
-                      {out->alpha_buf_next, 85, 4}, {out->kkt, 89, 1}};
+  const OSeg os[8] = {{out->X, O_X, 16}, {out->U, O_U, 8}, {out->slack, O_SLACK, 1}, {out->alpha, O_ALPHA, 20}, {out->alpha_buf_next, O_ABUF, 4},
+                      {out->kkt, O_KKT, 1}, {out->lam, O_LAM, 16}, {out->x_qp, O_XQP, 24}};
   for (int i = 0; i < 8; i++) if (os[i].h) memcpy(os[i].h, ho + os[i].row * Bs, sizeof(double) * os[i].rows * Bs);
   int32_t* const oi[4] = {out->status, out->qp_iters, out->nlp_iters, out->n_fact};
   for (int i = 0; i < 4; i++) if (oi[i]) memcpy(oi[i], hoi + (size_t)i * Bs, sizeof(int32_t) * Bs);
@@ -498,7 +532,11 @@ static int launch(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const c
     CK(cudaMalloc(&c->d_perm, sizeof(int) * (2 * (size_t)B + 2 * CBF_MAX_CHUNKS)));
     c->perm_cap = B;
   }
-  return launch_on(c, B, B, mode, in, out, xstart, st, c->d_perm);
+  int rc = ctx_enter(c, st);
+  if (rc) return rc;
+  rc = launch_on(c, B, B, mode, in, out, xstart, st, c->d_perm);
+  if (rc) return rc;
+  return ctx_leave(c, st);
 }
 
 int cbfnmpc_solve_batch(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* in, const cbfnmpc_out* out, void* cuda_stream) {
@@ -518,6 +556,7 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
   const int K = (mode == CBFNMPC_MODE_QP_NLP) ? in->n_obs : 0;
   if (mode == CBFNMPC_MODE_QP_NLP && (!in->obs_xy || K < 1 || K > c->max_obs)) return fail(CBFNMPC_ERR_ARG, "NLP mode needs 1..max_obs obstacles");
   CK(cudaSetDevice(c->device));
+  if (c->have_last) { CK(cudaEventSynchronize(c->ev_last)); c->have_last = false; }  // an earlier asynchronous call on a caller's stream
   if (B <= c->small_cap) return solve_small(c, B, mode, in, out, K);
   const size_t Bs = (size_t)B;
   // Large batches are cut into equal column ranges, each on its own stream: the upload of one range overlaps the solves of
@@ -526,8 +565,8 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
   // path is the upload of everything, one kernel and the download of the last range.  All uploads and launches are enqueued
   // before any download.  Measured on B200 with 4096 instances: 1 / 2 / 4 / 8 ranges -> 0.932 / 0.890 / 0.880 / 0.903 ms
   // (4 ranges shrinking by 0.556, so that in theory they finish together: 0.874 - 1.0 ms, worse and erratic).
-  // Device staging (pitch B): x0 4 | xdes 16 | feet 8 | alpha_buf 4 | obs 2K rows of doubles; outputs X 16 | U 8 | lam 16 |
-  // slack 1 | x_qp 24 | alpha 20 | abuf_next 4 | kkt 1.
+  // Device staging (pitch B): x0 4 | xdes 16 | feet 8 | alpha_buf 4 | obs 2K rows of doubles; outputs in the order of
+  // the O_* rows (X 16 | U 8 | slack 1 | alpha 20 | abuf_next 4 | kkt 1 | lam 16 | x_qp 24).
   const int nch = B >= 4096 ? 4 : (B >= 1024 ? 2 : 1);
   size_t cut[CBF_MAX_CHUNKS + 1];
   for (int k = 0; k <= nch; k++) cut[k] = Bs * k / nch;
@@ -536,8 +575,8 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
   struct Seg { const double* h; size_t row, rows; };
   const Seg segs[5] = {{in->x0, 0, 4}, {in->xdes, 4, 16}, {in->feet_xy, 20, 8}, {in->alpha_buf, 28, 4}, {in->obs_xy, 32, 2 * (size_t)K}};
   struct OSeg { double* h; size_t row, rows; };
-  const OSeg os[8] = {{out->X, 0, 16}, {out->U, 16, 8}, {out->lam, 24, 16}, {out->slack, 40, 1}, {out->x_qp, 41, 24}, {out->alpha, 65, 20},
-                      {out->alpha_buf_next, 85, 4}, {out->kkt, 89, 1}};
+  const OSeg os[8] = {{out->X, O_X, 16}, {out->U, O_U, 8}, {out->slack, O_SLACK, 1}, {out->alpha, O_ALPHA, 20}, {out->alpha_buf_next, O_ABUF, 4},
+                      {out->kkt, O_KKT, 1}, {out->lam, O_LAM, 16}, {out->x_qp, O_XQP, 24}};
   int32_t* const oi[4] = {out->status, out->qp_iters, out->nlp_iters, out->n_fact};
   const size_t pitch = sizeof(double) * Bs;
   for (int k = 0; k < nch; k++) {
@@ -547,7 +586,7 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
     for (int i = 0; i < 5;) {
       if (!segs[i].h || segs[i].rows == 0) { i++; continue; }
       int j = i; size_t rows = segs[i].rows;
-      while (j + 1 < 5 && segs[j + 1].h == segs[j].h + segs[j].rows * Bs && segs[j + 1].rows > 0) { j++; rows += segs[j].rows; }
+      while (j + 1 < 5 && segs[j + 1].h == segs[j].h + segs[j].rows * Bs && segs[j + 1].rows > 0 && segs[j + 1].row == segs[j].row + segs[j].rows) { j++; rows += segs[j].rows; }
       CK(cudaMemcpy2DAsync(d + segs[i].row * Bs + b0, pitch, segs[i].h + b0, pitch, sizeof(double) * n, rows, cudaMemcpyHostToDevice, st));
       i = j + 1;
     }
@@ -555,8 +594,8 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
     CK(cudaMemcpy2DAsync(c->d_contact + b0, sizeof(int) * Bs, in->contact + b0, sizeof(int) * Bs, sizeof(int) * n, 4, cudaMemcpyHostToDevice, st));
     cbfnmpc_in din = {d + b0, d + 4 * Bs + b0, d + 20 * Bs + b0, c->d_contact + b0, d + 32 * Bs + b0, K, d + 28 * Bs + b0};
     cbfnmpc_out dout;
-    dout.X = o + b0; dout.U = o + 16 * Bs + b0; dout.lam = o + 24 * Bs + b0; dout.slack = o + 40 * Bs + b0; dout.x_qp = o + 41 * Bs + b0;
-    dout.alpha = o + 65 * Bs + b0; dout.alpha_buf_next = o + 85 * Bs + b0; dout.kkt = o + 89 * Bs + b0;
+    dout.X = o + O_X * Bs + b0; dout.U = o + O_U * Bs + b0; dout.lam = o + O_LAM * Bs + b0; dout.slack = o + O_SLACK * Bs + b0;
+    dout.x_qp = o + O_XQP * Bs + b0; dout.alpha = o + O_ALPHA * Bs + b0; dout.alpha_buf_next = o + O_ABUF * Bs + b0; dout.kkt = o + O_KKT * Bs + b0;
     dout.status = c->d_outi + b0; dout.qp_iters = c->d_outi + Bs + b0; dout.nlp_iters = c->d_outi + 2 * Bs + b0;
     dout.n_fact = c->d_outi + 3 * Bs + b0;
     dout.active = (uint64_t*)c->d_active + b0;
@@ -569,7 +608,7 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
     for (int i = 0; i < 8;) {
       if (!os[i].h) { i++; continue; }
       int j = i; size_t rows = os[i].rows;
-      while (j + 1 < 8 && os[j + 1].h == os[j].h + os[j].rows * Bs) { j++; rows += os[j].rows; }
+      while (j + 1 < 8 && os[j + 1].h == os[j].h + os[j].rows * Bs && os[j + 1].row == os[j].row + os[j].rows) { j++; rows += os[j].rows; }
       CK(cudaMemcpy2DAsync(os[i].h + b0, pitch, o + os[i].row * Bs + b0, pitch, sizeof(double) * n, rows, cudaMemcpyDeviceToHost, st));
       i = j + 1;
     }
@@ -618,10 +657,12 @@ int cbfnmpc_pack_inputs(cbfnmpc_ctx* c, int B, const cbfnmpc_raw_in* raw, const 
   io.x0 = (double*)packed->x0; io.xdes = (double*)packed->xdes; io.feet = (double*)packed->feet_xy; io.obs = (double*)packed->obs_xy;
   io.contact = (int*)packed->contact;
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  rc = ctx_enter(c, st);
+  if (rc) return rc;
   cbfnmpc_pack_kernel<<<(B + 255) / 256, 256, 0, st>>>(io);
   CK(cudaGetLastError());
   c->launches++;
-  return CBFNMPC_OK;
+  return ctx_leave(c, st);
 }
 
 int cbfnmpc_team_states(cbfnmpc_ctx* c, int B, int team_size, const double* q, const double* dq, double* state_other, void* cuda_stream) {
@@ -669,8 +710,9 @@ int cbfnmpc_qp_dense_batch(cbfnmpc_ctx* c, int B, int n, int p, int m, const dou
 
 int cbfnmpc_generate_reference(cbfnmpc_ctx* c, int n_teams, const double* Pstart, const double* Pobs, int n_obs, double goal_x, double goal_y,
                                int loop, double* Pr, double* Prd, void* cuda_stream) {
-  if (!c || !Pstart || !Pobs || !Pr || !Prd || n_teams < 1 || n_obs < 1 || n_obs > 512 || loop < 120)
-    return fail(CBFNMPC_ERR_ARG, "cbfnmpc_generate_reference: bad argument");
+  // the obstacles of a CTA's 32 teams sit in shared memory: 512 B per obstacle, 227 KB per CTA at most
+  if (!c || !Pstart || !Pobs || !Pr || !Prd || n_teams < 1 || n_obs < 1 || n_obs > CBF_REFGEN_MAX_OBS || loop < 120)
+    return fail(CBFNMPC_ERR_ARG, "cbfnmpc_generate_reference: bad argument (1 <= n_obs <= 440, loop >= 120)");
   CK(cudaSetDevice(c->device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
   cbfnmpc_refgen_kernel<<<(n_teams + 31) / 32, 128, sizeof(double) * 64 * (size_t)n_obs, st>>>(n_teams, Pstart, Pobs, n_obs, goal_x, goal_y, loop, Pr, Prd);
@@ -694,18 +736,18 @@ int cbfnmpc_closed_loop(cbfnmpc_ctx* c, int B, int n_cycles, int mode, const cbf
   double* o = c->d_out;  // staging layout of cbfnmpc_solve_batch_host
   cbfnmpc_out dout;
   memset(&dout, 0, sizeof(dout));
-  dout.X = o; dout.U = o + 16 * Bs; dout.alpha_buf_next = o + 85 * Bs; dout.kkt = o + 89 * Bs; dout.status = c->d_outi;
+  dout.X = o + O_X * Bs; dout.U = o + O_U * Bs; dout.alpha_buf_next = o + O_ABUF * Bs; dout.kkt = o + O_KKT * Bs; dout.status = c->d_outi;
   for (int cyc = 0; cyc < n_cycles; cyc++) {
     int rc = cbfnmpc_run_cycle(c, B, mode, raw, w->alpha_buf, &dout, st);
     if (rc) return rc;
     RollIO io;
     io.w = *w; io.X = dout.X; io.abuf_next = dout.alpha_buf_next; io.agent_initial = raw->agent_initial; io.Pobs_real = raw->Pobs_real;
-    io.status = dout.status; io.team = raw->team; io.B = B; io.n_obs = raw->n_obs; io.cycle = cyc; io.fail_radius = fail_radius;
+    io.status = dout.status; io.team = raw->team; io.B = B; io.n_obs = raw->n_obs; io.cycle = cyc; io.fail_radius = fail_radius; io.n_teams = raw->n_teams;
     cbfnmpc_rollout_kernel<<<(B + 255) / 256, 256, 0, st>>>(io);
     CK(cudaGetLastError());
     c->launches++;
   }
-  return CBFNMPC_OK;
+  return ctx_leave(c, st);
 }
 
 long long cbfnmpc_launch_count(const cbfnmpc_ctx* c) { return c ? c->launches : 0; }
@@ -795,6 +837,17 @@ static bool close_vec(const double* a, const std::vector<double>& b, double tol)
   return true;
 }
 
+int cbfnmpc_pack_dense(const cbfnmpc_ctx* c, const double x0[4], const double xdes[16], const double* F, int cc, double* Q, double* f,
+                       double* Aeq, double* beq, double* G, double* h) {
+  if (!c || !x0 || !xdes || !F || !Q || !f || !Aeq || !beq || !G || !h || (cc != 2 && cc != 4)) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_pack_dense: bad argument");
+  std::vector<double> Q2, f2, A2, b2, G2, h2;
+  host_pack_dense(&c->gains, x0, xdes, F, cc, Q2, f2, A2, b2, G2, h2);
+  memcpy(Q, Q2.data(), sizeof(double) * Q2.size()); memcpy(f, f2.data(), sizeof(double) * f2.size());
+  memcpy(Aeq, A2.data(), sizeof(double) * A2.size()); memcpy(beq, b2.data(), sizeof(double) * b2.size());
+  memcpy(G, G2.data(), sizeof(double) * G2.size()); memcpy(h, h2.data(), sizeof(double) * h2.size());
+  return CBFNMPC_OK;
+}
+
 int cbfnmpc_solve_dense_nlptuple(cbfnmpc_ctx* c, int nv, int p, int mi, const double* Q, const double* f, const double* Aeq,
                                  const double* beq, const double* G, const double* h, const double* x0_start, const double obs[2],
                                  int mode_nlp, double* x_out, int* status, double* kkt) {
@@ -833,6 +886,7 @@ int cbfnmpc_solve_dense_nlptuple(cbfnmpc_ctx* c, int nv, int p, int mi, const do
   for (int i = 0; i < 4; i++) hin[28 + i] = 0.0;
   hin[32] = obs ? obs[0] : 0.0; hin[33] = obs ? obs[1] : 0.0;
   cudaStream_t st = c->stream;
+  if (c->have_last) { CK(cudaEventSynchronize(c->ev_last)); c->have_last = false; }
   CK(cudaMemcpyAsync(c->d_in, hin, sizeof(hin), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(c->d_contact, contact, sizeof(contact), cudaMemcpyHostToDevice, st));
   double xs[41] = {0};
@@ -842,14 +896,14 @@ int cbfnmpc_solve_dense_nlptuple(cbfnmpc_ctx* c, int nv, int p, int mi, const do
   double* o = c->d_out;
   cbfnmpc_out dout;
   memset(&dout, 0, sizeof(dout));
-  dout.X = o; dout.U = o + 16; dout.lam = o + 24; dout.slack = o + 40; dout.kkt = o + 89; dout.status = c->d_outi;
+  dout.X = o + O_X; dout.U = o + O_U; dout.lam = o + O_LAM; dout.slack = o + O_SLACK; dout.kkt = o + O_KKT; dout.status = c->d_outi;
   int rc = launch(c, 1, mode_nlp ? CBFNMPC_MODE_QP_NLP : CBFNMPC_MODE_QP, &din, &dout, mode_nlp ? c->d_xstart : nullptr, st);
   if (rc) return rc;
-  double ho[41]; int hs = 0; double hk = 0;
-  CK(cudaMemcpyAsync(ho, o, sizeof(double) * 41, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(&hk, o + 89, sizeof(double), cudaMemcpyDeviceToHost, st));
+  double hall[O_ROWS]; double ho[41]; int hs = 0; double hk = 0;
+  CK(cudaMemcpyAsync(hall, o, sizeof(double) * O_ROWS, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(&hs, c->d_outi, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  memcpy(ho, hall + O_X, sizeof(double) * 24); memcpy(ho + 24, hall + O_LAM, sizeof(double) * 16); ho[40] = hall[O_SLACK]; hk = hall[O_KKT];
   memcpy(x_out, ho, sizeof(double) * 24);
   for (int i = 0; i < 4 * cc; i++) x_out[24 + i] = ho[24 + i];
   x_out[nv - 1] = ho[40];

@@ -1372,6 +1372,18 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
     if (act) nl_done = S.nlp_iter(P);
   }
   if (!valid) return;
+  if (badin) {  // non-finite inputs: nothing was solved; only the status fields are written (include/cbfnmpc.h), like lane_store_bad
+    if (j == 0) {
+      if (io.status) io.status[b] = 4;
+      if (io.kkt) io.kkt[b] = 0.0;
+      if (io.qp_iters) io.qp_iters[b] = 0;
+      if (io.nlp_iters) io.nlp_iters[b] = 0;
+      if (io.n_fact) io.n_fact[b] = 0;
+      if (io.slack) io.slack[b] = 0.0;
+      if (io.active) { io.active[b] = 0ull; io.active[B + b] = 0ull; }
+    }
+    return;
+  }
   // ---- store
   if (io.X) { LUNR for (int i = 0; i < 4; i++) io.X[(size_t)(4 * j + i) * B + b] = S.x.xs[i]; }
   if (io.U) { LUNR for (int a = 0; a < 2; a++) io.U[(size_t)(2 * j + a) * B + b] = S.x.us[a]; }

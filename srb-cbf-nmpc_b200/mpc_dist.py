@@ -102,6 +102,7 @@ class MPC_dist:
     # ---- getters (include/MPC_dist.hpp:178-181, MPC_dist.cpp:1272-1276)
     def get_alphaCOM(self): return self.alpha_COM_traj_e_.copy()
     def get_MPCsol(self): return self.mpc_state_e_x_eventbased_.reshape(16, 1).copy()
+    def get_MPCsol_u(self): return self.mpc_state_e_u_eventbased_.reshape(4, 1).copy()   # mpc_state_e_u_eventbased_, hpp:63, cpp:438-440 (u_x only)
     def get_lastState(self): return np.array([self.q[0], self.q[1], self.dq[0], self.dq[1]])
     def getDomain(self): return self.domain_
 
