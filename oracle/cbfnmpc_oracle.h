@@ -7,9 +7,13 @@
  *   - QP stage  (orc_qp_mehrotra): restates iSWIFT (optimization/iSWIFT/src/Prime.c:127-230, Auxilary.c);
  *     pinned against the reference's own C core compiled in place (oracle/_ref/libiswift_ref.so) on the
  *     reference's canned QP (include/Matrices_small.h) and on restated MPC QPs -- tests/test_oracle_qp.py.
- *   - NLP stage (orc_nlp_ipm): **parity unpinned**.  The reference solves it with ifopt + SNOPT 7.7.7
- *     (src/MPC_dist.cpp:363-421), neither of which is in /root/reference or installable offline, and the
- *     reference holds no golden vector for it.  The NLP itself (rows, bounds, Jacobian, cost:
+ *   - NLP stage (orc_nlp_ipm): **weakly pinned** (round 2; "parity unpinned" in the strict sense: no runnable reference
+ *     solver).  The reference solves it with ifopt + SNOPT 7.7.7 (src/MPC_dist.cpp:363-421), neither of which is in
+ *     /root/reference or installable offline.  The one NLP output the reference tree holds, the SNOPT print file
+ *     /root/reference/print_file.out, is turned into a fixture by tests/golden/make_snopt_pin.py (inputs reconstructed from
+ *     the logged start point and gradients): on it the QP stage equals SNOPT's logged start point (= iSWIFT's optimum) to
+ *     5e-10 and the NLP stage reaches SNOPT's active set (distance rows 1 and 4) with slack 0.7549 against 0.76247 and
+ *     objective 773.25 against SNOPT's unfinished 803.70 (tests/test_oracle_nlp.py, tests/test_gpu_boundary.py).  The NLP itself (rows, bounds, Jacobian, cost:
  *     include/dec_vars_constr_cost.h:245-438) is restated exactly; the solver is this repo's primal-dual
  *     filter interior-point method (DESIGN.md "IPM-F"), cross-checked against scipy SLSQP/trust-constr in
  *     tests/test_oracle_nlp.py and against the golden vectors minted by tests/golden/make_golden.py.

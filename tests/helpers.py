@@ -100,3 +100,32 @@ def wide_fuzz_instances(n, seed=2025):
         obs = np.hstack([obs, np.repeat(obs[:, -1:], 20 - K, 1)])
         out.append((x0, xdes, feet, contact, obs))
     return out
+
+
+def snopt_pin_checks(x, x_qp, status, kkt, active_dist, fix):
+    """The asserts both the oracle (CPU) and the CUDA path (GPU) must pass on the reference's one recorded NLP run
+    (tests/golden/snopt_print_file.npz, minted by tests/golden/make_snopt_pin.py from /root/reference/print_file.out).
+    x = [X16 | U8 | Lambda16 | delta].  A WEAK pin: the inputs are reconstructed from the print file (x_des to ~1e-9, x_0 to ~1e-7,
+    obstacle = (0.85, -0.65) of src/A1_Sim_4_agents.cpp:872-873 recovered by a fit to 2e-4) and SNOPT's printed point has 5 digits and
+    is not converged (its own exit: "requested accuracy could not be achieved", primal infeasibility 3.1e-4, dual 1.6e3)."""
+    xf = fix["x_final"]
+    # (1) QP stage: SNOPT's derivative check logs its start point = iSWIFT's QP optimum (MPC_dist.cpp:356-361, 403) to 9 digits
+    assert np.abs(x_qp[:24] - fix["x_start"]).max() < 5e-9
+    # (2) NLP stage: converged to the BASELINE bar
+    assert status == 0 and kkt < 1e-8
+    # (3) same active set on the distance rows as SNOPT's final basis: rows 1 and 4 at their bound with positive duals, 2 and 3 free
+    assert list(active_dist) == [True, False, False, True]
+    assert (fix["dist_duals"] > 0).tolist() == [True, False, False, True]
+    # (4) slack within 2e-2 of SNOPT's 0.76247 (measured: 7.6e-3)
+    assert abs(x[40] - xf[40]) < 2e-2
+    # (5) a feasible point whose objective is not above SNOPT's 803.70 (measured: 773.25 -- SNOPT stopped early; scipy SLSQP
+    #     continues from SNOPT's printed point to our answer, tests/test_oracle_nlp.py)
+    w = np.array([300.0] * 12 + [2000.0] * 4 + [0.1] * 8 + [0.0] * 16 + [3000.0])
+    f = np.zeros(41); f[:16] = -w[:16] * fix["xdes"]
+    obj = lambda v: 0.5 * (w * v * v).sum() + f @ v
+    assert abs(obj(xf) - float(fix["objective"])) < 2e-2            # the reconstruction reproduces SNOPT's printed objective
+    assert obj(x) <= float(fix["objective"]) * (1 + 1e-3)
+    # (6) planned positions within 1e-2 m of SNOPT's (measured 6e-3; velocities and inputs differ by up to 0.15: they are what
+    #     SNOPT had not finished optimising)
+    pos = [0, 2, 4, 6, 8, 10, 12, 14]
+    assert np.abs(x[pos] - xf[pos]).max() < 1e-2

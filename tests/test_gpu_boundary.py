@@ -198,3 +198,19 @@ def test_bad_team_or_agent_index_is_bad_input(pkg):
     st = o["status"][0].cpu().numpy()
     assert (st[[4, 5, 6, 7]] == 4).all() and (st[:4] != 4).all(), st
     s.close()
+
+
+def test_weak_pin_against_the_reference_snopt_print_file(pkg):
+    """The reference's one recorded NLP run (print_file.out) through the CUDA path: QP stage equals SNOPT's logged start point
+    (= iSWIFT's optimum) to 5e-9, NLP stage reaches SNOPT's active set with a lower objective (helpers.snopt_pin_checks)."""
+    from srb_cbf_nmpc_b200 import capi
+    fix = np.load(os.path.join(ROOT, "tests", "golden", "snopt_print_file.npz"))
+    inst = (fix["x0"], fix["xdes"], fix["feet"], list(fix["contact"]), fix["obs"].reshape(2, 1))
+    s = pkg.BatchSolver(device=0, max_batch=4, max_obs=4)
+    out = s.solve_host(capi.soa_from_instances([inst]), mode=capi.MODE_QP_NLP)
+    x = np.concatenate([out["X"][:, 0], out["U"][:, 0], out["lam"][:, 0], out["slack"][:, 0]])
+    act = H.active_rows_mask(out, 0, 4)
+    H.snopt_pin_checks(x, out["x_qp"][:, 0], int(out["status"][0, 0]), float(out["kkt"][0, 0]), [(92 + k) in act for k in range(4)], fix)
+    ref = H.oracle_batch([inst], mode=1)
+    assert H.compare(out, ref)["worst"] < 1e-7
+    s.close()

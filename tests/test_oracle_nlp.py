@@ -182,3 +182,36 @@ def test_extended_rows_give_kkt_points_that_scipy_confirms():
         else:
             assert res.fun > fo - 1e-6 * max(1.0, abs(fo)) or cons(res.x).min() < -1e-6   # scipy never finds a better feasible point
     assert n_ok >= 8
+
+
+def test_weak_pin_against_the_reference_snopt_print_file():
+    """The only NLP output the reference tree holds (print_file.out): see helpers.snopt_pin_checks for what is asserted and why the
+    pin is weak.  Also: scipy SLSQP started AT SNOPT's printed point moves on to the oracle's answer, i.e. the printed point is an
+    unfinished iterate of the same NLP, not another local solution."""
+    import helpers as H
+    from scipy.optimize import minimize
+    fix = np.load(os.path.join(GOLD, "snopt_print_file.npz"))
+    obs = fix["obs"]
+    r = O.solve_instance(fix["x0"], fix["xdes"], fix["feet"], fix["contact"], obs.reshape(2, 1), mode=1)
+    mG = 92
+    H.snopt_pin_checks(r["x"], r["x_qp"], r["status"], r["kkt"], r["z"][mG:mG + 4] > r["s"][mG:mG + 4], fix)
+    assert r["qp_iters"] <= 25 and r["qp_flag"] == 0
+    Q, f, A, b, G, h = O.pack_dense(fix["x0"], fix["xdes"], fix["feet"])
+    g = O.default_gains()
+    idx = [1, 5, 9, 13, 3, 7, 11, 15]
+
+    def dist(v): return np.array([(v[4 * k] - obs[0]) ** 2 + (v[4 * k + 2] - obs[1]) ** 2 + v[40] - g.eps_dist for k in range(4)])
+
+    def djac(v):
+        J = np.zeros((4, 41))
+        for k in range(4):
+            J[k, 4 * k] = 2 * (v[4 * k] - obs[0]); J[k, 4 * k + 2] = 2 * (v[4 * k + 2] - obs[1]); J[k, 40] = 1
+        return J
+    cons = [{"type": "eq", "fun": lambda v: A @ v - b, "jac": lambda v: A}, {"type": "ineq", "fun": lambda v: h - G @ v, "jac": lambda v: -G},
+            {"type": "ineq", "fun": dist, "jac": djac}, {"type": "ineq", "fun": lambda v: np.concatenate([g.v_max - v[idx], g.v_max + v[idx]])}]
+    xf = fix["x_final"]
+    assert np.abs(A @ xf - b).max() < 2e-5 and dist(xf).min() > -3.2e-4     # SNOPT's point: feasible to its printed 3.1e-4
+    res = minimize(lambda v: 0.5 * v @ Q @ v + f @ v, xf, jac=lambda v: Q @ v + f, constraints=cons, method="SLSQP",
+                   options=dict(maxiter=500, ftol=1e-14))
+    assert res.fun < float(fix["objective"]) - 25.0                          # 803.70 -> 773.24: SNOPT's point was not a minimum
+    assert np.abs(res.x[:16] - r["x"][:16]).max() < 1e-3 and abs(res.x[40] - r["x"][40]) < 1e-3
