@@ -998,3 +998,8 @@ int orc_solve_batch(const orc_gains *g, const orc_options *o, int B, const doubl
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
   return 0;
 }
+
+/* dense LDL' of this file for cbfnmpc_oracle_ext.c (the extended-mode checker) */
+int orc_bk_factor(int n, double *A, int lda, int *ipiv) { return bk_factor(n, A, lda, ipiv); }
+void orc_bk_inertia(int n, const double *A, int lda, const int *ipiv, int *npos, int *nneg, int *nzero) { bk_inertia(n, A, lda, ipiv, npos, nneg, nzero); }
+void orc_bk_solve(int n, const double *A, int lda, const int *ipiv, double *b) { bk_solve(n, A, lda, ipiv, b); }

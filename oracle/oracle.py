@@ -38,7 +38,7 @@ class Result(C.Structure):
 def build(force=False):
     """Compile liborc.so (always possible) and _ref/libiswift_ref.so (only where /root/reference exists)."""
     lib = os.path.join(HERE, "liborc.so")
-    src = [os.path.join(HERE, f) for f in ("cbfnmpc_oracle.c", "cbfnmpc_oracle.h")]
+    src = [os.path.join(HERE, f) for f in ("cbfnmpc_oracle.c", "cbfnmpc_oracle.h", "cbfnmpc_oracle_ext.c", "cbfnmpc_oracle_ext.h")]
     stale = (not os.path.exists(lib)) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in src)
     ref = os.path.join(HERE, "_ref", "libiswift_ref.so")
     need_ref = os.path.isdir("/root/reference/optimization/iSWIFT/src") and (
@@ -68,12 +68,12 @@ def build_native():
     flags = " ".join(sorted(_cpu_flags()))
     tag = hashlib.sha1(flags.encode()).hexdigest()[:10]
     out = os.path.join(HERE, "_native", "liborc_native_%s.so" % tag)
-    src = os.path.join(HERE, "cbfnmpc_oracle.c")
-    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+    src = os.path.join(HERE, "cbfnmpc_oracle.c"); src2 = os.path.join(HERE, "cbfnmpc_oracle_ext.c")
+    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(src2)):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
     try:
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-std=gnu99", "-w", "-shared", "-o", out, src, "-lm", "-lpthread"])
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-std=gnu99", "-w", "-shared", "-o", out, src, src2, "-lm", "-lpthread"])
         return out
     except Exception:
         return None
@@ -352,3 +352,76 @@ def closed_loop(world, n_cycles, mode=1, fail_radius=0.5, nthreads=8):
             diag = 1 if i in (0, 3) else 0
             w["contact"][i] = np.where(g <= 1, 1, np.where(g & 1, diag, 1 - diag))
     return traj
+
+
+# ------------------------------------------------------------------------------------------------ extended mode
+EXT_NMAX, EXT_KMAX = 8, 19
+EXT_NV_MAX = EXT_NMAX * 10 + 1
+
+
+class ExtResult(C.Structure):
+    _fields_ = [("x", C.c_double * EXT_NV_MAX), ("x_qp", C.c_double * EXT_NV_MAX), ("kkt", C.c_double), ("mu", C.c_double),
+                ("N", C.c_int), ("c", C.c_int), ("nv", C.c_int), ("n_rows", C.c_int), ("status", C.c_int), ("qp_flag", C.c_int),
+                ("qp_iters", C.c_int), ("nlp_iters", C.c_int), ("n_fact", C.c_int), ("n_ls", C.c_int), ("n_bump", C.c_int),
+                ("zd", C.c_double * (EXT_NMAX * EXT_KMAX)), ("sd", C.c_double * (EXT_NMAX * EXT_KMAX))]
+
+
+def _ext_lib():
+    L = lib()
+    if not getattr(L, "_ext_ready", False):
+        vp = C.c_void_p
+        L.orc_ext_pack_dense.argtypes = [C.POINTER(Gains), C.c_int, dp, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp]
+        L.orc_ext_solve.argtypes = [C.POINTER(Gains), C.POINTER(Options), C.c_int, dp, dp, dp, ip, C.c_int, dp, C.c_double, C.c_int,
+                                    C.c_double, vp, C.POINTER(ExtResult)]
+        L.orc_ext_solve_teams.argtypes = [C.POINTER(Gains), C.POINTER(Options), C.c_int, C.c_int, C.c_int, dp, dp, dp, ip, C.c_int, dp,
+                                          C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(ExtResult), ip]
+        L._ext_ready = True
+    return L
+
+
+def ext_pack_dense(N, x0, xdes, F, g=None):
+    """F: (ND, 2, c) stance matrices, one per gait domain."""
+    g = g or default_gains()
+    F = np.asarray(F, float); c = F.shape[2]
+    nv, p, mi = N * (6 + c) + 1, 7 * N, 16 * N - 4 + 2 * c * N
+    Q = np.zeros(nv * nv); f = np.zeros(nv); A = np.zeros(p * nv); b = np.zeros(p); G = np.zeros(mi * nv); h = np.zeros(mi)
+    _ext_lib().orc_ext_pack_dense(C.byref(g), N, _f(x0), _f(xdes), _f(F).ravel(), c, Q, f, A, b, G, h)
+    return (Q.reshape(nv, nv, order="F"), f, A.reshape(p, nv, order="F"), b, G.reshape(mi, nv, order="F"), h)
+
+
+def ext_res_to_dict(r):
+    N, c, nv, K = r.N, r.c, r.nv, r.n_rows
+    x = np.array(r.x[:max(nv, 1)])
+    d = dict(status=r.status, N=N, c=c, nv=nv, kkt=r.kkt, mu=r.mu, qp_flag=r.qp_flag, qp_iters=r.qp_iters, nlp_iters=r.nlp_iters,
+             n_fact=r.n_fact, n_ls=r.n_ls, n_bump=r.n_bump, x=x, x_qp=np.array(r.x_qp[:max(nv, 1)]))
+    if nv > 0:
+        d.update(X=x[:4 * N], U=x[4 * N:6 * N], lam=x[6 * N:6 * N + c * N], slack=x[nv - 1],
+                 zd=np.array(r.zd[:K * N]).reshape(K, N), sd=np.array(r.sd[:K * N]).reshape(K, N))
+    return d
+
+
+def ext_solve(x0, xdes, feet, contact, obs, nbr=None, N=4, eps_obs=None, eps_nbr=2.2, g=None, o=None):
+    """One extended-mode agent with FIXED neighbour trajectories.  feet (ND, 2, 4); obs (2, K_obs); nbr (n_nbr, N, 2) or None."""
+    g = g or default_gains(); o = o or default_options()
+    obs = _f(obs); K = obs.shape[1] if obs.size else 0
+    nn = 0 if nbr is None else np.asarray(nbr).shape[0]
+    nb = _f(nbr) if nn else None
+    r = ExtResult()
+    _ext_lib().orc_ext_solve(C.byref(g), C.byref(o), N, _f(x0), _f(xdes), _f(feet).ravel(), np.ascontiguousarray(contact, np.int32), K,
+                             obs.ravel(), g.eps_dist if eps_obs is None else eps_obs, nn, eps_nbr, nb.ctypes.data if nn else None, C.byref(r))
+    return ext_res_to_dict(r)
+
+
+EXT_RELAX, EXT_PUB_TOL = 0.7, 1e-10
+
+
+def ext_solve_teams(x0, xdes, feet, contact, obs, T, N=4, eps_obs=None, eps_nbr=2.2, relax=EXT_RELAX, pub_tol=EXT_PUB_TOL, nthreads=8, g=None, o=None):
+    """nteams teams of T agents (agent-major arrays with leading dimension nteams * T): x0 (B,4) xdes (B,4N) feet (B,ND,2,4)
+    contact (B,4) obs (B,2,K_obs).  T = 1: independent agents.  Returns (list of result dicts, team iteration counts)."""
+    g = g or default_gains(); o = o or default_options()
+    B = x0.shape[0]; nteams = B // T; K = obs.shape[2]
+    res = (ExtResult * B)(); ti = np.zeros(nteams, np.int32)
+    _ext_lib().orc_ext_solve_teams(C.byref(g), C.byref(o), nteams, T, N, _f(x0).ravel(), _f(xdes).ravel(), _f(feet).ravel(),
+                                   np.ascontiguousarray(contact, np.int32).ravel(), K, _f(obs).ravel(), g.eps_dist if eps_obs is None else eps_obs,
+                                   eps_nbr, relax, pub_tol, nthreads, res, ti)
+    return [ext_res_to_dict(r) for r in res], ti

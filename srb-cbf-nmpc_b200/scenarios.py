@@ -88,3 +88,66 @@ def mc_worlds(B, n_cycles, seed=20251018 + 6000, n_obs=20, v_ref=0.2):
                 Pr_refined=Pr, Prd_refined=Prd, ref_cols=ref_cols, n_teams=B, Pobs_real=obs, n_obs=n_obs,
                 alpha_buf=np.stack([p0[0], 0 * p0[0], p0[1], 0 * p0[0]]),
                 success=np.ones(B, np.int32), distance_to_fail=np.full(B, 10.0), n_not_converged=np.zeros(B, np.int32))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Extended mode (BASELINE configs 4 and 5; no reference implementation exists).  Instances are tuples
+# (x0[4], xdes[4N], feet_xy[ND,2,4], contact[4], obs_xy[2,K_obs]).
+# ---------------------------------------------------------------------------------------------------------------------
+TEAM_OFFSETS = np.array([[0.0, 0.0], [0.0, -0.9], [-1.0, 0.0], [-1.0, -0.9]])   # Pstart of SIM:1013 / SIM4:862 relative to the leader
+EPS_NBR = float(np.float32(2.2))   # dec_vars_constr_cost.h:402 "epsilon = 2.2 // for robot to robot" (a float literal there)
+
+
+def _ext_agent(rng, p0, v0, goal, N, K_obs, contact, obs_all):
+    nominal = np.array([[0.183, 0.183, -0.183, -0.183], [-0.132, 0.132, -0.132, 0.132]])
+    x0 = np.array([p0[0], v0[0], p0[1], v0[1]])
+    vref = 0.2 * (goal - p0) / np.linalg.norm(goal - p0)
+    xdes = np.zeros(4 * N)
+    for k in range(N):
+        pk = p0 + vref * (k + 1) * TS
+        xdes[4 * k:4 * k + 4] = [pk[0], vref[0], pk[1], vref[1]]
+    feet = np.zeros((N // 4, 2, 4))
+    feet[0] = p0[:, None] + nominal + rng.uniform(-0.03, 0.03, (2, 4))
+    for d in range(1, N // 4):                       # later domains: nominal stance about the reference position at the domain's start
+        feet[d] = (p0 + vref * 4 * d * TS)[:, None] + nominal
+    d2 = ((obs_all - p0[:, None]) ** 2).sum(0)
+    near = np.argsort(d2, kind="stable")[:K_obs]     # the K_obs nearest obstacles, nearest first
+    return x0, xdes, feet, contact, obs_all[:, near].copy()
+
+
+def cfg4_teams(n_teams, seed=20251018 + 4000, N=4, K_obs=1):
+    """Four-robot teams (BASELINE config 4): leader as cfg 3, the others at the reference's Pstart offsets from it, every member
+    with 3 neighbour rows per grid point (+ K_obs obstacle rows).  The members of a team share the contact pattern and the
+    obstacle field.  Returns a flat, team-major list of 4 * n_teams instances."""
+    ss = np.random.SeedSequence(seed)
+    goal = np.array([10.0, 0.0])
+    out = []
+    for child in ss.spawn(n_teams):
+        rng = np.random.Generator(np.random.PCG64(child))
+        lead = np.array([rng.uniform(1, 9), rng.uniform(-2, 2)])
+        u = rng.uniform()
+        contact = [1, 1, 1, 1] if u < 0.5 else ([0, 1, 1, 0] if u < 0.75 else [1, 0, 0, 1])
+        ox = rng.uniform(0, 9, 20) + rng.uniform(-0.6, 0.6, 20); oy = rng.uniform(-2, 2, 20) + rng.uniform(-0.6, 0.6, 20)
+        obs_all = np.vstack([np.clip(ox, 1, 9), np.clip(oy, -3, 3)])
+        for a in range(4):
+            out.append(_ext_agent(rng, lead + TEAM_OFFSETS[a], rng.uniform(-0.3, 0.3, 2), goal, N, K_obs, contact, obs_all))
+    return out
+
+
+def cfg5_instances(B, seed=20251018 + 5000, N=8, K_obs=16, team=True):
+    """Long-horizon stress (BASELINE config 5): N = 8 grid points (two gait domains), the 16 nearest obstacles as rows at every
+    grid point, plus (team=True) the 3 neighbour rows of a four-robot team: B must then be a multiple of 4."""
+    if team:
+        return cfg4_teams(B // 4, seed=seed, N=N, K_obs=K_obs)
+    ss = np.random.SeedSequence(seed)
+    goal = np.array([10.0, 0.0])
+    out = []
+    for child in ss.spawn(B):
+        rng = np.random.Generator(np.random.PCG64(child))
+        p0 = np.array([rng.uniform(0, 9), rng.uniform(-2, 2)])
+        u = rng.uniform()
+        contact = [1, 1, 1, 1] if u < 0.5 else ([0, 1, 1, 0] if u < 0.75 else [1, 0, 0, 1])
+        ox = rng.uniform(0, 9, 20) + rng.uniform(-0.6, 0.6, 20); oy = rng.uniform(-2, 2, 20) + rng.uniform(-0.6, 0.6, 20)
+        obs_all = np.vstack([np.clip(ox, 1, 9), np.clip(oy, -3, 3)])
+        out.append(_ext_agent(rng, p0, rng.uniform(-0.3, 0.3, 2), goal, N, K_obs, contact, obs_all))
+    return out
