@@ -224,6 +224,68 @@ int cbfnmpc_qp_dense_batch(cbfnmpc_ctx *ctx, int B, int n, int p, int m, const d
                            const double *b, const double *G, const double *h, double *x, double *y, double *z, int32_t *status,
                            int32_t *iters, void *cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * EXTENDED MODE (BASELINE configs 4 and 5).  NO REFERENCE IMPLEMENTATION EXISTS: the reference's NLP has
+ * N = 4 grid points, one obstacle and no inter-agent rows (src/MPC_dist.cpp:81-454).  Generalised along the reference's own hints:
+ *   N = 4 or 8 grid points (N / 4 gait domains, one stance matrix per domain);
+ *   n_obs obstacle rows per grid point   |p_k - o_i|^2   + delta >= eps_obs   (the row of dec_vars_constr_cost.h:262-265, for EVERY
+ *     obstacle handed in -- the caller pre-selects, e.g. the 16 nearest);
+ *   neighbour rows per grid point        |p_k - p^j_k|^2 + delta >= eps_nbr   (DV:402 "epsilon = 2.2 // for robot to robot"; the
+ *     reference's disabled rule MPC_dist.cpp:391 extrapolates the neighbour's current state instead);
+ *   teams: team_size consecutive instances form a team whose members solve together and read each other's published trajectories
+ *     at the top of every interior-point iteration (under-relaxed Jacobi: pub <- pub + relax (iterate - pub); finished when nobody
+ *     stepped and every |iterate - pub| <= pub_tol).  The members of a team must share the stance class (4 feet / diagonal pair).
+ * With N = 4, n_obs = 1, no neighbours the answers are those of cbfnmpc_solve_batch given the closest obstacle.
+ * Arrays are structure-of-arrays, batch index fastest, like cbfnmpc_in / cbfnmpc_out:
+ *   x0 [4][B]; xdes [4N][B]; feet_xy [8 N/4][B] (per gait domain: x of the 4 feet, then y); contact [4][B];
+ *   obs_xy [2 n_obs][B] (x of all rows, then y); alpha_buf [4][B] optional;
+ *   nbr_traj [n_nbr][2N][B] optional, team_size 1 only: FIXED neighbour trajectories (rows 2k, 2k+1 = x, y at grid point k)
+ * Outputs (any may be NULL): X [4N][B], U [2N][B], lam [4N][B], slack [B], x_qp [6N][B], alpha [20][B] (Bezier fit of the first gait
+ * domain), alpha_buf_next [4][B], kkt [B], pub [2N][B] (published trajectory at the end), status / qp_iters / nlp_iters / team_iters [B]. */
+typedef struct {
+  int N, team_size;
+  double eps_obs, eps_nbr; /* defaults (double)1.9f, (double)2.2f */
+  double relax, pub_tol;   /* defaults 0.7, 1e-10 */
+} cbfnmpc_ext_cfg;
+typedef struct {
+  const double *x0, *xdes, *feet_xy;
+  const int32_t *contact;
+  const double *obs_xy;
+  int n_obs;
+  const double *alpha_buf;
+  const double *nbr_traj;
+  int n_nbr;
+} cbfnmpc_ext_in;
+typedef struct {
+  double *X, *U, *lam, *slack, *x_qp, *alpha, *alpha_buf_next, *kkt, *pub;
+  int32_t *status, *qp_iters, *nlp_iters, *team_iters;
+} cbfnmpc_ext_out;
+void cbfnmpc_ext_default_cfg(cbfnmpc_ext_cfg *cfg);
+/* device pointers, asynchronous on `cuda_stream`; a team (team_size x N lanes) lives in one warp and exchanges by shuffles */
+int cbfnmpc_ext_solve_batch(cbfnmpc_ctx *ctx, int B, const cbfnmpc_ext_cfg *cfg, const cbfnmpc_ext_in *in, const cbfnmpc_ext_out *out,
+                            void *cuda_stream);
+/* host pointers: copies in, solves, copies out, synchronises */
+int cbfnmpc_ext_solve_batch_host(cbfnmpc_ctx *ctx, int B, const cbfnmpc_ext_cfg *cfg, const cbfnmpc_ext_in *in, const cbfnmpc_ext_out *out);
+
+/* AGENT-SHARDED teams (BASELINE config 4 as worded: the members of a team live on different GPUs; SURVEY.md 8e collective C1).
+ * cbfnmpc_comm_unique_id / cbfnmpc_comm_init create the library's own NCCL communicator over the ranks that share teams (the id,
+ * 128 bytes, is made by one rank and handed to the others by the host program's own means).  cbfnmpc_ext_solve_sharded: this rank
+ * holds members [rank m, (rank + 1) m) of EVERY one of n_teams teams, m = team_size / nranks, member-major (instance b =
+ * local member * n_teams + team, B_local = m n_teams; arrays as above with B = B_local, device pointers, nbr_traj unused).  One kernel
+ * launch per interior-point iteration, an ncclAllGather of every member's published trajectory ((2N + 2) n_teams doubles each) in
+ * between; without a communicator (nranks = 1) the same path runs on one GPU with a device copy instead of the all-gather.
+ * Answers equal those of cbfnmpc_ext_solve_batch on the team-major layout. */
+typedef struct {
+  int launches, iterations, exchanges, nranks;
+  long long bytes_per_exchange; /* contributed by this rank per all-gather */
+  float total_ms;               /* device time of the whole call (CUDA events) */
+} cbfnmpc_ext_stats;
+int cbfnmpc_comm_unique_id(void *id128);
+int cbfnmpc_comm_init(cbfnmpc_ctx *ctx, int nranks, int rank, const void *id128);
+int cbfnmpc_comm_destroy(cbfnmpc_ctx *ctx);
+int cbfnmpc_ext_solve_sharded(cbfnmpc_ctx *ctx, int n_teams, const cbfnmpc_ext_cfg *cfg, const cbfnmpc_ext_in *in,
+                              const cbfnmpc_ext_out *out, cbfnmpc_ext_stats *stats, void *cuda_stream);
+
 /* FP64 DFMA peak microbenchmark (TFLOP/s) used as the roofline denominator by bench.py */
 int cbfnmpc_measure_fp64_peak(cbfnmpc_ctx *ctx, double *tflops);
 

@@ -48,6 +48,14 @@ def load():
     L.cbfnmpc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.cbfnmpc_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.cbfnmpc_solve_dense_nlptuple.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.cbfnmpc_ext_default_cfg.argtypes = [C.POINTER(capi.ExtCfg)]
+    L.cbfnmpc_ext_solve_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(capi.ExtCfg), C.POINTER(capi.ExtIn), C.POINTER(capi.ExtOut), C.c_void_p]
+    L.cbfnmpc_ext_solve_batch_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(capi.ExtCfg), C.POINTER(capi.ExtIn), C.POINTER(capi.ExtOut)]
+    L.cbfnmpc_comm_unique_id.argtypes = [C.c_void_p]
+    L.cbfnmpc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.cbfnmpc_comm_destroy.argtypes = [C.c_void_p]
+    L.cbfnmpc_ext_solve_sharded.argtypes = [C.c_void_p, C.c_int, C.POINTER(capi.ExtCfg), C.POINTER(capi.ExtIn), C.POINTER(capi.ExtOut),
+                                            C.POINTER(capi.ExtStats), C.c_void_p]
     L.cbfnmpc_pack_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
     _lib = L
     return L
@@ -57,7 +65,8 @@ EXPORTS = ["cbfnmpc_version", "cbfnmpc_last_error", "cbfnmpc_default_gains", "cb
            "cbfnmpc_destroy", "cbfnmpc_set_gains", "cbfnmpc_set_options", "cbfnmpc_solve_batch", "cbfnmpc_solve_batch_host",
            "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak",
            "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle", "cbfnmpc_closed_loop", "cbfnmpc_generate_reference", "cbfnmpc_qp_dense_batch",
-           "cbfnmpc_team_states", "cbfnmpc_pack_dense"]
+           "cbfnmpc_team_states", "cbfnmpc_pack_dense", "cbfnmpc_ext_default_cfg", "cbfnmpc_ext_solve_batch", "cbfnmpc_ext_solve_batch_host",
+           "cbfnmpc_comm_unique_id", "cbfnmpc_comm_init", "cbfnmpc_comm_destroy", "cbfnmpc_ext_solve_sharded"]
 
 
 def default_gains():
@@ -170,6 +179,73 @@ class BatchSolver:
             setattr(w, k, world.get(k))
         r = self._raw_struct(raw)
         self._ck(self.L.cbfnmpc_closed_loop(self.ctx, B, n_cycles, mode, C.byref(r), C.byref(w), fail_radius, stream))
+
+    # ---- extended mode (include/cbfnmpc.h "EXTENDED MODE"; no reference implementation exists)
+    def ext_cfg(self, N=4, team_size=1, **kw):
+        cfg = capi.ExtCfg(); self.L.cbfnmpc_ext_default_cfg(C.byref(cfg))
+        cfg.N, cfg.team_size = N, team_size
+        for k, v in kw.items(): setattr(cfg, k, v)
+        return cfg
+
+    def ext_solve_host(self, d, N=4, team_size=1, nbr_traj=None, out=None, **cfgkw):
+        """d: capi.ext_soa_from_instances(...); nbr_traj: optional (n_nbr, 2N, B) fixed neighbour trajectories (team_size 1)."""
+        B = d["x0"].shape[1]
+        out = out if out is not None else capi.ext_alloc_out(B, N)
+        cfg = self.ext_cfg(N, team_size, **cfgkw)
+        si = capi.ExtIn()
+        for k in ("x0", "xdes", "feet_xy", "obs_xy", "alpha_buf"):
+            capi._check(k, d[k], np.float64, d[k].shape[0], B); setattr(si, k, d[k].ctypes.data)
+        capi._check("contact", d["contact"], np.int32, 4, B); si.contact = d["contact"].ctypes.data
+        si.n_obs = int(d["n_obs"])
+        if nbr_traj is not None:
+            nbr_traj = np.ascontiguousarray(nbr_traj, dtype=np.float64)
+            capi._check("nbr_traj", nbr_traj, np.float64, nbr_traj.shape[0] * 2 * N, B)
+            si.nbr_traj = nbr_traj.ctypes.data; si.n_nbr = nbr_traj.shape[0]
+        so = capi.ExtOut()
+        rows = capi.ext_out_rows(N)
+        for k, v in out.items():
+            if v is None: continue
+            capi._check(k, v, np.int32 if k in capi.EXT_OUT_I32 else np.float64, 1 if k in capi.EXT_OUT_I32 else rows[k], B)
+            setattr(so, k, v.ctypes.data)
+        self._ck(self.L.cbfnmpc_ext_solve_batch_host(self.ctx, B, C.byref(cfg), C.byref(si), C.byref(so)))
+        return out
+
+    def _ext_structs(self, in_ptrs, out_ptrs, n_obs, n_nbr=0):
+        si = capi.ExtIn(); so = capi.ExtOut()
+        for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy", "alpha_buf", "nbr_traj"):
+            setattr(si, k, in_ptrs.get(k))
+        si.n_obs, si.n_nbr = n_obs, n_nbr
+        for k, _ in capi.ExtOut._fields_:
+            setattr(so, k, out_ptrs.get(k))
+        return si, so
+
+    def ext_solve_device(self, B, in_ptrs, out_ptrs, n_obs, N=4, team_size=1, n_nbr=0, stream=None, **cfgkw):
+        cfg = self.ext_cfg(N, team_size, **cfgkw)
+        si, so = self._ext_structs(in_ptrs, out_ptrs, n_obs, n_nbr)
+        self._ck(self.L.cbfnmpc_ext_solve_batch(self.ctx, B, C.byref(cfg), C.byref(si), C.byref(so), stream))
+
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        rc = load().cbfnmpc_comm_unique_id(buf)
+        if rc != 0:
+            raise CbfNmpcError("cbfnmpc_comm_unique_id failed (%d): %s" % (rc, load().cbfnmpc_last_error().decode()))
+        return bytes(buf)
+
+    def comm_init(self, nranks, rank, uid):
+        self._ck(self.L.cbfnmpc_comm_init(self.ctx, nranks, rank, C.c_char_p(uid)))
+
+    def comm_destroy(self):
+        self._ck(self.L.cbfnmpc_comm_destroy(self.ctx))
+
+    def ext_solve_sharded(self, n_teams, in_ptrs, out_ptrs, n_obs, N=4, team_size=4, stream=None, **cfgkw):
+        """Agent-sharded teams (member-major layout, device pointers); returns the cbfnmpc_ext_stats of the call."""
+        cfg = self.ext_cfg(N, team_size, **cfgkw)
+        si, so = self._ext_structs(in_ptrs, out_ptrs, n_obs)
+        st = capi.ExtStats()
+        self._ck(self.L.cbfnmpc_ext_solve_sharded(self.ctx, n_teams, C.byref(cfg), C.byref(si), C.byref(so), C.byref(st), stream))
+        return dict(launches=st.launches, iterations=st.iterations, exchanges=st.exchanges, nranks=st.nranks,
+                    bytes_per_exchange=st.bytes_per_exchange, total_ms=st.total_ms)
 
     def launch_count(self):
         return int(self.L.cbfnmpc_launch_count(self.ctx))

@@ -104,3 +104,49 @@ def out_struct(o, B=None):
         _check(k, v, dt, rows, v.size // rows if B is None else B)
         setattr(s, k, v.ctypes.data)
     return s
+
+
+# ---------------------------------------------------------------------------------------------------------------- extended mode
+class ExtCfg(C.Structure):
+    _fields_ = [("N", C.c_int), ("team_size", C.c_int), ("eps_obs", C.c_double), ("eps_nbr", C.c_double), ("relax", C.c_double), ("pub_tol", C.c_double)]
+
+
+class ExtIn(C.Structure):
+    _fields_ = [("x0", C.c_void_p), ("xdes", C.c_void_p), ("feet_xy", C.c_void_p), ("contact", C.c_void_p), ("obs_xy", C.c_void_p), ("n_obs", C.c_int),
+                ("alpha_buf", C.c_void_p), ("nbr_traj", C.c_void_p), ("n_nbr", C.c_int)]
+
+
+class ExtOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("X", "U", "lam", "slack", "x_qp", "alpha", "alpha_buf_next", "kkt", "pub", "status", "qp_iters", "nlp_iters", "team_iters")]
+
+
+class ExtStats(C.Structure):
+    _fields_ = [("launches", C.c_int), ("iterations", C.c_int), ("exchanges", C.c_int), ("nranks", C.c_int), ("bytes_per_exchange", C.c_longlong),
+                ("total_ms", C.c_float)]
+
+
+def ext_out_rows(N):
+    return dict(X=4 * N, U=2 * N, lam=4 * N, slack=1, x_qp=6 * N, alpha=20, alpha_buf_next=4, kkt=1, pub=2 * N)
+
+
+EXT_OUT_I32 = ("status", "qp_iters", "nlp_iters", "team_iters")
+
+
+def ext_soa_from_instances(insts, N):
+    """[(x0, xdes[4N], feet[ND,2,4], contact, obs[2,K]), ...] -> SoA arrays of cbfnmpc_ext_in."""
+    B = len(insts); K = insts[0][4].shape[1]; ND = N // 4
+    d = dict(x0=np.zeros((4, B)), xdes=np.zeros((4 * N, B)), feet_xy=np.zeros((8 * ND, B)), contact=np.zeros((4, B), np.int32),
+             obs_xy=np.zeros((2 * max(K, 1), B)), alpha_buf=np.zeros((4, B)))
+    for b, (x0, xdes, feet, contact, obs) in enumerate(insts):
+        d["x0"][:, b] = x0; d["xdes"][:, b] = xdes; d["feet_xy"][:, b] = np.asarray(feet, float).reshape(8 * ND); d["contact"][:, b] = contact
+        if K:
+            d["obs_xy"][:2 * K, b] = np.asarray(obs).reshape(2 * K)
+        d["alpha_buf"][:, b] = (x0[0], 0.0, x0[2], 0.0)
+    d["n_obs"] = K
+    return d
+
+
+def ext_alloc_out(B, N):
+    o = {k: np.zeros((n, B)) for k, n in ext_out_rows(N).items()}
+    o.update({k: np.zeros((1, B), np.int32) for k in EXT_OUT_I32})
+    return o

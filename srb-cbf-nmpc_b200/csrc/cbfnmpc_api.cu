@@ -1,5 +1,6 @@
 // cbfnmpc_api.cu -- C ABI (include/cbfnmpc.h) + the CUDA kernels.  sm_100a only; no CPU path of any kind.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string>
@@ -10,6 +11,7 @@
 #endif
 #include "cbfnmpc_lane.h"
 #include "cbfnmpc_qpdense.h"
+#include "cbfnmpc_ext_kernels.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
 // The solver (cbfnmpc_lane.h): one instance = 4 adjacent lanes, 8 instances per warp, LANE_NT / 32 warps per CTA.
@@ -339,6 +341,14 @@ struct cbfnmpc_ctx {
   double* d_xstart;              // 41 (dense entry point)
   int* d_perm;                   // 2 * max_batch + 2: class lists + counts (grown on demand for device-pointer batches)
   int perm_cap;
+  // extended mode (cbfnmpc_ext_api.cuh): class lists over teams, host staging, resumable state, published trajectories, NCCL
+  int* x_perm; int x_perm_cap;
+  double *x_in, *x_out; int* x_int; size_t x_in_cap, x_out_cap, x_int_cap;
+  double* x_state; size_t x_state_cap;
+  double* x_pub; size_t x_pub_cap;
+  int *x_active, *x_active_h;
+  cudaEvent_t x_ev[2], x_t0, x_t1;
+  void* comm; int comm_size, comm_rank;
   // small host-buffer batches (<= small_cap instances): one pinned block up, one down (see solve_small)
   int small_cap;
   unsigned char *h_sin, *h_sout, *d_sin, *d_sout;
@@ -352,6 +362,7 @@ static size_t small_out_bytes(int B) { return sizeof(double) * (size_t)92 * B + 
 
 extern "C" {
 
+int cbfnmpc_comm_destroy(cbfnmpc_ctx* c);
 int cbfnmpc_version(void) { return 100; }
 const char* cbfnmpc_last_error(void) { return g_err.c_str(); }
 void cbfnmpc_default_gains(cbfnmpc_gains* g) { host_default_gains(g); }
@@ -404,6 +415,9 @@ void cbfnmpc_destroy(cbfnmpc_ctx* c) {
   if (c->have_last) cudaEventSynchronize(c->ev_last);  // the caller's stream of the last call
   cudaFree(c->d_in); cudaFree(c->d_contact); cudaFree(c->d_out); cudaFree(c->d_outi); cudaFree(c->d_active); cudaFree(c->d_xstart); cudaFree(c->d_perm);
   cudaFree(c->d_sin); cudaFree(c->d_sout); cudaFreeHost(c->h_sin); cudaFreeHost(c->h_sout);
+  cbfnmpc_comm_destroy(c);
+  cudaFree(c->x_perm); cudaFree(c->x_in); cudaFree(c->x_out); cudaFree(c->x_int); cudaFree(c->x_state); cudaFree(c->x_pub);
+  if (c->x_active) { cudaFree(c->x_active); cudaFreeHost(c->x_active_h); cudaEventDestroy(c->x_ev[0]); cudaEventDestroy(c->x_ev[1]); cudaEventDestroy(c->x_t0); cudaEventDestroy(c->x_t1); }
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_last);
   for (int k = 1; k < CBF_MAX_CHUNKS; k++) cudaStreamDestroy(c->cstream[k]);
   cudaStreamDestroy(c->stream);
@@ -911,5 +925,7 @@ int cbfnmpc_solve_dense_nlptuple(cbfnmpc_ctx* c, int nv, int p, int mi, const do
   if (kkt) *kkt = hk;
   return CBFNMPC_OK;
 }
+
+#include "cbfnmpc_ext_api.cuh"
 
 }  // extern "C"

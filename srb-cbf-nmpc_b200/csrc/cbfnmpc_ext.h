@@ -48,8 +48,14 @@ struct ExtIO {
   double* state;
   int* n_active;         // incremented by every team that still iterates when the launch ends
   int B, ld, N, K_obs, n_nbr, T;
-  int xmode;             // 0: no neighbours; 1: team in one warp (shuffles); 2: neighbours' trajectories in io.nbr
-  int phase;             // 0: whole solve in one launch; 1: QP stage + publish, save; 2: NLP start, save; 3: n_run iterations, save
+  int xmode;             // 0: no neighbours; 1: team in one warp (shuffles); 2: fixed neighbour trajectories in io.nbr;
+                         // 3: members of a team in different launches / on different GPUs: published trajectories of ALL members
+                         //    in io.gathered, [member][2N + 2][n_teams] (filled by an all-gather between the launches); this launch
+                         //    holds members member0 .. of every team, member-major: instance b = (member - member0) * n_teams + team
+  const double* gathered;
+  int n_teams, member0;
+  int phase;             // 0: whole solve in one launch.  Resumable (xmode 2, an all-gather between launches): 1: QP stage, publish, save;
+                         // 2: NLP start, publish, save; 3: one iteration, publish, save; 4: store the outputs
   int n_run;
 };
 
@@ -95,10 +101,15 @@ struct XDims {
 #define XPERS_PUBX pr(d::F_PERS + 5)
 #define XPERS_PUBY pr(d::F_PERS + 6)
 #define XPERS_MOVED pr(d::F_PERS + 7)
-constexpr int ext_npriv(int K) { return XDims<4>::NFIX + XROW * K; }
+#ifdef CBF_HOST_EMU
+#define XHD
+#else
+#define XHD __host__ __device__
+#endif
+XHD constexpr int ext_npriv(int K) { return XDims<4>::NFIX + XROW * K; }
 // registers of a lane that survive between launches of a resumable run (after the private columns)
-#define XSTATE_REGS 32
-constexpr int ext_nstate(int K) { return ext_npriv(K) + XSTATE_REGS; }
+#define XSTATE_REGS 40
+XHD constexpr int ext_nstate(int K) { return ext_npriv(K) + XSTATE_REGS; }
 
 struct XKV { double xs[4], us[2], lm[4], dl, pi[4], nu[2], eta; };
 struct XConst { double Fl[2], D[6], qw; };
@@ -1072,6 +1083,11 @@ struct XSolver {
 // One group = one extended-mode solve; the groups of a team run the NLP stage in lock step (one exchange per iteration).
 // `b` = instance index (team-major: b = team * T + member), valid per TEAM.  Shared by the CUDA kernel and tests/emu.
 // ===================================================================================================================
+#ifndef CBF_HOST_EMU
+XDEV void atomicAdd_int(int* p, int v) { atomicAdd(p, v); }
+#else
+XDEV void atomicAdd_int(int* p, int v) { *p += v; }
+#endif
 template <int W> XDEV double t_max(const XGrp<W>& g, double v, int T) {   // maximum over the team (v already uniform in each group)
   for (int m = W; m < T * W; m <<= 1) v = fmax(v, x_shfl(g.tmask, v, g.tbase + ((x_lane() - g.tbase) ^ m)));
   return v;
@@ -1088,6 +1104,50 @@ XDEV void ext_store_bad(const ExtIO& io, int b, int j) {
   if (io.team_iters) io.team_iters[b] = 0;
 }
 
+// Registers of a lane that survive between the launches of a resumable run (agent-sharded teams: one launch per iteration, an
+// all-gather of the published trajectories in between); stored behind the private columns in io.state.
+template <int C, int W>
+struct XCarry {
+  double abuf_j, pubx, puby, moved, moved_prev;
+  int badin, fin, team_it, stepped_prev, team_done;
+};
+template <int C, int W>
+XDEV void ext_save(const ExtIO& io, int b, int npriv, const XSolver<C, W>& S, const XCarry<C, W>& cy) {
+  double* st = io.state + (size_t)b * W + S.g.j;
+  const size_t sd = (size_t)io.ld * W;
+  for (int f = 0; f < npriv; f++) st[(size_t)f * sd] = S.pr(f);
+  double* r = st + (size_t)npriv * sd;
+  int q = 0;
+  XUNR for (int i = 0; i < 4; i++) { r[(q++) * sd] = S.x.xs[i]; r[(q++) * sd] = S.x.lm[i]; r[(q++) * sd] = S.x.pi[i]; }
+  XUNR for (int a = 0; a < 2; a++) { r[(q++) * sd] = S.x.us[a]; r[(q++) * sd] = S.x.nu[a]; r[(q++) * sd] = S.c.Fl[a]; }
+  XUNR for (int t = 0; t < 6; t++) r[(q++) * sd] = S.c.D[t];
+  r[(q++) * sd] = S.x.dl; r[(q++) * sd] = S.x.eta; r[(q++) * sd] = S.c.qw; r[(q++) * sd] = S.mu; r[(q++) * sd] = S.kkt;
+  r[(q++) * sd] = cy.abuf_j; r[(q++) * sd] = cy.pubx; r[(q++) * sd] = cy.puby; r[(q++) * sd] = cy.moved; r[(q++) * sd] = cy.moved_prev;
+  // flags and counters, packed into two doubles' worth of integers each
+  r[(q++) * sd] = (double)(S.status | (S.qp_flag << 4) | ((int)S.first_ic << 8) | ((int)S.hold << 9) | (cy.badin << 10) | (cy.fin << 11) |
+                           (cy.stepped_prev << 12) | (cy.team_done << 13) | (S.nfilt << 16));
+  r[(q++) * sd] = (double)S.qp_iters; r[(q++) * sd] = (double)S.nlp_iters; r[(q++) * sd] = (double)S.nl_it; r[(q++) * sd] = (double)S.n_fact;
+  r[(q++) * sd] = (double)cy.team_it;
+}
+template <int C, int W>
+XDEV void ext_restore(const ExtIO& io, int b, int npriv, XSolver<C, W>& S, XCarry<C, W>& cy) {
+  const double* st = io.state + (size_t)b * W + S.g.j;
+  const size_t sd = (size_t)io.ld * W;
+  for (int f = 0; f < npriv; f++) S.pr(f) = st[(size_t)f * sd];
+  const double* r = st + (size_t)npriv * sd;
+  int q = 0;
+  XUNR for (int i = 0; i < 4; i++) { S.x.xs[i] = r[(q++) * sd]; S.x.lm[i] = r[(q++) * sd]; S.x.pi[i] = r[(q++) * sd]; }
+  XUNR for (int a = 0; a < 2; a++) { S.x.us[a] = r[(q++) * sd]; S.x.nu[a] = r[(q++) * sd]; S.c.Fl[a] = r[(q++) * sd]; }
+  XUNR for (int t = 0; t < 6; t++) S.c.D[t] = r[(q++) * sd];
+  S.x.dl = r[(q++) * sd]; S.x.eta = r[(q++) * sd]; S.c.qw = r[(q++) * sd]; S.mu = r[(q++) * sd]; S.kkt = r[(q++) * sd];
+  cy.abuf_j = r[(q++) * sd]; cy.pubx = r[(q++) * sd]; cy.puby = r[(q++) * sd]; cy.moved = r[(q++) * sd]; cy.moved_prev = r[(q++) * sd];
+  const int fl = (int)r[(q++) * sd];
+  S.status = fl & 15; S.qp_flag = (fl >> 4) & 15; S.first_ic = (fl >> 8) & 1; S.hold = (fl >> 9) & 1; cy.badin = (fl >> 10) & 1; cy.fin = (fl >> 11) & 1;
+  cy.stepped_prev = (fl >> 12) & 1; cy.team_done = (fl >> 13) & 1; S.nfilt = fl >> 16;
+  S.qp_iters = (int)r[(q++) * sd]; S.nlp_iters = (int)r[(q++) * sd]; S.nl_it = (int)r[(q++) * sd]; S.n_fact = (int)r[(q++) * sd];
+  cy.team_it = (int)r[(q++) * sd];
+}
+
 template <int C, int W>
 XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, XPriv pr) {
   typedef XDims<C> d;
@@ -1100,94 +1160,150 @@ XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, X
   S.nsq = d::NSQ - (j == 0 ? 2 : 0); S.nsn = d::NS - (j == 0 ? 2 : 0);
   S.K_obs = io.K_obs; S.K = io.K_obs + io.n_nbr;
   S.status = 1; S.qp_iters = 0; S.qp_flag = 3; S.nlp_iters = 0; S.n_fact = 0; S.kkt = 0.0; S.hold = false; S.nl_it = 0; S.mu = 0.0; S.first_ic = true; S.nfilt = 0;
+  S.sigma = 0.0; S.qp_it = 0;
   const size_t ld = (size_t)io.ld;
   const bool jacobi = io.n_nbr > 0;
-  double abuf_j = 0.0;
-  bool qp_done = true, badin = false;
-  if (valid) {
-    XUNR for (int i = 0; i < 4; i++) { pr(d::F_XDES + i) = io.xdes[(size_t)(4 * j + i) * ld + b]; pr(d::F_XIN + i) = io.x0[(size_t)i * ld + b]; }
-    abuf_j = (io.abuf && j < 4) ? io.abuf[(size_t)j * ld + b] : 0.0;
-    const int dm = j >> 2;   // gait domain of this grid point
-    double feet[8];
-    XUNR for (int t = 0; t < 8; t++) feet[t] = io.feet[(size_t)(8 * dm + t) * ld + b];
-    const int c0 = io.contact[b];
-    double F[8];
-    XUNR for (int a = 0; a < 2; a++) {   // stance matrix (MPC_dist.cpp:1238-1252)
-      if (C == 4) { XUNR for (int i = 0; i < 4; i++) F[4 * a + i] = feet[4 * a + i]; }
-      else {
-        F[4 * a] = (c0 == 0) ? feet[4 * a + 1] : feet[4 * a]; F[4 * a + 1] = (c0 == 0) ? feet[4 * a + 2] : feet[4 * a + 3];
-        F[4 * a + 2] = 0.0; F[4 * a + 3] = 0.0;
+  const int npriv = ext_npriv(S.K);
+  XCarry<C, W> cy;
+  cy.abuf_j = 0.0; cy.pubx = 0.0; cy.puby = 0.0; cy.moved = 0.0; cy.moved_prev = 0.0; cy.badin = 0; cy.fin = 0; cy.team_it = 0; cy.stepped_prev = 1; cy.team_done = 0;
+  if (io.phase <= 1) {
+    bool qp_done = true, badin = false;
+    if (valid) {
+      XUNR for (int i = 0; i < 4; i++) { pr(d::F_XDES + i) = io.xdes[(size_t)(4 * j + i) * ld + b]; pr(d::F_XIN + i) = io.x0[(size_t)i * ld + b]; }
+      cy.abuf_j = (io.abuf && j < 4) ? io.abuf[(size_t)j * ld + b] : 0.0;
+      const int dm = j >> 2;   // gait domain of this grid point
+      double feet[8];
+      XUNR for (int t = 0; t < 8; t++) feet[t] = io.feet[(size_t)(8 * dm + t) * ld + b];
+      const int c0 = io.contact[b];
+      double F[8];
+      XUNR for (int a = 0; a < 2; a++) {   // stance matrix (MPC_dist.cpp:1238-1252)
+        if (C == 4) { XUNR for (int i = 0; i < 4; i++) F[4 * a + i] = feet[4 * a + i]; }
+        else {
+          F[4 * a] = (c0 == 0) ? feet[4 * a + 1] : feet[4 * a]; F[4 * a + 1] = (c0 == 0) ? feet[4 * a + 2] : feet[4 * a + 3];
+          F[4 * a + 2] = 0.0; F[4 * a + 3] = 0.0;
+        }
+        S.c.Fl[a] = F[4 * a + C - 1];
       }
-      S.c.Fl[a] = F[4 * a + C - 1];
+      XUNR for (int t = 0; t < 6; t++) S.c.D[t] = 0.0;
+      XUNR for (int k = 0; k < 2; k++) XUNR for (int a = 0; a < NW; a++) S.c.D[k * NW + a] = F[4 * k + a] - F[4 * k + C - 1];
+      S.c.qw = (j == W - 1) ? P.Pw : P.Qw;
+      double chk = 0.0;
+      for (int r = 0; r < io.K_obs; r++) {
+        const double ox = io.obs[(size_t)r * ld + b], oy = io.obs[(size_t)(io.K_obs + r) * ld + b];
+        S.row(r, XR_CX) = ox; S.row(r, XR_CY) = oy;
+        chk += 0.0 * ox + 0.0 * oy;
+      }
+      XUNR for (int i = 0; i < 4; i++) chk += 0.0 * pr(d::F_XDES + i) + 0.0 * pr(d::F_XIN + i);
+      XUNR for (int t = 0; t < 8; t++) chk += 0.0 * F[t];
+      badin = !g_all(g, chk == 0.0);
+      if (badin) S.status = 4;
+      else qp_done = S.qp_init(P);
     }
-    XUNR for (int t = 0; t < 6; t++) S.c.D[t] = 0.0;
-    XUNR for (int k = 0; k < 2; k++) XUNR for (int a = 0; a < NW; a++) S.c.D[k * NW + a] = F[4 * k + a] - F[4 * k + C - 1];
-    S.c.qw = (j == W - 1) ? P.Pw : P.Qw;
-    double chk = 0.0;
-    for (int r = 0; r < io.K_obs; r++) {
-      const double ox = io.obs[(size_t)r * ld + b], oy = io.obs[(size_t)(io.K_obs + r) * ld + b];
-      S.row(r, XR_CX) = ox; S.row(r, XR_CY) = oy;
-      chk += 0.0 * ox + 0.0 * oy;
+    // ---- QP stage (independent per instance)
+    for (;;) {
+      const bool act = valid && !badin && !qp_done;
+      if (!g_any(g, act)) break;
+      qp_done = S.qp_iter(P);
     }
-    XUNR for (int i = 0; i < 4; i++) chk += 0.0 * pr(d::F_XDES + i) + 0.0 * pr(d::F_XIN + i);
-    XUNR for (int t = 0; t < 8; t++) chk += 0.0 * F[t];
-    badin = !g_all(g, chk == 0.0);
-    if (badin) S.status = 4;
-    else qp_done = S.qp_init(P);
+    cy.badin = badin ? 1 : 0;
+    cy.fin = (!valid || badin) ? 1 : 0;
+    if (valid && !badin && io.xqp) {
+      XUNR for (int i = 0; i < 4; i++) io.xqp[(size_t)(4 * j + i) * ld + b] = S.x.xs[i];
+      XUNR for (int a = 0; a < 2; a++) io.xqp[(size_t)(4 * W + 2 * j + a) * ld + b] = S.x.us[a];
+    }
+    // published trajectory: the QP positions first (a member with bad input stays where it was measured)
+    if (valid) { cy.pubx = badin ? pr(d::F_XIN + 0) : S.x.xs[0]; cy.puby = badin ? pr(d::F_XIN + 2) : S.x.xs[2]; }
+  } else if (valid) {
+    ext_restore<C, W>(io, b, npriv, S, cy);
   }
-  // ---- QP stage (independent per instance)
-  for (;;) {
-    const bool act = valid && !badin && !qp_done;
-    if (!g_any(g, act)) break;
-    qp_done = S.qp_iter(P);
-  }
-  bool fin = !valid || badin;     // finished for good
-  if (valid && !badin && io.xqp) {
-    XUNR for (int i = 0; i < 4; i++) io.xqp[(size_t)(4 * j + i) * ld + b] = S.x.xs[i];
-    XUNR for (int a = 0; a < 2; a++) io.xqp[(size_t)(4 * W + 2 * j + a) * ld + b] = S.x.us[a];
-  }
-  // ---- NLP stage.  Published trajectory: the QP positions first (a member with bad input stays where it was measured)
-  double pubx = 0.0, puby = 0.0, moved = 0.0;
-  if (valid) { pubx = badin ? pr(d::F_XIN + 0) : S.x.xs[0]; puby = badin ? pr(d::F_XIN + 2) : S.x.xs[2]; }
+  const bool resumable = io.phase != 0;
+  const int tix = (io.xmode == 3) ? b % io.n_teams : b;                  // team index / column inside a member block
+  const int mloc = (io.xmode == 3) ? b / io.n_teams : 0;                // member block of this launch
+  const size_t mstride = (size_t)(2 * W + 2) * (size_t)io.n_teams;      // one member block of the published trajectories
+  auto write_pub = [&](int stepped, double mv) {   // send buffer: positions, then (stepped, moved) of the iteration just done
+    if (!valid || !io.pub) return;
+    double* pb = io.pub + (size_t)mloc * mstride;
+    const size_t pl = (size_t)io.n_teams;
+    pb[(size_t)(2 * j) * pl + tix] = cy.pubx; pb[(size_t)(2 * j + 1) * pl + tix] = cy.puby;
+    if (j == 0) { pb[(size_t)(2 * W) * pl + tix] = (double)stepped; pb[(size_t)(2 * W + 1) * pl + tix] = mv; }
+  };
+  auto nbr_block = [&](int i) {   // published trajectory of this instance's i-th neighbour (xmode 3)
+    const int a = io.member0 + mloc, bb = i < a ? i : i + 1;
+    return io.gathered + (size_t)bb * mstride;
+  };
+  if (io.phase == 1) { write_pub(1, 0.0); if (valid) ext_save<C, W>(io, b, npriv, S, cy); return; }
   double nbx[3] = {0.0, 0.0, 0.0}, nby[3] = {0.0, 0.0, 0.0};
   auto exchange = [&]() {
     if (io.xmode == 1) {
-      for (int i = 0; i < io.n_nbr; i++) { const int bb = i < g.a ? i : i + 1; nbx[i] = t_from(g, pubx, bb); nby[i] = t_from(g, puby, bb); }
+      for (int i = 0; i < io.n_nbr; i++) { const int bb = i < g.a ? i : i + 1; nbx[i] = t_from(g, cy.pubx, bb); nby[i] = t_from(g, cy.puby, bb); }
     } else if (io.xmode == 2 && valid) {
       for (int i = 0; i < io.n_nbr; i++) { nbx[i] = io.nbr[i][(size_t)(2 * j) * ld + b]; nby[i] = io.nbr[i][(size_t)(2 * j + 1) * ld + b]; }
+    } else if (io.xmode == 3 && valid) {
+      for (int i = 0; i < io.n_nbr; i++) {
+        const double* nb = nbr_block(i);
+        nbx[i] = nb[(size_t)(2 * j) * io.n_teams + tix]; nby[i] = nb[(size_t)(2 * j + 1) * io.n_teams + tix];
+      }
     }
   };
-  exchange();
-  if (!fin) { S.set_nbr(nbx, nby); fin = S.nlp_init(XP); }
-  int team_it = 0;
-  for (;;) {
-    // publish: pos <- pos + omega (iterate - pos); moved = distance still to go
-    if (valid && !badin) {
-      pubx += XP.relax * (S.x.xs[0] - pubx); puby += XP.relax * (S.x.xs[2] - puby);
-      moved = g_max(g, fmax(fabs(S.x.xs[0] - pubx), fabs(S.x.xs[2] - puby)));
+  auto publish = [&]() {   // pos <- pos + omega (iterate - pos); moved = distance still to go
+    if (valid && !cy.badin) {
+      cy.pubx += XP.relax * (S.x.xs[0] - cy.pubx); cy.puby += XP.relax * (S.x.xs[2] - cy.puby);
+      cy.moved = g_max(g, fmax(fabs(S.x.xs[0] - cy.pubx), fabs(S.x.xs[2] - cy.puby)));
     }
+  };
+  if (io.phase == 0 || io.phase == 2) {
     exchange();
-    bool stepped = false;
-    if (!fin) {
+    if (!cy.fin) { S.set_nbr(nbx, nby); cy.fin = S.nlp_init(XP) ? 1 : 0; }
+    cy.moved_prev = 0.0;
+    publish();
+    if (io.phase == 2) {   // the first resumed launch counts its (vacuous) "previous iteration stepped" check: start one below
+      cy.team_it = -1; cy.stepped_prev = 1;
+      write_pub(1, 0.0); if (valid) ext_save<C, W>(io, b, npriv, S, cy); return;
+    }
+  }
+  // ---- iterations: [exchange; team finished (flags of the previous iteration)?; iterate; publish]
+  bool first = io.phase == 0;
+  if (io.phase != 4) for (;;) {
+    exchange();
+    if (!first && !cy.team_done) {
+      bool more;
+      if (io.xmode == 1) {
+        more = t_any(g, cy.stepped_prev != 0) || t_max(g, cy.moved_prev, io.T) > XP.pub_tol;
+      } else if (io.xmode == 3) {
+        bool st = cy.stepped_prev != 0; double mv = cy.moved_prev;
+        if (valid) for (int i = 0; i < io.n_nbr; i++) {
+          const double* nb = nbr_block(i);
+          st = st || nb[(size_t)(2 * W) * io.n_teams + tix] != 0.0; mv = fmax(mv, nb[(size_t)(2 * W + 1) * io.n_teams + tix]);
+        }
+        more = st || mv > XP.pub_tol;
+      } else {
+        more = cy.stepped_prev != 0;
+      }
+      if (more) { cy.team_it++; if (cy.team_it >= 4 * P.max_iter) more = false; }
+      if (!more) cy.team_done = 1;
+    }
+    first = false;
+    if (cy.team_done && !resumable) break;
+    int stepped = 0;
+    if (!cy.team_done && !cy.fin) {
       S.set_nbr(nbx, nby);
       const int rc = S.nlp_iter(XP, jacobi);
       stepped = rc == 0;
-      if (rc == 2) fin = true;
+      if (rc == 2) cy.fin = 1;
     }
-    bool more;
-    if (io.xmode == 1) {
-      const bool any_stepped = t_any(g, stepped);
-      const double mv = t_max(g, moved, io.T);
-      more = any_stepped || mv > XP.pub_tol;
-    } else {
-      more = stepped;   // no neighbours, or neighbour trajectories that do not change during this launch
+    cy.stepped_prev = stepped; cy.moved_prev = cy.moved;
+    if (!cy.team_done) publish();
+    if (resumable) {
+      write_pub(stepped, cy.moved_prev);
+      if (valid && !cy.team_done && j == 0 && io.n_active) atomicAdd_int(io.n_active, 1);
+      break;
     }
-    if (!more) break;
-    team_it++;
-    if (team_it >= 4 * P.max_iter) break;
   }
+  if (resumable && !(io.phase == 4)) { if (valid) ext_save<C, W>(io, b, npriv, S, cy); return; }
   if (!valid) return;
-  if (badin) { ext_store_bad<C, W>(io, b, j); return; }
+  if (cy.badin) { ext_store_bad<C, W>(io, b, j); return; }
+  const double abuf_j = cy.abuf_j, pubx = cy.pubx, puby = cy.puby;
+  const int team_it = cy.team_it;
   // ---- store
   if (io.X) { XUNR for (int i = 0; i < 4; i++) io.X[(size_t)(4 * j + i) * ld + b] = S.x.xs[i]; }
   if (io.U) { XUNR for (int a = 0; a < 2; a++) io.U[(size_t)(2 * j + a) * ld + b] = S.x.us[a]; }
@@ -1195,7 +1311,8 @@ XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, X
     XUNR for (int i = 0; i < C; i++) io.lam[(size_t)(C * j + i) * ld + b] = S.x.lm[i];
     XUNR for (int i = 0; i < 4 - C; i++) io.lam[(size_t)(W * C + (4 - C) * j + i) * ld + b] = 0.0;
   }
-  if (io.pub && io.xmode != 2) { io.pub[(size_t)(2 * j) * ld + b] = pubx; io.pub[(size_t)(2 * j + 1) * ld + b] = puby; }
+  if (io.pub && !resumable) { io.pub[(size_t)(2 * j) * ld + b] = pubx; io.pub[(size_t)(2 * j + 1) * ld + b] = puby; }
+  (void)pubx; (void)puby;
   {  // Bezier fit of the first gait domain (MPC_dist.cpp:784-855): lane r < 4 fits state row r through x_1 .. x_4
     double Y[5];
     Y[0] = abuf_j;

@@ -1,0 +1,284 @@
+// cbfnmpc_ext_api.cuh -- C ABI of the extended mode (include/cbfnmpc.h, "extended mode").  Included by cbfnmpc_api.cu inside its
+// extern "C" block.  NCCL is reached through dlopen (libnccl.so.2): the library loads, and every other entry point works, on
+// machines without NCCL; only the agent-sharded call with more than one rank needs it.
+
+// ---- NCCL by name (the five entry points used; types as in nccl.h)
+typedef struct { char internal[128]; } xnccl_uid;
+typedef void* xnccl_comm;
+struct XNccl {
+  void* h;
+  int (*GetUniqueId)(xnccl_uid*);
+  int (*CommInitRank)(xnccl_comm*, int, xnccl_uid, int);
+  int (*AllGather)(const void*, void*, size_t, int, xnccl_comm, cudaStream_t);
+  int (*CommDestroy)(xnccl_comm);
+  const char* (*GetErrorString)(int);
+};
+static XNccl g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+static int xnccl_load() {
+  if (g_nccl.h) return CBFNMPC_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(CBFNMPC_ERR_ARG, std::string("NCCL is not available: ") + dlerror());
+  g_nccl.GetUniqueId = (int (*)(xnccl_uid*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(xnccl_comm*, int, xnccl_uid, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, xnccl_comm, cudaStream_t))dlsym(h, "ncclAllGather");
+  g_nccl.CommDestroy = (int (*)(xnccl_comm))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
+    return fail(CBFNMPC_ERR_ARG, "NCCL library lacks an entry point");
+  g_nccl.h = h;
+  return CBFNMPC_OK;
+}
+#define XNCCL_DOUBLE 8 /* ncclFloat64 */
+#define NK(call)                                                                                                        \
+  do {                                                                                                                  \
+    int r_ = (call);                                                                                                    \
+    if (r_ != 0) return fail(CBFNMPC_ERR_CUDA, std::string(#call) + ": " + g_nccl.GetErrorString(r_));                  \
+  } while (0)
+
+void cbfnmpc_ext_default_cfg(cbfnmpc_ext_cfg* c) {
+  if (!c) return;
+  c->N = 4; c->team_size = 1;
+  c->eps_obs = (double)1.9f;    // dec_vars_constr_cost.h:401
+  c->eps_nbr = (double)2.2f;    // :402 "for robot to robot"
+  c->relax = 0.7; c->pub_tol = 1e-10;
+}
+
+static int ext_check(const cbfnmpc_ctx* c, int B, const cbfnmpc_ext_cfg* cfg, const cbfnmpc_ext_in* in, const cbfnmpc_ext_out* out, int T) {
+  if (!c || !cfg || !in || !out || B < 1) return fail(CBFNMPC_ERR_ARG, "extended mode: bad argument");
+  if (cfg->N != 4 && cfg->N != 8) return fail(CBFNMPC_ERR_ARG, "extended mode: N must be 4 or 8");
+  if (T != 1 && T != 2 && T != 4) return fail(CBFNMPC_ERR_ARG, "extended mode: team_size must be 1, 2 or 4");
+  if (T * cfg->N > 32) return fail(CBFNMPC_ERR_ARG, "extended mode: a team (team_size x N lanes) must fit in one warp");
+  if (B % T != 0) return fail(CBFNMPC_ERR_ARG, "extended mode: batch must be a multiple of team_size");
+  if (!in->x0 || !in->xdes || !in->feet_xy || !in->contact) return fail(CBFNMPC_ERR_ARG, "extended mode: missing input array");
+  if (in->n_obs < 0 || (in->n_obs > 0 && !in->obs_xy)) return fail(CBFNMPC_ERR_ARG, "extended mode: obstacle array missing");
+  if (!(cfg->relax > 0.0 && cfg->relax <= 1.0) || !(cfg->pub_tol >= 0.0)) return fail(CBFNMPC_ERR_ARG, "extended mode: relax in (0, 1], pub_tol >= 0");
+  return CBFNMPC_OK;
+}
+
+static void ext_fill_io(ExtIO* io, int B, int ld, const cbfnmpc_ext_cfg* cfg, const cbfnmpc_ext_in* in, const cbfnmpc_ext_out* out) {
+  memset(io, 0, sizeof(*io));
+  io->x0 = in->x0; io->xdes = in->xdes; io->feet = in->feet_xy; io->contact = in->contact; io->obs = in->obs_xy; io->abuf = in->alpha_buf;
+  io->X = out->X; io->U = out->U; io->lam = out->lam; io->slack = out->slack; io->xqp = out->x_qp; io->alpha = out->alpha;
+  io->abuf_next = out->alpha_buf_next; io->kkt = out->kkt; io->status = out->status; io->qp_iters = out->qp_iters; io->nlp_iters = out->nlp_iters;
+  io->team_iters = out->team_iters; io->pub = out->pub;
+  io->B = B; io->ld = ld; io->N = cfg->N; io->K_obs = in->n_obs;
+}
+
+static int ext_launch(cbfnmpc_ctx* c, const XParams& XP, const ExtIO& io, int n_teams, int* perm, cudaStream_t st, bool classify) {
+  const int K = io.K_obs + io.n_nbr;
+  const size_t smem = sizeof(double) * (size_t)ext_npriv(K) * XNT;
+  if (smem > 227 * 1024) return fail(CBFNMPC_ERR_ARG, "extended mode: too many rows per grid point for the shared memory of one SM");
+  int* counts = perm + 2 * (size_t)n_teams;
+  if (classify) {
+    cbfnmpc_ext_classify_kernel<<<1, 1024, 0, st>>>(io, n_teams, perm, counts);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  const int tpw = XNT / (io.T * io.N);
+  const int grid = (n_teams + tpw - 1) / tpw + 1;
+  if (io.N == 4) {
+    CK(cudaFuncSetAttribute(cbfnmpc_ext_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cbfnmpc_ext_kernel<4><<<grid, XNT, smem, st>>>(XP, io, n_teams, perm, counts);
+  } else {
+    CK(cudaFuncSetAttribute(cbfnmpc_ext_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cbfnmpc_ext_kernel<8><<<grid, XNT, smem, st>>>(XP, io, n_teams, perm, counts);
+  }
+  CK(cudaGetLastError());
+  c->launches++;
+  return CBFNMPC_OK;
+}
+
+static int ext_perm(cbfnmpc_ctx* c, int n_teams, cudaStream_t st) {
+  if (n_teams > c->x_perm_cap) {
+    CK(cudaStreamSynchronize(st));
+    if (c->x_perm) CK(cudaFree(c->x_perm));
+    CK(cudaMalloc(&c->x_perm, sizeof(int) * (2 * (size_t)n_teams + 2)));
+    c->x_perm_cap = n_teams;
+  }
+  return CBFNMPC_OK;
+}
+
+static void ext_xparams(const cbfnmpc_ctx* c, const cbfnmpc_ext_cfg* cfg, XParams* XP) {
+  XP->k = c->kp; XP->eps_obs = cfg->eps_obs; XP->eps_nbr = cfg->eps_nbr; XP->relax = cfg->relax; XP->pub_tol = cfg->pub_tol;
+}
+
+int cbfnmpc_ext_solve_batch(cbfnmpc_ctx* c, int B, const cbfnmpc_ext_cfg* cfg, const cbfnmpc_ext_in* in, const cbfnmpc_ext_out* out, void* cuda_stream) {
+  const int T = cfg ? cfg->team_size : 0;
+  int rc = ext_check(c, B, cfg, in, out, T);
+  if (rc) return rc;
+  if (T > 1 && in->nbr_traj) return fail(CBFNMPC_ERR_ARG, "extended mode: fixed neighbour trajectories need team_size 1");
+  if (in->n_nbr < 0 || in->n_nbr > 3 || (in->n_nbr > 0 && !in->nbr_traj && T == 1)) return fail(CBFNMPC_ERR_ARG, "extended mode: bad neighbour data");
+  const int n_nbr = T > 1 ? T - 1 : in->n_nbr;
+  if (in->n_obs + n_nbr < 1) return fail(CBFNMPC_ERR_ARG, "extended mode: at least one distance row per grid point");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  ExtIO io;
+  ext_fill_io(&io, B, B, cfg, in, out);
+  io.T = T; io.n_nbr = n_nbr; io.xmode = T > 1 ? 1 : (n_nbr > 0 ? 2 : 0); io.phase = 0;
+  for (int i = 0; i < n_nbr && T == 1; i++) io.nbr[i] = in->nbr_traj + (size_t)i * (2 * cfg->N) * B;
+  XParams XP; ext_xparams(c, cfg, &XP);
+  const int n_teams = B / T;
+  rc = ext_perm(c, n_teams, st);
+  if (rc) return rc;
+  rc = ctx_enter(c, st);
+  if (rc) return rc;
+  CK(cudaEventRecord(c->ev0, st));
+  rc = ext_launch(c, XP, io, n_teams, c->x_perm, st, true);
+  if (rc) return rc;
+  CK(cudaEventRecord(c->ev1, st)); c->timed = true;
+  return ctx_leave(c, st);
+}
+
+// host staging of the extended mode (grow-only)
+static int ext_staging(cbfnmpc_ctx* c, size_t n_in, size_t n_out, size_t n_int) {
+  if (n_in > c->x_in_cap) { if (c->x_in) CK(cudaFree(c->x_in)); CK(cudaMalloc(&c->x_in, sizeof(double) * n_in)); c->x_in_cap = n_in; }
+  if (n_out > c->x_out_cap) { if (c->x_out) CK(cudaFree(c->x_out)); CK(cudaMalloc(&c->x_out, sizeof(double) * n_out)); c->x_out_cap = n_out; }
+  if (n_int > c->x_int_cap) { if (c->x_int) CK(cudaFree(c->x_int)); CK(cudaMalloc(&c->x_int, sizeof(int) * n_int)); c->x_int_cap = n_int; }
+  return CBFNMPC_OK;
+}
+
+int cbfnmpc_ext_solve_batch_host(cbfnmpc_ctx* c, int B, const cbfnmpc_ext_cfg* cfg, const cbfnmpc_ext_in* in, const cbfnmpc_ext_out* out) {
+  const int T = cfg ? cfg->team_size : 0;
+  int rc = ext_check(c, B, cfg, in, out, T);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  if (c->have_last) { CK(cudaEventSynchronize(c->ev_last)); c->have_last = false; }
+  const int N = cfg->N, ND = N / 4, K = in->n_obs, nn = (T == 1 && in->nbr_traj) ? in->n_nbr : 0;
+  const size_t Bs = (size_t)B;
+  // inputs: x0 4 | xdes 4N | feet 8 ND | abuf 4 | obs 2K | nbr nn 2N ; outputs: X 4N | U 2N | lam 4N | slack 1 | xqp 6N | alpha 20 | abuf_next 4 | kkt 1 | pub 2N
+  const size_t rin = 4 + 4 * N + 8 * ND + 4 + 2 * K + (size_t)nn * 2 * N, rout = 4 * N + 2 * N + 4 * N + 1 + 6 * N + 20 + 4 + 1 + 2 * N;
+  rc = ext_staging(c, rin * Bs, rout * Bs, 8 * Bs);
+  if (rc) return rc;
+  cudaStream_t st = c->stream;
+  double* d = c->x_in; size_t o = 0;
+  cbfnmpc_ext_in din = *in;
+  auto up = [&](const double* h, size_t rows, const double** dst) -> int {
+    if (rows == 0) { *dst = nullptr; return 0; }
+    if (h) CK(cudaMemcpyAsync(d + o * Bs, h, sizeof(double) * rows * Bs, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(d + o * Bs, 0, sizeof(double) * rows * Bs, st));
+    *dst = d + o * Bs; o += rows; return 0;
+  };
+  if ((rc = up(in->x0, 4, &din.x0)) || (rc = up(in->xdes, 4 * N, &din.xdes)) || (rc = up(in->feet_xy, 8 * ND, &din.feet_xy)) ||
+      (rc = up(in->alpha_buf, 4, &din.alpha_buf)) || (rc = up(in->obs_xy, 2 * K, &din.obs_xy)) || (rc = up(nn ? in->nbr_traj : nullptr, (size_t)nn * 2 * N, &din.nbr_traj)))
+    return rc;
+  if (!nn) din.nbr_traj = nullptr;
+  din.n_nbr = nn;
+  CK(cudaMemcpyAsync(c->x_int, in->contact, sizeof(int) * 4 * Bs, cudaMemcpyHostToDevice, st));
+  din.contact = c->x_int;
+  double* q = c->x_out; size_t p = 0;
+  cbfnmpc_ext_out dout;
+  memset(&dout, 0, sizeof(dout));
+  struct OS { double** dev; double* host; size_t rows; };
+  OS os[9] = {{&dout.X, out->X, (size_t)4 * N}, {&dout.U, out->U, (size_t)2 * N}, {&dout.lam, out->lam, (size_t)4 * N}, {&dout.slack, out->slack, 1},
+              {&dout.x_qp, out->x_qp, (size_t)6 * N}, {&dout.alpha, out->alpha, 20}, {&dout.alpha_buf_next, out->alpha_buf_next, 4}, {&dout.kkt, out->kkt, 1},
+              {&dout.pub, out->pub, (size_t)2 * N}};
+  for (int i = 0; i < 9; i++) { *os[i].dev = q + p * Bs; p += os[i].rows; }
+  int* di = c->x_int + 4 * Bs;
+  dout.status = di; dout.qp_iters = di + Bs; dout.nlp_iters = di + 2 * Bs; dout.team_iters = di + 3 * Bs;
+  CK(cudaMemsetAsync(di, 0, sizeof(int) * 4 * Bs, st));
+  rc = cbfnmpc_ext_solve_batch(c, B, cfg, &din, &dout, st);
+  if (rc) return rc;
+  for (int i = 0; i < 9; i++) if (os[i].host) CK(cudaMemcpyAsync(os[i].host, *os[i].dev, sizeof(double) * os[i].rows * Bs, cudaMemcpyDeviceToHost, st));
+  int32_t* const oi[4] = {out->status, out->qp_iters, out->nlp_iters, out->team_iters};
+  for (int i = 0; i < 4; i++) if (oi[i]) CK(cudaMemcpyAsync(oi[i], di + (size_t)i * Bs, sizeof(int) * Bs, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  c->have_last = false;
+  return CBFNMPC_OK;
+}
+
+// ---- agent-sharded teams: the path's one collective
+int cbfnmpc_comm_unique_id(void* id128) {
+  if (!id128) return fail(CBFNMPC_ERR_ARG, "null argument");
+  int rc = xnccl_load();
+  if (rc) return rc;
+  xnccl_uid u;
+  NK(g_nccl.GetUniqueId(&u));
+  memcpy(id128, u.internal, 128);
+  return CBFNMPC_OK;
+}
+int cbfnmpc_comm_init(cbfnmpc_ctx* c, int nranks, int rank, const void* id128) {
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_comm_init: bad argument");
+  int rc = xnccl_load();
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  if (c->comm) { g_nccl.CommDestroy((xnccl_comm)c->comm); c->comm = nullptr; }
+  xnccl_uid u; memcpy(u.internal, id128, 128);
+  xnccl_comm cm = nullptr;
+  NK(g_nccl.CommInitRank(&cm, nranks, u, rank));
+  c->comm = cm; c->comm_size = nranks; c->comm_rank = rank;
+  return CBFNMPC_OK;
+}
+int cbfnmpc_comm_destroy(cbfnmpc_ctx* c) {
+  if (!c) return fail(CBFNMPC_ERR_ARG, "null argument");
+  if (c->comm && g_nccl.h) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); g_nccl.CommDestroy((xnccl_comm)c->comm); }
+  c->comm = nullptr; c->comm_size = 1; c->comm_rank = 0;
+  return CBFNMPC_OK;
+}
+
+// This rank holds members [rank * mpr, (rank + 1) * mpr) of EVERY one of n_teams teams (mpr = team_size / nranks), member-major:
+// instance b = (member - rank * mpr) * n_teams + team.  One launch per interior-point iteration; between the launches the published
+// trajectories of all members are all-gathered (NCCL over NVLink; a device copy when nranks = 1).  The launch of iteration i + 1 is
+// enqueued before the host looks at the "teams still iterating" counter of iteration i (two pinned slots), so the stream never
+// drains; iterations of teams that have finished are no-ops.
+int cbfnmpc_ext_solve_sharded(cbfnmpc_ctx* c, int n_teams, const cbfnmpc_ext_cfg* cfg, const cbfnmpc_ext_in* in, const cbfnmpc_ext_out* out,
+                              cbfnmpc_ext_stats* stats, void* cuda_stream) {
+  if (!c || !cfg) return fail(CBFNMPC_ERR_ARG, "null argument");
+  const int T = cfg->team_size, G = c->comm ? c->comm_size : 1, rank = c->comm ? c->comm_rank : 0;
+  if (T < 2 || T % G != 0) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_ext_solve_sharded: team_size must be a multiple (>= 2) of the communicator's size");
+  const int mpr = T / G, B = mpr * n_teams;
+  int rc = ext_check(c, B, cfg, in, out, 1);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  const int N = cfg->N, n_nbr = T - 1, K = in->n_obs + n_nbr;
+  const size_t blk = (size_t)(2 * N + 2) * n_teams;   // one member's published block
+  const size_t n_state = (size_t)ext_nstate(K) * (size_t)B * N, n_pub = blk * mpr, n_gath = blk * T;
+  if (n_state > c->x_state_cap) { CK(cudaStreamSynchronize(st)); if (c->x_state) CK(cudaFree(c->x_state)); CK(cudaMalloc(&c->x_state, sizeof(double) * n_state)); c->x_state_cap = n_state; }
+  if (n_gath + n_pub > c->x_pub_cap) { CK(cudaStreamSynchronize(st)); if (c->x_pub) CK(cudaFree(c->x_pub)); CK(cudaMalloc(&c->x_pub, sizeof(double) * (n_gath + n_pub))); c->x_pub_cap = n_gath + n_pub; }
+  if (!c->x_active) { CK(cudaMalloc(&c->x_active, sizeof(int) * 2)); CK(cudaHostAlloc(&c->x_active_h, sizeof(int) * 2, cudaHostAllocDefault)); CK(cudaEventCreateWithFlags(&c->x_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->x_ev[1], cudaEventDisableTiming)); CK(cudaEventCreate(&c->x_t0)); CK(cudaEventCreate(&c->x_t1)); }
+  double* pub = c->x_pub; double* gathered = c->x_pub + n_pub;
+  ExtIO io;
+  ext_fill_io(&io, B, B, cfg, in, out);
+  io.pub = pub; io.gathered = gathered; io.n_teams = n_teams; io.member0 = rank * mpr;
+  io.T = 1; io.n_nbr = n_nbr; io.xmode = 3; io.state = c->x_state;
+  XParams XP; ext_xparams(c, cfg, &XP);
+  rc = ext_perm(c, B, st);
+  if (rc) return rc;
+  rc = ctx_enter(c, st);
+  if (rc) return rc;
+  auto gather = [&]() -> int {
+    if (G == 1) CK(cudaMemcpyAsync(gathered, pub, sizeof(double) * n_pub, cudaMemcpyDeviceToDevice, st));
+    else NK(g_nccl.AllGather(pub, gathered, n_pub, XNCCL_DOUBLE, (xnccl_comm)c->comm, st));
+    return CBFNMPC_OK;
+  };
+  CK(cudaEventRecord(c->x_t0, st));
+  io.phase = 1; io.n_active = nullptr;
+  if ((rc = ext_launch(c, XP, io, B, c->x_perm, st, true)) || (rc = gather())) return rc;
+  io.phase = 2;
+  if ((rc = ext_launch(c, XP, io, B, c->x_perm, st, false)) || (rc = gather())) return rc;
+  const int cap = 4 * c->opts.max_iter + 2;
+  int it = 0, done_at = -1;
+  for (; it < cap; it++) {
+    const int s = it & 1;
+    CK(cudaMemsetAsync(c->x_active + s, 0, sizeof(int), st));
+    io.phase = 3; io.n_active = c->x_active + s;
+    if ((rc = ext_launch(c, XP, io, B, c->x_perm, st, false)) || (rc = gather())) return rc;
+    CK(cudaMemcpyAsync(c->x_active_h + s, c->x_active + s, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c->x_ev[s], st));
+    if (it >= 1) {   // look at the previous iteration's counter while this one runs
+      CK(cudaEventSynchronize(c->x_ev[s ^ 1]));
+      if (c->x_active_h[s ^ 1] == 0) { done_at = it - 1; it++; break; }
+    }
+  }
+  io.phase = 4; io.n_active = nullptr;
+  if ((rc = ext_launch(c, XP, io, B, c->x_perm, st, false))) return rc;
+  CK(cudaEventRecord(c->x_t1, st));
+  if (stats) {
+    CK(cudaEventSynchronize(c->x_t1));
+    float ms = 0.0f; CK(cudaEventElapsedTime(&ms, c->x_t0, c->x_t1));
+    stats->launches = it + 3; stats->iterations = done_at >= 0 ? done_at + 1 : it; stats->exchanges = it + 2;
+    stats->bytes_per_exchange = (long long)(sizeof(double) * n_pub); stats->total_ms = ms; stats->nranks = G;
+  }
+  return ctx_leave(c, st);
+}

@@ -129,3 +129,26 @@ def snopt_pin_checks(x, x_qp, status, kkt, active_dist, fix):
     #     SNOPT had not finished optimising)
     pos = [0, 2, 4, 6, 8, 10, 12, 14]
     assert np.abs(x[pos] - xf[pos]).max() < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------- extended mode
+def ext_arrays(insts):
+    return (np.array([i[0] for i in insts]), np.array([i[1] for i in insts]), np.array([i[2] for i in insts]),
+            np.array([i[3] for i in insts], np.int32), np.array([i[4] for i in insts]))
+
+
+def ext_compare(out, res, T=1):
+    """CUDA extended-mode outputs against the list of oracle result dicts.  Teams are compared only when every member converged in
+    both (the answer of a team with a failed member depends on where that member froze)."""
+    B = len(res)
+    st = out["status"][0]; rs = np.array([r["status"] for r in res])
+    okm = (st == 0) & (rs == 0)
+    if T > 1:
+        okt = okm.reshape(-1, T).all(1); okm = np.repeat(okt, T)
+    worst = 0.0
+    for b in np.nonzero(okm)[0]:
+        r = res[b]
+        sx = max(1.0, np.abs(r["X"]).max()); su = max(1.0, np.abs(r["U"]).max())
+        worst = max(worst, np.abs(out["X"][:, b] - r["X"]).max() / sx, np.abs(out["U"][:, b] - r["U"]).max() / su,
+                    abs(out["slack"][0, b] - r["slack"]) / max(1.0, abs(r["slack"])))
+    return dict(status_equal=(st == rs), compared=okm, worst=worst, iters_equal=(out["nlp_iters"][0] == np.array([r["nlp_iters"] for r in res])))
