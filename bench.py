@@ -113,6 +113,100 @@ def cpu_baseline(insts, seconds_target=12.0, nthreads=None):
             "n": n, "seconds": dt, "converged": conv}
 
 
+def extended_blocks(pkg, capi, S, SH, torch, dist, dev, local, rank, world, teams_per_gpu=2048, cpu=True):
+    """BASELINE configs 4 and 5 (extended mode): NO REFERENCE IMPLEMENTATION EXISTS -- the checker is
+    oracle/cbfnmpc_oracle_ext.c.  Per GPU: teams_per_gpu four-robot teams.
+      cfg4: N = 4, 1 obstacle + 3 neighbour rows per grid point -- (a) team-major: a team in one warp, exchange by shuffles, no
+            collective; (b) agent-sharded: the members of a team on different GPUs (one GPU: different member blocks), one launch per
+            interior-point iteration and the library's own ncclAllGather of the published trajectories in between.
+      cfg5: N = 8, 16 obstacle + 3 neighbour rows per grid point, team-major.
+    Times are device times (CUDA events recorded by the library on its launch stream), max over ranks; solves/s counts converged
+    members only."""
+    import numpy as np
+    T = 4
+    out = {"note": "extended mode: no reference implementation exists (SURVEY.md 0 / A.6); checker = oracle/cbfnmpc_oracle_ext.c"}
+
+    def red(times, work):
+        return SH.reduce_over_ranks(dist, times, work, dev)
+
+    def device_batch(insts, N):
+        B = len(insts)
+        d = capi.ext_soa_from_instances(insts, N)
+        tin = {k: torch.from_numpy(d[k]).to(dev) for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy", "alpha_buf")}
+        tout = {k: torch.zeros((n, B), dtype=torch.float64, device=dev) for k, n in capi.ext_out_rows(N).items() if k != "pub"}
+        tout.update({k: torch.zeros((1, B), dtype=torch.int32, device=dev) for k in capi.EXT_OUT_I32})
+        return d, {k: v.data_ptr() for k, v in tin.items()}, {k: v.data_ptr() for k, v in tout.items()}, tin, tout
+
+    for name, N, K_obs, seed in (("cfg4", 4, 1, 20251018 + 4000), ("cfg5", 8, 16, 20251018 + 5000)):
+        insts = S.cfg4_teams(teams_per_gpu, seed=seed + 17 * rank, N=N, K_obs=K_obs)     # every rank its own teams
+        B = len(insts)
+        solver = pkg.BatchSolver(device=local, max_batch=B, max_obs=max(K_obs, 1))
+        d, ip, op, tin, tout = device_batch(insts, N)
+        ms = []
+        for _ in range(4):
+            solver.ext_solve_device(B, ip, op, d["n_obs"], N=N, team_size=T, eps_nbr=S.EPS_NBR)
+            torch.cuda.synchronize(dev)
+            ms.append(solver.last_kernel_ms())
+        st = tout["status"][0].cpu().numpy(); ti = tout["team_iters"][0].cpu().numpy()[::T]; ni = tout["nlp_iters"][0].cpu().numpy()
+        (tmax,), (conv, inst) = red([min(ms[1:])], [int((st == 0).sum()), B])
+        blk = {"workload": "%d four-robot teams per GPU, N = %d grid points, %d obstacle + 3 neighbour rows per grid point" % (teams_per_gpu, N, K_obs),
+               "team_major": {"kernel": "cbfnmpc_ext_kernel<%d>" % N, "ms_per_solve_of_all_teams": tmax, "converged_solves_per_s": conv / (tmax * 1e-3),
+                              "converged_fraction": conv / inst, "instances": int(inst), "collective": "none (a team lives in one warp; exchange by shuffles)",
+                              "team_iterations": {"mean": float(ti.mean()), "p99": float(np.percentile(ti, 99)), "max": int(ti.max())},
+                              "nlp_iterations_mean": float(ni[st == 0].mean()) if (st == 0).any() else None}}
+        if name == "cfg4":
+            # agent-sharded: groups of G = min(world, 4) ranks share teams; the library's own NCCL communicator per group
+            grp, grank, G, mpr, n_groups = SH.sharded_group(rank, world, T)
+            if G > 1:
+                uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+                if grank == 0:
+                    uid = torch.frombuffer(bytearray(pkg.BatchSolver.comm_unique_id()), dtype=torch.uint8).to(dev)
+                subs = [dist.new_group(list(range(g * G, (g + 1) * G))) for g in range(n_groups)]
+                dist.broadcast(uid, src=grp * G, group=subs[grp])
+                solver.comm_init(G, grank, bytes(uid.cpu().numpy().tobytes()))
+            n_teams = teams_per_gpu * G          # the group's teams: every rank of the group holds mpr members of each
+            ginsts = S.cfg4_teams(n_teams, seed=seed + 1000 + grp, N=N, K_obs=K_obs)
+            idx = SH.member_major(n_teams, T, list(range(grank * mpr, (grank + 1) * mpr)))
+            mine = [ginsts[i] for i in idx]
+            s2 = solver if G > 1 else pkg.BatchSolver(device=local, max_batch=len(mine), max_obs=max(K_obs, 1))
+            if G > 1 and len(mine) > B:
+                pass
+            d2, ip2, op2, tin2, tout2 = device_batch(mine, N)
+            stats = None
+            for _ in range(3):
+                if dist is not None: dist.barrier()
+                stats = s2.ext_solve_sharded(n_teams, ip2, op2, d2["n_obs"], N=N, team_size=T, eps_nbr=S.EPS_NBR)
+                torch.cuda.synchronize(dev)
+            st2 = tout2["status"][0].cpu().numpy()
+            (t2,), (conv2, inst2) = red([stats["total_ms"]], [int((st2 == 0).sum()), len(mine)])
+            blk["agent_sharded"] = {"layout": "%d rank(s) per team, %d member(s) of every team per rank, %d group(s)" % (G, mpr, n_groups),
+                                    "collective": ("ncclAllGather inside libcbfnmpc.so, one per interior-point iteration" if G > 1 else
+                                                   "one GPU: device copy in place of the all-gather (same launches, same buffers)"),
+                                    "ms_per_solve_of_all_teams": t2, "converged_solves_per_s": conv2 / (t2 * 1e-3), "instances": int(inst2),
+                                    "iterations": stats["iterations"], "launches": stats["launches"], "exchanges": stats["exchanges"],
+                                    "allgather_bytes_per_rank_and_iteration": stats["bytes_per_exchange"],
+                                    "ms_per_iteration": t2 / max(stats["launches"], 1)}
+            if G > 1: solver.comm_destroy()
+            if s2 is not solver: s2.close()
+        if cpu and rank == 0 and world == 1:
+            # the checker on the host cores, bounded sample (dense LDL' of the whole KKT matrix per iteration: a checker, not a tuned solver)
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle as O
+            nt = 1024 if N == 4 else 96
+            sub = insts[:T * nt]
+            arr = (np.array([i[0] for i in sub]), np.array([i[1] for i in sub]), np.array([i[2] for i in sub]), np.array([i[3] for i in sub], np.int32), np.array([i[4] for i in sub]))
+            nthreads = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            res, _ = O.ext_solve_teams(*arr, T=T, N=N, eps_nbr=S.EPS_NBR, nthreads=nthreads)
+            dt = time.perf_counter() - t0
+            cc = sum(1 for r in res if r["status"] == 0)
+            blk["cpu_checker"] = {"value": cc / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
+                                  "sample": "%d teams (%d solves, %d converged) in %.2f s on %d host threads; oracle/cbfnmpc_oracle_ext.c (dense)" % (nt, T * nt, cc, dt, nthreads)}
+        out[name] = blk
+        solver.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -121,6 +215,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extended", action="store_true", help="skip the extended-mode blocks (BASELINE configs 4 and 5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     import numpy as np
@@ -271,6 +366,9 @@ def main():
     (total_ms_max, e2e_s_max, e2e_p_s_max), (conv_all, conv_e2e_all, flops_all, launches_all, inst_all, conv_e2e_p_all) = SH.reduce_over_ranks(
         dist, [total_ms, e2e_s, e2e_pageable_s], [conv, conv_e2e, flops, launches, B, conv_e2e_p], dev)
     fp64_peak = solver.fp64_peak_tflops()
+    extended = None
+    if not args.no_extended:
+        extended = extended_blocks(pkg, capi, S, SH, torch, dist, dev, local, rank, world, cpu=not args.no_cpu_baseline)
     bi, bo = algorithmic_bytes(K_obs)
     if rank == 0:
         ms_per_step = total_ms_max / args.steps
@@ -332,6 +430,8 @@ def main():
             except Exception as e:  # the C++ example is optional for the bench line
                 lat["cpp_host"] = {"error": str(e)[:200]}
         line["latency"] = lat
+        if extended is not None:
+            line["extended"] = extended
         print(json.dumps(line))
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()

@@ -510,7 +510,7 @@ int orc_ext_solve(const orc_gains *g, const orc_options *o, int N, const double 
 
 int orc_ext_solve_team(const orc_gains *g, const orc_options *o, int T, int N, const double *x0, const double *xdes, const double *feet_xy,
                        const int *contact, int K_obs, const double *obs_xy, double eps_obs, double eps_nbr, double relax, double pub_tol,
-                       orc_ext_result *res, int *team_iters) {
+                       int max_team_iters, orc_ext_result *res, int *team_iters) {
   const int ND = N / 4, nn = T - 1;
   orc_ext *ag[8];
   double pos[8][2 * ORC_EXT_NMAX], nbr[7 * 2 * ORC_EXT_NMAX];
@@ -544,7 +544,7 @@ int orc_ext_solve_team(const orc_gains *g, const orc_options *o, int T, int N, c
     }
     if (!stepped && moved <= pub_tol) break;
     iters++;
-    if (iters >= 4 * o->max_iter) break;
+    if (iters >= max_team_iters) break;
   }
 #undef GATHER
   int all = 1;
@@ -557,7 +557,7 @@ int orc_ext_solve_team(const orc_gains *g, const orc_options *o, int T, int N, c
 }
 
 typedef struct {
-  const orc_gains *g; const orc_options *o; int nteams, T, N, K_obs, tid, nthreads; double eps_obs, eps_nbr, relax, pub_tol;
+  const orc_gains *g; const orc_options *o; int nteams, T, N, K_obs, tid, nthreads; double eps_obs, eps_nbr, relax, pub_tol; int max_team_iters;
   const double *x0, *xdes, *feet, *obs; const int *contact; orc_ext_result *res; int *team_iters;
 } teams_arg;
 
@@ -566,20 +566,20 @@ static void *teams_worker(void *vp) {
   const int T = a->T, N = a->N, ND = N / 4;
   for (int t = a->tid; t < a->nteams; t += a->nthreads)
     orc_ext_solve_team(a->g, a->o, T, N, a->x0 + 4 * (size_t)T * t, a->xdes + 4 * (size_t)N * T * t, a->feet + 8 * (size_t)ND * T * t,
-                       a->contact + 4 * (size_t)T * t, a->K_obs, a->obs + 2 * (size_t)a->K_obs * T * t, a->eps_obs, a->eps_nbr, a->relax, a->pub_tol,
+                       a->contact + 4 * (size_t)T * t, a->K_obs, a->obs + 2 * (size_t)a->K_obs * T * t, a->eps_obs, a->eps_nbr, a->relax, a->pub_tol, a->max_team_iters,
                        a->res + (size_t)T * t, a->team_iters ? a->team_iters + t : NULL);
   return NULL;
 }
 
 int orc_ext_solve_teams(const orc_gains *g, const orc_options *o, int nteams, int T, int N, const double *x0, const double *xdes,
                         const double *feet_xy, const int *contact, int K_obs, const double *obs_xy, double eps_obs, double eps_nbr,
-                        double relax, double pub_tol, int nthreads, orc_ext_result *res, int *team_iters) {
+                        double relax, double pub_tol, int max_team_iters, int nthreads, orc_ext_result *res, int *team_iters) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
   pthread_t th[256];
   teams_arg args[256];
   for (int t = 0; t < nthreads; t++) {
-    teams_arg a = {g, o, nteams, T, N, K_obs, t, nthreads, eps_obs, eps_nbr, relax, pub_tol, x0, xdes, feet_xy, obs_xy, contact, res, team_iters};
+    teams_arg a = {g, o, nteams, T, N, K_obs, t, nthreads, eps_obs, eps_nbr, relax, pub_tol, max_team_iters, x0, xdes, feet_xy, obs_xy, contact, res, team_iters};
     args[t] = a;
     if (nthreads > 1) pthread_create(&th[t], NULL, teams_worker, &args[t]);
   }

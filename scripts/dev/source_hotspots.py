@@ -53,7 +53,7 @@ if len(rows) != len(lines):
 fn_at = []
 hpath = os.path.join(ROOT, "srb-cbf-nmpc_b200", "csrc", HEADER)
 for n, l in enumerate(open(hpath), 1):
-    m = re.match(r"\s{0,2}(?:template\s*<[^>]*>\s*)?(?:LDEV|LMEM|__device__(?:\s+__forceinline__)?)\s+[\w:<>\s\*&]*?(\w+)\s*\(", l)
+    m = re.match(r"\s{0,2}(?:template\s*<[^>]*>\s*)?(?:LDEV|LMEM|XDEV|XMEM|__device__(?:\s+__forceinline__)?)\s+[\w:<>\s\*&]*?(\w+)\s*\(", l)
     if m: fn_at.append((n, m.group(1)))
 def fn_of(f, n):
     if f != HEADER: return f

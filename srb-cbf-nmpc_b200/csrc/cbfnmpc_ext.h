@@ -34,6 +34,7 @@
 struct XParams {
   KParams k;
   double eps_obs, eps_nbr, relax, pub_tol;
+  int max_team_it;   // iterations of a team's loop (a team that has not settled by then keeps the statuses its members have)
 };
 
 struct ExtIO {
@@ -1279,7 +1280,7 @@ XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, X
       } else {
         more = cy.stepped_prev != 0;
       }
-      if (more) { cy.team_it++; if (cy.team_it >= 4 * P.max_iter) more = false; }
+      if (more) { cy.team_it++; if (cy.team_it >= XP.max_team_it) more = false; }
       if (!more) cy.team_done = 1;
     }
     first = false;

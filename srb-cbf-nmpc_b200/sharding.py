@@ -70,3 +70,21 @@ def exchange_state_other(dist, q, dq, device=None):
         allb = torch.stack(parts)
     others = torch.tensor([r for r in range(world) if r != rank], dtype=torch.long, device=mine.device)
     return allb.index_select(0, others).reshape(4 * (world - 1), mine.shape[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------- extended mode
+def sharded_group(rank, world, team_size):
+    """Agent-sharded teams over `world` ranks (cbfnmpc_ext_solve_sharded): ranks are cut into groups of G = min(world, team_size)
+    ranks that share teams; inside a group rank g holds members [g m, (g + 1) m), m = team_size / G, of every team of the group.
+    Returns (group index, rank inside the group, G, members per rank, number of groups)."""
+    G = min(world, team_size)
+    if team_size % G != 0 or world % G != 0:
+        raise ValueError("world size %d and team size %d do not tile" % (world, team_size))
+    return rank // G, rank % G, G, team_size // G, world // G
+
+
+def member_major(n_teams, team_size, members):
+    """Indices into a team-major batch (instance = team * team_size + member) of the member-major local batch that holds `members`
+    of every team (local instance = local member * n_teams + team)."""
+    import numpy as np
+    return np.array([t * team_size + m for m in members for t in range(n_teams)], dtype=np.int64)

@@ -88,3 +88,30 @@ def test_two_rank_state_other_exchange():
     (_, q0, dq0, so0), (_, q1, dq1, so1) = res
     assert so0.shape == so1.shape == (4, 5)
     assert np.array_equal(so0, np.vstack([q1, dq1])) and np.array_equal(so1, np.vstack([q0, dq0]))
+
+
+def test_agent_sharded_layout_of_the_extended_mode():
+    """Host-side logic of cbfnmpc_ext_solve_sharded's layout: groups of ranks that share teams, member blocks per rank, and the
+    member-major <-> team-major index maps (what examples/agent_sharded_ext.py and bench.py build their local batches with)."""
+    import numpy as np
+    from srb_cbf_nmpc_b200 import sharding as SH
+    assert SH.sharded_group(0, 1, 4) == (0, 0, 1, 4, 1)
+    assert SH.sharded_group(1, 2, 4) == (0, 1, 2, 2, 1)
+    assert SH.sharded_group(3, 4, 4) == (0, 3, 4, 1, 1)
+    assert SH.sharded_group(6, 8, 4) == (1, 2, 4, 1, 2)
+    n_teams, T = 5, 4
+    seen = np.zeros(n_teams * T, int)
+    for world in (1, 2, 4):
+        seen[:] = 0
+        for rank in range(world):
+            grp, grank, G, mpr, ng = SH.sharded_group(rank, world, T)
+            idx = SH.member_major(n_teams, T, list(range(grank * mpr, (grank + 1) * mpr)))
+            assert len(idx) == mpr * n_teams
+            # local instance = local member * n_teams + team; the neighbour blocks of the gathered buffer are indexed by GLOBAL member
+            for li, gi in enumerate(idx):
+                assert gi // T == li % n_teams and gi % T == grank * mpr + li // n_teams
+            seen[idx] += 1
+        assert (seen == 1).all()
+    import pytest
+    with pytest.raises(ValueError):
+        SH.sharded_group(0, 3, 4)
