@@ -6,6 +6,8 @@
 //   build:  g++ -std=c++17 -O2 -Iinclude examples/team_cycles.cpp -Lsrb-cbf-nmpc_b200/lib -lcbfnmpc -Wl,-rpath,'$ORIGIN/../srb-cbf-nmpc_b200/lib' -o examples/team_cycles
 //   run  :  examples/team_cycles [cycles] [use_snopt 0/1]      prints one line per agent and cycle:
 //           cycle agent status kkt slack X[16] alpha[20]
+//           examples/team_cycles --extended [cycles] [k_obs]  the team solved with inter-agent rows (extended mode: BASELINE config 2,
+//                                                             no reference implementation exists); same output lines as the plain run
 //           examples/team_cycles --nlptuple [cycles]          every cycle also solved through the dense nlpTuple boundary
 //                                                             (cbfnmpc_pack_dense + cbfnmpc_solve_dense_nlptuple); one JSON line
 //           examples/team_cycles --latency [cycles]           one JSON line: p50 / p90 wall time of MPC_dist_gpu::run_NMPC() (one
@@ -23,8 +25,10 @@ int main(int argc, char** argv) {
   using namespace cbfnmpc;
   const bool latency = argc > 1 && std::strcmp(argv[1], "--latency") == 0;
   const bool check_tuple = argc > 1 && std::strcmp(argv[1], "--nlptuple") == 0;
-  const int cycles = (latency || check_tuple) ? (argc > 2 ? atoi(argv[2]) : (latency ? 300 : 4)) : (argc > 1 ? atoi(argv[1]) : 3);
-  const bool nlp = (latency || check_tuple) ? true : (argc > 2 ? atoi(argv[2]) != 0 : true);
+  const bool extended = argc > 1 && std::strcmp(argv[1], "--extended") == 0;   // BASELINE config 2: inter-agent rows (extended mode)
+  const int cycles = (latency || check_tuple || extended) ? (argc > 2 ? atoi(argv[2]) : (latency ? 300 : 4)) : (argc > 1 ? atoi(argv[1]) : 3);
+  const bool nlp = (latency || check_tuple || extended) ? true : (argc > 2 ? atoi(argv[2]) != 0 : true);
+  const int k_obs_ext = (extended && argc > 3) ? atoi(argv[3]) : 1;
   double tuple_x[4][41] = {{0}}, tuple_worst = 0.0; int tuple_status[4] = {0}, tuple_status_mismatch = 0;
   const bool tuple_four[2] = {true, false};  // stance: 4 feet during the first two cycles, a diagonal pair afterwards
   const int ncols = 4 * (cycles + 1);
@@ -87,7 +91,7 @@ int main(int argc, char** argv) {
         t_one.push_back(ms(t0, t1));
       }
       auto t0 = now();
-      team.run_NMPC();
+      if (extended) team.run_NMPC_extended(k_obs_ext); else team.run_NMPC();
       auto t1 = now();
       t_team.push_back(ms(t0, t1));
       for (int a = 0; a < 4; a++) {

@@ -21,6 +21,7 @@
 // does sequentially).
 #pragma once
 #include <cstdint>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -253,9 +254,47 @@ class MPC_dist_gpu_team {
     for (int b = 0; b < B; b++) agents_[b]->consume(bt, b);
   }
 
+  // EXTENDED MODE (include/cbfnmpc.h; SURVEY.md A.6 -- no reference implementation exists): the same cycle with inter-agent rows.
+  // Every agent gets one distance row per grid point against each of its k_obs nearest real obstacles and against every team
+  // mate's predicted position at that grid point (threshold eps_nbr: dec_vars_constr_cost.h:402 "epsilon = 2.2 // for robot to
+  // robot"); the team mates' trajectories are exchanged at every interior-point iteration inside the solve.  This is BASELINE
+  // config 2 ("4-agent team with inter-agent CBFs, one cycle per agent").  The team must have 1, 2 or 4 agents in one stance class.
+  void run_NMPC_extended(int k_obs = 1, const cbfnmpc_ext_cfg* cfg_in = nullptr) {
+    const int B = (int)agents_.size(), N = 4;
+    if (B != 1 && B != 2 && B != 4) throw Error(CBFNMPC_ERR_ARG, "extended mode: teams of 1, 2 or 4 agents");
+    Batch bt(B, agents_[0]->n_obs());
+    for (int b = 0; b < B; b++) agents_[b]->pack(bt, b);
+    const int K = bt.K < k_obs ? bt.K : k_obs;
+    std::vector<double> obs(2 * (size_t)K * B);
+    for (int b = 0; b < B; b++) {   // the K nearest obstacles of agent b, nearest first (ties: lower index)
+      std::vector<int> idx(bt.K);
+      for (int k = 0; k < bt.K; k++) idx[k] = k;
+      const double px = bt.x0[b], py = bt.x0[2 * (size_t)B + b];
+      std::stable_sort(idx.begin(), idx.end(), [&](int i, int j) {
+        const double di = std::hypot(bt.obs[(size_t)i * B + b] - px, bt.obs[(size_t)(bt.K + i) * B + b] - py);
+        const double dj = std::hypot(bt.obs[(size_t)j * B + b] - px, bt.obs[(size_t)(bt.K + j) * B + b] - py);
+        return di < dj;
+      });
+      for (int k = 0; k < K; k++) { obs[(size_t)k * B + b] = bt.obs[(size_t)idx[k] * B + b]; obs[(size_t)(K + k) * B + b] = bt.obs[(size_t)(bt.K + idx[k]) * B + b]; }
+    }
+    cbfnmpc_ext_cfg cfg;
+    if (cfg_in) cfg = *cfg_in; else cbfnmpc_ext_default_cfg(&cfg);
+    cfg.N = N; cfg.team_size = B;
+    cbfnmpc_ext_in in = {bt.x0.data(), bt.xdes.data(), bt.feet.data(), bt.contact.data(), obs.data(), K, bt.abuf.data(), nullptr, 0};
+    std::vector<int32_t> team_iters(B);
+    cbfnmpc_ext_out out = {bt.X.data(), bt.U.data(), bt.lam.data(), bt.slack.data(), bt.xqp.data(), bt.alpha.data(), bt.abuf_next.data(), bt.kkt.data(), nullptr,
+                           bt.status.data(), bt.qp_iters.data(), bt.nlp_iters.data(), team_iters.data()};
+    int rc = cbfnmpc_ext_solve_batch_host(ctx_->get(), B, &cfg, &in, &out);
+    if (rc != CBFNMPC_OK) throw Error(rc, std::string("cbfnmpc_ext_solve_batch_host: ") + cbfnmpc_last_error());
+    for (int b = 0; b < B; b++) agents_[b]->consume(bt, b);
+    team_iters_ = team_iters[0];
+  }
+  int team_iters() const { return team_iters_; }
+
  private:
   Context* ctx_;
   std::vector<MPC_dist_gpu*> agents_;
+  int team_iters_ = 0;
 };
 
 }  // namespace cbfnmpc

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 
 #define EPSM 2.220446049250313e-16
@@ -22,7 +23,7 @@ struct orc_ext {
   int *ipiv;
   double filt_t[16], filt_p[16]; int nfilt;
   double mu, tau, dw_last, theta_max, theta_min, E0;
-  int first_ic, status, it, n_fact, n_ls, n_bump, started, finished;
+  int first_ic, status, it, n_fact, n_ls, n_bump, started, finished, mu_age, mu_stall;
   double x_qp[ORC_EXT_NV_MAX]; int qp_flag, qp_iters;
 };
 
@@ -90,6 +91,9 @@ void orc_ext_pack_dense(const orc_gains *g, int N, const double *x0, const doubl
 }
 
 /* velocity variable of one-sided row q (0 .. 2N-1): v_x of grid points 0..N-1, then v_y (DV:270-279 order) */
+/* ORC_EXT_TRACE=1 in the environment: one line per iteration and agent on stderr (debugging aid) */
+static int ext_trace(void) { static int t = -1; if (t < 0) t = getenv("ORC_EXT_TRACE") ? 1 : 0; return t; }
+
 static int vel_idx(int N, int q) { return q < N ? 4 * q + 1 : 4 * (q - N) + 3; }
 
 static void ext_cons(const orc_ext *e, const double *x, double *cv) { /* c(x) >= 0: [h - Gx | d - eps | vmax - v | vmax + v] */
@@ -236,7 +240,7 @@ orc_ext *orc_ext_create(const orc_gains *g, const orc_options *o, int N, const d
   e->s = e->rd + nv; e->z = e->s + m; e->st = e->z + m; e->ds = e->st + m; e->dz = e->ds + m; e->sig = e->dz + m; e->sprev = e->sig + m;
   e->y = e->sprev + m; e->dy = e->y + p; e->re = e->dy + p;
   e->ipiv = (int *)malloc(sizeof(int) * NK);
-  e->status = 1;
+  e->status = 1; e->mu_stall = 6;
   return e;
 }
 
@@ -267,7 +271,7 @@ void orc_ext_begin(orc_ext *e, const double *nbr) {
   ext_interior_start(e, e->x);
   ext_cons(e, e->x, e->s);
   e->mu = o->mu_init; e->tau = fmax(o->tau_min, 1 - e->mu); e->dw_last = 0.0;
-  e->first_ic = 1; e->status = 1; e->it = 0; e->n_fact = 0; e->n_ls = 0; e->n_bump = 0; e->nfilt = 0; e->finished = 0; e->started = 1;
+  e->mu_age = 0; e->first_ic = 1; e->status = 1; e->it = 0; e->n_fact = 0; e->n_ls = 0; e->n_bump = 0; e->nfilt = 0; e->finished = 0; e->started = 1;
   for (int r = 0; r < m; r++) {
     if (!(e->s[r] > 0)) e->status = 4;
     e->z[r] = e->mu / e->s[r];
@@ -332,6 +336,7 @@ int orc_ext_iter(orc_ext *e, const double *nbr) {
   for (int r = 0; r < m; r++) e_c = fmax(e_c, fabs(s[r] * z[r]));
   double E0 = fmax(e_d, fmax(e_p, e_c));
   e->E0 = E0;
+  if (ext_trace()) fprintf(stderr, "[%p] it %d mu %.2e E0 %.3e ed %.2e ep %.2e ec %.2e dl %.6f\n", (void *)e, it, e->mu, E0, e_d, e_p, e_c, x[n - 1]);
   for (int r = 0; r < m; r++) e->sprev[r] = s[r];
   {
     int spos = 1;
@@ -343,15 +348,28 @@ int orc_ext_iter(orc_ext *e, const double *nbr) {
     for (int r = 0; r < m; r++) zmax = fmax(zmax, z[r]);
     if (!(zmax < o->z_div) || !isfinite(E0) || !spos) { e->status = 2; e->finished = 1; return 2; }
   }
-  for (;;) { /* barrier update (Ipopt eq. 7) */
-    double emu = 0;
-    for (int r = 0; r < m; r++) emu = fmax(emu, fabs(s[r] * z[r] - e->mu));
-    emu = fmax(emu, fmax(e_d, e_p));
-    if (emu <= o->kappa_eps * e->mu && e->mu > o->tol / 10) {
+  {
+    int decreased = 0;
+    for (;;) { /* barrier update (Ipopt eq. 7) */
+      double emu = 0;
+      for (int r = 0; r < m; r++) emu = fmax(emu, fabs(s[r] * z[r] - e->mu));
+      emu = fmax(emu, fmax(e_d, e_p));
+      if (emu <= o->kappa_eps * e->mu && e->mu > o->tol / 10) {
+        e->mu = fmax(o->tol / 10, fmin(o->kappa_mu * e->mu, pow(e->mu, o->theta_mu)));
+        e->tau = fmax(o->tau_min, 1 - e->mu);
+        e->nfilt = 0;
+        decreased = 1;
+      } else break;
+    }
+    /* IPM-F-J only: neighbours that keep moving can hold the barrier subproblem's error just above kappa_eps mu for good (each
+     * move costs the agent a little slack, the repair perturbs its dual residual: 0.2 % of the config-4 teams); after mu_stall
+     * iterations without a decrease the barrier parameter is lowered anyway */
+    if (decreased) e->mu_age = 0;
+    else if (e->n_nbr > 0 && ++e->mu_age >= e->mu_stall && e->mu > o->tol / 10) {
       e->mu = fmax(o->tol / 10, fmin(o->kappa_mu * e->mu, pow(e->mu, o->theta_mu)));
       e->tau = fmax(o->tau_min, 1 - e->mu);
-      e->nfilt = 0;
-    } else break;
+      e->mu_age = 0;
+    }
   }
   const double mu = e->mu, tau = e->tau;
   double *sig = e->sig, *rhs = e->rhs, *sol = e->sol, *dx = e->dx, *dy = e->dy, *ds = e->ds, *dz = e->dz, *xt = e->xt, *st = e->st;
@@ -454,6 +472,7 @@ int orc_ext_iter(orc_ext *e, const double *nbr) {
     if (accepted) break;
     alpha *= 0.5;
   }
+  if (ext_trace()) fprintf(stderr, "[%p]    dw %.1e apmax %.3e admax %.3e ddl %.3e dphi %.3e alpha %.3e acc %d ftype %d ph %.10e nfilt %d th %.2e\n", (void *)e, dw, a_pmax, a_dmax, dx[n - 1], dphi, alpha, accepted, ftype, ph, e->nfilt, th);
   if (!accepted) { e->status = 2; e->finished = 1; return 2; }
   if (!ftype) {
     if (e->nfilt >= o->filter_cap) {
@@ -510,7 +529,7 @@ int orc_ext_solve(const orc_gains *g, const orc_options *o, int N, const double 
 
 int orc_ext_solve_team(const orc_gains *g, const orc_options *o, int T, int N, const double *x0, const double *xdes, const double *feet_xy,
                        const int *contact, int K_obs, const double *obs_xy, double eps_obs, double eps_nbr, double relax, double pub_tol,
-                       int max_team_iters, orc_ext_result *res, int *team_iters) {
+                       int max_team_iters, int mu_stall, orc_ext_result *res, int *team_iters) {
   const int ND = N / 4, nn = T - 1;
   orc_ext *ag[8];
   double pos[8][2 * ORC_EXT_NMAX], nbr[7 * 2 * ORC_EXT_NMAX];
@@ -518,7 +537,7 @@ int orc_ext_solve_team(const orc_gains *g, const orc_options *o, int T, int N, c
   for (int a = 0; a < T; a++) {
     ag[a] = orc_ext_create(g, o, N, x0 + 4 * a, xdes + 4 * N * a, feet_xy + 8 * ND * a, contact + 4 * a, K_obs, obs_xy + 2 * (size_t)K_obs * a,
                            eps_obs, nn, eps_nbr);
-    if (ag[a]) orc_ext_qp(ag[a]);
+    if (ag[a]) { ag[a]->mu_stall = mu_stall; orc_ext_qp(ag[a]); }
   }
   for (int a = 0; a < T; a++) { /* a member with bad input stays where it was measured */
     if (ag[a]) orc_ext_positions(ag[a], pos[a]);
@@ -557,7 +576,7 @@ int orc_ext_solve_team(const orc_gains *g, const orc_options *o, int T, int N, c
 }
 
 typedef struct {
-  const orc_gains *g; const orc_options *o; int nteams, T, N, K_obs, tid, nthreads; double eps_obs, eps_nbr, relax, pub_tol; int max_team_iters;
+  const orc_gains *g; const orc_options *o; int nteams, T, N, K_obs, tid, nthreads; double eps_obs, eps_nbr, relax, pub_tol; int max_team_iters, mu_stall;
   const double *x0, *xdes, *feet, *obs; const int *contact; orc_ext_result *res; int *team_iters;
 } teams_arg;
 
@@ -566,20 +585,20 @@ static void *teams_worker(void *vp) {
   const int T = a->T, N = a->N, ND = N / 4;
   for (int t = a->tid; t < a->nteams; t += a->nthreads)
     orc_ext_solve_team(a->g, a->o, T, N, a->x0 + 4 * (size_t)T * t, a->xdes + 4 * (size_t)N * T * t, a->feet + 8 * (size_t)ND * T * t,
-                       a->contact + 4 * (size_t)T * t, a->K_obs, a->obs + 2 * (size_t)a->K_obs * T * t, a->eps_obs, a->eps_nbr, a->relax, a->pub_tol, a->max_team_iters,
+                       a->contact + 4 * (size_t)T * t, a->K_obs, a->obs + 2 * (size_t)a->K_obs * T * t, a->eps_obs, a->eps_nbr, a->relax, a->pub_tol, a->max_team_iters, a->mu_stall,
                        a->res + (size_t)T * t, a->team_iters ? a->team_iters + t : NULL);
   return NULL;
 }
 
 int orc_ext_solve_teams(const orc_gains *g, const orc_options *o, int nteams, int T, int N, const double *x0, const double *xdes,
                         const double *feet_xy, const int *contact, int K_obs, const double *obs_xy, double eps_obs, double eps_nbr,
-                        double relax, double pub_tol, int max_team_iters, int nthreads, orc_ext_result *res, int *team_iters) {
+                        double relax, double pub_tol, int max_team_iters, int mu_stall, int nthreads, orc_ext_result *res, int *team_iters) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
   pthread_t th[256];
   teams_arg args[256];
   for (int t = 0; t < nthreads; t++) {
-    teams_arg a = {g, o, nteams, T, N, K_obs, t, nthreads, eps_obs, eps_nbr, relax, pub_tol, max_team_iters, x0, xdes, feet_xy, obs_xy, contact, res, team_iters};
+    teams_arg a = {g, o, nteams, T, N, K_obs, t, nthreads, eps_obs, eps_nbr, relax, pub_tol, max_team_iters, mu_stall, x0, xdes, feet_xy, obs_xy, contact, res, team_iters};
     args[t] = a;
     if (nthreads > 1) pthread_create(&th[t], NULL, teams_worker, &args[t]);
   }

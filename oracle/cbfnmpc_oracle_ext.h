@@ -59,15 +59,16 @@ int orc_ext_solve(const orc_gains *g, const orc_options *o, int N, const double 
 /* ... and a team of T agents (n_nbr = T - 1; neighbour j of agent a = the j-th OTHER member, in team order), under-relaxed Jacobi:
  * every member publishes pos <- pos + relax (iterate - pos) at the top of an iteration (relax = 0.7: plain Jacobi, relax = 1,
  * overshoots when two members push each other away and oscillates on ~5 % of the config-4 teams); the team has finished when
- * nobody stepped and every published trajectory is within pub_tol of its iterate, or after max_team_iters iterations.  Arrays are agent-major: x0 T x 4, xdes T x 4N, feet_xy T x 8 ND, contact T x 4, obs_xy T x 2 x K_obs.  *team_iters =
+ * nobody stepped and every published trajectory is within pub_tol of its iterate, or after max_team_iters iterations.  In team
+ * mode a member whose barrier parameter has not decreased for mu_stall iterations lowers it anyway (see orc_ext_iter).  Arrays are agent-major: x0 T x 4, xdes T x 4N, feet_xy T x 8 ND, contact T x 4, obs_xy T x 2 x K_obs.  *team_iters =
  * iterations of the team loop.  Returns 0 when every member converged. */
 int orc_ext_solve_team(const orc_gains *g, const orc_options *o, int T, int N, const double *x0, const double *xdes, const double *feet_xy,
                        const int *contact, int K_obs, const double *obs_xy, double eps_obs, double eps_nbr, double relax, double pub_tol,
-                       int max_team_iters, orc_ext_result *res, int *team_iters);
+                       int max_team_iters, int mu_stall, orc_ext_result *res, int *team_iters);
 /* nteams teams (or, with T = 1, independent agents) on nthreads host threads; arrays as above with a leading team index */
 int orc_ext_solve_teams(const orc_gains *g, const orc_options *o, int nteams, int T, int N, const double *x0, const double *xdes,
                         const double *feet_xy, const int *contact, int K_obs, const double *obs_xy, double eps_obs, double eps_nbr,
-                        double relax, double pub_tol, int max_team_iters, int nthreads, orc_ext_result *res, int *team_iters);
+                        double relax, double pub_tol, int max_team_iters, int mu_stall, int nthreads, orc_ext_result *res, int *team_iters);
 
 int orc_bk_factor(int n, double *A, int lda, int *ipiv);
 void orc_bk_inertia(int n, const double *A, int lda, const int *ipiv, int *npos, int *nneg, int *nzero);

@@ -374,7 +374,7 @@ def _ext_lib():
         L.orc_ext_solve.argtypes = [C.POINTER(Gains), C.POINTER(Options), C.c_int, dp, dp, dp, ip, C.c_int, dp, C.c_double, C.c_int,
                                     C.c_double, vp, C.POINTER(ExtResult)]
         L.orc_ext_solve_teams.argtypes = [C.POINTER(Gains), C.POINTER(Options), C.c_int, C.c_int, C.c_int, dp, dp, dp, ip, C.c_int, dp,
-                                          C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(ExtResult), ip]
+                                          C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(ExtResult), ip]
         L._ext_ready = True
     return L
 
@@ -412,10 +412,10 @@ def ext_solve(x0, xdes, feet, contact, obs, nbr=None, N=4, eps_obs=None, eps_nbr
     return ext_res_to_dict(r)
 
 
-EXT_RELAX, EXT_PUB_TOL, EXT_MAX_TEAM_ITERS = 0.7, 1e-10, 100
+EXT_RELAX, EXT_PUB_TOL, EXT_MAX_TEAM_ITERS, EXT_MU_STALL = 0.7, 1e-10, 100, 6
 
 
-def ext_solve_teams(x0, xdes, feet, contact, obs, T, N=4, eps_obs=None, eps_nbr=2.2, relax=EXT_RELAX, pub_tol=EXT_PUB_TOL, max_team_iters=EXT_MAX_TEAM_ITERS, nthreads=8, g=None, o=None):
+def ext_solve_teams(x0, xdes, feet, contact, obs, T, N=4, eps_obs=None, eps_nbr=2.2, relax=EXT_RELAX, pub_tol=EXT_PUB_TOL, max_team_iters=EXT_MAX_TEAM_ITERS, mu_stall=EXT_MU_STALL, nthreads=8, g=None, o=None):
     """nteams teams of T agents (agent-major arrays with leading dimension nteams * T): x0 (B,4) xdes (B,4N) feet (B,ND,2,4)
     contact (B,4) obs (B,2,K_obs).  T = 1: independent agents.  Returns (list of result dicts, team iteration counts)."""
     g = g or default_gains(); o = o or default_options()
@@ -423,5 +423,5 @@ def ext_solve_teams(x0, xdes, feet, contact, obs, T, N=4, eps_obs=None, eps_nbr=
     res = (ExtResult * B)(); ti = np.zeros(nteams, np.int32)
     _ext_lib().orc_ext_solve_teams(C.byref(g), C.byref(o), nteams, T, N, _f(x0).ravel(), _f(xdes).ravel(), _f(feet).ravel(),
                                    np.ascontiguousarray(contact, np.int32).ravel(), K, _f(obs).ravel(), g.eps_dist if eps_obs is None else eps_obs,
-                                   eps_nbr, relax, pub_tol, max_team_iters, nthreads, res, ti)
+                                   eps_nbr, relax, pub_tol, max_team_iters, mu_stall, nthreads, res, ti)
     return [ext_res_to_dict(r) for r in res], ti

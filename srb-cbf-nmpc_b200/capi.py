@@ -108,7 +108,7 @@ def out_struct(o, B=None):
 
 # ---------------------------------------------------------------------------------------------------------------- extended mode
 class ExtCfg(C.Structure):
-    _fields_ = [("N", C.c_int), ("team_size", C.c_int), ("eps_obs", C.c_double), ("eps_nbr", C.c_double), ("relax", C.c_double), ("pub_tol", C.c_double), ("max_team_iters", C.c_int)]
+    _fields_ = [("N", C.c_int), ("team_size", C.c_int), ("eps_obs", C.c_double), ("eps_nbr", C.c_double), ("relax", C.c_double), ("pub_tol", C.c_double), ("max_team_iters", C.c_int), ("mu_stall_iters", C.c_int)]
 
 
 class ExtIn(C.Structure):

@@ -22,7 +22,10 @@
 #include "ext_prims.h"
 
 #define XNT 32   // threads per CTA = one warp = stride of the thread-private shared-memory columns
-#define XKC 2    // rows per grid point kept in quasi-definite form when their Sigma exceeds the cap
+#ifndef XKC
+#define XKC 1    // rows per grid point kept in quasi-definite form when their Sigma exceeds the cap (1 or 2).  A second stiff row of the same
+                 // grid point is condensed with its full Sigma; the accuracy that costs is restored by the iterative refinement.
+#endif
 #define XUNR _Pragma("unroll")
 #ifndef XSLOT_UNROLL
 #define XSLOT_UNROLL 2
@@ -34,6 +37,7 @@
 struct XParams {
   KParams k;
   double eps_obs, eps_nbr, relax, pub_tol;
+  int mu_stall;      // team mode: iterations without a decrease after which the barrier parameter is lowered anyway
   int max_team_it;   // iterations of a team's loop (a team that has not settled by then keeps the statuses its members have)
 };
 
@@ -85,6 +89,7 @@ struct XDims {
 };
 // per distance row: centre (2), slack, 1/slack, multiplier, e(dx), dz, slack of the previous iteration
 #define XJ_SFLOOR 1e-12
+#define XQD_CHECK 1e11   // largest Sigma of a lane's rows above which the Newton residual is checked (iterative refinement)
 #define XROW 8
 #define XR_CX 0
 #define XR_CY 1
@@ -109,7 +114,7 @@ struct XDims {
 #endif
 XHD constexpr int ext_npriv(int K) { return XDims<4>::NFIX + XROW * K; }
 // registers of a lane that survive between launches of a resumable run (after the private columns)
-#define XSTATE_REGS 40
+#define XSTATE_REGS 44
 XHD constexpr int ext_nstate(int K) { return ext_npriv(K) + XSTATE_REGS; }
 
 struct XKV { double xs[4], us[2], lm[4], dl, pi[4], nu[2], eta; };
@@ -172,11 +177,11 @@ template <int NW> XDEV void x_bwd(const double* L, double* b) {
 XDEV void x_chol2(int kc, double t00, double t10, double t11, double* Tc) {
   const double i0 = x_rsq(t00);
   Tc[0] = i0; Tc[1] = 0.0; Tc[2] = 1.0;
-  if (kc == 2) { const double l10 = t10 * i0; Tc[1] = l10; Tc[2] = x_rsq(t11 - l10 * l10); }
+  if (XKC == 2 && kc == 2) { const double l10 = t10 * i0; Tc[1] = l10; Tc[2] = x_rsq(t11 - l10 * l10); }
 }
 XDEV void x_chol2_solve(int kc, const double* Tc, double* b) {
   const double y0 = b[0] * Tc[0];
-  if (kc == 2) { const double y1 = (b[1] - Tc[1] * y0) * Tc[2]; b[1] = y1 * Tc[2]; b[0] = (y0 - Tc[1] * b[1]) * Tc[0]; }
+  if (XKC == 2 && kc == 2) { const double y1 = (b[1] - Tc[1] * y0) * Tc[2]; b[1] = y1 * Tc[2]; b[0] = (y0 - Tc[1] * b[1]) * Tc[0]; }
   else b[0] = y0 * Tc[0];
 }
 XDEV void x_Ax(const KParams& P, const double* x, double* y) {
@@ -202,7 +207,7 @@ struct XSolver {
   int nsq, nsn;
   int status, qp_iters, qp_flag, nlp_iters, n_fact;
   double kkt, mu, sigma;
-  int qp_it, nl_it, nfilt;
+  int qp_it, nl_it, nfilt, mu_age;
   bool first_ic, hold;
 
   XMEM double& row(int r, int fld) const { return pr(d::F_ROWS + XROW * r + fld); }
@@ -389,16 +394,16 @@ struct XSolver {
           }
         }
         t00 = cap[0].srinv + f.Ym[0][0] * f.Ym[0][0] + f.Ym[0][1] * f.Ym[0][1] + f.Ym[0][2] * f.Ym[0][2];
-        if (f.kc == 2) {
-          t10 = f.Ym[1][0] * f.Ym[0][0] + f.Ym[1][1] * f.Ym[0][1] + f.Ym[1][2] * f.Ym[0][2];
-          t11 = cap[1].srinv + f.Ym[1][0] * f.Ym[1][0] + f.Ym[1][1] * f.Ym[1][1] + f.Ym[1][2] * f.Ym[1][2];
+        if (XKC == 2 && f.kc == 2) {
+          t10 = f.Ym[XKC - 1][0] * f.Ym[0][0] + f.Ym[XKC - 1][1] * f.Ym[0][1] + f.Ym[XKC - 1][2] * f.Ym[0][2];
+          t11 = cap[XKC - 1].srinv + f.Ym[XKC - 1][0] * f.Ym[XKC - 1][0] + f.Ym[XKC - 1][1] * f.Ym[XKC - 1][1] + f.Ym[XKC - 1][2] * f.Ym[XKC - 1][2];
         }
         x_chol2(f.kc, t00, t10, t11, f.Tc);
         // V = Lt^-1 N~ ; P_j += V'V
         double V0[5], V1[5];
         XUNR for (int m = 0; m < 5; m++) {
           V0[m] = f.Nt[0][m] * f.Tc[0];
-          V1[m] = (f.kc == 2) ? (f.Nt[1][m] - f.Tc[1] * V0[m]) * f.Tc[2] : 0.0;
+          V1[m] = (XKC == 2 && f.kc == 2) ? (f.Nt[XKC - 1][m] - f.Tc[1] * V0[m]) * f.Tc[2] : 0.0;
         }
         XUNR for (int i = 0; i < 5; i++) XUNR for (int k = 0; k <= i; k++) Pout[xsy(i, k)] += V0[i] * V0[k] + V1[i] * V1[k];
       }
@@ -445,7 +450,8 @@ struct XSolver {
   }
 
   // Solve [H A'; A 0][dx; dy] = r with the current factorisation.  tq = multipliers t of this lane's quasi-definite rows.
-  XMEM void kkt_solve(const KParams& P, double dw, const XKV& r, XKV& dd, double* tq) const {
+  // rq = right-hand side of the quasi-definite rows (g'dx - t / (Sigma - cap) = rq; zero in the first solve, the residual in refinement)
+  XMEM void kkt_solve(const KParams& P, double dw, const XKV& r, const double* rq, XKV& dd, double* tq) const {
     XMain m; double d0[2];
     stage_eliminate(P, dw, r, m, d0);
     // ---- backward chain
@@ -467,11 +473,11 @@ struct XSolver {
       x_fwd<NW>(f.Lc, k0);
       XUNR for (int a = 0; a < 3; a++) ykr[a] = k0[a];
       x_bwd<NW>(f.Lc, k0);
-      double tt[XKC] = {0.0, 0.0};
+      double tt[2] = {0.0, 0.0};
       if (f.kc > 0) {
         XUNR for (int qq = 0; qq < XKC; qq++)
           if (qq < f.kc) {
-            double s = cap[qq].gx * m.cv[0] + cap[qq].gy * m.cv[2];
+            double s = cap[qq].gx * m.cv[0] + cap[qq].gy * m.cv[2] - rq[qq];
             XUNR for (int a = 0; a < NW; a++) s += f.Ym[qq][a] * ykr[a];
             tt[qq] = s;
           }
@@ -499,7 +505,7 @@ struct XSolver {
       double xp[5];
       XUNR for (int i = 0; i < 4; i++) { const double t = g_up(g, xn[i]); xp[i] = (step > 0 && g.j > 0) ? t : 0.0; }
       xp[4] = ddl;
-      double tl[XKC] = {0.0, 0.0};
+      double tl[2] = {0.0, 0.0};
       if (f.kc > 0) {
         XUNR for (int qq = 0; qq < XKC; qq++)
           if (qq < f.kc) { double s = 0.0; XUNR for (int i = 0; i < 5; i++) s += f.Nt[qq][i] * xp[i]; tl[qq] = s; }
@@ -570,8 +576,8 @@ struct XSolver {
     }
     qp_flag = 3; qp_iters = 0; qp_it = 0; sigma = 100.0;
     if (!factor<true>(P, 0.0, 0)) { qp_flag = 1; return true; }
-    double tq[2];
-    kkt_solve(P, 0.0, r, dd, tq);
+    double tq[2]; const double rq0[2] = {0.0, 0.0};
+    kkt_solve(P, 0.0, r, rq0, dd, tq);
     x = dd;
     XUNR for (int i = C; i < 4; i++) x.lm[i] = 0.0;
     double xp[4]; prev_state(x, false, xp);
@@ -655,8 +661,8 @@ struct XSolver {
       XUNR for (int i = 0; i < 4; i++) { r.xs[i] += rx.xs[i]; r.lm[i] += rx.lm[i]; r.pi[i] = rx.pi[i]; }
       XUNR for (int a = 0; a < 2; a++) { r.us[a] += rx.us[a]; r.nu[a] = rx.nu[a]; }
       r.dl = rx.dl; r.eta = rx.eta;
-      double tq[2];
-      kkt_solve(P, 0.0, r, dd, tq);
+      double tq[2]; const double rq0[2] = {0.0, 0.0};
+      kkt_solve(P, 0.0, r, rq0, dd, tq);
       double dxp[4]; prev_state(dd, true, dxp);
       scatter<false>(d::Q_DE, dd, dxp);
       double rp = 0.0, rdm = 0.0, s_dsz = 0.0, s_sdz = 0.0, s_dsdz = 0.0;
@@ -765,7 +771,7 @@ struct XSolver {
     XUNR for (int i = 0; i < 4; i++) x.pi[i] = 0.0;
     x.nu[0] = x.nu[1] = 0.0; x.eta = 0.0;
     filter_reset();
-    mu = P.mu_init; XPERS_TAU = fmax(P.tau_min, 1.0 - mu); XPERS_DWLAST = 0.0; first_ic = true; nl_it = 0; XPERS_ADPREV = 0.0; hold = false;
+    mu = P.mu_init; XPERS_TAU = fmax(P.tau_min, 1.0 - mu); XPERS_DWLAST = 0.0; first_ic = true; nl_it = 0; XPERS_ADPREV = 0.0; hold = false; mu_age = 0;
     slots_e(d::N_G, xp);
     bool interior = chk == 0.0;
     XSLOTS for (int s = 0; s < nsn; s++) {
@@ -891,43 +897,57 @@ struct XSolver {
       if (it == P.max_iter) return 2;
       if (!(zmax < P.z_div) || !(E0 < 1e300) || g_any(g, !spos)) { status = 2; return 2; }
     }
-    for (;;) {   // barrier update (Ipopt eq. 7)
-      const double emu = fmax(fmax(szmax - mu, mu - szmin), fmax(e_d, e_p));
-      if (emu <= P.kappa_eps * mu && mu > P.tol / 10.0) {
+    {
+      bool decreased = false;
+      for (;;) {   // barrier update (Ipopt eq. 7)
+        const double emu = fmax(fmax(szmax - mu, mu - szmin), fmax(e_d, e_p));
+        if (emu <= P.kappa_eps * mu && mu > P.tol / 10.0) {
+          mu = fmax(P.tol / 10.0, fmin(P.kappa_mu * mu, mu * sqrt(mu)));
+          XPERS_TAU = fmax(P.tau_min, 1.0 - mu);
+          filter_reset();
+          decreased = true;
+        } else break;
+      }
+      // IPM-F-J only: neighbours that keep moving can hold the subproblem's error just above kappa_eps mu for good (each move costs the
+      // agent a little slack, the repair perturbs its dual residual); after mu_stall iterations without a decrease mu is lowered anyway
+      if (decreased) mu_age = 0;
+      else if (jacobi && ++mu_age >= XP.mu_stall && mu > P.tol / 10.0) {
         mu = fmax(P.tol / 10.0, fmin(P.kappa_mu * mu, mu * sqrt(mu)));
         XPERS_TAU = fmax(P.tau_min, 1.0 - mu);
-        filter_reset();
-      } else break;
+        mu_age = 0;
+      }
     }
     // ---- Hessian blocks and right-hand side
     XKV r;
     int kc = 0;
+    double sig_max = 0.0;
     {
       assemble<true>(P, d::N_C, P.rho_lambda);
       // barrier-gradient weights of the slots (1/s_lo - 1/s_hi) -> N_D (the multiplier steps are written there afterwards)
       XSLOTS for (int s = 0; s < nsn; s++) pr(d::N_D + s) = pr(d::N_A + s) - pr(d::N_B + s);
       gather<true>(d::N_D, r);
       double rdl = 0.0, rx0 = 0.0, rx2 = 0.0;
-      cap[0].srinv = 1.0; cap[1].srinv = 1.0; cap[0].gx = cap[0].gy = cap[1].gx = cap[1].gy = 0.0; cap[0].row = cap[1].row = -1;
-      double s0 = 0.0, s1 = 0.0;   // the two largest Sigma above the cap
+      XUNR for (int q = 0; q < XKC; q++) { cap[q].srinv = 1.0; cap[q].gx = 0.0; cap[q].gy = 0.0; cap[q].row = -1; }
+      double s0 = 0.0, s1 = 0.0;   // the (two) largest Sigma above the cap
       for (int rr = 0; rr < K; rr++) {
         const double sg = row(rr, XR_Z) * row(rr, XR_RS);
         if (sg > P.sigma_cap) {
-          if (sg > s0) { s1 = s0; cap[1] = cap[0]; s0 = sg; cap[0].row = rr; }
-          else if (sg > s1) { s1 = sg; cap[1].row = rr; }
+          if (sg > s0) { if (XKC == 2) { s1 = s0; cap[XKC - 1] = cap[0]; } s0 = sg; cap[0].row = rr; }
+          else if (XKC == 2 && sg > s1) { s1 = sg; cap[XKC - 1].row = rr; }
         }
       }
-      kc = (cap[0].row >= 0 ? 1 : 0) + (cap[1].row >= 0 ? 1 : 0);
+      kc = (cap[0].row >= 0 ? 1 : 0) + ((XKC == 2 && cap[XKC - 1].row >= 0) ? 1 : 0);
+      sig_max = s0;
       for (int rr = 0; rr < K; rr++) {
         const double gx = 2.0 * (x.xs[0] - row(rr, XR_CX)), gy = 2.0 * (x.xs[2] - row(rr, XR_CY));
         const double z = row(rr, XR_Z), rs = row(rr, XR_RS), sg = z * rs;
-        const bool qd = (rr == cap[0].row) || (rr == cap[1].row);
+        const bool qd = (rr == cap[0].row) || (XKC == 2 && rr == cap[XKC - 1].row);
         const double sc = qd ? P.sigma_cap : sg;
         H.hx[0] += sc * gx * gx - 2.0 * z; H.hx[2] += sc * gy * gy - 2.0 * z; H.hxy += sc * gx * gy;
         H.bd[0] += sc * gx; H.bd[1] += sc * gy; H.hd += sc;
         rx0 += mu * rs * gx; rx2 += mu * rs * gy; rdl += mu * rs;
         if (rr == cap[0].row) { cap[0].gx = gx; cap[0].gy = gy; cap[0].srinv = x_rcp(sg - sc); }
-        if (rr == cap[1].row) { cap[1].gx = gx; cap[1].gy = gy; cap[1].srinv = x_rcp(sg - sc); }
+        if (XKC == 2 && rr == cap[XKC - 1].row) { cap[XKC - 1].gx = gx; cap[XKC - 1].gy = gy; cap[XKC - 1].srinv = x_rcp(sg - sc); }
       }
       XUNR for (int i = 0; i < 4; i++) { r.xs[i] = mu * r.xs[i] - gfy.xs[i]; r.lm[i] = (i < C) ? mu * r.lm[i] - gfy.lm[i] : 0.0; r.pi[i] = -re_pi[i]; }
       r.xs[0] += rx0; r.xs[2] += rx2;
@@ -950,40 +970,100 @@ struct XSolver {
       if (!ok) { status = 3; return 2; }
       if (dw > 0.0) { XPERS_DWLAST = dw; first_ic = false; }
     }
-    XKV dd; double tq[2];
-    kkt_solve(P, dw, r, dd, tq);
-    double ddp[4]; prev_state(dd, true, ddp);
-    scatter<true>(d::N_C, dd, ddp);     // e(dx) of the slots -> N_C
-    // ---- pass B: multiplier steps; pass C: step bounds and line-search constants
+    // ---- solve, then iterative refinement on the UNREDUCED Newton system (a row whose Sigma is ~1e15 and over which the stage's own
+    //      controls have little authority -- a 2-foot stance, say -- hands its stiffness on to the previous stage, where the recursion
+    //      then loses digits; one or two refinement solves with the same factors restore them)
+    XKV dd; double tq[2] = {0.0, 0.0};
     double rp = 0.0, rdm = 0.0, prod = 1.0, prod2 = 1.0, dsum = 0.0;
-    XSLOTS for (int s = 0; s < nsn; s++) {
-      const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
-      const double rlo = pr(d::N_A + s), rhi = pr(d::N_B + s), de = pr(d::N_C + s);
-      const double dzl = (mu - slo * zlo) * rlo - zlo * rlo * de;
-      const double dzh = (mu - shi * zhi) * rhi + zhi * rhi * de;
-      pr(d::N_D + s) = dzl; pr(d::N_E + s) = dzh;
-      rp = fmax(rp, fmax(-de * rlo, de * rhi));
-      rdm = fmax(rdm, fmax(-dzl * x_rcp(zlo), -dzh * x_rcp(zhi)));
-      const double ss = slo * shi;
-      if (s & 1) prod *= ss; else prod2 *= ss;
-      dsum += de * rlo - de * rhi;
+    {
+      XKV& rcur = r; double rq[2] = {0.0, 0.0};   // the right-hand side is consumed by the first solve; refinement reuses its storage
+      // checked only when some row is stiff enough to matter (measured: residual 5e-9 of the right-hand side at Sigma ~ 1e11,
+      // 1e-6 .. 1 at 1e13 .. 1e15; below that the recursion is accurate to round-off)
+      const bool any_qd = g_any(g, sig_max > XQD_CHECK);
+      for (int rf = 0;; rf++) {
+        XKV d2; double t2[2];
+        kkt_solve(P, dw, rcur, rq, d2, t2);
+        if (rf == 0) { dd = d2; tq[0] = t2[0]; tq[1] = t2[1]; }
+        else {
+          XUNR for (int i = 0; i < 4; i++) { dd.xs[i] += d2.xs[i]; dd.lm[i] += d2.lm[i]; dd.pi[i] += d2.pi[i]; }
+          XUNR for (int a = 0; a < 2; a++) { dd.us[a] += d2.us[a]; dd.nu[a] += d2.nu[a]; }
+          dd.dl += d2.dl; dd.eta += d2.eta; tq[0] += t2[0]; tq[1] += t2[1];
+        }
+        double ddp[4]; prev_state(dd, true, ddp);
+        scatter<true>(d::N_C, dd, ddp);     // e(dx) of the slots -> N_C
+        // pass B / C: multiplier steps (slots: N_D, N_E; rows: XR_DZ), the weights z + dz for the residual (slots: N_G), step bounds
+        // and line-search constants (recomputed when a refinement solve follows)
+        rp = 0.0; rdm = 0.0; prod = 1.0; prod2 = 1.0; dsum = 0.0;
+        XSLOTS for (int s = 0; s < nsn; s++) {
+          const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
+          const double rlo = pr(d::N_A + s), rhi = pr(d::N_B + s), de = pr(d::N_C + s);
+          const double dzl = (mu - slo * zlo) * rlo - zlo * rlo * de;
+          const double dzh = (mu - shi * zhi) * rhi + zhi * rhi * de;
+          pr(d::N_D + s) = dzl; pr(d::N_E + s) = dzh;
+          if (any_qd) pr(d::N_G + s) = (zlo + dzl) - (zhi + dzh);
+          rp = fmax(rp, fmax(-de * rlo, de * rhi));
+          rdm = fmax(rdm, fmax(-dzl * x_rcp(zlo), -dzh * x_rcp(zhi)));
+          const double ss = slo * shi;
+          if (s & 1) prod *= ss; else prod2 *= ss;
+          dsum += de * rlo - de * rhi;
+        }
+        double jx0 = 0.0, jx2 = 0.0, jdl = 0.0, zsum = 0.0, rqn[2] = {0.0, 0.0}, prodr = 1.0;
+        for (int rr = 0; rr < K; rr++) {
+          const double gx = 2.0 * (x.xs[0] - row(rr, XR_CX)), gy = 2.0 * (x.xs[2] - row(rr, XR_CY));
+          const double s = row(rr, XR_S), rs = row(rr, XR_RS), z = row(rr, XR_Z);
+          const double de = gx * dd.xs[0] + gy * dd.xs[2] + dd.dl;
+          double dz = (mu - s * z) * rs - z * rs * de;
+          if (rr == cap[0].row) { dz = (mu - s * z) * rs - P.sigma_cap * de - tq[0]; rqn[0] = cap[0].srinv * tq[0] - de; }
+          if (XKC == 2 && rr == cap[XKC - 1].row) { dz = (mu - s * z) * rs - P.sigma_cap * de - tq[1]; rqn[1] = cap[XKC - 1].srinv * tq[1] - de; }
+          row(rr, XR_DE) = de; row(rr, XR_DZ) = dz;
+          const double zn = z + dz;
+          jx0 += gx * zn; jx2 += gy * zn; jdl += zn; zsum += z;
+          rp = fmax(rp, -de * rs);
+          rdm = fmax(rdm, -dz * x_rcp(z));
+          prodr *= s;
+          dsum += de * rs;
+          if ((rr & 3) == 3) { prod *= prodr; prodr = 1.0; }
+        }
+        prod *= prodr;
+        // without a quasi-definite row the recursion is accurate to round-off (measured: residual 1e-12 of the right-hand side)
+        if (rf >= P.max_refine || !any_qd) break;
+        // rho1 = -(grad f + A'(y + dy) + W~ dx - J'(z + dz)),  rho2 = -(A (x + dx) - b),  rho_q = t / (Sigma - cap) - g'dx
+        // (grad f + A'y and the equality residual of the iterate are recomputed here, rarely, instead of living across the solve)
+        XKV jz2, gd, gf0; double dpin[4], xp0[4], pin0[4], rp0[4], rn0[2], re0;
+        prev_state(x, false, xp0); next_pi(x, pin0);
+        grad_Aty(P, x, x, pin0, true, gf0);
+        eq_residual(P, x, xp0, false, rp0, rn0, re0);
+        gather<true>(d::N_G, jz2);
+        jz2.xs[0] += jx0; jz2.xs[2] += jx2;
+        next_pi(dd, dpin);
+        grad_Aty(P, dd, dd, dpin, false, gd);
+        double nres = fmax(fabs(rqn[0]), fabs(rqn[1]));
+        XUNR for (int i = 0; i < 4; i++) {
+          const double ht = c.qw + dw - ((i & 1) ? 0.0 : 2.0 * zsum);
+          rcur.xs[i] = -(gf0.xs[i] + gd.xs[i] + ht * dd.xs[i] - jz2.xs[i]);
+          nres = fmax(nres, fabs(rcur.xs[i]));
+        }
+        XUNR for (int a = 0; a < 2; a++) { rcur.us[a] = -(gf0.us[a] + gd.us[a] + (P.Rw + dw) * dd.us[a] - jz2.us[a]); nres = fmax(nres, fabs(rcur.us[a])); }
+        XUNR for (int i = 0; i < 4; i++) {
+          rcur.lm[i] = (i < C) ? -(gf0.lm[i] + gd.lm[i] + (dw + P.rho_lambda) * dd.lm[i] - jz2.lm[i]) : 0.0;
+          nres = fmax(nres, fabs(rcur.lm[i]));
+        }
+        rcur.dl = -(gf0.dl + ((g.j == W - 1) ? (P.slw + dw) * dd.dl : 0.0) - jdl);   // this lane's share of the slack variable's row
+        const double rdl_all = g_sum(g, rcur.dl);
+        nres = fmax(nres, fabs(rdl_all));
+        {
+          double hp[4], hn[2], he;
+          eq_residual(P, dd, ddp, true, hp, hn, he);
+          XUNR for (int i = 0; i < 4; i++) { rcur.pi[i] = -(rp0[i] + hp[i]); nres = fmax(nres, fabs(rcur.pi[i])); }
+          XUNR for (int a = 0; a < 2; a++) { rcur.nu[a] = -(rn0[a] + hn[a]); nres = fmax(nres, fabs(rcur.nu[a])); }
+          rcur.eta = -(re0 + he); nres = fmax(nres, fabs(rcur.eta));
+        }
+        nres = g_max(g, nres);
+        XDBG("   refine %d: newton residual %.3e (rhs %.3e)\n", rf, nres, fmax(e_d, e_p));
+        if (!(nres > fmax(P.refine_rel * fmax(e_d, e_p), P.refine_abs))) break;
+        rq[0] = rqn[0]; rq[1] = rqn[1];
+      }
     }
-    double prodr = 1.0;
-    for (int rr = 0; rr < K; rr++) {
-      const double gx = 2.0 * (x.xs[0] - row(rr, XR_CX)), gy = 2.0 * (x.xs[2] - row(rr, XR_CY));
-      const double s = row(rr, XR_S), rs = row(rr, XR_RS), z = row(rr, XR_Z);
-      const double de = gx * dd.xs[0] + gy * dd.xs[2] + dd.dl;
-      double dz = (mu - s * z) * rs - z * rs * de;
-      if (rr == cap[0].row) dz = (mu - s * z) * rs - P.sigma_cap * de - tq[0];
-      if (rr == cap[1].row) dz = (mu - s * z) * rs - P.sigma_cap * de - tq[1];
-      row(rr, XR_DE) = de; row(rr, XR_DZ) = dz;
-      rp = fmax(rp, -de * rs);
-      rdm = fmax(rdm, -dz * x_rcp(z));
-      prodr *= s;
-      dsum += de * rs;
-      if ((rr & 3) == 3) { prod *= prodr; prodr = 1.0; }
-    }
-    prod *= prodr;
     rp = g_max(g, rp); rdm = g_max(g, rdm);
     const double tau = XPERS_TAU;
     const double a_pmax = (rp > tau) ? tau / rp : 1.0, a_dmax = (rdm > tau) ? tau / rdm : 1.0;
@@ -1128,7 +1208,7 @@ XDEV void ext_save(const ExtIO& io, int b, int npriv, const XSolver<C, W>& S, co
   r[(q++) * sd] = (double)(S.status | (S.qp_flag << 4) | ((int)S.first_ic << 8) | ((int)S.hold << 9) | (cy.badin << 10) | (cy.fin << 11) |
                            (cy.stepped_prev << 12) | (cy.team_done << 13) | (S.nfilt << 16));
   r[(q++) * sd] = (double)S.qp_iters; r[(q++) * sd] = (double)S.nlp_iters; r[(q++) * sd] = (double)S.nl_it; r[(q++) * sd] = (double)S.n_fact;
-  r[(q++) * sd] = (double)cy.team_it;
+  r[(q++) * sd] = (double)cy.team_it; r[(q++) * sd] = (double)S.mu_age;
 }
 template <int C, int W>
 XDEV void ext_restore(const ExtIO& io, int b, int npriv, XSolver<C, W>& S, XCarry<C, W>& cy) {
@@ -1146,7 +1226,7 @@ XDEV void ext_restore(const ExtIO& io, int b, int npriv, XSolver<C, W>& S, XCarr
   S.status = fl & 15; S.qp_flag = (fl >> 4) & 15; S.first_ic = (fl >> 8) & 1; S.hold = (fl >> 9) & 1; cy.badin = (fl >> 10) & 1; cy.fin = (fl >> 11) & 1;
   cy.stepped_prev = (fl >> 12) & 1; cy.team_done = (fl >> 13) & 1; S.nfilt = fl >> 16;
   S.qp_iters = (int)r[(q++) * sd]; S.nlp_iters = (int)r[(q++) * sd]; S.nl_it = (int)r[(q++) * sd]; S.n_fact = (int)r[(q++) * sd];
-  cy.team_it = (int)r[(q++) * sd];
+  cy.team_it = (int)r[(q++) * sd]; S.mu_age = (int)r[(q++) * sd];
 }
 
 template <int C, int W>
@@ -1161,7 +1241,7 @@ XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, X
   S.nsq = d::NSQ - (j == 0 ? 2 : 0); S.nsn = d::NS - (j == 0 ? 2 : 0);
   S.K_obs = io.K_obs; S.K = io.K_obs + io.n_nbr;
   S.status = 1; S.qp_iters = 0; S.qp_flag = 3; S.nlp_iters = 0; S.n_fact = 0; S.kkt = 0.0; S.hold = false; S.nl_it = 0; S.mu = 0.0; S.first_ic = true; S.nfilt = 0;
-  S.sigma = 0.0; S.qp_it = 0;
+  S.sigma = 0.0; S.qp_it = 0; S.mu_age = 0;
   const size_t ld = (size_t)io.ld;
   const bool jacobi = io.n_nbr > 0;
   const int npriv = ext_npriv(S.K);

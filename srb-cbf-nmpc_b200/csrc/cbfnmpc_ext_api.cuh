@@ -42,6 +42,7 @@ void cbfnmpc_ext_default_cfg(cbfnmpc_ext_cfg* c) {
   c->eps_obs = (double)1.9f;    // dec_vars_constr_cost.h:401
   c->eps_nbr = (double)2.2f;    // :402 "for robot to robot"
   c->relax = 0.7; c->pub_tol = 1e-10;
+  c->mu_stall_iters = 6;        // team mode: 0.2 % of the config-4 teams otherwise stall with the barrier parameter stuck
   c->max_team_iters = 100;      // 99 % of the config-4 teams settle within 60 iterations; the rest cycle at the round-off floor
 }
 
@@ -53,7 +54,7 @@ static int ext_check(const cbfnmpc_ctx* c, int B, const cbfnmpc_ext_cfg* cfg, co
   if (B % T != 0) return fail(CBFNMPC_ERR_ARG, "extended mode: batch must be a multiple of team_size");
   if (!in->x0 || !in->xdes || !in->feet_xy || !in->contact) return fail(CBFNMPC_ERR_ARG, "extended mode: missing input array");
   if (in->n_obs < 0 || (in->n_obs > 0 && !in->obs_xy)) return fail(CBFNMPC_ERR_ARG, "extended mode: obstacle array missing");
-  if (!(cfg->relax > 0.0 && cfg->relax <= 1.0) || !(cfg->pub_tol >= 0.0) || cfg->max_team_iters < 1) return fail(CBFNMPC_ERR_ARG, "extended mode: relax in (0, 1], pub_tol >= 0, max_team_iters >= 1");
+  if (!(cfg->relax > 0.0 && cfg->relax <= 1.0) || !(cfg->pub_tol >= 0.0) || cfg->max_team_iters < 1 || cfg->mu_stall_iters < 1) return fail(CBFNMPC_ERR_ARG, "extended mode: relax in (0, 1], pub_tol >= 0, max_team_iters >= 1");
   return CBFNMPC_OK;
 }
 
@@ -101,7 +102,7 @@ static int ext_perm(cbfnmpc_ctx* c, int n_teams, cudaStream_t st) {
 }
 
 static void ext_xparams(const cbfnmpc_ctx* c, const cbfnmpc_ext_cfg* cfg, XParams* XP) {
-  XP->k = c->kp; XP->eps_obs = cfg->eps_obs; XP->eps_nbr = cfg->eps_nbr; XP->relax = cfg->relax; XP->pub_tol = cfg->pub_tol; XP->max_team_it = cfg->max_team_iters;
+  XP->k = c->kp; XP->eps_obs = cfg->eps_obs; XP->eps_nbr = cfg->eps_nbr; XP->relax = cfg->relax; XP->pub_tol = cfg->pub_tol; XP->max_team_it = cfg->max_team_iters; XP->mu_stall = cfg->mu_stall_iters;
 }
 
 int cbfnmpc_ext_solve_batch(cbfnmpc_ctx* c, int B, const cbfnmpc_ext_cfg* cfg, const cbfnmpc_ext_in* in, const cbfnmpc_ext_out* out, void* cuda_stream) {

@@ -122,6 +122,23 @@ class MPC_dist_team:
         for i, a in enumerate(self.agents):
             a.state_other = np.concatenate([last[k] for k in range(len(self.agents)) if k != i])
 
+    def run_NMPC_extended(self, k_obs=1, **cfg):
+        """EXTENDED MODE (no reference implementation exists; include/cbfnmpc.h): the cycle with inter-agent rows -- one distance
+        row per grid point against each of an agent's k_obs nearest real obstacles and against every team mate's predicted position
+        (threshold eps_nbr, dec_vars_constr_cost.h:402), team mates' trajectories exchanged at every interior-point iteration.
+        BASELINE config 2.  Teams of 1, 2 or 4 agents in one stance class."""
+        insts = []
+        for a in self.agents:
+            x0, xdes, feet, contact, obs = a._instance()
+            order = np.argsort(np.hypot(obs[0] - x0[0], obs[1] - x0[2]), kind="stable")[:k_obs]
+            insts.append((x0, xdes, np.asarray(feet)[None], contact, obs[:, order].copy()))
+        d = capi.ext_soa_from_instances(insts, 4)
+        for b, a in enumerate(self.agents):
+            d["alpha_buf"][:, b] = a.mpc_state_alpha_buffer_
+        out = self.solver.ext_solve_host(d, N=4, team_size=len(self.agents), **cfg)
+        for b, a in enumerate(self.agents): a._consume(out, b)
+        return out
+
     def run_NMPC(self):
         insts = [a._instance() for a in self.agents]
         bufs = [a.mpc_state_alpha_buffer_ for a in self.agents]

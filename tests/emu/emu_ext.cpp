@@ -76,7 +76,7 @@ static int run_warp() {
 struct emu_ext_args {
   int B, N, T, K_obs, n_nbr, xmode;
   double eps_obs, eps_nbr, relax, pub_tol;
-  int max_team_iters;
+  int max_team_iters, mu_stall;
   const double *x0, *xdes, *feet, *obs, *abuf, *nbr;   // nbr: [n_nbr][2N + 2][B] (xmode 2)
   const int* contact;
   double *X, *U, *lam, *slack, *xqp, *alpha, *abuf_next, *kkt, *pub;
@@ -86,7 +86,7 @@ struct emu_ext_args {
 extern "C" int emu_ext_solve(const cbfnmpc_gains* g, const cbfnmpc_options* o, const emu_ext_args* a) {
   XParams XP;
   host_fill_kparams(g, o, &XP.k);
-  XP.eps_obs = a->eps_obs; XP.eps_nbr = a->eps_nbr; XP.relax = a->relax; XP.pub_tol = a->pub_tol; XP.max_team_it = a->max_team_iters;
+  XP.eps_obs = a->eps_obs; XP.eps_nbr = a->eps_nbr; XP.relax = a->relax; XP.pub_tol = a->pub_tol; XP.max_team_it = a->max_team_iters; XP.mu_stall = a->mu_stall;
   ExtIO io;
   memset(&io, 0, sizeof(io));
   io.x0 = a->x0; io.xdes = a->xdes; io.feet = a->feet; io.contact = a->contact; io.obs = a->obs; io.abuf = a->abuf;

@@ -13,7 +13,7 @@ _lib = None
 
 
 class Args(C.Structure):
-    _fields_ = [(k, C.c_int) for k in ("B", "N", "T", "K_obs", "n_nbr", "xmode")] + [(k, C.c_double) for k in ("eps_obs", "eps_nbr", "relax", "pub_tol")] + [("max_team_iters", C.c_int)] + \
+    _fields_ = [(k, C.c_int) for k in ("B", "N", "T", "K_obs", "n_nbr", "xmode")] + [(k, C.c_double) for k in ("eps_obs", "eps_nbr", "relax", "pub_tol")] + [("max_team_iters", C.c_int), ("mu_stall", C.c_int)] + \
                [(k, C.c_void_p) for k in ("x0", "xdes", "feet", "obs", "abuf", "nbr", "contact", "X", "U", "lam", "slack", "xqp", "alpha", "abuf_next",
                                           "kkt", "pub", "status", "qp_iters", "nlp_iters", "team_iters")]
 
@@ -48,7 +48,7 @@ def ext_alloc_out(B, N):
     return o
 
 
-def solve(insts, N=4, T=1, nbr=None, eps_obs=None, eps_nbr=2.2, relax=0.7, pub_tol=1e-10, max_team_iters=100, gains=None, options=None, trace=False):
+def solve(insts, N=4, T=1, nbr=None, eps_obs=None, eps_nbr=2.2, relax=0.7, pub_tol=1e-10, max_team_iters=100, mu_stall=6, gains=None, options=None, trace=False):
     """nbr: (B, n_nbr, N, 2) fixed neighbour trajectories (T == 1) or None; T == 4: teams exchange through the emulated warp."""
     global _lib
     L = C.CDLL(build(trace=trace))
@@ -74,7 +74,7 @@ def solve(insts, N=4, T=1, nbr=None, eps_obs=None, eps_nbr=2.2, relax=0.7, pub_t
         a.n_nbr, a.xmode, a.nbr = nn, 2, nb.ctypes.data
     else:
         a.n_nbr, a.xmode = 0, 0
-    a.eps_obs = g.eps_dist if eps_obs is None else eps_obs; a.eps_nbr = eps_nbr; a.relax = relax; a.pub_tol = pub_tol; a.max_team_iters = max_team_iters
+    a.eps_obs = g.eps_dist if eps_obs is None else eps_obs; a.eps_nbr = eps_nbr; a.relax = relax; a.pub_tol = pub_tol; a.max_team_iters = max_team_iters; a.mu_stall = mu_stall
     for k, kk in (("x0", "x0"), ("xdes", "xdes"), ("feet", "feet_xy"), ("obs", "obs_xy"), ("abuf", "alpha_buf"), ("contact", "contact")):
         setattr(a, k, d[kk].ctypes.data)
     for k, kk in (("X", "X"), ("U", "U"), ("lam", "lam"), ("slack", "slack"), ("xqp", "x_qp"), ("alpha", "alpha"), ("abuf_next", "alpha_buf_next"),
