@@ -16,6 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 launches = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "launches_%s.csv" % tag)
 rep = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "prof_%s.ncu-rep" % tag)
+# optional: what the full capture is of (default: the faithful solve kernel on the bench workload, which also refreshes profiles/traffic.json)
+what = sys.argv[4] if len(sys.argv) > 4 else "one `cbfnmpc_lane_kernel` launch (4096 cfg-3 instances, `scripts/dev/bench_quick.py 4096`)"
+is_headline = len(sys.argv) <= 4
 out_md = [("# ncu summary `%s`\n" % tag)]
 summary = {"tag": tag}
 
@@ -51,7 +54,7 @@ if os.path.exists(rep):
             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__average_warp_latency_per_inst_issued.ratio",
             "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
             "sm__icc_request_hit_rate.pct", "sm__cycles_active.avg"]
-    out_md.append("## `ncu --set full --clock-control none` of one `cbfnmpc_lane_kernel` launch (4096 cfg-3 instances, `scripts/dev/bench_quick.py 4096`)\n")
+    out_md.append("## `ncu --set full --clock-control none` of %s\n" % what)
     out_md.append("| metric | value | unit |\n|---|---|---|")
     summary["metrics"] = {}
     for k in keys:
@@ -93,8 +96,9 @@ if os.path.exists(rep):
     summary["inst_total"] = tot; summary["inst_static"] = len(sr) - 2; summary["fp64_share"] = fp / tot; summary["local_share"] = (c["LDL"] + c["STL"]) / tot
 
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-if "traffic_bytes" in summary:
+if "traffic_bytes" in summary and is_headline:
     json.dump({"traffic_bytes": summary["traffic_bytes"], "read_bytes": summary["traffic_read_bytes"], "write_bytes": summary["traffic_write_bytes"],
+               "kernel_version": tag,
                "source": "profiles/%s_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one cbfnmpc_lane_kernel launch (4096 cfg-3 instances, ncu --set full)" % tag},
               open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 open(os.path.join(ROOT, "profiles", "%s_ncu_summary.md" % tag), "w").write("\n".join(out_md) + "\n")
