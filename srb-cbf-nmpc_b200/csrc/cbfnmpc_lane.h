@@ -686,7 +686,11 @@ struct LaneSolver {
       r.nu[0] = -rnu[0]; r.nu[1] = -rnu[1]; r.eta = -reta;
     }
     info.qp_flag = 3; info.qp_iters = 0; qp_it = 0; sigma = 100.0;  // GlobalOptions.h:26
-    if (!l_riccati<C, true>(g, P, c, H, 0.0, f)) { info.qp_flag = 1; return true; }
+    {
+      const bool okr = l_riccati<C, true>(g, P, c, H, 0.0, f);
+      g_keep(g, okr);
+      if (!okr) { info.qp_flag = 1; return true; }
+    }
     l_kkt_solve_plain<C>(g, P, c, H, f, 0.0, r, dd);
     x = dd;
     LUNR for (int i = C; i < 4; i++) x.lm[i] = 0.0;
@@ -719,8 +723,7 @@ struct LaneSolver {
   // one Mehrotra predictor-corrector iteration (Prime.c:138-218).  Returns true when the stage is finished.
   // Slot passes: A (residuals, reciprocals, predictor weights), B (affine step statistics), C (corrector right-hand side),
   // D (final step and step lengths), E (update).  One instance of the KKT solve serves predictor and corrector.
-  LMEM bool qp_iter(const KParams& P) {
-    if (qp_it >= P.qp_maxit) return true;
+  LMEM bool qp_iter(const KParams& P) {   // (the iteration limit is tested at the end: the caller never enters with qp_it >= qp_maxit)
     double xp[4], pin[4];
     prev_state(x, false, xp); next_pi(x, pin);
     l_scatter<C, false>(g, pr, d::Q_EV, x, xp);
@@ -751,19 +754,32 @@ struct LaneSolver {
       sz = g_sum(g, acc_sz);
       const double lim = P.qp_reltol / sqrt(3.0);
       LANE_DBG("qp it %d rx %.3e ry %.3e rz %.3e mu %.3e sigma %.3e\n", qp_it, sqrt(nrx), sqrt(nry), sqrt(nrz), sz / d::MQP, sigma);
-      if (sqrt(nrx) < lim && sqrt(nrz) < lim && sqrt(nry) < lim && sz / d::MQP < P.qp_abstol) { info.qp_flag = 0; return true; }
+      const bool conv = sqrt(nrx) < lim && sqrt(nrz) < lim && sqrt(nry) < lim && sz / d::MQP < P.qp_abstol;
+      g_keep(g, !conv);
+      if (conv) { info.qp_flag = 0; return true; }
       mu = sz / d::MQP;
     }
-    if (predictor) {
-      l_assemble<C, false>(g, P, c, pr, d::Q_E, 0.0, 0.0, H);
-      info.n_fact++;
-      if (!l_riccati<C, true>(g, P, c, H, 0.0, f)) { info.qp_flag = 1; return true; }
-    } else {
-      sigma = 0.0;  // E, G hold zeros: pure corrector with the previous factor
+    {
+      bool okr = true;
+      const unsigned sv = g_enter(g, predictor);   // (sigma == 0 -- a pure corrector step -- is rare; the groups of a warp then differ)
+      if (predictor) {
+        l_assemble<C, false>(g, P, c, pr, d::Q_E, 0.0, 0.0, H);
+        info.n_fact++;
+        okr = l_riccati<C, true>(g, P, c, H, 0.0, f);
+      } else {
+        sigma = 0.0;  // E, G hold zeros: pure corrector with the previous factor
+      }
+      g_leave(g, sv);
+      g_keep(g, okr);
+      if (!okr) { info.qp_flag = 1; return true; }
     }
     double ap = 1.0, ad = 1.0;
     KV dd;
-    for (int ph = predictor ? 0 : 1; ph < 2; ph++) {
+    const unsigned sv_ph = g.mask;
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ph++) {
+      if (ph == 0) g_keep(g, predictor); else g_leave(g, sv_ph);
+      if (ph == 0 && !predictor) continue;
       const double sm = sigma * mu;
       if (ph == 1) {
         // ---- pass C: corrector right-hand side, ds = -s z - ds_aff dz_aff + sigma mu (form_ds, Auxilary.c:250-267) -> DE
@@ -836,7 +852,7 @@ struct LaneSolver {
     }
     qp_it++;
     info.qp_iters = qp_it;
-    return false;
+    return qp_it >= P.qp_maxit;
   }
 
   // QP-only answer (use_snopt == false): unscaled KKT error of the QP
@@ -1043,9 +1059,13 @@ struct LaneSolver {
 #endif
       // converged: KKT error <= tol, or <= acc_tol once the barrier parameter sits at its floor (there the dual residual is at
       // its FP64 noise level, s = mu / z ~ 1e-13 for active rows, and may hover just above tol for many iterations)
-      if (E0 <= P.tol || (mu <= P.tol / 10.0 && E0 <= P.acc_tol)) { info.status = 0; return true; }
-      if (it == P.max_iter) { info.status = 1; return true; }
-      if (!(zmax < P.z_div) || !(E0 < 1e300) || g_any(g, !spos)) { info.status = 2; return true; }
+      const bool anyneg = g_any(g, !spos);
+      int ex = -1;
+      if (E0 <= P.tol || (mu <= P.tol / 10.0 && E0 <= P.acc_tol)) ex = 0;
+      else if (it == P.max_iter) ex = 1;
+      else if (!(zmax < P.z_div) || !(E0 < 1e300) || anyneg) ex = 2;
+      g_keep(g, ex < 0);
+      if (ex >= 0) { info.status = ex; return true; }
     }
     // ---- barrier update (Ipopt eq. 7): max_i |s_i z_i - mu| from the extreme products
     for (;;) {
@@ -1075,20 +1095,32 @@ struct LaneSolver {
     {
       const double dw_last = PERS_DWLAST;
       bool ok = false;
+      const unsigned sv_ic = g.mask;
       for (;;) {
         info.n_fact++;
         ok = l_riccati<C, false>(g, P, c, H, dw, f);
-        if (ok) ok = l_border_factor<C>(g, P, c, H, f, dw, pr, bf);
-        if (ok) break;
-        if (dw == 0.0) dw = (dw_last == 0.0) ? P.dw_first : fmax(P.dw_min, P.kw_minus * dw_last);
-        else dw *= (first_ic && dw_last == 0.0) ? P.kw_plus_first : P.kw_plus;
-        if (dw > P.dw_max) break;
+        {
+          const unsigned sv = g_enter(g, ok);
+          if (ok) ok = l_border_factor<C>(g, P, c, H, f, dw, pr, bf);
+          g_leave(g, sv);
+        }
+        bool again = !ok;
+        if (again) {
+          if (dw == 0.0) dw = (dw_last == 0.0) ? P.dw_first : fmax(P.dw_min, P.kw_minus * dw_last);
+          else dw *= (first_ic && dw_last == 0.0) ? P.kw_plus_first : P.kw_plus;
+          if (dw > P.dw_max) again = false;
+        }
+        g_keep(g, again);
+        if (!again) break;
       }
+      g_leave(g, sv_ic);
+      g_keep(g, ok);
       if (!ok) { info.status = 3; return true; }
       if (dw > 0.0) { PERS_DWLAST = dw; first_ic = false; }
     }
     // ---- solve, then iterative refinement on the unreduced Newton system (one instance of the solve for both)
     KV dd;
+    const unsigned sv_rf = g.mask;
     for (int rf = 0;; rf++) {
       KV d2; double tb2[4];
       l_kkt_solve_border<C>(g, P, c, H, f, dw, pr, bf, r, d2, tb2);
@@ -1165,7 +1197,9 @@ struct LaneSolver {
       nres = g_max(g, nres);
       const double nrhs = fmax(e_d, e_p);
       LANE_DBG("   refine %d nres %.2e nrhs %.2e\n", rf, nres, nrhs);
-      if (!(nres > fmax(P.refine_rel * nrhs, P.refine_abs))) break;
+      const bool more = nres > fmax(P.refine_rel * nrhs, P.refine_abs);
+      g_keep(g, more);
+      if (!more) break;
       {
         KV jb; double wdb;
         l_gather<C, true>(g, pr, d::N_EV, H.gv, jb, wdb);
@@ -1174,6 +1208,7 @@ struct LaneSolver {
         r.dl += wdb;
       }
     }
+    g_leave(g, sv_rf);
     const double quad = dd.xs[0] * dd.xs[0] + dd.xs[2] * dd.xs[2];
     // ---- pass C: fraction to the boundary (alpha_max = min(1, tau / max_i(-ds_i / s_i))) and the line-search constants
     //      phi = f - mu sum log s, its directional derivative, sum of slack products (for log)
@@ -1213,7 +1248,10 @@ struct LaneSolver {
     // ---- filter line search (theta = ||A x - b||_1 shrinks by (1 - alpha)); pass D per trial
     double alpha = a_pmax;
     bool accepted = false, ftype = false;
-    while (alpha >= P.alpha_min) {
+    const unsigned sv_ls = g.mask;
+    bool going = alpha >= P.alpha_min;
+    g_keep(g, going);
+    while (going) {
       // phi(x + alpha dx) - phi(x) = alpha g'dx + 1/2 alpha^2 dx'Q dx - mu sum log(s_t / s)
       double prod = 1.0, prod2 = 1.0;
       bool pos = true;
@@ -1230,11 +1268,13 @@ struct LaneSolver {
       }
       const bool allpos = g_all(g, pos);
       const double dlog = g_sum(g, allpos ? log(prod) + log(prod2) : 0.0);
-      if (allpos) {
+      const bool anysmall = g_any(g, smin < 1e-12);
+      {
         const double tht = (1.0 - alpha) * th;
         const double dph = alpha * gdx + 0.5 * alpha * alpha * dQd - mu * dlog;
         const double pht = ph + dph;
-        if (tht <= PERS_THMAX && filter_ok(tht, pht)) {
+        const bool fok = filter_ok(tht, pht);   // (a vote: evaluated by every group, used when the trial point is interior)
+        if (allpos && tht <= PERS_THMAX && fok) {
           const bool sw = dphi < 0.0 && alpha * (dphi * dphi) > th;  // switching condition, s_phi = 2, s_theta = 1, delta = 1
           if (th <= PERS_THMIN && sw) {
             if (dph - 10.0 * CBF_EPSM * fabs(ph) <= P.eta_phi * alpha * dphi) { accepted = true; ftype = true; }
@@ -1243,7 +1283,9 @@ struct LaneSolver {
           }
         }
       }
-      if (accepted && g_any(g, smin < 1e-12)) {
+      const bool recheck = accepted && anysmall;
+      const unsigned sv_rc = g_enter(g, recheck);
+      if (recheck) {
         // The test above works on the linearised slacks s + alpha ds.  Late in the run tau = 1 - mu lets an active slack shrink
         // by a factor mu in one step, to below the rounding (~1e-15) of the O(1) positions it is computed from.  When a trial
         // slack is that small, the slacks that pass A will compute at x + alpha dx -- by the same expressions, from the same
@@ -1262,11 +1304,15 @@ struct LaneSolver {
         }
         accepted = g_all(g, okp);
       }
-      if (accepted) break;
-      alpha *= 0.5;
+      g_leave(g, sv_rc);
+      if (!accepted) alpha *= 0.5;
+      going = !accepted && alpha >= P.alpha_min;
+      g_keep(g, going);
     }
+    g_leave(g, sv_ls);
     LANE_LOG(alpha); LANE_LOG(ph); LANE_LOG(dphi);
     LANE_DBG("   alpha %.3e acc %d ftype %d ph %.10e dphi %.3e\n", alpha, (int)accepted, (int)ftype, ph, dphi);
+    g_keep(g, accepted);
     if (!accepted) { info.status = 2; return true; }
     if (!ftype) filter_add(P, (1.0 - P.gamma_theta) * th, ph - P.gamma_phi * th);
     // ---- update (the multiplier step z += a_dmax dz is applied by pass A of the next iteration)
@@ -1291,12 +1337,13 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
   LaneSolver<C> S;
   S.g = grp_make(); S.pr = pr;
   S.nsq = l_nslots<C, false>(S.g); S.nsn = l_nslots<C, true>(S.g);
-  const Grp& g = S.g;
+  Grp& g = S.g;   // g.mask follows the mask discipline of lane_prims.h: set here at every point where all 32 lanes are present
   const int j = g.j;
   const size_t B = (size_t)io.ld;  // array pitch
   S.info.status = 1; S.info.qp_iters = 0; S.info.qp_flag = 3; S.info.nlp_iters = 0; S.info.n_fact = 0; S.info.kkt = 0.0;
   double abuf_j = 0.0;
   bool qp_done = true, badin = false;
+  g.mask = w_ballot_full(valid);
   if (valid) {
     // ---- load (SoA, one instance; lane j takes stage j)
     LUNR for (int i = 0; i < 4; i++) { pr(d::F_XDES + i) = io.xdes[(size_t)(4 * j + i) * B + b]; pr(d::F_XIN + i) = io.x0[(size_t)i * B + b]; }
@@ -1339,24 +1386,28 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
     LUNR for (int i = 0; i < 4; i++) chk += 0.0 * pr(d::F_XDES + i) + 0.0 * pr(d::F_XIN + i);
     LUNR for (int t = 0; t < 8; t++) chk += 0.0 * F[t];
     badin = !g_all(g, chk == 0.0);
+    const unsigned sv = g_enter(g, !badin);
     if (badin) {
       S.info.status = 4;
     } else if (io.xstart == nullptr) {
-      qp_done = S.qp_init(P);
+      qp_done = S.qp_init(P) || P.qp_maxit <= 0;
     } else {
       LUNR for (int i = 0; i < 4; i++) { S.x.xs[i] = io.xstart[(size_t)(4 * j + i) * B + b]; S.x.lm[i] = (i < C) ? io.xstart[(size_t)(24 + C * j + i) * B + b] : 0.0; S.x.pi[i] = 0.0; }
       LUNR for (int a = 0; a < 2; a++) { S.x.us[a] = io.xstart[(size_t)(16 + 2 * j + a) * B + b]; S.x.nu[a] = 0.0; }
       S.x.dl = io.xstart[(size_t)(24 + 4 * C) * B + b]; S.x.eta = 0.0;
       S.info.qp_flag = 0;
     }
+    g_leave(g, sv);
   }
   // ---- QP stage: the groups of a CTA iterate together (pace_go) until the last one has finished
   for (;;) {
     const bool act = valid && !qp_done;
-    if (!pace_go(pace, act)) break;
+    g.mask = w_ballot_full(act);
+    if (!pace_go(pace, g.mask != 0u)) break;
     if (act) qp_done = S.qp_iter(P);
   }
   bool nl_done = true;
+  g.mask = w_ballot_full(valid && !badin);
   if (valid && !badin) {
     if (io.xqp) {
       LUNR for (int i = 0; i < 4; i++) io.xqp[(size_t)(4 * j + i) * B + b] = S.x.xs[i];
@@ -1368,9 +1419,11 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
   // ---- NLP stage
   for (;;) {
     const bool act = valid && !nl_done;
-    if (!pace_go(pace, act)) break;
+    g.mask = w_ballot_full(act);
+    if (!pace_go(pace, g.mask != 0u)) break;
     if (act) nl_done = S.nlp_iter(P);
   }
+  g.mask = w_ballot_full(valid && !badin);
   if (!valid) return;
   if (badin) {  // non-finite inputs: nothing was solved; only the status fields are written (include/cbfnmpc.h), like lane_store_bad
     if (j == 0) {

@@ -1,10 +1,20 @@
 // lane_prims.h -- primitives of the lane-per-stage solver: one NMPC instance = one group of 4 adjacent lanes
 // (lane j of the group owns horizon stage j), 8 instances per warp.
 //
-// CUDA build (the product): width-4 shuffles / ballots restricted to the group's own lane mask, so that groups of one
-// warp may diverge from each other (different iteration counts, inertia corrections, line-search lengths).
-// CBF_HOST_EMU build (tests/emu only, never part of libcbfnmpc.so): the same names on 4 cooperative fibers, so the
-// kernel source can be checked against the oracle on a CPU-only machine.  Not a fallback; the C ABI never reaches it.
+// CUDA build (the product): width-4 shuffles / ballots.  Their member mask is NOT the group's own nibble: `Grp::mask` is the
+// WARP-UNIFORM set of lanes that execute the current region (a vote result, held in a uniform register), so that a shuffle
+// compiles to the bare SHFL behind one BRA.DIV.  With per-group masks ptxas has to prove at run time that the masks of the
+// active lanes partition the active set: S2R + MATCH.ANY + REDUX.OR + LOP3 in front of every cluster of shuffles -- 14.5 % of
+// the stall samples of the round-1 kernel (profiles/r02a_ncu_summary.md).  The price is a discipline: groups of one warp still
+// differ in iteration counts, inertia corrections, refinement solves and line-search lengths, so every region whose condition
+// is not warp-uniform and that contains a shuffle or a vote is bracketed by g_enter / g_leave (the mask shrinks to the lanes
+// that go in), a loop that groups leave at different trip counts shrinks the mask at its back edge (g_keep), and an early
+// return is announced by g_keep right before it.  Rule: no return inside a bracketed region.
+// CBF_HOST_EMU build (tests/emu only, never part of libcbfnmpc.so): the same names on 32 cooperative fibers (one warp = 8
+// groups) with mask-based rendezvous -- every lane named in the mask has to arrive with the same mask, and in the sitecheck
+// build at the same source-level site, before any of them leaves; anything else is reported as a deadlock -- so the kernel
+// source, including the mask discipline, is checked against the oracle on a CPU-only machine.  Not a fallback; the C ABI
+// never reaches it.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -15,13 +25,12 @@
 #define LMEM __device__ __forceinline__
 #define LFULL 0xffffffffu
 struct Grp {
-  unsigned mask;  // the 4 lanes of this group
+  unsigned mask;  // warp-uniform: the lanes that execute the current region (whole groups only)
   int j;          // stage owned by this lane (0..3)
 };
-// (Making the thread index opaque to stop ptxas from re-reading SR_TID wherever it needs the mask again was tried: the registers
-// it then holds cost more in spills than the S2R latency -- 0.746 instead of 0.72 ms per 4096 solves.)
 LDEV int l_tid() { return (int)threadIdx.x; }
-LDEV Grp grp_make() { Grp g; const int lane = l_tid() & 31; g.j = lane & 3; g.mask = 0xFu << (lane & ~3); return g; }
+LDEV Grp grp_make() { Grp g; g.j = l_tid() & 3; g.mask = LFULL; return g; }
+LDEV unsigned l_gsh() { return (unsigned)l_tid() & 28u; }  // first lane of this lane's group
 LDEV double g_idx(const Grp& g, double v, int src) { return __shfl_sync(g.mask, v, src, 4); }
 LDEV double g_up(const Grp& g, double v) { return __shfl_up_sync(g.mask, v, 1, 4); }      // from lane j-1 (lane 0: own value)
 LDEV double g_down(const Grp& g, double v) { return __shfl_down_sync(g.mask, v, 1, 4); }  // from lane j+1 (lane 3: own value)
@@ -29,9 +38,14 @@ LDEV double g_xor(const Grp& g, double v, int m) { return __shfl_xor_sync(g.mask
 LDEV unsigned g_xor_u(const Grp& g, unsigned v, int m) { return __shfl_xor_sync(g.mask, v, m, 4); }
 // bit k = predicate of lane k of the group.  (Flags are exchanged with votes, never as converted doubles through shuffles:
 // ptxas 12.9 drops one of the F2I conversions of a shuffled (double)flag sequence -- see DESIGN.md, "toolchain notes".)
-LDEV unsigned g_bits(const Grp& g, bool p) { return (__ballot_sync(g.mask, p) >> ((threadIdx.x & 31) & ~3)) & 0xFu; }
-LDEV bool g_any(const Grp& g, bool p) { return (__ballot_sync(g.mask, p) & g.mask) != 0u; }
-LDEV bool g_all(const Grp& g, bool p) { return (__ballot_sync(g.mask, p) & g.mask) == g.mask; }
+LDEV unsigned g_bits(const Grp& g, bool p) { return (__ballot_sync(g.mask, p) >> l_gsh()) & 0xFu; }
+LDEV bool g_any(const Grp& g, bool p) { return g_bits(g, p) != 0u; }
+LDEV bool g_all(const Grp& g, bool p) { return g_bits(g, !p) == 0u; }
+// mask discipline (see the header comment); all of these are executed by every lane of the current mask
+LDEV unsigned w_ballot_full(bool p) { return __ballot_sync(LFULL, p); }                    // all 32 lanes are present
+LDEV unsigned g_enter(Grp& g, bool p) { const unsigned sv = g.mask; g.mask = __ballot_sync(sv, p); return sv; }  // before `if (p) { ... }`
+LDEV void g_leave(Grp& g, unsigned sv) { g.mask = sv; }                                    // after it
+LDEV void g_keep(Grp& g, bool stay) { g.mask = __ballot_sync(g.mask, stay); }              // before `if (!stay) break / return`
 // Loop control ("does any group of this CTA still iterate").  The warps of a CTA are kept within ONE solver iteration of each
 // other so that they fetch the same instruction-cache lines, but they do not wait for each other every iteration: round r ends
 // with an arrival on mbarrier r & 1 and a wait for round r - 1 only.  A warp whose own groups have all finished has nothing to
@@ -63,9 +77,8 @@ LDEV Pace pace_make(unsigned long long* bars, int* flags) {
   __syncthreads();
   return p;
 }
-LDEV bool pace_go(Pace& p, bool act) {
+LDEV bool pace_go(Pace& p, bool mine) {  // mine: some group of this warp still iterates (warp-uniform)
   constexpr int NWARP = LANE_NT / 32;
-  const bool mine = __any_sync(LFULL, act);
   const int r = p.r, k = r & 1;
   if (r > 0) pace_wait(p.bar + 8 * (k ^ 1), ((r - 1) >> 1) & 1);  // everybody has finished round r - 1
   if ((p.me & 31) == 0) {
@@ -86,7 +99,7 @@ LDEV bool pace_go(Pace& p, bool act) {
 }
 #else
 LDEV Pace pace_make(unsigned long long*, int*) { return Pace(); }
-LDEV bool pace_go(Pace&, bool act) { return __any_sync(LFULL, act); }
+LDEV bool pace_go(Pace&, bool mine) { return mine; }
 #endif
 LDEV double l_rcp(double v) {  // 1/v: MUFU.RCP64H seed + two Newton steps (~1 ulp for normal operands)
 #if defined(CBF_EXACT_DIV) || defined(CBF_EXACT_RCP)
@@ -137,43 +150,49 @@ __device__ int g_dbg_n;
 // the 4 lanes of a group always meet at the SAME site (what __shfl_sync with the group mask requires on the device)
 #define LDEV static inline __attribute__((always_inline))
 #define LMEM inline __attribute__((always_inline))
+#define LFULL 0xffffffffu
 namespace lemu {
-struct GroupCtx {
-  int cur;         // fiber currently running (0..3)
-  double xd[4];    // exchange buffers
-  uint64_t xi[4];
+struct WarpCtx {
+  int cur;          // fiber (lane) currently running (0..31)
+  double xd[32];    // exchange buffers
+  uint64_t xi[32];
 };
-extern GroupCtx g_grp;
-void barrier();  // all 4 fibers arrive before any leaves
+extern WarpCtx g_warp;
+void rendezvous(unsigned mask);  // every lane of `mask` arrives (with the same mask, at the same site) before any of them leaves
 }  // namespace lemu
 struct Grp { unsigned mask; int j; };
-LDEV Grp grp_make() { Grp g; g.j = lemu::g_grp.cur; g.mask = 0xFu; return g; }
+LDEV int l_tid() { return lemu::g_warp.cur; }
+LDEV Grp grp_make() { Grp g; g.j = l_tid() & 3; g.mask = LFULL; return g; }
+LDEV unsigned l_gsh() { return (unsigned)l_tid() & 28u; }
 LDEV double g_idx(const Grp& g, double v, int src) {
-  lemu::g_grp.xd[g.j] = v; lemu::barrier();
-  double r = lemu::g_grp.xd[src & 3]; lemu::barrier();
+  lemu::g_warp.xd[l_tid()] = v; lemu::rendezvous(g.mask);
+  double r = lemu::g_warp.xd[l_gsh() + (src & 3)]; lemu::rendezvous(g.mask);
   return r;
 }
 LDEV double g_up(const Grp& g, double v) { return g_idx(g, v, g.j > 0 ? g.j - 1 : g.j); }
 LDEV double g_down(const Grp& g, double v) { return g_idx(g, v, g.j < 3 ? g.j + 1 : g.j); }
 LDEV double g_xor(const Grp& g, double v, int m) { return g_idx(g, v, g.j ^ m); }
 LDEV unsigned g_xor_u(const Grp& g, unsigned v, int m) {
-  lemu::g_grp.xi[g.j] = v; lemu::barrier();
-  unsigned r = (unsigned)lemu::g_grp.xi[(g.j ^ m) & 3]; lemu::barrier();
+  lemu::g_warp.xi[l_tid()] = v; lemu::rendezvous(g.mask);
+  unsigned r = (unsigned)lemu::g_warp.xi[l_gsh() + ((g.j ^ m) & 3)]; lemu::rendezvous(g.mask);
   return r;
 }
-LDEV bool g_any(const Grp& g, bool p) {
-  lemu::g_grp.xi[g.j] = p ? 1u : 0u; lemu::barrier();
-  bool r = (lemu::g_grp.xi[0] | lemu::g_grp.xi[1] | lemu::g_grp.xi[2] | lemu::g_grp.xi[3]) != 0; lemu::barrier();
+LDEV unsigned l_ballot(unsigned mask, bool p) {
+  lemu::g_warp.xi[l_tid()] = p ? 1u : 0u; lemu::rendezvous(mask);
+  unsigned r = 0;
+  for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) r |= (unsigned)(lemu::g_warp.xi[l] & 1u) << l;
+  lemu::rendezvous(mask);
   return r;
 }
-LDEV bool g_all(const Grp& g, bool p) { return !g_any(g, !p); }
-LDEV unsigned g_bits(const Grp& g, bool p) {
-  lemu::g_grp.xi[g.j] = p ? 1u : 0u; lemu::barrier();
-  unsigned r = (unsigned)(lemu::g_grp.xi[0] | (lemu::g_grp.xi[1] << 1) | (lemu::g_grp.xi[2] << 2) | (lemu::g_grp.xi[3] << 3)); lemu::barrier();
-  return r;
-}
+LDEV unsigned g_bits(const Grp& g, bool p) { return (l_ballot(g.mask, p) >> l_gsh()) & 0xFu; }
+LDEV bool g_any(const Grp& g, bool p) { return g_bits(g, p) != 0u; }
+LDEV bool g_all(const Grp& g, bool p) { return g_bits(g, !p) == 0u; }
+LDEV unsigned w_ballot_full(bool p) { return l_ballot(LFULL, p); }
+LDEV unsigned g_enter(Grp& g, bool p) { const unsigned sv = g.mask; g.mask = l_ballot(sv, p); return sv; }
+LDEV void g_leave(Grp& g, unsigned sv) { g.mask = sv; }
+LDEV void g_keep(Grp& g, bool stay) { g.mask = l_ballot(g.mask, stay); }
 struct Pace {};
-LDEV bool pace_go(Pace&, bool act) { Grp g = grp_make(); return g_any(g, act); }  // the emulated CTA is one group
+LDEV bool pace_go(Pace&, bool mine) { return mine; }  // the emulated CTA is one warp
 #ifdef CBF_EMU_GPUMATH  // mimic the CUDA build's rounding: low-precision seed + two Newton steps (not correctly rounded)
 LDEV double l_rcp(double v) { double r = (double)(float)(1.0 / v); r = fma(fma(-v, r, 1.0), r, r); r = fma(fma(-v, r, 1.0), r, r); return r; }
 LDEV double l_rsq(double v) { double r = (double)(float)(1.0 / sqrt(v)); const double h = 0.5 * v; r = fma(fma(-h * r, r, 0.5), r, r); r = fma(fma(-h * r, r, 0.5), r, r); return r; }
@@ -187,12 +206,12 @@ LDEV double l_mul_rn(double a, double b) { volatile double r = a * b; return r; 
 LDEV double l_add_rn(double a, double b) { volatile double r = a + b; return r; }
 #ifdef CBF_DBGBUF
 extern double g_dbg[8192]; extern int g_dbg_n;
-#define LANE_LOG(v) do { if (lemu::g_grp.cur == 0 && g_dbg_n < 8192) g_dbg[g_dbg_n++] = (v); } while (0)
+#define LANE_LOG(v) do { if (lemu::g_warp.cur == 0 && g_dbg_n < 8192) g_dbg[g_dbg_n++] = (v); } while (0)
 #else
 #define LANE_LOG(v) do { } while (0)
 #endif
 #ifdef CBF_TRACE
-#define LANE_DBG(...) do { if (lemu::g_grp.cur == 0) fprintf(stderr, __VA_ARGS__); } while (0)
+#define LANE_DBG(...) do { if (lemu::g_warp.cur == 0) fprintf(stderr, __VA_ARGS__); } while (0)
 #else
 #define LANE_DBG(...) do { } while (0)
 #endif
