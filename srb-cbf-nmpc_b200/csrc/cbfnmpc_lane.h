@@ -760,26 +760,37 @@ struct LaneSolver {
       mu = sz / d::MQP;
     }
     {
-      bool okr = true;
-      const unsigned sv = g_enter(g, predictor);   // (sigma == 0 -- a pure corrector step -- is rare; the groups of a warp then differ)
-      if (predictor) {
-        l_assemble<C, false>(g, P, c, pr, d::Q_E, 0.0, 0.0, H);
-        info.n_fact++;
-        okr = l_riccati<C, true>(g, P, c, H, 0.0, f);
-      } else {
-        sigma = 0.0;  // E, G hold zeros: pure corrector with the previous factor
+      // sigma == 0 -- a pure corrector step with the PREVIOUS Hessian blocks and factor (Prime.c:176-180) -- is rare; a group in
+      // that state parks them in the border / filter / gradient columns (unused in this stage) while the warp refactorises
+      const bool keep = !predictor;
+      const bool any_keep = w_any(g, keep);
+      if (any_keep && keep) {
+        LUNR for (int t = 0; t < 10; t++) pr(d::F_PVB + t) = f.Pn[t];
+        LUNR for (int t = 0; t < 6; t++) pr(d::F_PVB + 10 + t) = f.Lc[t];
+        LUNR for (int t = 0; t < 12; t++) pr(d::F_KVB + t) = f.K[t];
+        LUNR for (int t = 0; t < 4; t++) { pr(d::F_FILT + t) = H.hx[t]; pr(d::F_GFY + t) = H.hl[t]; }
+        LUNR for (int t = 0; t < 2; t++) { pr(d::F_GFY + 4 + t) = H.hu[t]; pr(d::F_GFY + 6 + t) = H.hxu[t]; }
       }
-      g_leave(g, sv);
+      l_assemble<C, false>(g, P, c, pr, d::Q_E, 0.0, 0.0, H);
+      const bool okr = l_riccati<C, true>(g, P, c, H, 0.0, f) || keep;
+      if (predictor) info.n_fact++;
+      if (any_keep && keep) {
+        LUNR for (int t = 0; t < 10; t++) f.Pn[t] = pr(d::F_PVB + t);
+        LUNR for (int t = 0; t < 6; t++) f.Lc[t] = pr(d::F_PVB + 10 + t);
+        LUNR for (int t = 0; t < 12; t++) f.K[t] = pr(d::F_KVB + t);
+        LUNR for (int t = 0; t < 4; t++) { H.hx[t] = pr(d::F_FILT + t); H.hl[t] = pr(d::F_GFY + t); }
+        LUNR for (int t = 0; t < 2; t++) { H.hu[t] = pr(d::F_GFY + 4 + t); H.hxu[t] = pr(d::F_GFY + 6 + t); }
+      }
+      if (!predictor) sigma = 0.0;  // E, G hold zeros
       g_keep(g, okr);
       if (!okr) { info.qp_flag = 1; return true; }
     }
     double ap = 1.0, ad = 1.0;
     KV dd;
-    const unsigned sv_ph = g.mask;
+    const bool any_pred = w_any(g, predictor);
 #pragma unroll 1
-    for (int ph = 0; ph < 2; ph++) {
-      if (ph == 0) g_keep(g, predictor); else g_leave(g, sv_ph);
-      if (ph == 0 && !predictor) continue;
+    for (int ph = any_pred ? 0 : 1; ph < 2; ph++) {   // (a group without a predictor step runs ph 0 as a zombie)
+      const bool mine = ph == 1 || predictor;
       const double sm = sigma * mu;
       if (ph == 1) {
         // ---- pass C: corrector right-hand side, ds = -s z - ds_aff dz_aff + sigma mu (form_ds, Auxilary.c:250-267) -> DE
@@ -825,7 +836,7 @@ struct LaneSolver {
         rdm = fmax(rdm, fmax(-dzh * izh, -dzl * izl));
         if (aff) {
           s_dsz += dsl * zlo + dsh * zhi; s_sdz += slo * dzl + shi * dzh; s_dsdz += dsl * dzl + dsh * dzh;
-          pr(d::Q_E + s) = dsl * dzl; pr(d::Q_G + s) = dsh * dzh;
+          if (mine) { pr(d::Q_E + s) = dsl * dzl; pr(d::Q_G + s) = dsh * dzh; }
         } else {
           pr(d::Q_A + s) = dsl; pr(d::Q_B + s) = dsh; pr(d::Q_C + s) = dzl; pr(d::Q_D + s) = dzh;
         }
@@ -836,8 +847,10 @@ struct LaneSolver {
         // sum (s + ap ds)(z + ad dz) = s'z + ap ds'z + ad s'dz + ap ad ds'dz
         const double num = sz + g_sum(g, ap * s_dsz + ad * s_sdz + (ap * ad) * s_dsdz);
         const double rho = num / sz, mr = rho < 1.0 ? rho : 1.0;
-        sigma = mr * mr * mr;
-        if (sigma < 0.0) sigma = 0.0;
+        if (mine) {
+          sigma = mr * mr * mr;
+          if (sigma < 0.0) sigma = 0.0;
+        }
       }
     }
     ap = fmin(0.99 * ap, 1.0); ad = fmin(0.99 * ad, 1.0);
@@ -1095,32 +1108,29 @@ struct LaneSolver {
     {
       const double dw_last = PERS_DWLAST;
       bool ok = false;
-      const unsigned sv_ic = g.mask;
+      bool need = true;  // this group wants (another) factorisation; one that does not reproduces its factors (same H, same dw)
       for (;;) {
-        info.n_fact++;
-        ok = l_riccati<C, false>(g, P, c, H, dw, f);
-        {
-          const unsigned sv = g_enter(g, ok);
-          if (ok) ok = l_border_factor<C>(g, P, c, H, f, dw, pr, bf);
-          g_leave(g, sv);
+        if (need) info.n_fact++;
+        const bool okf = l_riccati<C, false>(g, P, c, H, dw, f);
+        const bool okb = l_border_factor<C>(g, P, c, H, f, dw, pr, bf);
+        if (need) {
+          ok = okf && okb;
+          need = !ok;
+          if (need) {
+            if (dw == 0.0) dw = (dw_last == 0.0) ? P.dw_first : fmax(P.dw_min, P.kw_minus * dw_last);
+            else dw *= (first_ic && dw_last == 0.0) ? P.kw_plus_first : P.kw_plus;
+            if (dw > P.dw_max) need = false;
+          }
         }
-        bool again = !ok;
-        if (again) {
-          if (dw == 0.0) dw = (dw_last == 0.0) ? P.dw_first : fmax(P.dw_min, P.kw_minus * dw_last);
-          else dw *= (first_ic && dw_last == 0.0) ? P.kw_plus_first : P.kw_plus;
-          if (dw > P.dw_max) again = false;
-        }
-        g_keep(g, again);
-        if (!again) break;
+        if (!w_any(g, need)) break;
       }
-      g_leave(g, sv_ic);
       g_keep(g, ok);
       if (!ok) { info.status = 3; return true; }
       if (dw > 0.0) { PERS_DWLAST = dw; first_ic = false; }
     }
     // ---- solve, then iterative refinement on the unreduced Newton system (one instance of the solve for both)
     KV dd;
-    const unsigned sv_rf = g.mask;
+    bool refining = true;  // this group takes the correction of the current solve
     for (int rf = 0;; rf++) {
       KV d2; double tb2[4];
       l_kkt_solve_border<C>(g, P, c, H, f, dw, pr, bf, r, d2, tb2);
@@ -1131,13 +1141,15 @@ struct LaneSolver {
         nlp_scatter_de(d::N_C, d2, d2p);
       } else {
         nlp_scatter_de(d::N_G, d2, d2p);
-        LUNR for (int i = 0; i < 4; i++) { dd.xs[i] += d2.xs[i]; dd.lm[i] += d2.lm[i]; dd.pi[i] += d2.pi[i]; }
-        LUNR for (int a = 0; a < 2; a++) { dd.us[a] += d2.us[a]; dd.nu[a] += d2.nu[a]; }
-        dd.dl += d2.dl; dd.eta += d2.eta;
+        if (refining) {
+          LUNR for (int i = 0; i < 4; i++) { dd.xs[i] += d2.xs[i]; dd.lm[i] += d2.lm[i]; dd.pi[i] += d2.pi[i]; }
+          LUNR for (int a = 0; a < 2; a++) { dd.us[a] += d2.us[a]; dd.nu[a] += d2.nu[a]; }
+          dd.dl += d2.dl; dd.eta += d2.eta;
+        }
       }
       // pass B: slot steps de -> C, dz_lo -> D, dz_hi -> E (rf = 0: from scratch; later: corrections), then the residual
       // weights of the complementarity rows: J'(z + dz) weights -> G, rc / s weights -> EV
-      const bool first = rf == 0;
+      const bool first = rf == 0, upd = first || refining;
       LSLOTS for (int s = 0; s < nsn; s++) {
         const bool vhi = s != d::SD;
         const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
@@ -1157,9 +1169,9 @@ struct LaneSolver {
           const double ch = vhi ? rch0 * rhi + zhi * rhi * dde : 0.0;
           if (s == d::SD && H.capped) cl = rcl0 * rlo - H.sc * dde - tbj;
           de += dde; dzl += cl; dzh += ch;
-          pr(d::N_C + s) = de;
+          if (upd) pr(d::N_C + s) = de;
         }
-        pr(d::N_D + s) = dzl; pr(d::N_E + s) = dzh;
+        if (upd) { pr(d::N_D + s) = dzl; pr(d::N_E + s) = dzh; }
         const double rcl = (mu - slo * zlo) - (slo * dzl + zlo * de);
         const double rch = vhi ? (mu - shi * zhi) - (shi * dzh - zhi * de) : 0.0;
         pr(d::N_G + s) = (zlo + dzl) - (zhi + dzh);
@@ -1197,9 +1209,8 @@ struct LaneSolver {
       nres = g_max(g, nres);
       const double nrhs = fmax(e_d, e_p);
       LANE_DBG("   refine %d nres %.2e nrhs %.2e\n", rf, nres, nrhs);
-      const bool more = nres > fmax(P.refine_rel * nrhs, P.refine_abs);
-      g_keep(g, more);
-      if (!more) break;
+      refining = refining && nres > fmax(P.refine_rel * nrhs, P.refine_abs);
+      if (!w_any(g, refining)) break;
       {
         KV jb; double wdb;
         l_gather<C, true>(g, pr, d::N_EV, H.gv, jb, wdb);
@@ -1208,7 +1219,6 @@ struct LaneSolver {
         r.dl += wdb;
       }
     }
-    g_leave(g, sv_rf);
     const double quad = dd.xs[0] * dd.xs[0] + dd.xs[2] * dd.xs[2];
     // ---- pass C: fraction to the boundary (alpha_max = min(1, tau / max_i(-ds_i / s_i))) and the line-search constants
     //      phi = f - mu sum log s, its directional derivative, sum of slack products (for log)
@@ -1248,10 +1258,8 @@ struct LaneSolver {
     // ---- filter line search (theta = ||A x - b||_1 shrinks by (1 - alpha)); pass D per trial
     double alpha = a_pmax;
     bool accepted = false, ftype = false;
-    const unsigned sv_ls = g.mask;
-    bool going = alpha >= P.alpha_min;
-    g_keep(g, going);
-    while (going) {
+    bool going = alpha >= P.alpha_min;   // this group still looks for its step length
+    while (w_any(g, going)) {
       // phi(x + alpha dx) - phi(x) = alpha g'dx + 1/2 alpha^2 dx'Q dx - mu sum log(s_t / s)
       double prod = 1.0, prod2 = 1.0;
       bool pos = true;
@@ -1274,7 +1282,7 @@ struct LaneSolver {
         const double dph = alpha * gdx + 0.5 * alpha * alpha * dQd - mu * dlog;
         const double pht = ph + dph;
         const bool fok = filter_ok(tht, pht);   // (a vote: evaluated by every group, used when the trial point is interior)
-        if (allpos && tht <= PERS_THMAX && fok) {
+        if (going && allpos && tht <= PERS_THMAX && fok) {
           const bool sw = dphi < 0.0 && alpha * (dphi * dphi) > th;  // switching condition, s_phi = 2, s_theta = 1, delta = 1
           if (th <= PERS_THMIN && sw) {
             if (dph - 10.0 * CBF_EPSM * fabs(ph) <= P.eta_phi * alpha * dphi) { accepted = true; ftype = true; }
@@ -1283,9 +1291,8 @@ struct LaneSolver {
           }
         }
       }
-      const bool recheck = accepted && anysmall;
-      const unsigned sv_rc = g_enter(g, recheck);
-      if (recheck) {
+      const bool recheck = going && accepted && anysmall;
+      if (w_any(g, recheck)) {
         // The test above works on the linearised slacks s + alpha ds.  Late in the run tau = 1 - mu lets an active slack shrink
         // by a factor mu in one step, to below the rounding (~1e-15) of the O(1) positions it is computed from.  When a trial
         // slack is that small, the slacks that pass A will compute at x + alpha dx -- by the same expressions, from the same
@@ -1302,14 +1309,12 @@ struct LaneSolver {
           const double e = pr(d::N_EV + s);
           okp = okp && (e - l_slot_lo<C, true>(P, s) > 0.0) && ((s != d::SD) ? (l_slot_hi<C, true>(P, s) - e > 0.0) : true);
         }
-        accepted = g_all(g, okp);
+        const bool okall = g_all(g, okp);
+        if (recheck) accepted = okall;
       }
-      g_leave(g, sv_rc);
-      if (!accepted) alpha *= 0.5;
-      going = !accepted && alpha >= P.alpha_min;
-      g_keep(g, going);
+      if (going && !accepted) alpha *= 0.5;
+      going = going && !accepted && alpha >= P.alpha_min;
     }
-    g_leave(g, sv_ls);
     LANE_LOG(alpha); LANE_LOG(ph); LANE_LOG(dphi);
     LANE_DBG("   alpha %.3e acc %d ftype %d ph %.10e dphi %.3e\n", alpha, (int)accepted, (int)ftype, ph, dphi);
     g_keep(g, accepted);

@@ -6,10 +6,17 @@
 // compiles to the bare SHFL behind one BRA.DIV.  With per-group masks ptxas has to prove at run time that the masks of the
 // active lanes partition the active set: S2R + MATCH.ANY + REDUX.OR + LOP3 in front of every cluster of shuffles -- 14.5 % of
 // the stall samples of the round-1 kernel (profiles/r02a_ncu_summary.md).  The price is a discipline: groups of one warp still
-// differ in iteration counts, inertia corrections, refinement solves and line-search lengths, so every region whose condition
-// is not warp-uniform and that contains a shuffle or a vote is bracketed by g_enter / g_leave (the mask shrinks to the lanes
-// that go in), a loop that groups leave at different trip counts shrinks the mask at its back edge (g_keep), and an early
-// return is announced by g_keep right before it.  Rule: no return inside a bracketed region.
+// differ in iteration counts, inertia corrections, refinement solves and line-search lengths.  (1) A region whose condition is
+// not warp-uniform and that contains a shuffle or a vote is bracketed by g_enter / g_leave (the mask shrinks to the lanes that
+// go in), and an early return is announced by g_keep right before it; no return inside a bracketed region.  (2) A LOOP that
+// contains shuffles keeps the mask it was entered with and runs while ANY group of the mask needs another trip (w_any); a group
+// that needs none runs through the extra trips as a zombie -- same instructions, every write to state that outlives the loop
+// guarded by the flag next to the loop.  That costs no time (the lanes of a warp share one instruction stream anyway) and keeps
+// the mask out of loop-carried registers: a mask that is the phi of a loop sits in a vector register and brings MATCH.ANY back
+// (measured: narrowing at the back edges left the MATCH count of the hot loops unchanged).  A fully warp-synchronous variant
+// (all 32 lanes always, finished groups as zombies of whole iterations, FULL mask) was measured too: no MATCH / REDUX at all
+// and 14 % less code, but 4 % slower than this one at 4096 instances and 11 % slower for a lone instance (zombie lanes still
+// cost shared-memory wavefronts and local-memory sectors).
 // CBF_HOST_EMU build (tests/emu only, never part of libcbfnmpc.so): the same names on 32 cooperative fibers (one warp = 8
 // groups) with mask-based rendezvous -- every lane named in the mask has to arrive with the same mask, and in the sitecheck
 // build at the same source-level site, before any of them leaves; anything else is reported as a deadlock -- so the kernel
@@ -45,7 +52,8 @@ LDEV bool g_all(const Grp& g, bool p) { return g_bits(g, !p) == 0u; }
 LDEV unsigned w_ballot_full(bool p) { return __ballot_sync(LFULL, p); }                    // all 32 lanes are present
 LDEV unsigned g_enter(Grp& g, bool p) { const unsigned sv = g.mask; g.mask = __ballot_sync(sv, p); return sv; }  // before `if (p) { ... }`
 LDEV void g_leave(Grp& g, unsigned sv) { g.mask = sv; }                                    // after it
-LDEV void g_keep(Grp& g, bool stay) { g.mask = __ballot_sync(g.mask, stay); }              // before `if (!stay) break / return`
+LDEV void g_keep(Grp& g, bool stay) { g.mask = __ballot_sync(g.mask, stay); }              // before `if (!stay) return`
+LDEV bool w_any(const Grp& g, bool p) { return __ballot_sync(g.mask, p) != 0u; }           // over all groups of the current mask
 // Loop control ("does any group of this CTA still iterate").  The warps of a CTA are kept within ONE solver iteration of each
 // other so that they fetch the same instruction-cache lines, but they do not wait for each other every iteration: round r ends
 // with an arrival on mbarrier r & 1 and a wait for round r - 1 only.  A warp whose own groups have all finished has nothing to
@@ -191,6 +199,7 @@ LDEV unsigned w_ballot_full(bool p) { return l_ballot(LFULL, p); }
 LDEV unsigned g_enter(Grp& g, bool p) { const unsigned sv = g.mask; g.mask = l_ballot(sv, p); return sv; }
 LDEV void g_leave(Grp& g, unsigned sv) { g.mask = sv; }
 LDEV void g_keep(Grp& g, bool stay) { g.mask = l_ballot(g.mask, stay); }
+LDEV bool w_any(const Grp& g, bool p) { return l_ballot(g.mask, p) != 0u; }
 struct Pace {};
 LDEV bool pace_go(Pace&, bool mine) { return mine; }  // the emulated CTA is one warp
 #ifdef CBF_EMU_GPUMATH  // mimic the CUDA build's rounding: low-precision seed + two Newton steps (not correctly rounded)
