@@ -412,7 +412,7 @@ def ext_solve(x0, xdes, feet, contact, obs, nbr=None, N=4, eps_obs=None, eps_nbr
     return ext_res_to_dict(r)
 
 
-EXT_RELAX, EXT_PUB_TOL, EXT_MAX_TEAM_ITERS, EXT_MU_STALL = 0.7, 1e-10, 100, 6
+EXT_RELAX, EXT_PUB_TOL, EXT_MAX_TEAM_ITERS, EXT_MU_STALL = 0.7, 1e-10, 64, 6
 
 
 def ext_solve_teams(x0, xdes, feet, contact, obs, T, N=4, eps_obs=None, eps_nbr=2.2, relax=EXT_RELAX, pub_tol=EXT_PUB_TOL, max_team_iters=EXT_MAX_TEAM_ITERS, mu_stall=EXT_MU_STALL, nthreads=8, g=None, o=None):

@@ -48,7 +48,7 @@ def ext_alloc_out(B, N):
     return o
 
 
-def solve(insts, N=4, T=1, nbr=None, eps_obs=None, eps_nbr=2.2, relax=0.7, pub_tol=1e-10, max_team_iters=100, mu_stall=6, gains=None, options=None, trace=False):
+def solve(insts, N=4, T=1, nbr=None, eps_obs=None, eps_nbr=2.2, relax=0.7, pub_tol=1e-10, max_team_iters=64, mu_stall=6, gains=None, options=None, trace=False):
     """nbr: (B, n_nbr, N, 2) fixed neighbour trajectories (T == 1) or None; T == 4: teams exchange through the emulated warp."""
     global _lib
     L = C.CDLL(build(trace=trace))
