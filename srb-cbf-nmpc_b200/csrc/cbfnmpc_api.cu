@@ -402,6 +402,13 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
   }
   // function attributes are per device: set them for every context, not once per process
   CK(cudaFuncSetAttribute(cbfnmpc_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LANE_NPRIV * LANE_NT * sizeof(double))));
+  {
+    // two CTAs per SM need 2 x (93.2 + 1) KB of shared memory: ask for exactly the carve-out step that holds them, so that the rest of
+    // the 256 KB stays L1 -- the kernel's stack (spilled registers: 408 B x 128 threads per SM) then fits in it instead of going to L2
+    const int need_kb = (int)((2 * (LANE_NPRIV * LANE_NT * sizeof(double) + 1024) + 1023) / 1024);
+    const int pct = (100 * need_kb + 227) / 228;
+    CK(cudaFuncSetAttribute(cbfnmpc_lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct < 100 ? pct : 100));
+  }
   CK(cudaFuncSetAttribute(cbfnmpc_qpdense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QD_WARPS * sizeof(QDenseWS))));
   CK(cudaFuncSetAttribute(cbfnmpc_refgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * CBF_REFGEN_MAX_OBS)));
   *out = c;

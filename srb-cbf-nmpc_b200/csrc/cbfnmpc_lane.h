@@ -10,8 +10,9 @@
 //                   "IPM-F" of DESIGN.md (feasible w.r.t. inequalities, exact Hessian, inertia correction);
 //   epilogue      : Bezier fit of MPC_dist.cpp:784-855.
 // KKT systems: per-stage elimination of (u_j, lambda_j) through u = F lambda, 1'lambda = 1; Riccati/Cholesky
-// recursion over the horizon as a chain lane 3 -> 2 -> 1 -> 0 (each lane keeps its stage's factors in registers);
-// 5x5 Schur complement for the global slack variable and the (capped) distance rows.
+// recursion over the horizon as a chain lane 3 -> 2 -> 1 -> 0 (each lane keeps its stage's factors in registers) on the
+// 5-state (x, delta): the slack variable of the distance rows rides along as a fifth state, a distance row whose Sigma
+// exceeds the cap keeps its remainder inside its stage in quasi-definite form.
 //
 // The iterate, the Hessian blocks and the Riccati factors live in registers (compile-time indices only); per-row state
 // (slacks, multipliers, reciprocals, steps) and a few vectors that would otherwise be spilled live in thread-private
@@ -45,21 +46,18 @@ struct LaneHess {        // stage blocks of H = W + dw I + J' Sigma J  (dw is ad
   double hx[4], hxy;     // x_{j+1}: diagonal, (p_x, p_y) coupling
   double hu[2], hxu[2];  // u_j diagonal; coupling x_j position <-> u_j (friction rows)
   double hl[4];          // lambda_j diagonal
-  double bd[2], hd;      // coupling p_{j+1} <-> slack variable; slack-variable diagonal (group value)
+  double bd[2], hd;      // coupling p_{j+1} <-> this stage's copy of the slack variable; its diagonal (the row's Sigma; + P.slw at stage 3)
   double gv[2];          // gradient of the distance row wrt p_{j+1}: 2 (p - o)
   double sc, srinv;      // capped Sigma of the distance row, 1 / (Sigma - sc) when capped
-  int capped;
+  int capped;            // the remainder of the row is kept in quasi-definite form (l_factor)
 };
 
-struct LaneFact {        // Riccati factors of stage j
-  double Pn[10];         // P_{j+1}, packed lower (i >= k: i (i + 1) / 2 + k)
-  double K[12];          // K_j = R~^-1 S~_j: [a * 4 + k]  (S~_j itself is not kept: S~'R~^-1 v = K'v in the substitutions)
+struct LaneFact {        // Riccati factors of stage j on the 5-state xi = (x, delta)
+  double Pn[15];         // cost-to-go at xi_{j+1}, packed lower (i >= k: i (i + 1) / 2 + k)
+  double K[15];          // K_j = R~^-1 S~_j: [a * 5 + m]  (S~_j itself is not kept: S~'R~^-1 v = K'v in the substitutions)
   double Lc[6];          // chol(R~_j): (1/l00, l10, 1/l11, l20, l21, 1/l22)
-};
-
-struct LaneBorder {      // border part of the factorisation (NLP): group values replicated in the 4 lanes
-  double L[10], Tic[4], cb[4], den;
-  int cap[4];
+  double Zm[3], Nt[5], Ym[3], Tc;  // quasi-definite row: R~^-1 M', N~ = N - M R~^-1 S~, L^-1 M', 1 / sqrt(T)
+  double p0dd;           // cost-to-go curvature of delta_0 (lane 0's value, replicated)
 };
 
 LDEV int sy(int i, int k) { return i >= k ? (i * (i + 1)) / 2 + k : (k * (k + 1)) / 2 + i; }
@@ -79,17 +77,13 @@ struct LaneDims {
   // The friction slots come last so that lane 0 (which has none: x_0 is fixed) simply runs shorter slot loops.
   static constexpr int SX = 0, SU = 4, SL = 6, SFQ = 6 + C, NSQP = 8 + C, SV = 6 + C, SD = 8 + C, SFN = 9 + C, NS = 11 + C;
   // thread-private shared-memory fields.  QP stage: 12 per slot, stride NSQP; NLP stage: 11 per slot, stride NS (the two
-  // stages never overlap); then the border vectors and the filter.
+  // stages never overlap); then the filter and a few parked vectors.
   static constexpr int Q_SLO = 0, Q_SHI = NSQP, Q_ZLO = 2 * NSQP, Q_ZHI = 3 * NSQP, Q_A = 4 * NSQP, Q_B = 5 * NSQP, Q_C = 6 * NSQP,
                        Q_D = 7 * NSQP, Q_E = 8 * NSQP, Q_G = 9 * NSQP, Q_EV = 10 * NSQP, Q_DE = 11 * NSQP, Q_END = 12 * NSQP;
   static constexpr int N_SLO = 0, N_SHI = NS, N_ZLO = 2 * NS, N_ZHI = 3 * NS, N_A = 4 * NS, N_B = 5 * NS, N_C = 6 * NS, N_D = 7 * NS,
                        N_E = 8 * NS, N_G = 9 * NS, N_EV = 10 * NS, N_END = 11 * NS;
-  static constexpr int F_PVB = Q_END > N_END ? Q_END : N_END;  // 4 border columns x 4
-  static constexpr int F_KVB = F_PVB + 16;     // 4 border columns x NW (3)
-  static constexpr int F_FILT = F_KVB + 12;    // this lane's share of the filter: entries p = 4 q + j (q = 0, 1), (theta, phi) each
-  static constexpr int F_GFY = F_FILT + 4;     // grad f + A'y of the iterate (11) and its dynamics residual (4), parked here between
-  static constexpr int F_REP = F_GFY + 11;     // the right-hand side and the refinement check instead of being spilled
-  static constexpr int F_XDES = F_REP + 4;     // desired state of this lane's stage (4)
+  static constexpr int F_FILT = Q_END > N_END ? Q_END : N_END;  // this lane's share of the filter: entries p = 4 q + j (q = 0, 1), (theta, phi) each
+  static constexpr int F_XDES = F_FILT + 4;    // desired state of this lane's stage (4)
   static constexpr int F_XIN = F_XDES + 4;     // measured state x_0 (4; used by lane 0)
   static constexpr int F_PERS = F_XIN + 4;     // values that live across iterations and are read once or twice per iteration:
                                                // tau, dw_last, theta_max, theta_min, ad_prev (out of the register file)
@@ -107,6 +101,7 @@ constexpr int LANE_NPRIV = LaneDims<4>::NPRIV;
 // in the QP stage (FLOOR; this only damps the motion of lambda inside its optimal face).  The NLP stage reports every
 // non-positive pivot instead and lets the inertia correction add dw I, which is what keeps its line search well scaled.  iSWIFT's LDL' / the oracle's Bunch-Kaufman work on the
 // unreduced KKT matrix and do not meet this cancellation (Auxilary.c:332-420).
+#define LANE_QD_CHECK 1e11   // largest Sigma of a group's distance rows above which the Newton residual is checked (iterative refinement)
 #define CHOL_FLOOR 1e-12
 #define CHOL_NOISE 1e-9
 template <bool FLOOR>
@@ -151,26 +146,6 @@ LDEV void l_chol_bwd(const double* L, double* b) {  // b <- L^-T b
 template <int NW>
 LDEV void l_chol_solve(const double* L, double* b) { l_chol_fwd<NW>(L, b); l_chol_bwd<NW>(L, b); }
 
-// 4x4 Cholesky (packed lower, inverse diagonals stored) and solve
-LDEV bool l_chol4(const double* T, double* L) {
-  bool ok = true;
-  const double d0 = T[0]; ok = ok && d0 > 0.0 && d0 < 1e300; const double i0 = l_rsq(d0);
-  const double l10 = T[1] * i0, l20 = T[3] * i0, l30 = T[6] * i0;
-  const double d1 = T[2] - l10 * l10; ok = ok && d1 > 0.0; const double i1 = l_rsq(d1);
-  const double l21 = (T[4] - l20 * l10) * i1, l31 = (T[7] - l30 * l10) * i1;
-  const double d2 = T[5] - l20 * l20 - l21 * l21; ok = ok && d2 > 0.0; const double i2 = l_rsq(d2);
-  const double l32 = (T[8] - l30 * l20 - l31 * l21) * i2;
-  const double d3 = T[9] - l30 * l30 - l31 * l31 - l32 * l32; ok = ok && d3 > 0.0; const double i3 = l_rsq(d3);
-  L[0] = i0; L[1] = l10; L[2] = i1; L[3] = l20; L[4] = l21; L[5] = i2; L[6] = l30; L[7] = l31; L[8] = l32; L[9] = i3;
-  return ok;
-}
-LDEV void l_chol4_solve(const double* L, const double* b, double* k) {
-  const double y0 = b[0] * L[0], y1 = (b[1] - L[1] * y0) * L[2], y2 = (b[2] - L[3] * y0 - L[4] * y1) * L[5],
-               y3 = (b[3] - L[6] * y0 - L[7] * y1 - L[8] * y2) * L[9];
-  k[3] = y3 * L[9]; k[2] = (y2 - L[8] * k[3]) * L[5]; k[1] = (y1 - L[4] * k[2] - L[7] * k[3]) * L[2];
-  k[0] = (y0 - L[1] * k[1] - L[3] * k[2] - L[6] * k[3]) * L[0];
-}
-
 // LIP maps (per axis b: position index 2b, velocity index 2b+1; MPC_dist.cpp:117-127)
 LDEV void l_Ax(const KParams& P, const double* x, double* y) {        // y = A x
   LUNR for (int b = 0; b < 2; b++) {
@@ -213,7 +188,7 @@ LDEV void l_eq_residual(const KParams& P, const LaneConst& c, const KV& v, const
 
 // grad f(x) + A' y restricted to this lane's variables; pin = pi of lane j+1 (0 at lane 3)
 template <int C>
-LDEV void l_grad_Aty(const KParams& P, const LaneConst& c, const Priv& pr, const KV& x, const KV& y, const double* pin, bool with_grad, KV& g) {
+LDEV void l_grad_Aty(const KParams& P, const LaneConst& c, const Priv& pr, const KV& x, const KV& y, const double* pin, bool with_grad, int j, KV& g) {
   double at[4];
   l_ATx(P, pin, at);
   LUNR for (int i = 0; i < 4; i++) {
@@ -231,7 +206,7 @@ LDEV void l_grad_Aty(const KParams& P, const LaneConst& c, const Priv& pr, const
     LUNR for (int i = 0; i < C - 1; i++) g.lm[i] = gl - (c.D[i] * y.nu[0] + c.D[(C - 1) + i] * y.nu[1]);
     g.lm[C - 1] = gl;
   }
-  g.dl = with_grad ? P.slw * x.dl : 0.0;
+  g.dl = (with_grad && j == 3) ? P.slw * x.dl : 0.0;   // this lane's share: the slack variable's cost sits at the last stage's copy
 }
 
 // shuffle helpers: 4-vector from the previous / next lane (zero at the chain ends unless `first` supplies lane 0's value)
@@ -243,56 +218,67 @@ LDEV void l_from_next(const Grp& g, const double* v, double* out) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Riccati / Cholesky factorisation as a chain over the 4 lanes.  Every lane evaluates its stage at every step; lane j
-// holds valid data from step 4 - j on, so after 4 steps all stages are factorised (no divergent code, no extra issue
-// slots: the idle lanes of a step would execute the same instructions masked off).
+// Riccati / Cholesky factorisation as a chain over the 4 lanes, on the 5-state xi = (x, delta): the slack variable rides along
+// as a fifth state (delta_{j+1} = delta_j, delta_0 free; its cost P.slw and the inertia shift dw sit at the last stage's copy),
+// so a distance row is an ordinary row of its own stage and there is no border.  (Round 1 eliminated the slack variable and the
+// capped part of the 4 distance rows through a 5 x 5 Schur complement whose 4 border columns went through a backward / forward
+// chain of their own at every factorisation: 24 chain steps per iteration, 11 % of the stall samples, 28 private columns.  This
+// form needs 12 steps; it is the recursion of the extended-mode kernel, cbfnmpc_ext.h, where it reproduces the oracle's iterates
+// to 1e-14 without refinement on the cfg-3 set.)
+// Every lane evaluates its stage at every step; lane j holds valid data from step 3 - j on, so after 4 steps all stages are
+// factorised (no divergent code, no extra issue slots: the idle lanes of a step would execute the same instructions masked off).
+// A distance row whose Sigma exceeds P.sigma_cap is condensed only up to the cap; the remainder stays inside its stage in
+// quasi-definite form and is eliminated AFTER the stage's controls:  T = 1 / (Sigma - cap) + M R~^-1 M',  N~ = N - M R~^-1 S~,
+// P_j += N~' T^-1 N~  (all numbers stay O(curvature) while the stage's controls have authority over the row; when they do not,
+// the stiffness moves to the previous stage and the recursion loses digits there: iterative refinement in nlp_iter).
 // Returns false when a pivot block of this group is not positive definite.
 // ---------------------------------------------------------------------------------------------------------------
 template <int C, bool FLOOR>
-LDEV bool l_riccati(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, double dw, LaneFact& f) {
+LDEV bool l_factor(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, double dw, LaneFact& f) {
   constexpr int NW = LaneDims<C>::NW;
-  // cost on x_j (previous lane's hx, hxy), needed by stage j
-  double hxp[4], hxyp;
-  LUNR for (int i = 0; i < 4; i++) hxp[i] = g_up(g, H.hx[i]);
-  hxyp = g_up(g, H.hxy);
-  // terminal cost-to-go at this lane if it were the last stage; P_{j+1} of lanes < 3 arrives through the chain
-  double Pown[10];
-  LUNR for (int i = 0; i < 4; i++) LUNR for (int k = 0; k <= i; k++) Pown[sy(i, k)] = (i == k) ? H.hx[i] + dw : ((i == 2 && k == 0) ? H.hxy : 0.0);
-  double Pout[10];
-  LUNR for (int t = 0; t < 10; t++) { Pout[t] = 0.0; f.Pn[t] = Pown[t]; }
+  // own blocks of the cost on xi_{j+1}; the cost-to-go of lanes < 3 adds what lane j+1 hands down
+  double Pown[15];
+  LUNR for (int t = 0; t < 15; t++) Pown[t] = 0.0;
+  LUNR for (int i = 0; i < 4; i++) Pown[sy(i, i)] = H.hx[i] + dw;
+  Pown[sy(2, 0)] = H.hxy; Pown[sy(4, 0)] = H.bd[0]; Pown[sy(4, 2)] = H.bd[1];
+  Pown[sy(4, 4)] = H.hd + ((g.j == 3) ? dw : 0.0);
+  double Pout[15];
+  LUNR for (int t = 0; t < 15; t++) { Pout[t] = 0.0; f.Pn[t] = Pown[t]; }
   bool ok = true;
 #pragma unroll 1
   for (int step = 0; step < 4; step++) {
-    // P_{j+1}: lane 3 uses its own terminal block, the others what lane j+1 produced in the previous step
     if (step > 0) {
-      LUNR for (int t = 0; t < 10; t++) { const double v = g_down(g, Pout[t]); if (g.j < 3) f.Pn[t] = v; }
+      LUNR for (int t = 0; t < 15; t++) { const double v = g_down(g, Pout[t]); if (g.j < 3) f.Pn[t] = Pown[t] + v; }
     }
     const double* Pn = f.Pn;
-    // PA = Pn A   (A block diagonal per axis)
-    double PA[16];
-    LUNR for (int i = 0; i < 4; i++) LUNR for (int b = 0; b < 2; b++) {
-      const double p0 = Pn[sy(i, 2 * b)], p1 = Pn[sy(i, 2 * b + 1)];
-      PA[4 * i + 2 * b] = p0 * P.a11 + p1 * P.a21;
-      PA[4 * i + 2 * b + 1] = p0 * P.a12 + p1 * P.a22;
+    double PA[25];   // Pn A^ (A^ = diag(A2, A2, 1))
+    LUNR for (int i = 0; i < 5; i++) {
+      LUNR for (int b = 0; b < 2; b++) {
+        const double p0 = Pn[sy(i, 2 * b)], p1 = Pn[sy(i, 2 * b + 1)];
+        PA[5 * i + 2 * b] = p0 * P.a11 + p1 * P.a21;
+        PA[5 * i + 2 * b + 1] = p0 * P.a12 + p1 * P.a22;
+      }
+      PA[5 * i + 4] = Pn[sy(i, 4)];
     }
-    // G = Bd' Pn (2 x 4), M2 = Bd' Pn Bd (2 x 2 sym), GA = Bd' PA (2 x 4)
-    double G[8], GA[8];
-    LUNR for (int cc = 0; cc < 2; cc++) LUNR for (int m = 0; m < 4; m++) {
-      G[4 * cc + m] = P.bp * Pn[sy(2 * cc, m)] + P.bv * Pn[sy(2 * cc + 1, m)];
-      GA[4 * cc + m] = P.bp * PA[4 * (2 * cc) + m] + P.bv * PA[4 * (2 * cc + 1) + m];
+    double GA[10];   // B'Pn A^ (2 x 5)
+    LUNR for (int cc = 0; cc < 2; cc++) {
+      LUNR for (int m = 0; m < 5; m++) GA[5 * cc + m] = P.bp * PA[5 * (2 * cc) + m] + P.bv * PA[5 * (2 * cc + 1) + m];
     }
-    double N2[3];  // (00, 10, 11) of M2 + diag(hu + dw)
-    N2[0] = P.bp * G[0] + P.bv * G[1] + (H.hu[0] + dw);
-    N2[1] = P.bp * G[4] + P.bv * G[5];
-    N2[2] = P.bp * G[6] + P.bv * G[7] + (H.hu[1] + dw);
+    // N2 = B'Pn B + diag(hu + dw)
+    double N2[3];
+    {
+      const double g00 = P.bp * Pn[sy(0, 0)] + P.bv * Pn[sy(1, 0)], g01 = P.bp * Pn[sy(0, 1)] + P.bv * Pn[sy(1, 1)];
+      const double g22 = P.bp * Pn[sy(2, 2)] + P.bv * Pn[sy(3, 2)], g23 = P.bp * Pn[sy(2, 3)] + P.bv * Pn[sy(3, 3)];
+      const double g10 = P.bp * Pn[sy(2, 0)] + P.bv * Pn[sy(3, 0)], g11 = P.bp * Pn[sy(2, 1)] + P.bv * Pn[sy(3, 1)];
+      N2[0] = P.bp * g00 + P.bv * g01 + (H.hu[0] + dw);
+      N2[1] = P.bp * g10 + P.bv * g11;
+      N2[2] = P.bp * g22 + P.bv * g23 + (H.hu[1] + dw);
+    }
     // R~ = D' N2 D + (hl_last + dw) 11' + diag(hl + dw)
     double Rt[6];
     {
-      double T1[6];  // T1[cc][b] = sum_c' N2[cc][c'] D[c'][b]
-      LUNR for (int b = 0; b < NW; b++) {
-        T1[b] = N2[0] * c.D[b] + N2[1] * c.D[NW + b];
-        T1[NW + b] = N2[1] * c.D[b] + N2[2] * c.D[NW + b];
-      }
+      double T1[6];
+      LUNR for (int b = 0; b < NW; b++) { T1[b] = N2[0] * c.D[b] + N2[1] * c.D[NW + b]; T1[NW + b] = N2[1] * c.D[b] + N2[2] * c.D[NW + b]; }
       const double hlast = H.hl[C - 1] + dw;
       LUNR for (int a = 0; a < NW; a++) LUNR for (int b = 0; b <= a; b++) {
         double s = c.D[a] * T1[b] + c.D[NW + a] * T1[NW + b] + hlast;
@@ -301,126 +287,62 @@ LDEV bool l_riccati(const Grp& g, const KParams& P, const LaneConst& c, const La
       }
     }
     const bool okc = l_chol<NW, FLOOR>(Rt, f.Lc);
-    // S~ = D' (GA + hxu on the position columns)
-    GA[0] += H.hxu[0]; GA[4 + 2] += H.hxu[1];
-    double Y[12];
-    double St[12];
-    LUNR for (int a = 0; a < NW; a++) LUNR for (int k = 0; k < 4; k++) St[4 * a + k] = c.D[a] * GA[k] + c.D[NW + a] * GA[4 + k];
-    // Y = L^-1 S~, K = L^-T Y, column by column
-    LUNR for (int k = 0; k < 4; k++) {
+    // S~ = D' (GA + hxu on the position columns);  Y = L^-1 S~,  K = L^-T Y, column by column
+    GA[0] += H.hxu[0]; GA[5 + 2] += H.hxu[1];
+    double Y[15];
+    LUNR for (int m = 0; m < 5; m++) {
       double col[3] = {0.0, 0.0, 0.0};
-      LUNR for (int a = 0; a < NW; a++) col[a] = St[4 * a + k];
+      LUNR for (int a = 0; a < NW; a++) col[a] = c.D[a] * GA[m] + c.D[NW + a] * GA[5 + m];
       l_chol_fwd<NW>(f.Lc, col);
-      LUNR for (int a = 0; a < NW; a++) Y[4 * a + k] = col[a];
+      LUNR for (int a = 0; a < NW; a++) Y[5 * a + m] = col[a];
       l_chol_bwd<NW>(f.Lc, col);
-      LUNR for (int a = 0; a < NW; a++) f.K[4 * a + k] = col[a];
+      LUNR for (int a = 0; a < NW; a++) f.K[5 * a + m] = col[a];
     }
-    // P_j = Q~ - Y'Y,  Q~ = A' PA + diag(hx_{j} + dw) + hxy_{j}
-    LUNR for (int i = 0; i < 4; i++) LUNR for (int k = 0; k <= i; k++) {
-      const int bi = i >> 1, ri = i & 1;
-      double s = (ri ? P.a12 : P.a11) * PA[4 * (2 * bi) + k] + (ri ? P.a22 : P.a21) * PA[4 * (2 * bi + 1) + k];
-      if (i == k) s += hxp[i] + dw;
-      if (i == 2 && k == 0) s += hxyp;
-      LUNR for (int a = 0; a < NW; a++) s -= Y[4 * a + i] * Y[4 * a + k];
+    // P_j (without lane j-1's own blocks) = A^'PA - Y'Y
+    LUNR for (int i = 0; i < 5; i++) LUNR for (int k = 0; k <= i; k++) {
+      double s;
+      if (i < 4) { const int bi = i >> 1, ri = i & 1; s = (ri ? P.a12 : P.a11) * PA[5 * (2 * bi) + k] + (ri ? P.a22 : P.a21) * PA[5 * (2 * bi + 1) + k]; }
+      else s = PA[5 * 4 + k];
+      LUNR for (int a = 0; a < NW; a++) s -= Y[5 * a + i] * Y[5 * a + k];
       Pout[sy(i, k)] = s;
+    }
+    // the row kept in quasi-definite form (the distance row of x_{j+1} acts on xi_j through A^ and B)
+    if (H.capped) {
+      double col[3] = {0.0, 0.0, 0.0};
+      LUNR for (int a = 0; a < NW; a++) col[a] = P.bp * (H.gv[0] * c.D[a] + H.gv[1] * c.D[NW + a]);
+      l_chol_fwd<NW>(f.Lc, col);
+      LUNR for (int a = 0; a < 3; a++) f.Ym[a] = (a < NW) ? col[a] : 0.0;
+      l_chol_bwd<NW>(f.Lc, col);
+      LUNR for (int a = 0; a < 3; a++) f.Zm[a] = (a < NW) ? col[a] : 0.0;
+      const double Nq[5] = {H.gv[0] * P.a11, H.gv[0] * P.a12, H.gv[1] * P.a11, H.gv[1] * P.a12, 1.0};
+      LUNR for (int m = 0; m < 5; m++) {
+        double s = Nq[m];
+        LUNR for (int a = 0; a < NW; a++) s -= f.Ym[a] * Y[5 * a + m];
+        f.Nt[m] = s;
+      }
+      const double t00 = H.srinv + f.Ym[0] * f.Ym[0] + f.Ym[1] * f.Ym[1] + f.Ym[2] * f.Ym[2];
+      f.Tc = l_rsq(t00);
+      double V0[5];
+      LUNR for (int m = 0; m < 5; m++) V0[m] = f.Nt[m] * f.Tc;
+      LUNR for (int i = 0; i < 5; i++) LUNR for (int k = 0; k <= i; k++) Pout[sy(i, k)] += V0[i] * V0[k];
     }
     ok = okc;
   }
-  if (g.j == 0) { LUNR for (int t = 0; t < 12; t++) f.K[t] = 0.0; }  // x_0 is fixed: no feedback at stage 0
-  return g_all(g, ok);
+  // x_0 is fixed (the chains feed lane 0 with zeros) but delta_0 is free: its curvature is lane 0's Pout(4,4), which must be positive
+  const double p0 = g_idx(g, Pout[sy(4, 4)], 0);
+  f.p0dd = p0;
+  return g_all(g, ok) && (p0 > 0.0) && (p0 < 1e300);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Substitutions.  NB = number of border right-hand sides carried along with the (optional) main one.
-//   backward: lane j receives from lane j+1, adds its own right-hand side, keeps pv (p_{j+1}) and kv, passes on;
-//   forward : lane j receives x_j from lane j-1, produces x_{j+1} (and, for the main RHS, w and the dynamics multiplier).
+// Solve  [H A'; A 0][dx; dy] = [r1; r2]  with the current factorisation (r.xs,us,lm = r1 of this lane's variables, r.dl = this
+// lane's SHARE of the slack variable's row; r.pi,nu,eta = r2).  One backward chain (lane j receives from lane j+1, adds its own
+// right-hand side, keeps pv and kv, passes on), the slack variable from lane 0's cost-to-go, one forward chain.
+// rq: right-hand side of this lane's quasi-definite row (g'dx - t / (Sigma - cap) = rq; zero in the first solve, the residual
+// in refinement); tq: its multiplier t.
 // ---------------------------------------------------------------------------------------------------------------
-struct LaneMain { double rx[4], rw[3], cv[4], pv[4], kv[3]; };  // main RHS after the stage elimination + its backward vectors
+struct LaneMain { double rx[5], rw[3], cv[4], pv[5], kv[3], tt; };
 
-template <int C, bool MAIN, int NB>
-LDEV void l_backward(const Grp& g, const KParams& P, const LaneConst& c, const LaneFact& f, LaneMain& m, const double (*brhs)[4],
-                     double (*bpv)[4], double (*bkv)[3]) {
-  constexpr int NW = LaneDims<C>::NW, NCH = (MAIN ? 1 : 0) + NB;
-  double out[NCH > 0 ? NCH : 1][4];
-  LUNR for (int r = 0; r < NCH; r++) LUNR for (int i = 0; i < 4; i++) out[r][i] = 0.0;
-#pragma unroll 1
-  for (int step = 0; step < 4; step++) {
-    LUNR for (int r = 0; r < NCH; r++) {
-      const bool is_main = MAIN && r == 0;
-      const int rb = MAIN ? r - 1 : r;
-      double inc[4];
-      if (step > 0) l_from_next(g, out[r], inc);
-      else { LUNR for (int i = 0; i < 4; i++) inc[i] = 0.0; }
-      double pn[4], q[4];
-      LUNR for (int i = 0; i < 4; i++) pn[i] = (is_main ? m.rx[i] : brhs[rb][i]) + inc[i];
-      LUNR for (int i = 0; i < 4; i++) {
-        double s = -pn[i];
-        if (is_main) { LUNR for (int k = 0; k < 4; k++) s += f.Pn[sy(i, k)] * m.cv[k]; }
-        q[i] = s;
-      }
-      const double g0 = P.bp * q[0] + P.bv * q[1], g1 = P.bp * q[2] + P.bv * q[3];
-      double k[3] = {0.0, 0.0, 0.0}, kr[3] = {0.0, 0.0, 0.0};
-      LUNR for (int a = 0; a < NW; a++) { kr[a] = (is_main ? m.rw[a] : 0.0) - (c.D[a] * g0 + c.D[NW + a] * g1); k[a] = kr[a]; }
-      l_chol_solve<NW>(f.Lc, k);
-      double aq[4];
-      l_ATx(P, q, aq);
-      LUNR for (int i = 0; i < 4; i++) {  // -A'q - S~'R~^-1 kr = -A'q - K'kr
-        double s = -aq[i];
-        LUNR for (int a = 0; a < NW; a++) s -= f.K[4 * a + i] * kr[a];
-        out[r][i] = s;
-      }
-      if (is_main) { LUNR for (int i = 0; i < 4; i++) m.pv[i] = pn[i]; LUNR for (int a = 0; a < NW; a++) m.kv[a] = k[a]; }
-      else { LUNR for (int i = 0; i < 4; i++) bpv[rb][i] = pn[i]; LUNR for (int a = 0; a < NW; a++) bkv[rb][a] = k[a]; }
-    }
-  }
-}
-
-// mode 0: positions of x_{j+1} only (pos[r][2]);  mode 1 (main only): dx.xs, w, dy.pi
-template <int C, bool MAIN, int NB, int MODE>
-LDEV void l_forward(const Grp& g, const KParams& P, const LaneConst& c, const LaneFact& f, const LaneMain& m, const double (*bpv)[4],
-                    const double (*bkv)[3], double (*pos)[2], double* dxs, double* wout, double* dpi) {
-  constexpr int NW = LaneDims<C>::NW, NCH = (MAIN ? 1 : 0) + NB;
-  double xn[NCH > 0 ? NCH : 1][4];
-  LUNR for (int r = 0; r < NCH; r++) LUNR for (int i = 0; i < 4; i++) xn[r][i] = 0.0;
-#pragma unroll 1
-  for (int step = 0; step < 4; step++) {
-    LUNR for (int r = 0; r < NCH; r++) {
-      const bool is_main = MAIN && r == 0;
-      const int rb = MAIN ? r - 1 : r;
-      double xp[4];
-      if (step > 0) l_from_prev(g, xn[r], xp);
-      else { LUNR for (int i = 0; i < 4; i++) xp[i] = 0.0; }
-      double w[3] = {0.0, 0.0, 0.0};
-      LUNR for (int a = 0; a < NW; a++) {
-        double s = is_main ? m.kv[a] : bkv[rb][a];
-        LUNR for (int k = 0; k < 4; k++) s -= f.K[4 * a + k] * xp[k];
-        w[a] = s;
-      }
-      double d0 = 0.0, d1 = 0.0;
-      LUNR for (int a = 0; a < NW; a++) { d0 += c.D[a] * w[a]; d1 += c.D[NW + a] * w[a]; }
-      double ax[4];
-      l_Ax(P, xp, ax);
-      ax[0] += P.bp * d0; ax[1] += P.bv * d0; ax[2] += P.bp * d1; ax[3] += P.bv * d1;
-      if (is_main) { LUNR for (int i = 0; i < 4; i++) ax[i] += m.cv[i]; }
-      LUNR for (int i = 0; i < 4; i++) xn[r][i] = ax[i];
-      if (MODE == 0) { pos[r][0] = ax[0]; pos[r][1] = ax[2]; }
-      else if (is_main) {
-        LUNR for (int i = 0; i < 4; i++) {
-          double s = -m.pv[i];
-          LUNR for (int k = 0; k < 4; k++) s += f.Pn[sy(i, k)] * ax[k];
-          dxs[i] = ax[i]; dpi[i] = s;
-        }
-        LUNR for (int a = 0; a < NW; a++) wout[a] = w[a];
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Solve  [H A'; A 0][dx; dy] = [r1; r2]  with the current factorisation (r.xs,us,lm,dl = r1; r.pi,nu,eta = r2).
-// BORDER: the slack variable and the capped distance rows are coupled through the 5x5 Schur complement of `bf`, whose
-// border vectors are read from the thread-private columns; tb = border multipliers of the capped rows (group values).
-// ---------------------------------------------------------------------------------------------------------------
 template <int C>
 LDEV void l_stage_eliminate(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, double dw, const KV& r, LaneMain& m, double* d0) {
   constexpr int NW = LaneDims<C>::NW;
@@ -440,11 +362,12 @@ LDEV void l_stage_eliminate(const Grp& g, const KParams& P, const LaneConst& c, 
     m.rx[2 * b] = r.xs[2 * b] - ((g.j < 3) ? t : 0.0);
     m.rx[2 * b + 1] = r.xs[2 * b + 1];
   }
+  m.rx[4] = r.dl;
 }
 
 template <int C>
 LDEV void l_recover(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, double dw, const KV& r, const double* d0,
-                    const double* w, double ddl, KV& d) {
+                    const double* w, KV& d) {
   constexpr int NW = LaneDims<C>::NW;
   const double e0 = r.eta;
   double wsum_ = 0.0, du0 = d0[0], du1 = d0[1];
@@ -460,90 +383,90 @@ LDEV void l_recover(const Grp& g, const KParams& P, const LaneConst& c, const La
   LUNR for (int a = 0; a < 2; a++)
     d.nu[a] = r.us[a] - (H.hu[a] + dw) * du[a] - (P.bp * d.pi[2 * a] + P.bv * d.pi[2 * a + 1]) - H.hxu[a] * xpp[a];
   d.eta = r.lm[C - 1] - (H.hl[C - 1] + dw) * dll + c.Fl[0] * d.nu[0] + c.Fl[1] * d.nu[1];
+}
+
+template <int C>
+LDEV void l_kkt_solve(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, const LaneFact& f, double dw, const KV& r,
+                      double rq, KV& d, double& tq) {
+  constexpr int NW = LaneDims<C>::NW;
+  LaneMain m; double d0[2];
+  l_stage_eliminate<C>(g, P, c, H, dw, r, m, d0);
+  // ---- backward chain
+  double out[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int step = 0; step < 4; step++) {
+    double inc[5];
+    LUNR for (int i = 0; i < 5; i++) { const double t = g_down(g, out[i]); inc[i] = (step > 0 && g.j < 3) ? t : 0.0; }
+    double pn[5], q[5];
+    LUNR for (int i = 0; i < 5; i++) pn[i] = m.rx[i] + inc[i];
+    LUNR for (int i = 0; i < 5; i++) {
+      double s = -pn[i];
+      LUNR for (int k = 0; k < 4; k++) s += f.Pn[sy(i, k)] * m.cv[k];
+      q[i] = s;
+    }
+    const double g0 = P.bp * q[0] + P.bv * q[1], g1 = P.bp * q[2] + P.bv * q[3];
+    double k0[3] = {0.0, 0.0, 0.0}, kr[3] = {0.0, 0.0, 0.0}, ykr[3] = {0.0, 0.0, 0.0};
+    LUNR for (int a = 0; a < NW; a++) { kr[a] = m.rw[a] - (c.D[a] * g0 + c.D[NW + a] * g1); k0[a] = kr[a]; }
+    l_chol_fwd<NW>(f.Lc, k0);
+    LUNR for (int a = 0; a < NW; a++) ykr[a] = k0[a];
+    l_chol_bwd<NW>(f.Lc, k0);
+    double tt = 0.0;
+    if (H.capped) {
+      double s = H.gv[0] * m.cv[0] + H.gv[1] * m.cv[2] - rq;
+      LUNR for (int a = 0; a < NW; a++) s += f.Ym[a] * ykr[a];
+      tt = s * f.Tc * f.Tc;
+    }
+    double aq[4];
+    l_ATx(P, q, aq);
+    LUNR for (int i = 0; i < 5; i++) {
+      double s = (i < 4) ? -aq[i] : -q[4];
+      LUNR for (int a = 0; a < NW; a++) s -= f.K[5 * a + i] * kr[a];
+      if (H.capped) s -= f.Nt[i] * tt;
+      out[i] = s;
+    }
+    LUNR for (int i = 0; i < 5; i++) m.pv[i] = pn[i];
+    LUNR for (int a = 0; a < 3; a++) m.kv[a] = k0[a];
+    m.tt = tt;
+  }
+  // ---- delta_0 (x_0 is fixed): P_0(4,4) ddelta = p_0(4)
+  const double ddl = g_idx(g, out[4], 0) * l_rcp(f.p0dd);
+  // ---- forward chain
+  double xn[4] = {0.0, 0.0, 0.0, 0.0}, w[3] = {0.0, 0.0, 0.0};
+  tq = 0.0;
+#pragma unroll 1
+  for (int step = 0; step < 4; step++) {
+    double xp[5];
+    LUNR for (int i = 0; i < 4; i++) { const double t = g_up(g, xn[i]); xp[i] = (step > 0 && g.j > 0) ? t : 0.0; }
+    xp[4] = ddl;
+    double tl = 0.0;
+    if (H.capped) {
+      double s = 0.0;
+      LUNR for (int i = 0; i < 5; i++) s += f.Nt[i] * xp[i];
+      tl = s * f.Tc * f.Tc + m.tt;
+    }
+    LUNR for (int a = 0; a < 3; a++) w[a] = 0.0;
+    LUNR for (int a = 0; a < NW; a++) {
+      double s = m.kv[a];
+      LUNR for (int k = 0; k < 5; k++) s -= f.K[5 * a + k] * xp[k];
+      if (H.capped) s -= f.Zm[a] * tl;
+      w[a] = s;
+    }
+    double e0 = 0.0, e1 = 0.0;
+    LUNR for (int a = 0; a < NW; a++) { e0 += c.D[a] * w[a]; e1 += c.D[NW + a] * w[a]; }
+    double ax[4];
+    l_Ax(P, xp, ax);
+    ax[0] += P.bp * e0; ax[1] += P.bv * e0; ax[2] += P.bp * e1; ax[3] += P.bv * e1;
+    LUNR for (int i = 0; i < 4; i++) { ax[i] += m.cv[i]; xn[i] = ax[i]; }
+    LUNR for (int i = 0; i < 4; i++) {
+      double s = -m.pv[i] + f.Pn[sy(i, 4)] * ddl;
+      LUNR for (int k = 0; k < 4; k++) s += f.Pn[sy(i, k)] * ax[k];
+      d.xs[i] = ax[i]; d.pi[i] = s;
+    }
+    if (H.capped) { d.pi[0] += H.gv[0] * tl; d.pi[2] += H.gv[1] * tl; }
+    tq = tl;
+  }
   d.dl = ddl;
-}
-
-// plain solve (QP stage): the slack variable is decoupled
-template <int C>
-LDEV void l_kkt_solve_plain(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, const LaneFact& f, double dw, const KV& r, KV& d) {
-  LaneMain m; double d0[2], w[3];
-  l_stage_eliminate<C>(g, P, c, H, dw, r, m, d0);
-  l_backward<C, true, 0>(g, P, c, f, m, nullptr, nullptr, nullptr);
-  l_forward<C, true, 0, 1>(g, P, c, f, m, nullptr, nullptr, nullptr, d.xs, w, d.pi);
-  l_recover<C>(g, P, c, H, dw, r, d0, w, r.dl / (H.hd + dw), d);
-}
-
-// border factorisation (NLP stage): solves the 4 distance-row columns (column k: gv at stage k), derives the slack
-// variable's column by superposition (its x-part is sum_k sc_k * column k), builds and factorises the Schur complement.
-template <int C>
-LDEV bool l_border_factor(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, const LaneFact& f, double dw,
-                          const Priv& pr, LaneBorder& bf) {
-  typedef LaneDims<C> d;
-  constexpr int NW = d::NW;
-  double brhs[4][4], bpv[4][4], bkv[4][3], posb[4][2], posd[2];
-  LUNR for (int k = 0; k < 4; k++) {
-    brhs[k][0] = (g.j == k) ? H.gv[0] : 0.0; brhs[k][1] = 0.0; brhs[k][2] = (g.j == k) ? H.gv[1] : 0.0; brhs[k][3] = 0.0;
-  }
-  LaneMain dummy;
-  l_backward<C, false, 4>(g, P, c, f, dummy, brhs, bpv, bkv);
-  l_forward<C, false, 4, 0>(g, P, c, f, dummy, bpv, bkv, posb, nullptr, nullptr, nullptr);
-  LUNR for (int k = 0; k < 4; k++) {
-    LUNR for (int i = 0; i < 4; i++) pr(d::F_PVB + 4 * k + i) = bpv[k][i];
-    LUNR for (int a = 0; a < NW; a++) pr(d::F_KVB + 3 * k + a) = bkv[k][a];
-  }
-  // group values: sc_k, capped_k of every stage
-  double sck[4];
-  const unsigned capbits = g_bits(g, H.capped != 0);
-  LUNR for (int k = 0; k < 4; k++) { sck[k] = g_idx(g, H.sc, k); bf.cap[k] = (int)((capbits >> k) & 1u); }
-  // slack-variable column by superposition; positions at this lane's stage
-  posd[0] = 0.0; posd[1] = 0.0;
-  LUNR for (int k = 0; k < 4; k++) { posd[0] += sck[k] * posb[k][0]; posd[1] += sck[k] * posb[k][1]; }
-  // row j of T, cb_j, and this lane's share of a
-  double Trow[4];
-  LUNR for (int l = 0; l < 4; l++) {
-    double v;
-    if (H.capped && bf.cap[l]) { v = H.gv[0] * posb[l][0] + H.gv[1] * posb[l][1]; if (l == g.j) v += H.srinv; }
-    else v = (l == g.j) ? 1.0 : 0.0;
-    Trow[l] = v;
-  }
-  const double cbj = H.capped ? 1.0 - (H.gv[0] * posd[0] + H.gv[1] * posd[1]) : 0.0;
-  const double a = H.hd + dw - g_sum(g, H.bd[0] * posd[0] + H.bd[1] * posd[1]);
-  double T[10];
-  LUNR for (int k = 0; k < 4; k++) LUNR for (int l = 0; l <= k; l++) T[(k * (k + 1)) / 2 + l] = g_idx(g, Trow[l], k);
-  LUNR for (int k = 0; k < 4; k++) bf.cb[k] = g_idx(g, cbj, k);
-  bool ok = l_chol4(T, bf.L);
-  l_chol4_solve(bf.L, bf.cb, bf.Tic);
-  bf.den = a + bf.cb[0] * bf.Tic[0] + bf.cb[1] * bf.Tic[1] + bf.cb[2] * bf.Tic[2] + bf.cb[3] * bf.Tic[3];
-  ok = ok && (bf.den > 0.0);
-  return g_all(g, ok);
-}
-
-// bordered solve (NLP stage).  posb / posd: positions of the border columns at this lane's stage (from l_border_factor).
-template <int C>
-LDEV void l_kkt_solve_border(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, const LaneFact& f, double dw,
-                             const Priv& pr, const LaneBorder& bf, const KV& r, KV& d, double* tb) {
-  typedef LaneDims<C> dm;
-  constexpr int NW = dm::NW;
-  LaneMain m; double d0[2], w[3];
-  l_stage_eliminate<C>(g, P, c, H, dw, r, m, d0);
-  l_backward<C, true, 0>(g, P, c, f, m, nullptr, nullptr, nullptr);
-  double pos0[1][2];
-  l_forward<C, true, 0, 0>(g, P, c, f, m, nullptr, nullptr, pos0, nullptr, nullptr, nullptr);
-  const double rtj = H.capped ? H.gv[0] * pos0[0][0] + H.gv[1] * pos0[0][1] : 0.0;
-  const double rd = r.dl - g_sum(g, H.bd[0] * pos0[0][0] + H.bd[1] * pos0[0][1]);
-  double rt[4], kk[4];
-  LUNR for (int k = 0; k < 4; k++) rt[k] = g_idx(g, rtj, k);
-  l_chol4_solve(bf.L, rt, kk);
-  const double ddl = (rd - (bf.cb[0] * kk[0] + bf.cb[1] * kk[1] + bf.cb[2] * kk[2] + bf.cb[3] * kk[3])) * l_rcp(bf.den);
-  double t[4], sck[4];
-  LUNR for (int k = 0; k < 4; k++) { t[k] = bf.Tic[k] * ddl + kk[k]; sck[k] = g_idx(g, H.sc, k); tb[k] = t[k]; }
-  // combine the backward-pass vectors: p <- p0 - ddl p_delta - sum_{k capped} t_k p_k, p_delta = sum_k sc_k p_k
-  double coef[4];
-  LUNR for (int k = 0; k < 4; k++) coef[k] = ddl * sck[k] + (bf.cap[k] ? t[k] : 0.0);
-  LUNR for (int i = 0; i < 4; i++) { double s = m.pv[i]; LUNR for (int k = 0; k < 4; k++) s -= coef[k] * pr(dm::F_PVB + 4 * k + i); m.pv[i] = s; }
-  LUNR for (int a = 0; a < NW; a++) { double s = m.kv[a]; LUNR for (int k = 0; k < 4; k++) s -= coef[k] * pr(dm::F_KVB + 3 * k + a); m.kv[a] = s; }
-  l_forward<C, true, 0, 1>(g, P, c, f, m, nullptr, nullptr, nullptr, d.xs, w, d.pi);
-  l_recover<C>(g, P, c, H, dw, r, d0, w, ddl, d);
+  l_recover<C>(g, P, c, H, dw, r, d0, w, d);
 }
 
 // ===============================================================================================================
@@ -577,7 +500,7 @@ LDEV void l_scatter(const Grp& g, const Priv& pr, int fld, const KV& v, const do
   if (NL) { LUNR for (int a = 0; a < 2; a++) pr(fld + d::SV + a) = v.xs[2 * a + 1]; }
 }
 // acc.(xs,us,lm) = J'w for the per-slot weights w in field fld (weight of +grad e; 0 in the invalid slots);
-// wd = sum over the group of the distance-row weights
+// wd = weight of this lane's distance row = its share of the slack variable's entry
 template <int C, bool NL>
 LDEV void l_gather(const Grp& g, const Priv& pr, int fld, const double* gv, KV& acc, double& wd) {
   typedef LaneDims<C> d;
@@ -592,7 +515,7 @@ LDEV void l_gather(const Grp& g, const Priv& pr, int fld, const double* gv, KV& 
   if (NL) {
     const double wdj = pr(fld + d::SD);
     LUNR for (int a = 0; a < 2; a++) { acc.xs[2 * a + 1] += pr(fld + d::SV + a); acc.xs[2 * a] += gv[a] * wdj; }
-    wd = g_sum(g, wdj);
+    wd = wdj;
   }
 }
 // stage Hessian blocks from the slot weights Sigma in field fld; NL: distance-row data already in H (gv, sc, zd)
@@ -611,9 +534,9 @@ LDEV void l_assemble(const Grp& g, const KParams& P, const LaneConst& c, const P
   if (NL) {
     LUNR for (int a = 0; a < 2; a++) { H.hx[2 * a + 1] += pr(fld + d::SV + a); H.hx[2 * a] += H.sc * H.gv[a] * H.gv[a] - 2.0 * zd; H.bd[a] = H.sc * H.gv[a]; }
     H.hxy = H.sc * H.gv[0] * H.gv[1];
-    H.hd = P.slw + g_sum(g, H.sc);
+    H.hd = H.sc + ((g.j == 3) ? P.slw : 0.0);
   } else {
-    H.hxy = 0.0; H.bd[0] = 0.0; H.bd[1] = 0.0; H.hd = P.slw;
+    H.hxy = 0.0; H.bd[0] = 0.0; H.bd[1] = 0.0; H.hd = (g.j == 3) ? P.slw : 0.0;
   }
 }
 
@@ -647,14 +570,14 @@ struct LaneSolver {
   // residual parts shared by qp_iter and qp_final_kkt: -(Px + c + A'y + G'z) and b - Ax; z-weights must be in Q_DE
   LMEM void qp_dual_eq(const KParams& P, const double* xp, const double* pin, KV& rx, double& acc_rx, double& acc_ry) {
     KV gfy, jz; double wd;
-    l_grad_Aty<C>(P, c, pr, x, x, pin, true, gfy);
+    l_grad_Aty<C>(P, c, pr, x, x, pin, true, g.j, gfy);
     l_gather<C, false>(g, pr, d::Q_DE, H.gv, jz, wd);
     acc_rx = 0.0; acc_ry = 0.0;
     LUNR for (int i = 0; i < 4; i++) { rx.xs[i] = -(gfy.xs[i] - jz.xs[i]); acc_rx += rx.xs[i] * rx.xs[i]; }
     LUNR for (int a = 0; a < 2; a++) { rx.us[a] = -(gfy.us[a] - jz.us[a]); acc_rx += rx.us[a] * rx.us[a]; }
     LUNR for (int i = 0; i < 4; i++) { rx.lm[i] = (i < C) ? -(gfy.lm[i] - jz.lm[i]) : 0.0; acc_rx += rx.lm[i] * rx.lm[i]; }
     rx.dl = -gfy.dl;
-    if (g.j == 0) acc_rx += rx.dl * rx.dl;
+    acc_rx += rx.dl * rx.dl;
     double rpi[4], rnu[2], reta;
     l_eq_residual<C>(P, c, x, xp, false, rpi, rnu, reta);
     LUNR for (int i = 0; i < 4; i++) { rx.pi[i] = -rpi[i]; acc_ry += rpi[i] * rpi[i]; }
@@ -687,11 +610,11 @@ struct LaneSolver {
     }
     info.qp_flag = 3; info.qp_iters = 0; qp_it = 0; sigma = 100.0;  // GlobalOptions.h:26
     {
-      const bool okr = l_riccati<C, true>(g, P, c, H, 0.0, f);
+      const bool okr = l_factor<C, true>(g, P, c, H, 0.0, f);
       g_keep(g, okr);
       if (!okr) { info.qp_flag = 1; return true; }
     }
-    l_kkt_solve_plain<C>(g, P, c, H, f, 0.0, r, dd);
+    { double tq; l_kkt_solve<C>(g, P, c, H, f, 0.0, r, 0.0, dd, tq); }
     x = dd;
     LUNR for (int i = C; i < 4; i++) x.lm[i] = 0.0;
     // slacks and multipliers shifted positive (Auxilary.c:724-746)
@@ -760,28 +683,16 @@ struct LaneSolver {
       mu = sz / d::MQP;
     }
     {
-      // sigma == 0 -- a pure corrector step with the PREVIOUS Hessian blocks and factor (Prime.c:176-180) -- is rare; a group in
-      // that state parks them in the border / filter / gradient columns (unused in this stage) while the warp refactorises
-      const bool keep = !predictor;
-      const bool any_keep = w_any(g, keep);
-      if (any_keep && keep) {
-        LUNR for (int t = 0; t < 10; t++) pr(d::F_PVB + t) = f.Pn[t];
-        LUNR for (int t = 0; t < 6; t++) pr(d::F_PVB + 10 + t) = f.Lc[t];
-        LUNR for (int t = 0; t < 12; t++) pr(d::F_KVB + t) = f.K[t];
-        LUNR for (int t = 0; t < 4; t++) { pr(d::F_FILT + t) = H.hx[t]; pr(d::F_GFY + t) = H.hl[t]; }
-        LUNR for (int t = 0; t < 2; t++) { pr(d::F_GFY + 4 + t) = H.hu[t]; pr(d::F_GFY + 6 + t) = H.hxu[t]; }
+      bool okr = true;
+      const unsigned sv = g_enter(g, predictor);   // (sigma == 0 -- a pure corrector step with the previous factor, Prime.c:176-180 -- is rare)
+      if (predictor) {
+        l_assemble<C, false>(g, P, c, pr, d::Q_E, 0.0, 0.0, H);
+        info.n_fact++;
+        okr = l_factor<C, true>(g, P, c, H, 0.0, f);
+      } else {
+        sigma = 0.0;  // E, G hold zeros
       }
-      l_assemble<C, false>(g, P, c, pr, d::Q_E, 0.0, 0.0, H);
-      const bool okr = l_riccati<C, true>(g, P, c, H, 0.0, f) || keep;
-      if (predictor) info.n_fact++;
-      if (any_keep && keep) {
-        LUNR for (int t = 0; t < 10; t++) f.Pn[t] = pr(d::F_PVB + t);
-        LUNR for (int t = 0; t < 6; t++) f.Lc[t] = pr(d::F_PVB + 10 + t);
-        LUNR for (int t = 0; t < 12; t++) f.K[t] = pr(d::F_KVB + t);
-        LUNR for (int t = 0; t < 4; t++) { H.hx[t] = pr(d::F_FILT + t); H.hl[t] = pr(d::F_GFY + t); }
-        LUNR for (int t = 0; t < 2; t++) { H.hu[t] = pr(d::F_GFY + 4 + t); H.hxu[t] = pr(d::F_GFY + 6 + t); }
-      }
-      if (!predictor) sigma = 0.0;  // E, G hold zeros
+      g_leave(g, sv);
       g_keep(g, okr);
       if (!okr) { info.qp_flag = 1; return true; }
     }
@@ -809,7 +720,7 @@ struct LaneSolver {
       LUNR for (int i = 0; i < 4; i++) { r.xs[i] += rx.xs[i]; r.lm[i] += rx.lm[i]; r.pi[i] = rx.pi[i]; }
       LUNR for (int a = 0; a < 2; a++) { r.us[a] += rx.us[a]; r.nu[a] = rx.nu[a]; }
       r.dl = rx.dl; r.eta = rx.eta;
-      l_kkt_solve_plain<C>(g, P, c, H, f, 0.0, r, dd);
+      { double tq; l_kkt_solve<C>(g, P, c, H, f, 0.0, r, 0.0, dd, tq); }
       double dxp[4]; prev_state(dd, true, dxp);
       l_scatter<C, false>(g, pr, d::Q_DE, dd, dxp);
       // ---- pass B (affine: max step lengths, findsteplength Auxilary.c:271-294, and rho, Auxilary.c:600-609)
@@ -1036,9 +947,9 @@ struct LaneSolver {
       zd = pr(d::N_ZLO + d::SD);
       // ---- KKT error
       KV jz; double wd;
-      l_grad_Aty<C>(P, c, pr, x, x, pin, true, gfy);
+      l_grad_Aty<C>(P, c, pr, x, x, pin, true, g.j, gfy);
       l_gather<C, true>(g, pr, d::N_G, H.gv, jz, wd);
-      double rdm = fabs(gfy.dl - wd);
+      double rdm = fabs(P.slw * x.dl - g_sum(g, wd));   // the slack variable's row: the sum of the lanes' shares
       LUNR for (int i = 0; i < 4; i++) rdm = fmax(rdm, fabs(gfy.xs[i] - jz.xs[i]));
       LUNR for (int a = 0; a < 2; a++) rdm = fmax(rdm, fabs(gfy.us[a] - jz.us[a]));
       LUNR for (int i = 0; i < C; i++) rdm = fmax(rdm, fabs(gfy.lm[i] - jz.lm[i]));
@@ -1051,8 +962,6 @@ struct LaneSolver {
       const double e_c = szmax;                                  // complementarity error max_i s_i z_i (s, z > 0)
       const double zmax = g_max(g, l_from_hiword(zhw));          // to 2^-20 relative: only compared with z_div
       th = g_sum(g, res);
-      LUNR for (int i = 0; i < 4; i++) { pr(d::F_GFY + i) = gfy.xs[i]; pr(d::F_GFY + 6 + i) = gfy.lm[i]; pr(d::F_REP + i) = re_pi[i]; }
-      pr(d::F_GFY + 4) = gfy.us[0]; pr(d::F_GFY + 5) = gfy.us[1]; pr(d::F_GFY + 10) = gfy.dl;
       const bool nan_seen = g_any(g, !(rdm == rdm) || !(rem == rem) || !(e_c == e_c) || !(zmax == zmax));
       const double E0 = nan_seen ? 1e300 : fmax(e_d, fmax(e_p, e_c));
       info.kkt = E0; info.nlp_iters = it;
@@ -1067,7 +976,7 @@ struct LaneSolver {
         tx = g_max(g, tx); tu = g_max(g, tu); tl = g_max(g, tl); gx = g_max(g, gx); jx = g_max(g, jx); py = g_max(g, py); ny = g_max(g, ny);
         const double ey = g_max(g, fabs(x.eta)), xm = g_max(g, fmax(fabs(x.xs[0]), fabs(x.xs[2])));
         LANE_DBG("   ed parts: x %.2e u %.2e lam %.2e dl %.2e | |gfy.x| %.2e |jz.x| %.2e |pi| %.2e |nu| %.2e |eta| %.2e |pos| %.2e szmin %.2e szmax %.2e\n",
-                 tx, tu, tl, fabs(gfy.dl - wd), gx, jx, py, ny, ey, xm, szmin, szmax);
+                 tx, tu, tl, fabs(P.slw * x.dl - g_sum(g, wd)), gx, jx, py, ny, ey, xm, szmin, szmax);
       }
 #endif
       // converged: KKT error <= tol, or <= acc_tol once the barrier parameter sits at its floor (there the dual residual is at
@@ -1091,8 +1000,12 @@ struct LaneSolver {
     }
     // ---- Hessian blocks and right-hand side (distance row: capped split)
     KV r;
+    bool qd_mine, any_qd;   // some row of this group / of some group of the warp is stiff enough for the Newton residual to be worth
+                            // a check (see the refinement loop; the groups of a warp go through the check together)
     {
       const double sg = pr(d::N_C + d::SD);
+      qd_mine = g_any(g, sg > LANE_QD_CHECK);
+      any_qd = w_any(g, qd_mine);
       const bool cap = sg > P.sigma_cap;
       H.sc = fmin(sg, P.sigma_cap); H.capped = cap ? 1 : 0; H.srinv = cap ? l_rcp(sg - H.sc) : 0.0;
       l_assemble<C, true>(g, P, c, pr, d::N_C, P.rho_lambda, zd, H);
@@ -1104,17 +1017,15 @@ struct LaneSolver {
     }
     // ---- factorisation with inertia correction (Ipopt algorithm IC)
     double dw = 0.0;
-    LaneBorder bf;
     {
       const double dw_last = PERS_DWLAST;
       bool ok = false;
       bool need = true;  // this group wants (another) factorisation; one that does not reproduces its factors (same H, same dw)
       for (;;) {
         if (need) info.n_fact++;
-        const bool okf = l_riccati<C, false>(g, P, c, H, dw, f);
-        const bool okb = l_border_factor<C>(g, P, c, H, f, dw, pr, bf);
+        const bool okf = l_factor<C, false>(g, P, c, H, dw, f);
         if (need) {
-          ok = okf && okb;
+          ok = okf;
           need = !ok;
           if (need) {
             if (dw == 0.0) dw = (dw_last == 0.0) ? P.dw_first : fmax(P.dw_min, P.kw_minus * dw_last);
@@ -1128,95 +1039,77 @@ struct LaneSolver {
       if (!ok) { info.status = 3; return true; }
       if (dw > 0.0) { PERS_DWLAST = dw; first_ic = false; }
     }
-    // ---- solve, then iterative refinement on the unreduced Newton system (one instance of the solve for both)
-    KV dd;
-    bool refining = true;  // this group takes the correction of the current solve
-    for (int rf = 0;; rf++) {
-      KV d2; double tb2[4];
-      l_kkt_solve_border<C>(g, P, c, H, f, dw, pr, bf, r, d2, tb2);
-      double d2p[4]; prev_state(d2, true, d2p);
-      const double tbj = l_sel4(tb2, g.j);
-      if (rf == 0) {
-        dd = d2;
-        nlp_scatter_de(d::N_C, d2, d2p);
-      } else {
-        nlp_scatter_de(d::N_G, d2, d2p);
-        if (refining) {
+    // ---- solve, then iterative refinement on the UNREDUCED Newton system (one instance of the solve for both).  A row whose
+    //      Sigma is ~1e15 and over which the stage's own controls have little authority (a diagonal-pair stance has one control
+    //      direction) hands its stiffness on to the previous stage, where the recursion then loses digits: measured residual 5e-9
+    //      of the right-hand side at Sigma ~ 1e11, 1e-6 .. 1 at 1e13 .. 1e15; below that the recursion is accurate to round-off,
+    //      so the residual is evaluated only when some row of the group is above LANE_QD_CHECK.
+    KV dd; double tq = 0.0;
+    {
+      double rq = 0.0;
+      bool refining = qd_mine;  // this group checks its residual and takes the correction of the next solve
+      for (int rf = 0;; rf++) {
+        KV d2; double t2;
+        l_kkt_solve<C>(g, P, c, H, f, dw, r, rq, d2, t2);
+        if (rf == 0) { dd = d2; tq = t2; }
+        else if (refining) {
           LUNR for (int i = 0; i < 4; i++) { dd.xs[i] += d2.xs[i]; dd.lm[i] += d2.lm[i]; dd.pi[i] += d2.pi[i]; }
           LUNR for (int a = 0; a < 2; a++) { dd.us[a] += d2.us[a]; dd.nu[a] += d2.nu[a]; }
-          dd.dl += d2.dl; dd.eta += d2.eta;
+          dd.dl += d2.dl; dd.eta += d2.eta; tq += t2;
         }
-      }
-      // pass B: slot steps de -> C, dz_lo -> D, dz_hi -> E (rf = 0: from scratch; later: corrections), then the residual
-      // weights of the complementarity rows: J'(z + dz) weights -> G, rc / s weights -> EV
-      const bool first = rf == 0, upd = first || refining;
-      LSLOTS for (int s = 0; s < nsn; s++) {
-        const bool vhi = s != d::SD;
-        const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
-        const double rlo = pr(d::N_A + s), rhi = pr(d::N_B + s);
-        double de, dzl, dzh;
-        if (first) {
-          de = pr(d::N_C + s);
-          dzl = (mu - slo * zlo) * rlo - zlo * rlo * de;
-          dzh = vhi ? (mu - shi * zhi) * rhi + zhi * rhi * de : 0.0;
-          if (s == d::SD && H.capped) dzl = (mu - slo * zlo) * rlo - H.sc * de - tbj;
-        } else {
-          de = pr(d::N_C + s); dzl = pr(d::N_D + s); dzh = pr(d::N_E + s);
-          const double dde = pr(d::N_G + s);
-          const double rcl0 = (mu - slo * zlo) - (slo * dzl + zlo * de);
-          const double rch0 = vhi ? (mu - shi * zhi) - (shi * dzh - zhi * de) : 0.0;
-          double cl = rcl0 * rlo - zlo * rlo * dde;
-          const double ch = vhi ? rch0 * rhi + zhi * rhi * dde : 0.0;
-          if (s == d::SD && H.capped) cl = rcl0 * rlo - H.sc * dde - tbj;
-          de += dde; dzl += cl; dzh += ch;
-          if (upd) pr(d::N_C + s) = de;
+        double ddp[4]; prev_state(dd, true, ddp);
+        nlp_scatter_de(d::N_C, dd, ddp);
+        // pass B: multiplier steps dz_lo -> D, dz_hi -> E from the slot steps de (C); J'(z + dz) weights -> G for the residual
+        LSLOTS for (int s = 0; s < nsn; s++) {
+          const bool vhi = s != d::SD;
+          const double slo = pr(d::N_SLO + s), shi = pr(d::N_SHI + s), zlo = pr(d::N_ZLO + s), zhi = pr(d::N_ZHI + s);
+          const double rlo = pr(d::N_A + s), rhi = pr(d::N_B + s), de = pr(d::N_C + s);
+          double dzl = (mu - slo * zlo) * rlo - zlo * rlo * de;
+          const double dzh = vhi ? (mu - shi * zhi) * rhi + zhi * rhi * de : 0.0;
+          if (s == d::SD && H.capped) dzl = (mu - slo * zlo) * rlo - H.sc * de - tq;
+          pr(d::N_D + s) = dzl; pr(d::N_E + s) = dzh;
+          if (any_qd) pr(d::N_G + s) = (zlo + dzl) - (zhi + dzh);
         }
-        if (upd) { pr(d::N_D + s) = dzl; pr(d::N_E + s) = dzh; }
-        const double rcl = (mu - slo * zlo) - (slo * dzl + zlo * de);
-        const double rch = vhi ? (mu - shi * zhi) - (shi * dzh - zhi * de) : 0.0;
-        pr(d::N_G + s) = (zlo + dzl) - (zhi + dzh);
-        pr(d::N_EV + s) = rcl * rlo - rch * rhi;
-      }
-      if (rf >= P.max_refine) break;
-      // rho1 = -(grad f + A'(y+dy) + Htilde dx - J'(z+dz)),  rho2 = -(A (x+dx) - b)
-      KV gd, jz2; double wd2, dpin[4], dxp[4];
-      next_pi(dd, dpin); prev_state(dd, true, dxp);
-      l_grad_Aty<C>(P, c, pr, dd, dd, dpin, false, gd);
-      KV gf; double rp_[4];   // parked by pass A
-      LUNR for (int i = 0; i < 4; i++) { gf.xs[i] = pr(d::F_GFY + i); gf.lm[i] = pr(d::F_GFY + 6 + i); rp_[i] = pr(d::F_REP + i); }
-      gf.us[0] = pr(d::F_GFY + 4); gf.us[1] = pr(d::F_GFY + 5); gf.dl = pr(d::F_GFY + 10);
-      l_gather<C, true>(g, pr, d::N_G, H.gv, jz2, wd2);
-      double nres = 0.0;
-      LUNR for (int i = 0; i < 4; i++) {
-        const double ht = c.qw + dw - ((i & 1) ? 0.0 : 2.0 * zd);
-        r.xs[i] = -(gf.xs[i] + gd.xs[i] + ht * dd.xs[i] - jz2.xs[i]);
-        nres = fmax(nres, fabs(r.xs[i]));
-      }
-      LUNR for (int a = 0; a < 2; a++) { r.us[a] = -(gf.us[a] + gd.us[a] + (P.Rw + dw) * dd.us[a] - jz2.us[a]); nres = fmax(nres, fabs(r.us[a])); }
-      LUNR for (int i = 0; i < 4; i++) {
-        r.lm[i] = (i < C) ? -(gf.lm[i] + gd.lm[i] + (dw + P.rho_lambda) * dd.lm[i] - jz2.lm[i]) : 0.0;
-        nres = fmax(nres, fabs(r.lm[i]));
-      }
-      r.dl = -(gf.dl + (P.slw + dw) * dd.dl - wd2);
-      nres = fmax(nres, fabs(r.dl));
-      {
-        double hp[4], hn[2], he;
-        l_eq_residual<C>(P, c, dd, dxp, true, hp, hn, he);
-        LUNR for (int i = 0; i < 4; i++) { r.pi[i] = -(rp_[i] + hp[i]); nres = fmax(nres, fabs(r.pi[i])); }
-        LUNR for (int a = 0; a < 2; a++) { r.nu[a] = -(re_nu[a] + hn[a]); nres = fmax(nres, fabs(r.nu[a])); }
-        r.eta = -(re_eta + he); nres = fmax(nres, fabs(r.eta));
-      }
-      nres = g_max(g, nres);
-      const double nrhs = fmax(e_d, e_p);
-      LANE_DBG("   refine %d nres %.2e nrhs %.2e\n", rf, nres, nrhs);
-      refining = refining && nres > fmax(P.refine_rel * nrhs, P.refine_abs);
-      if (!w_any(g, refining)) break;
-      {
-        KV jb; double wdb;
-        l_gather<C, true>(g, pr, d::N_EV, H.gv, jb, wdb);
-        LUNR for (int i = 0; i < 4; i++) { r.xs[i] += jb.xs[i]; r.lm[i] += jb.lm[i]; }
-        LUNR for (int a = 0; a < 2; a++) r.us[a] += jb.us[a];
-        r.dl += wdb;
+        if (rf >= P.max_refine || !any_qd) break;
+        // rho1 = -(grad f + A'(y+dy) + Htilde dx - J'(z+dz)),  rho2 = -(A (x+dx) - b),  rho_q = t / (Sigma - cap) - g'dx
+        // (grad f + A'y and the equality residual of the iterate are recomputed here, rarely, instead of living across the solve)
+        const double rqn = H.capped ? H.srinv * tq - pr(d::N_C + d::SD) : 0.0;
+        KV gd, jz2, gf; double wd2, dpin[4], rp_[4], rn_[2], re_;
+        {
+          double xp0[4], pin0[4];
+          prev_state(x, false, xp0); next_pi(x, pin0);
+          l_grad_Aty<C>(P, c, pr, x, x, pin0, true, g.j, gf);
+          l_eq_residual<C>(P, c, x, xp0, false, rp_, rn_, re_);
+        }
+        next_pi(dd, dpin);
+        l_grad_Aty<C>(P, c, pr, dd, dd, dpin, false, g.j, gd);
+        l_gather<C, true>(g, pr, d::N_G, H.gv, jz2, wd2);
+        double nres = fabs(rqn);
+        LUNR for (int i = 0; i < 4; i++) {
+          const double ht = c.qw + dw - ((i & 1) ? 0.0 : 2.0 * zd);
+          r.xs[i] = -(gf.xs[i] + gd.xs[i] + ht * dd.xs[i] - jz2.xs[i]);
+          nres = fmax(nres, fabs(r.xs[i]));
+        }
+        LUNR for (int a = 0; a < 2; a++) { r.us[a] = -(gf.us[a] + gd.us[a] + (P.Rw + dw) * dd.us[a] - jz2.us[a]); nres = fmax(nres, fabs(r.us[a])); }
+        LUNR for (int i = 0; i < 4; i++) {
+          r.lm[i] = (i < C) ? -(gf.lm[i] + gd.lm[i] + (dw + P.rho_lambda) * dd.lm[i] - jz2.lm[i]) : 0.0;
+          nres = fmax(nres, fabs(r.lm[i]));
+        }
+        r.dl = -(gf.dl + ((g.j == 3) ? (P.slw + dw) * dd.dl : 0.0) - wd2);   // this lane's share of the slack variable's row
+        nres = fmax(nres, fabs(g_sum(g, r.dl)));
+        {
+          double hp[4], hn[2], he;
+          l_eq_residual<C>(P, c, dd, ddp, true, hp, hn, he);
+          LUNR for (int i = 0; i < 4; i++) { r.pi[i] = -(rp_[i] + hp[i]); nres = fmax(nres, fabs(r.pi[i])); }
+          LUNR for (int a = 0; a < 2; a++) { r.nu[a] = -(rn_[a] + hn[a]); nres = fmax(nres, fabs(r.nu[a])); }
+          r.eta = -(re_ + he); nres = fmax(nres, fabs(r.eta));
+        }
+        nres = g_max(g, nres);
+        const double nrhs = fmax(e_d, e_p);
+        LANE_DBG("   refine %d nres %.2e nrhs %.2e\n", rf, nres, nrhs);
+        refining = refining && nres > fmax(P.refine_rel * nrhs, P.refine_abs);
+        if (!w_any(g, refining)) break;
+        rq = rqn;
       }
     }
     const double quad = dd.xs[0] * dd.xs[0] + dd.xs[2] * dd.xs[2];
