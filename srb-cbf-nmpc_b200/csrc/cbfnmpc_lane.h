@@ -567,6 +567,44 @@ struct LaneSolver {
   // =============================================================================================================
   double sigma; int qp_it;
 
+  // ---------------------------------------------------------------------------------------------------------------
+  // Pivot foot.  The stage elimination removes ONE support weight through 1'lambda = 1 -- the one in the last place -- so the
+  // reduced Hessian carries h_last 11' (h = the lambda block of H).  A last weight that sits on its bound (h = z / s ~ 1e10 ..
+  // 1e16 late in a stage) buries the O(1) curvature of the other directions under that term: the Newton step lost its lambda
+  // rows, the dual residual stalled (1.6e-4 against iSWIFT's 5.8e-7 limit) and the QP stage ran into its iteration limit where
+  // iSWIFT converges -- the round-1 "known limit", one wide-fuzz instance in 1200.  The feet are therefore RELABELLED when the last
+  // one becomes much stiffer than the softest (one always is soft: the weights sum to 1): the two change places in everything
+  // this lane indexes by foot -- lambda, its slot columns, D and Fl -- and `perm` (position -> foot, 2 bits each) remembers the
+  // order for the outputs.  Rare (a few instances per thousand, once), lane-local, no shuffle; huge entries then sit on the
+  // diagonal of the reduced Hessian only, where the Cholesky factorisation takes them first.
+  // ---------------------------------------------------------------------------------------------------------------
+  int perm;
+  LMEM void repivot(bool nlp) {
+    constexpr int NW = d::NW;
+    int p = C - 1; double hm = H.hl[C - 1];
+    LUNR for (int a = 0; a < NW; a++) { if (H.hl[a] < hm) { hm = H.hl[a]; p = a; } }
+    if (p == C - 1 || !(H.hl[C - 1] > 1e3 * hm)) return;
+    double dp0 = 0.0, dp1 = 0.0;
+    LUNR for (int a = 0; a < NW; a++) {
+      if (a == p) {
+        dp0 = c.D[a]; dp1 = c.D[NW + a];
+        const double t = x.lm[a]; x.lm[a] = x.lm[C - 1]; x.lm[C - 1] = t;
+        const double h = H.hl[a]; H.hl[a] = H.hl[C - 1]; H.hl[C - 1] = h;
+      }
+    }
+    LUNR for (int a = 0; a < NW; a++) { c.D[a] = ((a == p) ? 0.0 : c.D[a]) - dp0; c.D[NW + a] = ((a == p) ? 0.0 : c.D[NW + a]) - dp1; }
+    c.Fl[0] += dp0; c.Fl[1] += dp1;
+    // slot columns that carry state from one iteration to the next: slacks and multipliers (QP); multipliers and their pending steps (NLP)
+    const int f0 = nlp ? d::N_ZLO : d::Q_SLO, f1 = nlp ? d::N_ZHI : d::Q_SHI, f2 = nlp ? d::N_D : d::Q_ZLO, f3 = nlp ? d::N_E : d::Q_ZHI;
+    const int sa = d::SL + p, sb = d::SL + C - 1;
+    { const double t = pr(f0 + sa); pr(f0 + sa) = pr(f0 + sb); pr(f0 + sb) = t; }
+    { const double t = pr(f1 + sa); pr(f1 + sa) = pr(f1 + sb); pr(f1 + sb) = t; }
+    { const double t = pr(f2 + sa); pr(f2 + sa) = pr(f2 + sb); pr(f2 + sb) = t; }
+    { const double t = pr(f3 + sa); pr(f3 + sa) = pr(f3 + sb); pr(f3 + sb) = t; }
+    const int fa = (perm >> (2 * p)) & 3, fb = (perm >> (2 * (C - 1))) & 3;
+    perm = (perm & ~((3 << (2 * p)) | (3 << (2 * (C - 1))))) | (fb << (2 * p)) | (fa << (2 * (C - 1)));
+  }
+
   // residual parts shared by qp_iter and qp_final_kkt: -(Px + c + A'y + G'z) and b - Ax; z-weights must be in Q_DE
   LMEM void qp_dual_eq(const KParams& P, const double* xp, const double* pin, KV& rx, double& acc_rx, double& acc_ry) {
     KV gfy, jz; double wd;
@@ -647,6 +685,7 @@ struct LaneSolver {
   // Slot passes: A (residuals, reciprocals, predictor weights), B (affine step statistics), C (corrector right-hand side),
   // D (final step and step lengths), E (update).  One instance of the KKT solve serves predictor and corrector.
   LMEM bool qp_iter(const KParams& P) {   // (the iteration limit is tested at the end: the caller never enters with qp_it >= qp_maxit)
+    if (sigma > 0.0) repivot(false);   // (a corrector-only step keeps the previous factor, and with it the order of the feet)
     double xp[4], pin[4];
     prev_state(x, false, xp); next_pi(x, pin);
     l_scatter<C, false>(g, pr, d::Q_EV, x, xp);
@@ -908,6 +947,7 @@ struct LaneSolver {
   // refinement solves (code footprint: DESIGN.md section 5).
   LMEM bool nlp_iter(const KParams& P) {
     const int it = nl_it;
+    if (it > 0) repivot(true);
     double xp[4], pin[4];
     prev_state(x, false, xp); next_pi(x, pin);
     // ---- pass A
@@ -1239,6 +1279,7 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
   const int j = g.j;
   const size_t B = (size_t)io.ld;  // array pitch
   S.info.status = 1; S.info.qp_iters = 0; S.info.qp_flag = 3; S.info.nlp_iters = 0; S.info.n_fact = 0; S.info.kkt = 0.0;
+  S.perm = 0xE4;   // position i holds foot i
   double abuf_j = 0.0;
   bool qp_done = true, badin = false;
   g.mask = w_ballot_full(valid);
@@ -1339,7 +1380,7 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
   if (io.X) { LUNR for (int i = 0; i < 4; i++) io.X[(size_t)(4 * j + i) * B + b] = S.x.xs[i]; }
   if (io.U) { LUNR for (int a = 0; a < 2; a++) io.U[(size_t)(2 * j + a) * B + b] = S.x.us[a]; }
   if (io.lam) {
-    LUNR for (int i = 0; i < C; i++) io.lam[(size_t)(C * j + i) * B + b] = S.x.lm[i];
+    LUNR for (int i = 0; i < C; i++) io.lam[(size_t)(C * j + ((S.perm >> (2 * i)) & 3)) * B + b] = S.x.lm[i];
     LUNR for (int i = 0; i < 4 - C; i++) io.lam[(size_t)(4 * C + (4 - C) * j + i) * B + b] = 0.0;
   }
   // Bezier fit  alpha = Y Minv'   (MPC_dist.cpp:784-855, effective semantics): lane r fits state row r
@@ -1369,7 +1410,7 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
         int rlo = -1, rhi = -1;
         if (s < d::SU) { rhi = 12 + 4 * j + s; rlo = 28 + 4 * j + s; }
         else if (s < d::SL) { rhi = 44 + 2 * j + (s - d::SU); rlo = 52 + 2 * j + (s - d::SU); }
-        else if (s < d::SL + C) { rlo = 60 + C * j + (s - d::SL); rhi = 60 + 4 * C + C * j + (s - d::SL); }
+        else if (s < d::SL + C) { const int ft = (S.perm >> (2 * (s - d::SL))) & 3; rlo = 60 + C * j + ft; rhi = 60 + 4 * C + C * j + ft; }
         else if (s >= SF) { rhi = 2 * (j - 1) + (s - SF); rlo = 6 + rhi; }
         else if (s < d::SD) { const int q = (s - d::SV) ? 4 + j : j; rhi = d::MQP + 4 + q; rlo = d::MQP + 12 + q; }
         else { rlo = d::MQP + j; }

@@ -74,8 +74,8 @@ def test_non_finite_and_absurd_inputs_come_back_flagged():
 
 def test_wide_fuzz_against_the_oracle():
     """The kernel source against the oracle far outside the cfg-3 distribution (helpers.wide_fuzz_instances): same statuses and the
-    same answers in QP -> NLP mode; in QP mode the same answers, and the same statuses but for the rare 4-foot instance whose
-    degenerate support-weight direction stalls the dual residual just above iSWIFT's limit (known limit)."""
+    same answers in QP -> NLP mode; in QP mode the same answers, statuses and iteration counts (the rare 4-foot instance whose last
+    support weight sits on its bound, which stalled in round 1, is what LaneSolver::repivot is for)."""
     insts = H.wide_fuzz_instances(300)
     out = emu.solve(insts, mode=1); ref = H.oracle_batch(insts, mode=1)
     c = H.compare(out, ref)
@@ -83,6 +83,6 @@ def test_wide_fuzz_against_the_oracle():
     assert (out["status"][0] == 0).sum() > 150 and (out["status"][0] == 2).sum() > 20      # both outcomes are exercised
     outq = emu.solve(insts, mode=0); refq = H.oracle_batch(insts, mode=0)
     both = (outq["status"][0] == 0) & (refq["status"] == 0)
-    assert (outq["status"][0] == refq["status"]).mean() >= 0.99 and both.sum() > 250
+    assert (outq["status"][0] == refq["status"]).all() and both.sum() > 250
     assert np.abs(outq["X"].T - refq["X"])[both].max() < 1e-8
     assert (outq["qp_iters"][0][both] == refq["qp_iters"][both]).all()

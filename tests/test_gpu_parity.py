@@ -168,9 +168,10 @@ def test_wide_fuzz_against_the_oracle(pkg):
     outq = s.solve_host(capi.soa_from_instances(insts), mode=capi.MODE_QP)
     refq = H.oracle_batch(insts, mode=0, nthreads=16)
     both = (outq["status"][0] == 0) & (refq["status"] == 0)
-    # QP mode: a few 4-foot instances stall just above iSWIFT's dual-residual limit (known limit) and
-    # come back as MAXITER with X right to 1e-6; everything else agrees
-    assert (outq["status"][0] == refq["status"]).mean() >= 0.99 and both.sum() > 1700
+    # QP mode (the reference's default, use_snopt = false): EVERY status equal to iSWIFT's, and the same iteration count on every
+    # instance both converge on (round 1 lost a 4-foot instance in ~1200 whose last support weight sat on its bound: LaneSolver::repivot)
+    assert (outq["status"][0] == refq["status"]).all(), np.nonzero(outq["status"][0] != refq["status"])[0][:20]
+    assert both.sum() > 1700 and (outq["qp_iters"][0][both] == refq["qp_iters"][both]).all()
     assert np.abs(outq["X"].T - refq["X"])[both].max() < 1e-7
     assert np.abs(outq["X"].T - refq["X"])[refq["status"] == 0].max() < 1e-5
     s.close()
