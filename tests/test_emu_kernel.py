@@ -86,3 +86,27 @@ def test_wide_fuzz_against_the_oracle():
     assert (outq["status"][0] == refq["status"]).all() and both.sum() > 250
     assert np.abs(outq["X"].T - refq["X"])[both].max() < 1e-8
     assert (outq["qp_iters"][0][both] == refq["qp_iters"][both]).all()
+
+
+def test_qp_mode_against_the_reference_iswift_core():
+    """QP mode (use_snopt = false, the reference's default) of the kernel source against the REFERENCE's own iSWIFT core
+    (oracle/_ref, compiled from /root/reference/optimization/iSWIFT): every status equal on a wide fuzz, iteration counts equal on
+    all but the odd instance where the core's LDL' dynamic regularisation (ldl.c:273-275) costs it extra iterations that the dense
+    restatement does not need either."""
+    import oracle as O
+    if O.ref_lib() is None:
+        import pytest
+        pytest.skip("oracle/_ref not built (the reference tree is absent)")
+    insts = H.wide_fuzz_instances(600)
+    outq = emu.solve(insts, mode=0)
+    O.use_reference_qp(True)
+    try:
+        refq = H.oracle_batch(insts, mode=0)
+    finally:
+        O.use_reference_qp(False)
+    st, rs = outq["status"][0], refq["status"]
+    assert (st == rs).all(), np.nonzero(st != rs)[0]
+    both = (st == 0) & (rs == 0)
+    assert both.sum() > 500
+    assert (outq["qp_iters"][0][both] == refq["qp_iters"][both]).mean() > 0.995
+    assert np.abs(outq["X"].T - refq["X"])[both].max() < 1e-6
