@@ -110,3 +110,20 @@ def test_qp_mode_against_the_reference_iswift_core():
     assert both.sum() > 500
     assert (outq["qp_iters"][0][both] == refq["qp_iters"][both]).mean() > 0.995
     assert np.abs(outq["X"].T - refq["X"])[both].max() < 1e-6
+
+
+def test_support_weights_come_back_in_the_order_of_the_feet():
+    """LaneSolver::repivot relabels the feet of a lane while it solves; the outputs must not show it: u = F lambda and 1'lambda = 1
+    hold with the reported lambda in the caller's foot order, and where lambda is unique (at least two feet of a stage unloaded --
+    which is also when the last foot's block becomes stiff and the relabelling happens) it equals the oracle's."""
+    insts = [i for i in H.wide_fuzz_instances(500) if sum(i[3]) == 4]
+    for mode in (0, 1):
+        out = emu.solve(insts, mode=mode); ref = H.oracle_batch(insts, mode=mode)
+        ok = (out["status"][0] == 0) & (ref["status"] == 0)
+        lam = out["lam"].T[ok].reshape(-1, 4, 4); rl = ref["lam"][ok].reshape(-1, 4, 4)      # [instance, stage, foot]
+        U = out["U"].T[ok].reshape(-1, 4, 2)
+        F = np.array([np.asarray(insts[i][2]) for i in np.nonzero(ok)[0]])                    # [instance, 2, 4]
+        assert np.abs(U - np.einsum("nkf,nsf->nsk", F, lam)).max() < 1e-12 and np.abs(1 - lam.sum(2)).max() < 1e-12
+        uniq = (rl < 1e-7).sum(2) >= 2
+        assert uniq.sum() > 100 and (rl[:, :, 3] < 1e-7).sum() > 20          # the last foot is unloaded often enough
+        assert np.abs(lam - rl)[uniq].max() < 1e-9
