@@ -430,6 +430,27 @@ def main():
             except Exception as e:  # the C++ example is optional for the bench line
                 lat["cpp_host"] = {"error": str(e)[:200]}
         line["latency"] = lat
+        # larger batches per launch (several waves of CTAs per SM): the same kernel, device-resident inputs, kernel time alone
+        if world == 1:
+            sweep = {}
+            for Bs in (8192, 32768):
+                ins = S.cfg3_instances(Bs, seed=20251018 + 7000 + Bs)
+                ds = capi.soa_from_instances(ins)
+                s3 = pkg.BatchSolver(device=local, max_batch=Bs, max_obs=int(ds["n_obs"]))
+                ti = {k: torch.from_numpy(ds[k]).to(dev) for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy", "alpha_buf")}
+                to = {k: torch.zeros((n, Bs), dtype=torch.float64, device=dev) for k, n in capi.OUT_F64.items()}
+                to.update({k: torch.zeros((n, Bs), dtype=torch.int32, device=dev) for k, n in capi.OUT_I32.items()})
+                to["active"] = torch.zeros((2, Bs), dtype=torch.int64, device=dev)
+                ip = {k: v.data_ptr() for k, v in ti.items()}; op = {k: v.data_ptr() for k, v in to.items()}
+                ms = []
+                for i in range(6):
+                    flush.fill_(1)
+                    s3.solve_device(Bs, ip, op, int(ds["n_obs"]), mode=capi.MODE_QP_NLP); torch.cuda.synchronize(dev)
+                    if i >= 2: ms.append(s3.last_kernel_ms())
+                cv = int((to["status"][0] == 0).sum().item())
+                sweep[str(Bs)] = {"kernel_ms": statistics.mean(ms), "converged_solves_per_s": cv / (statistics.mean(ms) * 1e-3), "converged_fraction": cv / Bs}
+                s3.close()
+            line["batch_sweep"] = sweep
         if extended is not None:
             line["extended"] = extended
         print(json.dumps(line))
