@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(1024, 1) cbfnmpc_classify_kernel(const __grid_
   if (threadIdx.x < 2) counts[threadIdx.x] = base[threadIdx.x];
 }
 
+#ifdef CBF_CTATIME  // debug builds only (scripts/dev/cta_times.py): duration and SM of every warp of the last cbfnmpc_lane_kernel launch
+__device__ long long g_ctat[3 * 2 * 8192];
+#endif
 __global__ void __launch_bounds__(LANE_NT, 1) cbfnmpc_lane_kernel(const __grid_constant__ KParams P, const __grid_constant__ BatchIO io,
                                                                   const int* __restrict__ perm, const int* __restrict__ counts, int sm_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -66,6 +69,9 @@ __global__ void __launch_bounds__(LANE_NT, 1) cbfnmpc_lane_kernel(const __grid_c
   // b + nsm share SM b: give those two the neighbouring work items 2b, 2b + 1 (same stance class except at the class boundary)
   // so that the two CTAs of an SM share instruction-cache lines.  SMs that get a single CTA take the items after the pairs.
   int cta = blockIdx.x;
+#ifdef CBF_CTATIME
+  long long ctat0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ctat0));
+#endif
   {
     const int nsm = sm_count, total = (int)gridDim.x, first = total < 2 * nsm ? total : 2 * nsm;
     const int npair = first > nsm ? first - nsm : 0;
@@ -82,6 +88,15 @@ __global__ void __launch_bounds__(LANE_NT, 1) cbfnmpc_lane_kernel(const __grid_c
     const bool valid = slot < n2;
     lane_run_group<2>(P, io, valid ? perm[io.B + slot] : 0, valid, pr, pace_make(pace_bar, pace_flag));
   }
+#ifdef CBF_CTATIME
+  __syncwarp();
+  if ((tid & 31) == 0 && blockIdx.x < 8192) {
+    long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    long long* o = g_ctat + 3 * (2 * (size_t)blockIdx.x + (tid >> 5));
+    o[0] = t1 - ctat0; o[1] = cta; o[2] = smid;
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -647,6 +662,12 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
   return CBFNMPC_OK;
 }
 
+#ifdef CBF_CTATIME
+int cbfnmpc_debug_ctatime(long long* out, int n) {  // debug builds only
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, g_ctat, sizeof(long long) * (size_t)n);
+}
+#endif
 #ifdef CBF_DBGBUF
 int cbfnmpc_debug_read(double* out, int reset) {  // debug builds only
   int n = 0;

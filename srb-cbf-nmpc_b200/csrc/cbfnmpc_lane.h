@@ -58,9 +58,28 @@ struct LaneFact {        // Riccati factors of stage j on the 5-state xi = (x, d
   double Lc[6];          // chol(R~_j): (1/l00, l10, 1/l11, l20, l21, 1/l22)
   double Zm[3], Nt[5], Ym[3], Tc;  // quasi-definite row: R~^-1 M', N~ = N - M R~^-1 S~, L^-1 M', 1 / sqrt(T)
   double p0dd;           // cost-to-go curvature of delta_0 (lane 0's value, replicated)
+  int nfix;              // R~_j was factorised in the basis T = [e0, e1, w_n] (l_null_dir); K, Zm, Ym and the solves follow it
 };
 
 LDEV int sy(int i, int k) { return i >= k ? (i * (i + 1)) / 2 + k : (k * (k + 1)) / 2 + i; }
+// Four stance feet: the support weights have ONE direction that moves nothing else -- F n = 0, 1'n = 0 -- and in the control
+// basis of the stage elimination (lambda = lambda_p + E w, D = F E) it is the null vector of D: w_n = (n0, n1, 1) / scale = the
+// cross product of D's two rows.  Its curvature is only what the bounds of the support weights give (Sigma_lambda ~ mu / s^2 ~
+// 1e-5 late in a solve) while the rest of R~ = D' N2 D + ... carries the stiffest state bound of the stage (Sigma ~ 1e13 for an
+// active velocity bound): formed entry by entry, the rounding of the large part (1e13 x 2e-16) buries the small one, the Newton
+// step along n is noise and the support-weight rows of the dual residual hover at ~mu / s (measured: one instance of the
+// 8 x 4096 bench set needed 21 instead of 12 iterations and set the time of its whole launch).  The factorisation therefore
+// works in the basis T = [e0, e1, w_n]: row and column 2 of T'R~T have no D term at all (D w_n = 0) and are written down from the
+// lambda block alone; right-hand sides get their third component the same way, and w = T w' at the end.
+template <int C>
+LDEV bool l_null_dir(const LaneConst& c, double& n0, double& n1) {
+  if (C != 4) { n0 = 0.0; n1 = 0.0; return false; }
+  const double c0 = c.D[1] * c.D[5] - c.D[2] * c.D[4], c1 = c.D[2] * c.D[3] - c.D[0] * c.D[5], c2 = c.D[0] * c.D[4] - c.D[1] * c.D[3];
+  const bool ok = fabs(c2) > 1e-3 * fmax(fabs(c0), fabs(c1));   // feet 0, 1 and the pivot foot not (nearly) in line
+  const double r = ok ? l_rcp(c2) : 0.0;
+  n0 = c0 * r; n1 = c1 * r;
+  return ok;
+}
 LDEV double l_sel4(const double* v, int j) { return j == 0 ? v[0] : (j == 1 ? v[1] : (j == 2 ? v[2] : v[3])); }
 
 // thread-private shared-memory column
@@ -245,6 +264,10 @@ LDEV bool l_factor(const Grp& g, const KParams& P, const LaneConst& c, const Lan
   double Pout[15];
   LUNR for (int t = 0; t < 15; t++) { Pout[t] = 0.0; f.Pn[t] = Pown[t]; }
   bool ok = true;
+  double n0, n1;
+  const bool nullok = !FLOOR && l_null_dir<C>(c, n0, n1);   // NLP stage only (the QP stage has no state bound beyond the +-1e3 boxes)
+  const double nsum = n0 + n1 + 1.0;
+  f.nfix = 0;
 #pragma unroll 1
   for (int step = 0; step < 4; step++) {
     if (step > 0) {
@@ -280,12 +303,25 @@ LDEV bool l_factor(const Grp& g, const KParams& P, const LaneConst& c, const Lan
       double T1[6];
       LUNR for (int b = 0; b < NW; b++) { T1[b] = N2[0] * c.D[b] + N2[1] * c.D[NW + b]; T1[NW + b] = N2[1] * c.D[b] + N2[2] * c.D[NW + b]; }
       const double hlast = H.hl[C - 1] + dw;
+      double dmax = 0.0;   // largest diagonal entry of the D part
       LUNR for (int a = 0; a < NW; a++) LUNR for (int b = 0; b <= a; b++) {
-        double s = c.D[a] * T1[b] + c.D[NW + a] * T1[NW + b] + hlast;
-        if (a == b) s += H.hl[a] + dw;
+        const double dd = c.D[a] * T1[b] + c.D[NW + a] * T1[NW + b];
+        double s = dd + hlast;
+        if (a == b) { s += H.hl[a] + dw; dmax = fmax(dmax, dd); }
         Rt[(a * (a + 1)) / 2 + b] = s;
       }
+      // basis T = [e0, e1, w_n] (l_null_dir) when the D part is what would bury the null direction's curvature -- three orders above
+      // everything the lambda block puts into row 2 of T'R~T: that row and column then hold the lambda block alone.  Otherwise
+      // (stiff support-weight bounds: they sit on the diagonal of the plain form, where the factorisation takes them first, and
+      // would be spread over row 2 by T) the plain basis is the accurate one.
+      if (nullok) {
+        const double h0 = H.hl[0] + dw, h1 = H.hl[1] + dw, h2 = H.hl[NW - 1] + dw, hs = hlast * nsum;
+        const double t0 = h0 * n0 * n0, t1 = h1 * n1 * n1, t2 = hs * nsum;
+        f.nfix = (1e3 * fmax(fmax(t0, t1), fmax(t2, h2)) < dmax) ? 1 : 0;
+        if (f.nfix) { Rt[3] = hs + h0 * n0; Rt[4] = hs + h1 * n1; Rt[5] = t2 + t0 + t1 + h2; }
+      }
     }
+    const bool nfix = f.nfix != 0;
     const bool okc = l_chol<NW, FLOOR>(Rt, f.Lc);
     // S~ = D' (GA + hxu on the position columns);  Y = L^-1 S~,  K = L^-T Y, column by column
     GA[0] += H.hxu[0]; GA[5 + 2] += H.hxu[1];
@@ -293,6 +329,7 @@ LDEV bool l_factor(const Grp& g, const KParams& P, const LaneConst& c, const Lan
     LUNR for (int m = 0; m < 5; m++) {
       double col[3] = {0.0, 0.0, 0.0};
       LUNR for (int a = 0; a < NW; a++) col[a] = c.D[a] * GA[m] + c.D[NW + a] * GA[5 + m];
+      if (nfix) col[NW - 1] = 0.0;   // w_n' D'(.) = 0
       l_chol_fwd<NW>(f.Lc, col);
       LUNR for (int a = 0; a < NW; a++) Y[5 * a + m] = col[a];
       l_chol_bwd<NW>(f.Lc, col);
@@ -310,6 +347,7 @@ LDEV bool l_factor(const Grp& g, const KParams& P, const LaneConst& c, const Lan
     if (H.capped) {
       double col[3] = {0.0, 0.0, 0.0};
       LUNR for (int a = 0; a < NW; a++) col[a] = P.bp * (H.gv[0] * c.D[a] + H.gv[1] * c.D[NW + a]);
+      if (nfix) col[NW - 1] = 0.0;
       l_chol_fwd<NW>(f.Lc, col);
       LUNR for (int a = 0; a < 3; a++) f.Ym[a] = (a < NW) ? col[a] : 0.0;
       l_chol_bwd<NW>(f.Lc, col);
@@ -341,10 +379,11 @@ LDEV bool l_factor(const Grp& g, const KParams& P, const LaneConst& c, const Lan
 // rq: right-hand side of this lane's quasi-definite row (g'dx - t / (Sigma - cap) = rq; zero in the first solve, the residual
 // in refinement); tq: its multiplier t.
 // ---------------------------------------------------------------------------------------------------------------
-struct LaneMain { double rx[5], rw[3], cv[4], pv[5], kv[3], tt; };
+struct LaneMain { double rx[5], rw[3], cv[4], pv[5], kv[3], tt; };   // (rw, kv and the factors K, Zm live in the basis T of l_null_dir)
 
 template <int C>
-LDEV void l_stage_eliminate(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, double dw, const KV& r, LaneMain& m, double* d0) {
+LDEV void l_stage_eliminate(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, double dw, const KV& r, LaneMain& m, double* d0,
+                            bool nfix, double n0, double n1) {
   constexpr int NW = LaneDims<C>::NW;
   const double e0 = r.eta;
   LUNR for (int a = 0; a < 2; a++) d0[a] = c.Fl[a] * e0 + r.nu[a];
@@ -352,6 +391,7 @@ LDEV void l_stage_eliminate(const Grp& g, const KParams& P, const LaneConst& c, 
   const double ru0 = r.us[0] - (H.hu[0] + dw) * d0[0], ru1 = r.us[1] - (H.hu[1] + dw) * d0[1];
   LUNR for (int a = 0; a < 3; a++) m.rw[a] = 0.0;
   LUNR for (int a = 0; a < NW; a++) m.rw[a] = r.lm[a] - last + c.D[a] * ru0 + c.D[NW + a] * ru1;
+  if (nfix) m.rw[NW - 1] = n0 * (r.lm[0] - last) + n1 * (r.lm[1] - last) + (r.lm[NW - 1] - last);   // w_n'(.): no D term
   LUNR for (int b = 0; b < 2; b++) {
     m.cv[2 * b] = P.bp * d0[b] - r.pi[2 * b];
     m.cv[2 * b + 1] = P.bv * d0[b] - r.pi[2 * b + 1];
@@ -385,12 +425,14 @@ LDEV void l_recover(const Grp& g, const KParams& P, const LaneConst& c, const La
   d.eta = r.lm[C - 1] - (H.hl[C - 1] + dw) * dll + c.Fl[0] * d.nu[0] + c.Fl[1] * d.nu[1];
 }
 
-template <int C>
+template <int C, bool NL>
 LDEV void l_kkt_solve(const Grp& g, const KParams& P, const LaneConst& c, const LaneHess& H, const LaneFact& f, double dw, const KV& r,
                       double rq, KV& d, double& tq) {
   constexpr int NW = LaneDims<C>::NW;
   LaneMain m; double d0[2];
-  l_stage_eliminate<C>(g, P, c, H, dw, r, m, d0);
+  double n0, n1;
+  const bool nfix = NL && l_null_dir<C>(c, n0, n1) && f.nfix != 0;
+  l_stage_eliminate<C>(g, P, c, H, dw, r, m, d0, nfix, n0, n1);
   // ---- backward chain
   double out[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
@@ -407,6 +449,7 @@ LDEV void l_kkt_solve(const Grp& g, const KParams& P, const LaneConst& c, const 
     const double g0 = P.bp * q[0] + P.bv * q[1], g1 = P.bp * q[2] + P.bv * q[3];
     double k0[3] = {0.0, 0.0, 0.0}, kr[3] = {0.0, 0.0, 0.0}, ykr[3] = {0.0, 0.0, 0.0};
     LUNR for (int a = 0; a < NW; a++) { kr[a] = m.rw[a] - (c.D[a] * g0 + c.D[NW + a] * g1); k0[a] = kr[a]; }
+    if (nfix) { kr[NW - 1] = m.rw[NW - 1]; k0[NW - 1] = kr[NW - 1]; }
     l_chol_fwd<NW>(f.Lc, k0);
     LUNR for (int a = 0; a < NW; a++) ykr[a] = k0[a];
     l_chol_bwd<NW>(f.Lc, k0);
@@ -451,6 +494,7 @@ LDEV void l_kkt_solve(const Grp& g, const KParams& P, const LaneConst& c, const 
       if (H.capped) s -= f.Zm[a] * tl;
       w[a] = s;
     }
+    if (nfix) { w[0] += n0 * w[NW - 1]; w[1] += n1 * w[NW - 1]; }   // w = T w'
     double e0 = 0.0, e1 = 0.0;
     LUNR for (int a = 0; a < NW; a++) { e0 += c.D[a] * w[a]; e1 += c.D[NW + a] * w[a]; }
     double ax[4];
@@ -652,7 +696,7 @@ struct LaneSolver {
       g_keep(g, okr);
       if (!okr) { info.qp_flag = 1; return true; }
     }
-    { double tq; l_kkt_solve<C>(g, P, c, H, f, 0.0, r, 0.0, dd, tq); }
+    { double tq; l_kkt_solve<C, false>(g, P, c, H, f, 0.0, r, 0.0, dd, tq); }
     x = dd;
     LUNR for (int i = C; i < 4; i++) x.lm[i] = 0.0;
     // slacks and multipliers shifted positive (Auxilary.c:724-746)
@@ -759,7 +803,7 @@ struct LaneSolver {
       LUNR for (int i = 0; i < 4; i++) { r.xs[i] += rx.xs[i]; r.lm[i] += rx.lm[i]; r.pi[i] = rx.pi[i]; }
       LUNR for (int a = 0; a < 2; a++) { r.us[a] += rx.us[a]; r.nu[a] = rx.nu[a]; }
       r.dl = rx.dl; r.eta = rx.eta;
-      { double tq; l_kkt_solve<C>(g, P, c, H, f, 0.0, r, 0.0, dd, tq); }
+      { double tq; l_kkt_solve<C, false>(g, P, c, H, f, 0.0, r, 0.0, dd, tq); }
       double dxp[4]; prev_state(dd, true, dxp);
       l_scatter<C, false>(g, pr, d::Q_DE, dd, dxp);
       // ---- pass B (affine: max step lengths, findsteplength Auxilary.c:271-294, and rho, Auxilary.c:600-609)
@@ -1007,6 +1051,19 @@ struct LaneSolver {
       info.kkt = E0; info.nlp_iters = it;
       LANE_LOG(1000.0 + it); LANE_LOG(mu); LANE_LOG(E0); LANE_LOG(e_d); LANE_LOG(e_p); LANE_LOG(e_c); LANE_LOG(th);
       LANE_DBG("it %d mu %.2e E0 %.3e ed %.2e ep %.2e ec %.2e zmax %.2e th %.2e\n", it, mu, E0, e_d, e_p, e_c, zmax, th);
+#ifdef CBF_DBGBUF
+      {   // dual residual by variable class: X, U, lambda, slack variable
+        double tx = 0, tu = 0, tl = 0;
+        LUNR for (int i = 0; i < 4; i++) tx = fmax(tx, fabs(gfy.xs[i] - jz.xs[i]));
+        LUNR for (int a = 0; a < 2; a++) tu = fmax(tu, fabs(gfy.us[a] - jz.us[a]));
+        LUNR for (int i = 0; i < C; i++) tl = fmax(tl, fabs(gfy.lm[i] - jz.lm[i]));
+        const double tdl = fabs(P.slw * x.dl - g_sum(g, wd));
+        for (int k = 0; k < 4; k++) {
+          const double v0 = g_idx(g, tx, k), v1 = g_idx(g, tu, k), v2 = g_idx(g, tl, k);
+          LANE_LOG(-3000.0 - k); LANE_LOG(v0); LANE_LOG(v1); LANE_LOG(v2); LANE_LOG(tdl);
+        }
+      }
+#endif
 #ifdef CBF_TRACE
       {
         double tx = 0, tu = 0, tl = 0, gx = 0, jx = 0, py = 0, ny = 0;
@@ -1090,7 +1147,7 @@ struct LaneSolver {
       bool refining = qd_mine;  // this group checks its residual and takes the correction of the next solve
       for (int rf = 0;; rf++) {
         KV d2; double t2;
-        l_kkt_solve<C>(g, P, c, H, f, dw, r, rq, d2, t2);
+        l_kkt_solve<C, true>(g, P, c, H, f, dw, r, rq, d2, t2);
         if (rf == 0) { dd = d2; tq = t2; }
         else if (refining) {
           LUNR for (int i = 0; i < 4; i++) { dd.xs[i] += d2.xs[i]; dd.lm[i] += d2.lm[i]; dd.pi[i] += d2.pi[i]; }
@@ -1158,6 +1215,9 @@ struct LaneSolver {
     double a_pmax, a_dmax, ph, dphi, dQd, gdx;
     {
       double rp = 0.0, rdm = 0.0, prod = 1.0, prod2 = 1.0, dsum = 0.0;
+#ifdef CBF_DBGBUF
+      double dbg_zq = -1e300, dbg_de = 0, dbg_slo = 0, dbg_shi = 0, dbg_zlo = 0, dbg_zhi = 0; int dbg_slot = -1;
+#endif
       LSLOTS for (int s = 0; s < nsn; s++) {
         const bool vhi = s != d::SD;
         const double de = pr(d::N_C + s), rlo = pr(d::N_A + s), rhi = pr(d::N_B + s);
@@ -1166,6 +1226,9 @@ struct LaneSolver {
         double zq = -pr(d::N_D + s) * l_rcp(pr(d::N_ZLO + s));
         if (vhi) zq = fmax(zq, -pr(d::N_E + s) * l_rcp(pr(d::N_ZHI + s)));
         rdm = fmax(rdm, zq);
+#ifdef CBF_DBGBUF
+        if (zq > dbg_zq) { dbg_zq = zq; dbg_slot = s; dbg_de = de; dbg_slo = pr(d::N_SLO + s); dbg_shi = pr(d::N_SHI + s); dbg_zlo = pr(d::N_ZLO + s); dbg_zhi = pr(d::N_ZHI + s); }
+#endif
         const double ss = pr(d::N_SLO + s) * pr(d::N_SHI + s);
         if (s & 1) prod *= ss; else prod2 *= ss;
         dsum += de * rlo - (vhi ? de * rhi : 0.0);
@@ -1174,6 +1237,12 @@ struct LaneSolver {
       const double tau = PERS_TAU;
       a_pmax = (rp > tau) ? tau / rp : 1.0; a_dmax = (rdm > tau) ? tau / rdm : 1.0;
       LANE_LOG(dw); LANE_LOG(a_pmax); LANE_LOG(a_dmax);
+#ifdef CBF_DBGBUF
+      for (int k = 0; k < 4; k++) {   // per lane: the slot that limits the dual step
+        const double v0 = g_idx(g, dbg_zq, k), v1 = g_idx(g, (double)dbg_slot, k), v2 = g_idx(g, dbg_de, k), v3 = g_idx(g, dbg_slo, k), v4 = g_idx(g, dbg_shi, k), v5 = g_idx(g, dbg_zlo, k), v6 = g_idx(g, dbg_zhi, k);
+        LANE_LOG(-2000.0 - k); LANE_LOG(v0); LANE_LOG(v1); LANE_LOG(v2); LANE_LOG(v3); LANE_LOG(v4); LANE_LOG(v5); LANE_LOG(v6);
+      }
+#endif
       LANE_DBG("   dw %.1e apmax %.3e admax %.3e ddl %.3e\n", dw, a_pmax, a_dmax, dd.dl);
       // f(x) = sum_j x_j (1/2 Q_jj x_j + f_j)   (DV:423-428)
       double f0 = 0.0, gd = 0.0, qd = 0.0;
