@@ -121,6 +121,10 @@ long long cbfnmpc_launch_count(const cbfnmpc_ctx *ctx);
 /* last solve kernel's duration in ms measured with CUDA events on the launch stream (synchronises).  A host-buffer call on a
  * large batch launches one kernel per column range (see cbfnmpc_solve_batch_host); the first range's kernel is the one timed. */
 int cbfnmpc_last_kernel_ms(cbfnmpc_ctx *ctx, float *ms);
+/* on = 0: do not record the event pair around the solve kernel (cbfnmpc_last_kernel_ms then answers for the last launch that was
+ * timed).  Without the event between them the solve kernel is launched as a programmatic dependent of the classify pre-pass, which
+ * takes its launch latency out of the call (a few microseconds per launch).  Default: on. */
+int cbfnmpc_set_kernel_timing(cbfnmpc_ctx *ctx, int on);
 
 /* One instance in the reference's own dense layout (column-major Eigen matrices of pack_nlp_data.h:11-29).
  * The compact form is recovered from the matrices; CBFNMPC_ERR_STRUCTURE if they are not MPC_dist-shaped. */

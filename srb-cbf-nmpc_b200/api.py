@@ -46,6 +46,7 @@ def load():
     L.cbfnmpc_launch_count.argtypes = [C.c_void_p]
     L.cbfnmpc_launch_count.restype = C.c_longlong
     L.cbfnmpc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.cbfnmpc_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     L.cbfnmpc_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.cbfnmpc_solve_dense_nlptuple.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L.cbfnmpc_ext_default_cfg.argtypes = [C.POINTER(capi.ExtCfg)]
@@ -63,7 +64,7 @@ def load():
 
 EXPORTS = ["cbfnmpc_version", "cbfnmpc_last_error", "cbfnmpc_default_gains", "cbfnmpc_default_options", "cbfnmpc_create",
            "cbfnmpc_destroy", "cbfnmpc_set_gains", "cbfnmpc_set_options", "cbfnmpc_solve_batch", "cbfnmpc_solve_batch_host",
-           "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak",
+           "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_set_kernel_timing", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak",
            "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle", "cbfnmpc_closed_loop", "cbfnmpc_generate_reference", "cbfnmpc_qp_dense_batch",
            "cbfnmpc_team_states", "cbfnmpc_pack_dense", "cbfnmpc_ext_default_cfg", "cbfnmpc_ext_solve_batch", "cbfnmpc_ext_solve_batch_host",
            "cbfnmpc_comm_unique_id", "cbfnmpc_comm_init", "cbfnmpc_comm_destroy", "cbfnmpc_ext_solve_sharded"]
@@ -249,6 +250,10 @@ class BatchSolver:
 
     def launch_count(self):
         return int(self.L.cbfnmpc_launch_count(self.ctx))
+
+    def set_kernel_timing(self, on):
+        """Event pair around the solve kernel on / off (off: the solve kernel becomes a programmatic dependent of the classify pre-pass)."""
+        self._ck(self.L.cbfnmpc_set_kernel_timing(self.ctx, 1 if on else 0))
 
     def last_kernel_ms(self):
         ms = C.c_float(0); self._ck(self.L.cbfnmpc_last_kernel_ms(self.ctx, C.byref(ms))); return ms.value

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(1024, 1) cbfnmpc_classify_kernel(const __grid_
   __shared__ int wcnt[2][32];
   __shared__ int base[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  asm volatile("griddepcontrol.launch_dependents;");   // a solve kernel launched as programmatic dependent may be placed now (launch_on)
   if (threadIdx.x < 2) base[threadIdx.x] = 0;
   __syncthreads();
   for (int b0 = 0; b0 < io.B; b0 += 1024) {
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(LANE_NT, 1) cbfnmpc_lane_kernel(const __grid_c
   __shared__ unsigned long long pace_bar[2];
   __shared__ int pace_flag[2 * ((LANE_NT + 31) / 32)];
   const int grp = tid >> 2;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // class lists of the preceding cbfnmpc_classify_kernel (no-op for an ordinary launch)
   const int n4 = counts[0], n2 = counts[1];
   const int c4 = (n4 + IPC - 1) / IPC;
   // The first 2 x (number of SMs) CTAs are resident at once and are handed out breadth-first over the SMs, so blockIdx b and
@@ -345,6 +347,7 @@ struct cbfnmpc_ctx {
   cudaStream_t last_stream;  // the stream it was recorded on (a call on another stream waits for it first)
   bool have_last;
   bool timed;
+  bool timing_on;            // record the event pair around the solve kernel (cbfnmpc_set_kernel_timing; default on)
   int sm_count;
   long long launches;
   // staging for the host-pointer entry points
@@ -394,6 +397,7 @@ int cbfnmpc_create(cbfnmpc_ctx** out, int device, int max_batch, int max_obs) {
   cbfnmpc_ctx* c = new cbfnmpc_ctx();
   c->device = device; c->max_batch = max_batch; c->max_obs = max_obs; c->launches = 0; c->timed = false;
   { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); c->sm_count = prop.multiProcessorCount; }
+  c->timing_on = true;
   host_default_gains(&c->gains); host_default_options(&c->opts);
   host_fill_kparams(&c->gains, &c->opts, &c->kp);
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -494,8 +498,20 @@ static int launch_on(cbfnmpc_ctx* c, int B, int ld, int mode, const cbfnmpc_in* 
     CK(cudaGetLastError());
     c->launches++;
   }
+  timed = timed && c->timing_on;
   if (timed) CK(cudaEventRecord(c->ev0, st));  // the event pair brackets the solve kernel alone
-  cbfnmpc_lane_kernel<<<(B + ipc - 1) / ipc + 1, LANE_NT, LANE_NPRIV * LANE_NT * sizeof(double), st>>>(c->kp, io, perm, counts, c->sm_count);
+  {
+    // Without the event in between, the solve kernel is a programmatic dependent of the classify kernel: its CTAs are placed while
+    // the class lists are still being written and wait for them at griddepcontrol.wait (the launch latency leaves the step).
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)((B + ipc - 1) / ipc + 1)); cfg.blockDim = dim3(LANE_NT);
+    cfg.dynamicSmemBytes = LANE_NPRIV * LANE_NT * sizeof(double); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (classify && !timed) ? 1 : 0;
+    const int* cperm = perm; const int* ccounts = counts;
+    CK(cudaLaunchKernelEx(&cfg, cbfnmpc_lane_kernel, c->kp, io, cperm, ccounts, c->sm_count));
+  }
   CK(cudaGetLastError());
   if (timed) { CK(cudaEventRecord(c->ev1, st)); c->timed = true; }
   c->launches++;
@@ -793,6 +809,12 @@ int cbfnmpc_closed_loop(cbfnmpc_ctx* c, int B, int n_cycles, int mode, const cbf
 }
 
 long long cbfnmpc_launch_count(const cbfnmpc_ctx* c) { return c ? c->launches : 0; }
+
+int cbfnmpc_set_kernel_timing(cbfnmpc_ctx* c, int on) {
+  if (!c) return fail(CBFNMPC_ERR_ARG, "null argument");
+  c->timing_on = on != 0;
+  return CBFNMPC_OK;
+}
 
 int cbfnmpc_last_kernel_ms(cbfnmpc_ctx* c, float* ms) {
   if (!c || !ms) return fail(CBFNMPC_ERR_ARG, "null argument");

@@ -486,6 +486,29 @@ def test_host_call_pinned_and_pageable_buffers_agree(pkg, solver):
         assert np.array_equal(on[k], ref[k]), k
 
 
+def test_kernel_timing_off_same_answers(pkg):
+    """cbfnmpc_set_kernel_timing(0): no event pair around the solve kernel, which is then launched as a programmatic dependent of the
+    classify pre-pass (griddepcontrol) -- bit-identical answers, repeated calls included (the class lists of call i + 1 are written
+    while nothing of call i is left), for a large batch (4 column ranges) and a mid-size one (one launch)."""
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    s = pkg.BatchSolver(device=0, max_batch=4500, max_obs=20)
+    for B in (4500, 700):
+        insts = S.cfg3_instances(B, seed=77 + B)
+        # every fifth instance with a bad contact pattern: answered by the classify pre-pass
+        insts = [(i[0], i[1], i[2], (1, 1, 1, 0) if k % 5 == 0 else i[3], i[4]) for k, i in enumerate(insts)]
+        d = capi.soa_from_instances(insts)
+        s.set_kernel_timing(True)
+        ref = s.solve_host(d, mode=capi.MODE_QP_NLP)
+        s.set_kernel_timing(False)
+        for rep in range(3):
+            out = s.solve_host(d, mode=capi.MODE_QP_NLP)
+            for k in ref:
+                assert np.array_equal(out[k], ref[k]), (B, rep, k)
+        assert (out["status"][0][::5] == 4).all() and (out["status"][0] == 0).sum() > B // 2
+    s.set_kernel_timing(True)
+    s.close()
+
+
 def test_ragged_batch_sizes_and_edge_inputs(pkg):
     """Batch sizes around the group / warp / CTA granularities (8 instances per warp, 16 per CTA, two stance classes), a batch
     made only of bad contact patterns, a single obstacle column, and far-away obstacles (first-minimum rule with the
