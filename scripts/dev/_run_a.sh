@@ -1,3 +1,3 @@
-timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -5
-timeout 600 python bench.py --no-extended > gpurun_out/bench_v22b.json 2> gpurun_out/bench_v22b.err; tail -3 gpurun_out/bench_v22b.err
-timeout 100 python scripts/dev/step_overhead.py 2>&1 | tail -8
+timeout 200 python scripts/dev/ext_quick.py cfg4 cfg5 2>&1 | tail -2
+CBFNMPC_LIB=$PWD/build/libcbfnmpc_extn.so timeout 200 python scripts/dev/ext_quick.py cfg4 cfg5 2>&1 | tail -2
+CBFNMPC_LIB=$PWD/build/libcbfnmpc_extn.so timeout 600 python -m pytest tests/test_gpu_ext.py -x -q 2>&1 | tail -3
