@@ -124,16 +124,6 @@ struct XHess {
   double hu[2], hxu[2], hl[4];
 };
 struct XCap { double gx, gy, srinv; int row; };   // a row kept in quasi-definite form
-// null vector w_n = (n0, n1, 1) of D for a four-foot stance (cbfnmpc_lane.h l_null_dir: the free direction of the support weights)
-template <int C, class CT>
-XDEV bool x_null_dir(const CT& c, double& n0, double& n1) {
-  if (C != 4) { n0 = 0.0; n1 = 0.0; return false; }
-  const double c0 = c.D[1] * c.D[5] - c.D[2] * c.D[4], c1 = c.D[2] * c.D[3] - c.D[0] * c.D[5], c2 = c.D[0] * c.D[4] - c.D[1] * c.D[3];
-  const bool ok = fabs(c2) > 1e-3 * fmax(fabs(c0), fabs(c1));
-  const double r = ok ? x_rcp(c2) : 0.0;
-  n0 = c0 * r; n1 = c1 * r;
-  return ok;
-}
 struct XFact {
   double Pn[15];          // cost-to-go at xi_{j+1}, 5 x 5 packed lower
   double K[15];           // R~^-1 S~ : [a * 5 + m]
@@ -144,7 +134,6 @@ struct XFact {
   double Tc[3];           // chol(T): (1/l00, l10, 1/l11)
   double p0dd;            // lane 0: cost-to-go curvature of delta_0 (all lanes hold lane 0's value after the factorisation)
   int kc;
-  int nfix;               // R~ was factorised in the basis T = [e0, e1, w_n] (cbfnmpc_lane.h l_null_dir); K, Zm, Ym and the solves follow it
 };
 struct XMain { double rx[5], rw[3], cv[4], pv[5], kv[3], tt[XKC]; };
 
@@ -328,10 +317,6 @@ struct XSolver {
     XUNR for (int t = 0; t < 15; t++) { Pout[t] = 0.0; f.Pn[t] = Pown[t]; }
     f.kc = kc_in;
     bool ok = true;
-    double n0, n1;
-    const bool nullok = !FLOOR && x_null_dir<C>(c, n0, n1);   // interior-point iterations only, as in cbfnmpc_lane.h
-    const double nsum = n0 + n1 + 1.0;
-    f.nfix = 0;
 #pragma unroll 1
     for (int step = 0; step < W; step++) {
       if (step > 0) {   // P_{j+1} = own blocks + what lane j+1 produced in the previous step
@@ -364,28 +349,18 @@ struct XSolver {
         double T1[6];
         XUNR for (int b = 0; b < NW; b++) { T1[b] = N2[0] * c.D[b] + N2[1] * c.D[NW + b]; T1[NW + b] = N2[1] * c.D[b] + N2[2] * c.D[NW + b]; }
         const double hlast = H.hl[C - 1] + dw;
-        double dmax = 0.0;
         XUNR for (int a = 0; a < NW; a++) XUNR for (int b = 0; b <= a; b++) {
-          const double dd = c.D[a] * T1[b] + c.D[NW + a] * T1[NW + b];
-          double s = dd + hlast;
-          if (a == b) { s += H.hl[a] + dw; dmax = fmax(dmax, dd); }
+          double s = c.D[a] * T1[b] + c.D[NW + a] * T1[NW + b] + hlast;
+          if (a == b) s += H.hl[a] + dw;
           Rt[(a * (a + 1)) / 2 + b] = s;
         }
-        if (nullok) {   // basis T = [e0, e1, w_n] when the D part would bury the null direction's curvature (cbfnmpc_lane.h l_factor)
-          const double h0 = H.hl[0] + dw, h1 = H.hl[1] + dw, h2 = H.hl[NW - 1] + dw, hs = hlast * nsum;
-          const double t0 = h0 * n0 * n0, t1 = h1 * n1 * n1, t2 = hs * nsum;
-          f.nfix = (1e3 * fmax(fmax(t0, t1), fmax(t2, h2)) < dmax) ? 1 : 0;
-          if (f.nfix) { Rt[3] = hs + h0 * n0; Rt[4] = hs + h1 * n1; Rt[5] = t2 + t0 + t1 + h2; }
-        }
       }
-      const bool nfix = f.nfix != 0;
       const bool okc = x_chol<NW, FLOOR>(Rt, f.Lc);
       GA[0] += H.hxu[0]; GA[5 + 2] += H.hxu[1];
       double Y[15];
       XUNR for (int m = 0; m < 5; m++) {
         double col[3] = {0.0, 0.0, 0.0};
         XUNR for (int a = 0; a < NW; a++) col[a] = c.D[a] * GA[m] + c.D[NW + a] * GA[5 + m];
-        if (nfix) col[NW - 1] = 0.0;   // w_n' D'(.) = 0
         x_fwd<NW>(f.Lc, col);
         XUNR for (int a = 0; a < 3; a++) Y[5 * a + m] = (a < NW) ? col[a] : 0.0;
         x_bwd<NW>(f.Lc, col);
@@ -406,7 +381,6 @@ struct XSolver {
           if (q < f.kc) {
             double col[3] = {0.0, 0.0, 0.0};
             XUNR for (int a = 0; a < NW; a++) col[a] = P.bp * (cap[q].gx * c.D[a] + cap[q].gy * c.D[NW + a]);
-            if (nfix) col[NW - 1] = 0.0;
             x_fwd<NW>(f.Lc, col);
             XUNR for (int a = 0; a < 3; a++) f.Ym[q][a] = (a < NW) ? col[a] : 0.0;
             x_bwd<NW>(f.Lc, col);
@@ -444,14 +418,13 @@ struct XSolver {
   }
 
   // right-hand side after the elimination of (u_j, lambda_j) through u = F lambda, 1'lambda = 1 (cbfnmpc_lane.h l_stage_eliminate)
-  XMEM void stage_eliminate(const KParams& P, double dw, const XKV& r, XMain& m, double* d0, bool nfix, double n0, double n1) const {
+  XMEM void stage_eliminate(const KParams& P, double dw, const XKV& r, XMain& m, double* d0) const {
     const double e0 = r.eta;
     XUNR for (int a = 0; a < 2; a++) d0[a] = c.Fl[a] * e0 + r.nu[a];
     const double last = r.lm[C - 1] - (H.hl[C - 1] + dw) * e0;
     const double ru0 = r.us[0] - (H.hu[0] + dw) * d0[0], ru1 = r.us[1] - (H.hu[1] + dw) * d0[1];
     XUNR for (int a = 0; a < 3; a++) m.rw[a] = 0.0;
     XUNR for (int a = 0; a < NW; a++) m.rw[a] = r.lm[a] - last + c.D[a] * ru0 + c.D[NW + a] * ru1;
-    if (nfix) m.rw[NW - 1] = n0 * (r.lm[0] - last) + n1 * (r.lm[1] - last) + (r.lm[NW - 1] - last);   // w_n'(.): no D term
     XUNR for (int b = 0; b < 2; b++) { m.cv[2 * b] = P.bp * d0[b] - r.pi[2 * b]; m.cv[2 * b + 1] = P.bv * d0[b] - r.pi[2 * b + 1]; }
     XUNR for (int b = 0; b < 2; b++) {
       const double t = g_down(g, H.hxu[b] * d0[b]);
@@ -480,9 +453,7 @@ struct XSolver {
   // rq = right-hand side of the quasi-definite rows (g'dx - t / (Sigma - cap) = rq; zero in the first solve, the residual in refinement)
   XMEM void kkt_solve(const KParams& P, double dw, const XKV& r, const double* rq, XKV& dd, double* tq) const {
     XMain m; double d0[2];
-    double n0, n1;
-    const bool nfix = x_null_dir<C>(c, n0, n1) && f.nfix != 0;
-    stage_eliminate(P, dw, r, m, d0, nfix, n0, n1);
+    stage_eliminate(P, dw, r, m, d0);
     // ---- backward chain
     double out[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
@@ -499,7 +470,6 @@ struct XSolver {
       const double g0 = P.bp * q[0] + P.bv * q[1], g1 = P.bp * q[2] + P.bv * q[3];
       double k0[3] = {0.0, 0.0, 0.0}, kr[3] = {0.0, 0.0, 0.0}, ykr[3];
       XUNR for (int a = 0; a < NW; a++) { kr[a] = m.rw[a] - (c.D[a] * g0 + c.D[NW + a] * g1); k0[a] = kr[a]; }
-      if (nfix) { kr[NW - 1] = m.rw[NW - 1]; k0[NW - 1] = kr[NW - 1]; }
       x_fwd<NW>(f.Lc, k0);
       XUNR for (int a = 0; a < 3; a++) ykr[a] = k0[a];
       x_bwd<NW>(f.Lc, k0);
@@ -549,7 +519,6 @@ struct XSolver {
         if (f.kc > 0) { XUNR for (int qq = 0; qq < XKC; qq++) if (qq < f.kc) s -= f.Zm[qq][a] * tl[qq]; }
         w[a] = s;
       }
-      if (nfix) { w[0] += n0 * w[NW - 1]; w[1] += n1 * w[NW - 1]; }   // w = T w'
       double e0 = 0.0, e1 = 0.0;
       XUNR for (int a = 0; a < NW; a++) { e0 += c.D[a] * w[a]; e1 += c.D[NW + a] * w[a]; }
       double ax[4];
