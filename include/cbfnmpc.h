@@ -113,7 +113,7 @@ int cbfnmpc_set_options(cbfnmpc_ctx *ctx, const cbfnmpc_options *o);
 
 /* device pointers; asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream) */
 int cbfnmpc_solve_batch(cbfnmpc_ctx *ctx, int B, int mode, const cbfnmpc_in *in, const cbfnmpc_out *out, void *cuda_stream);
-/* host pointers; copies in, solves, copies out, synchronises.  Batches of >= 1024 instances travel as 2-4 column ranges on
+/* host pointers; copies in, solves, copies out, synchronises.  Batches of >= 16384 instances travel as 2 column ranges on
  * separate streams so that copies overlap solves; pinned buffers laid out back to back need one copy per range and direction. */
 int cbfnmpc_solve_batch_host(cbfnmpc_ctx *ctx, int B, int mode, const cbfnmpc_in *in, const cbfnmpc_out *out);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */

@@ -611,15 +611,18 @@ int cbfnmpc_solve_batch_host(cbfnmpc_ctx* c, int B, int mode, const cbfnmpc_in* 
   if (c->have_last) { CK(cudaEventSynchronize(c->ev_last)); c->have_last = false; }  // an earlier asynchronous call on a caller's stream
   if (B <= c->small_cap) return solve_small(c, B, mode, in, out, K);
   const size_t Bs = (size_t)B;
-  // Large batches are cut into equal column ranges, each on its own stream: the upload of one range overlaps the solves of
-  // the earlier ones and the downloads of the earlier ones overlap the solves of the later ones.  A range's kernel does not
-  // get faster with fewer instances (it is latency-bound), so the kernels simply run side by side; what stays on the critical
-  // path is the upload of everything, one kernel and the download of the last range.  All uploads and launches are enqueued
-  // before any download.  Measured on B200 with 4096 instances: 1 / 2 / 4 / 8 ranges -> 0.932 / 0.890 / 0.880 / 0.903 ms
-  // (4 ranges shrinking by 0.556, so that in theory they finish together: 0.874 - 1.0 ms, worse and erratic).
+  // Column ranges, each on its own stream, let the upload of one range overlap the solves of the earlier ones and the downloads of
+  // the earlier ones overlap the solves of the later ones; every range costs a classify + solve launch pair of its own, and side by
+  // side those pairs take longer than one (four quarter batches of 1024 on four streams: 0.573 ms against 0.529 ms for one launch of
+  // 4096, device-resident).  With the round-1 kernel (0.75 ms per 4096) four ranges were the optimum (1 / 2 / 4 / 8 ranges: 0.932 /
+  // 0.890 / 0.880 / 0.903 ms); with the round-2 kernel the copies of a 4096 batch (0.06 + 0.045 ms) are worth less than the extra
+  // launches -- measured host call (scripts/dev/e2e_parts.py), 1 / 2 / 4 ranges: 2048: 0.543 / 0.554 / 0.580; 4096: 0.647 / 0.654 /
+  // 0.666; 8192: 0.995 / 1.062 / 1.022; 16384: 1.899 / 1.863 / 2.048; 32768: 3.487 / 3.317 / 3.425 ms -- so one range below 16384
+  // instances and two from there on.  All uploads and launches are enqueued before any download.
   // Device staging (pitch B): x0 4 | xdes 16 | feet 8 | alpha_buf 4 | obs 2K rows of doubles; outputs in the order of
   // the O_* rows (X 16 | U 8 | slack 1 | alpha 20 | abuf_next 4 | kkt 1 | lam 16 | x_qp 24).
-  const int nch = B >= 4096 ? 4 : (B >= 1024 ? 2 : 1);
+  int nch = B >= 16384 ? 2 : 1;
+  if (const char* e = getenv("CBFNMPC_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= CBF_MAX_CHUNKS) nch = v; }   // tuning experiments only
   size_t cut[CBF_MAX_CHUNKS + 1];
   for (int k = 0; k <= nch; k++) cut[k] = Bs * k / nch;
   double* d = c->d_in;
