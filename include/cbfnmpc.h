@@ -285,12 +285,21 @@ typedef struct {
   int launches, iterations, exchanges, nranks;
   long long bytes_per_exchange; /* contributed by this rank per all-gather */
   float total_ms;               /* device time of the whole call (CUDA events) */
+  int fused;                    /* 1: the exchange ran inside one launch over peer-memory mailboxes (cbfnmpc_ext_solve_fused) */
 } cbfnmpc_ext_stats;
 int cbfnmpc_comm_unique_id(void *id128);
 int cbfnmpc_comm_init(cbfnmpc_ctx *ctx, int nranks, int rank, const void *id128);
 int cbfnmpc_comm_destroy(cbfnmpc_ctx *ctx);
 int cbfnmpc_ext_solve_sharded(cbfnmpc_ctx *ctx, int n_teams, const cbfnmpc_ext_cfg *cfg, const cbfnmpc_ext_in *in,
                               const cbfnmpc_ext_out *out, cbfnmpc_ext_stats *stats, void *cuda_stream);
+/* The same teams, same arguments and same answers, with the exchange INSIDE one launch: every member stores its published block
+ * straight into mailboxes in the memory of the ranks that hold its team mates (peer memory over NVLink, mapped once through CUDA
+ * IPC) and waits on per-(member, team) sequence flags in its own -- no launch and no collective between the interior-point
+ * iterations.  Collective over the communicator like cbfnmpc_ext_solve_sharded; synchronises the stream before it returns.  Needs
+ * every CTA of the launch resident at once (about 4700 instances of config 4 per B200) and peer access between the ranks; where
+ * either is missing it runs cbfnmpc_ext_solve_sharded instead (stats->fused tells which). */
+int cbfnmpc_ext_solve_fused(cbfnmpc_ctx *ctx, int n_teams, const cbfnmpc_ext_cfg *cfg, const cbfnmpc_ext_in *in,
+                            const cbfnmpc_ext_out *out, cbfnmpc_ext_stats *stats, void *cuda_stream);
 
 /* FP64 DFMA peak microbenchmark (TFLOP/s) used as the roofline denominator by bench.py */
 int cbfnmpc_measure_fp64_peak(cbfnmpc_ctx *ctx, double *tflops);

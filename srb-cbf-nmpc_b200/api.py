@@ -57,6 +57,8 @@ def load():
     L.cbfnmpc_comm_destroy.argtypes = [C.c_void_p]
     L.cbfnmpc_ext_solve_sharded.argtypes = [C.c_void_p, C.c_int, C.POINTER(capi.ExtCfg), C.POINTER(capi.ExtIn), C.POINTER(capi.ExtOut),
                                             C.POINTER(capi.ExtStats), C.c_void_p]
+    L.cbfnmpc_ext_solve_fused.argtypes = [C.c_void_p, C.c_int, C.POINTER(capi.ExtCfg), C.POINTER(capi.ExtIn), C.POINTER(capi.ExtOut),
+                                          C.POINTER(capi.ExtStats), C.c_void_p]
     L.cbfnmpc_pack_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
     _lib = L
     return L
@@ -67,7 +69,7 @@ EXPORTS = ["cbfnmpc_version", "cbfnmpc_last_error", "cbfnmpc_default_gains", "cb
            "cbfnmpc_launch_count", "cbfnmpc_last_kernel_ms", "cbfnmpc_set_kernel_timing", "cbfnmpc_solve_dense_nlptuple", "cbfnmpc_measure_fp64_peak",
            "cbfnmpc_pack_inputs", "cbfnmpc_run_cycle", "cbfnmpc_closed_loop", "cbfnmpc_generate_reference", "cbfnmpc_qp_dense_batch",
            "cbfnmpc_team_states", "cbfnmpc_pack_dense", "cbfnmpc_ext_default_cfg", "cbfnmpc_ext_solve_batch", "cbfnmpc_ext_solve_batch_host",
-           "cbfnmpc_comm_unique_id", "cbfnmpc_comm_init", "cbfnmpc_comm_destroy", "cbfnmpc_ext_solve_sharded"]
+           "cbfnmpc_comm_unique_id", "cbfnmpc_comm_init", "cbfnmpc_comm_destroy", "cbfnmpc_ext_solve_sharded", "cbfnmpc_ext_solve_fused"]
 
 
 def default_gains():
@@ -246,7 +248,17 @@ class BatchSolver:
         st = capi.ExtStats()
         self._ck(self.L.cbfnmpc_ext_solve_sharded(self.ctx, n_teams, C.byref(cfg), C.byref(si), C.byref(so), C.byref(st), stream))
         return dict(launches=st.launches, iterations=st.iterations, exchanges=st.exchanges, nranks=st.nranks,
-                    bytes_per_exchange=st.bytes_per_exchange, total_ms=st.total_ms)
+                    bytes_per_exchange=st.bytes_per_exchange, total_ms=st.total_ms, fused=st.fused)
+
+    def ext_solve_fused(self, n_teams, in_ptrs, out_ptrs, n_obs, N=4, team_size=4, stream=None, **cfgkw):
+        """Agent-sharded teams with the exchange inside ONE launch (peer-memory mailboxes); same layout and answers as ext_solve_sharded,
+        which it falls back to where the launch cannot be resident at once or the ranks cannot map each other's memory (stats['fused'])."""
+        cfg = self.ext_cfg(N, team_size, **cfgkw)
+        si, so = self._ext_structs(in_ptrs, out_ptrs, n_obs)
+        st = capi.ExtStats()
+        self._ck(self.L.cbfnmpc_ext_solve_fused(self.ctx, n_teams, C.byref(cfg), C.byref(si), C.byref(so), C.byref(st), stream))
+        return dict(launches=st.launches, iterations=st.iterations, exchanges=st.exchanges, nranks=st.nranks,
+                    bytes_per_exchange=st.bytes_per_exchange, total_ms=st.total_ms, fused=st.fused)
 
     def launch_count(self):
         return int(self.L.cbfnmpc_launch_count(self.ctx))

@@ -122,7 +122,7 @@ class ExtOut(C.Structure):
 
 class ExtStats(C.Structure):
     _fields_ = [("launches", C.c_int), ("iterations", C.c_int), ("exchanges", C.c_int), ("nranks", C.c_int), ("bytes_per_exchange", C.c_longlong),
-                ("total_ms", C.c_float)]
+                ("total_ms", C.c_float), ("fused", C.c_int)]
 
 
 def ext_out_rows(N):

@@ -367,6 +367,9 @@ struct cbfnmpc_ctx {
   int *x_active, *x_active_h;
   cudaEvent_t x_ev[2], x_t0, x_t1;
   void* comm; int comm_size, comm_rank;
+  // cbfnmpc_ext_solve_fused: own mailbox, the mailboxes of the communicator's ranks mapped into this process (CUDA IPC; f_peer[rank] ==
+  // f_mbox), control words {error, largest team iteration count}, a few doubles for the handle exchange / the start barrier
+  double* f_mbox; size_t f_mbox_cap; double* f_peer[8]; int* f_ctl; double* f_bar; bool f_disabled;
   // small host-buffer batches (<= small_cap instances): one pinned block up, one down (see solve_small)
   int small_cap;
   unsigned char *h_sin, *h_sout, *d_sin, *d_sout;
@@ -443,6 +446,8 @@ void cbfnmpc_destroy(cbfnmpc_ctx* c) {
   cudaFree(c->d_sin); cudaFree(c->d_sout); cudaFreeHost(c->h_sin); cudaFreeHost(c->h_sout);
   cbfnmpc_comm_destroy(c);
   cudaFree(c->x_perm); cudaFree(c->x_in); cudaFree(c->x_out); cudaFree(c->x_int); cudaFree(c->x_state); cudaFree(c->x_pub);
+  for (int r = 0; r < 8; r++) if (c->f_peer[r] && c->f_peer[r] != c->f_mbox) cudaIpcCloseMemHandle(c->f_peer[r]);
+  cudaFree(c->f_mbox); cudaFree(c->f_ctl); cudaFree(c->f_bar);
   if (c->x_active) { cudaFree(c->x_active); cudaFreeHost(c->x_active_h); cudaEventDestroy(c->x_ev[0]); cudaEventDestroy(c->x_ev[1]); cudaEventDestroy(c->x_t0); cudaEventDestroy(c->x_t1); }
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_last);
   for (int k = 1; k < CBF_MAX_CHUNKS; k++) cudaStreamDestroy(c->cstream[k]);

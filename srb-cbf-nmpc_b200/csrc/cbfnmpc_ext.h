@@ -59,6 +59,14 @@ struct ExtIO {
                          //    holds members member0 .. of every team, member-major: instance b = (member - member0) * n_teams + team
   const double* gathered;
   int n_teams, member0;
+  // xmode 4 (cbfnmpc_ext_solve_fused): as xmode 3, but ONE launch for the whole solve -- every member writes its published block
+  // straight into the mailboxes of all ranks of its team's group (peer memory over NVLink: mbox[r] is rank r's mailbox mapped into
+  // this process; own rank included) and waits on per-(member, team) sequence flags in its OWN mailbox: no launch and no collective
+  // between the iterations.  Mailbox: double [2 parities][T members][2N + 2 rows][n_teams], then int flags [2][T][n_teams].
+  double* mbox[8];
+  int n_grp;             // ranks of the group (<= 8)
+  int* fused_err;        // set when a wait ran into the watchdog (a peer that never published)
+  int* fused_its;        // atomicMax of the team iteration counts
   int phase;             // 0: whole solve in one launch.  Resumable (xmode 2, an all-gather between launches): 1: QP stage, publish, save;
                          // 2: NLP start, publish, save; 3: one iteration, publish, save; 4: store the outputs
   int n_run;
@@ -1229,7 +1237,31 @@ XDEV void ext_restore(const ExtIO& io, int b, int npriv, XSolver<C, W>& S, XCarr
   cy.team_it = (int)r[(q++) * sd]; S.mu_age = (int)r[(q++) * sd];
 }
 
-template <int C, int W>
+#ifndef CBF_HOST_EMU
+#define XFUSED_WATCHDOG 40000000000ll   // cycles (~20 s) a member waits for a neighbour's flag before it gives up
+XDEV int x_ld_flag(const int* p) { int v; asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+XDEV void x_st_flag(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+XDEV double x_ld_peer(const double* p) { double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
+XDEV void x_st_peer(double* p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+XDEV void x_fence_sys() { __threadfence_system(); }
+XDEV long long x_clock() { return clock64(); }
+XDEV void x_sleep() { __nanosleep(200); }
+XDEV void x_atomic_max(int* p, int v) { atomicMax(p, v); }
+XDEV int x_atomic_exch(int* p, int v) { return atomicExch(p, v); }
+#else
+#define XFUSED_WATCHDOG 4000000000ll
+XDEV int x_ld_flag(const int* p) { return *(volatile const int*)p; }
+XDEV void x_st_flag(int* p, int v) { *(volatile int*)p = v; }
+XDEV double x_ld_peer(const double* p) { return *(volatile const double*)p; }
+XDEV void x_st_peer(double* p, double v) { *(volatile double*)p = v; }
+XDEV void x_fence_sys() { }
+XDEV long long x_clock() { return 0; }
+XDEV void x_sleep() { }
+XDEV void x_atomic_max(int* p, int v) { if (v > *p) *p = v; }
+XDEV int x_atomic_exch(int* p, int v) { const int o = *p; *p = v; return o; }
+#endif
+
+template <int C, int W, bool FUSED = false>
 XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, XPriv pr) {
   typedef XDims<C> d;
   constexpr int NW = d::NW;
@@ -1298,8 +1330,8 @@ XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, X
     ext_restore<C, W>(io, b, npriv, S, cy);
   }
   const bool resumable = io.phase != 0;
-  const int tix = (io.xmode == 3) ? b % io.n_teams : b;                  // team index / column inside a member block
-  const int mloc = (io.xmode == 3) ? b / io.n_teams : 0;                // member block of this launch
+  const int tix = (io.xmode >= 3) ? b % io.n_teams : b;                  // team index / column inside a member block
+  const int mloc = (io.xmode >= 3) ? b / io.n_teams : 0;                // member block of this launch
   const size_t mstride = (size_t)(2 * W + 2) * (size_t)io.n_teams;      // one member block of the published trajectories
   auto write_pub = [&](int stepped, double mv) {   // send buffer: positions, then (stepped, moved) of the iteration just done
     if (!valid || !io.pub) return;
@@ -1314,7 +1346,60 @@ XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, X
   };
   if (io.phase == 1) { write_pub(1, 0.0); if (valid) ext_save<C, W>(io, b, npriv, S, cy); return; }
   double nbx[3] = {0.0, 0.0, 0.0}, nby[3] = {0.0, 0.0, 0.0};
+  // ---- xmode 4 (FUSED): published blocks go straight into the mailboxes of the group's ranks; sequence flags instead of a collective
+  int fseq = 0; bool fst = false; double fmv = 0.0;   // publications so far; neighbours' "stepped" / "distance still to go" of the last exchange
+  const int t_all = io.n_nbr + 1;
+  const size_t fl_off = (size_t)2 * t_all * mstride;   // flags follow the two parities of member blocks
+  auto fused_pub = [&](int stepped, double mv) {
+    fseq++;
+    const int par = fseq & 1, a = io.member0 + mloc;
+    if (valid) {
+      const size_t off = (size_t)(par * t_all + a) * mstride, pl = (size_t)io.n_teams;
+      for (int r = 0; r < io.n_grp; r++) {
+        double* pb = io.mbox[r] + off;
+        x_st_peer(pb + (size_t)(2 * j) * pl + tix, cy.pubx); x_st_peer(pb + (size_t)(2 * j + 1) * pl + tix, cy.puby);
+        if (j == 0) { x_st_peer(pb + (size_t)(2 * W) * pl + tix, (double)stepped); x_st_peer(pb + (size_t)(2 * W + 1) * pl + tix, mv); }
+      }
+      x_fence_sys();
+    }
+    (void)g_all(g, true);   // every lane of the instance has written and fenced its rows before lane 0 raises the flags
+    if (valid && j == 0) {
+      for (int r = 0; r < io.n_grp; r++) {
+        int* fl = reinterpret_cast<int*>(io.mbox[r] + fl_off);
+        x_st_flag(fl + (size_t)(par * t_all + a) * io.n_teams + tix, fseq);
+      }
+    }
+  };
+  auto fused_exchange = [&]() {   // wait for publication number fseq of every neighbour, then read it from the own mailbox
+    bool timed_out = false;
+    fst = false; fmv = 0.0;
+    if (valid) {
+      const int par = fseq & 1, a = io.member0 + mloc;
+      const double* loc = io.mbox[io.member0 / (t_all / io.n_grp)];   // this rank's own mailbox (ranks hold t_all / n_grp members each)
+      const int* fl = reinterpret_cast<const int*>(loc + fl_off);
+      const size_t pl = (size_t)io.n_teams;
+      for (int i = 0; i < io.n_nbr; i++) {
+        const int bb = i < a ? i : i + 1;
+        const int* f = fl + (size_t)(par * t_all + bb) * io.n_teams + tix;
+        const long long t0 = x_clock();
+        while (x_ld_flag(f) < fseq) {   // (a member with a bad contact pattern is published "for good" by the classify kernel: INT_MAX)
+          x_sleep();
+          if (x_clock() - t0 > XFUSED_WATCHDOG || x_ld_flag(io.fused_err) != 0) { timed_out = true; break; }
+        }
+        const double* nb = loc + (size_t)(par * t_all + bb) * mstride;
+        nbx[i] = x_ld_peer(nb + (size_t)(2 * j) * pl + tix); nby[i] = x_ld_peer(nb + (size_t)(2 * j + 1) * pl + tix);
+        fst = fst || x_ld_peer(nb + (size_t)(2 * W) * pl + tix) != 0.0;
+        fmv = fmax(fmv, x_ld_peer(nb + (size_t)(2 * W + 1) * pl + tix));
+      }
+    }
+    if (g_any(g, timed_out)) {   // a neighbour never published: give up (the host reports the error), leave the loops
+      if (valid && j == 0) x_atomic_exch(io.fused_err, 1);
+      cy.team_done = 1; cy.fin = 1; fst = false; fmv = 0.0;
+    }
+  };
+  if (FUSED) fused_pub(1, 0.0);   // the QP positions (phase 1 of the resumable path)
   auto exchange = [&]() {
+    if (FUSED) { fused_exchange(); return; }
     if (io.xmode == 1) {
       for (int i = 0; i < io.n_nbr; i++) { const int bb = i < g.a ? i : i + 1; nbx[i] = t_from(g, cy.pubx, bb); nby[i] = t_from(g, cy.puby, bb); }
     } else if (io.xmode == 2 && valid) {
@@ -1341,14 +1426,17 @@ XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, X
       cy.team_it = -1; cy.stepped_prev = 1;
       write_pub(1, 0.0); if (valid) ext_save<C, W>(io, b, npriv, S, cy); return;
     }
+    if (FUSED) { cy.team_it = -1; cy.stepped_prev = 1; fused_pub(1, 0.0); }   // as phase 2: same counts as the resumable path
   }
   // ---- iterations: [exchange; team finished (flags of the previous iteration)?; iterate; publish]
-  bool first = io.phase == 0;
+  bool first = io.phase == 0 && !FUSED;
   if (io.phase != 4) for (;;) {
     exchange();
     if (!first && !cy.team_done) {
       bool more;
-      if (io.xmode == 1) {
+      if (FUSED) {
+        more = (cy.stepped_prev != 0 || fst) || fmax(cy.moved_prev, fmv) > XP.pub_tol;
+      } else if (io.xmode == 1) {
         more = t_any(g, cy.stepped_prev != 0) || t_max(g, cy.moved_prev, io.T) > XP.pub_tol;
       } else if (io.xmode == 3) {
         bool st = cy.stepped_prev != 0; double mv = cy.moved_prev;
@@ -1374,6 +1462,7 @@ XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, X
     }
     cy.stepped_prev = stepped; cy.moved_prev = cy.moved;
     if (!cy.team_done) publish();
+    if (FUSED) fused_pub(stepped, cy.moved_prev);
     if (resumable) {
       write_pub(stepped, cy.moved_prev);
       if (valid && !cy.team_done && j == 0 && io.n_active) atomicAdd_int(io.n_active, 1);
@@ -1385,6 +1474,7 @@ XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, X
   if (cy.badin) { ext_store_bad<C, W>(io, b, j); return; }
   const double abuf_j = cy.abuf_j, pubx = cy.pubx, puby = cy.puby;
   const int team_it = cy.team_it;
+  if (FUSED && j == 0 && io.fused_its) x_atomic_max(io.fused_its, team_it);
   // ---- store
   if (io.X) { XUNR for (int i = 0; i < 4; i++) io.X[(size_t)(4 * j + i) * ld + b] = S.x.xs[i]; }
   if (io.U) { XUNR for (int a = 0; a < 2; a++) io.U[(size_t)(2 * j + a) * ld + b] = S.x.us[a]; }
@@ -1419,6 +1509,28 @@ XDEV void ext_run_group(const XParams& XP, const ExtIO& io, int b, bool valid, X
     if (io.nlp_iters) io.nlp_iters[b] = S.nlp_iters;
     if (io.team_iters) io.team_iters[b] = team_it;
   }
+}
+
+// xmode 4: an instance that no lane will run (bad contact pattern, status 4) still has team mates waiting for its publications: the
+// classify kernel publishes it once and for all -- its measured position at every grid point, "did not step", nothing left to go --
+// into both parities of every mailbox of the group, with flags that satisfy every wait.
+XDEV void ext_fused_publish_bad(const ExtIO& io, int b) {
+  const int W = io.N, t_all = io.n_nbr + 1;
+  const int tix = b % io.n_teams, a = io.member0 + b / io.n_teams;
+  const size_t mstride = (size_t)(2 * W + 2) * (size_t)io.n_teams, pl = (size_t)io.n_teams, ld = (size_t)io.ld;
+  const double px = io.x0[b], py = io.x0[2 * ld + b];
+  for (int r = 0; r < io.n_grp; r++)
+    for (int par = 0; par < 2; par++) {
+      double* pb = io.mbox[r] + (size_t)(par * t_all + a) * mstride;
+      for (int k = 0; k < W; k++) { x_st_peer(pb + (size_t)(2 * k) * pl + tix, px); x_st_peer(pb + (size_t)(2 * k + 1) * pl + tix, py); }
+      x_st_peer(pb + (size_t)(2 * W) * pl + tix, 0.0); x_st_peer(pb + (size_t)(2 * W + 1) * pl + tix, 0.0);
+    }
+  x_fence_sys();
+  for (int r = 0; r < io.n_grp; r++)
+    for (int par = 0; par < 2; par++) {
+      int* fl = reinterpret_cast<int*>(io.mbox[r] + (size_t)2 * t_all * mstride);
+      x_st_flag(fl + (size_t)(par * t_all + a) * io.n_teams + tix, 0x7fffffff);
+    }
 }
 
 // contact pattern -> number of stance feet (4, 2 or -1) of a TEAM: every member must have the same pattern class

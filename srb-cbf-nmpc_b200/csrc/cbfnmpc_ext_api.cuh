@@ -190,6 +190,13 @@ int cbfnmpc_ext_solve_batch_host(cbfnmpc_ctx* c, int B, const cbfnmpc_ext_cfg* c
   return CBFNMPC_OK;
 }
 
+// mailboxes of cbfnmpc_ext_solve_fused: unmap the peers', free the own one (the next fused call sets them up again)
+static void ext_fused_release(cbfnmpc_ctx* c) {
+  for (int r = 0; r < 8; r++) { if (c->f_peer[r] && c->f_peer[r] != c->f_mbox) cudaIpcCloseMemHandle(c->f_peer[r]); c->f_peer[r] = nullptr; }
+  if (c->f_mbox) cudaFree(c->f_mbox);
+  c->f_mbox = nullptr; c->f_mbox_cap = 0; c->f_disabled = false;
+}
+
 // ---- agent-sharded teams: the path's one collective
 int cbfnmpc_comm_unique_id(void* id128) {
   if (!id128) return fail(CBFNMPC_ERR_ARG, "null argument");
@@ -206,6 +213,7 @@ int cbfnmpc_comm_init(cbfnmpc_ctx* c, int nranks, int rank, const void* id128) {
   if (rc) return rc;
   CK(cudaSetDevice(c->device));
   if (c->comm) { g_nccl.CommDestroy((xnccl_comm)c->comm); c->comm = nullptr; }
+  CK(cudaStreamSynchronize(c->stream)); ext_fused_release(c);
   xnccl_uid u; memcpy(u.internal, id128, 128);
   xnccl_comm cm = nullptr;
   NK(g_nccl.CommInitRank(&cm, nranks, u, rank));
@@ -215,6 +223,7 @@ int cbfnmpc_comm_init(cbfnmpc_ctx* c, int nranks, int rank, const void* id128) {
 int cbfnmpc_comm_destroy(cbfnmpc_ctx* c) {
   if (!c) return fail(CBFNMPC_ERR_ARG, "null argument");
   if (c->comm && g_nccl.h) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); g_nccl.CommDestroy((xnccl_comm)c->comm); }
+  cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); ext_fused_release(c);
   c->comm = nullptr; c->comm_size = 1; c->comm_rank = 0;
   return CBFNMPC_OK;
 }
@@ -281,7 +290,121 @@ int cbfnmpc_ext_solve_sharded(cbfnmpc_ctx* c, int n_teams, const cbfnmpc_ext_cfg
     CK(cudaEventSynchronize(c->x_t1));
     float ms = 0.0f; CK(cudaEventElapsedTime(&ms, c->x_t0, c->x_t1));
     stats->launches = it + 3; stats->iterations = done_at >= 0 ? done_at + 1 : it; stats->exchanges = it + 2;
-    stats->bytes_per_exchange = (long long)(sizeof(double) * n_pub); stats->total_ms = ms; stats->nranks = G;
+    stats->bytes_per_exchange = (long long)(sizeof(double) * n_pub); stats->total_ms = ms; stats->nranks = G; stats->fused = 0;
   }
   return ctx_leave(c, st);
 }
+
+// ---- the same teams with the exchange INSIDE one launch: peer-memory mailboxes instead of a collective per iteration
+// Collective over the communicator (every rank calls it with the same sizes).  Mailbox of a rank: [2 parities][T members][2N + 2
+// rows][n_teams] doubles + [2][T][n_teams] int flags; the ranks exchange CUDA IPC handles of their mailboxes once (through the
+// library's own ncclAllGather) and map each other's.  Returns with c->f_disabled set -- on EVERY rank -- when some rank could not map
+// a peer (the caller then uses the per-iteration path).
+static int ext_fused_setup(cbfnmpc_ctx* c, size_t need, cudaStream_t st) {
+  const int G = c->comm ? c->comm_size : 1, rank = c->comm ? c->comm_rank : 0;
+  if (G > 8) { c->f_disabled = true; return CBFNMPC_OK; }
+  if (!c->f_ctl) { CK(cudaMalloc(&c->f_ctl, sizeof(int) * 4)); CK(cudaMalloc(&c->f_bar, sizeof(double) * 16 * 9)); }
+  if (c->f_mbox && need <= c->f_mbox_cap) return CBFNMPC_OK;
+  CK(cudaStreamSynchronize(st));
+  ext_fused_release(c);
+  CK(cudaMalloc(&c->f_mbox, sizeof(double) * need)); c->f_mbox_cap = need;
+  CK(cudaMemset(c->f_mbox, 0, sizeof(double) * need));
+  c->f_peer[rank] = c->f_mbox;
+  if (G == 1) return CBFNMPC_OK;
+  // handles: 64 bytes = 8 doubles per rank, slot 0 = own, slots 1 .. G = gathered
+  cudaIpcMemHandle_t h, all[8];
+  bool ok = cudaIpcGetMemHandle(&h, c->f_mbox) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); memset(&h, 0, sizeof(h)); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  CK(cudaMemcpyAsync(c->f_bar, &h, 64, cudaMemcpyHostToDevice, st));
+  NK(g_nccl.AllGather(c->f_bar, c->f_bar + 8, 8, XNCCL_DOUBLE, (xnccl_comm)c->comm, st));
+  CK(cudaMemcpyAsync(all, c->f_bar + 8, 64 * (size_t)G, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int r = 0; r < G && ok; r++) {
+    if (r == rank) continue;
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    c->f_peer[r] = (double*)p;
+  }
+  // did everybody get there?
+  const double mine = ok ? 1.0 : 0.0; double oks[8];
+  CK(cudaMemcpyAsync(c->f_bar, &mine, sizeof(double), cudaMemcpyHostToDevice, st));
+  NK(g_nccl.AllGather(c->f_bar, c->f_bar + 8, 1, XNCCL_DOUBLE, (xnccl_comm)c->comm, st));
+  CK(cudaMemcpyAsync(oks, c->f_bar + 8, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int r = 0; r < G; r++) if (oks[r] == 0.0) ok = false;
+  if (!ok) { ext_fused_release(c); c->f_disabled = true; }
+  return CBFNMPC_OK;
+}
+
+int cbfnmpc_ext_solve_fused(cbfnmpc_ctx* c, int n_teams, const cbfnmpc_ext_cfg* cfg, const cbfnmpc_ext_in* in, const cbfnmpc_ext_out* out,
+                            cbfnmpc_ext_stats* stats, void* cuda_stream) {
+  if (!c || !cfg) return fail(CBFNMPC_ERR_ARG, "null argument");
+  const int T = cfg->team_size, G = c->comm ? c->comm_size : 1, rank = c->comm ? c->comm_rank : 0;
+  if (T < 2 || T > 4 || T % G != 0) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_ext_solve_fused: team_size (2 .. 4) must be a multiple of the communicator's size");
+  const int mpr = T / G, B = mpr * n_teams;
+  int rc = ext_check(c, B, cfg, in, out, 1);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  const int N = cfg->N, n_nbr = T - 1, K = in->n_obs + n_nbr;
+  // every CTA must be resident at once: a member waits for members that run in other CTAs, here and on the peers
+  const size_t smem = sizeof(double) * (size_t)ext_npriv(K) * XNT;
+  const int tpw = XNT / N, items = (B + tpw - 1) / tpw + 1;
+  int per_sm = 0;
+  if (smem <= 227 * 1024) {
+    if (N == 4) { CK(cudaFuncSetAttribute(cbfnmpc_ext_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbfnmpc_ext_fused_kernel<4>, XNT, smem)); }
+    else { CK(cudaFuncSetAttribute(cbfnmpc_ext_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbfnmpc_ext_fused_kernel<8>, XNT, smem)); }
+  }
+  const size_t blk = (size_t)(2 * N + 2) * n_teams;
+  const size_t need = 2 * (size_t)T * blk + ((size_t)2 * T * n_teams + 1) / 2 + 2;
+  bool fused = items <= per_sm * c->sm_count && !c->f_disabled;
+  if (fused) {   // (the capacity test has the same outcome on every rank: same sizes, same devices)
+    rc = ext_fused_setup(c, need, st);
+    if (rc) return rc;
+    fused = !c->f_disabled;
+  }
+  if (!fused) {
+    rc = cbfnmpc_ext_solve_sharded(c, n_teams, cfg, in, out, stats, cuda_stream);
+    if (stats) stats->fused = 0;
+    return rc;
+  }
+  if (!c->x_active) { CK(cudaMalloc(&c->x_active, sizeof(int) * 2)); CK(cudaHostAlloc(&c->x_active_h, sizeof(int) * 2, cudaHostAllocDefault)); CK(cudaEventCreateWithFlags(&c->x_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->x_ev[1], cudaEventDisableTiming)); CK(cudaEventCreate(&c->x_t0)); CK(cudaEventCreate(&c->x_t1)); }
+  ExtIO io;
+  ext_fill_io(&io, B, B, cfg, in, out);
+  io.n_teams = n_teams; io.member0 = rank * mpr;
+  io.T = 1; io.n_nbr = n_nbr; io.xmode = 4; io.phase = 0;
+  for (int r = 0; r < G; r++) io.mbox[r] = c->f_peer[r];
+  io.n_grp = G; io.fused_err = c->f_ctl; io.fused_its = c->f_ctl + 1;
+  XParams XP; ext_xparams(c, cfg, &XP);
+  rc = ext_perm(c, B, st);
+  if (rc) return rc;
+  rc = ctx_enter(c, st);
+  if (rc) return rc;
+  // own flags and control words to zero, then a barrier over the communicator: nobody writes into a mailbox before its owner has
+  // cleared it, and nobody starts before everybody has finished the previous call
+  CK(cudaMemsetAsync(c->f_mbox + 2 * (size_t)T * blk, 0, sizeof(int) * 2 * (size_t)T * n_teams, st));
+  CK(cudaMemsetAsync(c->f_ctl, 0, sizeof(int) * 4, st));
+  if (G > 1) NK(g_nccl.AllGather(c->f_bar, c->f_bar + 8, 1, XNCCL_DOUBLE, (xnccl_comm)c->comm, st));
+  CK(cudaEventRecord(c->x_t0, st));
+  int* perm = c->x_perm; int* counts = perm + 2 * (size_t)B;
+  cbfnmpc_ext_classify_kernel<<<1, 1024, 0, st>>>(io, B, perm, counts);
+  CK(cudaGetLastError());
+  if (N == 4) cbfnmpc_ext_fused_kernel<4><<<items, XNT, smem, st>>>(XP, io, B, perm, counts);
+  else cbfnmpc_ext_fused_kernel<8><<<items, XNT, smem, st>>>(XP, io, B, perm, counts);
+  CK(cudaGetLastError());
+  c->launches += 2;
+  CK(cudaEventRecord(c->x_t1, st));
+  int ctl[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(ctl, c->f_ctl, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (stats) {
+    float ms = 0.0f; CK(cudaEventElapsedTime(&ms, c->x_t0, c->x_t1));
+    stats->launches = 2; stats->iterations = ctl[1] + 1; stats->exchanges = ctl[1] + 3;
+    stats->bytes_per_exchange = (long long)(sizeof(double) * blk * mpr) * (G - 1); stats->total_ms = ms; stats->nranks = G; stats->fused = 1;
+  }
+  rc = ctx_leave(c, st);
+  if (ctl[0] != 0) return fail(CBFNMPC_ERR_CUDA, "cbfnmpc_ext_solve_fused: a member waited in vain for a neighbour's publication (watchdog)");
+  return rc;
+}
+

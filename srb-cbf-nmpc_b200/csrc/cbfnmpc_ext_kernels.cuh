@@ -15,7 +15,10 @@ __global__ void __launch_bounds__(1024, 1) cbfnmpc_ext_classify_kernel(const __g
   for (int t0 = 0; t0 < n_teams; t0 += 1024) {
     const int t = t0 + threadIdx.x;
     const int cls = (t < n_teams) ? ext_classify_team(io, t) : 0;
-    if (t < n_teams && cls < 0) { for (int m = 0; m < io.T; m++) ext_store_bad<4, 4>(io, t * io.T + m, 0); }
+    if (t < n_teams && cls < 0) {
+      for (int m = 0; m < io.T; m++) ext_store_bad<4, 4>(io, t * io.T + m, 0);
+      if (io.xmode == 4) ext_fused_publish_bad(io, t);   // its team mates (other CTAs, other GPUs) wait for its publications
+    }
     const unsigned m4 = __ballot_sync(0xffffffffu, cls == 4), m2 = __ballot_sync(0xffffffffu, cls == 2);
     if (lane == 0) { wcnt[0][warp] = __popc(m4); wcnt[1][warp] = __popc(m2); }
     __syncthreads();
@@ -59,3 +62,29 @@ __global__ void __launch_bounds__(XNT, 1) cbfnmpc_ext_kernel(const __grid_consta
     ext_run_group<2, W>(XP, io, valid ? perm[n_teams + slot] * io.T + member : 0, valid, pr);
   }
 }
+
+// The whole solve of agent-sharded teams in ONE launch (cbfnmpc_ext_solve_fused, io.xmode == 4): members publish into the mailboxes
+// of their group's ranks (peer memory) and wait on sequence flags.  Every CTA of the grid must be resident at once -- a member
+// waits for members that run in other CTAs, here and on the other GPUs -- which the host checks before it launches.
+template <int W>
+__global__ void __launch_bounds__(XNT, 1) cbfnmpc_ext_fused_kernel(const __grid_constant__ XParams XP, const __grid_constant__ ExtIO io, int n_teams,
+                                                                   const int* __restrict__ perm, const int* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = (int)threadIdx.x;
+  XPriv pr; pr.base = reinterpret_cast<double*>(smem_raw) + lane;
+  const int tpw = XNT / W;   // instances per warp (io.T == 1: every instance is its own "team" of the class lists)
+  const int n4 = counts[0], n2 = counts[1];
+  const int w4 = (n4 + tpw - 1) / tpw;
+  const int warp = (int)blockIdx.x;
+  if (warp < w4) {
+    const int slot = warp * tpw + lane / W;
+    const bool valid = slot < n4;
+    ext_run_group<4, W, true>(XP, io, valid ? perm[slot] : 0, valid, pr);
+  } else {
+    const int slot = (warp - w4) * tpw + lane / W;
+    if ((warp - w4) * tpw >= n2) return;
+    const bool valid = slot < n2;
+    ext_run_group<2, W, true>(XP, io, valid ? perm[n_teams + slot] : 0, valid, pr);
+  }
+}
+

@@ -140,6 +140,46 @@ def test_ext_sharded_path_on_one_gpu_equals_the_warp_path(pkg):
         s.close()
 
 
+def test_ext_fused_path_on_one_gpu_equals_the_sharded_path(pkg):
+    """cbfnmpc_ext_solve_fused without a communicator: the whole solve in ONE launch, the members of a team in different CTAs, their
+    published trajectories exchanged through the mailbox and its sequence flags (on several GPUs: through each other's memory).  Bit for
+    bit the answers, statuses and iteration counts of the per-iteration path; a member with a bad contact pattern does not stall its
+    team mates; a launch that cannot be resident at once runs the per-iteration path instead."""
+    import torch
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    dev = torch.device("cuda", 0)
+    for N, K, n_teams, bad in ((4, 1, 64, False), (8, 16, 16, False), (4, 1, 96, True), (4, 1, 2048, False)):
+        insts = S.cfg4_teams(n_teams, N=N, K_obs=K)
+        if bad:
+            a, b_, c_, d_, e = insts[4 * 5 + 2]; insts[4 * 5 + 2] = (a, b_, c_, [1, 0, 0, 0], e)   # member 2 of team 5: one foot
+        B = 4 * n_teams
+        s = pkg.BatchSolver(device=0, max_batch=B, max_obs=20)
+        mm = [insts[4 * t + m] for m in range(4) for t in range(n_teams)]           # member-major
+        d = capi.ext_soa_from_instances(mm, N)
+        tin = {k: torch.from_numpy(d[k]).to(dev) for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy", "alpha_buf")}
+        res = []
+        for fn in (s.ext_solve_sharded, s.ext_solve_fused, s.ext_solve_fused):
+            tout = {k: torch.zeros((n, B), dtype=torch.float64, device=dev) for k, n in capi.ext_out_rows(N).items() if k != "pub"}
+            tout.update({k: torch.zeros((1, B), dtype=torch.int32, device=dev) for k in capi.EXT_OUT_I32})
+            stats = fn(n_teams, {k: v.data_ptr() for k, v in tin.items()}, {k: v.data_ptr() for k, v in tout.items()}, d["n_obs"],
+                       N=N, team_size=4, eps_nbr=S.EPS_NBR)
+            torch.cuda.synchronize()
+            res.append((stats, {k: v.cpu().numpy() for k, v in tout.items()}))
+        (ss, so), (fs, fo), (fs2, fo2) = res
+        assert fs["fused"] == (0 if n_teams == 2048 else 1) and ss["fused"] == 0
+        keep = np.ones(B, bool)
+        if bad:
+            keep[[m * n_teams + 5 for m in range(4)]] = False      # the per-iteration path reads an unwritten block for that member
+            st = fo["status"][0]
+            assert st[2 * n_teams + 5] == 4 and (st[[m * n_teams + 5 for m in (0, 1, 3)]] != 4).all()
+        for k in so:
+            assert np.array_equal(so[k][..., keep], fo[k][..., keep]), (N, n_teams, k)
+            assert np.array_equal(fo[k], fo2[k]), (N, n_teams, k, "second call")
+        if fs["fused"]:
+            assert fs["launches"] == 2 and fs["iterations"] == fo["team_iters"][0].max() + 1
+        s.close()
+
+
 def test_ext_edge_inputs(pkg, solver):
     """Mixed stance classes inside a team and bad contact patterns (status 4 for the whole team), non-finite data of one member
     (that member status 4, the others still solve against its measured position; a non-finite POSITION would reach them as a NaN row), argument checks."""
