@@ -118,7 +118,8 @@ def extended_blocks(pkg, capi, S, SH, torch, dist, dev, local, rank, world, team
     oracle/cbfnmpc_oracle_ext.c.  Per GPU: teams_per_gpu four-robot teams.
       cfg4: N = 4, 1 obstacle + 3 neighbour rows per grid point -- (a) team-major: a team in one warp, exchange by shuffles, no
             collective; (b) agent-sharded: the members of a team on different GPUs (one GPU: different member blocks), one launch per
-            interior-point iteration and the library's own ncclAllGather of the published trajectories in between.
+            interior-point iteration and the library's own ncclAllGather of the published trajectories in between; (c) the same with
+            the exchange inside the launch (cbfnmpc_ext_solve_fused: peer-memory mailboxes and sequence flags, no collective).
       cfg5: N = 8, 16 obstacle + 3 neighbour rows per grid point, team-major.
     Times are device times (CUDA events recorded by the library on its launch stream), max over ranks; solves/s counts converged
     members only."""
@@ -186,6 +187,23 @@ def extended_blocks(pkg, capi, S, SH, torch, dist, dev, local, rank, world, team
                                     "iterations": stats["iterations"], "launches": stats["launches"], "exchanges": stats["exchanges"],
                                     "allgather_bytes_per_rank_and_iteration": stats["bytes_per_exchange"],
                                     "ms_per_iteration": t2 / max(stats["launches"], 1)}
+            # the same teams with the exchange inside the launch: peer-memory mailboxes (NVLink) + sequence flags, no collective
+            d3, ip3, op3, tin3, tout3 = device_batch(mine, N)
+            fstats = None
+            for _ in range(3):
+                if dist is not None: dist.barrier()
+                fstats = s2.ext_solve_fused(n_teams, ip2, op3, d2["n_obs"], N=N, team_size=T, eps_nbr=S.EPS_NBR)
+                torch.cuda.synchronize(dev)
+            same = all(torch.equal(tout2[k], tout3[k]) for k in tout2)
+            (t3, neq, ffl), _ = red([fstats["total_ms"], 0.0 if same else 1.0, -float(fstats["fused"])], [0])
+            blk["agent_sharded_fused"] = {"exchange": ("every member stores its published trajectory into the memory of the ranks that hold its team mates "
+                                                       "(CUDA IPC mapped peer memory over NVLink) and waits on sequence flags, inside the launch" if G > 1 else
+                                                       "one GPU: mailbox and sequence flags in the own memory (members of a team in different CTAs)"),
+                                          "in_one_launch_per_slice": bool(ffl == -1.0), "launches": fstats["launches"], "iterations": fstats["iterations"],
+                                          "ms_per_solve_of_all_teams": t3, "converged_solves_per_s": conv2 / (t3 * 1e-3),
+                                          "peer_bytes_per_rank_and_iteration": fstats["bytes_per_exchange"],
+                                          "ms_per_iteration": t3 / max(fstats["iterations"], 1),
+                                          "bit_identical_to_the_per_iteration_path": bool(neq == 0.0)}
             if G > 1: solver.comm_destroy()
             if s2 is not solver: s2.close()
         if cpu and rank == 0 and world == 1:

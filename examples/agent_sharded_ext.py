@@ -9,7 +9,9 @@ cbfnmpc_ext_solve_sharded calls ncclAllGather between its per-iteration launches
 
 World 2: each rank holds 2 members of every team; world 4: one member each; world 8: two groups of 4 ranks, each with its own teams.
 Rank 0 checks the gathered answers against the same teams solved team-major on its own GPU (members of a team in one warp,
-exchange by shuffles) and prints one JSON line."""
+exchange by shuffles) and prints one JSON line.  The same teams are then solved by cbfnmpc_ext_solve_fused -- the exchange inside
+ONE launch, members storing their published trajectories into each other's GPU memory (NVLink peer access) and waiting on sequence
+flags -- and compared bit for bit ("fused" block of the line)."""
 import json
 import os
 import sys
@@ -58,6 +60,21 @@ for rep in range(3):   # the last repetition is the one reported
     stats = solver.ext_solve_sharded(n_teams, ip, op, d["n_obs"], N=N, team_size=T, eps_nbr=S.EPS_NBR)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+# the same teams with the exchange inside ONE launch (cbfnmpc_ext_solve_fused: peer-memory mailboxes instead of a collective per
+# iteration); answers must be bit-identical to the per-iteration path's
+tout2 = {k: torch.zeros_like(v) for k, v in tout.items()}
+op2 = {k: v.data_ptr() for k, v in tout2.items()}
+fstats = None
+for rep in range(3):
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fstats = solver.ext_solve_fused(n_teams, ip, op2, d["n_obs"], N=N, team_size=T, eps_nbr=S.EPS_NBR)
+    torch.cuda.synchronize()
+    fwall = time.perf_counter() - t0
+same = all(torch.equal(tout[k], tout2[k]) for k in tout)
+ft = torch.tensor([fstats["total_ms"], fwall * 1e3, 0.0 if same else 1.0, float(fstats["fused"])], dtype=torch.float64, device=dev)
+fmax = ft.clone(); dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
+fmin = ft.clone(); dist.all_reduce(fmin, op=dist.ReduceOp.MIN)
 # collect (X, slack, status, team_iters) of every rank on rank 0
 pack = torch.cat([tout["X"], tout["slack"], tout["status"].double(), tout["team_iters"].double()]).contiguous()
 allp = [torch.empty_like(pack) for _ in range(world)]
@@ -86,7 +103,12 @@ if rank == 0:
                team_iters_equal=float((ti == ref["team_iters"][0])[ok].mean()), teams_compared=int(ok.sum() // T))
     conv = int((st == 0).sum()) * n_groups
     res["converged_solves_per_s"] = conv / (res["device_ms"] * 1e-3)
+    res["fused"] = dict(in_one_launch=bool(fmin[3] == 1.0), device_ms=float(fmax[0]), wall_ms=float(fmax[1]), launches=fstats["launches"],
+                        iterations=fstats["iterations"], peer_bytes_per_rank_and_iteration=fstats["bytes_per_exchange"],
+                        ms_per_iteration=float(fmax[0]) / max(fstats["iterations"], 1), converged_solves_per_s=conv / (float(fmax[0]) * 1e-3),
+                        bit_identical_to_the_per_iteration_path=bool(fmax[2] == 0.0))
     print(json.dumps(res))
     assert res["status_equal"] == 1.0 and res["max_abs_diff_X"] < 1e-9, res
+    assert res["fused"]["bit_identical_to_the_per_iteration_path"], res["fused"]
 solver.comm_destroy()
 dist.barrier(); dist.destroy_process_group()

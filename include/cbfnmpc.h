@@ -295,9 +295,10 @@ int cbfnmpc_ext_solve_sharded(cbfnmpc_ctx *ctx, int n_teams, const cbfnmpc_ext_c
 /* The same teams, same arguments and same answers, with the exchange INSIDE one launch: every member stores its published block
  * straight into mailboxes in the memory of the ranks that hold its team mates (peer memory over NVLink, mapped once through CUDA
  * IPC) and waits on per-(member, team) sequence flags in its own -- no launch and no collective between the interior-point
- * iterations.  Collective over the communicator like cbfnmpc_ext_solve_sharded; synchronises the stream before it returns.  Needs
- * every CTA of the launch resident at once (about 4700 instances of config 4 per B200) and peer access between the ranks; where
- * either is missing it runs cbfnmpc_ext_solve_sharded instead (stats->fused tells which). */
+ * iterations.  Collective over the communicator like cbfnmpc_ext_solve_sharded; synchronises the stream before it returns.  A
+ * launch must be resident at once (its members wait for each other): batches beyond that (about 4700 instances of config 4 per
+ * B200) run as a few launches over slices of the teams.  Needs peer access between the ranks; where that is missing it runs
+ * cbfnmpc_ext_solve_sharded instead (stats->fused tells which). */
 int cbfnmpc_ext_solve_fused(cbfnmpc_ctx *ctx, int n_teams, const cbfnmpc_ext_cfg *cfg, const cbfnmpc_ext_in *in,
                             const cbfnmpc_ext_out *out, cbfnmpc_ext_stats *stats, void *cuda_stream);
 

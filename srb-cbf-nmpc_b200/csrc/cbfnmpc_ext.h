@@ -65,6 +65,8 @@ struct ExtIO {
   // between the iterations.  Mailbox: double [2 parities][T members][2N + 2 rows][n_teams], then int flags [2][T][n_teams].
   double* mbox[8];
   int n_grp;             // ranks of the group (<= 8)
+  int slice_t0, slice_ns;   // this launch runs teams [slice_t0, slice_t0 + slice_ns) only (0, 0: all): a launch must be resident at once,
+                            // so a batch beyond that is solved in slices; item i of the class lists is instance (i / ns) n_teams + t0 + i % ns
   int* fused_err;        // set when a wait ran into the watchdog (a peer that never published)
   int* fused_its;        // atomicMax of the team iteration counts
   int phase;             // 0: whole solve in one launch.  Resumable (xmode 2, an all-gather between launches): 1: QP stage, publish, save;

@@ -350,7 +350,7 @@ int cbfnmpc_ext_solve_fused(cbfnmpc_ctx* c, int n_teams, const cbfnmpc_ext_cfg* 
   const int N = cfg->N, n_nbr = T - 1, K = in->n_obs + n_nbr;
   // every CTA must be resident at once: a member waits for members that run in other CTAs, here and on the peers
   const size_t smem = sizeof(double) * (size_t)ext_npriv(K) * XNT;
-  const int tpw = XNT / N, items = (B + tpw - 1) / tpw + 1;
+  const int tpw = XNT / N;
   int per_sm = 0;
   if (smem <= 227 * 1024) {
     if (N == 4) { CK(cudaFuncSetAttribute(cbfnmpc_ext_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbfnmpc_ext_fused_kernel<4>, XNT, smem)); }
@@ -358,7 +358,10 @@ int cbfnmpc_ext_solve_fused(cbfnmpc_ctx* c, int n_teams, const cbfnmpc_ext_cfg* 
   }
   const size_t blk = (size_t)(2 * N + 2) * n_teams;
   const size_t need = 2 * (size_t)T * blk + ((size_t)2 * T * n_teams + 1) / 2 + 2;
-  bool fused = items <= per_sm * c->sm_count && !c->f_disabled;
+  // teams per launch: what is resident at once (the class lists pad two classes: one spare CTA); larger batches run in slices of teams
+  const int cap_inst = (per_sm * c->sm_count - 2) * tpw;
+  const int ns_max = cap_inst / mpr;
+  bool fused = ns_max >= 1 && !c->f_disabled;
   if (fused) {   // (the capacity test has the same outcome on every rank: same sizes, same devices)
     rc = ext_fused_setup(c, need, st);
     if (rc) return rc;
@@ -387,20 +390,27 @@ int cbfnmpc_ext_solve_fused(cbfnmpc_ctx* c, int n_teams, const cbfnmpc_ext_cfg* 
   CK(cudaMemsetAsync(c->f_ctl, 0, sizeof(int) * 4, st));
   if (G > 1) NK(g_nccl.AllGather(c->f_bar, c->f_bar + 8, 1, XNCCL_DOUBLE, (xnccl_comm)c->comm, st));
   CK(cudaEventRecord(c->x_t0, st));
-  int* perm = c->x_perm; int* counts = perm + 2 * (size_t)B;
-  cbfnmpc_ext_classify_kernel<<<1, 1024, 0, st>>>(io, B, perm, counts);
-  CK(cudaGetLastError());
-  if (N == 4) cbfnmpc_ext_fused_kernel<4><<<items, XNT, smem, st>>>(XP, io, B, perm, counts);
-  else cbfnmpc_ext_fused_kernel<8><<<items, XNT, smem, st>>>(XP, io, B, perm, counts);
-  CK(cudaGetLastError());
-  c->launches += 2;
+  int n_launch = 0;
+  const int n_slices = (n_teams + ns_max - 1) / ns_max;
+  for (int k = 0; k < n_slices; k++) {   // (equal slices; a slice's teams are independent of every other slice's)
+    const int t0 = (int)((long long)n_teams * k / n_slices), t1 = (int)((long long)n_teams * (k + 1) / n_slices), ns = t1 - t0;
+    const int Bk = mpr * ns, items = (Bk + tpw - 1) / tpw + 1;
+    io.slice_t0 = t0; io.slice_ns = ns;
+    int* perm = c->x_perm; int* counts = perm + 2 * (size_t)Bk;
+    cbfnmpc_ext_classify_kernel<<<1, 1024, 0, st>>>(io, Bk, perm, counts);
+    CK(cudaGetLastError());
+    if (N == 4) cbfnmpc_ext_fused_kernel<4><<<items, XNT, smem, st>>>(XP, io, Bk, perm, counts);
+    else cbfnmpc_ext_fused_kernel<8><<<items, XNT, smem, st>>>(XP, io, Bk, perm, counts);
+    CK(cudaGetLastError());
+    c->launches += 2; n_launch += 2;
+  }
   CK(cudaEventRecord(c->x_t1, st));
   int ctl[4] = {0, 0, 0, 0};
   CK(cudaMemcpyAsync(ctl, c->f_ctl, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (stats) {
     float ms = 0.0f; CK(cudaEventElapsedTime(&ms, c->x_t0, c->x_t1));
-    stats->launches = 2; stats->iterations = ctl[1] + 1; stats->exchanges = ctl[1] + 3;
+    stats->launches = n_launch; stats->iterations = ctl[1] + 1; stats->exchanges = ctl[1] + 3;
     stats->bytes_per_exchange = (long long)(sizeof(double) * blk * mpr) * (G - 1); stats->total_ms = ms; stats->nranks = G; stats->fused = 1;
   }
   rc = ctx_leave(c, st);

@@ -13,9 +13,11 @@ __global__ void __launch_bounds__(1024, 1) cbfnmpc_ext_classify_kernel(const __g
   if (threadIdx.x < 2) base[threadIdx.x] = 0;
   __syncthreads();
   for (int t0 = 0; t0 < n_teams; t0 += 1024) {
-    const int t = t0 + threadIdx.x;
-    const int cls = (t < n_teams) ? ext_classify_team(io, t) : 0;
-    if (t < n_teams && cls < 0) {
+    const int ti = t0 + threadIdx.x;
+    // (fused runs in slices of teams, io.T == 1: item ti of this launch is instance t of the member-major batch)
+    const int t = (io.xmode == 4 && io.slice_ns > 0) ? (ti / io.slice_ns) * io.n_teams + io.slice_t0 + ti % io.slice_ns : ti;
+    const int cls = (ti < n_teams) ? ext_classify_team(io, t) : 0;
+    if (ti < n_teams && cls < 0) {
       for (int m = 0; m < io.T; m++) ext_store_bad<4, 4>(io, t * io.T + m, 0);
       if (io.xmode == 4) ext_fused_publish_bad(io, t);   // its team mates (other CTAs, other GPUs) wait for its publications
     }

@@ -144,7 +144,7 @@ def test_ext_fused_path_on_one_gpu_equals_the_sharded_path(pkg):
     """cbfnmpc_ext_solve_fused without a communicator: the whole solve in ONE launch, the members of a team in different CTAs, their
     published trajectories exchanged through the mailbox and its sequence flags (on several GPUs: through each other's memory).  Bit for
     bit the answers, statuses and iteration counts of the per-iteration path; a member with a bad contact pattern does not stall its
-    team mates; a launch that cannot be resident at once runs the per-iteration path instead."""
+    team mates; a batch that cannot be resident at once runs as launches over slices of the teams."""
     import torch
     from srb_cbf_nmpc_b200 import capi, scenarios as S
     dev = torch.device("cuda", 0)
@@ -166,7 +166,7 @@ def test_ext_fused_path_on_one_gpu_equals_the_sharded_path(pkg):
             torch.cuda.synchronize()
             res.append((stats, {k: v.cpu().numpy() for k, v in tout.items()}))
         (ss, so), (fs, fo), (fs2, fo2) = res
-        assert fs["fused"] == (0 if n_teams == 2048 else 1) and ss["fused"] == 0
+        assert fs["fused"] == 1 and ss["fused"] == 0
         keep = np.ones(B, bool)
         if bad:
             keep[[m * n_teams + 5 for m in range(4)]] = False      # the per-iteration path reads an unwritten block for that member
@@ -176,7 +176,7 @@ def test_ext_fused_path_on_one_gpu_equals_the_sharded_path(pkg):
             assert np.array_equal(so[k][..., keep], fo[k][..., keep]), (N, n_teams, k)
             assert np.array_equal(fo[k], fo2[k]), (N, n_teams, k, "second call")
         if fs["fused"]:
-            assert fs["launches"] == 2 and fs["iterations"] == fo["team_iters"][0].max() + 1
+            assert fs["launches"] == (4 if n_teams == 2048 else 2) and fs["iterations"] == fo["team_iters"][0].max() + 1
         s.close()
 
 
