@@ -306,6 +306,10 @@ static int ext_fused_setup(cbfnmpc_ctx* c, size_t need, cudaStream_t st) {
   if (!c->f_ctl) { CK(cudaMalloc(&c->f_ctl, sizeof(int) * 4)); CK(cudaMalloc(&c->f_bar, sizeof(double) * 16 * 9)); }
   if (c->f_mbox && need <= c->f_mbox_cap) return CBFNMPC_OK;
   CK(cudaStreamSynchronize(st));
+  // growing: every rank first unmaps its peers' mailboxes, then all meet, and only then does anybody free its own (an exporter must
+  // not free memory that an importer still has open)
+  for (int r = 0; r < 8; r++) { if (c->f_peer[r] && c->f_peer[r] != c->f_mbox) cudaIpcCloseMemHandle(c->f_peer[r]); c->f_peer[r] = nullptr; }
+  if (G > 1) { NK(g_nccl.AllGather(c->f_bar, c->f_bar + 8, 1, XNCCL_DOUBLE, (xnccl_comm)c->comm, st)); CK(cudaStreamSynchronize(st)); }
   ext_fused_release(c);
   CK(cudaMalloc(&c->f_mbox, sizeof(double) * need)); c->f_mbox_cap = need;
   CK(cudaMemset(c->f_mbox, 0, sizeof(double) * need));
