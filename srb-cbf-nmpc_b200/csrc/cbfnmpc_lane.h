@@ -1337,7 +1337,43 @@ struct LaneSolver {
 // One group = one run_NMPC(): load (updateState + planners' outputs), closest obstacle, QP stage, NLP stage,
 // Bezier epilogue, store.  Shared by the CUDA kernel and the tests/emu harness.
 // ===============================================================================================================
-template <int C>
+// LATE: the obstacles are looked at AFTER the QP stage (which does not use them) and only once io.obs_flag shows io.obs_seq -- the
+// host-buffer call uploads them on a second stream while the QP stage runs.  Same arithmetic, same answers.
+template <int C, bool LATE>
+LDEV bool lane_closest_obstacle(const BatchIO& io, const Grp& g, const Priv& pr, int b, double& ox, double& oy) {
+  typedef LaneDims<C> d;
+  const size_t B = (size_t)io.ld;
+  const int j = g.j;
+  if (LATE && io.obs_flag) {
+#ifndef CBF_HOST_EMU
+    long long t0 = clock64();
+    for (;;) {
+      int v; asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(io.obs_flag) : "memory");
+      if (v == io.obs_seq || clock64() - t0 > 20000000000ll) break;   // (10 s: the copy was never issued; the answers will say so)
+      __nanosleep(100);
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+#endif
+  }
+  // closest obstacle to the current position: first strict minimum of the Euclidean distance (MPC_dist.cpp:371-396)
+  const double px = pr(d::F_XIN + 0), py = pr(d::F_XIN + 2);
+  double best = 1000.0; int bi = 0x7fffffff;
+  for (int k = j; k < io.n_obs; k += 4) {
+    const double dx = px - io.obs[(size_t)k * B + b], dy = py - io.obs[(size_t)(io.n_obs + k) * B + b];
+    const double dd = sqrt(l_add_rn(l_mul_rn(dx, dx), l_mul_rn(dy, dy)));
+    if (dd < best) { best = dd; bi = k; }
+  }
+  LUNR for (int m = 1; m < 4; m <<= 1) {
+    const double ob = g_xor(g, best, m); const int oi = (int)g_xor_u(g, (unsigned)bi, m);
+    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (bi == 0x7fffffff) bi = 0;
+  ox = io.obs[(size_t)bi * B + b]; oy = io.obs[(size_t)(io.n_obs + bi) * B + b];
+  if (!LATE) return true;   // (the caller's own finiteness check covers them)
+  return g_all(g, 0.0 * ox + 0.0 * oy == 0.0);
+}
+
+template <int C, bool LATE = false>
 LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid, Priv pr, Pace pace = Pace()) {
   typedef LaneDims<C> d;
   constexpr int NW = d::NW;
@@ -1372,23 +1408,8 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
     LUNR for (int t = 0; t < 6; t++) S.c.D[t] = 0.0;
     LUNR for (int k = 0; k < 2; k++) LUNR for (int a = 0; a < NW; a++) S.c.D[k * NW + a] = F[4 * k + a] - F[4 * k + C - 1];
     S.c.qw = (j == 3) ? P.Pw : P.Qw;
-    // closest obstacle to the current position: first strict minimum of the Euclidean distance (MPC_dist.cpp:371-396)
     S.c.ox = 0.0; S.c.oy = 0.0;
-    if (io.mode == 1) {
-      const double px = pr(d::F_XIN + 0), py = pr(d::F_XIN + 2);
-      double best = 1000.0; int bi = 0x7fffffff;
-      for (int k = j; k < io.n_obs; k += 4) {
-        const double dx = px - io.obs[(size_t)k * B + b], dy = py - io.obs[(size_t)(io.n_obs + k) * B + b];
-        const double dd = sqrt(l_add_rn(l_mul_rn(dx, dx), l_mul_rn(dy, dy)));
-        if (dd < best) { best = dd; bi = k; }
-      }
-      LUNR for (int m = 1; m < 4; m <<= 1) {
-        const double ob = g_xor(g, best, m); const int oi = (int)g_xor_u(g, (unsigned)bi, m);
-        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (bi == 0x7fffffff) bi = 0;
-      S.c.ox = io.obs[(size_t)bi * B + b]; S.c.oy = io.obs[(size_t)(io.n_obs + bi) * B + b];
-    }
+    if (!LATE && io.mode == 1) (void)lane_closest_obstacle<C, false>(io, g, pr, b, S.c.ox, S.c.oy);
     // non-finite data (0 * v is 0 only for finite v) are answered with status 4 before anything is solved
     double chk = 0.0 * S.c.ox + 0.0 * S.c.oy;
     LUNR for (int i = 0; i < 4; i++) chk += 0.0 * pr(d::F_XDES + i) + 0.0 * pr(d::F_XIN + i);
@@ -1416,6 +1437,12 @@ LDEV void lane_run_group(const KParams& P, const BatchIO& io, int b, bool valid,
   }
   bool nl_done = true;
   g.mask = w_ballot_full(valid && !badin);
+  if (LATE && io.mode == 1) {   // the obstacles now (they were on their way during the QP stage); non-finite ones are bad input
+    bool late_bad = false;
+    if (valid && !badin) late_bad = !lane_closest_obstacle<C, true>(io, g, pr, b, S.c.ox, S.c.oy);
+    if (late_bad) { badin = true; S.info.status = 4; }
+    g.mask = w_ballot_full(valid && !badin);
+  }
   if (valid && !badin) {
     if (io.xqp) {
       LUNR for (int i = 0; i < 4; i++) io.xqp[(size_t)(4 * j + i) * B + b] = S.x.xs[i];

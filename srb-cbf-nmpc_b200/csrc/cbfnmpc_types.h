@@ -27,4 +27,7 @@ struct BatchIO {
   unsigned long long* active;
   int B, mode;
   int ld;  // leading dimension of every array (>= B; > B when the batch is a column range of a larger SoA block)
+  // host-buffer calls (cbfnmpc_lane_kernel_late): the obstacles travel on a second stream WHILE the QP stage runs; a word copied
+  // behind them in that stream is what the kernel waits for before it looks at them (obs_flag == nullptr: they are there)
+  const int* obs_flag; int obs_seq;
 };

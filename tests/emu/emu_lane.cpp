@@ -114,7 +114,7 @@ int emu_solve_batch_host(const cbfnmpc_gains* g, const cbfnmpc_options* o, int B
   io.X = out->X; io.U = out->U; io.lam = out->lam; io.slack = out->slack; io.xqp = out->x_qp; io.alpha = out->alpha;
   io.abuf_next = out->alpha_buf_next; io.kkt = out->kkt; io.status = out->status; io.qp_iters = out->qp_iters;
   io.nlp_iters = out->nlp_iters; io.n_fact = out->n_fact; io.active = (unsigned long long*)out->active;
-  io.B = B; io.ld = B; io.mode = mode;
+  io.B = B; io.ld = B; io.mode = mode; io.obs_flag = nullptr; io.obs_seq = 0;
   // stance classes as the device sorts them (cbfnmpc_classify_kernel): all 4-foot instances, then the diagonal pairs, 8 per warp
   for (int cls = 4; cls >= 2; cls -= 2) {
     int list[8], n = 0;

@@ -166,6 +166,40 @@ def test_non_finite_inputs_leave_the_outputs_untouched(pkg):
         s.close()
 
 
+def test_host_call_with_late_obstacles_equals_the_device_call(pkg):
+    """The host-buffer call (one column range) uploads the obstacles on a second stream while the QP stage runs and
+    cbfnmpc_lane_kernel_late looks at them afterwards: bit for bit the answers of the device-pointer call (cbfnmpc_lane_kernel,
+    obstacles read at load); an instance whose obstacles are not finite is still bad input (status 4, nothing written), in QP mode
+    the obstacles are not looked at."""
+    import torch
+    from srb_cbf_nmpc_b200 import capi, scenarios as S
+    dev = torch.device("cuda", 0)
+    for B in (300, 4096):
+        insts = S.cfg3_instances(B, seed=4242 + B)
+        for i in (3, B - 2):
+            a, b, c, d_, e = insts[i]; e = np.array(e, float); e[:] = np.nan if i == 3 else np.inf; insts[i] = (a, b, c, d_, e)
+        d = capi.soa_from_instances(insts)
+        s = pkg.BatchSolver(device=0, max_batch=B, max_obs=20)
+        out = capi.alloc_out(B)
+        for k in ("X", "U", "alpha", "alpha_buf_next", "lam", "x_qp"): out[k][...] = -777.0
+        for rep in range(2):   # (the "landed" word counts calls)
+            s.solve_host(d, mode=capi.MODE_QP_NLP, out=out)
+        tin = {k: torch.from_numpy(d[k]).to(dev) for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy", "alpha_buf")}
+        tout = {k: torch.full((n, B), -777.0, dtype=torch.float64, device=dev) for k, n in capi.OUT_F64.items()}
+        tout.update({k: torch.zeros((n, B), dtype=torch.int32, device=dev) for k, n in capi.OUT_I32.items()})
+        tout["active"] = torch.zeros((2, B), dtype=torch.int64, device=dev)
+        s.solve_device(B, {k: v.data_ptr() for k, v in tin.items()}, {k: v.data_ptr() for k, v in tout.items()}, 20)
+        torch.cuda.synchronize()
+        assert (out["status"][0][[3, B - 2]] == 4).all() and (out["status"][0] == 4).sum() == 2 and (out["status"][0] == 0).sum() > B // 2
+        good = np.ones(B, bool); good[[3, B - 2]] = False   # (a status-4 column of the host call is whatever the staging held)
+        for k in ("X", "U", "alpha", "alpha_buf_next", "lam", "x_qp", "slack", "kkt", "status", "qp_iters", "nlp_iters", "n_fact"):
+            assert np.array_equal(out[k][:, good], tout[k].cpu().numpy()[:, good]), (B, k)
+        assert (tout["X"].cpu().numpy()[:, ~good] == -777.0).all()
+        outq = s.solve_host(d, mode=capi.MODE_QP)
+        assert (outq["status"][0] == 0).all()
+        s.close()
+
+
 def test_bad_team_or_agent_index_is_bad_input(pkg):
     """cbfnmpc_pack_inputs: a team / agent index outside the per-team arrays is answered with status 4, nothing is read out of bounds."""
     import torch
