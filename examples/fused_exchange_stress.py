@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Stress of cbfnmpc_ext_solve_fused on 2 or 4 GPUs (one process per GPU): batch sizes that grow and shrink (the mailboxes are
 re-allocated and re-mapped), N = 4 and N = 8, a member with a bad contact pattern, repeated calls, the communicator destroyed and
-made again; after every call the answers must equal cbfnmpc_ext_solve_sharded's bit for bit on every rank.
+made again; after every call the answers must equal cbfnmpc_ext_solve_sharded's bit for bit on every rank.  With CBFNMPC_NO_IPC=1 in
+the environment no rank can map a peer: every rank must then take the per-iteration path (and still agree).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 examples/fused_exchange_stress.py"""
 import json, os, sys
@@ -57,6 +58,7 @@ for rnd in range(2):
         log.append(dict(round=rnd, N=N, n_teams=n_teams, bad=bad, fused=bool(flag[1] == -1.0), identical=bool(flag[0] == 0.0),
                         sharded_ms=outs[0][0]["total_ms"], fused_ms=outs[2][0]["total_ms"], launches=outs[2][0]["launches"]))
         assert flag[0] == 0.0, log[-1]
+        assert bool(flag[1] == -1.0) == (os.environ.get("CBFNMPC_NO_IPC") is None or G == 1), log[-1]   # (CBFNMPC_NO_IPC=1: every rank falls back)
     solver.comm_destroy(); dist.barrier(); make_comm()   # the communicator goes and comes back: the mailboxes are mapped again
 if rank == 0:
     print(json.dumps(dict(world=world, ranks_per_team=G, cases=log, all_identical=all(c["identical"] for c in log), all_fused=all(c["fused"] for c in log))))

@@ -317,7 +317,7 @@ static int ext_fused_setup(cbfnmpc_ctx* c, size_t need, cudaStream_t st) {
   if (G == 1) return CBFNMPC_OK;
   // handles: 64 bytes = 8 doubles per rank, slot 0 = own, slots 1 .. G = gathered
   cudaIpcMemHandle_t h, all[8];
-  bool ok = cudaIpcGetMemHandle(&h, c->f_mbox) == cudaSuccess;
+  bool ok = cudaIpcGetMemHandle(&h, c->f_mbox) == cudaSuccess && getenv("CBFNMPC_NO_IPC") == nullptr;   // (the variable: to test the fallback)
   if (!ok) { cudaGetLastError(); memset(&h, 0, sizeof(h)); }
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
   CK(cudaMemcpyAsync(c->f_bar, &h, 64, cudaMemcpyHostToDevice, st));
