@@ -405,7 +405,7 @@ struct cbfnmpc_ctx {
   void* comm; int comm_size, comm_rank;
   // cbfnmpc_ext_solve_fused: own mailbox, the mailboxes of the communicator's ranks mapped into this process (CUDA IPC; f_peer[rank] ==
   // f_mbox), control words {error, largest team iteration count}, a few doubles for the handle exchange / the start barrier
-  double* f_mbox; size_t f_mbox_cap; double* f_peer[8]; int* f_ctl; double* f_bar; bool f_disabled;
+  double* f_mbox; size_t f_mbox_cap; double* f_peer[8]; int* f_ctl; double* f_bar; bool f_disabled, f_mapped;
   // small host-buffer batches (<= small_cap instances): one pinned block up, one down (see solve_small)
   int small_cap;
   unsigned char *h_sin, *h_sout, *d_sin, *d_sout;

@@ -191,10 +191,18 @@ int cbfnmpc_ext_solve_batch_host(cbfnmpc_ctx* c, int B, const cbfnmpc_ext_cfg* c
 }
 
 // mailboxes of cbfnmpc_ext_solve_fused: unmap the peers', free the own one (the next fused call sets them up again)
-static void ext_fused_release(cbfnmpc_ctx* c) {
+// (An exporter must not free memory that an importer still has open, and the ranks of a communicator do not leave it at the same
+//  moment: when a communicator goes, only the mappings of the PEERS' mailboxes are closed; the own mailbox stays allocated and is
+//  exported again to the next communicator.  It is freed when it has to grow -- after a barrier over the ranks, ext_fused_setup --
+//  and with the context.)
+static void ext_fused_unmap(cbfnmpc_ctx* c) {
   for (int r = 0; r < 8; r++) { if (c->f_peer[r] && c->f_peer[r] != c->f_mbox) cudaIpcCloseMemHandle(c->f_peer[r]); c->f_peer[r] = nullptr; }
+  c->f_mapped = false; c->f_disabled = false;
+}
+static void ext_fused_release(cbfnmpc_ctx* c) {
+  ext_fused_unmap(c);
   if (c->f_mbox) cudaFree(c->f_mbox);
-  c->f_mbox = nullptr; c->f_mbox_cap = 0; c->f_disabled = false;
+  c->f_mbox = nullptr; c->f_mbox_cap = 0;
 }
 
 // ---- agent-sharded teams: the path's one collective
@@ -213,7 +221,7 @@ int cbfnmpc_comm_init(cbfnmpc_ctx* c, int nranks, int rank, const void* id128) {
   if (rc) return rc;
   CK(cudaSetDevice(c->device));
   if (c->comm) { g_nccl.CommDestroy((xnccl_comm)c->comm); c->comm = nullptr; }
-  CK(cudaStreamSynchronize(c->stream)); ext_fused_release(c);
+  CK(cudaStreamSynchronize(c->stream)); ext_fused_unmap(c);
   xnccl_uid u; memcpy(u.internal, id128, 128);
   xnccl_comm cm = nullptr;
   NK(g_nccl.CommInitRank(&cm, nranks, u, rank));
@@ -223,7 +231,7 @@ int cbfnmpc_comm_init(cbfnmpc_ctx* c, int nranks, int rank, const void* id128) {
 int cbfnmpc_comm_destroy(cbfnmpc_ctx* c) {
   if (!c) return fail(CBFNMPC_ERR_ARG, "null argument");
   if (c->comm && g_nccl.h) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); g_nccl.CommDestroy((xnccl_comm)c->comm); }
-  cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); ext_fused_release(c);
+  cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); ext_fused_unmap(c);
   c->comm = nullptr; c->comm_size = 1; c->comm_rank = 0;
   return CBFNMPC_OK;
 }
@@ -304,17 +312,20 @@ static int ext_fused_setup(cbfnmpc_ctx* c, size_t need, cudaStream_t st) {
   const int G = c->comm ? c->comm_size : 1, rank = c->comm ? c->comm_rank : 0;
   if (G > 8) { c->f_disabled = true; return CBFNMPC_OK; }
   if (!c->f_ctl) { CK(cudaMalloc(&c->f_ctl, sizeof(int) * 4)); CK(cudaMalloc(&c->f_bar, sizeof(double) * 16 * 9)); }
-  if (c->f_mbox && need <= c->f_mbox_cap) return CBFNMPC_OK;
+  if (c->f_mbox && c->f_mapped && need <= c->f_mbox_cap) return CBFNMPC_OK;
   CK(cudaStreamSynchronize(st));
-  // growing: every rank first unmaps its peers' mailboxes, then all meet, and only then does anybody free its own (an exporter must
-  // not free memory that an importer still has open)
-  for (int r = 0; r < 8; r++) { if (c->f_peer[r] && c->f_peer[r] != c->f_mbox) cudaIpcCloseMemHandle(c->f_peer[r]); c->f_peer[r] = nullptr; }
-  if (G > 1) { NK(g_nccl.AllGather(c->f_bar, c->f_bar + 8, 1, XNCCL_DOUBLE, (xnccl_comm)c->comm, st)); CK(cudaStreamSynchronize(st)); }
-  ext_fused_release(c);
-  CK(cudaMalloc(&c->f_mbox, sizeof(double) * need)); c->f_mbox_cap = need;
-  CK(cudaMemset(c->f_mbox, 0, sizeof(double) * need));
+  // (re)mapping: every rank first closes its mappings of the peers' mailboxes; when the own mailbox has to grow all ranks meet
+  // before anybody frees its own (an exporter must not free memory that an importer still has open)
+  ext_fused_unmap(c);
+  if (!c->f_mbox || need > c->f_mbox_cap) {   // (same outcome on every rank: same call history)
+    if (G > 1) { NK(g_nccl.AllGather(c->f_bar, c->f_bar + 8, 1, XNCCL_DOUBLE, (xnccl_comm)c->comm, st)); CK(cudaStreamSynchronize(st)); }
+    if (c->f_mbox) CK(cudaFree(c->f_mbox));
+    c->f_mbox = nullptr; c->f_mbox_cap = 0;
+    CK(cudaMalloc(&c->f_mbox, sizeof(double) * need)); c->f_mbox_cap = need;
+    CK(cudaMemset(c->f_mbox, 0, sizeof(double) * need));
+  }
   c->f_peer[rank] = c->f_mbox;
-  if (G == 1) return CBFNMPC_OK;
+  if (G == 1) { c->f_mapped = true; return CBFNMPC_OK; }
   // handles: 64 bytes = 8 doubles per rank, slot 0 = own, slots 1 .. G = gathered
   cudaIpcMemHandle_t h, all[8];
   bool ok = cudaIpcGetMemHandle(&h, c->f_mbox) == cudaSuccess && getenv("CBFNMPC_NO_IPC") == nullptr;   // (the variable: to test the fallback)
@@ -337,7 +348,8 @@ static int ext_fused_setup(cbfnmpc_ctx* c, size_t need, cudaStream_t st) {
   CK(cudaMemcpyAsync(oks, c->f_bar + 8, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   for (int r = 0; r < G; r++) if (oks[r] == 0.0) ok = false;
-  if (!ok) { ext_fused_release(c); c->f_disabled = true; }
+  if (!ok) { ext_fused_unmap(c); c->f_disabled = true; }
+  else c->f_mapped = true;
   return CBFNMPC_OK;
 }
 
