@@ -49,7 +49,8 @@ for rnd in range(2):
         d = capi.ext_soa_from_instances(mine, N)
         tin = {k: torch.from_numpy(d[k]).to(dev) for k in ("x0", "xdes", "feet_xy", "contact", "obs_xy", "alpha_buf")}
         outs = []
-        for fn in (solver.ext_solve_sharded, solver.ext_solve_fused, solver.ext_solve_fused):
+        for fi, fn in enumerate((solver.ext_solve_sharded, solver.ext_solve_fused, solver.ext_solve_fused)):
+            if os.environ.get("STRESS_VERBOSE"): print("rank", rank, "round", rnd, "case", N, n_teams, bad, "call", fi, flush=True)
             tout = {k: torch.zeros((n, B), dtype=torch.float64, device=dev) for k, n in capi.ext_out_rows(N).items() if k != "pub"}
             tout.update({k: torch.zeros((1, B), dtype=torch.int32, device=dev) for k in capi.EXT_OUT_I32})
             dist.barrier()
@@ -63,6 +64,7 @@ for rnd in range(2):
         flag = torch.tensor([0.0 if same else 1.0, -float(outs[1][0]["fused"])], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MAX)
         log.append(dict(round=rnd, N=N, n_teams=n_teams, bad=bad, fused=bool(flag[1] == -1.0), identical=bool(flag[0] == 0.0),
                         sharded_ms=outs[0][0]["total_ms"], fused_ms=outs[2][0]["total_ms"], launches=outs[2][0]["launches"]))
+        if rank == 0: print("case", json.dumps(log[-1]), flush=True)
         assert flag[0] == 0.0, log[-1]
         assert bool(flag[1] == -1.0) == (os.environ.get("CBFNMPC_NO_IPC") is None or G == 1), log[-1]   # (CBFNMPC_NO_IPC=1: every rank falls back)
     torch.cuda.synchronize(); dist.barrier()

@@ -30,6 +30,7 @@ static int xnccl_load() {
   return CBFNMPC_OK;
 }
 #define XNCCL_DOUBLE 8 /* ncclFloat64 */
+#define XNCCL_INT32 2  /* ncclInt32 */
 #define NK(call)                                                                                                        \
   do {                                                                                                                  \
     int r_ = (call);                                                                                                    \
@@ -245,7 +246,7 @@ int cbfnmpc_ext_solve_sharded(cbfnmpc_ctx* c, int n_teams, const cbfnmpc_ext_cfg
                               cbfnmpc_ext_stats* stats, void* cuda_stream) {
   if (!c || !cfg) return fail(CBFNMPC_ERR_ARG, "null argument");
   const int T = cfg->team_size, G = c->comm ? c->comm_size : 1, rank = c->comm ? c->comm_rank : 0;
-  if (T < 2 || T % G != 0) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_ext_solve_sharded: team_size must be a multiple (>= 2) of the communicator's size");
+  if (T < 2 || T % G != 0 || G > 8) return fail(CBFNMPC_ERR_ARG, "cbfnmpc_ext_solve_sharded: team_size must be a multiple (>= 2) of the communicator's size (<= 8)");
   const int mpr = T / G, B = mpr * n_teams;
   int rc = ext_check(c, B, cfg, in, out, 1);
   if (rc) return rc;
@@ -256,7 +257,7 @@ int cbfnmpc_ext_solve_sharded(cbfnmpc_ctx* c, int n_teams, const cbfnmpc_ext_cfg
   const size_t n_state = (size_t)ext_nstate(K) * (size_t)B * N, n_pub = blk * mpr, n_gath = blk * T;
   if (n_state > c->x_state_cap) { CK(cudaStreamSynchronize(st)); if (c->x_state) CK(cudaFree(c->x_state)); CK(cudaMalloc(&c->x_state, sizeof(double) * n_state)); c->x_state_cap = n_state; }
   if (n_gath + n_pub > c->x_pub_cap) { CK(cudaStreamSynchronize(st)); if (c->x_pub) CK(cudaFree(c->x_pub)); CK(cudaMalloc(&c->x_pub, sizeof(double) * (n_gath + n_pub))); c->x_pub_cap = n_gath + n_pub; }
-  if (!c->x_active) { CK(cudaMalloc(&c->x_active, sizeof(int) * 2)); CK(cudaHostAlloc(&c->x_active_h, sizeof(int) * 2, cudaHostAllocDefault)); CK(cudaEventCreateWithFlags(&c->x_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->x_ev[1], cudaEventDisableTiming)); CK(cudaEventCreate(&c->x_t0)); CK(cudaEventCreate(&c->x_t1)); }
+  if (!c->x_active) { CK(cudaMalloc(&c->x_active, sizeof(int) * 18)); CK(cudaHostAlloc(&c->x_active_h, sizeof(int) * 18, cudaHostAllocDefault)); CK(cudaEventCreateWithFlags(&c->x_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->x_ev[1], cudaEventDisableTiming)); CK(cudaEventCreate(&c->x_t0)); CK(cudaEventCreate(&c->x_t1)); }
   double* pub = c->x_pub; double* gathered = c->x_pub + n_pub;
   ExtIO io;
   ext_fill_io(&io, B, B, cfg, in, out);
@@ -284,11 +285,22 @@ int cbfnmpc_ext_solve_sharded(cbfnmpc_ctx* c, int n_teams, const cbfnmpc_ext_cfg
     CK(cudaMemsetAsync(c->x_active + s, 0, sizeof(int), st));
     io.phase = 3; io.n_active = c->x_active + s;
     if ((rc = ext_launch(c, XP, io, B, c->x_perm, st, false)) || (rc = gather())) return rc;
-    CK(cudaMemcpyAsync(c->x_active_h + s, c->x_active + s, sizeof(int), cudaMemcpyDeviceToHost, st));
+    // The counter that ends the loop must be the same on every rank (a rank that stopped calling the all-gather would leave the
+    // others waiting in it): the ranks' local counts are gathered and summed.  Local counts alone differ when a rank holds no
+    // RUNNING member of a team that still iterates elsewhere -- a member with a bad contact pattern and no team mate on its rank.
+    if (G > 1) {
+      NK(g_nccl.AllGather(c->x_active + s, c->x_active + 2 + 8 * s, 1, XNCCL_INT32, (xnccl_comm)c->comm, st));
+      CK(cudaMemcpyAsync(c->x_active_h + 2 + 8 * s, c->x_active + 2 + 8 * s, sizeof(int) * G, cudaMemcpyDeviceToHost, st));
+    } else {
+      CK(cudaMemcpyAsync(c->x_active_h + s, c->x_active + s, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaEventRecord(c->x_ev[s], st));
     if (it >= 1) {   // look at the previous iteration's counter while this one runs
       CK(cudaEventSynchronize(c->x_ev[s ^ 1]));
-      if (c->x_active_h[s ^ 1] == 0) { done_at = it - 1; it++; break; }
+      int active = 0;
+      if (G > 1) { for (int r = 0; r < G; r++) active += c->x_active_h[2 + 8 * (s ^ 1) + r]; }
+      else active = c->x_active_h[s ^ 1];
+      if (active == 0) { done_at = it - 1; it++; break; }
     }
   }
   io.phase = 4; io.n_active = nullptr;
@@ -388,7 +400,7 @@ int cbfnmpc_ext_solve_fused(cbfnmpc_ctx* c, int n_teams, const cbfnmpc_ext_cfg* 
     if (stats) stats->fused = 0;
     return rc;
   }
-  if (!c->x_active) { CK(cudaMalloc(&c->x_active, sizeof(int) * 2)); CK(cudaHostAlloc(&c->x_active_h, sizeof(int) * 2, cudaHostAllocDefault)); CK(cudaEventCreateWithFlags(&c->x_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->x_ev[1], cudaEventDisableTiming)); CK(cudaEventCreate(&c->x_t0)); CK(cudaEventCreate(&c->x_t1)); }
+  if (!c->x_active) { CK(cudaMalloc(&c->x_active, sizeof(int) * 18)); CK(cudaHostAlloc(&c->x_active_h, sizeof(int) * 18, cudaHostAllocDefault)); CK(cudaEventCreateWithFlags(&c->x_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->x_ev[1], cudaEventDisableTiming)); CK(cudaEventCreate(&c->x_t0)); CK(cudaEventCreate(&c->x_t1)); }
   ExtIO io;
   ext_fill_io(&io, B, B, cfg, in, out);
   io.n_teams = n_teams; io.member0 = rank * mpr;
