@@ -6,11 +6,13 @@ the environment no rank can map a peer: every rank must then take the per-iterat
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 examples/fused_exchange_stress.py
 
-Status at the end of round 2: passes on 2 GPUs (also with CBFNMPC_NO_IPC=1).  The one attempt on 4 GPUs did not finish within its
-400 s limit (no output: a blocking host call, not the in-kernel watchdog) before the GPU budget of the round ran out; the plain
-4- and 8-GPU runs of the fused path (examples/agent_sharded_ext.py, bench.py at N = 4 and 8: no re-allocation, no second
-communicator) are green.  Suspected and changed since: a rank used to FREE its mailbox when its communicator went while peers could
-still have it mapped; now only the peers' mappings are closed there."""
+Status at the end of round 2: passes on 2 GPUs (also with CBFNMPC_NO_IPC=1).  The first attempt on 4 GPUs ran into its time limit; a
+second one with per-call progress output (STRESS_VERBOSE=1) showed where: in the PER-ITERATION path of the case with the one-footed
+member -- the rank that holds that member (and, with one member per rank, no team mate of it) counted the team out, left its launch
+loop and with it the all-gathers its peers were still calling.  cbfnmpc_ext_solve_sharded now gathers and sums that counter over the
+ranks; the fix is verified on 2 GPUs (where the old code could not fail either), the 4-GPU re-run could not be made any more (the GPU
+budget of the round was spent).  The fused path itself, and the plain 4- and 8-GPU runs of both paths (examples/agent_sharded_ext.py,
+bench.py at N = 4 and 8), were green throughout."""
 import json, os, sys
 import numpy as np
 import torch
