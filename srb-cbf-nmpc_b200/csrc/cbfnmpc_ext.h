@@ -1253,14 +1253,14 @@ XDEV void x_sleep() { __nanosleep(200); }
 XDEV void x_atomic_max(int* p, int v) { atomicMax(p, v); }
 XDEV int x_atomic_exch(int* p, int v) { return atomicExch(p, v); }
 #else
-#define XFUSED_WATCHDOG 4000000000ll
+#define XFUSED_WATCHDOG 4000000ll   /* polls */
 XDEV int x_ld_flag(const int* p) { return *(volatile const int*)p; }
 XDEV void x_st_flag(int* p, int v) { *(volatile int*)p = v; }
 XDEV double x_ld_peer(const double* p) { return *(volatile const double*)p; }
 XDEV void x_st_peer(double* p, double v) { *(volatile double*)p = v; }
 XDEV void x_fence_sys() { }
-XDEV long long x_clock() { return 0; }
-XDEV void x_sleep() { }
+XDEV long long x_clock() { static long long polls = 0; return polls++; }   // (emulation: the watchdog counts polls)
+XDEV void x_sleep() { xemu::yield(); }
 XDEV void x_atomic_max(int* p, int v) { if (v > *p) *p = v; }
 XDEV int x_atomic_exch(int* p, int v) { const int o = *p; *p = v; return o; }
 #endif

@@ -51,6 +51,7 @@ struct WarpCtx {
 };
 extern WarpCtx g_warp;
 void rendezvous(unsigned mask);  // every lane of `mask` arrives (with the same mask) before any of them leaves
+void yield();                    // a lane that polls (the fused exchange's sequence flags) lets the other fibers run
 }  // namespace xemu
 XDEV int x_lane() { return xemu::g_warp.cur; }
 XDEV double x_shfl(unsigned mask, double v, int src) {

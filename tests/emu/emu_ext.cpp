@@ -21,14 +21,22 @@ void rendezvous(unsigned mask) {
   state[me] = 1; wmask[me] = mask;
   swapcontext(&lane_ctx[me], &sched_ctx);
 }
+void yield() {   // stays runnable; the scheduler comes back to it after the other lanes have had their turn
+  const int me = g_warp.cur;
+  swapcontext(&lane_ctx[me], &sched_ctx);
+}
 }  // namespace xemu
 
-static const XParams* g_XP; static const ExtIO* g_io; static int g_C, g_W, g_nlanes;
+static const XParams* g_XP; static const ExtIO* g_io; static int g_C, g_W, g_nlanes; static bool g_fused;
 static int g_b[32]; static bool g_valid[32];
 static double* g_priv;
 static void lane_main() {
   const int l = xemu::g_warp.cur;
   XPriv pr; pr.base = g_priv + l;
+  if (g_fused) {   // the fused exchange (xmode 4): mailbox and sequence flags in host memory, the polling lanes yield
+    if (g_W == 4) { if (g_C == 4) ext_run_group<4, 4, true>(*g_XP, *g_io, g_b[l], g_valid[l], pr); else ext_run_group<2, 4, true>(*g_XP, *g_io, g_b[l], g_valid[l], pr); }
+    else { if (g_C == 4) ext_run_group<4, 8, true>(*g_XP, *g_io, g_b[l], g_valid[l], pr); else ext_run_group<2, 8, true>(*g_XP, *g_io, g_b[l], g_valid[l], pr); }
+  } else
   if (g_W == 4) { if (g_C == 4) ext_run_group<4, 4>(*g_XP, *g_io, g_b[l], g_valid[l], pr); else ext_run_group<2, 4>(*g_XP, *g_io, g_b[l], g_valid[l], pr); }
   else { if (g_C == 4) ext_run_group<4, 8>(*g_XP, *g_io, g_b[l], g_valid[l], pr); else ext_run_group<2, 8>(*g_XP, *g_io, g_b[l], g_valid[l], pr); }
   xemu::state[l] = 2;
@@ -95,6 +103,17 @@ extern "C" int emu_ext_solve(const cbfnmpc_gains* g, const cbfnmpc_options* o, c
   io.X = a->X; io.U = a->U; io.lam = a->lam; io.slack = a->slack; io.xqp = a->xqp; io.alpha = a->alpha; io.abuf_next = a->abuf_next; io.kkt = a->kkt;
   io.status = a->status; io.qp_iters = a->qp_iters; io.nlp_iters = a->nlp_iters; io.team_iters = a->team_iters;
   io.B = a->B; io.ld = a->B; io.N = a->N; io.K_obs = a->K_obs; io.n_nbr = a->n_nbr; io.T = a->T; io.xmode = a->xmode; io.phase = 0; io.n_run = 0;
+  // xmode 4 (the fused exchange of cbfnmpc_ext_solve_fused on ONE emulated warp): member-major batch of ONE group of ranks, a->T == 1,
+  // a->n_nbr + 1 members per team, B / (n_nbr + 1) teams; every instance of the batch must sit in the warp that runs (its team mates
+  // poll for it), i.e. B <= 32 / N instances of one stance class
+  double* mbox = nullptr; int fctl[4] = {0, 0, 0, 0};
+  g_fused = a->xmode == 4;
+  if (g_fused) {
+    const int t_all = a->n_nbr + 1, n_teams = a->B / t_all;
+    const size_t blk = (size_t)(2 * a->N + 2) * n_teams, need = 2 * (size_t)t_all * blk + (size_t)t_all * n_teams + 2;
+    mbox = (double*)calloc(need, sizeof(double));
+    io.mbox[0] = mbox; io.n_grp = 1; io.n_teams = n_teams; io.member0 = 0; io.fused_err = fctl; io.fused_its = fctl + 1;
+  }
   const int W = a->N, K = a->K_obs + a->n_nbr;
   const int npriv = ext_npriv(K);
   g_priv = (double*)malloc(sizeof(double) * (size_t)npriv * 32);
@@ -107,7 +126,10 @@ extern "C" int emu_ext_solve(const cbfnmpc_gains* g, const cbfnmpc_options* o, c
     for (int t = 0; t < n_teams; t++) {
       const int c = ext_classify_team(io, t);
       if (c == cls) list[n++] = t;
-      else if (c < 0 && cls == 4) for (int m = 0; m < a->T; m++) ext_store_bad<4, 4>(io, t * a->T + m, 0);
+      else if (c < 0 && cls == 4) {
+        for (int m = 0; m < a->T; m++) ext_store_bad<4, 4>(io, t * a->T + m, 0);
+        if (io.xmode == 4) ext_fused_publish_bad(io, t);
+      }
     }
     g_C = cls;
     for (int w0 = 0; w0 < n && rc == 0; w0 += teams_per_warp) {
@@ -122,5 +144,8 @@ extern "C" int emu_ext_solve(const cbfnmpc_gains* g, const cbfnmpc_options* o, c
     free(list);
   }
   free(g_priv);
+  if (mbox) free(mbox);
+  if (g_fused && fctl[0] != 0) rc = -3;   // a member waited in vain
+  g_fused = false;
   return rc;
 }

@@ -48,8 +48,11 @@ def ext_alloc_out(B, N):
     return o
 
 
-def solve(insts, N=4, T=1, nbr=None, eps_obs=None, eps_nbr=2.2, relax=0.7, pub_tol=1e-10, max_team_iters=64, mu_stall=6, gains=None, options=None, trace=False):
-    """nbr: (B, n_nbr, N, 2) fixed neighbour trajectories (T == 1) or None; T == 4: teams exchange through the emulated warp."""
+def solve(insts, N=4, T=1, nbr=None, eps_obs=None, eps_nbr=2.2, relax=0.7, pub_tol=1e-10, max_team_iters=64, mu_stall=6, gains=None, options=None, trace=False,
+          fused_members=0):
+    """nbr: (B, n_nbr, N, 2) fixed neighbour trajectories (T == 1) or None; T == 4: teams exchange through the emulated warp.
+    fused_members = m > 1 (with T == 1): the batch is MEMBER-MAJOR (instance b = member * n_teams + team, m members per team) and the
+    members exchange through the mailbox and sequence flags of the fused path (xmode 4); the whole batch must fit one warp."""
     global _lib
     L = C.CDLL(build(trace=trace))
     L.emu_ext_solve.argtypes = [C.POINTER(capi.Gains), C.POINTER(capi.Options), C.POINTER(Args)]
@@ -63,7 +66,10 @@ def solve(insts, N=4, T=1, nbr=None, eps_obs=None, eps_nbr=2.2, relax=0.7, pub_t
     a = Args()
     a.B, a.N, a.T, a.K_obs = B, N, T, d["n_obs"]
     nb = None
-    if T > 1:
+    if fused_members > 1:
+        assert T == 1 and B % fused_members == 0 and B * N <= 32
+        a.n_nbr, a.xmode = fused_members - 1, 4
+    elif T > 1:
         a.n_nbr, a.xmode = T - 1, 1
     elif nbr is not None:
         nbr = np.asarray(nbr, float); nn = nbr.shape[1]

@@ -28,3 +28,32 @@ def test_emulated_ext_kernel_teams_and_long_horizon():
         assert c["status_equal"].all() and c["compared"].sum() >= 4 and c["worst"] < 1e-7
         okt = c["compared"].reshape(-1, 4).all(1)
         assert (np.abs(out["team_iters"][0][::4][okt] - ti[okt]) <= 1).all()
+
+
+def test_emulated_fused_exchange_equals_the_team_in_one_warp():
+    """The fused exchange of cbfnmpc_ext_solve_fused (xmode 4: members of a team in different groups, published trajectories and
+    sequence flags in a mailbox, polling members) run by the host emulation of the kernel source -- four-robot teams, N = 4 (two teams =
+    the eight groups of one warp) and N = 8 (one team), and a team with a one-footed member, which must not stall its team mates --
+    against the same teams exchanged by shuffles (xmode 1): same statuses, same team iteration counts, same answers."""
+    for N, K, n_teams in ((4, 1, 2), (8, 16, 1)):
+        pool = S.cfg4_teams(12, N=N, K_obs=K)
+        by_cls = {}
+        for t in range(12):
+            by_cls.setdefault(sum(pool[4 * t][3]), []).append(t)
+        teams = max(by_cls.values(), key=len)[:n_teams]                   # teams of ONE stance class: they share the emulated warp
+        insts = [pool[4 * t + m] for t in teams for m in range(4)]         # team-major
+        mm = [pool[4 * t + m] for m in range(4) for t in teams]            # member-major (the fused path's layout)
+        ref = emu_ext.solve(insts, N=N, T=4, eps_nbr=S.EPS_NBR)
+        out = emu_ext.solve(mm, N=N, T=1, eps_nbr=S.EPS_NBR, fused_members=4)
+        perm = np.array([m * n_teams + t for t in range(n_teams) for m in range(4)])   # team-major index -> member-major index
+        assert (out["status"][0][perm] == ref["status"][0]).all()
+        assert (out["team_iters"][0][perm] == ref["team_iters"][0]).all()
+        ok = ref["status"][0] == 0
+        assert ok.any()
+        assert np.abs(out["X"][:, perm] - ref["X"])[:, ok].max() < 1e-9 and np.abs(out["slack"][0][perm] - ref["slack"][0])[ok].max() < 1e-9
+    # a one-footed member (status 4, no lane runs it): published once and for all, its team mates finish
+    pool = S.cfg4_teams(4, N=4, K_obs=1)
+    mm = [pool[m] for m in range(4)]
+    a, b_, c_, d_, e = mm[2]; mm[2] = (a, b_, c_, [1, 0, 0, 0], e)
+    out = emu_ext.solve(mm, N=4, T=1, eps_nbr=S.EPS_NBR, fused_members=4)
+    assert out["status"][0][2] == 4 and (out["status"][0][[0, 1, 3]] != 4).all()
