@@ -39,8 +39,10 @@ def lib(sitecheck=False):
     return _libs[sitecheck]
 
 
-def solve(insts, mode=1, gains=None, options=None, xstart=None, sitecheck=False):
+def solve(insts, mode=1, gains=None, options=None, xstart=None, sitecheck=False, late=False):
+    """late: the instantiation of cbfnmpc_lane_kernel_late (obstacles looked at after the QP stage: the host-buffer call's kernel)"""
     L = lib(sitecheck)
+    L.emu_set_late_obstacles(1 if late else 0)
     g = capi.Gains(); L.cbfnmpc_default_gains(C.byref(g))
     o = capi.Options(); L.cbfnmpc_default_options(C.byref(o))
     for k, v in (gains or {}).items(): setattr(g, k, v)

@@ -36,10 +36,15 @@ __attribute__((noinline)) void rendezvous(unsigned mask) {
 static const KParams* g_P; static const BatchIO* g_io; static int g_C;
 static int g_b[32]; static bool g_valid[32];
 static double g_priv[LANE_NPRIV * 32];
+static bool g_late = false;
+extern "C" void emu_set_late_obstacles(int on) { g_late = on != 0; }
 static void lane_main() {
   const int l = lemu::g_warp.cur;
   Priv pr; pr.base = g_priv + l;
-  if (g_C == 4) lane_run_group<4>(*g_P, *g_io, g_b[l], g_valid[l], pr);
+  if (g_late) {   // the instantiation of cbfnmpc_lane_kernel_late: closest-obstacle step after the QP stage
+    if (g_C == 4) lane_run_group<4, true>(*g_P, *g_io, g_b[l], g_valid[l], pr);
+    else lane_run_group<2, true>(*g_P, *g_io, g_b[l], g_valid[l], pr);
+  } else if (g_C == 4) lane_run_group<4>(*g_P, *g_io, g_b[l], g_valid[l], pr);
   else lane_run_group<2>(*g_P, *g_io, g_b[l], g_valid[l], pr);
   lemu::state[l] = 2;
   swapcontext(&lemu::lane_ctx[l], &lemu::sched_ctx);

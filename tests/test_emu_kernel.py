@@ -127,3 +127,21 @@ def test_support_weights_come_back_in_the_order_of_the_feet():
         uniq = (rl < 1e-7).sum(2) >= 2
         assert uniq.sum() > 100 and (rl[:, :, 3] < 1e-7).sum() > 20          # the last foot is unloaded often enough
         assert np.abs(lam - rl)[uniq].max() < 1e-9
+
+
+def test_late_obstacle_instantiation_gives_the_same_answers():
+    """lane_run_group<C, true> (cbfnmpc_lane_kernel_late: the host-buffer call uploads the obstacles while the QP stage runs, the kernel
+    looks at them afterwards) against lane_run_group<C, false>: bit for bit the same answers; non-finite obstacles are still bad input
+    (status 4), in QP mode they are not looked at."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("scen", os.path.join(os.path.dirname(__file__), "..", "srb-cbf-nmpc_b200", "scenarios.py"))
+    S = importlib.util.module_from_spec(spec); spec.loader.exec_module(S)
+    insts = S.cfg3_instances(40, seed=31)
+    a, b, c, d, e = insts[5]; e = np.array(e, float); e[:] = np.nan; insts[5] = (a, b, c, d, e)
+    ref = emu.solve(insts, mode=1); out = emu.solve(insts, mode=1, late=True)
+    assert out["status"][0][5] == 4 and ref["status"][0][5] == 4 and (out["status"][0] == 0).sum() > 25
+    for k in ("X", "U", "slack", "status", "qp_iters", "nlp_iters", "kkt", "alpha"):
+        assert np.array_equal(out[k], ref[k]), k
+    outq = emu.solve(insts, mode=0, late=True)
+    assert (outq["status"][0] == 0).all()
+
